@@ -1,0 +1,421 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the OCN common-neighbour hot path.
+
+This module restates, in plain CPU torch, the op sequence the reference executes for the path
+named by BASELINE.json:north_star.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; the product package
+``ocn_b200`` never does (it fails loudly when the CUDA library is missing).
+
+Parity status: **unpinned at the third-party boundary.**  The reference is pure Python over
+torch-sparse 0.6.18 / torch-scatter 2.1.2 / PyG 2.6.1 (environment.yml:244-248) and an unpinned
+``pygho``; none of them is installable here and the reference ships no tests or golden vectors
+(SURVEY.md §4, §8c).  Each function below cites the reference lines it follows and, where the
+arithmetic lives in one of those libraries, states the library semantics it encodes
+("[recalled]" in SURVEY.md §8c).  The restatement is pinned by (i) the hand-derived vectors of
+SURVEY.md §8c (tests/test_oracle_golden.py), (ii) an independent dense brute force
+(oracle/brute.py), and (iii) golden fixtures produced by executing the reference's *own*
+``model.py`` predictor classes on top of a pure-torch emulation of those libraries
+(oracle/make_golden.py -> tests/golden/).
+
+All sparse matrices are passed as ``Sp`` (COO sorted by (row, col), int64 indices, fp32 values) --
+the layout torch_sparse.SparseTensor and a coalesced pygho.SparseTensor both expose.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+
+@dataclasses.dataclass
+class Sp:
+    row: Tensor            # int64 [nnz]
+    col: Tensor            # int64 [nnz]
+    val: Optional[Tensor]  # fp32 [nnz] or None (== all ones, torch_sparse "no value")
+    shape: Tuple[int, int]
+
+    @property
+    def nnz(self) -> int:
+        return int(self.row.numel())
+
+    def values(self) -> Tensor:
+        return self.val if self.val is not None else torch.ones(self.nnz, dtype=torch.float32)
+
+    def rowptr(self) -> Tensor:
+        rp = torch.zeros(self.shape[0] + 1, dtype=torch.int64)
+        torch.cumsum(torch.bincount(self.row, minlength=self.shape[0]), 0, out=rp[1:])
+        return rp
+
+    def to_dense(self) -> Tensor:
+        d = torch.zeros(self.shape, dtype=torch.float32)
+        d.index_put_((self.row, self.col), self.values(), accumulate=True)
+        return d
+
+
+def sp_from_csr(rowptr: Tensor, col: Tensor, n_cols: Optional[int] = None, val: Optional[Tensor] = None) -> Sp:
+    rowptr = rowptr.to(torch.int64).cpu()
+    n = rowptr.numel() - 1
+    row = torch.repeat_interleave(torch.arange(n, dtype=torch.int64), rowptr[1:] - rowptr[:-1])
+    return Sp(row, col.to(torch.int64).cpu(), None if val is None else val.float().cpu(), (n, n_cols or n))
+
+
+def sp_coalesce(row: Tensor, col: Tensor, val: Optional[Tensor], shape, reduce_sum: bool = True) -> Sp:
+    """Sort by (row, col) and merge duplicates (torch_sparse ``coalesce`` / torch COO ``coalesce``)."""
+    key = row * shape[1] + col
+    ukey, inv = torch.unique(key, return_inverse=True)
+    if val is None:
+        v = None
+    else:
+        v = torch.zeros(ukey.numel(), dtype=val.dtype).index_add_(0, inv, val)
+    return Sp(torch.div(ukey, shape[1], rounding_mode="floor"), ukey % shape[1], v, tuple(shape))
+
+
+# ----------------------------------------------------------------------------------------------
+# piece 1: per-target-edge row intersection  (utils.py:146-183, 248-285)
+# ----------------------------------------------------------------------------------------------
+
+def index_select_rows(adj: Sp, idx: Tensor) -> Sp:
+    """``adj[idx]`` (utils.py:256-257): torch_sparse row gather -- output row r is input row
+    idx[r], columns keep their ascending order [recalled]."""
+    rp = adj.rowptr()
+    start = rp[idx]
+    cnt = rp[idx + 1] - start
+    total = int(cnt.sum())
+    out_row = torch.repeat_interleave(torch.arange(idx.numel(), dtype=torch.int64), cnt)
+    base = torch.repeat_interleave(start - (torch.cumsum(cnt, 0) - cnt), cnt)
+    pos = torch.arange(total, dtype=torch.int64) + base
+    return Sp(out_row, adj.col[pos], None if adj.val is None else adj.val[pos], (idx.numel(), adj.shape[1]))
+
+
+def spm2elem(spm: Sp) -> Tensor:
+    """utils.py:154-160: pack (row<<32)+col."""
+    return torch.bitwise_left_shift(spm.row, 32).add_(spm.col)
+
+
+def elem2spm(element: Tensor, sizes) -> Sp:
+    """utils.py:146-151: unpack and fill value 1.0."""
+    col = torch.bitwise_and(element, 0xffffffff)
+    row = torch.bitwise_right_shift(element, 32)
+    return Sp(row, col, torch.ones(element.numel(), dtype=torch.float32), tuple(sizes))
+
+
+def spmoverlap_(adj1: Sp, adj2: Sp) -> Sp:
+    """utils.py:163-183, verbatim searchsorted semantics incl. the swap and the ``[:-1]``."""
+    assert adj1.shape == adj2.shape
+    element1 = spm2elem(adj1)
+    element2 = spm2elem(adj2)
+    if element2.shape[0] > element1.shape[0]:
+        element1, element2 = element2, element1
+    if element1.numel() == 0:
+        return elem2spm(element1, adj1.shape)
+    idx = torch.searchsorted(element1[:-1], element2)
+    mask = (element1[idx] == element2)
+    retelem = element2[mask]
+    return elem2spm(retelem, adj1.shape)
+
+
+def spmnotoverlap_(adj1: Sp, adj2: Sp) -> Tuple[Sp, Sp]:
+    """utils.py:186-206."""
+    element1 = spm2elem(adj1)
+    element2 = spm2elem(adj2)
+    idx = torch.searchsorted(element1[:-1], element2)
+    matchedmask = (element1[idx] == element2)
+    maskelem1 = torch.ones_like(element1, dtype=torch.bool)
+    maskelem1[idx[matchedmask]] = 0
+    return elem2spm(element1[maskelem1], adj1.shape), elem2spm(element2[~matchedmask], adj2.shape)
+
+
+def spmoverlap_notoverlap_(adj1: Sp, adj2: Sp) -> Tuple[Sp, Sp, Sp]:
+    """utils.py:210-244."""
+    element1 = spm2elem(adj1)
+    element2 = spm2elem(adj2)
+    if element1.shape[0] == 0:
+        return elem2spm(element1, adj1.shape), elem2spm(element1, adj1.shape), elem2spm(element2, adj1.shape)
+    idx = torch.searchsorted(element1[:-1], element2)
+    matchedmask = (element1[idx] == element2)
+    maskelem1 = torch.ones_like(element1, dtype=torch.bool)
+    maskelem1[idx[matchedmask]] = 0
+    return (elem2spm(element2[matchedmask], adj1.shape), elem2spm(element1[maskelem1], adj1.shape),
+            elem2spm(element2[~matchedmask], adj1.shape))
+
+
+def adjoverlap(adj1: Sp, adj2: Sp, tarei: Tensor) -> Sp:
+    """utils.py:248-285, ``calresadj=False, cnsampledeg=-1`` branch (the only one cn5/cn7 reach)."""
+    return spmoverlap_(index_select_rows(adj1, tarei[0]), index_select_rows(adj2, tarei[1]))
+
+
+# ----------------------------------------------------------------------------------------------
+# piece 3b: A^2  (NeighborOverlap_large.py:68-74,112-119; utils.py:287-329)
+# ----------------------------------------------------------------------------------------------
+
+def sp_matmul(a: Sp, b: Sp) -> Sp:
+    """Sparse x sparse with summed duplicates, coalesced (torch COO ``@`` at
+    NeighborOverlap_large.py:74; pygho ``spspmm(A,1,B,0)`` [recalled])."""
+    ta = torch.sparse_coo_tensor(torch.stack((a.row, a.col)), a.values(), a.shape)
+    tb = torch.sparse_coo_tensor(torch.stack((b.row, b.col)), b.values(), b.shape)
+    tc = torch.sparse.mm(ta, tb).coalesce()
+    r, c = tc.indices()
+    return Sp(r, c, tc.values().float(), (a.shape[0], b.shape[1]))
+
+
+def adj2_true(adj: Sp, keep_value: bool = False) -> Sp:
+    """``SparseTensor.from_torch_sparse_coo_tensor(spadj @ spadj, False)``: structure of A^2,
+    values dropped; the diagonal is part of it (Q12)."""
+    a2 = sp_matmul(adj, adj)
+    return a2 if keep_value else Sp(a2.row, a2.col, None, a2.shape)
+
+
+def adj2_folded(adj: Sp, block_size: int = 1024) -> Sp:
+    """``sparse_tensor_multiply`` (utils.py:287-329) as written: every [bs x bs] block product
+    is converted with block-local coordinates and summed without adding its (i, j) offset, so
+    all blocks land in the top-left corner; torch_sparse ``+`` = concat COO +
+    coalesce(sum), sizes = max [recalled]."""
+    n = adj.shape[0]
+    dense = adj.to_dense()
+    acc = torch.zeros(min(block_size, n), min(block_size, n), dtype=torch.float32)
+    for i in range(0, n, block_size):
+        for j in range(0, n, block_size):
+            blk = dense[i:i + block_size, :] @ dense[:, j:j + block_size]
+            acc[:blk.shape[0], :blk.shape[1]] += blk
+    r, c = torch.nonzero(acc, as_tuple=True)
+    return Sp(r, c, acc[r, c], (n, n))
+
+
+# ----------------------------------------------------------------------------------------------
+# piece 1 (pygho callers): weighted CN sets  (NeighborOverlapCitation2.py:78-104)
+# ----------------------------------------------------------------------------------------------
+
+def spsphadamard(a: Sp, b: Sp) -> Sp:
+    """pygho ``spsphadamard``: element-wise product on the index intersection [recalled]."""
+    ka = a.row * a.shape[1] + a.col
+    kb = b.row * b.shape[1] + b.col
+    if ka.numel() == 0 or kb.numel() == 0:
+        e = torch.zeros(0, dtype=torch.int64)
+        return Sp(e, e, torch.zeros(0), a.shape)
+    idx = torch.searchsorted(kb, ka).clamp_(max=kb.numel() - 1)
+    hit = kb[idx] == ka
+    return Sp(a.row[hit], a.col[hit], a.values()[hit] * b.values()[idx[hit]], a.shape)
+
+
+def get_cn(adj: Sp, tedge: Tensor, order: int = 2) -> List[Sp]:
+    """``get_cn1_cn2`` (NeighborOverlapCitation2.py:78-104 == NeighborOverlap_large_ppa.py:147-173),
+    extended to order 3 the way SURVEY Q1 specifies: ``Ej3 = spspmm(Ej2, 1, adj, 0)``.
+    Values: cn1 = 1, cn_k = number of k-walks j -> ... -> node."""
+    Ei = index_select_rows(adj, tedge[0])
+    Ej = index_select_rows(adj, tedge[1])
+    out = [spsphadamard(Ei, Ej)]
+    Ejk = Ej
+    for _ in range(1, order):
+        Ejk = sp_matmul(Ejk, adj)
+        out.append(spsphadamard(Ei, Ejk))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# piece 1b + 2: orthogonalised combination and CN-indicator SpMM
+# ----------------------------------------------------------------------------------------------
+
+def sp_sum_dim0(s: Sp) -> Tensor:
+    """torch_sparse ``SparseTensor.sum(dim=0)``: scatter-add of values over col [recalled]."""
+    return torch.zeros(s.shape[1], dtype=torch.float32).index_add_(0, s.col, s.values())
+
+
+def sp_mul_row(s: Sp, other: Tensor) -> Sp:
+    """``SparseTensor.mul(Tensor[1,N])``: value *= other[0, col], explicit zeros kept [recalled]."""
+    return Sp(s.row, s.col, s.values() * other.view(-1)[s.col], s.shape)
+
+
+def spmm_add(s: Sp, x: Tensor) -> Tensor:
+    """torch_sparse ``spmm_add``: CSR SpMM with sum reduction (model.py:2426-2427)."""
+    out = torch.zeros(s.shape[0], x.shape[1], dtype=x.dtype)
+    out.index_add_(0, s.row, s.values().unsqueeze(1) * x[s.col])
+    return out
+
+
+class InnerProdState:
+    """The ``innerprod`` buffer + python counter ``n`` of the predictors (model.py:2238-2250)."""
+
+    def __init__(self, value: float = 0.0, n: int = 0):
+        self.innerprod = torch.tensor([value], dtype=torch.float32)
+        self.n = n
+
+    def innerprod1(self, E1: Sp, E2: Sp, training: bool) -> Tensor:
+        if training:
+            innerprod = spsphadamard(E1, E2).values().sum()
+            self.n += 1
+            beta = self.n ** -1
+            self.innerprod *= (1 - beta)
+            self.innerprod += beta * innerprod
+        return self.innerprod  # NB: the buffer itself, later in-place updates alias (Q9)
+
+
+def _normalise_cn1(cn1: Sp, fill: float) -> Sp:
+    """model.py:2261-2272 (cn5, fill 0) / :3114-3126 (cn7, fill ``args.sum``)."""
+    col_sum = sp_sum_dim0(cn1)
+    col_sum[col_sum == 0] = 1
+    inv_col_sum = 1 / col_sum
+    non_empty_cols = col_sum != 1
+    inv_col_sum[~non_empty_cols] = fill
+    return sp_mul_row(cn1, inv_col_sum.view(1, -1))
+
+
+def _orthogonalise(cnk: Sp, bases: List[Sp], coeffs: List[Tensor]) -> Sp:
+    """model.py:2343-2423 (one base) / :2852-2933 (two bases): align on the unique index union,
+    subtract coeff*base, coalesce, column-normalise by the (signed) column sum (0 -> 1)."""
+    parts = [torch.stack((cnk.row, cnk.col))] + [torch.stack((b.row, b.col)) for b in bases]
+    unique_indices, inverse = torch.unique(torch.cat(parts, dim=1), dim=1, return_inverse=True)
+    nu = unique_indices.size(1)
+    aligned = []
+    off = 0
+    for s in [cnk] + bases:
+        a = torch.zeros(nu, dtype=torch.float32)
+        a[inverse[off:off + s.nnz]] = s.values()
+        aligned.append(a)
+        off += s.nnz
+    new_values = aligned[0]
+    for c, a in zip(coeffs, aligned[1:]):
+        new_values = new_values - c * a
+    col_sum = torch.zeros(cnk.shape[1], dtype=torch.float32)
+    col_sum.index_add_(0, unique_indices[1], new_values)
+    col_sum[col_sum == 0] = 1
+    inv_col_sum = 1 / col_sum
+    return Sp(unique_indices[0], unique_indices[1], new_values * inv_col_sum[unique_indices[1]], cnk.shape)
+
+
+def _scale_factor(base1: Sp, union_nnz: int) -> float:
+    """model.py:2370-2375: max |aligned C1-hat| over the union pattern, 1.0 when that is empty."""
+    if union_nnz > 0:
+        return float(base1.values().abs().max().item()) if base1.nnz > 0 else 0.0
+    return 1.0
+
+
+def cn5_aggregate(cn1: Sp, cn2: Sp, x: Tensor, tar_ei: Tensor, state: InnerProdState, training: bool):
+    """``CNLinkPredictorOringin.multidomainforward`` up to the MLP heads (model.py:2261-2429).
+    Returns (xcn1, xcn2, x_i * x_j, normalized_cn1, normalized_cn2)."""
+    normalized_cn1 = _normalise_cn1(cn1, 0.0)
+    inner_product = state.innerprod1(cn2, normalized_cn1, training)
+    union_nnz = int(torch.unique(torch.cat((cn2.row * cn2.shape[1] + cn2.col,
+                                            cn1.row * cn1.shape[1] + cn1.col))).numel())
+    scale_factor = _scale_factor(normalized_cn1, union_nnz)
+    normalized_inner_product = inner_product / scale_factor if scale_factor > 0 else inner_product
+    normalized_cn2 = _orthogonalise(cn2, [normalized_cn1], [normalized_inner_product.clone()])
+    xcn1 = spmm_add(normalized_cn1, x)
+    xcn2 = spmm_add(normalized_cn2, x)
+    xij = x[tar_ei[0]] * x[tar_ei[1]]
+    return xcn1, xcn2, xij, normalized_cn1, normalized_cn2
+
+
+def cn6_aggregate(cn1: Sp, cn2: Sp, cn3: Sp, x: Tensor, tar_ei: Tensor, state: InnerProdState, training: bool):
+    """``CNLinkPredictor3hopCNs.multidomainforward`` up to the MLP heads (model.py:2546-2940):
+    the order-3 template named by north_star's "depth 3" (SURVEY Q1, §8a-7).  All three
+    ``innerprod1`` calls share one running buffer; both order-3 coefficients read it after the
+    last update (Q9)."""
+    normalized_cn1 = _normalise_cn1(cn1, 0.0)
+    inner_product = state.innerprod1(cn2, normalized_cn1, training)
+    union_nnz = int(torch.unique(torch.cat((cn2.row * cn2.shape[1] + cn2.col,
+                                            cn1.row * cn1.shape[1] + cn1.col))).numel())
+    scale_factor = _scale_factor(normalized_cn1, union_nnz)
+    nip = (inner_product / scale_factor if scale_factor > 0 else inner_product).clone()
+    normalized_cn2 = _orthogonalise(cn2, [normalized_cn1], [nip])
+    xcn1 = spmm_add(normalized_cn1, x)
+    xcn2 = spmm_add(normalized_cn2, x)
+    inner_product1 = state.innerprod1(cn3, normalized_cn1, training)
+    inner_product2 = state.innerprod1(cn3, normalized_cn2, training)
+    union3 = int(torch.unique(torch.cat((cn3.row * cn3.shape[1] + cn3.col,
+                                         normalized_cn1.row * cn3.shape[1] + normalized_cn1.col,
+                                         normalized_cn2.row * cn3.shape[1] + normalized_cn2.col))).numel())
+    scale_factor = _scale_factor(normalized_cn1, union3)
+    if scale_factor > 0:
+        nip1, nip2 = inner_product1 / scale_factor, inner_product2 / scale_factor
+    else:
+        nip1, nip2 = inner_product1.clone(), inner_product2.clone()
+    normalized_cn3 = _orthogonalise(cn3, [normalized_cn1, normalized_cn2], [nip1, nip2])
+    xcn3 = spmm_add(normalized_cn3, x)
+    xij = x[tar_ei[0]] * x[tar_ei[1]]
+    return xcn1, xcn2, xcn3, xij, normalized_cn1, normalized_cn2, normalized_cn3
+
+
+def cn7_aggregate(cn1: Sp, cn2: Sp, x: Tensor, tar_ei: Tensor, args_sum: float):
+    """``CNLinkPredictorbaselearn.multidomainforward`` up to the MLP heads (model.py:3114-3216).
+    ``evaluate_polynomial(N, 0)`` is diag(T0)=I (model.py:2958-3019, Q4), so both ``spspmm`` calls
+    are identities; ``normalized_cn2`` is computed and dropped (Q4): xcn2 uses the raw cn2."""
+    normalized_cn1 = _normalise_cn1(cn1, float(args_sum))
+    xcn1 = spmm_add(normalized_cn1, x)
+    xcn2 = spmm_add(cn2, x)
+    xij = x[tar_ei[0]] * x[tar_ei[1]]
+    return xcn1, xcn2, xij, normalized_cn1
+
+
+# ----------------------------------------------------------------------------------------------
+# piece 3a: GNN neighbour aggregation
+# ----------------------------------------------------------------------------------------------
+
+def pure_conv(x: Tensor, adj: Sp, aggr: str) -> Tensor:
+    """``PureConv.forward`` (model.py:42-55)."""
+    if aggr == "mean":
+        deg = torch.bincount(adj.row, minlength=adj.shape[0]).clamp(min=1).float()
+        return spmm_add(adj, x) / deg.unsqueeze(1)
+    if aggr == "max":
+        out = torch.full((adj.shape[0], x.shape[1]), float("-inf"))
+        out.index_reduce_(0, adj.row, adj.values().unsqueeze(1) * x[adj.col], "amax", include_self=True)
+        out[torch.isinf(out)] = 0  # torch_scatter fills empty rows with 0 [recalled]
+        return out
+    if aggr == "sum":
+        return spmm_add(adj, x)
+    if aggr == "gcn":
+        rowsum = torch.zeros(adj.shape[0]).index_add_(0, adj.row, adj.values())
+        norm = torch.rsqrt_((1 + rowsum)).reshape(-1, 1)
+        x = norm * x
+        x = spmm_add(adj, x) + x
+        x = norm * x
+        return x
+    raise ValueError(aggr)
+
+
+def pure_conv3_gcn(x: Tensor, adj: Sp) -> Tensor:
+    """``PureConv3.forward`` aggr="gcn" before ``self.lin`` (model.py:135-141): symmetric
+    normalisation by 1+deg on both ends, *no* self term (Q13)."""
+    rowsum = torch.zeros(adj.shape[0]).index_add_(0, adj.row, adj.values())
+    norm = torch.rsqrt_((1 + rowsum))
+    enorm = norm[adj.row] * norm[adj.col]
+    return spmm_add(Sp(adj.row, adj.col, adj.values() * enorm, adj.shape), x)
+
+
+def gcnconv_propagate(x: Tensor, adj: Sp, normalize: bool, add_self_loops: bool, aggr: str = "sum") -> Tensor:
+    """PyG 2.6.1 ``GCNConv.propagate`` for a SparseTensor ``adj_t`` as configured by ``convdict``
+    (model.py:58-71): "gin" = plain sum, "gcn" = gcn_norm with self loops of weight 1 and
+    deg = rowsum(A+I) [recalled]. The dense ``lin``/bias stay in torch (out of scope)."""
+    if not normalize:
+        return pure_conv(x, adj, aggr)
+    n = adj.shape[0]
+    row, col, val = adj.row, adj.col, adj.values()
+    if add_self_loops:
+        keep = row != col
+        ar = torch.arange(n)
+        row, col, val = torch.cat((row[keep], ar)), torch.cat((col[keep], ar)), torch.cat((val[keep], torch.ones(n)))
+    deg = torch.zeros(n).index_add_(0, row, val)
+    dinv = deg.pow(-0.5)
+    dinv[torch.isinf(dinv)] = 0
+    w = dinv[row] * val * dinv[col]
+    return torch.zeros(n, x.shape[1]).index_add_(0, row, w.unsqueeze(1) * x[col])
+
+
+# ----------------------------------------------------------------------------------------------
+# metrics (ogb 1.3.6 Evaluator, NeighborOverlap_large.py:162-179, NeighborOverlapCitation2.py:256-259)
+# ----------------------------------------------------------------------------------------------
+
+def hits_at_k(y_pred_pos: Tensor, y_pred_neg: Tensor, k: int) -> float:
+    if y_pred_neg.numel() < k:
+        return 1.0
+    kth = torch.topk(y_pred_neg, k)[0][-1]
+    return float((y_pred_pos > kth).sum().item()) / max(1, y_pred_pos.numel())
+
+
+def mrr(y_pred_pos: Tensor, y_pred_neg: Tensor) -> Tensor:
+    """ogb >=1.3.3 ``_eval_mrr``: optimistic/pessimistic rank average."""
+    y_pred_pos = y_pred_pos.view(-1, 1)
+    optimistic = (y_pred_neg > y_pred_pos).sum(dim=1)
+    pessimistic = (y_pred_neg >= y_pred_pos).sum(dim=1)
+    ranking = 0.5 * (optimistic + pessimistic) + 1
+    return 1.0 / ranking.to(torch.float)
