@@ -1,0 +1,199 @@
+/*
+ * ocn_b200.h -- C ABI of the B200-native OCN common-neighbour hot path.
+ *
+ * The reference (qingpingmo/OCN) has no FFI of its own: it is pure Python over torch_sparse /
+ * pygho / PyG.  Each entry point below therefore names the reference *Python call site* whose
+ * arithmetic it replaces (file:line under /root/reference) -- that is the interface a
+ * maintainer binds (see INTEGRATION.md for the ctypes stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative OCN_E* code on failure, never throws;
+ *     ocn_last_error() returns a thread-local description of the last failure;
+ *   - all pointers are DEVICE pointers owned by the caller (torch), nothing is allocated or
+ *     freed inside the library; variable-size outputs use count -> caller allocates -> fill;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) of the current
+ *     device; no call synchronises;
+ *   - graphs are CSR: rowptr int64[n+1], col int32[nnz], columns ascending and duplicate free
+ *     inside a row (what torch_sparse.SparseTensor.csr() holds, with col narrowed to int32);
+ *   - features / weights are fp32, row-major contiguous; target edges are int64.
+ *   - the fused CN path (ocn_cn_*) requires a symmetric graph (the reference builds every adj
+ *     with to_symmetric(): ogbdataset.py:44-45, NeighborOverlap_large.py:63).
+ */
+#ifndef OCN_B200_H
+#define OCN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCN_OK 0
+#define OCN_EINVAL (-1)   /* bad argument */
+#define OCN_ECUDA (-2)    /* CUDA runtime / launch error */
+#define OCN_ENOSPACE (-3) /* caller-provided buffer too small */
+
+#define OCN_ABI_VERSION 1
+
+int ocn_abi_version(void);
+const char* ocn_last_error(void);
+/* number of SMs of the current device (grid sizing is done inside; exposed for bench.py) */
+int ocn_device_sm_count(void);
+
+/* ---- graph ------------------------------------------------------------------------------ */
+
+/* Checks, on device, what torch_sparse guarantees for an adj built by
+ * SparseTensor.from_edge_index(...).to_symmetric() (NeighborOverlap_large.py:59-63):
+ * out_flags[0] bit0 = a column out of [0,n), bit1 = a row not strictly ascending,
+ * bit2 = rowptr not monotone / rowptr[n] != nnz, bit3 = not symmetric. */
+int ocn_graph_validate(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t nnz,
+                       int32_t* out_flags, void* stream);
+
+/* ---- piece 1: generic per-target-edge row intersection ----------------------------------
+ * adjoverlap(adj1, adj2, tarei) with calresadj=False (utils.py:248-285 -> spmoverlap_
+ * utils.py:163-183): out row b = adj1[src[b]] (cap) adj2[dst[b]], columns ascending, value 1.
+ * adj1/adj2 may be different matrices with the same column space (e.g. A and an explicit A^2,
+ * NeighborOverlap_large.py:78-79). */
+int ocn_rows_intersect_count(const int64_t* rowptr1, const int32_t* col1,
+                             const int64_t* rowptr2, const int32_t* col2,
+                             const int64_t* src, const int64_t* dst, int64_t num_edges,
+                             int64_t* out_counts, void* stream);
+/* out_rowptr = exclusive scan of out_counts (int64[num_edges+1]), computed by the caller. */
+int ocn_rows_intersect_fill(const int64_t* rowptr1, const int32_t* col1,
+                            const int64_t* rowptr2, const int32_t* col2,
+                            const int64_t* src, const int64_t* dst, int64_t num_edges,
+                            const int64_t* out_rowptr, int64_t* out_col, void* stream);
+
+/* ---- pieces 1 + 1b + 2, fused: higher-order CN sets over A, A^2, A^3 ------------------------
+ * Replaces get_cn1_cn2 (NeighborOverlapCitation2.py:78-104, NeighborOverlap_large_ppa.py:147-173)
+ * and adjoverlap(adj, adj, e) / adjoverlap(adj, adj2, e) (NeighborOverlap_large.py:78-79)
+ * without materialising A^2/A^3, then the cn5 / cn7 / cn6 combination
+ * (model.py:2261-2429, 3114-3216, 2546-2940).
+ *
+ * A call processes a STREAM of num_edges target links cut into consecutive batches of
+ * batch_size links (the reference's PermIterator batches, utils.py:8-36); every batch is
+ * normalised on its own, exactly as one multidomainforward call would.
+ *
+ * Step 1  ocn_cn_plan      sizes + schedule              (sync-free; caller reads 4 int64 back)
+ * Step 2  ocn_cn_build     CN_k(e) = A[i] (*) A^k[j], k=1..order, as dense records over N(i)
+ *                          + per-batch column statistics
+ * Step 3  ocn_cn_stats     per-batch scalars (scale factor, inner products)
+ * Step 4  ocn_cn_aggregate xcn_k = C-hat_k @ x, x_i * x_j
+ *         ocn_cn_aggregate_bwd  grad_x += C-hat_k^T @ grad_xcn_k
+ *         ocn_cn_extract_count / _fill   the sparse [B x N] CN matrices themselves
+ * Step 5  ocn_cn_release   resets the column statistics touched by this stream
+ */
+
+/* plan[] int64 layout written by ocn_cn_plan (device): */
+#define OCN_PLAN_NUM_RECORDS 0 /* sum over edges of deg(src) */
+#define OCN_PLAN_NUM_RUNS 1    /* maximal runs of equal src inside a batch */
+#define OCN_PLAN_NUM_UNITS 2   /* work units of ocn_cn_build */
+#define OCN_PLAN_NUM_BATCHES 3
+#define OCN_PLAN_WORDS 8
+
+/* bytes of plan scratch the caller must provide for a stream of num_edges links */
+size_t ocn_cn_plan_bytes(int64_t num_edges);
+/* bytes of per-batch column statistics for one batch over n nodes */
+size_t ocn_cn_colstat_bytes(int64_t n);
+/* bytes per record */
+size_t ocn_cn_record_bytes(void);
+
+int ocn_cn_plan(const int64_t* rowptr, int64_t n,
+                const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t batch_size,
+                void* plan_scratch, size_t plan_scratch_bytes,
+                int64_t* out_plan /* device int64[OCN_PLAN_WORDS] */, void* stream);
+
+/* records: device buffer of >= plan[NUM_RECORDS] * ocn_cn_record_bytes() bytes.
+ * colstat: device buffer of num_batches * ocn_cn_colstat_bytes(n) bytes, ZERO on entry
+ *          (ocn_cn_release restores that), or NULL when only the sets are wanted.
+ * order in {1,2,3}; weighted != 0 keeps walk counts as values (pygho path), == 0 uses the 0/1
+ * structure (torch_sparse path). */
+int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n,
+                 const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t batch_size,
+                 int order, int weighted,
+                 const void* plan_scratch, const int64_t* plan,
+                 void* records, int64_t records_capacity, void* colstat, void* stream);
+
+/* variant: 5 = cn5/OCN (order 2) or its order-3 form (cn6 template), 7 = cn7/OCNP.
+ * fill   : weight of a node that is CN1 of exactly one edge of the batch (cn5: 0, cn7: args.sum).
+ * ip     : device fp32[3] = inner-product buffer value used for (C2|C1-hat), (C3|C1-hat), (C3|C2-hat);
+ *          eval mode passes the stored buffer three times (model.py:2241-2250, Q9).
+ * out_batch_scalars: device fp32[num_batches * 8]:
+ *          [0] scale = max|C1-hat|, [1] s12 = sum(C2 * C1-hat), [2] s13, [3] s23 (training only). */
+int ocn_cn_stats(const int64_t* rowptr, const int32_t* col, int64_t n,
+                 const int64_t* src, int64_t num_edges, int64_t batch_size,
+                 int order, int weighted, int variant, float fill, const float* ip,
+                 int stage /* 0: scale + s12, 1: s13 + s23 (needs stage 0 and final ip[0]) */,
+                 const void* plan_scratch, const void* records, const void* colstat,
+                 float* batch_scalars, void* stream);
+
+int ocn_cn_aggregate(const int64_t* rowptr, const int32_t* col, int64_t n,
+                     const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t batch_size,
+                     int order, int weighted, int variant, float fill, const float* ip,
+                     const void* plan_scratch, const void* records, const void* colstat,
+                     const float* batch_scalars,
+                     const float* x, int64_t feat,
+                     float* xcn1, float* xcn2, float* xcn3 /* NULL unless order 3 */,
+                     float* xij /* x[src]*x[dst], may be NULL */, void* stream);
+
+int ocn_cn_aggregate_bwd(const int64_t* rowptr, const int32_t* col, int64_t n,
+                         const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t batch_size,
+                         int order, int weighted, int variant, float fill, const float* ip,
+                         const void* plan_scratch, const void* records, const void* colstat,
+                         const float* batch_scalars,
+                         const float* x, int64_t feat,
+                         const float* g_xcn1, const float* g_xcn2, const float* g_xcn3, const float* g_xij,
+                         float* grad_x /* [n, feat], accumulated into */, void* stream);
+
+/* which: 1,2,3 = raw CN_k (value 1 / walk count); 11,12,13 = normalised C-hat_k as the predictor
+ * builds them (pattern of C-hat_2 = CN1 u CN2 etc., explicit zeros kept, model.py:2352-2391). */
+int ocn_cn_extract_count(const int64_t* rowptr, int64_t n, const int64_t* src, int64_t num_edges,
+                         int which, int weighted, const void* plan_scratch, const void* records,
+                         int64_t* out_counts, void* stream);
+int ocn_cn_extract_fill(const int64_t* rowptr, const int32_t* col, int64_t n,
+                        const int64_t* src, int64_t num_edges, int64_t batch_size,
+                        int which, int weighted, int variant, float fill, const float* ip,
+                        const void* plan_scratch, const void* records, const void* colstat,
+                        const float* batch_scalars,
+                        const int64_t* out_rowptr, int64_t* out_col, float* out_val, void* stream);
+
+int ocn_cn_release(const int64_t* rowptr, const int32_t* col, int64_t n,
+                   const int64_t* src, int64_t num_edges, int64_t batch_size,
+                   const void* plan_scratch, const void* records, void* colstat, void* stream);
+
+/* ---- piece 2 / 3a: CSR SpMM ---------------------------------------------------------------
+ * spmm_add / spmm_mean / spmm_max(src, other) (torch_sparse.matmul; model.py:6,45-53,2426-2427).
+ * val may be NULL (all ones). reduce: 0 sum, 1 mean, 2 max (empty rows -> 0). */
+int ocn_spmm_csr(const int64_t* rowptr, const int32_t* col, const float* val, int64_t num_rows,
+                 const float* x, int64_t feat, int reduce, float* out, void* stream);
+/* grad_x[col] += val * grad_out[row]  (transpose SpMM by scatter; reduce sum/mean only) */
+int ocn_spmm_csr_bwd(const int64_t* rowptr, const int32_t* col, const float* val, int64_t num_rows,
+                     const float* grad_out, int64_t feat, int reduce, float* grad_x, void* stream);
+
+/* GCN-style aggregation fused with its degree normalisation.
+ * mode 3: PureConv "gcn" (model.py:51-54)   out = nrm * (A (nrm*x) + nrm*x), nrm = rsqrt(1 + rowsum)
+ *         (== PyG GCNConv with self loops on a loop-free unit-weight graph, model.py:58-60)
+ * mode 4: PureConv3 "gcn" (model.py:136-140) out = (nrm_r * a_rc * nrm_c) x, no self term
+ * edge_w may be NULL (unit weights; DropAdj supplies rescaled values, model.py:219-229). */
+int ocn_gcn_norm(const int64_t* rowptr, const float* edge_w, int64_t n, float* out_norm, void* stream);
+int ocn_gcn_spmm(const int64_t* rowptr, const int32_t* col, const float* edge_w, int64_t n,
+                 const float* norm, int mode, const float* x, int64_t feat, float* out, void* stream);
+
+/* ---- piece 3b: A^2 SpGEMM -----------------------------------------------------------------
+ * spadj @ spadj (NeighborOverlap_large.py:74,119) and sparse_tensor_multiply (utils.py:287-329).
+ * fold == 0: the true A^2.  fold == bs > 0: the reference's adj2byblock result, every bs x bs
+ * block summed into the top-left corner.  Two phase: symbolic writes the nnz of
+ * every output row, numeric fills ascending columns (+ fp32 2-walk counts if out_val != NULL).
+ * scratch: ocn_spgemm_scratch_bytes(n) bytes, zero on first use (left zero on return). */
+size_t ocn_spgemm_scratch_bytes(int64_t n);
+int ocn_spgemm_a2_symbolic(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t fold,
+                           void* scratch, int64_t* out_row_nnz, void* stream);
+int ocn_spgemm_a2_numeric(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t fold,
+                          void* scratch, const int64_t* out_rowptr, int32_t* out_col, float* out_val,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCN_B200_H */

@@ -1,0 +1,19 @@
+"""ocn_b200 -- B200-native common-neighbour hot path of OCN.
+
+Importing the package does not load the CUDA library; the first op does, and raises if
+``libocn_b200.so`` is missing (there is no CPU fallback).
+"""
+from . import synth  # noqa: F401
+from .graph import Graph  # noqa: F401
+from .cn import CNSession, SparseRows, adjoverlap, cn_aggregate_eval, get_cn, get_cn1_cn2  # noqa: F401
+from .sparse_ops import (gcn_norm, gcnconv_propagate, pure_conv, pure_conv3_gcn, sparse_tensor_multiply,  # noqa: F401
+                         spgemm_a2, spmm, spmm_add, spmm_max, spmm_mean)
+from .predictor import (CNLinkPredictor3hopCNs, CNLinkPredictorbaselearn, CNLinkPredictorOringin,  # noqa: F401
+                        predictor_dict)
+
+__all__ = [
+    "Graph", "CNSession", "SparseRows", "adjoverlap", "cn_aggregate_eval", "get_cn", "get_cn1_cn2",
+    "gcn_norm", "gcnconv_propagate", "pure_conv", "pure_conv3_gcn", "sparse_tensor_multiply", "spgemm_a2",
+    "spmm", "spmm_add", "spmm_max", "spmm_mean", "CNLinkPredictorOringin", "CNLinkPredictor3hopCNs",
+    "CNLinkPredictorbaselearn", "predictor_dict", "synth",
+]

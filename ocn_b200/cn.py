@@ -1,0 +1,267 @@
+"""Host side of the fused common-neighbour path (pieces 1, 1b and 2 of north_star).
+
+Mirrors the reference call sites one-to-one:
+
+* ``adjoverlap(adj1, adj2, tarei)``            utils.py:248-285 (calresadj=False branch)
+* ``get_cn1_cn2(adj, tedge)``                  NeighborOverlapCitation2.py:78-104
+* ``cn_aggregate(...)``                        the part of ``multidomainforward`` between the CN sets
+                                               and the MLP heads (model.py:2261-2429 cn5, :3114-3216 cn7,
+                                               :2546-2940 order 3)
+
+Everything runs through the C ABI of ``include/ocn_b200.h`` on CUDA tensors; nothing here
+computes on the CPU.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .graph import Graph, _require_cuda
+
+PLAN_WORDS = 8
+COLSTAT_BUDGET_BYTES = 4 << 30  # per-wave cap for the per-batch column statistics
+
+
+@dataclasses.dataclass
+class SparseRows:
+    """A [B x N] sparse matrix in CSR, entries ascending by (row, col) -- the layout of the
+    torch_sparse.SparseTensor that ``adjoverlap`` returns (utils.py:146-151)."""
+    rowptr: Tensor          # int64 [B+1]
+    col: Tensor             # int64 [nnz]
+    value: Optional[Tensor]  # fp32 [nnz]
+    shape: Tuple[int, int]
+
+    def row(self) -> Tensor:
+        return torch.repeat_interleave(torch.arange(self.shape[0], device=self.col.device),
+                                       self.rowptr[1:] - self.rowptr[:-1])
+
+    def coo(self):
+        return self.row(), self.col, self.value
+
+    def sizes(self):
+        return self.shape
+
+    def nnz(self) -> int:
+        return int(self.col.numel())
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _edges(tarei: Tensor) -> Tuple[Tensor, Tensor]:
+    if tarei.dim() != 2 or tarei.shape[0] != 2:
+        raise ValueError("target links must be an int64 tensor of shape [2, B]")
+    e = tarei.to(torch.int64).contiguous()
+    return e[0], e[1]
+
+
+def adjoverlap(adj1: Graph, adj2: Graph, tarei: Tensor, filled1: bool = False, calresadj: bool = False,
+               cnsampledeg: int = -1, ressampledeg: int = -1) -> SparseRows:
+    """``utils.adjoverlap``: row b = adj1[tarei[0,b]] (cap) adj2[tarei[1,b]], value 1.0.
+
+    ``adj2`` may be any matrix over the same columns (A itself, an explicit A^2 from
+    ``spgemm_a2`` or the folded adj2byblock matrix)."""
+    if calresadj or cnsampledeg > 0 or ressampledeg > 0:
+        raise NotImplementedError("only the calresadj=False, cnsampledeg=-1 branch used by cn5/cn7 is on the hot path")
+    _require_cuda(tarei)
+    if adj1.sizes() != adj2.sizes():
+        raise AssertionError("adj1.sizes() == adj2.sizes()")  # utils.py:165
+    src, dst = _edges(tarei)
+    B = src.numel()
+    dev = adj1.device
+    counts = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        _lib.check(L.ocn_rows_intersect_count(_lib.ptr(adj1.rowptr), _lib.ptr(adj1.col), _lib.ptr(adj2.rowptr),
+                                              _lib.ptr(adj2.col), _lib.ptr(src), _lib.ptr(dst), B,
+                                              _lib.ptr(counts), st), "ocn_rows_intersect_count")
+        rowptr = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts[:B], 0, out=rowptr[1:])
+        nnz = int(rowptr[-1].item())
+        col = torch.empty(nnz, dtype=torch.int64, device=dev)
+        if nnz:
+            _lib.check(L.ocn_rows_intersect_fill(_lib.ptr(adj1.rowptr), _lib.ptr(adj1.col), _lib.ptr(adj2.rowptr),
+                                                 _lib.ptr(adj2.col), _lib.ptr(src), _lib.ptr(dst), B,
+                                                 _lib.ptr(rowptr), _lib.ptr(col), st), "ocn_rows_intersect_fill")
+    return SparseRows(rowptr, col, torch.ones(nnz, dtype=torch.float32, device=dev), (B, adj1.n_cols))
+
+
+class CNSession:
+    """One stream of target links against one graph: plan -> build -> stats -> aggregate / extract.
+
+    ``batch_size`` cuts the stream into the reference's link batches; every batch is
+    normalised independently (the column sums of model.py:2261 run over one batch)."""
+
+    def __init__(self, graph: Graph, tarei: Tensor, batch_size: Optional[int] = None):
+        _require_cuda(graph.col)
+        _require_cuda(tarei)
+        self.g = graph
+        self.src, self.dst = _edges(tarei)
+        self.T = int(self.src.numel())
+        if self.T == 0:
+            raise ValueError("empty link batch")
+        self.batch_size = int(batch_size or self.T)
+        self.nb = (self.T + self.batch_size - 1) // self.batch_size
+        self.dev = graph.device
+        L = _lib.lib()
+        self.L = L
+        self.plan_bytes = L.ocn_cn_plan_bytes(self.T)
+        self.plan_scratch = torch.empty(self.plan_bytes, dtype=torch.uint8, device=self.dev)
+        self.plan = torch.zeros(PLAN_WORDS, dtype=torch.int64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(L.ocn_cn_plan(_lib.ptr(graph.rowptr), graph.n, _lib.ptr(self.src), _lib.ptr(self.dst), self.T,
+                                     self.batch_size, _lib.ptr(self.plan_scratch), self.plan_bytes,
+                                     _lib.ptr(self.plan), _stream(self.dev)), "ocn_cn_plan")
+        host = self.plan.tolist()  # the one host sync of the session: buffer sizes
+        self.num_records, self.num_runs, self.num_units = host[0], host[1], host[2]
+        self.records = torch.empty(max(1, self.num_records) * L.ocn_cn_record_bytes(), dtype=torch.uint8,
+                                   device=self.dev)
+        self.colstat = torch.zeros(self.nb * L.ocn_cn_colstat_bytes(graph.n), dtype=torch.uint8, device=self.dev)
+        self.bscal = torch.zeros(self.nb * 8, dtype=torch.float32, device=self.dev)
+        self.order = 0
+        self.weighted = True
+        self._released = False
+
+    # -- steps ------------------------------------------------------------------------------
+    def build(self, order: int, weighted: bool, with_stats: bool = True) -> "CNSession":
+        g = self.g
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.ocn_cn_build(_lib.ptr(g.rowptr), _lib.ptr(g.col), g.n, _lib.ptr(self.src),
+                                           _lib.ptr(self.dst), self.T, self.batch_size, int(order), int(bool(weighted)),
+                                           _lib.ptr(self.plan_scratch), _lib.ptr(self.plan), _lib.ptr(self.records),
+                                           self.num_records, _lib.ptr(self.colstat) if with_stats else None,
+                                           _stream(self.dev)), "ocn_cn_build")
+        self.order, self.weighted = int(order), bool(weighted)
+        return self
+
+    def stats(self, variant: int, fill: float, ip: Tensor, stage: int = 0) -> Tensor:
+        g = self.g
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.ocn_cn_stats(_lib.ptr(g.rowptr), _lib.ptr(g.col), g.n, _lib.ptr(self.src), self.T,
+                                           self.batch_size, self.order, int(self.weighted), int(variant), float(fill),
+                                           _lib.ptr(ip), int(stage), _lib.ptr(self.plan_scratch),
+                                           _lib.ptr(self.records), _lib.ptr(self.colstat), _lib.ptr(self.bscal),
+                                           _stream(self.dev)), "ocn_cn_stats")
+        return self.bscal.view(self.nb, 8)
+
+    def aggregate(self, x: Tensor, variant: int, fill: float, ip: Tensor, want_xij: bool = True):
+        g = self.g
+        x = _check_x(x, g)
+        F = x.shape[1]
+        mk = lambda: torch.empty(self.T, F, dtype=torch.float32, device=self.dev)
+        xcn1, xcn2 = mk(), (mk() if self.order >= 2 else None)
+        xcn3 = mk() if (self.order >= 3 and variant == 5) else None
+        xij = mk() if want_xij else None
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.ocn_cn_aggregate(
+                _lib.ptr(g.rowptr), _lib.ptr(g.col), g.n, _lib.ptr(self.src), _lib.ptr(self.dst), self.T,
+                self.batch_size, self.order, int(self.weighted), int(variant), float(fill), _lib.ptr(ip),
+                _lib.ptr(self.plan_scratch), _lib.ptr(self.records), _lib.ptr(self.colstat), _lib.ptr(self.bscal),
+                _lib.ptr(x), F, _lib.ptr(xcn1), _lib.ptr(xcn2), _lib.ptr(xcn3), _lib.ptr(xij), _stream(self.dev)),
+                "ocn_cn_aggregate")
+        return xcn1, xcn2, xcn3, xij
+
+    def aggregate_bwd(self, x: Tensor, variant: int, fill: float, ip: Tensor, g1, g2, g3, gij, grad_x: Tensor):
+        g = self.g
+        c = lambda t: None if t is None else t.contiguous()
+        g1, g2, g3, gij = c(g1), c(g2), c(g3), c(gij)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.ocn_cn_aggregate_bwd(
+                _lib.ptr(g.rowptr), _lib.ptr(g.col), g.n, _lib.ptr(self.src), _lib.ptr(self.dst), self.T,
+                self.batch_size, self.order, int(self.weighted), int(variant), float(fill), _lib.ptr(ip),
+                _lib.ptr(self.plan_scratch), _lib.ptr(self.records), _lib.ptr(self.colstat), _lib.ptr(self.bscal),
+                _lib.ptr(x), x.shape[1], _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(g3), _lib.ptr(gij), _lib.ptr(grad_x),
+                _stream(self.dev)), "ocn_cn_aggregate_bwd")
+        return grad_x
+
+    def extract(self, which: int, variant: int = 5, fill: float = 0.0, ip: Optional[Tensor] = None) -> SparseRows:
+        """which 1/2/3: raw CN_k; 11/12/13: the normalised matrices the predictor feeds to spmm_add."""
+        g = self.g
+        counts = torch.zeros(self.T + 1, dtype=torch.int64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            st = _stream(self.dev)
+            _lib.check(self.L.ocn_cn_extract_count(_lib.ptr(g.rowptr), g.n, _lib.ptr(self.src), self.T, int(which),
+                                                   int(self.weighted), _lib.ptr(self.plan_scratch),
+                                                   _lib.ptr(self.records), _lib.ptr(counts), st),
+                       "ocn_cn_extract_count")
+            rowptr = torch.zeros(self.T + 1, dtype=torch.int64, device=self.dev)
+            torch.cumsum(counts[:self.T], 0, out=rowptr[1:])
+            nnz = int(rowptr[-1].item())
+            col = torch.empty(nnz, dtype=torch.int64, device=self.dev)
+            val = torch.empty(nnz, dtype=torch.float32, device=self.dev)
+            if ip is None:
+                ip = torch.zeros(3, dtype=torch.float32, device=self.dev)
+            if nnz:
+                _lib.check(self.L.ocn_cn_extract_fill(
+                    _lib.ptr(g.rowptr), _lib.ptr(g.col), g.n, _lib.ptr(self.src), self.T, self.batch_size, int(which),
+                    int(self.weighted), int(variant), float(fill), _lib.ptr(ip), _lib.ptr(self.plan_scratch),
+                    _lib.ptr(self.records), _lib.ptr(self.colstat), _lib.ptr(self.bscal), _lib.ptr(rowptr),
+                    _lib.ptr(col), _lib.ptr(val), st), "ocn_cn_extract_fill")
+        return SparseRows(rowptr, col, val, (self.T, g.n))
+
+    def release(self):
+        """Zero the column statistics this stream touched (the buffer is reusable afterwards)."""
+        g = self.g
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.ocn_cn_release(_lib.ptr(g.rowptr), _lib.ptr(g.col), g.n, _lib.ptr(self.src), self.T,
+                                             self.batch_size, _lib.ptr(self.plan_scratch), _lib.ptr(self.records),
+                                             _lib.ptr(self.colstat), _stream(self.dev)), "ocn_cn_release")
+        self._released = True
+
+
+def _check_x(x: Tensor, g: Graph) -> Tensor:
+    _require_cuda(x)
+    if x.dim() != 2 or x.shape[0] < g.n:
+        raise ValueError(f"x must be [N, F] with N >= {g.n}")
+    if x.dtype != torch.float32:
+        raise TypeError("x must be float32 (the reference computes the CN aggregation in fp32)")
+    return x.contiguous()
+
+
+def get_cn(adj: Graph, tedge: Tensor, order: int = 2, weighted: bool = True) -> List[SparseRows]:
+    """``get_cn1_cn2`` (NeighborOverlapCitation2.py:78-104) generalised to ``order`` sets.
+    weighted=True keeps the pygho walk counts as values, False gives the 0/1 structure that
+    ``adjoverlap(adj, adj2, e)`` yields in the _large drivers."""
+    s = CNSession(adj, tedge).build(order, weighted, with_stats=False)
+    return [s.extract(k) for k in range(1, order + 1)]
+
+
+def get_cn1_cn2(adj: Graph, tedge: Tensor):
+    cn1, cn2 = get_cn(adj, tedge, 2, True)
+    return cn1, cn2
+
+
+def waves(num_links: int, batch_size: int, n_nodes: int, budget_bytes: int = COLSTAT_BUDGET_BYTES):
+    """Split a long stream into waves whose per-batch column statistics fit ``budget_bytes``."""
+    per_batch = 32 * n_nodes
+    bpw = max(1, budget_bytes // per_batch)
+    step = bpw * batch_size
+    return [(s, min(num_links, s + step)) for s in range(0, num_links, step)]
+
+
+def cn_aggregate_eval(graph: Graph, tarei: Tensor, x: Tensor, batch_size: int, order: int, weighted: bool,
+                      variant: int, fill: float, ip: Tensor, want_xij: bool = True,
+                      budget_bytes: int = COLSTAT_BUDGET_BYTES):
+    """Inference-mode fused path for a whole stream (no autograd): returns xcn1, xcn2, xcn3, xij
+    of shape [T, F].  ``ip`` is the predictor's ``innerprod`` buffer broadcast to 3 entries."""
+    T = tarei.shape[1]
+    outs = None
+    for (s, e) in waves(T, batch_size, graph.n, budget_bytes):
+        sess = CNSession(graph, tarei[:, s:e], batch_size).build(order, weighted)
+        if variant == 5:
+            sess.stats(variant, fill, ip, 0)
+        part = sess.aggregate(x, variant, fill, ip, want_xij)
+        if s == 0 and e == T:
+            return part
+        if outs is None:
+            outs = [None if p is None else torch.empty(T, p.shape[1], dtype=p.dtype, device=p.device) for p in part]
+        for o, p in zip(outs, part):
+            if o is not None:
+                o[s:e] = p
+    return tuple(outs)

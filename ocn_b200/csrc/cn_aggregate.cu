@@ -1,0 +1,606 @@
+// Batch statistics, orthogonalised weights, CN-indicator SpMM (forward / backward), sparse
+// extraction and release of the per-batch column statistics.
+//
+// Weight algebra (cn5: model.py:2261-2423, order 3: model.py:2546-2933, cn7: model.py:3114-3126).
+// For node k of batch b with c1 = #links having k in CN1, S2 = sum_b C2[b,k], S3 = sum_b C3[b,k]:
+//   w1(k)      = 1/c1 if c1 >= 2 else fill                   (singletons get `fill`)
+//   C1h[e,k]   = w1(k) on CN1(e)
+//   scale      = max |C1h| = 1 / min{c1 : c1 >= 2}           (0 if there is none)
+//   ipn_x      = ip_x / scale if scale > 0 else ip_x
+//   C2'[e,k]   = C2[e,k] - ipn_a * C1h[e,k]     on CN1(e) u CN2(e)
+//   c2(k)      = sum_e C2'[e,k] = S2 - (ipn_a * w1(k)) * c1   (c1 >= 2; exact integer part, one
+//                rounding for the correction -- the reference adds the per-link terms one by
+//                one in fp32, which differs by rounding only)          ; 0 -> 1
+//   C2h        = C2' * (1 / c2(k))
+//   C3'[e,k]   = C3 - ipn_b * C1h - ipn_c * C2h  on CN1 u CN2 u CN3
+//   c3(k)      = S3 - (ipn_b * w1) * c1 - ipn_c * (c2raw * (1/c2))          ; 0 -> 1
+//   C3h        = C3' * (1 / c3(k))
+#include "common.cuh"
+
+namespace ocn {
+
+struct WeightParams {
+    int order, weighted, variant;
+    float fill, ipn_a, ipn_b, ipn_c;
+};
+
+struct EntryWeights {
+    float w1, w2, w3;   // C1h, C2h (cn7: raw C2), C3h values of this (link, node)
+    bool in1, in2, in3; // membership in the three patterns
+};
+
+__device__ __forceinline__ EntryWeights entry_weights(Record rec, uint32_t c1cnt, unsigned long long s2,
+                                                      unsigned long long s3, const WeightParams& P) {
+    EntryWeights W;
+    const bool has1 = (rec.x >> 31) != 0u;
+    const uint32_t C2 = rec.x & 0x7fffffffu, C3 = rec.y;
+    const float c2v = P.weighted ? (float)C2 : (C2 ? 1.0f : 0.0f);
+    const float c3v = P.weighted ? (float)C3 : (C3 ? 1.0f : 0.0f);
+    const float w1k = (c1cnt >= 2u) ? __fdiv_rn(1.0f, (float)c1cnt) : P.fill;
+    const float h1 = has1 ? w1k : 0.0f;
+    W.in1 = has1;
+    W.w1 = h1;
+    W.in2 = has1 || (P.order >= 2 && C2 != 0u);
+    W.in3 = W.in2 || (P.order >= 3 && C3 != 0u);
+    W.w2 = 0.0f;
+    W.w3 = 0.0f;
+    if (P.variant == 7) {
+        W.in2 = (P.order >= 2 && C2 != 0u);
+        W.w2 = c2v;
+        W.in3 = false;
+        return W;
+    }
+    if (P.order < 2) return W;
+    const float c1f = (float)c1cnt;
+    const float corr1a = (c1cnt >= 2u) ? __fmul_rn(__fmul_rn(P.ipn_a, w1k), c1f) : 0.0f;
+    const float c2raw = __fsub_rn((float)s2, corr1a);
+    const float c2sum = (c2raw == 0.0f) ? 1.0f : c2raw;
+    const float inv2 = __fdiv_rn(1.0f, c2sum);
+    const float v2 = __fsub_rn(c2v, __fmul_rn(P.ipn_a, h1));
+    W.w2 = W.in2 ? __fmul_rn(v2, inv2) : 0.0f;
+    if (P.order < 3) return W;
+    const float corr1b = (c1cnt >= 2u) ? __fmul_rn(__fmul_rn(P.ipn_b, w1k), c1f) : 0.0f;
+    const float t2 = (c2raw == 0.0f) ? 0.0f : __fmul_rn(c2raw, inv2);
+    const float c3raw = __fsub_rn(__fsub_rn((float)s3, corr1b), __fmul_rn(P.ipn_c, t2));
+    const float c3sum = (c3raw == 0.0f) ? 1.0f : c3raw;
+    const float inv3 = __fdiv_rn(1.0f, c3sum);
+    const float v3 = __fsub_rn(__fsub_rn(c3v, __fmul_rn(P.ipn_b, h1)), __fmul_rn(P.ipn_c, W.w2));
+    W.w3 = W.in3 ? __fmul_rn(v3, inv3) : 0.0f;
+    return W;
+}
+
+__device__ __forceinline__ WeightParams make_params(int order, int weighted, int variant, float fill,
+                                                    const float* __restrict__ ip, const float* __restrict__ bscal) {
+    WeightParams P;
+    P.order = order;
+    P.weighted = weighted;
+    P.variant = variant;
+    P.fill = fill;
+    const float scale = bscal ? bscal[0] : 0.0f;
+    const float a = ip ? ip[0] : 0.0f, b = ip ? ip[1] : 0.0f, c = ip ? ip[2] : 0.0f;
+    P.ipn_a = scale > 0.0f ? __fdiv_rn(a, scale) : a;
+    P.ipn_b = scale > 0.0f ? __fdiv_rn(b, scale) : b;
+    P.ipn_c = scale > 0.0f ? __fdiv_rn(c, scale) : c;
+    return P;
+}
+
+__device__ __forceinline__ void load_colstat(const ColStat* cs, uint32_t& c1, unsigned long long& s2,
+                                             unsigned long long& s3) {
+    const uint4 a = __ldcg(reinterpret_cast<const uint4*>(cs));
+    c1 = a.x;
+    s2 = ((unsigned long long)a.w << 32) | a.z;
+    const uint2 b = __ldcg(reinterpret_cast<const uint2*>(cs) + 2);
+    s3 = ((unsigned long long)b.y << 32) | b.x;
+}
+
+// ---- batch scalars -------------------------------------------------------------------------
+// batch_scalars[b*8 + {0: scale, 1: s12, 2: s13, 3: s23, 4: (u32) min c1>=2}]
+__global__ void k_stats_init(float* __restrict__ bscal, int64_t num_batches, int stage) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= num_batches) return;
+    if (stage == 0) {
+        bscal[b * 8 + 0] = 0.0f;
+        bscal[b * 8 + 1] = 0.0f;
+        bscal[b * 8 + 2] = 0.0f;
+        bscal[b * 8 + 3] = 0.0f;
+        reinterpret_cast<uint32_t*>(bscal)[b * 8 + 4] = 0xffffffffu;
+    }
+}
+
+// one warp per link: min over CN1 members of the column count, and the link's partial sums
+__global__ void k_stats(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
+                        const int64_t* __restrict__ src, int64_t T, int64_t batch_size, int order, int weighted,
+                        int variant, float fill, const float* __restrict__ ip, int stage,
+                        const int64_t* __restrict__ rec_off, const Record* __restrict__ records,
+                        const ColStat* __restrict__ colstat, float* __restrict__ bscal, float* __restrict__ partial) {
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int lane = lane_id();
+    for (int64_t t = warp; t < T; t += nwarps) {
+        const int64_t b = t / batch_size;
+        const int64_t i = src[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs, ro = rec_off[t];
+        const ColStat* cs = colstat + b * n;
+        WeightParams P = make_params(order, weighted, variant, fill, ip, stage == 0 ? nullptr : bscal + b * 8);
+        uint32_t minc = 0xffffffffu;
+        float s_a = 0.0f, s_b = 0.0f;
+        for (int64_t base = 0; base < d; base += 32) {
+            const int64_t p = base + lane;
+            if (p < d) {
+                const Record rec = records[ro + p];
+                if (rec.x | rec.y) {
+                    const int32_t k = ldg_i32(col + rs + p);
+                    uint32_t c1;
+                    unsigned long long s2, s3;
+                    load_colstat(cs + k, c1, s2, s3);
+                    const EntryWeights W = entry_weights(rec, c1, s2, s3, P);
+                    const uint32_t C2 = rec.x & 0x7fffffffu, C3 = rec.y;
+                    if (stage == 0) {
+                        if (W.in1 && c1 >= 2u) minc = c1 < minc ? c1 : minc;
+                        if (W.in1 && C2) s_a += (weighted ? (float)C2 : 1.0f) * W.w1;
+                    } else {
+                        if (C3) {
+                            const float c3v = weighted ? (float)C3 : 1.0f;
+                            if (W.in1) s_a += c3v * W.w1;
+                            if (W.in2) s_b += c3v * W.w2;
+                        }
+                    }
+                }
+            }
+        }
+        if (stage == 0) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                uint32_t other = __shfl_xor_sync(0xffffffffu, minc, o);
+                minc = other < minc ? other : minc;
+            }
+            s_a = warp_sum(s_a);
+            if (lane == 0) {
+                if (minc != 0xffffffffu) atomicMin(reinterpret_cast<uint32_t*>(bscal) + b * 8 + 4, minc);
+                partial[t] = s_a;
+            }
+        } else {
+            s_a = warp_sum(s_a);
+            s_b = warp_sum(s_b);
+            if (lane == 0) {
+                partial[T + 1 + t] = s_a;
+                partial[2 * (T + 1) + t] = s_b;
+            }
+        }
+    }
+}
+
+// one CTA per batch: fixed-order tree sum of the link partials (run-to-run deterministic)
+__global__ void k_stats_finalize(int64_t T, int64_t batch_size, int stage, const float* __restrict__ partial,
+                                 float* __restrict__ bscal) {
+    __shared__ float sh[2][256];
+    const int64_t b = blockIdx.x;
+    const int64_t t0 = b * batch_size, t1 = (t0 + batch_size < T) ? t0 + batch_size : T;
+    float a = 0.0f, c = 0.0f;
+    for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+        if (stage == 0) a += partial[t];
+        else { a += partial[T + 1 + t]; c += partial[2 * (T + 1) + t]; }
+    }
+    sh[0][threadIdx.x] = a;
+    sh[1][threadIdx.x] = c;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (stage == 0) {
+            const uint32_t minc = reinterpret_cast<const uint32_t*>(bscal)[b * 8 + 4];
+            bscal[b * 8 + 0] = (minc == 0xffffffffu) ? 0.0f : __fdiv_rn(1.0f, (float)minc);
+            bscal[b * 8 + 1] = sh[0][0];
+        } else {
+            bscal[b * 8 + 2] = sh[0][0];
+            bscal[b * 8 + 3] = sh[1][0];
+        }
+    }
+}
+
+// ---- CN-indicator SpMM ---------------------------------------------------------------------
+// One warp per link.  A feature row is covered by LPR lanes (VPL float4 each); 32/LPR rows are
+// gathered at once.  The three weighted sums share one gather of x[k,:] because all three CN
+// sets live on N(src).  Summation order is fixed (ascending position), so results are
+// run-to-run deterministic.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+k_cn_aggregate(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
+               const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t T, int64_t batch_size,
+               int order, int weighted, int variant, float fill, const float* __restrict__ ip,
+               const int64_t* __restrict__ rec_off, const Record* __restrict__ records,
+               const ColStat* __restrict__ colstat, const float* __restrict__ bscal,
+               const float* __restrict__ x, int nvec, int lpr,
+               float* __restrict__ xcn1, float* __restrict__ xcn2, float* __restrict__ xcn3, float* __restrict__ xij) {
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    const int rpw = 32 / lpr;          // rows gathered at once
+    const int grp = lane / lpr;        // which of them this lane works on
+    const int sub = lane - grp * lpr;  // position inside the row
+    const int64_t F = (int64_t)nvec * 4;
+    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+    for (int64_t t = warp; t < T; t += nwarps) {
+        const int64_t b = t / batch_size;
+        const int64_t i = src[t], j = dst[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs, ro = rec_off[t];
+        const ColStat* cs = colstat + b * n;
+        const WeightParams P = make_params(order, weighted, variant, fill, ip, bscal + b * 8);
+        float4 a1[VPL], a2[VPL], a3[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) a1[v] = a2[v] = a3[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t base = 0; base < d; base += 32) {
+            const int64_t p = base + lane;
+            int32_t k = 0;
+            float w1 = 0.f, w2 = 0.f, w3 = 0.f;
+            bool nz = false;
+            if (p < d) {
+                const Record rec = records[ro + p];
+                if (rec.x | rec.y) {
+                    k = ldg_i32(col + rs + p);
+                    uint32_t c1;
+                    unsigned long long s2, s3;
+                    load_colstat(cs + k, c1, s2, s3);
+                    const EntryWeights W = entry_weights(rec, c1, s2, s3, P);
+                    nz = W.in1 || W.in2 || W.in3;
+                    w1 = W.w1; w2 = W.w2; w3 = W.w3;
+                }
+            }
+            unsigned active = __ballot_sync(0xffffffffu, nz);
+            while (active) {
+                unsigned tmp = active;
+                for (int q = 0; q < grp; ++q) tmp &= tmp - 1;
+                const int sl = tmp ? (__ffs(tmp) - 1) : -1;
+                for (int q = 0; q < rpw && active; ++q) active &= active - 1;
+                const int srcl = sl < 0 ? 0 : sl;
+                const int32_t kk = __shfl_sync(0xffffffffu, k, srcl);
+                const float u1 = __shfl_sync(0xffffffffu, w1, srcl);
+                const float u2 = __shfl_sync(0xffffffffu, w2, srcl);
+                const float u3 = __shfl_sync(0xffffffffu, w3, srcl);
+                if (sl >= 0) {
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        const int c = sub + v * lpr;
+                        if (c < nvec) {
+                            const float4 xv = __ldg(x4 + (int64_t)kk * nvec + c);
+                            a1[v].x = fmaf(u1, xv.x, a1[v].x); a1[v].y = fmaf(u1, xv.y, a1[v].y);
+                            a1[v].z = fmaf(u1, xv.z, a1[v].z); a1[v].w = fmaf(u1, xv.w, a1[v].w);
+                            a2[v].x = fmaf(u2, xv.x, a2[v].x); a2[v].y = fmaf(u2, xv.y, a2[v].y);
+                            a2[v].z = fmaf(u2, xv.z, a2[v].z); a2[v].w = fmaf(u2, xv.w, a2[v].w);
+                            a3[v].x = fmaf(u3, xv.x, a3[v].x); a3[v].y = fmaf(u3, xv.y, a3[v].y);
+                            a3[v].z = fmaf(u3, xv.z, a3[v].z); a3[v].w = fmaf(u3, xv.w, a3[v].w);
+                        }
+                    }
+                }
+            }
+        }
+        // combine the row groups (fixed butterfly order)
+        for (int o = lpr; o < 32; o <<= 1) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                a1[v].x += __shfl_xor_sync(0xffffffffu, a1[v].x, o); a1[v].y += __shfl_xor_sync(0xffffffffu, a1[v].y, o);
+                a1[v].z += __shfl_xor_sync(0xffffffffu, a1[v].z, o); a1[v].w += __shfl_xor_sync(0xffffffffu, a1[v].w, o);
+                a2[v].x += __shfl_xor_sync(0xffffffffu, a2[v].x, o); a2[v].y += __shfl_xor_sync(0xffffffffu, a2[v].y, o);
+                a2[v].z += __shfl_xor_sync(0xffffffffu, a2[v].z, o); a2[v].w += __shfl_xor_sync(0xffffffffu, a2[v].w, o);
+                a3[v].x += __shfl_xor_sync(0xffffffffu, a3[v].x, o); a3[v].y += __shfl_xor_sync(0xffffffffu, a3[v].y, o);
+                a3[v].z += __shfl_xor_sync(0xffffffffu, a3[v].z, o); a3[v].w += __shfl_xor_sync(0xffffffffu, a3[v].w, o);
+            }
+        }
+        if (grp == 0) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int c = sub + v * lpr;
+                if (c < nvec) {
+                    reinterpret_cast<float4*>(xcn1 + t * F)[c] = a1[v];
+                    if (xcn2) reinterpret_cast<float4*>(xcn2 + t * F)[c] = a2[v];
+                    if (xcn3) reinterpret_cast<float4*>(xcn3 + t * F)[c] = a3[v];
+                }
+            }
+        }
+        if (xij) {
+            for (int c = lane; c < nvec; c += 32) {
+                const float4 xa = __ldg(x4 + i * nvec + c), xb = __ldg(x4 + j * nvec + c);
+                reinterpret_cast<float4*>(xij + t * F)[c] = make_float4(xa.x * xb.x, xa.y * xb.y, xa.z * xb.z, xa.w * xb.w);
+            }
+        }
+    }
+}
+
+// backward: grad_x[k,:] += w1*g1[t,:] + w2*g2[t,:] + w3*g3[t,:]; pair term by the product rule.
+__global__ void __launch_bounds__(256)
+k_cn_aggregate_bwd(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
+                   const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t T, int64_t batch_size,
+                   int order, int weighted, int variant, float fill, const float* __restrict__ ip,
+                   const int64_t* __restrict__ rec_off, const Record* __restrict__ records,
+                   const ColStat* __restrict__ colstat, const float* __restrict__ bscal,
+                   const float* __restrict__ x, int64_t F,
+                   const float* __restrict__ g1, const float* __restrict__ g2, const float* __restrict__ g3,
+                   const float* __restrict__ gij, float* __restrict__ grad_x) {
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    for (int64_t t = warp; t < T; t += nwarps) {
+        const int64_t b = t / batch_size;
+        const int64_t i = src[t], j = dst[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs, ro = rec_off[t];
+        const ColStat* cs = colstat + b * n;
+        const WeightParams P = make_params(order, weighted, variant, fill, ip, bscal + b * 8);
+        for (int64_t base = 0; base < d; base += 32) {
+            const int64_t p = base + lane;
+            int32_t k = 0;
+            float w1 = 0.f, w2 = 0.f, w3 = 0.f;
+            bool nz = false;
+            if (p < d) {
+                const Record rec = records[ro + p];
+                if (rec.x | rec.y) {
+                    k = ldg_i32(col + rs + p);
+                    uint32_t c1;
+                    unsigned long long s2, s3;
+                    load_colstat(cs + k, c1, s2, s3);
+                    const EntryWeights W = entry_weights(rec, c1, s2, s3, P);
+                    nz = W.in1 || W.in2 || W.in3;
+                    w1 = W.w1; w2 = W.w2; w3 = W.w3;
+                }
+            }
+            unsigned active = __ballot_sync(0xffffffffu, nz);
+            while (active) {
+                const int sl = __ffs(active) - 1;
+                active &= active - 1;
+                const int32_t kk = __shfl_sync(0xffffffffu, k, sl);
+                const float u1 = __shfl_sync(0xffffffffu, w1, sl);
+                const float u2 = __shfl_sync(0xffffffffu, w2, sl);
+                const float u3 = __shfl_sync(0xffffffffu, w3, sl);
+                for (int64_t c = lane; c < F; c += 32) {
+                    float g = 0.f;
+                    if (g1) g = fmaf(u1, g1[t * F + c], g);
+                    if (g2) g = fmaf(u2, g2[t * F + c], g);
+                    if (g3) g = fmaf(u3, g3[t * F + c], g);
+                    if (g != 0.f) atomicAdd(grad_x + (int64_t)kk * F + c, g);
+                }
+            }
+        }
+        if (gij) {
+            for (int64_t c = lane; c < F; c += 32) {
+                const float g = gij[t * F + c];
+                atomicAdd(grad_x + i * F + c, g * x[j * F + c]);
+                atomicAdd(grad_x + j * F + c, g * x[i * F + c]);
+            }
+        }
+    }
+}
+
+// ---- sparse extraction ---------------------------------------------------------------------
+__device__ __forceinline__ bool in_which(Record rec, int which) {
+    const bool has1 = (rec.x >> 31) != 0u;
+    const bool has2 = (rec.x & 0x7fffffffu) != 0u, has3 = rec.y != 0u;
+    switch (which) {
+        case 1: case 11: return has1;
+        case 2: return has2;
+        case 3: return has3;
+        case 12: return has1 || has2;
+        case 13: return has1 || has2 || has3;
+    }
+    return false;
+}
+
+template <bool FILL>
+__global__ void k_cn_extract(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
+                             const int64_t* __restrict__ src, int64_t T, int64_t batch_size, int which, int order,
+                             int weighted, int variant, float fill, const float* __restrict__ ip,
+                             const int64_t* __restrict__ rec_off, const Record* __restrict__ records,
+                             const ColStat* __restrict__ colstat, const float* __restrict__ bscal,
+                             int64_t* __restrict__ out_counts, const int64_t* __restrict__ out_rowptr,
+                             int64_t* __restrict__ out_col, float* __restrict__ out_val) {
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    for (int64_t t = warp; t < T; t += nwarps) {
+        const int64_t b = t / batch_size;
+        const int64_t i = src[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs, ro = rec_off[t];
+        WeightParams P;
+        if (FILL && which > 10) P = make_params(order, weighted, variant, fill, ip, bscal + b * 8);
+        int64_t count = 0;
+        const int64_t obase = FILL ? out_rowptr[t] : 0;
+        for (int64_t base = 0; base < d; base += 32) {
+            const int64_t p = base + lane;
+            Record rec = make_uint2(0u, 0u);
+            if (p < d) rec = records[ro + p];
+            const bool hit = in_which(rec, which);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (FILL && hit) {
+                const int64_t o = obase + count + __popc(m & ((1u << lane) - 1));
+                const int32_t k = ldg_i32(col + rs + p);
+                out_col[o] = k;
+                if (out_val) {
+                    float v;
+                    if (which == 1) v = 1.0f;
+                    else if (which == 2) v = weighted ? (float)(rec.x & 0x7fffffffu) : 1.0f;
+                    else if (which == 3) v = weighted ? (float)rec.y : 1.0f;
+                    else {
+                        uint32_t c1;
+                        unsigned long long s2, s3;
+                        load_colstat(colstat + b * n + k, c1, s2, s3);
+                        const EntryWeights W = entry_weights(rec, c1, s2, s3, P);
+                        v = which == 11 ? W.w1 : (which == 12 ? W.w2 : W.w3);
+                    }
+                    out_val[o] = v;
+                }
+            }
+            count += __popc(m);
+        }
+        if (!FILL && lane == 0) out_counts[t] = count;
+    }
+}
+
+// ---- release -------------------------------------------------------------------------------
+__global__ void k_cn_release(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
+                             const int64_t* __restrict__ src, int64_t T, int64_t batch_size,
+                             const int64_t* __restrict__ rec_off, const Record* __restrict__ records,
+                             ColStat* __restrict__ colstat) {
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    for (int64_t t = warp; t < T; t += nwarps) {
+        const int64_t b = t / batch_size;
+        const int64_t i = src[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs, ro = rec_off[t];
+        for (int64_t p = lane; p < d; p += 32) {
+            const Record rec = records[ro + p];
+            if (rec.x | rec.y) {
+                uint4* c = reinterpret_cast<uint4*>(colstat + b * n + ldg_i32(col + rs + p));
+                c[0] = make_uint4(0u, 0u, 0u, 0u);
+                c[1] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+    }
+}
+
+static int grid_for_warps(int64_t items) {
+    int64_t want = (items + 7) / 8;
+    int64_t cap = (int64_t)sm_count() * 8;
+    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+}  // namespace ocn
+
+using namespace ocn;
+
+#define PLAN_PTRS()                                                        \
+    PlanLayout L = plan_layout(num_edges);                                 \
+    const char* pbase = (const char*)plan_scratch;                         \
+    const int64_t* rec_off = (const int64_t*)(pbase + L.rec_off);          \
+    float* partial = (float*)(const_cast<char*>(pbase) + L.partial);       \
+    (void)partial; (void)rec_off;
+
+extern "C" {
+
+int ocn_cn_stats(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, int64_t num_edges,
+                 int64_t batch_size, int order, int weighted, int variant, float fill, const float* ip, int stage,
+                 const void* plan_scratch, const void* records, const void* colstat, float* batch_scalars,
+                 void* stream) {
+    OCN_CHECK_ARG(rowptr && col && src && plan_scratch && colstat && batch_scalars, "ocn_cn_stats: null pointer");
+    OCN_CHECK_ARG(num_edges > 0 && batch_size > 0 && n > 0, "ocn_cn_stats: sizes must be positive");
+    OCN_CHECK_ARG(stage == 0 || stage == 1, "ocn_cn_stats: stage must be 0 or 1");
+    OCN_CHECK_ARG(variant == 5 || variant == 7, "ocn_cn_stats: variant must be 5 or 7");
+    cudaStream_t st = (cudaStream_t)stream;
+    PLAN_PTRS();
+    const int64_t nb = (num_edges + batch_size - 1) / batch_size;
+    k_stats_init<<<(int)((nb + 255) / 256), 256, 0, st>>>(batch_scalars, nb, stage);
+    OCN_LAUNCH_CHECK();
+    k_stats<<<grid_for_warps(num_edges), 256, 0, st>>>(rowptr, col, n, src, num_edges, batch_size, order, weighted,
+                                                       variant, fill, ip, stage, rec_off, (const Record*)records,
+                                                       (const ColStat*)colstat, batch_scalars, partial);
+    OCN_LAUNCH_CHECK();
+    k_stats_finalize<<<(int)nb, 256, 0, st>>>(num_edges, batch_size, stage, partial, batch_scalars);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+int ocn_cn_aggregate(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst,
+                     int64_t num_edges, int64_t batch_size, int order, int weighted, int variant, float fill,
+                     const float* ip, const void* plan_scratch, const void* records, const void* colstat,
+                     const float* batch_scalars, const float* x, int64_t feat, float* xcn1, float* xcn2, float* xcn3,
+                     float* xij, void* stream) {
+    OCN_CHECK_ARG(rowptr && col && src && dst && plan_scratch && colstat && batch_scalars && x && xcn1,
+                  "ocn_cn_aggregate: null pointer");
+    OCN_CHECK_ARG(num_edges > 0 && batch_size > 0 && n > 0, "ocn_cn_aggregate: sizes must be positive");
+    OCN_CHECK_ARG(variant == 5 || variant == 7, "ocn_cn_aggregate: variant must be 5 (cn5/cn6) or 7 (cn7)");
+    OCN_CHECK_ARG(order >= 1 && order <= 3, "ocn_cn_aggregate: order must be 1..3");
+    OCN_CHECK_ARG(feat > 0 && feat % 4 == 0 && feat <= 1024,
+                  "ocn_cn_aggregate: feature width must be a multiple of 4 and <= 1024 (got %lld)", (long long)feat);
+    cudaStream_t st = (cudaStream_t)stream;
+    PLAN_PTRS();
+    const int nvec = (int)(feat / 4);
+    int lpr = 1;
+    while (lpr < nvec && lpr < 32) lpr <<= 1;
+    const int vpl = (nvec + 31) / 32;
+    const int grid = grid_for_warps(num_edges);
+#define AGG(V)                                                                                                       \
+    k_cn_aggregate<V><<<grid, 256, 0, st>>>(rowptr, col, n, src, dst, num_edges, batch_size, order, weighted, variant, \
+                                            fill, ip, rec_off, (const Record*)records, (const ColStat*)colstat,      \
+                                            batch_scalars, x, nvec, lpr, xcn1, xcn2, xcn3, xij)
+    if (vpl <= 1) AGG(1);
+    else if (vpl <= 2) AGG(2);
+    else if (vpl <= 4) AGG(4);
+    else AGG(8);
+#undef AGG
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+int ocn_cn_aggregate_bwd(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src,
+                         const int64_t* dst, int64_t num_edges, int64_t batch_size, int order, int weighted,
+                         int variant, float fill, const float* ip, const void* plan_scratch, const void* records,
+                         const void* colstat, const float* batch_scalars, const float* x, int64_t feat,
+                         const float* g_xcn1, const float* g_xcn2, const float* g_xcn3, const float* g_xij,
+                         float* grad_x, void* stream) {
+    OCN_CHECK_ARG(rowptr && col && src && dst && plan_scratch && colstat && batch_scalars && grad_x,
+                  "ocn_cn_aggregate_bwd: null pointer");
+    OCN_CHECK_ARG(num_edges > 0 && batch_size > 0 && n > 0 && feat > 0, "ocn_cn_aggregate_bwd: sizes must be positive");
+    OCN_CHECK_ARG(g_xij == nullptr || x != nullptr, "ocn_cn_aggregate_bwd: x is needed for the pair term");
+    cudaStream_t st = (cudaStream_t)stream;
+    PLAN_PTRS();
+    k_cn_aggregate_bwd<<<grid_for_warps(num_edges), 256, 0, st>>>(
+        rowptr, col, n, src, dst, num_edges, batch_size, order, weighted, variant, fill, ip, rec_off,
+        (const Record*)records, (const ColStat*)colstat, batch_scalars, x, feat, g_xcn1, g_xcn2, g_xcn3, g_xij, grad_x);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+int ocn_cn_extract_count(const int64_t* rowptr, int64_t n, const int64_t* src, int64_t num_edges, int which,
+                         int weighted, const void* plan_scratch, const void* records, int64_t* out_counts,
+                         void* stream) {
+    OCN_CHECK_ARG(rowptr && src && plan_scratch && records && out_counts, "ocn_cn_extract_count: null pointer");
+    OCN_CHECK_ARG(which == 1 || which == 2 || which == 3 || which == 11 || which == 12 || which == 13,
+                  "ocn_cn_extract_count: which must be 1,2,3,11,12,13");
+    OCN_CHECK_ARG(num_edges > 0, "ocn_cn_extract_count: num_edges must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    PLAN_PTRS();
+    k_cn_extract<false><<<grid_for_warps(num_edges), 256, 0, st>>>(
+        rowptr, nullptr, n, src, num_edges, 1, which, 3, weighted, 5, 0.f, nullptr, rec_off, (const Record*)records,
+        nullptr, nullptr, out_counts, nullptr, nullptr, nullptr);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+int ocn_cn_extract_fill(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, int64_t num_edges,
+                        int64_t batch_size, int which, int weighted, int variant, float fill, const float* ip,
+                        const void* plan_scratch, const void* records, const void* colstat,
+                        const float* batch_scalars, const int64_t* out_rowptr, int64_t* out_col, float* out_val,
+                        void* stream) {
+    OCN_CHECK_ARG(rowptr && col && src && plan_scratch && records && out_rowptr && out_col,
+                  "ocn_cn_extract_fill: null pointer");
+    OCN_CHECK_ARG(which == 1 || which == 2 || which == 3 || which == 11 || which == 12 || which == 13,
+                  "ocn_cn_extract_fill: which must be 1,2,3,11,12,13");
+    OCN_CHECK_ARG(which < 10 || (colstat && batch_scalars) || !out_val,
+                  "ocn_cn_extract_fill: normalised values need colstat and batch_scalars");
+    OCN_CHECK_ARG(num_edges > 0 && batch_size > 0, "ocn_cn_extract_fill: sizes must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    PLAN_PTRS();
+    const int order = which > 10 ? which - 10 : which;
+    k_cn_extract<true><<<grid_for_warps(num_edges), 256, 0, st>>>(
+        rowptr, col, n, src, num_edges, batch_size, which, order, weighted, variant, fill, ip, rec_off,
+        (const Record*)records, (const ColStat*)colstat, batch_scalars, nullptr, out_rowptr, out_col, out_val);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+int ocn_cn_release(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, int64_t num_edges,
+                   int64_t batch_size, const void* plan_scratch, const void* records, void* colstat, void* stream) {
+    OCN_CHECK_ARG(rowptr && col && src && plan_scratch && records && colstat, "ocn_cn_release: null pointer");
+    OCN_CHECK_ARG(num_edges > 0 && batch_size > 0, "ocn_cn_release: sizes must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    PLAN_PTRS();
+    k_cn_release<<<grid_for_warps(num_edges), 256, 0, st>>>(rowptr, col, n, src, num_edges, batch_size, rec_off,
+                                                             (const Record*)records, (ColStat*)colstat);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,139 @@
+// ocn_cn_plan: device-side schedule for a stream of target links.
+//
+// The stream is cut into batches of batch_size links (utils.py:8-36 PermIterator).  Inside a
+// batch, maximal runs of consecutive links with the same source node share everything that
+// depends on N(src) -- in the citation2 evaluation stream every source is repeated against
+// 1000 destinations (NeighborOverlapCitation2.py:248-252).  A work unit of ocn_cn_build is
+// (run, chunk of kPChunk positions of N(src), sub-list of kEdgeSub links of the run).
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace ocn {
+
+static size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+PlanLayout plan_layout(int64_t T) {
+    PlanLayout L;
+    size_t off = 0;
+    L.rec_off = off;       off += align16(sizeof(int64_t) * (T + 1));
+    L.run_id = off;        off += align16(sizeof(int32_t) * (T + 1));
+    L.run_start = off;     off += align16(sizeof(int32_t) * (T + 2));
+    L.run_unit_off = off;  off += align16(sizeof(int64_t) * (T + 2));
+    L.partial = off;       off += align16(sizeof(float) * 3 * (T + 1));
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, b1, (int64_t*)nullptr, (int64_t*)nullptr, (int)(T + 2));
+    cub::DeviceScan::InclusiveSum(nullptr, b2, (int32_t*)nullptr, (int32_t*)nullptr, (int)(T + 2));
+    L.cub_temp = off;
+    L.cub_temp_bytes = align16((b1 > b2 ? b1 : b2) + 256);
+    off += L.cub_temp_bytes;
+    L.total = off;
+    return L;
+}
+
+__global__ void k_plan_edges(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ src, int64_t T,
+                             int64_t batch_size, int64_t* __restrict__ rec_off, int32_t* __restrict__ flag) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > T) return;
+    if (t == T) {
+        rec_off[t] = 0;
+        flag[t] = 0;
+        return;
+    }
+    int64_t i = src[t];
+    rec_off[t] = rowptr[i + 1] - rowptr[i];
+    flag[t] = (t % batch_size == 0 || src[t - 1] != i) ? 1 : 0;
+}
+
+// after the inclusive scan flag[t] = run index + 1
+__global__ void k_plan_runs(const int64_t* __restrict__ src, int64_t T, int64_t batch_size,
+                            const int32_t* __restrict__ run_incl, int32_t* __restrict__ run_start,
+                            int64_t* __restrict__ plan) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    bool first = (t % batch_size == 0) || src[t - 1] != src[t];
+    int32_t r = run_incl[t] - 1;
+    if (first) run_start[r] = (int32_t)t;
+    if (t == T - 1) {
+        run_start[r + 1] = (int32_t)T;
+        plan[OCN_PLAN_NUM_RUNS] = r + 1;
+    }
+}
+
+__global__ void k_plan_units(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ src, int64_t T,
+                             const int32_t* __restrict__ run_start, const int64_t* __restrict__ plan,
+                             int64_t* __restrict__ run_units) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > T + 1) return;
+    int64_t n_runs = plan[OCN_PLAN_NUM_RUNS];
+    int64_t u = 0;
+    if (r < n_runs) {
+        int64_t t0 = run_start[r], len = run_start[r + 1] - t0;
+        int64_t i = src[t0];
+        int64_t d = rowptr[i + 1] - rowptr[i];
+        u = ((d + kPChunk - 1) / kPChunk) * ((len + kEdgeSub - 1) / kEdgeSub);
+    }
+    run_units[r] = u;
+}
+
+__global__ void k_plan_finish(int64_t T, int64_t batch_size, const int64_t* __restrict__ rec_off,
+                              const int64_t* __restrict__ run_unit_off, int64_t* __restrict__ plan) {
+    plan[OCN_PLAN_NUM_RECORDS] = rec_off[T];
+    plan[OCN_PLAN_NUM_UNITS] = run_unit_off[plan[OCN_PLAN_NUM_RUNS]];
+    plan[OCN_PLAN_NUM_BATCHES] = (T + batch_size - 1) / batch_size;
+    plan[4] = 0;  // dynamic unit counter of ocn_cn_build
+    plan[5] = 0;
+    plan[6] = 0;
+    plan[7] = 0;
+}
+
+}  // namespace ocn
+
+using namespace ocn;
+
+extern "C" {
+
+size_t ocn_cn_plan_bytes(int64_t num_edges) {
+    if (num_edges < 0) return 0;
+    return plan_layout(num_edges).total;
+}
+size_t ocn_cn_colstat_bytes(int64_t n) { return n < 0 ? 0 : sizeof(ColStat) * (size_t)n; }
+size_t ocn_cn_record_bytes(void) { return sizeof(Record); }
+
+int ocn_cn_plan(const int64_t* rowptr, int64_t n, const int64_t* src, const int64_t* dst, int64_t num_edges,
+                int64_t batch_size, void* plan_scratch, size_t plan_scratch_bytes, int64_t* out_plan, void* stream) {
+    (void)dst;
+    OCN_CHECK_ARG(rowptr && out_plan && plan_scratch, "ocn_cn_plan: null pointer");
+    OCN_CHECK_ARG(n > 0 && num_edges > 0 && batch_size > 0, "ocn_cn_plan: n, num_edges and batch_size must be positive");
+    OCN_CHECK_ARG(num_edges < (int64_t(1) << 30), "ocn_cn_plan: at most 2^30 links per call");
+    OCN_CHECK_ARG(src, "ocn_cn_plan: null edge pointer");
+    PlanLayout L = plan_layout(num_edges);
+    if (plan_scratch_bytes < L.total)
+        return fail(OCN_ENOSPACE, "ocn_cn_plan: plan scratch %zu < %zu bytes", plan_scratch_bytes, L.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)plan_scratch;
+    int64_t* rec_off = (int64_t*)(base + L.rec_off);
+    int32_t* run_id = (int32_t*)(base + L.run_id);
+    int32_t* run_start = (int32_t*)(base + L.run_start);
+    int64_t* run_unit_off = (int64_t*)(base + L.run_unit_off);
+    void* tmp = base + L.cub_temp;
+    size_t tmp_bytes = L.cub_temp_bytes;
+    int64_t T = num_edges;
+    int threads = 256;
+    int blocks = (int)((T + 1 + threads - 1) / threads);
+    k_plan_edges<<<blocks, threads, 0, st>>>(rowptr, src, T, batch_size, rec_off, run_id);
+    OCN_LAUNCH_CHECK();
+    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, rec_off, rec_off, (int)(T + 1), st));
+    OCN_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, run_id, run_id, (int)(T + 1), st));
+    k_plan_runs<<<blocks, threads, 0, st>>>(src, T, batch_size, run_id, run_start, out_plan);
+    OCN_LAUNCH_CHECK();
+    int blocks2 = (int)((T + 2 + threads - 1) / threads);
+    k_plan_units<<<blocks2, threads, 0, st>>>(rowptr, src, T, run_start, out_plan, run_unit_off);
+    OCN_LAUNCH_CHECK();
+    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, run_unit_off, run_unit_off, (int)(T + 2), st));
+    k_plan_finish<<<1, 1, 0, st>>>(T, batch_size, rec_off, run_unit_off, out_plan);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// Shared device/host helpers of libocn_b200 (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/ocn_b200.h"
+
+namespace ocn {
+
+// ---- error plumbing (no exceptions cross the C ABI) --------------------------------------
+std::string& last_error();
+int fail(int code, const char* fmt, ...);
+
+#define OCN_CHECK_ARG(cond, ...)                         \
+    do {                                                 \
+        if (!(cond)) return ::ocn::fail(OCN_EINVAL, __VA_ARGS__); \
+    } while (0)
+
+#define OCN_CUDA(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return ::ocn::fail(OCN_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                               __FILE__, __LINE__);                                         \
+    } while (0)
+
+#define OCN_LAUNCH_CHECK() OCN_CUDA(cudaGetLastError())
+
+int sm_count();
+
+// ---- constants shared by the plan and the build kernel -----------------------------------
+constexpr int kPChunk = 32;   // positions of N(src) handled by one work unit (one mask word)
+constexpr int kEdgeSub = 64;  // target links of a run handled by one work unit
+
+// one record per (target link, position p in N(src)):
+//   x = C2 | (C1 << 31)   (C1 in {0,1}; C2 = #2-walks dst->..->N(src)[p], < 2^31)
+//   y = C3                (#3-walks)
+using Record = uint2;
+
+// per-batch, per-node column statistics (32 B = one L2 sector)
+struct __align__(32) ColStat {
+    uint32_t c1;   // number of links of the batch that have this node in CN1
+    uint32_t pad0;
+    unsigned long long s2;  // sum over links of C2 (weighted) or [C2>0]
+    unsigned long long s3;  // same for C3
+    unsigned long long pad1;
+};
+static_assert(sizeof(ColStat) == 32, "ColStat must be one sector");
+
+// plan scratch layout (offsets in bytes, all 16-B aligned)
+struct PlanLayout {
+    size_t rec_off;        // int64[T+1]
+    size_t run_id;         // int32[T+1]
+    size_t run_start;      // int32[T+2]
+    size_t run_unit_off;   // int64[T+2]
+    size_t partial;        // float[3*T]
+    size_t cub_temp;       // bytes
+    size_t cub_temp_bytes;
+    size_t total;
+};
+PlanLayout plan_layout(int64_t num_edges);
+
+// ---- small device helpers ------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ int32_t ldg_i32(const int32_t* p) { return __ldg(p); }
+__device__ __forceinline__ int64_t ldg_i64(const int64_t* p) { return __ldg(reinterpret_cast<const long long*>(p)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// lower_bound on an ascending int32 row in global memory; returns true if key present
+__device__ __forceinline__ bool row_contains(const int32_t* __restrict__ row, int64_t len, int32_t key) {
+    int64_t lo = 0, hi = len;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        int32_t v = __ldg(row + mid);
+        if (v < key) lo = mid + 1; else hi = mid;
+    }
+    return lo < len && __ldg(row + lo) == key;
+}
+
+}  // namespace ocn

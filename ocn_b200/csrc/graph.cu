@@ -1,0 +1,153 @@
+// ABI basics, graph validation and the generic two-matrix row intersection.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace ocn {
+
+std::string& last_error() {
+    static thread_local std::string s;
+    return s;
+}
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error() = buf;
+    return code;
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+        cached = p.multiProcessorCount;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+// ---- validation ---------------------------------------------------------------------------
+__global__ void k_validate(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
+                           int64_t nnz, int32_t* __restrict__ flags) {
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int lane = lane_id();
+    int bad = 0;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        int64_t s = rowptr[r], e = rowptr[r + 1];
+        if (s > e || s < 0 || e > nnz) { bad |= 4; continue; }
+        for (int64_t o = s + lane; o < e; o += 32) {
+            int32_t c = col[o];
+            if (c < 0 || c >= n) { bad |= 1; continue; }
+            if (o > s && col[o - 1] >= c) bad |= 2;
+            // symmetry: r must be in row c
+            int64_t cs = rowptr[c], ce = rowptr[c + 1];
+            if (cs <= ce && cs >= 0 && ce <= nnz) {
+                if (!row_contains(col + cs, ce - cs, (int32_t)r)) bad |= 8;
+            }
+        }
+    }
+    if (warp == 0 && lane == 0 && (rowptr[0] != 0 || rowptr[n] != nnz)) bad |= 4;
+    if (bad) atomicOr(flags, bad);
+}
+
+// ---- generic rows intersect ---------------------------------------------------------------
+// One warp per target link.  The shorter row is walked 32 columns at a time, each lane binary
+// searches its column in the longer row; matches are emitted in ascending column order with a
+// ballot (both rows are ascending, so walking either one keeps the output ascending).
+template <bool FILL>
+__global__ void k_rows_intersect(const int64_t* __restrict__ rowptr1, const int32_t* __restrict__ col1,
+                                 const int64_t* __restrict__ rowptr2, const int32_t* __restrict__ col2,
+                                 const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                 int64_t num_edges, int64_t* __restrict__ out_counts,
+                                 const int64_t* __restrict__ out_rowptr, int64_t* __restrict__ out_col) {
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int lane = lane_id();
+    for (int64_t t = warp; t < num_edges; t += nwarps) {
+        int64_t i = src[t], j = dst[t];
+        int64_t s1 = rowptr1[i], l1 = rowptr1[i + 1] - s1;
+        int64_t s2 = rowptr2[j], l2 = rowptr2[j + 1] - s2;
+        const int32_t* a = col1 + s1;
+        const int32_t* b = col2 + s2;
+        if (l1 > l2) {
+            const int32_t* tp = a; a = b; b = tp;
+            int64_t tl = l1; l1 = l2; l2 = tl;
+        }
+        int64_t count = 0;
+        int64_t obase = FILL ? out_rowptr[t] : 0;
+        for (int64_t base = 0; base < l1; base += 32) {
+            int64_t o = base + lane;
+            bool hit = false;
+            int32_t c = 0;
+            if (o < l1) {
+                c = __ldg(a + o);
+                hit = row_contains(b, l2, c);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (FILL && hit) out_col[obase + count + __popc(m & ((1u << lane) - 1))] = c;
+            count += __popc(m);
+        }
+        if (!FILL && lane == 0) out_counts[t] = count;
+    }
+}
+
+}  // namespace ocn
+
+using namespace ocn;
+
+extern "C" {
+
+int ocn_abi_version(void) { return OCN_ABI_VERSION; }
+const char* ocn_last_error(void) { return last_error().c_str(); }
+int ocn_device_sm_count(void) { return sm_count(); }
+
+int ocn_graph_validate(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t nnz, int32_t* out_flags,
+                       void* stream) {
+    OCN_CHECK_ARG(rowptr && out_flags && n >= 0 && nnz >= 0, "ocn_graph_validate: null pointer or negative size");
+    OCN_CHECK_ARG(col || nnz == 0, "ocn_graph_validate: col is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    OCN_CUDA(cudaMemsetAsync(out_flags, 0, sizeof(int32_t), st));
+    if (n == 0) return OCN_OK;
+    int blocks = sm_count() * 8;
+    k_validate<<<blocks, 256, 0, st>>>(rowptr, col, n, nnz, out_flags);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+int ocn_rows_intersect_count(const int64_t* rowptr1, const int32_t* col1, const int64_t* rowptr2,
+                             const int32_t* col2, const int64_t* src, const int64_t* dst, int64_t num_edges,
+                             int64_t* out_counts, void* stream) {
+    OCN_CHECK_ARG(rowptr1 && rowptr2 && num_edges >= 0, "ocn_rows_intersect_count: bad arguments");
+    if (num_edges == 0) return OCN_OK;
+    OCN_CHECK_ARG(src && dst && out_counts, "ocn_rows_intersect_count: null edge/out pointer");
+    int64_t want = (num_edges + 7) / 8;
+    int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
+    k_rows_intersect<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr1, col1, rowptr2, col2, src, dst,
+                                                                       num_edges, out_counts, nullptr, nullptr);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+int ocn_rows_intersect_fill(const int64_t* rowptr1, const int32_t* col1, const int64_t* rowptr2,
+                            const int32_t* col2, const int64_t* src, const int64_t* dst, int64_t num_edges,
+                            const int64_t* out_rowptr, int64_t* out_col, void* stream) {
+    OCN_CHECK_ARG(rowptr1 && rowptr2 && num_edges >= 0, "ocn_rows_intersect_fill: bad arguments");
+    if (num_edges == 0) return OCN_OK;
+    OCN_CHECK_ARG(src && dst && out_rowptr, "ocn_rows_intersect_fill: null edge/out pointer");
+    int64_t want = (num_edges + 7) / 8;
+    int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
+    k_rows_intersect<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr1, col1, rowptr2, col2, src, dst,
+                                                                      num_edges, nullptr, out_rowptr, out_col);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+}  // extern "C"

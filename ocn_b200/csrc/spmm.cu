@@ -1,0 +1,239 @@
+// CSR SpMM family: spmm_add / spmm_mean / spmm_max (torch_sparse.matmul, model.py:6,45-53,2426-2427),
+// its transpose-by-scatter backward, and the GCN-normalised aggregation of PureConv / PureConv3 /
+// GCNConv (model.py:42-55, 128-142, 58-71).
+//
+// One warp per output row; a feature row is covered by LPR lanes with VPL float4 each and
+// 32/LPR neighbour rows are gathered at once (128-bit coalesced loads), partial sums are
+// combined with a fixed butterfly, so results are run-to-run deterministic.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace ocn {
+
+enum { kSum = 0, kMean = 1, kMax = 2, kGcnSelf = 3, kGcnNoSelf = 4 };
+
+template <int VPL>
+__global__ void __launch_bounds__(256)
+k_spmm(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+       const float* __restrict__ norm, int64_t num_rows, const float* __restrict__ x, int nvec, int lpr, int mode,
+       float* __restrict__ out) {
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    const int rpw = 32 / lpr, grp = lane / lpr, sub = lane - grp * lpr;
+    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+    const bool is_max = mode == kMax;
+    for (int64_t r = warp; r < num_rows; r += nwarps) {
+        const int64_t s = rowptr[r], e = rowptr[r + 1];
+        const float nr = (mode >= kGcnSelf) ? norm[r] : 1.0f;
+        float4 acc[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            acc[v] = is_max ? make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t base = s; base < e; base += 32) {
+            const int64_t o = base + lane;
+            int32_t c = 0;
+            float w = 0.f;
+            if (o < e) {
+                c = ldg_i32(col + o);
+                w = val ? __ldg(val + o) : 1.0f;
+            }
+            const int cnt = (int)((e - base) < 32 ? (e - base) : 32);
+            for (int q = 0; q < cnt; q += rpw) {
+                const int sl = q + grp;
+                const int srcl = sl < cnt ? sl : 0;
+                const int32_t cc = __shfl_sync(0xffffffffu, c, srcl);
+                float ww = __shfl_sync(0xffffffffu, w, srcl);
+                if (sl < cnt) {
+                    float pre = 1.0f;
+                    if (mode == kGcnSelf) pre = norm[cc];
+                    else if (mode == kGcnNoSelf) ww = ww * (nr * norm[cc]);
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        const int k = sub + v * lpr;
+                        if (k < nvec) {
+                            float4 xv = __ldg(x4 + (int64_t)cc * nvec + k);
+                            if (mode == kGcnSelf) { xv.x *= pre; xv.y *= pre; xv.z *= pre; xv.w *= pre; }
+                            if (is_max) {
+                                acc[v].x = fmaxf(acc[v].x, ww * xv.x); acc[v].y = fmaxf(acc[v].y, ww * xv.y);
+                                acc[v].z = fmaxf(acc[v].z, ww * xv.z); acc[v].w = fmaxf(acc[v].w, ww * xv.w);
+                            } else {
+                                acc[v].x = fmaf(ww, xv.x, acc[v].x); acc[v].y = fmaf(ww, xv.y, acc[v].y);
+                                acc[v].z = fmaf(ww, xv.z, acc[v].z); acc[v].w = fmaf(ww, xv.w, acc[v].w);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        for (int o = lpr; o < 32; o <<= 1) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const float ox = __shfl_xor_sync(0xffffffffu, acc[v].x, o), oy = __shfl_xor_sync(0xffffffffu, acc[v].y, o);
+                const float oz = __shfl_xor_sync(0xffffffffu, acc[v].z, o), ow = __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+                if (is_max) {
+                    acc[v].x = fmaxf(acc[v].x, ox); acc[v].y = fmaxf(acc[v].y, oy);
+                    acc[v].z = fmaxf(acc[v].z, oz); acc[v].w = fmaxf(acc[v].w, ow);
+                } else {
+                    acc[v].x += ox; acc[v].y += oy; acc[v].z += oz; acc[v].w += ow;
+                }
+            }
+        }
+        if (grp == 0) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int k = sub + v * lpr;
+                if (k < nvec) {
+                    float4 a = acc[v];
+                    if (is_max && e == s) a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (mode == kMean) {
+                        const float inv = 1.0f / (float)((e - s) > 0 ? (e - s) : 1);
+                        a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+                    } else if (mode == kGcnSelf) {
+                        float4 xs = __ldg(x4 + r * nvec + k);
+                        a.x = nr * (a.x + nr * xs.x); a.y = nr * (a.y + nr * xs.y);
+                        a.z = nr * (a.z + nr * xs.z); a.w = nr * (a.w + nr * xs.w);
+                    }
+                    reinterpret_cast<float4*>(out)[r * nvec + k] = a;
+                }
+            }
+        }
+    }
+}
+
+// scalar fallback for feature widths that are not a multiple of 4
+__global__ void k_spmm_scalar(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                              const float* __restrict__ val, const float* __restrict__ norm, int64_t num_rows,
+                              const float* __restrict__ x, int64_t F, int mode, float* __restrict__ out) {
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    for (int64_t r = warp; r < num_rows; r += nwarps) {
+        const int64_t s = rowptr[r], e = rowptr[r + 1];
+        const float nr = (mode >= kGcnSelf) ? norm[r] : 1.0f;
+        for (int64_t f = lane; f < F; f += 32) {
+            float acc = mode == kMax ? -FLT_MAX : 0.f;
+            for (int64_t o = s; o < e; ++o) {
+                const int32_t c = col[o];
+                float w = val ? val[o] : 1.0f;
+                float xv = x[(int64_t)c * F + f];
+                if (mode == kGcnSelf) xv *= norm[c];
+                else if (mode == kGcnNoSelf) w = w * (nr * norm[c]);
+                acc = mode == kMax ? fmaxf(acc, w * xv) : fmaf(w, xv, acc);
+            }
+            if (mode == kMax && e == s) acc = 0.f;
+            if (mode == kMean) acc *= 1.0f / (float)((e - s) > 0 ? (e - s) : 1);
+            if (mode == kGcnSelf) acc = nr * (acc + nr * x[r * F + f]);
+            out[r * F + f] = acc;
+        }
+    }
+}
+
+__global__ void k_spmm_bwd(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                           const float* __restrict__ val, int64_t num_rows, const float* __restrict__ g, int64_t F,
+                           int mode, float* __restrict__ grad_x) {
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    for (int64_t r = warp; r < num_rows; r += nwarps) {
+        const int64_t s = rowptr[r], e = rowptr[r + 1];
+        const float rowscale = mode == kMean ? 1.0f / (float)((e - s) > 0 ? (e - s) : 1) : 1.0f;
+        for (int64_t o = s; o < e; ++o) {
+            const int32_t c = ldg_i32(col + o);
+            const float w = (val ? __ldg(val + o) : 1.0f) * rowscale;
+            for (int64_t f = lane; f < F; f += 32) atomicAdd(grad_x + (int64_t)c * F + f, w * g[r * F + f]);
+        }
+    }
+}
+
+__global__ void k_gcn_norm(const int64_t* __restrict__ rowptr, const float* __restrict__ ew, int64_t n,
+                           float* __restrict__ out) {
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const int64_t s = rowptr[r], e = rowptr[r + 1];
+        float sum;
+        if (ew == nullptr) {
+            sum = (float)(e - s);
+        } else {
+            float a = 0.f;
+            for (int64_t o = s + lane; o < e; o += 32) a += ew[o];
+            sum = warp_sum(a);
+        }
+        if (lane == 0) out[r] = rsqrtf(1.0f + sum);
+    }
+}
+
+static int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* val, const float* norm,
+                       int64_t num_rows, const float* x, int64_t feat, int mode, float* out, cudaStream_t st) {
+    int64_t want = (num_rows + 7) / 8;
+    int64_t cap = (int64_t)sm_count() * 16;
+    const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    if (feat % 4 != 0 || feat > 1024) {
+        k_spmm_scalar<<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, feat, mode, out);
+    } else {
+        const int nvec = (int)(feat / 4);
+        int lpr = 1;
+        while (lpr < nvec && lpr < 32) lpr <<= 1;
+        const int vpl = (nvec + 31) / 32;
+        if (vpl <= 1) k_spmm<1><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, nvec, lpr, mode, out);
+        else if (vpl <= 2) k_spmm<2><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, nvec, lpr, mode, out);
+        else if (vpl <= 4) k_spmm<4><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, nvec, lpr, mode, out);
+        else k_spmm<8><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, nvec, lpr, mode, out);
+    }
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+}  // namespace ocn
+
+using namespace ocn;
+
+extern "C" {
+
+int ocn_spmm_csr(const int64_t* rowptr, const int32_t* col, const float* val, int64_t num_rows, const float* x,
+                 int64_t feat, int reduce, float* out, void* stream) {
+    OCN_CHECK_ARG(rowptr && x && out, "ocn_spmm_csr: null pointer");
+    OCN_CHECK_ARG(num_rows >= 0 && feat > 0, "ocn_spmm_csr: bad sizes");
+    OCN_CHECK_ARG(reduce >= 0 && reduce <= 2, "ocn_spmm_csr: reduce must be 0 (sum), 1 (mean) or 2 (max)");
+    if (num_rows == 0) return OCN_OK;
+    return launch_spmm(rowptr, col, val, nullptr, num_rows, x, feat, reduce, out, (cudaStream_t)stream);
+}
+
+int ocn_spmm_csr_bwd(const int64_t* rowptr, const int32_t* col, const float* val, int64_t num_rows,
+                     const float* grad_out, int64_t feat, int reduce, float* grad_x, void* stream) {
+    OCN_CHECK_ARG(rowptr && grad_out && grad_x, "ocn_spmm_csr_bwd: null pointer");
+    OCN_CHECK_ARG(num_rows >= 0 && feat > 0, "ocn_spmm_csr_bwd: bad sizes");
+    OCN_CHECK_ARG(reduce == 0 || reduce == 1, "ocn_spmm_csr_bwd: reduce must be 0 (sum) or 1 (mean)");
+    if (num_rows == 0) return OCN_OK;
+    int64_t want = (num_rows + 7) / 8;
+    int64_t cap = (int64_t)sm_count() * 16;
+    const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    k_spmm_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, col, val, num_rows, grad_out, feat, reduce, grad_x);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+int ocn_gcn_norm(const int64_t* rowptr, const float* edge_w, int64_t n, float* out_norm, void* stream) {
+    OCN_CHECK_ARG(rowptr && out_norm && n >= 0, "ocn_gcn_norm: bad arguments");
+    if (n == 0) return OCN_OK;
+    int64_t want = (n + 7) / 8;
+    int64_t cap = (int64_t)sm_count() * 16;
+    const int grid = (int)(want < cap ? want : cap);
+    k_gcn_norm<<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, edge_w, n, out_norm);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+int ocn_gcn_spmm(const int64_t* rowptr, const int32_t* col, const float* edge_w, int64_t n, const float* norm,
+                 int mode, const float* x, int64_t feat, float* out, void* stream) {
+    OCN_CHECK_ARG(rowptr && norm && x && out, "ocn_gcn_spmm: null pointer");
+    OCN_CHECK_ARG(mode == kGcnSelf || mode == kGcnNoSelf, "ocn_gcn_spmm: mode must be 3 (self term) or 4 (no self term)");
+    OCN_CHECK_ARG(n >= 0 && feat > 0, "ocn_gcn_spmm: bad sizes");
+    if (n == 0) return OCN_OK;
+    return launch_spmm(rowptr, col, edge_w, norm, n, x, feat, mode, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,194 @@
+"""Host-side mirror of the reference predictors on top of the fused CUDA path.
+
+Same constructor arguments, parameter / buffer names (so ``state_dict`` interchanges with the
+reference's ``gmodel/*.pt`` checkpoints) and forward signatures as
+
+* ``CNLinkPredictorOringin``  = ``cn5`` = OCN      (model.py:2171-2443)
+* ``CNLinkPredictor3hopCNs``  = ``cn6``            (model.py:2447-2954; the order-3 template)
+* ``CNLinkPredictorbaselearn``= ``cn7`` = OCNP     (model.py:2958-3229)
+
+The dense MLP heads stay torch modules; everything between the target links and
+the three ``[B, F]`` aggregates runs in libocn_b200.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .cn import CNSession, SparseRows
+from .graph import Graph
+
+
+class DropAdj(nn.Module):
+    """Only the buffer of model.py:211-229 (kept for state_dict parity); cn5/cn6/cn7 never apply it."""
+
+    def __init__(self, dp: float = 0.0, doscale=True):
+        super().__init__()
+        self.dp = dp
+        self.register_buffer("ratio", torch.tensor(1 / (1 - dp)))
+        self.doscale = doscale
+
+
+def _mlp3(i, h, dropout, ln, last=True):
+    lnfn = (lambda d: nn.LayerNorm(d)) if ln else (lambda d: nn.Identity())
+    return nn.Sequential(nn.Linear(i, h), nn.Dropout(dropout, inplace=True), nn.ReLU(inplace=True),
+                         nn.Linear(h, h), lnfn(h), nn.Dropout(dropout, inplace=True), nn.ReLU(inplace=True),
+                         nn.Linear(h, h) if last else nn.Identity())
+
+
+class _CNAggregateFn(torch.autograd.Function):
+    """xcn_k = C-hat_k @ x and x_i * x_j; the weights do not depend on x or on any parameter."""
+
+    @staticmethod
+    def forward(ctx, x, sess: CNSession, variant: int, fill: float, ip3: Tensor):
+        xcn1, xcn2, xcn3, xij = sess.aggregate(x, variant, fill, ip3, want_xij=True)
+        ctx.sess, ctx.variant, ctx.fill = sess, variant, fill
+        ctx.save_for_backward(x, ip3)
+        ctx.has = (xcn2 is not None, xcn3 is not None)
+        z = lambda t: t if t is not None else x.new_zeros(0)
+        return xcn1, z(xcn2), z(xcn3), xij
+
+    @staticmethod
+    def backward(ctx, g1, g2, g3, gij):
+        x, ip3 = ctx.saved_tensors
+        gx = torch.zeros_like(x)
+        ctx.sess.aggregate_bwd(x, ctx.variant, ctx.fill, ip3, g1, g2 if ctx.has[0] else None,
+                               g3 if ctx.has[1] else None, gij, gx)
+        return gx, None, None, None, None
+
+
+class _OCNBase(nn.Module):
+    variant = 5
+    order = 2
+
+    def __init__(self, in_channels, hidden_channels, out_channels, num_layers, dropout, edrop=0.0, ln=False,
+                 cndeg=-1, use_xlin=False, tailact=False, twolayerlin=False, beta=1.0, weighted: bool = False):
+        super().__init__()
+        lnfn = (lambda d: nn.LayerNorm(d)) if ln else (lambda d: nn.Identity())
+        self.register_parameter("beta", nn.Parameter(beta * torch.ones((1))))
+        self.dropadj = DropAdj(edrop)
+        self.xlin = _mlp3(hidden_channels, hidden_channels, dropout, ln, last=False) if use_xlin else (lambda x: 0)
+        self.xcnlin = _mlp3(in_channels, hidden_channels, dropout, ln, last=not tailact)
+        self.xcn1lin = _mlp3(in_channels, hidden_channels, dropout, ln)
+        self.xcn2lin = _mlp3(in_channels, hidden_channels, dropout, ln)
+        self._extra_heads(in_channels, hidden_channels, dropout, ln)
+        self.xijlin = nn.Sequential(nn.Linear(in_channels, hidden_channels), lnfn(hidden_channels),
+                                    nn.Dropout(dropout, inplace=True), nn.ReLU(inplace=True),
+                                    nn.Linear(hidden_channels, hidden_channels) if not tailact else nn.Identity())
+        self.lin = nn.Sequential(nn.Linear(hidden_channels, hidden_channels), lnfn(hidden_channels),
+                                 nn.Dropout(dropout, inplace=True), nn.ReLU(inplace=True),
+                                 nn.Linear(hidden_channels, hidden_channels) if twolayerlin else nn.Identity(),
+                                 lnfn(hidden_channels) if twolayerlin else nn.Identity(),
+                                 nn.Dropout(dropout, inplace=True) if twolayerlin else nn.Identity(),
+                                 nn.ReLU(inplace=True) if twolayerlin else nn.Identity(),
+                                 nn.Linear(hidden_channels, out_channels))
+        self.cndeg = cndeg
+        self.register_parameter("alpha", nn.Parameter(torch.ones((3))))
+        self.register_buffer("innerprod", torch.tensor([0.0]))
+        self.n = 0
+        # values of CN_k for k >= 2: pygho walk counts (citation2/ppa drivers) or 0/1 (the _large drivers), SURVEY Q11
+        self.weighted = weighted
+
+    def _extra_heads(self, i, h, dropout, ln):
+        self.xcn4lin = _mlp3(i, h, dropout, ln)
+
+    # -- the fused CN stage -------------------------------------------------------------------
+    def _running_mean_update(self, s: Tensor):
+        """``innerprod1`` (model.py:2241-2250): n += 1; ip = ip*(1-1/n) + s/n, on device, no sync."""
+        self.n += 1
+        beta = self.n ** -1
+        self.innerprod *= (1 - beta)
+        self.innerprod += beta * s
+
+    def cn_stage(self, x: Tensor, adj: Graph, tar_ei: Tensor, fill: float = 0.0, sess: Optional[CNSession] = None):
+        if sess is None:
+            sess = CNSession(adj, tar_ei)
+            sess.build(self.order, self.weighted)
+        ip3 = self.innerprod.detach().float().repeat(3).contiguous()
+        if self.variant == 5:
+            if self.training and sess.nb != 1:
+                raise ValueError("training updates the inner-product running mean once per link batch; "
+                                 "pass one batch per call (the reference does, NeighborOverlapCitation2.py:162-179)")
+            bs = sess.stats(5, fill, ip3, 0)
+            if self.training:
+                self._running_mean_update(bs[0, 1].detach())
+                ip3 = self.innerprod.detach().float().repeat(3).contiguous()
+                if self.order >= 3:
+                    bs = sess.stats(5, fill, ip3, 1)
+                    self._running_mean_update(bs[0, 2].detach())
+                    # the second order-3 inner product is taken against C2-hat built with ip3[0]; its own
+                    # coefficient and the first one both read the buffer after this last update
+                    self._running_mean_update(bs[0, 3].detach())
+                    final = self.innerprod.detach().float()
+                    ip3 = torch.cat((ip3[:1], final, final)).contiguous()
+        xcn1, xcn2, xcn3, xij = _CNAggregateFn.apply(x, sess, self.variant, float(fill), ip3)
+        return xcn1, xcn2, (xcn3 if xcn3.numel() else None), xij, sess
+
+    def _head(self, xcn1, xcn2, xcn3, xij):
+        xij = self.xijlin(xij)
+        xcn1 = self.xcn1lin(xcn1)
+        xcn2 = self.xcn2lin(xcn2)
+        alpha = torch.sigmoid(self.alpha).cumprod(-1)
+        z = alpha[0] * xcn1 + alpha[1] * xcn2
+        if xcn3 is not None:
+            z = z + alpha[2] * self.xcn3lin(xcn3)
+        return self.lin(z + self.beta * xij)
+
+
+class CNLinkPredictorOringin(_OCNBase):
+    """cn5 / OCN.  ``cn1``/``cn2`` may be None (the sets are built from ``adj`` and ``tar_ei``
+    inside the fused path) or a prepared ``CNSession``."""
+    variant, order = 5, 2
+
+    def multidomainforward(self, x, adj, cn1, cn2, tar_ei, filled1: bool = False, cndropprobs: Iterable[float] = []):
+        sess = cn1 if isinstance(cn1, CNSession) else None
+        if isinstance(cn1, SparseRows) or isinstance(cn2, SparseRows):
+            raise TypeError("pass cn1=cn2=None (or a CNSession): the fused path builds the CN sets itself; "
+                            "explicit matrices go through ocn_b200.explicit.cn5_explicit")
+        xcn1, xcn2, _, xij, _ = self.cn_stage(x, adj, tar_ei, 0.0, sess)
+        return self._head(xcn1, xcn2, None, xij)
+
+    def forward(self, x, adj, cn1, cn2, tar_ei, filled1: bool = False):
+        return self.multidomainforward(x, adj, cn1, cn2, tar_ei, filled1, [])
+
+
+class CNLinkPredictor3hopCNs(_OCNBase):
+    """cn6: order-3 OCN (north_star "depth 3")."""
+    variant, order = 5, 3
+
+    def _extra_heads(self, i, h, dropout, ln):
+        self.xcn3lin = _mlp3(i, h, dropout, ln)
+
+    def multidomainforward(self, x, adj, cn1, cn2, cn3, tar_ei, args=None, cndropprobs: Iterable[float] = []):
+        sess = cn1 if isinstance(cn1, CNSession) else None
+        xcn1, xcn2, xcn3, xij, _ = self.cn_stage(x, adj, tar_ei, 0.0, sess)
+        return self._head(xcn1, xcn2, xcn3, xij)
+
+    def forward(self, x, adj, cn1, cn2, cn3, tar_ei, args=None):
+        return self.multidomainforward(x, adj, cn1, cn2, cn3, tar_ei, args)
+
+
+class CNLinkPredictorbaselearn(_OCNBase):
+    """cn7 / OCNP: singletons weigh ``args.sum``, CN2 enters raw."""
+    variant, order = 7, 2
+
+    def multidomainforward(self, x, adj, cn1, cn2, tar_ei, args, filled1: bool = False,
+                           cndropprobs: Iterable[float] = []):
+        sess = cn1 if isinstance(cn1, CNSession) else None
+        fill = float(getattr(args, "sum", args if isinstance(args, (int, float)) else 0.0))
+        xcn1, xcn2, _, xij, _ = self.cn_stage(x, adj, tar_ei, fill, sess)
+        return self._head(xcn1, xcn2, None, xij)
+
+    def forward(self, x, adj, cn1, cn2, tar_ei, filled1=False):
+        # the reference's forward passes `args` in the filled1 slot (model.py:3228-3229)
+        return self.multidomainforward(x, adj, cn1, cn2, tar_ei, filled1, [])
+
+
+predictor_dict = {
+    "cn5": CNLinkPredictorOringin,
+    "cn6": CNLinkPredictor3hopCNs,
+    "cn7": CNLinkPredictorbaselearn,
+}

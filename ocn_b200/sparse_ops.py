@@ -1,0 +1,164 @@
+"""SpMM / GCN aggregation / A^2 SpGEMM wrappers (pieces 2 and 3 of north_star) with autograd.
+
+Reference call sites: ``spmm_add/spmm_mean/spmm_max`` (model.py:6,45-53,2426-2427),
+``PureConv`` (model.py:42-55), ``PureConv3`` (model.py:128-142), ``GCNConv`` via ``convdict``
+(model.py:58-71), ``spadj @ spadj`` and ``sparse_tensor_multiply`` (NeighborOverlap_large.py:68-74,
+utils.py:287-329).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .cn import SparseRows, _stream
+from .graph import Graph, _require_cuda
+
+_REDUCE = {"sum": 0, "add": 0, "mean": 1, "max": 2}
+
+
+def _csr_of(src):
+    if isinstance(src, Graph):
+        return src.rowptr, src.col, src.value, src.n
+    if isinstance(src, SparseRows):
+        return src.rowptr, src.col.to(torch.int32), src.value, src.shape[0]
+    raise TypeError(f"expected Graph or SparseRows, got {type(src)}")
+
+
+def _spmm_raw(rowptr, col, val, rows, x, reduce: int) -> Tensor:
+    _require_cuda(x)
+    x = x.contiguous()
+    out = torch.empty(rows, x.shape[1], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().ocn_spmm_csr(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), rows, _lib.ptr(x),
+                                           x.shape[1], reduce, _lib.ptr(out), _stream(x.device)), "ocn_spmm_csr")
+    return out
+
+
+class _SpmmFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rowptr, col, val, rows, reduce):
+        ctx.save_for_backward(rowptr, col, val)
+        ctx.rows, ctx.reduce, ctx.xshape = rows, reduce, x.shape
+        return _spmm_raw(rowptr, col, val, rows, x.float(), reduce)
+
+    @staticmethod
+    def backward(ctx, g):
+        rowptr, col, val = ctx.saved_tensors
+        if ctx.reduce == 2:
+            raise NotImplementedError("spmm_max backward is not on the hot path (the reference's README configs use sum/gcn)")
+        g = g.contiguous().float()
+        gx = torch.zeros(ctx.xshape, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().ocn_spmm_csr_bwd(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), ctx.rows,
+                                                   _lib.ptr(g), g.shape[1], ctx.reduce, _lib.ptr(gx),
+                                                   _stream(g.device)), "ocn_spmm_csr_bwd")
+        return gx, None, None, None, None, None
+
+
+def spmm(src, other: Tensor, reduce: str = "sum") -> Tensor:
+    rowptr, col, val, rows = _csr_of(src)
+    return _SpmmFn.apply(other, rowptr, col, val, rows, _REDUCE[reduce])
+
+
+def spmm_add(src, other: Tensor) -> Tensor:
+    return spmm(src, other, "sum")
+
+
+def spmm_mean(src, other: Tensor) -> Tensor:
+    return spmm(src, other, "mean")
+
+
+def spmm_max(src, other: Tensor):
+    return spmm(src, other, "max"), None  # the reference only reads [0] (model.py:47)
+
+
+# ---- GCN-normalised aggregation ---------------------------------------------------------------
+
+def gcn_norm(g: Graph, edge_w: Optional[Tensor] = None) -> Tensor:
+    """rsqrt(1 + rowsum(A)) (model.py:51, :136)."""
+    out = torch.empty(g.n, dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.lib().ocn_gcn_norm(_lib.ptr(g.rowptr), _lib.ptr(edge_w), g.n, _lib.ptr(out), _stream(g.device)),
+                   "ocn_gcn_norm")
+    return out
+
+
+def _gcn_raw(g: Graph, edge_w, norm, mode: int, x: Tensor) -> Tensor:
+    x = x.contiguous()
+    out = torch.empty(g.n, x.shape[1], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().ocn_gcn_spmm(_lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(edge_w), g.n, _lib.ptr(norm),
+                                           mode, _lib.ptr(x), x.shape[1], _lib.ptr(out), _stream(x.device)),
+                   "ocn_gcn_spmm")
+    return out
+
+
+class _GcnFn(torch.autograd.Function):
+    """out = A-hat x with a symmetric A-hat (unit or symmetric edge weights), so grad_x = A-hat grad_out."""
+
+    @staticmethod
+    def forward(ctx, x, graph, norm, mode):
+        ctx.graph, ctx.mode = graph, mode
+        ctx.save_for_backward(norm)
+        return _gcn_raw(graph, None, norm, mode, x.float())
+
+    @staticmethod
+    def backward(ctx, g):
+        (norm,) = ctx.saved_tensors
+        return _gcn_raw(ctx.graph, None, norm, ctx.mode, g.contiguous().float()), None, None, None
+
+
+def pure_conv(x: Tensor, adj: Graph, aggr: str = "gcn", norm: Optional[Tensor] = None) -> Tensor:
+    """``PureConv.forward`` (model.py:42-55)."""
+    _require_cuda(x)
+    if aggr == "gcn":
+        return _GcnFn.apply(x, adj, norm if norm is not None else gcn_norm(adj), 3)
+    return spmm(adj, x, aggr)
+
+
+def pure_conv3_gcn(x: Tensor, adj: Graph, norm: Optional[Tensor] = None) -> Tensor:
+    """``PureConv3.forward`` aggr='gcn' before its Linear (model.py:135-141)."""
+    _require_cuda(x)
+    return _GcnFn.apply(x, adj, norm if norm is not None else gcn_norm(adj), 4)
+
+
+def gcnconv_propagate(x: Tensor, adj: Graph, normalize: bool, add_self_loops: bool = True, aggr: str = "sum") -> Tensor:
+    """Neighbour aggregation of PyG ``GCNConv`` as configured by ``convdict`` (model.py:58-71)."""
+    if not normalize:
+        return spmm(adj, x, aggr)
+    if not add_self_loops:
+        raise NotImplementedError("convdict never builds GCNConv(normalize=True, add_self_loops=False)")
+    return _GcnFn.apply(x, adj, gcn_norm(adj), 3)
+
+
+# ---- A^2 --------------------------------------------------------------------------------------
+
+def spgemm_a2(adj: Graph, fold: int = 0, with_value: bool = False) -> Graph:
+    """``spadj @ spadj`` (fold=0) or the reference's ``sparse_tensor_multiply(spadj, fold)``."""
+    _require_cuda(adj.col)
+    L = _lib.lib()
+    dev = adj.device
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        scratch = torch.zeros(L.ocn_spgemm_scratch_bytes(adj.n), dtype=torch.uint8, device=dev)
+        row_nnz = torch.zeros(adj.n, dtype=torch.int64, device=dev)
+        _lib.check(L.ocn_spgemm_a2_symbolic(_lib.ptr(adj.rowptr), _lib.ptr(adj.col), adj.n, int(fold),
+                                            _lib.ptr(scratch), _lib.ptr(row_nnz), st), "ocn_spgemm_a2_symbolic")
+        rowptr = torch.zeros(adj.n + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(row_nnz, 0, out=rowptr[1:])
+        nnz = int(rowptr[-1].item())
+        col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        val = torch.empty(nnz, dtype=torch.float32, device=dev) if with_value else None
+        if nnz:
+            _lib.check(L.ocn_spgemm_a2_numeric(_lib.ptr(adj.rowptr), _lib.ptr(adj.col), adj.n, int(fold),
+                                               _lib.ptr(scratch), _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), st),
+                       "ocn_spgemm_a2_numeric")
+    return Graph(rowptr, col, adj.n, val)
+
+
+def sparse_tensor_multiply(spadj: Graph, block_size: int = 1024) -> Graph:
+    """utils.py:326-329 as written (folded)."""
+    return spgemm_a2(spadj, fold=block_size, with_value=True)

@@ -1,0 +1,330 @@
+"""GPU parity tests: every CUDA entry point (through the C ABI) against the CPU oracle.
+
+Integer / index results are compared bit-exactly; floating-point results within
+|delta| <= RTOL * (1 + L1 mass of the sum), the tolerance SURVEY.md §8c-5 states, RTOL = 1e-5
+(1e-4 where a near-cancelling column sum is divided by).
+"""
+import numpy as np
+import pytest
+import torch
+
+import ocn_b200 as ob
+from ocn_b200 import synth
+from oracle import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RTOL = 1e-5
+
+
+def _graph(g):
+    return ob.Graph(g.rowptr.to(DEV), g.col.to(DEV), g.n)
+
+
+def _sp(g):
+    return R.sp_from_csr(g.rowptr.cpu(), g.col.cpu())
+
+
+def _assert_rows_equal(got: ob.SparseRows, ref: R.Sp, values=True, vtol=0.0):
+    rp = ref.rowptr()
+    assert torch.equal(got.rowptr.cpu(), rp), "row pointers differ"
+    assert torch.equal(got.col.cpu(), ref.col), "column indices differ"
+    if values:
+        gv, rv = got.value.cpu(), ref.values()
+        if vtol == 0.0:
+            assert torch.equal(gv, rv), "values differ"
+        else:
+            assert torch.allclose(gv, rv, rtol=vtol, atol=vtol), f"values differ by {(gv - rv).abs().max()}"
+
+
+def _close(got, ref, mass, rtol=RTOL):
+    err = (got.cpu().double() - ref.double()).abs()
+    bound = rtol * (1.0 + mass.double())
+    assert bool((err <= bound).all()), f"max err {err.max().item():.3e}, worst bound ratio {(err / bound).max().item():.2f}"
+
+
+GRAPHS = {
+    "tiny": lambda: synth.tiny_graph(60, 260, 3),
+    "tiny_dense": lambda: synth.tiny_graph(40, 900, 4),
+    "cora": lambda: synth.make_graph("cora"),
+    "pubmed": lambda: synth.make_graph("pubmed"),
+    "collab_s": lambda: synth.make_graph("collab", scale=0.02),
+    "citation2_s": lambda: synth.make_graph("citation2", scale=0.002),
+    "ddi_s": lambda: synth.make_graph("ddi", scale=0.08),
+}
+
+
+def test_library_loaded_and_validate():
+    g = synth.tiny_graph(50, 200, 1)
+    G = _graph(g)
+    assert G.validate() == 0
+    bad = ob.Graph(g.rowptr.to(DEV), torch.flip(g.col, [0]).to(DEV), g.n)
+    assert bad.validate() != 0
+    # asymmetric: keep the raw directed draws only
+    asym = ob.Graph.from_edge_index(torch.stack((g.raw_src, g.raw_dst)).to(DEV), g.n, symmetric=False)
+    assert asym.validate() & 8
+    sym = ob.Graph.from_edge_index(torch.stack((g.raw_src, g.raw_dst)).to(DEV), g.n)
+    keep = g.raw_src != g.raw_dst
+    if bool(keep.all()):
+        assert torch.equal(sym.rowptr.cpu(), g.rowptr) and torch.equal(sym.col.cpu(), g.col)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_dense", "cora", "pubmed"])
+def test_adjoverlap_generic_and_spgemm(name):
+    g = GRAPHS[name]()
+    G, A = _graph(g), _sp(g)
+    e = g.query_edges(512, "mixed")
+    ed = e.to(DEV)
+    _assert_rows_equal(ob.adjoverlap(G, G, ed), R.adjoverlap(A, A, e))
+    # true A^2 (structure and 2-walk counts), then adjoverlap(adj, adj2, e) as NeighborOverlap_large.py:78-79
+    a2 = R.adj2_true(A, keep_value=True)
+    G2 = ob.spgemm_a2(G, with_value=True)
+    assert torch.equal(G2.rowptr.cpu(), a2.rowptr())
+    assert torch.equal(G2.col.cpu().long(), a2.col)
+    assert torch.equal(G2.value.cpu(), a2.values())
+    _assert_rows_equal(ob.adjoverlap(G, G2, ed), R.adjoverlap(A, R.Sp(a2.row, a2.col, None, a2.shape), e))
+    # the reference's folded adj2byblock matrix
+    bs = 16 if g.n < 100 else 1024
+    f = R.adj2_folded(A, bs)
+    GF = ob.sparse_tensor_multiply(G, bs)
+    assert torch.equal(GF.rowptr.cpu(), f.rowptr())
+    assert torch.equal(GF.col.cpu().long(), f.col)
+    assert torch.equal(GF.value.cpu(), f.values())
+    _assert_rows_equal(ob.adjoverlap(G, GF, ed), R.adjoverlap(A, f, e))
+
+
+@pytest.mark.parametrize("name,B", [("tiny", 128), ("tiny_dense", 64), ("cora", 1152), ("pubmed", 2048),
+                                    ("collab_s", 4096), ("citation2_s", 2048), ("ddi_s", 256)])
+def test_cn_sets_bit_exact(name, B):
+    """CN_k index sets and walk counts, k = 1..3, against the pygho-style oracle."""
+    g = GRAPHS[name]()
+    G, A = _graph(g), _sp(g)
+    kind = "stream" if name.startswith("citation2") else "mixed"
+    e = g.query_edges(B, kind)
+    order = 3 if g.nnz < 60000 or name.startswith("citation2") else 2
+    got = ob.get_cn(G, e.to(DEV), order, weighted=True)
+    ref = R.get_cn(A, e, order)
+    for k in range(order):
+        _assert_rows_equal(got[k], ref[k])
+    # unweighted structure == adjoverlap(adj, adj2, e)
+    got_s = ob.get_cn(G, e.to(DEV), 2, weighted=False)
+    ref_s = R.adjoverlap(A, R.adj2_true(A), e)
+    _assert_rows_equal(got_s[1], ref_s)
+
+
+def _oracle_cns(A, e, order, weighted):
+    cns = R.get_cn(A, e, order)
+    if not weighted:
+        cns = [R.Sp(c.row, c.col, torch.ones(c.nnz), c.shape) for c in cns]
+    return cns
+
+
+def _mass(sp: R.Sp, x):
+    return R.spmm_add(R.Sp(sp.row, sp.col, sp.values().abs(), sp.shape), x.abs())
+
+
+@pytest.mark.parametrize("name,B,F", [("tiny", 96, 8), ("cora", 1152, 256), ("pubmed", 2048, 64), ("collab_s", 4096, 32),
+                                      ("citation2_s", 2048, 32)])
+@pytest.mark.parametrize("weighted,ip", [(True, 0.0), (False, 0.0), (True, 0.731), (False, 1.9)])
+def test_cn5_aggregate(name, B, F, weighted, ip):
+    g = GRAPHS[name]()
+    G, A = _graph(g), _sp(g)
+    e = g.query_edges(B, "stream" if name.startswith("citation2") else "mixed")
+    x = g.features(F)
+    cns = _oracle_cns(A, e, 2, weighted)
+    r1, r2, rij, n1, n2 = R.cn5_aggregate(cns[0], cns[1], x, e, R.InnerProdState(ip), training=False)
+    ip3 = torch.full((3,), ip, dtype=torch.float32, device=DEV)
+    sess = ob.CNSession(G, e.to(DEV)).build(2, weighted)
+    sess.stats(5, 0.0, ip3, 0)
+    x1, x2, x3, xij = sess.aggregate(x.to(DEV), 5, 0.0, ip3)
+    assert x3 is None
+    _close(x1, r1, _mass(n1, x))
+    _close(x2, r2, _mass(n2, x), rtol=1e-4 if ip else RTOL)
+    assert torch.equal(xij.cpu(), rij)
+    # the normalised matrices themselves: pattern bit-exact (explicit zeros kept), values close
+    _assert_rows_equal(sess.extract(11, 5, 0.0, ip3), n1, vtol=1e-6)
+    _assert_rows_equal(sess.extract(12, 5, 0.0, ip3), n2, vtol=1e-4 if ip else 1e-6)
+    sess.release()
+    assert int(sess.colstat.count_nonzero()) == 0
+
+
+@pytest.mark.parametrize("name,B,F", [("tiny", 96, 8), ("cora", 1152, 32), ("citation2_s", 2048, 32)])
+@pytest.mark.parametrize("ip", [0.0, 0.43])
+def test_cn6_order3_aggregate(name, B, F, ip):
+    g = GRAPHS[name]()
+    G, A = _graph(g), _sp(g)
+    e = g.query_edges(B, "stream" if name.startswith("citation2") else "mixed")
+    x = g.features(F)
+    cns = _oracle_cns(A, e, 3, True)
+    r1, r2, r3, rij, n1, n2, n3 = R.cn6_aggregate(cns[0], cns[1], cns[2], x, e, R.InnerProdState(ip), training=False)
+    ip3 = torch.full((3,), ip, dtype=torch.float32, device=DEV)
+    sess = ob.CNSession(G, e.to(DEV)).build(3, True)
+    sess.stats(5, 0.0, ip3, 0)
+    x1, x2, x3, xij = sess.aggregate(x.to(DEV), 5, 0.0, ip3)
+    tol = 1e-4 if ip else RTOL
+    _close(x1, r1, _mass(n1, x))
+    _close(x2, r2, _mass(n2, x), rtol=tol)
+    _close(x3, r3, _mass(n3, x), rtol=tol)
+    _assert_rows_equal(sess.extract(13, 5, 0.0, ip3), n3, vtol=tol)
+
+
+@pytest.mark.parametrize("name,B,F,fill", [("tiny", 96, 8, 1.0), ("pubmed", 2048, 256, 1.0), ("ddi_s", 512, 64, 0.0)])
+def test_cn7_aggregate(name, B, F, fill):
+    g = GRAPHS[name]()
+    G, A = _graph(g), _sp(g)
+    e = g.query_edges(B, "mixed")
+    x = g.features(F)
+    cns = _oracle_cns(A, e, 2, False)
+    r1, r2, rij, n1 = R.cn7_aggregate(cns[0], cns[1], x, e, fill)
+    ip3 = torch.zeros(3, device=DEV)
+    sess = ob.CNSession(G, e.to(DEV)).build(2, False)
+    x1, x2, _, xij = sess.aggregate(x.to(DEV), 7, fill, ip3)
+    _close(x1, r1, _mass(n1, x))
+    _close(x2, r2, _mass(cns[1], x))
+    assert torch.equal(xij.cpu(), rij)
+
+
+def test_stream_of_batches_equals_per_batch_calls():
+    g = GRAPHS["citation2_s"]()
+    G = _graph(g)
+    e = g.query_edges(5 * 512 + 100, "stream").to(DEV)
+    x = g.features(32).to(DEV)
+    ip3 = torch.full((3,), 0.25, device=DEV)
+    whole = ob.cn_aggregate_eval(G, e, x, 512, 3, True, 5, 0.0, ip3)
+    tiny_budget = ob.cn_aggregate_eval(G, e, x, 512, 3, True, 5, 0.0, ip3, budget_bytes=2 * 32 * g.n)
+    for s in range(0, e.shape[1], 512):
+        part = ob.cn_aggregate_eval(G, e[:, s:s + 512], x, 512, 3, True, 5, 0.0, ip3)
+        for w, t, p in zip(whole, tiny_budget, part):
+            assert torch.equal(w[s:s + 512], p), "stream result differs from the single-batch call (must be bit-identical)"
+            assert torch.equal(t[s:s + 512], p)
+
+
+def test_training_running_inner_product_and_backward():
+    """cn5 / cn6 in training mode: the running mean of model.py:2241-2250 over consecutive batches and
+    grad_x against autograd through the oracle."""
+    g = GRAPHS["cora"]()
+    G, A = _graph(g), _sp(g)
+    F = 16
+    torch.manual_seed(0)
+    for order, cls in ((2, ob.CNLinkPredictorOringin), (3, ob.CNLinkPredictor3hopCNs)):
+        pred = cls(F, F, 1, 3, 0.0, weighted=True).to(DEV).train()
+        st = R.InnerProdState()
+        for step in range(3):
+            e = torch.stack((synth.hash_randint(300, g.n, 50 + step, 1, "cpu"), synth.hash_randint(300, g.n, 50 + step, 2, "cpu")))
+            pe = g.query_edges(300, "pos")
+            e = torch.cat((e, pe), 1)
+            x = g.features(F).clone().requires_grad_(True)
+            cns = _oracle_cns(A, e, order, True)
+            if order == 2:
+                r1, r2, rij, n1, n2 = R.cn5_aggregate(cns[0], cns[1], x, e, st, training=True)
+                ref_outs, masses = [r1, r2], [_mass(n1, x.detach()), _mass(n2, x.detach())]
+            else:
+                r1, r2, r3, rij, n1, n2, n3 = R.cn6_aggregate(cns[0], cns[1], cns[2], x, e, st, training=True)
+                ref_outs = [r1, r2, r3]
+                masses = [_mass(n1, x.detach()), _mass(n2, x.detach()), _mass(n3, x.detach())]
+            xd = x.detach().to(DEV).requires_grad_(True)
+            x1, x2, x3, xij, _ = pred.cn_stage(xd, G, e.to(DEV))
+            assert pred.n == st.n
+            assert abs(pred.innerprod.item() - st.innerprod.item()) <= 1e-4 * (1 + abs(st.innerprod.item()))
+            got = [x1, x2] + ([x3] if order == 3 else [])
+            for a, b, m in zip(got, ref_outs, masses):
+                _close(a.detach(), b.detach(), m, rtol=2e-4)
+            wts = [torch.randn_like(o) for o in ref_outs] + [torch.randn_like(rij)]
+            loss_ref = sum((o * w).sum() for o, w in zip(ref_outs + [rij], wts))
+            loss_ref.backward()
+            loss = sum((o * w.to(DEV)).sum() for o, w in zip(got + [xij], wts))
+            loss.backward()
+            gm = x.grad.abs().max().item()
+            assert (xd.grad.cpu() - x.grad).abs().max().item() <= 5e-4 * (1 + gm)
+
+
+def test_predictor_end_to_end_matches_oracle_heads():
+    """Full cn5 / cn7 forward (MLP heads included) == oracle aggregates fed through the same heads."""
+    g = GRAPHS["pubmed"]()
+    G, A = _graph(g), _sp(g)
+    F = 32
+    e = g.query_edges(1024, "mixed")
+    x = g.features(F)
+    torch.manual_seed(1)
+    p5 = ob.CNLinkPredictorOringin(F, F, 1, 3, 0.0).to(DEV).eval()
+    p7 = ob.CNLinkPredictorbaselearn(F, F, 1, 3, 0.0).to(DEV).eval()
+    cns = _oracle_cns(A, e, 2, False)
+    with torch.no_grad():
+        out5 = p5(x.to(DEV), G, None, None, e.to(DEV)).cpu()
+        r1, r2, rij, _, _ = R.cn5_aggregate(cns[0], cns[1], x, e, R.InnerProdState(), training=False)
+        ref5 = p5.cpu()._head(r1, r2, None, rij)
+        assert torch.allclose(out5, ref5, rtol=1e-4, atol=1e-4)
+
+        class Args:
+            sum = 1
+        out7 = p7.multidomainforward(x.to(DEV), G, None, None, e.to(DEV), Args()).cpu()
+        r1, r2, rij, _ = R.cn7_aggregate(cns[0], cns[1], x, e, 1.0)
+        ref7 = p7.cpu()._head(r1, r2, None, rij)
+        assert torch.allclose(out7, ref7, rtol=1e-4, atol=1e-4)
+    pos, neg = out5[:512].flatten(), out5[512:].flatten()
+    assert abs(R.hits_at_k(pos, neg, 20) - R.hits_at_k(ref5[:512].flatten(), ref5[512:].flatten(), 20)) <= 0.01
+
+
+@pytest.mark.parametrize("name,F", [("tiny", 5), ("cora", 256), ("pubmed", 64), ("collab_s", 128), ("ddi_s", 64), ("citation2_s", 32)])
+def test_gnn_aggregation(name, F):
+    g = GRAPHS[name]()
+    G, A = _graph(g), _sp(g)
+    x = g.features(F)
+    xd = x.to(DEV)
+    ones = R.Sp(A.row, A.col, torch.ones(A.nnz), A.shape)
+    deg = (g.rowptr[1:] - g.rowptr[:-1]).float().unsqueeze(1)
+    mass_sum = R.spmm_add(ones, x.abs())
+    _close(ob.pure_conv(xd, G, "sum"), R.pure_conv(x, A, "sum"), mass_sum)
+    _close(ob.pure_conv(xd, G, "mean"), R.pure_conv(x, A, "mean"), mass_sum / deg.clamp(min=1))
+    assert torch.equal(ob.pure_conv(xd, G, "max").cpu(), R.pure_conv(x, A, "max"))
+    _close(ob.pure_conv(xd, G, "gcn"), R.pure_conv(x, A, "gcn"), mass_sum + x.abs())
+    _close(ob.pure_conv3_gcn(xd, G), R.pure_conv3_gcn(x, A), mass_sum)
+    _close(ob.gcnconv_propagate(xd, G, True, True), R.gcnconv_propagate(x, A, True, True), mass_sum + x.abs())
+    _close(ob.gcnconv_propagate(xd, G, False), R.gcnconv_propagate(x, A, False, False), mass_sum)
+    # backward of the sum / gcn aggregation (A-hat symmetric)
+    xr = x.clone().requires_grad_(True)
+    w = torch.randn(g.n, F)
+    (R.pure_conv(xr, A, "gcn") * w).sum().backward()
+    xg = xd.clone().requires_grad_(True)
+    (ob.pure_conv(xg, G, "gcn") * w.to(DEV)).sum().backward()
+    _close(xg.grad, xr.grad, R.spmm_add(ones, w.abs()) + w.abs(), rtol=1e-4)
+    xr = x.clone().requires_grad_(True)
+    (R.pure_conv(xr, A, "mean") * w).sum().backward()
+    xg = xd.clone().requires_grad_(True)
+    (ob.pure_conv(xg, G, "mean") * w.to(DEV)).sum().backward()
+    _close(xg.grad, xr.grad, R.spmm_add(ones, w.abs()), rtol=1e-4)
+
+
+def test_spmm_on_cn_matrix_with_values():
+    """spmm_add(normalized_cn, x) on an explicit [B x N] matrix (model.py:2426-2427)."""
+    g = GRAPHS["cora"]()
+    G, A = _graph(g), _sp(g)
+    e = g.query_edges(700, "mixed")
+    x = g.features(24)
+    cn2 = ob.get_cn(G, e.to(DEV), 2, True)[1]
+    ref = R.get_cn(A, e, 2)[1]
+    _close(ob.spmm_add(cn2, x.to(DEV)), R.spmm_add(ref, x), _mass(ref, x))
+
+
+def test_full_size_citation2_walk_counts():
+    """BASELINE.json configs[4] at full size: CN_k values of a few links against an independent
+    torch-on-GPU propagation u_k = A^k e_j (size-independent property: C_k = u_k restricted to N(i))."""
+    g = synth.make_graph("citation2", device=DEV)
+    G = ob.Graph(g.rowptr, g.col, g.n)
+    assert G.validate() == 0
+    e = g.query_edges(2048, "stream", device=DEV)
+    cns = ob.get_cn(G, e, 3, weighted=True)
+    row = G.row()
+    colL = g.col.long()
+    for b in (0, 777, 1500, 2047):
+        i, j = int(e[0, b]), int(e[1, b])
+        u = torch.zeros(g.n, dtype=torch.float64, device=DEV)
+        u[j] = 1
+        ni = colL[int(g.rowptr[i]):int(g.rowptr[i + 1])]
+        for k in range(3):
+            u = torch.zeros_like(u).index_add_(0, row, u[colL])
+            vals = u[ni]
+            keep = vals > 0
+            s, t = int(cns[k].rowptr[b]), int(cns[k].rowptr[b + 1])
+            assert torch.equal(cns[k].col[s:t], ni[keep])
+            assert torch.equal(cns[k].value[s:t].double(), vals[keep])
