@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- higher-order CN aggregation links/s on a citation2-shape synthetic graph.
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU op sequence (oracle port)
+
+One *step* = one pass of the hot path (CN sets of orders 1..3 -> batch normalisation /
+orthogonalisation -> CN-indicator SpMM + pair term) over ``--batches`` consecutive link batches of
+2048 links in the shape of the citation2 evaluation stream (NeighborOverlapCitation2.py:241-254:
+every source against 1000 uniform destinations).  Under torchrun every rank holds a replica of
+the graph and features and scores its own batches (weak scaling, no data-path collective); the
+end-to-end arm gathers the fp32 scores with NCCL.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the byte accounting.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "higher-order CN aggregation edges/sec (citation2 shape)"
+UNIT = "edges/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ocn_b200", choices=["ocn_b200", "reference"])
+    ap.add_argument("--graph", default="citation2")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--order", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=2048)
+    ap.add_argument("--batches", type=int, default=32, help="link batches per step")
+    ap.add_argument("--feat", type=int, default=32)
+    ap.add_argument("--cpu-sample", type=int, default=48, help="links of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(G, e, order, feat, batch):
+    """Bytes the fused path must move for these links with no cache credit (DESIGN.md "Byte accounting").
+    Returns (build_kernel_bytes, whole_step_bytes, survey_formula_bytes)."""
+    import ocn_b200 as ob  # noqa: F401
+    deg = G.degree()
+    colL = G.col.long()
+    Fv = torch.zeros(G.n, dtype=torch.int64, device=G.device).index_add_(0, G.row(), deg[colL])
+    i, j = e[0], e[1]
+    di, dj, Fi, Fj = deg[i], deg[j], Fv[i], Fv[j]
+    T = e.shape[1]
+    # j side, once per (link, 32-position chunk of N(i)): rowptr pair + N(j) + rowptr pairs of N(j) + frontier
+    chunks = torch.div(di + 31, 32, rounding_mode="floor").clamp(min=0)
+    per_link_j = 16 + (4 * dj if order >= 2 else 0) + ((8 * dj + 4 * Fj) if order >= 3 else 0)
+    j_bytes = int((per_link_j * chunks.clamp(min=1)).sum())
+    # i side, once per work unit (run x chunk x 16-link sub-list): N(i) chunk, its rowptr pairs, its rows
+    t = torch.arange(T, device=e.device)
+    first = (t % batch == 0) | (torch.cat((i[:1] - 1, i[:-1])) != i)
+    run_id = torch.cumsum(first.long(), 0) - 1
+    run_len = torch.bincount(run_id)
+    run_src = i[first]
+    subs = torch.div(run_len + 15, 16, rounding_mode="floor")
+    i_bytes = int((subs * (16 + 12 * deg[run_src] + 4 * Fv[run_src])).sum())
+    rec_bytes = int(8 * di.sum())
+    build = j_bytes + i_bytes + rec_bytes + 16 * T
+    # aggregate + stats + release: records re-read 3x, col of N(i), colstat 32 B per non-empty record (upper bound: all),
+    # feature gathers 4F per non-empty record (upper bound), outputs
+    agg = int((3 * 8 + 4 + 32 + 4 * feat) * di.sum()) + T * (4 * feat * (order + 1) + 2 * 4 * feat + 32)
+    survey = int((32 + 4 * (di + dj) + (8 * dj + 4 * Fj if order >= 2 else 0) + (8 * di + 4 * Fi if order >= 3 else 0)).sum()) \
+        + T * 4 * feat * (order + 1 + 2)
+    return build, build + agg, survey
+
+
+def run_reference(a, rank, world):
+    """CPU arm: the oracle's restatement of the reference op sequence (pygho-style get_cn ->
+    cn6/cn5 combination -> spmm_add), all host threads, on a bounded sample per step."""
+    if rank != 0:
+        return
+    from ocn_b200 import synth
+    from oracle import ref_ops as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = synth.make_graph(a.graph, device="cuda:0" if torch.cuda.is_available() else "cpu", scale=a.scale)
+    rowptr, col = g.rowptr.cpu(), g.col.cpu()
+    A = R.sp_from_csr(rowptr, col)
+    x = g.features(a.feat, device="cpu")
+    S = a.cpu_sample
+    e_all = g.query_edges((a.steps + a.warmup) * S, "stream", device="cpu")
+    st = R.InnerProdState()
+    times = []
+    for s in range(a.steps + a.warmup):
+        e = e_all[:, s * S:(s + 1) * S]
+        t0 = time.perf_counter()
+        cns = R.get_cn(A, e, a.order)
+        if a.order >= 3:
+            R.cn6_aggregate(cns[0], cns[1], cns[2], x, e, st, training=False)
+        else:
+            R.cn5_aggregate(cns[0], cns[1], x, e, st, training=False)
+        dt = time.perf_counter() - t0
+        if s >= a.warmup:
+            times.append(dt)
+    total = sum(times)
+    val = S * len(times) / total
+    sample = f"{S} links per step of the same citation2-shape stream (order {a.order}, F={a.feat}), torch CPU ops"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, g),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, g):
+    return {"workload": f"{a.graph}-shape synthetic graph (N={g.n}, nnz={g.nnz}), cn5 order {a.order} (cn6 template) "
+                        f"scoring, F={a.feat}, evaluation link stream (each source x 1000 uniform destinations)",
+            "link_batch": a.batch, "batches_per_step": a.batches, "links_per_step_per_gpu": a.batch * a.batches,
+            "weighted": True, "l2": "inputs larger than L2 (CSR col 244 MB + fresh links every step)",
+            "parallelism": f"graph replicated, link batches sharded over {a.gpus} GPU(s)"}
+
+
+def cpu_baseline(a, g, rowptr, col):
+    from oracle import ref_ops as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    A = R.sp_from_csr(rowptr, col)
+    x = g.features(a.feat, device="cpu")
+    S = a.cpu_sample
+    e_all = g.query_edges(2 * S, "stream", device="cpu")
+    best = None
+    for s in range(2):
+        e = e_all[:, s * S:(s + 1) * S]
+        t0 = time.perf_counter()
+        cns = R.get_cn(A, e, a.order)
+        if a.order >= 3:
+            R.cn6_aggregate(cns[0], cns[1], cns[2], x, e, R.InnerProdState(), training=False)
+        else:
+            R.cn5_aggregate(cns[0], cns[1], x, e, R.InnerProdState(), training=False)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": S / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{S} links of the same stream (order {a.order}, F={a.feat}); oracle/ref_ops.py get_cn + "
+                      f"cn6_aggregate, best of 2"}
+
+
+def main():
+    a = parse()
+    rank, world, local = dist_env()
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    import ocn_b200 as ob
+    from ocn_b200 import synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (ocn_b200 has no CPU path)")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    g = synth.make_graph(a.graph, device=dev, scale=a.scale)
+    G = ob.Graph(g.rowptr, g.col, g.n)
+    x = g.features(a.feat, device=dev)
+    T = a.batch * a.batches
+    nsteps = a.steps + a.warmup
+    # every rank scores its own slice of the stream; every step gets fresh links
+    e_all = g.query_edges(world * nsteps * T, "stream", device=dev)
+    e_rank = e_all[:, rank * nsteps * T:(rank + 1) * nsteps * T].contiguous()
+    e_host = e_rank.cpu().pin_memory()
+    torch.manual_seed(0)
+    cls = ob.CNLinkPredictor3hopCNs if a.order >= 3 else ob.CNLinkPredictorOringin
+    pred = cls(a.feat, a.feat, 1, 3, 0.0, weighted=True).to(dev).eval()
+    ip3 = torch.zeros(3, device=dev)
+
+    def step_device(s):
+        e = e_rank[:, s * T:(s + 1) * T]
+        sess = ob.CNSession(G, e, a.batch).build(a.order, True)
+        sess.stats(5, 0.0, ip3, 0)
+        return sess.aggregate(x, 5, 0.0, ip3)
+
+    def step_e2e(s):
+        e = e_host[:, s * T:(s + 1) * T].to(dev, non_blocking=True)
+        with torch.no_grad():
+            sess = ob.CNSession(G, e, a.batch).build(a.order, True)
+            if a.order >= 3:
+                out = pred(x, G, sess, None, None, e)
+            else:
+                out = pred(x, G, sess, None, e)
+        scores = out.squeeze(-1)
+        if world > 1:
+            import torch.distributed as dist
+            allsc = torch.empty(world * T, dtype=scores.dtype, device=dev)
+            dist.all_gather_into_tensor(allsc, scores.contiguous())
+            scores = allsc
+        return scores.cpu() if rank == 0 else scores[:1].cpu()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for s in range(a.warmup):
+            fn(s)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        for s in range(a.warmup, nsteps):
+            fn(s)
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        return ms, wall, clocks
+
+    ms_dev, _, clocks = timed(step_device)
+    ms_e2e_ev, wall_e2e, _ = timed(step_e2e)
+    ms_e2e = max(ms_e2e_ev, wall_e2e * 1e3)  # the D2H read ends after the last event: use the host clock too
+
+    # roofline of the dominant kernel (k_cn_build): events around it on its stream, fresh links each launch
+    build_ms = []
+    for s in range(a.warmup, nsteps):
+        e = e_rank[:, s * T:(s + 1) * T]
+        sess = ob.CNSession(G, e, a.batch)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        sess.build(a.order, True)
+        ev1.record()
+        torch.cuda.synchronize()
+        build_ms.append(ev0.elapsed_time(ev1))
+    build_avg = sum(build_ms) / len(build_ms)
+    bb = [algorithmic_bytes(G, e_rank[:, s * T:(s + 1) * T], a.order, a.feat, a.batch) for s in range(a.warmup, nsteps)]
+    build_bytes = sum(b[0] for b in bb) / len(bb)
+    step_bytes = sum(b[1] for b in bb) / len(bb)
+    survey_bytes = sum(b[2] for b in bb) / len(bb)
+    peak, peak_src = peaks()
+    achieved = build_bytes / (build_avg * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("k_cn_build_dram_bytes_per_launch")
+
+    if rank == 0:
+        links = world * T * a.steps
+        value = links / (ms_dev * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 walk counts / f32 features", "data": "synthetic", "config": workload_config(a, g),
+            "clocks": clocks,
+            "e2e": {"value": links / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * T,
+                    "d2h_bytes_per_step": 4 * T * (world if world > 1 else 1), "ms_per_step": ms_e2e / a.steps,
+                    "api": "CNLinkPredictor*.forward(h, adj, CNSession, ..., edges) -> scores.cpu()"},
+            "gpu_launches": 10 * a.steps,
+            "roofline": {"bound": "hbm", "kernel": "k_cn_build", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": build_bytes, "kernel_ms": build_avg,
+                         "kernel_share_of_step": build_avg / (ms_dev / a.steps),
+                         "whole_step_gbs": step_bytes / (ms_dev / a.steps * 1e-3) / 1e9,
+                         "survey_formula_gbs": survey_bytes / (ms_dev / a.steps * 1e-3) / 1e9},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(a, g, g.rowptr.cpu(), g.col.cpu())
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -8,120 +8,213 @@
 //     C3[p] = #{ m in N(j), l in N(m)    : bit p of mask_i(l) }      (= A^3[j, N(i)[p]])
 // so one shared-memory hash table  l -> mask_i(l)  (built once per run of links that share the
 // source i) turns the whole computation into a 3-level walk from j with one table probe per
-// visited node.  The j-side frontier is streamed from HBM exactly once per (link, table).
+// visited node.
 //
-// A work unit = (run, 32 positions of N(i), <= 64 links); see cn_plan.cu.  If the 32 rows do not
-// fit the table the unit processes them in greedy sub-chunks; a single row longer than the
-// table capacity is probed by binary search instead ("direct" mode).
+// Work unit = (run, 32 positions of N(i), <= kEdgeSub links), scheduled dynamically (cn_plan.cu).
+// The 32 rows N(N(i)[p]) are inserted as one flattened list; if it exceeds the table capacity the
+// unit makes several passes (table = next slice of the list, j-side walked again) and sums the
+// per-position counts in shared memory, so a hub next to the source needs no special case.
+//
+// The j-side frontier is streamed row by row, 8 x 32 columns per warp iteration (8 independent
+// 128-byte loads in flight per warp); the 32 per-position counters of every lane are kept
+// bit-sliced in registers and updated with carry-save adders (~9 ALU ops per probed column, no
+// shared-memory atomics on the hot path).  Links with a large frontier are walked by all warps of
+// the CTA, the others by one warp each.
 #include "common.cuh"
 
 namespace ocn {
 
-constexpr int kBuildThreads = 256;
+constexpr int kBuildThreads = 512;
 constexpr int kBuildWarps = kBuildThreads / 32;
-constexpr int kSlotBits = 13;
-constexpr int kSlots = 1 << kSlotBits;        // 8192 x 8 B = 64 KB
-constexpr int kCap = (kSlots * 3) / 4;        // max keys inserted per table
+constexpr int kSlots = 13312;                  // 104 KB of (key, mask) pairs -> 2 CTAs / SM
+constexpr int kCap = (kSlots * 5) / 8;         // keys inserted per pass (load factor 0.625)
 constexpr uint32_t kEmpty = 0xffffffffu;
+constexpr int kHiPlanes = 17;                  // bit-sliced counter: 3 + 17 planes (< 2^20 per lane)
+constexpr int kShortRow = 8;                   // rows this short are walked one per lane
+constexpr int kHeavyFrontier = 12288;          // links above this frontier size use the whole CTA
 
 struct BuildSmem {
     uint2 table[kSlots];
-    unsigned acc2[kBuildWarps][32];
-    unsigned acc3[kBuildWarps][32];
+    unsigned acc2[kEdgeSub][32];
+    unsigned acc3[kEdgeSub][32];
     unsigned long long tot2[32];
     unsigned long long tot3[32];
     long long krs[32];
     unsigned tot1[32];
+    unsigned m1[kEdgeSub];
+    int heavy[kEdgeSub];
     int kp[32];
     int kdeg[32];
     int kpre[33];
     long long unit;
-    int q1;
-    int direct;
+    int n_heavy;
 };
 
-__device__ __forceinline__ uint32_t ht_hash(uint32_t key) { return (key * 2654435769u) >> (32 - kSlotBits); }
+__device__ __forceinline__ uint32_t ht_home(uint32_t key) {
+    return __umulhi(key * 2654435769u, (uint32_t)kSlots);
+}
 
 __device__ __forceinline__ void ht_insert(uint2* table, uint32_t key, uint32_t bit) {
-    uint32_t slot = ht_hash(key);
+    uint32_t slot = ht_home(key);
     while (true) {
         uint32_t prev = atomicCAS(&table[slot].x, kEmpty, key);
         if (prev == kEmpty || prev == key) {
             atomicOr(&table[slot].y, bit);
             return;
         }
-        slot = (slot + 1) & (kSlots - 1);
+        slot = (slot + 1 == (uint32_t)kSlots) ? 0u : slot + 1;
     }
 }
 
 __device__ __forceinline__ uint32_t ht_lookup(const uint2* table, uint32_t key) {
-    uint32_t slot = ht_hash(key);
+    uint32_t slot = ht_home(key);
     while (true) {
-        uint2 e = table[slot];
+        const uint2 e = table[slot];
         if (e.x == key) return e.y;
         if (e.x == kEmpty) return 0u;
-        slot = (slot + 1) & (kSlots - 1);
+        slot = (slot + 1 == (uint32_t)kSlots) ? 0u : slot + 1;
     }
 }
 
-template <bool DIRECT>
-__device__ __forceinline__ uint32_t probe(const BuildSmem& S, const int32_t* __restrict__ col, int q0, uint32_t key) {
-    if (DIRECT) return row_contains(col + S.krs[q0], S.kdeg[q0], (int32_t)key) ? (1u << q0) : 0u;
-    return ht_lookup(S.table, key);
+// ---- bit-sliced per-position counters ---------------------------------------------------------
+struct Sliced {
+    uint32_t ones, twos, fours;
+    uint32_t hi[kHiPlanes];  // hi[b] has weight 8 << b
+};
+
+__device__ __forceinline__ void sliced_zero(Sliced& s) {
+    s.ones = s.twos = s.fours = 0u;
+#pragma unroll
+    for (int b = 0; b < kHiPlanes; ++b) s.hi[b] = 0u;
+}
+
+// carry-save adder: (h, l) = a + b + c bitwise
+__device__ __forceinline__ void csa(uint32_t& h, uint32_t& l, uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t u = a ^ b;
+    h = (a & b) | (u & c);
+    l = u ^ c;
+}
+
+// add eight 32-position masks to the counters
+__device__ __forceinline__ void sliced_add8(Sliced& s, const uint32_t (&m)[8]) {
+    uint32_t t0, t1, t2, t3, f0, f1, e0;
+    csa(t0, s.ones, s.ones, m[0], m[1]);
+    csa(t1, s.ones, s.ones, m[2], m[3]);
+    csa(f0, s.twos, s.twos, t0, t1);
+    csa(t2, s.ones, s.ones, m[4], m[5]);
+    csa(t3, s.ones, s.ones, m[6], m[7]);
+    csa(f1, s.twos, s.twos, t2, t3);
+    csa(e0, s.fours, s.fours, f0, f1);
+    uint32_t carry = e0;
+#pragma unroll
+    for (int b = 0; b < kHiPlanes; ++b) {
+        const uint32_t t = s.hi[b] & carry;
+        s.hi[b] ^= carry;
+        carry = t;
+    }
+}
+
+// lane p receives the sum over all lanes of position p's counter
+__device__ __forceinline__ uint32_t plane_sum(uint32_t word, int lane) {
+    uint32_t tot = 0;
+    if (__any_sync(0xffffffffu, word != 0u)) {
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, (word >> p) & 1u);
+            if (lane == p) tot = __popc(bal);
+        }
+    }
+    return tot;
+}
+
+__device__ __forceinline__ uint32_t sliced_flush(const Sliced& s, int lane) {
+    uint32_t total = plane_sum(s.ones, lane) + 2u * plane_sum(s.twos, lane) + 4u * plane_sum(s.fours, lane);
+#pragma unroll
+    for (int b = 0; b < kHiPlanes; ++b) total += plane_sum(s.hi[b], lane) << (3 + b);
+    return total;
 }
 
 __device__ __forceinline__ void add_bits(unsigned* acc, uint32_t mask) {
     while (mask) {
-        int b = __ffs(mask) - 1;
+        const int b = __ffs(mask) - 1;
         atomicAdd(&acc[b], 1u);
         mask &= mask - 1;
     }
 }
 
-// one warp, one link, against the table currently in shared memory
-template <bool DIRECT>
+// Walk the frontier of link slot `e` (destination j) with `nw` cooperating warps, this one being
+// `rank`.  Adds into S.acc2[e], S.acc3[e], S.m1[e].
 __device__ __forceinline__ void walk_link(BuildSmem& S, const int64_t* __restrict__ rowptr,
-                                          const int32_t* __restrict__ col, int64_t j, int order, int q0, int warp,
-                                          int lane, uint32_t& m1_out) {
-    unsigned* acc2 = S.acc2[warp];
-    unsigned* acc3 = S.acc3[warp];
-    acc2[lane] = 0;
-    acc3[lane] = 0;
-    __syncwarp();
-    m1_out = probe<DIRECT>(S, col, q0, (uint32_t)j);
-    if (order >= 2) {
-        int64_t rs_j = ldg_i64(rowptr + j);
-        int64_t dj = ldg_i64(rowptr + j + 1) - rs_j;
-        for (int64_t base = 0; base < dj; base += 32) {
-            int64_t o = base + lane;
-            int32_t m = -1;
-            int64_t rs_m = 0;
-            int dm = 0;
-            if (o < dj) {
-                m = ldg_i32(col + rs_j + o);
-                add_bits(acc2, probe<DIRECT>(S, col, q0, (uint32_t)m));
-                if (order >= 3) {
-                    rs_m = ldg_i64(rowptr + m);
-                    dm = (int)(ldg_i64(rowptr + m + 1) - rs_m);
-                }
-            }
+                                          const int32_t* __restrict__ col, int64_t j, int order, int e, int rank,
+                                          int nw, int lane) {
+    const uint2* table = S.table;
+    if (rank == 0) {
+        const uint32_t m1 = ht_lookup(table, (uint32_t)j);
+        if (lane == 0 && m1) atomicOr(&S.m1[e], m1);
+    }
+    if (order < 2) return;
+    const int64_t rs_j = ldg_i64(rowptr + j);
+    const int64_t dj = ldg_i64(rowptr + j + 1) - rs_j;
+    Sliced cnt;
+    sliced_zero(cnt);
+    int blk = 0;
+    for (int64_t base = 0; base < dj; base += 32, ++blk) {
+        const int64_t o = base + lane;
+        int32_t m = -1;
+        int64_t rs_m = 0;
+        int dm = 0;
+        if (o < dj) {
+            m = ldg_i32(col + rs_j + o);
             if (order >= 3) {
-                int cnt = (int)((dj - base) < 32 ? (dj - base) : 32);
-                for (int u = 0; u < cnt; ++u) {
-                    int64_t rs = __shfl_sync(0xffffffffu, rs_m, u);
-                    int d = __shfl_sync(0xffffffffu, dm, u);
-                    for (int oo = lane; oo < d; oo += 32) {
-                        int32_t l = ldg_i32(col + rs + oo);
-                        add_bits(acc3, probe<DIRECT>(S, col, q0, (uint32_t)l));
-                    }
+                rs_m = ldg_i64(rowptr + m);
+                dm = (int)(ldg_i64(rowptr + m + 1) - rs_m);
+            }
+        }
+        const bool mine = (blk % nw) == rank;
+        if (mine && m >= 0) add_bits(S.acc2[e], ht_lookup(table, (uint32_t)m));
+        if (order < 3) continue;
+        // short rows: one row per lane, all of them at once
+        if (mine) {
+            const bool is_short = m >= 0 && dm <= kShortRow;
+            if (__any_sync(0xffffffffu, is_short)) {
+                uint32_t mk[8];
+                int32_t l[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) l[u] = (is_short && u < dm) ? ldg_i32(col + rs_m + u) : -1;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) mk[u] = l[u] >= 0 ? ht_lookup(table, (uint32_t)l[u]) : 0u;
+                sliced_add8(cnt, mk);
+            }
+        }
+        // long rows: the cooperating warps stride over each row, 8 x 32 columns per iteration
+        unsigned longmask = __ballot_sync(0xffffffffu, m >= 0 && dm > kShortRow);
+        while (longmask) {
+            const int u = __ffs(longmask) - 1;
+            longmask &= longmask - 1;
+            const int64_t rs = __shfl_sync(0xffffffffu, rs_m, u);
+            const int d = __shfl_sync(0xffffffffu, dm, u);
+            const int first = (rank + nw - (u % nw)) % nw;  // rotate so medium rows spread over the warps
+            for (int b2 = first * 256; b2 < d; b2 += nw * 256) {
+                uint32_t mk[8];
+                int32_t l[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int idx = b2 + k * 32 + lane;
+                    l[k] = idx < d ? ldg_i32(col + rs + idx) : -1;
                 }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) mk[k] = l[k] >= 0 ? ht_lookup(table, (uint32_t)l[k]) : 0u;
+                sliced_add8(cnt, mk);
             }
         }
     }
-    __syncwarp();
+    if (order >= 3) {
+        const uint32_t total = sliced_flush(cnt, lane);
+        if (total) atomicAdd(&S.acc3[e][lane], total);
+    }
 }
 
-__global__ void __launch_bounds__(kBuildThreads)
+__global__ void __launch_bounds__(kBuildThreads, 2)
 k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
            const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t batch_size, int order,
            int weighted, const int64_t* __restrict__ rec_off, const int32_t* __restrict__ run_start,
@@ -139,10 +232,9 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
         __syncthreads();
         const int64_t unit = S.unit;
         if (unit >= n_units) break;
-        // run = last r with run_unit_off[r] <= unit
-        int64_t lo = 0, hi = n_runs;
+        int64_t lo = 0, hi = n_runs;  // run = last r with run_unit_off[r] <= unit
         while (hi - lo > 1) {
-            int64_t mid = (lo + hi) >> 1;
+            const int64_t mid = (lo + hi) >> 1;
             if (run_unit_off[mid] <= unit) lo = mid; else hi = mid;
         }
         const int64_t r = lo;
@@ -159,76 +251,102 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
         const int ne = (int)((t0 + len - e0) < kEdgeSub ? (t0 + len - e0) : kEdgeSub);
         const int64_t batch = t0 / batch_size;
 
-        if (tid < 32) {
-            S.tot1[tid] = 0;
-            S.tot2[tid] = 0;
-            S.tot3[tid] = 0;
-            if (tid < np) {
-                int32_t k = col[rs_i + p0 + tid];
-                int64_t krs = rowptr[k];
-                S.kp[tid] = k;
-                S.krs[tid] = krs;
-                S.kdeg[tid] = (int)(rowptr[k + 1] - krs);
+        if (warp == 0) {
+            S.tot1[lane] = 0;
+            S.tot2[lane] = 0;
+            S.tot3[lane] = 0;
+            int kd = 0;
+            if (lane < np) {
+                const int32_t k = col[rs_i + p0 + lane];
+                const int64_t krs = rowptr[k];
+                kd = (int)(rowptr[k + 1] - krs);
+                S.kp[lane] = k;
+                S.krs[lane] = krs;
+                S.kdeg[lane] = kd;
+            }
+            int incl = kd;  // inclusive warp scan of the row lengths
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            S.kpre[lane] = incl - kd;
+            if (lane == 31) S.kpre[32] = incl;
+        }
+        for (int s = tid; s < kEdgeSub * 32; s += kBuildThreads) {
+            (&S.acc2[0][0])[s] = 0u;
+            (&S.acc3[0][0])[s] = 0u;
+        }
+        if (tid < kEdgeSub) S.m1[tid] = 0u;
+        __syncthreads();
+        const int total_keys = S.kpre[32];
+        const int npass = total_keys > 0 ? (total_keys + kCap - 1) / kCap : 1;
+
+        for (int pass = 0; pass < npass; ++pass) {
+            __syncthreads();
+            for (int s = tid; s < kSlots / 2; s += kBuildThreads)
+                reinterpret_cast<uint4*>(S.table)[s] = make_uint4(kEmpty, 0u, kEmpty, 0u);
+            if (tid == 0) S.n_heavy = 0;
+            __syncthreads();
+            const int k_lo = pass * kCap, k_hi = (k_lo + kCap < total_keys) ? k_lo + kCap : total_keys;
+            for (int idx = k_lo + tid; idx < k_hi; idx += kBuildThreads) {
+                int a = 0, b = np;  // last position a with kpre[a] <= idx
+                while (b - a > 1) {
+                    const int mid = (a + b) >> 1;
+                    if (S.kpre[mid] <= idx) a = mid; else b = mid;
+                }
+                const int32_t l = ldg_i32(col + S.krs[a] + (idx - S.kpre[a]));
+                ht_insert(S.table, (uint32_t)l, 1u << a);
+            }
+            __syncthreads();
+            if (ne >= kBuildWarps && order >= 3) {
+                // one warp per link; links with a large frontier are deferred to the whole CTA
+                for (int e = warp; e < ne; e += kBuildWarps) {
+                    const int64_t j = dst[e0 + e];
+                    const int64_t rs_j = ldg_i64(rowptr + j);
+                    const int64_t dj = ldg_i64(rowptr + j + 1) - rs_j;
+                    long long fr = 0;
+                    for (int64_t o = lane; o < dj; o += 32) {
+                        const int32_t m = ldg_i32(col + rs_j + o);
+                        fr += ldg_i64(rowptr + m + 1) - ldg_i64(rowptr + m);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) fr += __shfl_xor_sync(0xffffffffu, fr, o);
+                    if (fr > kHeavyFrontier) {
+                        if (lane == 0) S.heavy[atomicAdd(&S.n_heavy, 1)] = e;
+                    } else {
+                        walk_link(S, rowptr, col, j, order, e, 0, 1, lane);
+                    }
+                }
+            } else if (order < 3) {
+                for (int e = warp; e < ne; e += kBuildWarps) walk_link(S, rowptr, col, dst[e0 + e], order, e, 0, 1, lane);
+            } else {
+                if (tid < ne) S.heavy[tid] = tid;
+                if (tid == 0) S.n_heavy = ne;
+            }
+            __syncthreads();
+            const int nh = S.n_heavy;
+            for (int h = 0; h < nh; ++h) {
+                const int e = S.heavy[h];
+                walk_link(S, rowptr, col, dst[e0 + e], order, e, warp, kBuildWarps, lane);
             }
         }
-        int q0 = 0;
-        while (q0 < np) {
-            __syncthreads();
-            if (tid == 0) {
-                int q = q0, sum = 0, direct = 0;
-                if (S.kdeg[q0] > kCap) {
-                    direct = 1;
-                    q = q0 + 1;
-                } else {
-                    while (q < np && sum + S.kdeg[q] <= kCap) {
-                        S.kpre[q] = sum;
-                        sum += S.kdeg[q];
-                        ++q;
-                    }
-                    S.kpre[q] = sum;
-                }
-                S.q1 = q;
-                S.direct = direct;
-            }
-            for (int s = tid; s < kSlots; s += kBuildThreads) S.table[s] = make_uint2(kEmpty, 0u);
-            __syncthreads();
-            const int q1 = S.q1;
-            const bool direct = S.direct != 0;
-            if (!direct) {
-                const int total = S.kpre[q1];
-                for (int idx = tid; idx < total; idx += kBuildThreads) {
-                    int a = q0, b = q1;  // last q in [q0,q1) with kpre[q] <= idx
-                    while (b - a > 1) {
-                        int mid = (a + b) >> 1;
-                        if (S.kpre[mid] <= idx) a = mid; else b = mid;
-                    }
-                    int32_t l = ldg_i32(col + S.krs[a] + (idx - S.kpre[a]));
-                    ht_insert(S.table, (uint32_t)l, 1u << a);
+        __syncthreads();
+        // records and per-unit column totals
+        for (int s = tid; s < ne * 32; s += kBuildThreads) {
+            const int e = s >> 5, p = s & 31;
+            if (p < np) {
+                const unsigned c1 = (S.m1[e] >> p) & 1u;
+                const unsigned c2 = S.acc2[e][p], c3 = S.acc3[e][p];
+                records[rec_off[e0 + e] + p0 + p] = make_uint2(c2 | (c1 << 31), c3);
+                if (colstat != nullptr) {
+                    if (c1) atomicAdd(&S.tot1[p], 1u);
+                    const unsigned long long v2 = weighted ? c2 : (c2 ? 1u : 0u);
+                    const unsigned long long v3 = weighted ? c3 : (c3 ? 1u : 0u);
+                    if (v2) atomicAdd(&S.tot2[p], v2);
+                    if (v3) atomicAdd(&S.tot3[p], v3);
                 }
             }
-            __syncthreads();
-            for (int e = warp; e < ne; e += kBuildWarps) {
-                const int64_t t = e0 + e;
-                const int64_t j = dst[t];
-                uint32_t m1;
-                if (direct) walk_link<true>(S, rowptr, col, j, order, q0, warp, lane, m1);
-                else walk_link<false>(S, rowptr, col, j, order, q0, warp, lane, m1);
-                if (lane >= q0 && lane < q1) {
-                    unsigned c1 = (m1 >> lane) & 1u;
-                    unsigned c2 = S.acc2[warp][lane];
-                    unsigned c3 = S.acc3[warp][lane];
-                    records[rec_off[t] + p0 + lane] = make_uint2(c2 | (c1 << 31), c3);
-                    if (colstat != nullptr) {
-                        if (c1) atomicAdd(&S.tot1[lane], 1u);
-                        unsigned long long v2 = weighted ? c2 : (c2 ? 1u : 0u);
-                        unsigned long long v3 = weighted ? c3 : (c3 ? 1u : 0u);
-                        if (v2) atomicAdd(&S.tot2[lane], v2);
-                        if (v3) atomicAdd(&S.tot3[lane], v3);
-                    }
-                }
-                __syncwarp();
-            }
-            q0 = q1;
         }
         __syncthreads();
         if (colstat != nullptr && tid < np) {
@@ -258,7 +376,7 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
     OCN_CUDA(cudaFuncSetAttribute(k_cn_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BuildSmem)));
     // restart the dynamic unit counter (plan[4])
     OCN_CUDA(cudaMemsetAsync((void*)(plan + 4), 0, sizeof(int64_t), st));
-    int blocks = sm_count() * 3;
+    const int blocks = sm_count() * 2;
     k_cn_build<<<blocks, kBuildThreads, sizeof(BuildSmem), st>>>(
         rowptr, col, n, src, dst, batch_size, order, weighted, (const int64_t*)(base + L.rec_off),
         (const int32_t*)(base + L.run_start), (const int64_t*)(base + L.run_unit_off), (int64_t*)plan,
