@@ -118,13 +118,13 @@ def algorithmic_bytes(G, e, order, feat, batch):
     chunks = torch.div(di + 31, 32, rounding_mode="floor").clamp(min=0)
     per_link_j = 16 + (4 * dj if order >= 2 else 0) + ((8 * dj + 4 * Fj) if order >= 3 else 0)
     j_bytes = int((per_link_j * chunks.clamp(min=1)).sum())
-    # i side, once per work unit (run x chunk x 16-link sub-list): N(i) chunk, its rowptr pairs, its rows
+    # i side, once per work unit (run x chunk x 32-link sub-list): N(i) chunk, its rowptr pairs, its rows
     t = torch.arange(T, device=e.device)
     first = (t % batch == 0) | (torch.cat((i[:1] - 1, i[:-1])) != i)
     run_id = torch.cumsum(first.long(), 0) - 1
     run_len = torch.bincount(run_id)
     run_src = i[first]
-    subs = torch.div(run_len + 15, 16, rounding_mode="floor")
+    subs = torch.div(run_len + 31, 32, rounding_mode="floor")
     i_bytes = int((subs * (16 + 12 * deg[run_src] + 4 * Fv[run_src])).sum())
     rec_bytes = int(8 * di.sum())
     build = j_bytes + i_bytes + rec_bytes + 16 * T

@@ -115,7 +115,7 @@ class CNSession:
         self.plan_scratch = torch.empty(self.plan_bytes, dtype=torch.uint8, device=self.dev)
         self.plan = torch.zeros(PLAN_WORDS, dtype=torch.int64, device=self.dev)
         with torch.cuda.device(self.dev):
-            _lib.check(L.ocn_cn_plan(_lib.ptr(graph.rowptr), graph.n, _lib.ptr(self.src), _lib.ptr(self.dst), self.T,
+            _lib.check(L.ocn_cn_plan(_lib.ptr(graph.rowptr), _lib.ptr(graph.col), graph.n, _lib.ptr(self.src), _lib.ptr(self.dst), self.T,
                                      self.batch_size, _lib.ptr(self.plan_scratch), self.plan_bytes,
                                      _lib.ptr(self.plan), _stream(self.dev)), "ocn_cn_plan")
         host = self.plan.tolist()  # the one host sync of the session: buffer sizes

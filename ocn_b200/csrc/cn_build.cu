@@ -6,132 +6,126 @@
 //     C1[p] = bit p of mask_i(j)
 //     C2[p] = #{ m in N(j)               : bit p of mask_i(m) }      (= A^2[j, N(i)[p]])
 //     C3[p] = #{ m in N(j), l in N(m)    : bit p of mask_i(l) }      (= A^3[j, N(i)[p]])
-// so one shared-memory hash table  l -> mask_i(l)  (built once per run of links that share the
-// source i) turns the whole computation into a 3-level walk from j with one table probe per
-// visited node.
+// so a shared-memory hash table  l -> mask_i(l)  (built once per group of links that share the
+// source i) turns the whole computation into a 3-level walk from j with one probe per visited node.
 //
-// Work unit = (run, 32 positions of N(i), <= kEdgeSub links), scheduled dynamically (cn_plan.cu).
-// The 32 rows N(N(i)[p]) are inserted as one flattened list; if it exceeds the table capacity the
-// unit makes several passes (table = next slice of the list, j-side walked again) and sums the
-// per-position counts in shared memory, so a hub next to the source needs no special case.
+// Work unit = (run of links with one source, 32 positions of N(i), table pass, <= kEdgeSub links),
+// handed out dynamically (cn_plan.cu).  The 32 rows N(N(i)[p]) form one flattened key list; pass q
+// holds keys [q*kCap, (q+1)*kCap) of it, so hubs next to the source need no special case.  Units
+// add their partial counts into the records with global atomics (records are zeroed first).
 //
-// The j-side frontier is streamed row by row, 8 x 32 columns per warp iteration (8 independent
-// 128-byte loads in flight per warp); the 32 per-position counters of every lane are kept
-// bit-sliced in registers and updated with carry-save adders (~9 ALU ops per probed column, no
-// shared-memory atomics on the hot path).  Links with a large frontier are walked by all warps of
-// the CTA, the others by one warp each.
+// Inside a unit
+//   * the table is paired with a 128 Kbit one-hash Bloom filter: > 90 % of the frontier misses the
+//     table (measured hit rate 0-8 %), and a miss costs one branch-free shared-memory bit test;
+//   * columns that pass the filter are compacted into a per-warp queue and looked up 32 at a time,
+//     so the divergent probe loops run with all lanes busy;
+//   * rows of the j-side frontier are pulled by the warps from a shared counter (row granularity),
+//     rows longer than kLongRow are deferred and then strided over by all warps of the CTA, so the
+//     heavy-tailed row lengths do not stall the CTA at a barrier;
+//   * frontier rows are streamed 8 x 32 columns per warp iteration: eight independent 128-byte
+//     loads in flight per warp.
 #include "common.cuh"
 
 namespace ocn {
 
 constexpr int kBuildThreads = 512;
 constexpr int kBuildWarps = kBuildThreads / 32;
-constexpr int kSlots = 13312;                  // 104 KB of (key, mask) pairs -> 2 CTAs / SM
-constexpr int kCap = (kSlots * 5) / 8;         // keys inserted per pass (load factor 0.625)
 constexpr uint32_t kEmpty = 0xffffffffu;
-constexpr int kHiPlanes = 17;                  // bit-sliced counter: 3 + 17 planes (< 2^20 per lane)
-constexpr int kShortRow = 8;                   // rows this short are walked one per lane
-constexpr int kHeavyFrontier = 12288;          // links above this frontier size use the whole CTA
+constexpr int kFilterBits = 17;                       // 131072-bit filter (16 KB)
+constexpr int kFilterWords = 1 << (kFilterBits - 5);
+constexpr int kQueue = 128;                           // per-warp queue of filter survivors
+constexpr int kLongRow = 2048;                        // rows longer than this are walked by the whole CTA
+constexpr int kMaxLong = 192;                         // deferred long rows per pass before an early flush
 
 struct BuildSmem {
-    uint2 table[kSlots];
+    uint2 table[kSlots + 7];
+    uint32_t filter[kFilterWords];
+    uint32_t qkey[kBuildWarps][kQueue];
     unsigned acc2[kEdgeSub][32];
     unsigned acc3[kEdgeSub][32];
-    unsigned long long tot2[32];
-    unsigned long long tot3[32];
+    long long lrs[kMaxLong];
     long long krs[32];
-    unsigned tot1[32];
-    unsigned m1[kEdgeSub];
-    int heavy[kEdgeSub];
+    long long jrs[kEdgeSub];
+    int ld[kMaxLong];
+    int le[kMaxLong];
     int kp[32];
     int kdeg[32];
     int kpre[33];
+    int jdeg[kEdgeSub];
+    int jpre[kEdgeSub + 1];
+    unsigned m1[kEdgeSub];
     long long unit;
-    int n_heavy;
+    int chunk, pass;
+    int next_item;
+    int n_long;
 };
 
-__device__ __forceinline__ uint32_t ht_home(uint32_t key) {
-    return __umulhi(key * 2654435769u, (uint32_t)kSlots);
+// queue entries carry the link slot in their top bits: node ids must stay below 2^kTagShift
+constexpr int kTagShift = 27;
+static_assert(kEdgeSub <= (1 << (32 - kTagShift)), "link slot does not fit the queue tag");
+
+// explicit shared-window accesses (32-bit shared addresses): keeps the hot loops free of the
+// generic-to-shared base recomputation the compiler otherwise emits per access
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ void ht_insert(uint2* table, uint32_t key, uint32_t bit) {
+struct SAddr {  // shared-window byte addresses of the hot structures
+    uint32_t table, filter, queue;
+};
+
+// double hashing on a prime-size table: home slot and a key-dependent step in [1, kSlots-1]
+__device__ __forceinline__ uint32_t ht_home(uint32_t key) { return __umulhi(key * 2654435769u, (uint32_t)kSlots); }
+__device__ __forceinline__ uint32_t ht_step(uint32_t key) { return 1u + __umulhi(key * 0xc2b2ae35u, (uint32_t)(kSlots - 1)); }
+
+// blocked 2-bit Bloom filter: one 32-bit word per key, two bits inside it
+__device__ __forceinline__ uint32_t flt_hash(uint32_t key) { return key * 0x85ebca6bu; }
+__device__ __forceinline__ uint32_t flt_word(uint32_t h) { return (h >> (32 - (kFilterBits - 5))) << 2; }  // byte offset
+__device__ __forceinline__ uint32_t flt_need(uint32_t h) { return (1u << ((h >> 13) & 31)) | (1u << ((h >> 8) & 31)); }
+
+__device__ __forceinline__ void ht_insert(BuildSmem& S, uint32_t key, uint32_t bit) {
+    const uint32_t h = flt_hash(key);
+    atomicOr(&S.filter[flt_word(h) >> 2], flt_need(h));
     uint32_t slot = ht_home(key);
+    const uint32_t step = ht_step(key);
     while (true) {
-        uint32_t prev = atomicCAS(&table[slot].x, kEmpty, key);
+        const uint32_t prev = atomicCAS(&S.table[slot].x, kEmpty, key);
         if (prev == kEmpty || prev == key) {
-            atomicOr(&table[slot].y, bit);
+            atomicOr(&S.table[slot].y, bit);
             return;
         }
-        slot = (slot + 1 == (uint32_t)kSlots) ? 0u : slot + 1;
+        slot += step;
+        if (slot >= (uint32_t)kSlots) slot -= (uint32_t)kSlots;
     }
 }
 
-__device__ __forceinline__ uint32_t ht_lookup(const uint2* table, uint32_t key) {
+__device__ __forceinline__ uint32_t ht_lookup(uint32_t stable, uint32_t key) {
     uint32_t slot = ht_home(key);
+    const uint32_t step = ht_step(key);
     while (true) {
-        const uint2 e = table[slot];
+        const uint2 e = lds64(stable + slot * 8u);
         if (e.x == key) return e.y;
         if (e.x == kEmpty) return 0u;
-        slot = (slot + 1 == (uint32_t)kSlots) ? 0u : slot + 1;
+        slot += step;
+        if (slot >= (uint32_t)kSlots) slot -= (uint32_t)kSlots;
     }
 }
 
-// ---- bit-sliced per-position counters ---------------------------------------------------------
-struct Sliced {
-    uint32_t ones, twos, fours;
-    uint32_t hi[kHiPlanes];  // hi[b] has weight 8 << b
-};
-
-__device__ __forceinline__ void sliced_zero(Sliced& s) {
-    s.ones = s.twos = s.fours = 0u;
-#pragma unroll
-    for (int b = 0; b < kHiPlanes; ++b) s.hi[b] = 0u;
-}
-
-// carry-save adder: (h, l) = a + b + c bitwise
-__device__ __forceinline__ void csa(uint32_t& h, uint32_t& l, uint32_t a, uint32_t b, uint32_t c) {
-    const uint32_t u = a ^ b;
-    h = (a & b) | (u & c);
-    l = u ^ c;
-}
-
-// add eight 32-position masks to the counters
-__device__ __forceinline__ void sliced_add8(Sliced& s, const uint32_t (&m)[8]) {
-    uint32_t t0, t1, t2, t3, f0, f1, e0;
-    csa(t0, s.ones, s.ones, m[0], m[1]);
-    csa(t1, s.ones, s.ones, m[2], m[3]);
-    csa(f0, s.twos, s.twos, t0, t1);
-    csa(t2, s.ones, s.ones, m[4], m[5]);
-    csa(t3, s.ones, s.ones, m[6], m[7]);
-    csa(f1, s.twos, s.twos, t2, t3);
-    csa(e0, s.fours, s.fours, f0, f1);
-    uint32_t carry = e0;
-#pragma unroll
-    for (int b = 0; b < kHiPlanes; ++b) {
-        const uint32_t t = s.hi[b] & carry;
-        s.hi[b] ^= carry;
-        carry = t;
-    }
-}
-
-// lane p receives the sum over all lanes of position p's counter
-__device__ __forceinline__ uint32_t plane_sum(uint32_t word, int lane) {
-    uint32_t tot = 0;
-    if (__any_sync(0xffffffffu, word != 0u)) {
-#pragma unroll
-        for (int p = 0; p < 32; ++p) {
-            const uint32_t bal = __ballot_sync(0xffffffffu, (word >> p) & 1u);
-            if (lane == p) tot = __popc(bal);
-        }
-    }
-    return tot;
-}
-
-__device__ __forceinline__ uint32_t sliced_flush(const Sliced& s, int lane) {
-    uint32_t total = plane_sum(s.ones, lane) + 2u * plane_sum(s.twos, lane) + 4u * plane_sum(s.fours, lane);
-#pragma unroll
-    for (int b = 0; b < kHiPlanes; ++b) total += plane_sum(s.hi[b], lane) << (3 + b);
-    return total;
+// branch-free: an invalid column (key = 0xffffffff, valid = false) still reads an in-range word
+__device__ __forceinline__ bool flt_test(uint32_t sfilter, uint32_t key) {
+    const uint32_t h = flt_hash(key);
+    const uint32_t w = lds32(sfilter + flt_word(h));
+    return ((w >> ((h >> 13) & 31)) & (w >> ((h >> 8) & 31)) & 1u) != 0u;
 }
 
 __device__ __forceinline__ void add_bits(unsigned* acc, uint32_t mask) {
@@ -142,89 +136,120 @@ __device__ __forceinline__ void add_bits(unsigned* acc, uint32_t mask) {
     }
 }
 
-// Walk the frontier of link slot `e` (destination j) with `nw` cooperating warps, this one being
-// `rank`.  Adds into S.acc2[e], S.acc3[e], S.m1[e].
-__device__ __forceinline__ void walk_link(BuildSmem& S, const int64_t* __restrict__ rowptr,
-                                          const int32_t* __restrict__ col, int64_t j, int order, int e, int rank,
-                                          int nw, int lane) {
-    const uint2* table = S.table;
-    if (rank == 0) {
-        const uint32_t m1 = ht_lookup(table, (uint32_t)j);
-        if (lane == 0 && m1) atomicOr(&S.m1[e], m1);
+// look up the first `count` (<= 32) queue entries of this warp, one per lane
+__device__ __forceinline__ void q_lookup(BuildSmem& S, const SAddr& A, uint32_t sq, int lane, int count) {
+    if (lane < count) {
+        const uint32_t w = lds32(sq + lane * 4u);
+        add_bits(S.acc3[w >> kTagShift], ht_lookup(A.table, w & ((1u << kTagShift) - 1u)));
     }
-    if (order < 2) return;
-    const int64_t rs_j = ldg_i64(rowptr + j);
-    const int64_t dj = ldg_i64(rowptr + j + 1) - rs_j;
-    Sliced cnt;
-    sliced_zero(cnt);
-    int blk = 0;
-    for (int64_t base = 0; base < dj; base += 32, ++blk) {
-        const int64_t o = base + lane;
-        int32_t m = -1;
-        int64_t rs_m = 0;
-        int dm = 0;
-        if (o < dj) {
-            m = ldg_i32(col + rs_j + o);
-            if (order >= 3) {
-                rs_m = ldg_i64(rowptr + m);
-                dm = (int)(ldg_i64(rowptr + m + 1) - rs_m);
-            }
+}
+
+// after a push: while at least 32 entries are queued, look 32 of them up and shift the rest down
+__device__ __forceinline__ void q_service(BuildSmem& S, const SAddr& A, uint32_t sq, int lane, int& tail) {
+    while (tail >= 32) {
+        __syncwarp();
+        q_lookup(S, A, sq, lane, 32);
+        __syncwarp();
+        const int rem = tail - 32;
+        for (int base = 0; base < rem; base += 32) {  // move entries [32, tail) to the front, 32 at a time
+            uint32_t k = 0;
+            if (base + lane < rem) k = lds32(sq + (32 + base + lane) * 4u);
+            __syncwarp();
+            if (base + lane < rem) sts32(sq + (base + lane) * 4u, k);
         }
-        const bool mine = (blk % nw) == rank;
-        if (mine && m >= 0) add_bits(S.acc2[e], ht_lookup(table, (uint32_t)m));
-        if (order < 3) continue;
-        // short rows: one row per lane, all of them at once
-        if (mine) {
-            const bool is_short = m >= 0 && dm <= kShortRow;
-            if (__any_sync(0xffffffffu, is_short)) {
-                uint32_t mk[8];
-                int32_t l[8];
+        tail = rem;
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void q_drain(BuildSmem& S, const SAddr& A, uint32_t sq, int lane, int& tail) {
+    q_service(S, A, sq, lane, tail);
+    __syncwarp();
+    q_lookup(S, A, sq, lane, tail);
+    __syncwarp();
+    tail = 0;
+}
+
+// stream columns [start, d) of one frontier row with stride `stride` (both multiples of 256),
+// push the filter survivors of link slot e into this warp's queue
+__device__ __forceinline__ void walk_row(BuildSmem& S, const SAddr& A, uint32_t sq, const int32_t* __restrict__ col,
+                                         int64_t rs, int d, int e, int start, int stride, int lane, int& tail) {
+    const uint32_t tag = (uint32_t)e << kTagShift;
+    for (int b2 = start; b2 < d; b2 += stride) {
+        int32_t l[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) l[u] = (is_short && u < dm) ? ldg_i32(col + rs_m + u) : -1;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) mk[u] = l[u] >= 0 ? ht_lookup(table, (uint32_t)l[u]) : 0u;
-                sliced_add8(cnt, mk);
-            }
+        for (int k = 0; k < 8; ++k) {
+            const int idx = b2 + k * 32 + lane;
+            l[k] = idx < d ? ldg_i32(col + rs + idx) : -1;
         }
-        // long rows: the cooperating warps stride over each row, 8 x 32 columns per iteration
-        unsigned longmask = __ballot_sync(0xffffffffu, m >= 0 && dm > kShortRow);
-        while (longmask) {
-            const int u = __ffs(longmask) - 1;
-            longmask &= longmask - 1;
-            const int64_t rs = __shfl_sync(0xffffffffu, rs_m, u);
-            const int d = __shfl_sync(0xffffffffu, dm, u);
-            const int first = (rank + nw - (u % nw)) % nw;  // rotate so medium rows spread over the warps
-            for (int b2 = first * 256; b2 < d; b2 += nw * 256) {
-                uint32_t mk[8];
-                int32_t l[8];
+        unsigned flags = 0u;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int idx = b2 + k * 32 + lane;
-                    l[k] = idx < d ? ldg_i32(col + rs + idx) : -1;
+        for (int k = 0; k < 8; ++k) {
+            const unsigned pass = (unsigned)flt_test(A.filter, (uint32_t)l[k]) & (unsigned)(l[k] >= 0);
+            flags |= pass << k;
+        }
+        if (!__any_sync(0xffffffffu, flags != 0u)) continue;
+        // exclusive warp scan of the per-lane survivor counts
+        const int cnt = __popc(flags);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (tail + total <= kQueue) {
+            uint32_t off = sq + (uint32_t)(tail + incl - cnt) * 4u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (flags & (1u << k)) {
+                    sts32(off, (uint32_t)l[k] | tag);
+                    off += 4u;
                 }
+            }
+            tail += total;
+            q_service(S, A, sq, lane, tail);
+        } else {
+            // rare: more survivors than queue space; push one column slot at a time
 #pragma unroll
-                for (int k = 0; k < 8; ++k) mk[k] = l[k] >= 0 ? ht_lookup(table, (uint32_t)l[k]) : 0u;
-                sliced_add8(cnt, mk);
+            for (int k = 0; k < 8; ++k) {
+                const bool p = (flags >> k) & 1u;
+                const unsigned bal = __ballot_sync(0xffffffffu, p);
+                if (p) sts32(sq + (uint32_t)(tail + __popc(bal & ((1u << lane) - 1u))) * 4u, (uint32_t)l[k] | tag);
+                tail += __popc(bal);
+                q_service(S, A, sq, lane, tail);
             }
         }
     }
-    if (order >= 3) {
-        const uint32_t total = sliced_flush(cnt, lane);
-        if (total) atomicAdd(&S.acc3[e][lane], total);
+}
+
+// all warps of the CTA stride over the deferred long rows
+__device__ __forceinline__ void flush_long_rows(BuildSmem& S, const SAddr& A, uint32_t sq,
+                                                const int32_t* __restrict__ col, int warp, int lane, int& tail) {
+    const int nl = S.n_long < kMaxLong ? S.n_long : kMaxLong;
+    for (int r = 0; r < nl; ++r) {
+        const int first = (warp + kBuildWarps - (r % kBuildWarps)) % kBuildWarps;
+        walk_row(S, A, sq, col, S.lrs[r], S.ld[r], S.le[r], first * 256, kBuildWarps * 256, lane, tail);
     }
 }
 
 __global__ void __launch_bounds__(kBuildThreads, 2)
 k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
-           const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t batch_size, int order,
-           int weighted, const int64_t* __restrict__ rec_off, const int32_t* __restrict__ run_start,
-           const int64_t* __restrict__ run_unit_off, int64_t* __restrict__ plan, Record* __restrict__ records,
-           ColStat* __restrict__ colstat) {
+           const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int order,
+           const int64_t* __restrict__ rec_off, const int32_t* __restrict__ run_start,
+           const int64_t* __restrict__ run_unit_off, int64_t* __restrict__ plan, Record* __restrict__ records) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BuildSmem& S = *reinterpret_cast<BuildSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    SAddr A;
+    A.table = sbase + (uint32_t)offsetof(BuildSmem, table);
+    A.filter = sbase + (uint32_t)offsetof(BuildSmem, filter);
+    A.queue = sbase + (uint32_t)offsetof(BuildSmem, qkey);
+    const uint32_t sq = A.queue + (uint32_t)warp * (kQueue * 4u);
     const int64_t n_units = plan[OCN_PLAN_NUM_UNITS];
     const int64_t n_runs = plan[OCN_PLAN_NUM_RUNS];
+    int tail = 0;  // this warp's queue fill (warp-uniform)
 
     while (true) {
         __syncthreads();
@@ -244,116 +269,182 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
         const int64_t rs_i = rowptr[i];
         const int64_t d = rowptr[i + 1] - rs_i;
         const int64_t n_es = (len + kEdgeSub - 1) / kEdgeSub;
-        const int64_t pc = local / n_es, es = local - pc * n_es;
-        const int64_t p0 = pc * kPChunk;
-        const int np = (int)((d - p0) < kPChunk ? (d - p0) : kPChunk);
+        const int64_t q = local / n_es, es = local - q * n_es;  // q = global pass index of this run
         const int64_t e0 = t0 + es * kEdgeSub;
         const int ne = (int)((t0 + len - e0) < kEdgeSub ? (t0 + len - e0) : kEdgeSub);
-        const int64_t batch = t0 / batch_size;
 
+        // warp 0: locate (chunk, pass) of q by walking the chunks of N(i); load the chunk's rows
         if (warp == 0) {
-            S.tot1[lane] = 0;
-            S.tot2[lane] = 0;
-            S.tot3[lane] = 0;
-            int kd = 0;
-            if (lane < np) {
-                const int32_t k = col[rs_i + p0 + lane];
-                const int64_t krs = rowptr[k];
-                kd = (int)(rowptr[k + 1] - krs);
-                S.kp[lane] = k;
-                S.krs[lane] = krs;
-                S.kdeg[lane] = kd;
+            int64_t rem = q;
+            int chunk = 0;
+            while (true) {
+                const int64_t p = (int64_t)chunk * kPChunk + lane;
+                int kd = 0, k = 0;
+                long long krs = 0;
+                if (p < d) {
+                    k = col[rs_i + p];
+                    krs = rowptr[k];
+                    kd = (int)(rowptr[k + 1] - krs);
+                }
+                int incl = kd;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                const int np_pass = (tot + kCap - 1) / kCap;
+                if (rem < np_pass || (int64_t)(chunk + 1) * kPChunk >= d) {
+                    S.kp[lane] = k;
+                    S.krs[lane] = krs;
+                    S.kdeg[lane] = kd;
+                    S.kpre[lane] = incl - kd;
+                    if (lane == 31) S.kpre[32] = incl;
+                    if (lane == 0) { S.chunk = chunk; S.pass = (int)rem; }
+                    break;
+                }
+                rem -= np_pass;
+                ++chunk;
             }
-            int incl = kd;  // inclusive warp scan of the row lengths
+        }
+        // warp 1: the links of this unit
+        if (warp == 1) {
+            int dj = 0;
+            if (lane < ne) {
+                const int64_t j = dst[e0 + lane];
+                const int64_t rs_j = rowptr[j];
+                dj = (order >= 2) ? (int)(rowptr[j + 1] - rs_j) : 0;
+                S.jrs[lane] = rs_j;
+                S.jdeg[lane] = dj;
+                S.m1[lane] = 0u;
+            }
+            int incl = dj;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += v;
             }
-            S.kpre[lane] = incl - kd;
-            if (lane == 31) S.kpre[32] = incl;
+            S.jpre[lane] = incl - dj;
+            if (lane == 31) S.jpre[kEdgeSub] = incl;
         }
         for (int s = tid; s < kEdgeSub * 32; s += kBuildThreads) {
             (&S.acc2[0][0])[s] = 0u;
             (&S.acc3[0][0])[s] = 0u;
         }
-        if (tid < kEdgeSub) S.m1[tid] = 0u;
+        for (int s = tid; s < (kSlots + 1) / 2; s += kBuildThreads)
+            reinterpret_cast<uint4*>(S.table)[s] = make_uint4(kEmpty, 0u, kEmpty, 0u);
+        for (int s = tid; s < kFilterWords; s += kBuildThreads) S.filter[s] = 0u;
+        if (tid == 0) { S.next_item = 0; S.n_long = 0; }
         __syncthreads();
-        const int total_keys = S.kpre[32];
-        const int npass = total_keys > 0 ? (total_keys + kCap - 1) / kCap : 1;
 
-        for (int pass = 0; pass < npass; ++pass) {
-            __syncthreads();
-            for (int s = tid; s < kSlots / 2; s += kBuildThreads)
-                reinterpret_cast<uint4*>(S.table)[s] = make_uint4(kEmpty, 0u, kEmpty, 0u);
-            if (tid == 0) S.n_heavy = 0;
-            __syncthreads();
-            const int k_lo = pass * kCap, k_hi = (k_lo + kCap < total_keys) ? k_lo + kCap : total_keys;
-            for (int idx = k_lo + tid; idx < k_hi; idx += kBuildThreads) {
-                int a = 0, b = np;  // last position a with kpre[a] <= idx
+        const int64_t p0 = (int64_t)S.chunk * kPChunk;
+        const int np = (int)((d - p0) < kPChunk ? (d - p0) : kPChunk);
+        const int total_keys = S.kpre[32];
+        const int k_lo = S.pass * kCap, k_hi = (k_lo + kCap < total_keys) ? k_lo + kCap : total_keys;
+        // keys [k_lo, k_hi) of the flattened list, an equal share per warp; inside a share the warp walks
+        // the rows it spans with coalesced loads (no per-key search, no barrier imbalance)
+        {
+            const int per = (k_hi - k_lo + kBuildWarps - 1) / kBuildWarps;
+            int pos = k_lo + warp * per;
+            const int end = (pos + per < k_hi) ? pos + per : k_hi;
+            if (pos < end) {
+                int a = 0, b = np;  // last row a with kpre[a] <= pos
                 while (b - a > 1) {
                     const int mid = (a + b) >> 1;
-                    if (S.kpre[mid] <= idx) a = mid; else b = mid;
+                    if (S.kpre[mid] <= pos) a = mid; else b = mid;
                 }
-                const int32_t l = ldg_i32(col + S.krs[a] + (idx - S.kpre[a]));
-                ht_insert(S.table, (uint32_t)l, 1u << a);
-            }
-            __syncthreads();
-            if (ne >= kBuildWarps && order >= 3) {
-                // one warp per link; links with a large frontier are deferred to the whole CTA
-                for (int e = warp; e < ne; e += kBuildWarps) {
-                    const int64_t j = dst[e0 + e];
-                    const int64_t rs_j = ldg_i64(rowptr + j);
-                    const int64_t dj = ldg_i64(rowptr + j + 1) - rs_j;
-                    long long fr = 0;
-                    for (int64_t o = lane; o < dj; o += 32) {
-                        const int32_t m = ldg_i32(col + rs_j + o);
-                        fr += ldg_i64(rowptr + m + 1) - ldg_i64(rowptr + m);
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) fr += __shfl_xor_sync(0xffffffffu, fr, o);
-                    if (fr > kHeavyFrontier) {
-                        if (lane == 0) S.heavy[atomicAdd(&S.n_heavy, 1)] = e;
-                    } else {
-                        walk_link(S, rowptr, col, j, order, e, 0, 1, lane);
-                    }
+                while (pos < end) {
+                    const int seg_end = S.kpre[a + 1] < end ? S.kpre[a + 1] : end;
+                    const int32_t* rowp = col + S.krs[a] - S.kpre[a];
+                    for (int idx = pos + lane; idx < seg_end; idx += 32) ht_insert(S, (uint32_t)ldg_i32(rowp + idx), 1u << a);
+                    pos = seg_end;
+                    ++a;
                 }
-            } else if (order < 3) {
-                for (int e = warp; e < ne; e += kBuildWarps) walk_link(S, rowptr, col, dst[e0 + e], order, e, 0, 1, lane);
-            } else {
-                if (tid < ne) S.heavy[tid] = tid;
-                if (tid == 0) S.n_heavy = ne;
-            }
-            __syncthreads();
-            const int nh = S.n_heavy;
-            for (int h = 0; h < nh; ++h) {
-                const int e = S.heavy[h];
-                walk_link(S, rowptr, col, dst[e0 + e], order, e, warp, kBuildWarps, lane);
             }
         }
         __syncthreads();
-        // records and per-unit column totals
+
+        // order 1: is j itself a key?  (one lookup per link)
+        if (tid < ne) {
+            const uint32_t m1 = ht_lookup(A.table, (uint32_t)dst[e0 + tid]);
+            if (m1) S.m1[tid] = m1;
+        }
+        if (order >= 2) {
+            // phase 1: warps pull (link, neighbour m of j) items; m itself feeds C2, its row feeds C3
+            const int n_items = S.jpre[kEdgeSub];
+            while (true) {
+                int item = 0;
+                if (lane == 0) item = atomicAdd(&S.next_item, 1);
+                item = __shfl_sync(0xffffffffu, item, 0);
+                if (item >= n_items) break;
+                int e = 0;  // last link slot with jpre[e] <= item
+#pragma unroll
+                for (int s = kEdgeSub / 2; s > 0; s >>= 1)
+                    if (S.jpre[e + s] <= item) e += s;
+                const int32_t m = ldg_i32(col + S.jrs[e] + (item - S.jpre[e]));
+                if (lane == 0 && flt_test(A.filter, (uint32_t)m)) add_bits(S.acc2[e], ht_lookup(A.table, (uint32_t)m));
+                if (order >= 3) {
+                    const int64_t rs_m = ldg_i64(rowptr + m);
+                    const int dm = (int)(ldg_i64(rowptr + m + 1) - rs_m);
+                    if (dm > kLongRow) {
+                        int slot = 0;
+                        if (lane == 0) slot = atomicAdd(&S.n_long, 1);
+                        slot = __shfl_sync(0xffffffffu, slot, 0);
+                        if (slot < kMaxLong) {
+                            if (lane == 0) { S.lrs[slot] = rs_m; S.ld[slot] = dm; S.le[slot] = e; }
+                        } else {
+                            walk_row(S, A, sq, col, rs_m, dm, e, 0, 256, lane, tail);  // list full: walk it alone
+                        }
+                    } else {
+                        walk_row(S, A, sq, col, rs_m, dm, e, 0, 256, lane, tail);
+                    }
+                }
+            }
+            if (order >= 3) {
+                __syncthreads();
+                flush_long_rows(S, A, sq, col, warp, lane, tail);
+                q_drain(S, A, sq, lane, tail);
+            }
+        }
+        __syncthreads();
+        // add this unit's partial counts into the records
         for (int s = tid; s < ne * 32; s += kBuildThreads) {
             const int e = s >> 5, p = s & 31;
             if (p < np) {
                 const unsigned c1 = (S.m1[e] >> p) & 1u;
                 const unsigned c2 = S.acc2[e][p], c3 = S.acc3[e][p];
-                records[rec_off[e0 + e] + p0 + p] = make_uint2(c2 | (c1 << 31), c3);
-                if (colstat != nullptr) {
-                    if (c1) atomicAdd(&S.tot1[p], 1u);
-                    const unsigned long long v2 = weighted ? c2 : (c2 ? 1u : 0u);
-                    const unsigned long long v3 = weighted ? c3 : (c3 ? 1u : 0u);
-                    if (v2) atomicAdd(&S.tot2[p], v2);
-                    if (v3) atomicAdd(&S.tot3[p], v3);
-                }
+                unsigned* rec = reinterpret_cast<unsigned*>(records + rec_off[e0 + e] + p0 + p);
+                const unsigned x = c2 | (c1 << 31);
+                if (x) atomicAdd(rec, x);
+                if (c3) atomicAdd(rec + 1, c3);
             }
         }
-        __syncthreads();
-        if (colstat != nullptr && tid < np) {
-            ColStat* cs = colstat + batch * n + S.kp[tid];
-            if (S.tot1[tid]) atomicAdd(&cs->c1, S.tot1[tid]);
-            if (S.tot2[tid]) atomicAdd(&cs->s2, S.tot2[tid]);
-            if (S.tot3[tid]) atomicAdd(&cs->s3, S.tot3[tid]);
+    }
+}
+
+// per-batch column statistics from the finished records: one warp per link
+__global__ void k_cn_colstat(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
+                             const int64_t* __restrict__ src, int64_t T, int64_t batch_size, int weighted,
+                             const int64_t* __restrict__ rec_off, const Record* __restrict__ records,
+                             ColStat* __restrict__ colstat) {
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    for (int64_t t = warp; t < T; t += nwarps) {
+        const int64_t i = src[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs, ro = rec_off[t];
+        ColStat* cs = colstat + (t / batch_size) * n;
+        for (int64_t p = lane; p < d; p += 32) {
+            const Record rec = records[ro + p];
+            if (rec.x | rec.y) {
+                ColStat* c = cs + ldg_i32(col + rs + p);
+                const unsigned c2 = rec.x & 0x7fffffffu;
+                if (rec.x >> 31) atomicAdd(&c->c1, 1u);
+                const unsigned long long v2 = weighted ? c2 : (c2 ? 1u : 0u);
+                const unsigned long long v3 = weighted ? rec.y : (rec.y ? 1u : 0u);
+                if (v2) atomicAdd(&c->s2, v2);
+                if (v3) atomicAdd(&c->s3, v3);
+            }
         }
     }
 }
@@ -370,17 +461,26 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
     OCN_CHECK_ARG(order >= 1 && order <= 3, "ocn_cn_build: order must be 1, 2 or 3 (got %d)", order);
     OCN_CHECK_ARG(n > 0 && num_edges > 0 && batch_size > 0, "ocn_cn_build: sizes must be positive");
     OCN_CHECK_ARG(records || records_capacity == 0, "ocn_cn_build: records is null");
+    OCN_CHECK_ARG(n < (int64_t(1) << kTagShift), "ocn_cn_build: at most 2^27 nodes (queue tag width)");
+    static_assert(kEdgeSub == 32, "one lane per link slot");
     cudaStream_t st = (cudaStream_t)stream;
     PlanLayout L = plan_layout(num_edges);
     const char* base = (const char*)plan_scratch;
+    const int64_t* rec_off = (const int64_t*)(base + L.rec_off);
     OCN_CUDA(cudaFuncSetAttribute(k_cn_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BuildSmem)));
-    // restart the dynamic unit counter (plan[4])
-    OCN_CUDA(cudaMemsetAsync((void*)(plan + 4), 0, sizeof(int64_t), st));
+    OCN_CUDA(cudaMemsetAsync((void*)(plan + 4), 0, sizeof(int64_t), st));  // restart the dynamic unit counter
+    if (records_capacity > 0) OCN_CUDA(cudaMemsetAsync(records, 0, sizeof(Record) * (size_t)records_capacity, st));
     const int blocks = sm_count() * 2;
     k_cn_build<<<blocks, kBuildThreads, sizeof(BuildSmem), st>>>(
-        rowptr, col, n, src, dst, batch_size, order, weighted, (const int64_t*)(base + L.rec_off),
-        (const int32_t*)(base + L.run_start), (const int64_t*)(base + L.run_unit_off), (int64_t*)plan,
-        (Record*)records, (ColStat*)colstat);
+        rowptr, col, n, src, dst, order, rec_off, (const int32_t*)(base + L.run_start),
+        (const int64_t*)(base + L.run_unit_off), (int64_t*)plan, (Record*)records);
     OCN_LAUNCH_CHECK();
+    if (colstat != nullptr) {
+        int64_t want = (num_edges + 7) / 8;
+        int64_t cap = (int64_t)sm_count() * 8;
+        k_cn_colstat<<<(int)(want < cap ? want : cap), 256, 0, st>>>(rowptr, col, n, src, num_edges, batch_size, weighted,
+                                                                    rec_off, (const Record*)records, (ColStat*)colstat);
+        OCN_LAUNCH_CHECK();
+    }
     return OCN_OK;
 }

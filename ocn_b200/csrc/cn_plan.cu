@@ -60,20 +60,33 @@ __global__ void k_plan_runs(const int64_t* __restrict__ src, int64_t T, int64_t 
     }
 }
 
-__global__ void k_plan_units(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ src, int64_t T,
-                             const int32_t* __restrict__ run_start, const int64_t* __restrict__ plan,
-                             int64_t* __restrict__ run_units) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per run: table passes of every 32-position chunk of N(src), times the link sub-lists
+__global__ void k_plan_units(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                             const int64_t* __restrict__ src, int64_t T, const int32_t* __restrict__ run_start,
+                             const int64_t* __restrict__ plan, int64_t* __restrict__ run_units) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (r > T + 1) return;
-    int64_t n_runs = plan[OCN_PLAN_NUM_RUNS];
+    const int64_t n_runs = plan[OCN_PLAN_NUM_RUNS];
     int64_t u = 0;
     if (r < n_runs) {
-        int64_t t0 = run_start[r], len = run_start[r + 1] - t0;
-        int64_t i = src[t0];
-        int64_t d = rowptr[i + 1] - rowptr[i];
-        u = ((d + kPChunk - 1) / kPChunk) * ((len + kEdgeSub - 1) / kEdgeSub);
+        const int64_t t0 = run_start[r], len = run_start[r + 1] - t0;
+        const int64_t i = src[t0];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
+        int64_t passes = 0;
+        for (int64_t c0 = 0; c0 < d; c0 += kPChunk) {
+            long long f = 0;
+            if (c0 + lane < d) {
+                const int32_t k = col[rs + c0 + lane];
+                f = rowptr[k + 1] - rowptr[k];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
+            passes += (f + kCap - 1) / kCap;
+        }
+        u = passes * ((len + kEdgeSub - 1) / kEdgeSub);
     }
-    run_units[r] = u;
+    if (lane == 0) run_units[r] = u;
 }
 
 __global__ void k_plan_finish(int64_t T, int64_t batch_size, const int64_t* __restrict__ rec_off,
@@ -100,10 +113,10 @@ size_t ocn_cn_plan_bytes(int64_t num_edges) {
 size_t ocn_cn_colstat_bytes(int64_t n) { return n < 0 ? 0 : sizeof(ColStat) * (size_t)n; }
 size_t ocn_cn_record_bytes(void) { return sizeof(Record); }
 
-int ocn_cn_plan(const int64_t* rowptr, int64_t n, const int64_t* src, const int64_t* dst, int64_t num_edges,
+int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst, int64_t num_edges,
                 int64_t batch_size, void* plan_scratch, size_t plan_scratch_bytes, int64_t* out_plan, void* stream) {
     (void)dst;
-    OCN_CHECK_ARG(rowptr && out_plan && plan_scratch, "ocn_cn_plan: null pointer");
+    OCN_CHECK_ARG(rowptr && col && out_plan && plan_scratch, "ocn_cn_plan: null pointer");
     OCN_CHECK_ARG(n > 0 && num_edges > 0 && batch_size > 0, "ocn_cn_plan: n, num_edges and batch_size must be positive");
     OCN_CHECK_ARG(num_edges < (int64_t(1) << 30), "ocn_cn_plan: at most 2^30 links per call");
     OCN_CHECK_ARG(src, "ocn_cn_plan: null edge pointer");
@@ -127,8 +140,8 @@ int ocn_cn_plan(const int64_t* rowptr, int64_t n, const int64_t* src, const int6
     OCN_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, run_id, run_id, (int)(T + 1), st));
     k_plan_runs<<<blocks, threads, 0, st>>>(src, T, batch_size, run_id, run_start, out_plan);
     OCN_LAUNCH_CHECK();
-    int blocks2 = (int)((T + 2 + threads - 1) / threads);
-    k_plan_units<<<blocks2, threads, 0, st>>>(rowptr, src, T, run_start, out_plan, run_unit_off);
+    int blocks2 = (int)(((T + 2) * 32 + threads - 1) / threads);
+    k_plan_units<<<blocks2, threads, 0, st>>>(rowptr, col, src, T, run_start, out_plan, run_unit_off);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, run_unit_off, run_unit_off, (int)(T + 2), st));
     k_plan_finish<<<1, 1, 0, st>>>(T, batch_size, rec_off, run_unit_off, out_plan);

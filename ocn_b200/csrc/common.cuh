@@ -34,7 +34,9 @@ int sm_count();
 
 // ---- constants shared by the plan and the build kernel -----------------------------------
 constexpr int kPChunk = 32;   // positions of N(src) handled by one work unit (one mask word)
-constexpr int kEdgeSub = 16;  // target links of a run handled by one work unit
+constexpr int kEdgeSub = 32;  // target links of a run handled by one work unit
+constexpr int kSlots = 9721;  // (key, mask) slots of the shared-memory table of ocn_cn_build (prime, 76 KB)
+constexpr int kCap = (kSlots * 7) / 10;  // keys inserted per table pass (load factor 0.7)
 
 // one record per (target link, position p in N(src)):
 //   x = C2 | (C1 << 31)   (C1 in {0,1}; C2 = #2-walks dst->..->N(src)[p], < 2^31)
