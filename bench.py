@@ -241,14 +241,14 @@ def main():
 
     def step_device(s):
         e = e_rank[:, s * T:(s + 1) * T]
-        sess = ob.CNSession(G, e, a.batch).build(a.order, True)
+        sess = ob.CNSession(G, e, a.batch, a.order).build(a.order, True)
         sess.stats(5, 0.0, ip3, 0)
         return sess.aggregate(x, 5, 0.0, ip3)
 
     def step_e2e(s):
         e = e_host[:, s * T:(s + 1) * T].to(dev, non_blocking=True)
         with torch.no_grad():
-            sess = ob.CNSession(G, e, a.batch).build(a.order, True)
+            sess = ob.CNSession(G, e, a.batch, a.order).build(a.order, True)
             if a.order >= 3:
                 out = pred(x, G, sess, None, None, e)
             else:
@@ -298,7 +298,7 @@ def main():
     build_ms = []
     for s in range(a.warmup, nsteps):
         e = e_rank[:, s * T:(s + 1) * T]
-        sess = ob.CNSession(G, e, a.batch)
+        sess = ob.CNSession(G, e, a.batch, a.order)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         sess.build(a.order, True)

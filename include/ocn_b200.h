@@ -101,6 +101,7 @@ size_t ocn_cn_record_bytes(void);
 
 int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n,
                 const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t batch_size,
+                int order /* highest CN order that will be built: sizes the work units */,
                 void* plan_scratch, size_t plan_scratch_bytes,
                 int64_t* out_plan /* device int64[OCN_PLAN_WORDS] */, void* stream);
 

@@ -98,7 +98,7 @@ class CNSession:
     ``batch_size`` cuts the stream into the reference's link batches; every batch is
     normalised independently (the column sums of model.py:2261 run over one batch)."""
 
-    def __init__(self, graph: Graph, tarei: Tensor, batch_size: Optional[int] = None):
+    def __init__(self, graph: Graph, tarei: Tensor, batch_size: Optional[int] = None, order: int = 3):
         _require_cuda(graph.col)
         _require_cuda(tarei)
         self.g = graph
@@ -115,14 +115,15 @@ class CNSession:
         self.plan_scratch = torch.empty(self.plan_bytes, dtype=torch.uint8, device=self.dev)
         self.plan = torch.zeros(PLAN_WORDS, dtype=torch.int64, device=self.dev)
         with torch.cuda.device(self.dev):
-            _lib.check(L.ocn_cn_plan(_lib.ptr(graph.rowptr), _lib.ptr(graph.col), graph.n, _lib.ptr(self.src), _lib.ptr(self.dst), self.T,
-                                     self.batch_size, _lib.ptr(self.plan_scratch), self.plan_bytes,
+            _lib.check(L.ocn_cn_plan(_lib.ptr(graph.rowptr), _lib.ptr(graph.col), graph.n, _lib.ptr(self.src),
+                                     _lib.ptr(self.dst), self.T, self.batch_size, int(order),
+                                     _lib.ptr(self.plan_scratch), self.plan_bytes,
                                      _lib.ptr(self.plan), _stream(self.dev)), "ocn_cn_plan")
         host = self.plan.tolist()  # the one host sync of the session: buffer sizes
         self.num_records, self.num_runs, self.num_units = host[0], host[1], host[2]
         self.records = torch.empty(max(1, self.num_records) * L.ocn_cn_record_bytes(), dtype=torch.uint8,
                                    device=self.dev)
-        self.colstat = torch.zeros(self.nb * L.ocn_cn_colstat_bytes(graph.n), dtype=torch.uint8, device=self.dev)
+        self.colstat = None  # borrowed by build(with_stats=True)
         self.bscal = torch.zeros(self.nb * 8, dtype=torch.float32, device=self.dev)
         self.order = 0
         self.weighted = True
@@ -131,6 +132,8 @@ class CNSession:
     # -- steps ------------------------------------------------------------------------------
     def build(self, order: int, weighted: bool, with_stats: bool = True) -> "CNSession":
         g = self.g
+        if with_stats and self.colstat is None:
+            self.colstat = _borrow_colstat(g, self.nb * self.L.ocn_cn_colstat_bytes(g.n))
         with torch.cuda.device(self.dev):
             _lib.check(self.L.ocn_cn_build(_lib.ptr(g.rowptr), _lib.ptr(g.col), g.n, _lib.ptr(self.src),
                                            _lib.ptr(self.dst), self.T, self.batch_size, int(order), int(bool(weighted)),
@@ -208,11 +211,32 @@ class CNSession:
     def release(self):
         """Zero the column statistics this stream touched (the buffer is reusable afterwards)."""
         g = self.g
+        if self.colstat is None or self._released:
+            return
         with torch.cuda.device(self.dev):
             _lib.check(self.L.ocn_cn_release(_lib.ptr(g.rowptr), _lib.ptr(g.col), g.n, _lib.ptr(self.src), self.T,
                                              self.batch_size, _lib.ptr(self.plan_scratch), _lib.ptr(self.records),
                                              _lib.ptr(self.colstat), _stream(self.dev)), "ocn_cn_release")
         self._released = True
+        _return_colstat(self.g, self.colstat)
+
+
+def _borrow_colstat(g: Graph, nbytes: int) -> Tensor:
+    """A zeroed buffer for the per-batch column statistics.  Buffers handed back by
+    ``CNSession.release`` (which re-zeroes exactly the touched entries) are reused, so a steady
+    stream of sessions does not pay a multi-GB memset per call."""
+    pool = g._ws.setdefault("colstat", [])
+    for k, buf in enumerate(pool):
+        if buf.numel() >= nbytes:
+            pool.pop(k)
+            return buf
+    return torch.zeros(nbytes, dtype=torch.uint8, device=g.device)
+
+
+def _return_colstat(g: Graph, buf: Tensor):
+    pool = g._ws.setdefault("colstat", [])
+    if len(pool) < 2:
+        pool.append(buf)
 
 
 def _check_x(x: Tensor, g: Graph) -> Tensor:
@@ -228,7 +252,7 @@ def get_cn(adj: Graph, tedge: Tensor, order: int = 2, weighted: bool = True) -> 
     """``get_cn1_cn2`` (NeighborOverlapCitation2.py:78-104) generalised to ``order`` sets.
     weighted=True keeps the pygho walk counts as values, False gives the 0/1 structure that
     ``adjoverlap(adj, adj2, e)`` yields in the _large drivers."""
-    s = CNSession(adj, tedge).build(order, weighted, with_stats=False)
+    s = CNSession(adj, tedge, None, order).build(order, weighted, with_stats=False)
     return [s.extract(k) for k in range(1, order + 1)]
 
 
@@ -253,10 +277,11 @@ def cn_aggregate_eval(graph: Graph, tarei: Tensor, x: Tensor, batch_size: int, o
     T = tarei.shape[1]
     outs = None
     for (s, e) in waves(T, batch_size, graph.n, budget_bytes):
-        sess = CNSession(graph, tarei[:, s:e], batch_size).build(order, weighted)
+        sess = CNSession(graph, tarei[:, s:e], batch_size, order).build(order, weighted)
         if variant == 5:
             sess.stats(variant, fill, ip, 0)
         part = sess.aggregate(x, variant, fill, ip, want_xij)
+        sess.release()
         if s == 0 and e == T:
             return part
         if outs is None:

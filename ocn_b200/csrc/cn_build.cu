@@ -9,8 +9,9 @@
 // so a shared-memory hash table  l -> mask_i(l)  (built once per group of links that share the
 // source i) turns the whole computation into a 3-level walk from j with one probe per visited node.
 //
-// Work unit = (run of links with one source, 32 positions of N(i), table pass, <= kEdgeSub links),
-// handed out dynamically (cn_plan.cu).  The 32 rows N(N(i)[p]) form one flattened key list; pass q
+// Work unit = (run of links with one source, 32 positions of N(i), table pass, cost window of the run),
+// handed out dynamically (cn_plan.cu).  A cost window holds about unit_budget() probed columns: many
+// light links (walked kEdgeSub at a time against the same table) or a slice of the rows of one heavy link.  The 32 rows N(N(i)[p]) form one flattened key list; pass q
 // holds keys [q*kCap, (q+1)*kCap) of it, so hubs next to the source need no special case.  Units
 // add their partial counts into the records with global atomics (records are zeroed first).
 //
@@ -237,7 +238,8 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
 k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
            const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int order,
            const int64_t* __restrict__ rec_off, const int32_t* __restrict__ run_start,
-           const int64_t* __restrict__ run_unit_off, int64_t* __restrict__ plan, Record* __restrict__ records) {
+           const int64_t* __restrict__ run_unit_off, const int64_t* __restrict__ cost_pre,
+           int64_t* __restrict__ plan, Record* __restrict__ records) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BuildSmem& S = *reinterpret_cast<BuildSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -249,11 +251,12 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
     const uint32_t sq = A.queue + (uint32_t)warp * (kQueue * 4u);
     const int64_t n_units = plan[OCN_PLAN_NUM_UNITS];
     const int64_t n_runs = plan[OCN_PLAN_NUM_RUNS];
+    const int64_t W = plan[OCN_PLAN_BUDGET];
     int tail = 0;  // this warp's queue fill (warp-uniform)
 
     while (true) {
         __syncthreads();
-        if (tid == 0) S.unit = (long long)atomicAdd((unsigned long long*)&plan[4], 1ull);
+        if (tid == 0) S.unit = (long long)atomicAdd((unsigned long long*)&plan[OCN_PLAN_UNIT_COUNTER], 1ull);
         __syncthreads();
         const int64_t unit = S.unit;
         if (unit >= n_units) break;
@@ -268,10 +271,28 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
         const int64_t i = src[t0];
         const int64_t rs_i = rowptr[i];
         const int64_t d = rowptr[i + 1] - rs_i;
-        const int64_t n_es = (len + kEdgeSub - 1) / kEdgeSub;
-        const int64_t q = local / n_es, es = local - q * n_es;  // q = global pass index of this run
-        const int64_t e0 = t0 + es * kEdgeSub;
-        const int ne = (int)((t0 + len - e0) < kEdgeSub ? (t0 + len - e0) : kEdgeSub);
+        // cost windows of the run: window s covers run-local cost [s*W, (s+1)*W)
+        const int64_t cbase = cost_pre[t0];
+        const int64_t run_cost = cost_pre[t0 + len] - cbase;
+        const int64_t n_win = (run_cost + W - 1) / W;
+        const int64_t q = local / n_win, win = local - q * n_win;  // q = global table-pass index of this run
+        const int64_t c_lo = win * W, c_hi = (c_lo + W < run_cost) ? c_lo + W : run_cost;
+        // links whose cost interval [P_t, P_t + c_t) meets the window
+        int64_t t_first, t_last;
+        {
+            int64_t a = t0, b = t0 + len;  // first t with cost_pre[t+1] - cbase > c_lo
+            while (a < b) {
+                const int64_t mid = (a + b) >> 1;
+                if (cost_pre[mid + 1] - cbase > c_lo) b = mid; else a = mid + 1;
+            }
+            t_first = a;
+            a = t0; b = t0 + len;          // first t with cost_pre[t] - cbase >= c_hi
+            while (a < b) {
+                const int64_t mid = (a + b) >> 1;
+                if (cost_pre[mid] - cbase >= c_hi) b = mid; else a = mid + 1;
+            }
+            t_last = a - 1;
+        }
 
         // warp 0: locate (chunk, pass) of q by walking the chunks of N(i); load the chunk's rows
         if (warp == 0) {
@@ -307,34 +328,9 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
                 ++chunk;
             }
         }
-        // warp 1: the links of this unit
-        if (warp == 1) {
-            int dj = 0;
-            if (lane < ne) {
-                const int64_t j = dst[e0 + lane];
-                const int64_t rs_j = rowptr[j];
-                dj = (order >= 2) ? (int)(rowptr[j + 1] - rs_j) : 0;
-                S.jrs[lane] = rs_j;
-                S.jdeg[lane] = dj;
-                S.m1[lane] = 0u;
-            }
-            int incl = dj;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            S.jpre[lane] = incl - dj;
-            if (lane == 31) S.jpre[kEdgeSub] = incl;
-        }
-        for (int s = tid; s < kEdgeSub * 32; s += kBuildThreads) {
-            (&S.acc2[0][0])[s] = 0u;
-            (&S.acc3[0][0])[s] = 0u;
-        }
         for (int s = tid; s < (kSlots + 1) / 2; s += kBuildThreads)
             reinterpret_cast<uint4*>(S.table)[s] = make_uint4(kEmpty, 0u, kEmpty, 0u);
         for (int s = tid; s < kFilterWords; s += kBuildThreads) S.filter[s] = 0u;
-        if (tid == 0) { S.next_item = 0; S.n_long = 0; }
         __syncthreads();
 
         const int64_t p0 = (int64_t)S.chunk * kPChunk;
@@ -362,61 +358,96 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
                 }
             }
         }
-        __syncthreads();
 
-        // order 1: is j itself a key?  (one lookup per link)
-        if (tid < ne) {
-            const uint32_t m1 = ht_lookup(A.table, (uint32_t)dst[e0 + tid]);
-            if (m1) S.m1[tid] = m1;
-        }
-        if (order >= 2) {
-            // phase 1: warps pull (link, neighbour m of j) items; m itself feeds C2, its row feeds C3
-            const int n_items = S.jpre[kEdgeSub];
-            while (true) {
-                int item = 0;
-                if (lane == 0) item = atomicAdd(&S.next_item, 1);
-                item = __shfl_sync(0xffffffffu, item, 0);
-                if (item >= n_items) break;
-                int e = 0;  // last link slot with jpre[e] <= item
+        // the links of the window, kEdgeSub slots at a time, all against the same table
+        for (int64_t g0 = t_first; g0 <= t_last; g0 += kEdgeSub) {
+            const int ne = (int)((t_last - g0 + 1) < kEdgeSub ? (t_last - g0 + 1) : kEdgeSub);
+            __syncthreads();  // table complete / previous group flushed
+            if (warp == 1) {
+                int dj = 0;
+                unsigned first_piece = 0u;
+                if (lane < ne) {
+                    const int64_t t = g0 + lane;
+                    const int64_t j = dst[t];
+                    const int64_t rs_j = rowptr[j];
+                    const int64_t dfull = (order >= 2) ? (rowptr[j + 1] - rs_j) : 0;
+                    const int64_t P = cost_pre[t] - cbase, c = cost_pre[t + 1] - cost_pre[t];
+                    const int64_t a = P > c_lo ? P : c_lo, b = (P + c) < c_hi ? (P + c) : c_hi;
+                    const int64_t row_lo = (a - P) * dfull / c;
+                    const int64_t row_hi = (b == P + c) ? dfull : (b - P) * dfull / c;
+                    first_piece = (a == P) ? 1u : 0u;
+                    S.jrs[lane] = rs_j + row_lo;
+                    dj = (int)(row_hi - row_lo);
+                    S.jdeg[lane] = dj;
+                }
+                S.m1[lane] = first_piece;  // bit 0 = "this unit owns the order-1 lookup of the link" (replaced below)
+                int incl = dj;
 #pragma unroll
-                for (int s = kEdgeSub / 2; s > 0; s >>= 1)
-                    if (S.jpre[e + s] <= item) e += s;
-                const int32_t m = ldg_i32(col + S.jrs[e] + (item - S.jpre[e]));
-                if (lane == 0 && flt_test(A.filter, (uint32_t)m)) add_bits(S.acc2[e], ht_lookup(A.table, (uint32_t)m));
-                if (order >= 3) {
-                    const int64_t rs_m = ldg_i64(rowptr + m);
-                    const int dm = (int)(ldg_i64(rowptr + m + 1) - rs_m);
-                    if (dm > kLongRow) {
-                        int slot = 0;
-                        if (lane == 0) slot = atomicAdd(&S.n_long, 1);
-                        slot = __shfl_sync(0xffffffffu, slot, 0);
-                        if (slot < kMaxLong) {
-                            if (lane == 0) { S.lrs[slot] = rs_m; S.ld[slot] = dm; S.le[slot] = e; }
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                S.jpre[lane] = incl - dj;
+                if (lane == 31) S.jpre[kEdgeSub] = incl;
+            }
+            for (int s = tid; s < kEdgeSub * 32; s += kBuildThreads) {
+                (&S.acc2[0][0])[s] = 0u;
+                (&S.acc3[0][0])[s] = 0u;
+            }
+            if (tid == 0) { S.next_item = 0; S.n_long = 0; }
+            __syncthreads();
+
+            // order 1: is j itself a key?  (one lookup per link, by the unit holding the link's first piece)
+            if (tid < ne) S.m1[tid] = S.m1[tid] ? ht_lookup(A.table, (uint32_t)dst[g0 + tid]) : 0u;
+            if (order >= 2) {
+                // phase 1: warps pull (link, neighbour m of j) items; m itself feeds C2, its row feeds C3
+                const int n_items = S.jpre[kEdgeSub];
+                while (true) {
+                    int item = 0;
+                    if (lane == 0) item = atomicAdd(&S.next_item, 1);
+                    item = __shfl_sync(0xffffffffu, item, 0);
+                    if (item >= n_items) break;
+                    int e = 0;  // last link slot with jpre[e] <= item
+#pragma unroll
+                    for (int s = kEdgeSub / 2; s > 0; s >>= 1)
+                        if (S.jpre[e + s] <= item) e += s;
+                    const int32_t m = ldg_i32(col + S.jrs[e] + (item - S.jpre[e]));
+                    if (lane == 0 && flt_test(A.filter, (uint32_t)m)) add_bits(S.acc2[e], ht_lookup(A.table, (uint32_t)m));
+                    if (order >= 3) {
+                        const int64_t rs_m = ldg_i64(rowptr + m);
+                        const int dm = (int)(ldg_i64(rowptr + m + 1) - rs_m);
+                        if (dm > kLongRow) {
+                            int slot = 0;
+                            if (lane == 0) slot = atomicAdd(&S.n_long, 1);
+                            slot = __shfl_sync(0xffffffffu, slot, 0);
+                            if (slot < kMaxLong) {
+                                if (lane == 0) { S.lrs[slot] = rs_m; S.ld[slot] = dm; S.le[slot] = e; }
+                            } else {
+                                walk_row(S, A, sq, col, rs_m, dm, e, 0, 256, lane, tail);  // list full: walk it alone
+                            }
                         } else {
-                            walk_row(S, A, sq, col, rs_m, dm, e, 0, 256, lane, tail);  // list full: walk it alone
+                            walk_row(S, A, sq, col, rs_m, dm, e, 0, 256, lane, tail);
                         }
-                    } else {
-                        walk_row(S, A, sq, col, rs_m, dm, e, 0, 256, lane, tail);
                     }
                 }
+                if (order >= 3) {
+                    __syncthreads();
+                    flush_long_rows(S, A, sq, col, warp, lane, tail);
+                    q_drain(S, A, sq, lane, tail);
+                }
             }
-            if (order >= 3) {
-                __syncthreads();
-                flush_long_rows(S, A, sq, col, warp, lane, tail);
-                q_drain(S, A, sq, lane, tail);
-            }
-        }
-        __syncthreads();
-        // add this unit's partial counts into the records
-        for (int s = tid; s < ne * 32; s += kBuildThreads) {
-            const int e = s >> 5, p = s & 31;
-            if (p < np) {
-                const unsigned c1 = (S.m1[e] >> p) & 1u;
-                const unsigned c2 = S.acc2[e][p], c3 = S.acc3[e][p];
-                unsigned* rec = reinterpret_cast<unsigned*>(records + rec_off[e0 + e] + p0 + p);
-                const unsigned x = c2 | (c1 << 31);
-                if (x) atomicAdd(rec, x);
-                if (c3) atomicAdd(rec + 1, c3);
+            __syncthreads();
+            // add this group's partial counts into the records
+            for (int s = tid; s < ne * 32; s += kBuildThreads) {
+                const int e = s >> 5, p = s & 31;
+                if (p < np) {
+                    const unsigned c1 = (S.m1[e] >> p) & 1u;
+                    const unsigned c2 = S.acc2[e][p], c3 = S.acc3[e][p];
+                    unsigned* rec = reinterpret_cast<unsigned*>(records + rec_off[g0 + e] + p0 + p);
+                    const unsigned x = c2 | (c1 << 31);
+                    if (x) atomicAdd(rec, x);
+                    if (c3) atomicAdd(rec + 1, c3);
+                }
             }
         }
     }
@@ -468,12 +499,12 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
     const char* base = (const char*)plan_scratch;
     const int64_t* rec_off = (const int64_t*)(base + L.rec_off);
     OCN_CUDA(cudaFuncSetAttribute(k_cn_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BuildSmem)));
-    OCN_CUDA(cudaMemsetAsync((void*)(plan + 4), 0, sizeof(int64_t), st));  // restart the dynamic unit counter
+    OCN_CUDA(cudaMemsetAsync((void*)(plan + OCN_PLAN_UNIT_COUNTER), 0, sizeof(int64_t), st));  // restart the dynamic unit counter
     if (records_capacity > 0) OCN_CUDA(cudaMemsetAsync(records, 0, sizeof(Record) * (size_t)records_capacity, st));
     const int blocks = sm_count() * 2;
     k_cn_build<<<blocks, kBuildThreads, sizeof(BuildSmem), st>>>(
         rowptr, col, n, src, dst, order, rec_off, (const int32_t*)(base + L.run_start),
-        (const int64_t*)(base + L.run_unit_off), (int64_t*)plan, (Record*)records);
+        (const int64_t*)(base + L.run_unit_off), (const int64_t*)(base + L.cost_pre), (int64_t*)plan, (Record*)records);
     OCN_LAUNCH_CHECK();
     if (colstat != nullptr) {
         int64_t want = (num_edges + 7) / 8;

@@ -20,6 +20,7 @@ PlanLayout plan_layout(int64_t T) {
     L.run_id = off;        off += align16(sizeof(int32_t) * (T + 1));
     L.run_start = off;     off += align16(sizeof(int32_t) * (T + 2));
     L.run_unit_off = off;  off += align16(sizeof(int64_t) * (T + 2));
+    L.cost_pre = off;      off += align16(sizeof(int64_t) * (T + 2));
     L.partial = off;       off += align16(sizeof(float) * 3 * (T + 1));
     size_t b1 = 0, b2 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, b1, (int64_t*)nullptr, (int64_t*)nullptr, (int)(T + 2));
@@ -60,9 +61,40 @@ __global__ void k_plan_runs(const int64_t* __restrict__ src, int64_t T, int64_t 
     }
 }
 
-// one warp per run: table passes of every 32-position chunk of N(src), times the link sub-lists
+// one warp per link: walk cost = number of columns the j-side walk probes (+ a constant)
+__global__ void k_plan_cost(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                            const int64_t* __restrict__ dst, int64_t T, int order, int64_t* __restrict__ cost,
+                            int64_t* __restrict__ plan) {
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t > T) return;
+    if (t == T) {
+        if (lane == 0) cost[t] = 0;
+        return;
+    }
+    const int64_t j = dst[t];
+    const int64_t rs = rowptr[j], d = rowptr[j + 1] - rs;
+    long long w = 0;
+    if (order >= 3) {
+        for (int64_t o = lane; o < d; o += 32) {
+            const int32_t m = col[rs + o];
+            w += rowptr[m + 1] - rowptr[m];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    }
+    if (order >= 2) w += d;
+    w += kLinkCost;
+    if (lane == 0) {
+        cost[t] = w;
+        atomicAdd((unsigned long long*)&plan[OCN_PLAN_TOTAL_COST], (unsigned long long)w);
+    }
+}
+
+// one warp per run: (table passes over all 32-position chunks of N(src)) x (cost windows of the run)
 __global__ void k_plan_units(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                              const int64_t* __restrict__ src, int64_t T, const int32_t* __restrict__ run_start,
+                             const int64_t* __restrict__ cost_pre, int resident_ctas,
                              const int64_t* __restrict__ plan, int64_t* __restrict__ run_units) {
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -84,19 +116,20 @@ __global__ void k_plan_units(const int64_t* __restrict__ rowptr, const int32_t* 
             for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
             passes += (f + kCap - 1) / kCap;
         }
-        u = passes * ((len + kEdgeSub - 1) / kEdgeSub);
+        const long long W = unit_budget(plan[OCN_PLAN_TOTAL_COST], resident_ctas);
+        const long long run_cost = cost_pre[t0 + len] - cost_pre[t0];
+        u = passes * ((run_cost + W - 1) / W);
     }
     if (lane == 0) run_units[r] = u;
 }
 
-__global__ void k_plan_finish(int64_t T, int64_t batch_size, const int64_t* __restrict__ rec_off,
+__global__ void k_plan_finish(int64_t T, int64_t batch_size, int resident_ctas, const int64_t* __restrict__ rec_off,
                               const int64_t* __restrict__ run_unit_off, int64_t* __restrict__ plan) {
     plan[OCN_PLAN_NUM_RECORDS] = rec_off[T];
     plan[OCN_PLAN_NUM_UNITS] = run_unit_off[plan[OCN_PLAN_NUM_RUNS]];
     plan[OCN_PLAN_NUM_BATCHES] = (T + batch_size - 1) / batch_size;
-    plan[4] = 0;  // dynamic unit counter of ocn_cn_build
-    plan[5] = 0;
-    plan[6] = 0;
+    plan[OCN_PLAN_UNIT_COUNTER] = 0;  // dynamic unit counter of ocn_cn_build
+    plan[OCN_PLAN_BUDGET] = unit_budget(plan[OCN_PLAN_TOTAL_COST], resident_ctas);
     plan[7] = 0;
 }
 
@@ -114,12 +147,12 @@ size_t ocn_cn_colstat_bytes(int64_t n) { return n < 0 ? 0 : sizeof(ColStat) * (s
 size_t ocn_cn_record_bytes(void) { return sizeof(Record); }
 
 int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst, int64_t num_edges,
-                int64_t batch_size, void* plan_scratch, size_t plan_scratch_bytes, int64_t* out_plan, void* stream) {
-    (void)dst;
+                int64_t batch_size, int order, void* plan_scratch, size_t plan_scratch_bytes, int64_t* out_plan, void* stream) {
     OCN_CHECK_ARG(rowptr && col && out_plan && plan_scratch, "ocn_cn_plan: null pointer");
     OCN_CHECK_ARG(n > 0 && num_edges > 0 && batch_size > 0, "ocn_cn_plan: n, num_edges and batch_size must be positive");
     OCN_CHECK_ARG(num_edges < (int64_t(1) << 30), "ocn_cn_plan: at most 2^30 links per call");
-    OCN_CHECK_ARG(src, "ocn_cn_plan: null edge pointer");
+    OCN_CHECK_ARG(src && dst, "ocn_cn_plan: null edge pointer");
+    OCN_CHECK_ARG(order >= 1 && order <= 3, "ocn_cn_plan: order must be 1..3");
     PlanLayout L = plan_layout(num_edges);
     if (plan_scratch_bytes < L.total)
         return fail(OCN_ENOSPACE, "ocn_cn_plan: plan scratch %zu < %zu bytes", plan_scratch_bytes, L.total);
@@ -132,19 +165,27 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
     void* tmp = base + L.cub_temp;
     size_t tmp_bytes = L.cub_temp_bytes;
     int64_t T = num_edges;
+    int64_t* cost_pre = (int64_t*)(base + L.cost_pre);
+    const int resident_ctas = sm_count() * 2;
     int threads = 256;
     int blocks = (int)((T + 1 + threads - 1) / threads);
+    OCN_CUDA(cudaMemsetAsync(out_plan, 0, sizeof(int64_t) * OCN_PLAN_WORDS, st));
     k_plan_edges<<<blocks, threads, 0, st>>>(rowptr, src, T, batch_size, rec_off, run_id);
     OCN_LAUNCH_CHECK();
+    int blocks_w = (int)(((T + 1) * 32 + threads - 1) / threads);
+    k_plan_cost<<<blocks_w, threads, 0, st>>>(rowptr, col, dst, T, order, cost_pre, out_plan);
+    OCN_LAUNCH_CHECK();
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, rec_off, rec_off, (int)(T + 1), st));
+    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cost_pre, cost_pre, (int)(T + 1), st));
     OCN_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, run_id, run_id, (int)(T + 1), st));
     k_plan_runs<<<blocks, threads, 0, st>>>(src, T, batch_size, run_id, run_start, out_plan);
     OCN_LAUNCH_CHECK();
     int blocks2 = (int)(((T + 2) * 32 + threads - 1) / threads);
-    k_plan_units<<<blocks2, threads, 0, st>>>(rowptr, col, src, T, run_start, out_plan, run_unit_off);
+    k_plan_units<<<blocks2, threads, 0, st>>>(rowptr, col, src, T, run_start, cost_pre, resident_ctas, out_plan,
+                                              run_unit_off);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, run_unit_off, run_unit_off, (int)(T + 2), st));
-    k_plan_finish<<<1, 1, 0, st>>>(T, batch_size, rec_off, run_unit_off, out_plan);
+    k_plan_finish<<<1, 1, 0, st>>>(T, batch_size, resident_ctas, rec_off, run_unit_off, out_plan);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
 }

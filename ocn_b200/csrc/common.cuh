@@ -59,12 +59,28 @@ struct PlanLayout {
     size_t run_id;         // int32[T+1]
     size_t run_start;      // int32[T+2]
     size_t run_unit_off;   // int64[T+2]
+    size_t cost_pre;       // int64[T+2]  exclusive prefix of the per-link walk cost
     size_t partial;        // float[3*T]
     size_t cub_temp;       // bytes
     size_t cub_temp_bytes;
     size_t total;
 };
 PlanLayout plan_layout(int64_t num_edges);
+
+// cost window (in probed columns) one work unit of ocn_cn_build covers: about 8 units per resident CTA,
+// clamped so that a unit amortises its table build but a heavy link is still split over many CTAs
+__host__ __device__ inline long long unit_budget(long long total_cost, int resident_ctas) {
+    long long w = total_cost / (8ll * (resident_ctas > 0 ? resident_ctas : 1));
+    if (w < 32768) w = 32768;
+    if (w > 262144) w = 262144;
+    return w;
+}
+constexpr int kLinkCost = 64;  // fixed cost added to every link so that empty links still advance
+
+// plan[] words beyond the public ones
+#define OCN_PLAN_UNIT_COUNTER 4
+#define OCN_PLAN_BUDGET 5
+#define OCN_PLAN_TOTAL_COST 6
 
 // ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

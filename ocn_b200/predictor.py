@@ -57,6 +57,8 @@ class _CNAggregateFn(torch.autograd.Function):
         gx = torch.zeros_like(x)
         ctx.sess.aggregate_bwd(x, ctx.variant, ctx.fill, ip3, g1, g2 if ctx.has[0] else None,
                                g3 if ctx.has[1] else None, gij, gx)
+        if not ctx.sess._released:
+            ctx.sess.release()
         return gx, None, None, None, None
 
 
@@ -105,7 +107,7 @@ class _OCNBase(nn.Module):
 
     def cn_stage(self, x: Tensor, adj: Graph, tar_ei: Tensor, fill: float = 0.0, sess: Optional[CNSession] = None):
         if sess is None:
-            sess = CNSession(adj, tar_ei)
+            sess = CNSession(adj, tar_ei, None, self.order)
             sess.build(self.order, self.weighted)
         ip3 = self.innerprod.detach().float().repeat(3).contiguous()
         if self.variant == 5:
@@ -125,6 +127,8 @@ class _OCNBase(nn.Module):
                     final = self.innerprod.detach().float()
                     ip3 = torch.cat((ip3[:1], final, final)).contiguous()
         xcn1, xcn2, xcn3, xij = _CNAggregateFn.apply(x, sess, self.variant, float(fill), ip3)
+        if not (torch.is_grad_enabled() and x.requires_grad):
+            sess.release()  # nothing will run backward through this session: hand the statistics buffer back
         return xcn1, xcn2, (xcn3 if xcn3.numel() else None), xij, sess
 
     def _head(self, xcn1, xcn2, xcn3, xij):

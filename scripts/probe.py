@@ -40,7 +40,7 @@ def main():
     for rep in range(a.reps):
         marks = [ev() for _ in range(6)]
         marks[0].record()
-        sess = ob.CNSession(G, e, a.batch)
+        sess = ob.CNSession(G, e, a.batch, a.order)
         marks[1].record()
         sess.build(a.order, True)
         marks[2].record()
