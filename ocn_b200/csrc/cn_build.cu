@@ -16,7 +16,7 @@
 // add their partial counts into the records with global atomics (records are zeroed first).
 //
 // Inside a unit
-//   * the table is paired with a 128 Kbit one-hash Bloom filter: > 90 % of the frontier misses the
+//   * the table is paired with a 256 Kbit one-hash bit filter: > 90 % of the frontier misses the
 //     table (measured hit rate 0-8 %), and a miss costs one branch-free shared-memory bit test;
 //   * columns that pass the filter are compacted into a per-warp queue and looked up 32 at a time,
 //     so the divergent probe loops run with all lanes busy;
@@ -29,13 +29,13 @@
 
 namespace ocn {
 
-constexpr int kBuildThreads = 512;
+constexpr int kBuildThreads = 1024;
 constexpr int kBuildWarps = kBuildThreads / 32;
 constexpr uint32_t kEmpty = 0xffffffffu;
-constexpr int kFilterBits = 17;                       // 131072-bit filter (16 KB)
+constexpr int kFilterBits = 18;                       // 262144-bit filter (32 KB)
 constexpr int kFilterWords = 1 << (kFilterBits - 5);
-constexpr int kQueue = 128;                           // per-warp queue of filter survivors
-constexpr int kLongRow = 2048;                        // rows longer than this are walked by the whole CTA
+constexpr int kQueue = 96;                            // per-warp queue of filter survivors
+constexpr int kLongRow = 4096;                        // rows longer than this are walked by the whole CTA
 constexpr int kMaxLong = 192;                         // deferred long rows per pass before an early flush
 
 struct BuildSmem {
@@ -81,24 +81,41 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-struct SAddr {  // shared-window byte addresses of the hot structures
+struct SAddr {  // shared-window byte addresses of the hot structures + the geometry used by this unit
     uint32_t table, filter, queue;
+    uint32_t tsize;   // table slots in use (prime); a small key set uses (and clears) a small table
+    uint32_t fshift;  // filter: byte offset of the word = (hash >> fshift) & fmask
+    uint32_t fmask;
 };
 
+// table / filter geometry for n keys: smallest prime size with load <= 0.7, >= 16 filter bits per key
+__device__ __forceinline__ void pick_geometry(int nkeys, SAddr& A) {
+    const uint32_t sizes[5] = {1301u, 2609u, 5227u, 10487u, (uint32_t)kSlots};
+    uint32_t ts = (uint32_t)kSlots;
+#pragma unroll
+    for (int k = 4; k >= 0; --k)
+        if ((long long)sizes[k] * 7 >= (long long)nkeys * 10) ts = sizes[k];
+    A.tsize = ts;
+    int bits = 10;
+    while (bits < kFilterBits && (1 << bits) < nkeys * 16) ++bits;
+    A.fshift = (uint32_t)(32 - (bits - 5) - 2);
+    A.fmask = (uint32_t)(((1 << (bits - 5)) - 1) << 2);
+}
+
 // double hashing on a prime-size table: home slot and a key-dependent step in [1, kSlots-1]
-__device__ __forceinline__ uint32_t ht_home(uint32_t key) { return __umulhi(key * 2654435769u, (uint32_t)kSlots); }
-__device__ __forceinline__ uint32_t ht_step(uint32_t key) { return 1u + __umulhi(key * 0xc2b2ae35u, (uint32_t)(kSlots - 1)); }
+__device__ __forceinline__ uint32_t ht_home(uint32_t key, uint32_t tsize) { return __umulhi(key * 2654435769u, tsize); }
+__device__ __forceinline__ uint32_t ht_step(uint32_t key, uint32_t tsize) { return 1u + __umulhi(key * 0xc2b2ae35u, tsize - 1u); }
 
-// blocked 2-bit Bloom filter: one 32-bit word per key, two bits inside it
+// one-hash bit filter: word from the top bits of the hash, bit from its low 5 bits
 __device__ __forceinline__ uint32_t flt_hash(uint32_t key) { return key * 0x85ebca6bu; }
-__device__ __forceinline__ uint32_t flt_word(uint32_t h) { return (h >> (32 - (kFilterBits - 5))) << 2; }  // byte offset
-__device__ __forceinline__ uint32_t flt_need(uint32_t h) { return (1u << ((h >> 13) & 31)) | (1u << ((h >> 8) & 31)); }
+__device__ __forceinline__ uint32_t flt_word(uint32_t h, const SAddr& A) { return (h >> A.fshift) & A.fmask; }  // byte offset
+__device__ __forceinline__ uint32_t flt_need(uint32_t h) { return 1u << (h & 31); }
 
-__device__ __forceinline__ void ht_insert(BuildSmem& S, uint32_t key, uint32_t bit) {
+__device__ __forceinline__ void ht_insert(BuildSmem& S, const SAddr& A, uint32_t key, uint32_t bit) {
     const uint32_t h = flt_hash(key);
-    atomicOr(&S.filter[flt_word(h) >> 2], flt_need(h));
-    uint32_t slot = ht_home(key);
-    const uint32_t step = ht_step(key);
+    atomicOr(&S.filter[flt_word(h, A) >> 2], flt_need(h));
+    uint32_t slot = ht_home(key, A.tsize);
+    const uint32_t step = ht_step(key, A.tsize);
     while (true) {
         const uint32_t prev = atomicCAS(&S.table[slot].x, kEmpty, key);
         if (prev == kEmpty || prev == key) {
@@ -106,28 +123,28 @@ __device__ __forceinline__ void ht_insert(BuildSmem& S, uint32_t key, uint32_t b
             return;
         }
         slot += step;
-        if (slot >= (uint32_t)kSlots) slot -= (uint32_t)kSlots;
+        if (slot >= A.tsize) slot -= A.tsize;
     }
 }
 
-__device__ __forceinline__ uint32_t ht_lookup(uint32_t stable, uint32_t key) {
-    uint32_t slot = ht_home(key);
-    const uint32_t step = ht_step(key);
+__device__ __forceinline__ uint32_t ht_lookup(const SAddr& A, uint32_t key) {
+    uint32_t slot = ht_home(key, A.tsize);
+    const uint32_t step = ht_step(key, A.tsize);
     while (true) {
-        const uint2 e = lds64(stable + slot * 8u);
+        const uint2 e = lds64(A.table + slot * 8u);
         if (e.x == key) return e.y;
         if (e.x == kEmpty) return 0u;
         slot += step;
-        if (slot >= (uint32_t)kSlots) slot -= (uint32_t)kSlots;
+        if (slot >= A.tsize) slot -= A.tsize;
     }
 }
 
-// branch-free: an invalid column (key = 0xffffffff, valid = false) still reads an in-range word
-__device__ __forceinline__ bool flt_test(uint32_t sfilter, uint32_t key) {
+// word of the filter with the key's bit shifted down to bit 0 (bits above it are garbage)
+__device__ __forceinline__ uint32_t flt_probe(const SAddr& A, uint32_t key) {
     const uint32_t h = flt_hash(key);
-    const uint32_t w = lds32(sfilter + flt_word(h));
-    return ((w >> ((h >> 13) & 31)) & (w >> ((h >> 8) & 31)) & 1u) != 0u;
+    return lds32(A.filter + flt_word(h, A)) >> (h & 31);
 }
+__device__ __forceinline__ bool flt_test(const SAddr& A, uint32_t key) { return (flt_probe(A, key) & 1u) != 0u; }
 
 __device__ __forceinline__ void add_bits(unsigned* acc, uint32_t mask) {
     while (mask) {
@@ -141,7 +158,7 @@ __device__ __forceinline__ void add_bits(unsigned* acc, uint32_t mask) {
 __device__ __forceinline__ void q_lookup(BuildSmem& S, const SAddr& A, uint32_t sq, int lane, int count) {
     if (lane < count) {
         const uint32_t w = lds32(sq + lane * 4u);
-        add_bits(S.acc3[w >> kTagShift], ht_lookup(A.table, w & ((1u << kTagShift) - 1u)));
+        add_bits(S.acc3[w >> kTagShift], ht_lookup(A, w & ((1u << kTagShift) - 1u)));
     }
 }
 
@@ -171,56 +188,78 @@ __device__ __forceinline__ void q_drain(BuildSmem& S, const SAddr& A, uint32_t s
     tail = 0;
 }
 
-// stream columns [start, d) of one frontier row with stride `stride` (both multiples of 256),
-// push the filter survivors of link slot e into this warp's queue
+// One step of the frontier walk: K x 32 consecutive columns starting at b2 (K independent 128-byte
+// loads in flight per warp), filter test, survivors of link slot `tag` compacted into the warp's queue.
+template <int K>
+__device__ __forceinline__ void walk_step(BuildSmem& S, const SAddr& A, uint32_t sq, const int32_t* __restrict__ rowp,
+                                          int d, uint32_t tag, int b2, int lane, int& tail) {
+    int32_t l[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int idx = b2 + k * 32 + lane;
+        l[k] = idx < d ? ldg_i32(rowp + idx) : -1;
+    }
+    if (K == 1) {
+        const bool pass = (l[0] >= 0) && flt_test(A, (uint32_t)l[0]);
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (bal == 0u) return;
+        if (pass) sts32(sq + (uint32_t)(tail + __popc(bal & ((1u << lane) - 1u))) * 4u, (uint32_t)l[0] | tag);
+        tail += __popc(bal);
+        q_service(S, A, sq, lane, tail);
+        return;
+    }
+    // funnel-shift accumulate: after K steps the K filter bits sit in the top K bits, first column lowest
+    unsigned acc = 0u;
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc = __funnelshift_r(acc, flt_probe(A, (uint32_t)l[k]), 1);
+    int nvalid = (d - b2 - lane + 31) >> 5;  // columns of this lane inside the row (the invalid ones trail)
+    nvalid = nvalid < 0 ? 0 : (nvalid > K ? K : nvalid);
+    const unsigned flags = (acc >> (32 - K)) & ((1u << nvalid) - 1u);
+    if (!__any_sync(0xffffffffu, flags != 0u)) return;
+    // exclusive warp scan of the per-lane survivor counts
+    const int cnt = __popc(flags);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (tail + total <= kQueue) {
+        uint32_t off = sq + (uint32_t)(tail + incl - cnt) * 4u;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (flags & (1u << k)) {
+                sts32(off, (uint32_t)l[k] | tag);
+                off += 4u;
+            }
+        }
+        tail += total;
+        q_service(S, A, sq, lane, tail);
+    } else {
+        // rare: more survivors than queue space; push one column slot at a time
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const bool p = (flags >> k) & 1u;
+            const unsigned bal = __ballot_sync(0xffffffffu, p);
+            if (p) sts32(sq + (uint32_t)(tail + __popc(bal & ((1u << lane) - 1u))) * 4u, (uint32_t)l[k] | tag);
+            tail += __popc(bal);
+            q_service(S, A, sq, lane, tail);
+        }
+    }
+}
+
+// stream columns of one frontier row: chunks [start + n*stride, +256) (start, stride multiples of 256);
+// the last partial chunk of the row takes a narrower step
 __device__ __forceinline__ void walk_row(BuildSmem& S, const SAddr& A, uint32_t sq, const int32_t* __restrict__ col,
                                          int64_t rs, int d, int e, int start, int stride, int lane, int& tail) {
     const uint32_t tag = (uint32_t)e << kTagShift;
+    const int32_t* rowp = col + rs;
     for (int b2 = start; b2 < d; b2 += stride) {
-        int32_t l[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int idx = b2 + k * 32 + lane;
-            l[k] = idx < d ? ldg_i32(col + rs + idx) : -1;
-        }
-        unsigned flags = 0u;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const unsigned pass = (unsigned)flt_test(A.filter, (uint32_t)l[k]) & (unsigned)(l[k] >= 0);
-            flags |= pass << k;
-        }
-        if (!__any_sync(0xffffffffu, flags != 0u)) continue;
-        // exclusive warp scan of the per-lane survivor counts
-        const int cnt = __popc(flags);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (tail + total <= kQueue) {
-            uint32_t off = sq + (uint32_t)(tail + incl - cnt) * 4u;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (flags & (1u << k)) {
-                    sts32(off, (uint32_t)l[k] | tag);
-                    off += 4u;
-                }
-            }
-            tail += total;
-            q_service(S, A, sq, lane, tail);
-        } else {
-            // rare: more survivors than queue space; push one column slot at a time
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const bool p = (flags >> k) & 1u;
-                const unsigned bal = __ballot_sync(0xffffffffu, p);
-                if (p) sts32(sq + (uint32_t)(tail + __popc(bal & ((1u << lane) - 1u))) * 4u, (uint32_t)l[k] | tag);
-                tail += __popc(bal);
-                q_service(S, A, sq, lane, tail);
-            }
-        }
+        const int rem = d - b2;
+        if (rem > 128) walk_step<8>(S, A, sq, rowp, d, tag, b2, lane, tail);
+        else if (rem > 32) walk_step<4>(S, A, sq, rowp, d, tag, b2, lane, tail);
+        else walk_step<1>(S, A, sq, rowp, d, tag, b2, lane, tail);
     }
 }
 
@@ -234,7 +273,7 @@ __device__ __forceinline__ void flush_long_rows(BuildSmem& S, const SAddr& A, ui
     }
 }
 
-__global__ void __launch_bounds__(kBuildThreads, 2)
+__global__ void __launch_bounds__(kBuildThreads, kBuildCtasPerSm)
 k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
            const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int order,
            const int64_t* __restrict__ rec_off, const int32_t* __restrict__ run_start,
@@ -245,6 +284,9 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
     SAddr A;
+    A.tsize = (uint32_t)kSlots;
+    A.fshift = 0u;
+    A.fmask = 0u;
     A.table = sbase + (uint32_t)offsetof(BuildSmem, table);
     A.filter = sbase + (uint32_t)offsetof(BuildSmem, filter);
     A.queue = sbase + (uint32_t)offsetof(BuildSmem, qkey);
@@ -328,15 +370,17 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
                 ++chunk;
             }
         }
-        for (int s = tid; s < (kSlots + 1) / 2; s += kBuildThreads)
-            reinterpret_cast<uint4*>(S.table)[s] = make_uint4(kEmpty, 0u, kEmpty, 0u);
-        for (int s = tid; s < kFilterWords; s += kBuildThreads) S.filter[s] = 0u;
         __syncthreads();
 
         const int64_t p0 = (int64_t)S.chunk * kPChunk;
         const int np = (int)((d - p0) < kPChunk ? (d - p0) : kPChunk);
         const int total_keys = S.kpre[32];
         const int k_lo = S.pass * kCap, k_hi = (k_lo + kCap < total_keys) ? k_lo + kCap : total_keys;
+        pick_geometry(k_hi - k_lo, A);
+        for (int s = tid; s < (int)(A.tsize + 1) / 2; s += kBuildThreads)
+            reinterpret_cast<uint4*>(S.table)[s] = make_uint4(kEmpty, 0u, kEmpty, 0u);
+        for (int s = tid; s <= (int)(A.fmask >> 2); s += kBuildThreads) S.filter[s] = 0u;
+        __syncthreads();
         // keys [k_lo, k_hi) of the flattened list, an equal share per warp; inside a share the warp walks
         // the rows it spans with coalesced loads (no per-key search, no barrier imbalance)
         {
@@ -352,7 +396,7 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
                 while (pos < end) {
                     const int seg_end = S.kpre[a + 1] < end ? S.kpre[a + 1] : end;
                     const int32_t* rowp = col + S.krs[a] - S.kpre[a];
-                    for (int idx = pos + lane; idx < seg_end; idx += 32) ht_insert(S, (uint32_t)ldg_i32(rowp + idx), 1u << a);
+                    for (int idx = pos + lane; idx < seg_end; idx += 32) ht_insert(S, A, (uint32_t)ldg_i32(rowp + idx), 1u << a);
                     pos = seg_end;
                     ++a;
                 }
@@ -398,7 +442,7 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
             __syncthreads();
 
             // order 1: is j itself a key?  (one lookup per link, by the unit holding the link's first piece)
-            if (tid < ne) S.m1[tid] = S.m1[tid] ? ht_lookup(A.table, (uint32_t)dst[g0 + tid]) : 0u;
+            if (tid < ne) S.m1[tid] = S.m1[tid] ? ht_lookup(A, (uint32_t)dst[g0 + tid]) : 0u;
             if (order >= 2) {
                 // phase 1: warps pull (link, neighbour m of j) items; m itself feeds C2, its row feeds C3
                 const int n_items = S.jpre[kEdgeSub];
@@ -412,7 +456,7 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
                     for (int s = kEdgeSub / 2; s > 0; s >>= 1)
                         if (S.jpre[e + s] <= item) e += s;
                     const int32_t m = ldg_i32(col + S.jrs[e] + (item - S.jpre[e]));
-                    if (lane == 0 && flt_test(A.filter, (uint32_t)m)) add_bits(S.acc2[e], ht_lookup(A.table, (uint32_t)m));
+                    if (lane == 0 && flt_test(A, (uint32_t)m)) add_bits(S.acc2[e], ht_lookup(A, (uint32_t)m));
                     if (order >= 3) {
                         const int64_t rs_m = ldg_i64(rowptr + m);
                         const int dm = (int)(ldg_i64(rowptr + m + 1) - rs_m);
@@ -501,7 +545,7 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
     OCN_CUDA(cudaFuncSetAttribute(k_cn_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BuildSmem)));
     OCN_CUDA(cudaMemsetAsync((void*)(plan + OCN_PLAN_UNIT_COUNTER), 0, sizeof(int64_t), st));  // restart the dynamic unit counter
     if (records_capacity > 0) OCN_CUDA(cudaMemsetAsync(records, 0, sizeof(Record) * (size_t)records_capacity, st));
-    const int blocks = sm_count() * 2;
+    const int blocks = sm_count() * kBuildCtasPerSm;
     k_cn_build<<<blocks, kBuildThreads, sizeof(BuildSmem), st>>>(
         rowptr, col, n, src, dst, order, rec_off, (const int32_t*)(base + L.run_start),
         (const int64_t*)(base + L.run_unit_off), (const int64_t*)(base + L.cost_pre), (int64_t*)plan, (Record*)records);

@@ -166,7 +166,7 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
     size_t tmp_bytes = L.cub_temp_bytes;
     int64_t T = num_edges;
     int64_t* cost_pre = (int64_t*)(base + L.cost_pre);
-    const int resident_ctas = sm_count() * 2;
+    const int resident_ctas = sm_count() * kBuildCtasPerSm;
     int threads = 256;
     int blocks = (int)((T + 1 + threads - 1) / threads);
     OCN_CUDA(cudaMemsetAsync(out_plan, 0, sizeof(int64_t) * OCN_PLAN_WORDS, st));

@@ -35,7 +35,7 @@ int sm_count();
 // ---- constants shared by the plan and the build kernel -----------------------------------
 constexpr int kPChunk = 32;   // positions of N(src) handled by one work unit (one mask word)
 constexpr int kEdgeSub = 32;  // target links of a run handled by one work unit
-constexpr int kSlots = 9721;  // (key, mask) slots of the shared-memory table of ocn_cn_build (prime, 76 KB)
+constexpr int kSlots = 20983;  // (key, mask) slots of the shared-memory table of ocn_cn_build (prime, 164 KB)
 constexpr int kCap = (kSlots * 7) / 10;  // keys inserted per table pass (load factor 0.7)
 
 // one record per (target link, position p in N(src)):
@@ -71,10 +71,11 @@ PlanLayout plan_layout(int64_t num_edges);
 // clamped so that a unit amortises its table build but a heavy link is still split over many CTAs
 __host__ __device__ inline long long unit_budget(long long total_cost, int resident_ctas) {
     long long w = total_cost / (8ll * (resident_ctas > 0 ? resident_ctas : 1));
-    if (w < 32768) w = 32768;
-    if (w > 262144) w = 262144;
+    if (w < 65536) w = 65536;
+    if (w > 524288) w = 524288;
     return w;
 }
+constexpr int kBuildCtasPerSm = 1;  // one 1024-thread CTA per SM owns (almost) all shared memory
 constexpr int kLinkCost = 64;  // fixed cost added to every link so that empty links still advance
 
 // plan[] words beyond the public ones

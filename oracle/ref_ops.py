@@ -159,6 +159,29 @@ def sp_matmul(a: Sp, b: Sp) -> Sp:
     return Sp(r, c, tc.values().float(), (a.shape[0], b.shape[1]))
 
 
+def spspmm_expand(a: Sp, b: Sp) -> Sp:
+    """pygho ``spspmm(A, 1, B, 0)`` the way pygho computes it [recalled]: every nonzero (r, k) of A is
+    expanded against row k of B (searchsorted/cumsum bookkeeping), the products are keyed by (r, c),
+    sorted/uniqued and scatter-summed.  Pure index arithmetic -- no library SpGEMM."""
+    rp = getattr(b, "_rowptr_cache", None)
+    if rp is None:
+        rp = b.rowptr()
+        b._rowptr_cache = rp
+    start = rp[a.col]
+    cnt = rp[a.col + 1] - start
+    total = int(cnt.sum())
+    if total == 0:
+        e = torch.zeros(0, dtype=torch.int64)
+        return Sp(e, e, torch.zeros(0), (a.shape[0], b.shape[1]))
+    owner = torch.repeat_interleave(torch.arange(a.nnz, dtype=torch.int64), cnt)
+    pos = torch.arange(total, dtype=torch.int64) + torch.repeat_interleave(start - (torch.cumsum(cnt, 0) - cnt), cnt)
+    key = a.row[owner] * b.shape[1] + b.col[pos]
+    val = a.values()[owner] * (b.val[pos] if b.val is not None else 1.0)
+    ukey, inv = torch.unique(key, return_inverse=True)
+    out = torch.zeros(ukey.numel(), dtype=torch.float32).index_add_(0, inv, val)
+    return Sp(torch.div(ukey, b.shape[1], rounding_mode="floor"), ukey % b.shape[1], out, (a.shape[0], b.shape[1]))
+
+
 def adj2_true(adj: Sp, keep_value: bool = False) -> Sp:
     """``SparseTensor.from_torch_sparse_coo_tensor(spadj @ spadj, False)``: structure of A^2,
     values dropped; the diagonal is part of it (Q12)."""
@@ -207,7 +230,7 @@ def get_cn(adj: Sp, tedge: Tensor, order: int = 2) -> List[Sp]:
     out = [spsphadamard(Ei, Ej)]
     Ejk = Ej
     for _ in range(1, order):
-        Ejk = sp_matmul(Ejk, adj)
+        Ejk = spspmm_expand(Ejk, adj)
         out.append(spsphadamard(Ei, Ejk))
     return out
 

@@ -1,0 +1,93 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/ocn_b200.h declares,
+argument validation works without a GPU, the product never falls back to the CPU, host-side logic."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+import ocn_b200 as ob
+from ocn_b200 import _lib, synth
+from ocn_b200.cn import waves
+
+
+def test_library_exports_every_header_symbol():
+    L = _lib.lib()
+    syms = _lib.header_symbols()
+    assert len(syms) >= 24
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/ocn_b200.h but not exported"
+        assert s in _lib._SIGS, f"{s} has no ctypes signature"
+    assert L.ocn_abi_version() == 1
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    L = _lib.lib()
+    assert L.ocn_cn_plan_bytes(-1) == 0 and L.ocn_cn_plan_bytes(1000) > 1000 * 8
+    assert L.ocn_cn_record_bytes() == 8 and L.ocn_cn_colstat_bytes(10) == 320
+    rc = L.ocn_cn_build(None, None, 0, None, None, 0, 0, 2, 1, None, None, None, 0, None, None)
+    assert rc == -1 and b"null pointer" in L.ocn_last_error()
+    rc = L.ocn_spmm_csr(None, None, None, 4, None, 32, 0, None, None)
+    assert rc == -1
+    rc = L.ocn_spgemm_a2_symbolic(None, None, 4, 0, None, None, None)
+    assert rc == -1
+
+
+def test_no_cpu_fallback():
+    g = synth.tiny_graph(30, 80, 1)
+    G = ob.Graph(g.rowptr, g.col, g.n)  # CPU tensors
+    e = g.query_edges(8, "neg")
+    with pytest.raises(_lib.OcnError):
+        ob.adjoverlap(G, G, e)
+    with pytest.raises(_lib.OcnError):
+        ob.CNSession(G, e)
+    with pytest.raises(_lib.OcnError):
+        ob.spmm_add(G, torch.zeros(30, 4))
+    with pytest.raises(_lib.OcnError):
+        ob.pure_conv(torch.zeros(30, 4), G, "gcn")
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "ocn_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_graph_and_synth_host_logic():
+    g = synth.make_graph("cora")
+    assert g.n == 2708 and abs(g.nnz - 10556) < 400
+    keep = g.raw_src != g.raw_dst  # the generator drops self loops, from_edge_index (like the reference) keeps them
+    G = ob.Graph.from_edge_index(torch.stack((g.raw_src[keep], g.raw_dst[keep])), g.n)
+    assert torch.equal(G.rowptr, g.rowptr) and torch.equal(G.col, g.col)
+    deg = G.degree()
+    assert int(deg.sum()) == g.nnz and G.sizes() == (2708, 2708)
+    # symmetric, sorted, deduplicated
+    r = G.row()
+    key = r * g.n + G.col.long()
+    assert bool((key[1:] > key[:-1]).all())
+    rev = torch.sort(G.col.long() * g.n + r).values
+    assert torch.equal(rev, key)
+    # generators are seed-deterministic and device independent by construction (integer hash)
+    g2 = synth.make_graph("cora")
+    assert torch.equal(g2.col, g.col)
+    e = g.query_edges(3000, "stream")
+    assert e.shape == (2, 3000) and bool((e[0, :1000] == e[0, 0]).all()) and bool((deg[e[0]] > 0).all())
+
+
+def test_waves_cover_the_stream():
+    w = waves(10 * 2048 + 5, 2048, 1000, budget_bytes=3 * 32 * 1000)
+    assert w[0] == (0, 3 * 2048) and w[-1][1] == 10 * 2048 + 5
+    assert all(a[1] == b[0] for a, b in zip(w, w[1:]))
+
+
+def test_predictor_state_dict_keys_match_reference_layout():
+    p = ob.CNLinkPredictorOringin(32, 32, 1, 3, 0.0)
+    keys = set(p.state_dict().keys())
+    for k in ("beta", "alpha", "innerprod", "dropadj.ratio", "xcn1lin.0.weight", "xcn2lin.7.bias", "xcn4lin.3.weight",
+              "xijlin.0.weight", "xijlin.4.bias", "lin.0.weight", "lin.8.weight", "xcnlin.7.weight"):
+        assert k in keys, k
+    p6 = ob.CNLinkPredictor3hopCNs(32, 32, 1, 3, 0.0)
+    assert "xcn3lin.7.weight" in p6.state_dict() and "xcn4lin.0.weight" not in p6.state_dict()
