@@ -1,0 +1,107 @@
+"""Golden fixtures produced by EXECUTING the reference's own model.py / utils.py / get_cn1_cn2
+(oracle/make_golden.py, on a pure-torch stand-in of torch_sparse / pygho).
+
+* CPU: the oracle restatement (oracle/ref_ops.py) must reproduce them  -> pins the oracle.
+* GPU: the CUDA path (through the C ABI and the predictor mirror, loading the reference's
+  state_dict) must reproduce them                                       -> parity with the reference code.
+"""
+import glob
+import os
+
+import pytest
+import torch
+
+import ocn_b200 as ob
+from oracle import ref_ops as R
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_model_*.pt")))
+assert len(GOLDEN) >= 9
+
+
+def _load(path):
+    return torch.load(path, weights_only=False)
+
+
+def _sp(d):
+    return R.Sp(d["row"], d["col"], d["val"], tuple(d["shape"]))
+
+
+def _same_sparse(a: R.Sp, d, values=True):
+    assert torch.equal(a.row, d["row"]) and torch.equal(a.col, d["col"])
+    if values:
+        assert torch.equal(a.values(), d["val"] if d["val"] is not None else torch.ones(a.nnz))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[10:-3] for p in GOLDEN])
+def test_oracle_reproduces_reference_execution(path):
+    fx = _load(path)
+    A = R.sp_from_csr(fx["rowptr"], fx["col"])
+    x = fx["x"]
+    st = R.InnerProdState()
+    training = fx["mode"] == "train"
+    a2 = R.adj2_true(A) if fx["style"] == "large" else None
+    for call in fx["calls"]:
+        e = call["edges"]
+        if fx["style"] == "large":
+            cn1, cn2 = R.adjoverlap(A, A, e), R.adjoverlap(A, a2, e)
+            cns = [cn1, cn2]
+        else:
+            cns = R.get_cn(A, e, 3 if fx["predictor"] == "cn6" else 2)
+        _same_sparse(cns[0], call["cn1"])
+        _same_sparse(cns[1], call["cn2"])
+        if fx["predictor"] == "cn6":
+            _same_sparse(cns[2], call["cn3"])
+            out = R.cn6_aggregate(cns[0], cns[1], cns[2], x, e, st, training)
+            assert torch.allclose(out[2], call["xcn3lin"], rtol=1e-5, atol=1e-6)
+        elif fx["predictor"] == "cn7":
+            out = R.cn7_aggregate(cns[0], cns[1], x, e, fx["fill"])
+        else:
+            out = R.cn5_aggregate(cns[0], cns[1], x, e, st, training)
+        assert torch.allclose(out[0], call["xcn1lin"], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(out[1], call["xcn2lin"], rtol=1e-5, atol=1e-6)
+        assert torch.equal(x[e[0]] * x[e[1]], call["xijlin"])
+        if fx["predictor"] != "cn7":
+            assert torch.allclose(st.innerprod, call["innerprod"], rtol=1e-6, atol=1e-7) and st.n == call["n"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[10:-3] for p in GOLDEN])
+def test_cuda_path_reproduces_reference_execution(path):
+    fx = _load(path)
+    dev = "cuda:0"
+    G = ob.Graph(fx["rowptr"].to(dev), fx["col"].to(dev), fx["n"])
+    x = fx["x"].to(dev)
+    F = fx["F"]
+    cls = {"cn5": ob.CNLinkPredictorOringin, "cn6": ob.CNLinkPredictor3hopCNs, "cn7": ob.CNLinkPredictorbaselearn}[fx["predictor"]]
+    pred = cls(F, F, 1, 3, 0.0, ln=fx["ln"], weighted=(fx["style"] == "pygho")).to(dev)
+    pred.load_state_dict({k: v.to(dev) for k, v in fx["state_dict"].items()})
+    pred.train() if fx["mode"] == "train" else pred.eval()
+    order = 3 if fx["predictor"] == "cn6" else 2
+
+    class Args:
+        sum = fx["fill"]
+
+    for call in fx["calls"]:
+        e = call["edges"].to(dev)
+        # CN index sets / values, bit-exact
+        got = ob.get_cn(G, e, order, weighted=(fx["style"] == "pygho"))
+        for k in range(order):
+            ref = call[f"cn{k + 1}"]
+            rp = torch.zeros(e.shape[1] + 1, dtype=torch.long)
+            torch.cumsum(torch.bincount(ref["row"], minlength=e.shape[1]), 0, out=rp[1:])
+            assert torch.equal(got[k].rowptr.cpu(), rp) and torch.equal(got[k].col.cpu(), ref["col"])
+            assert torch.equal(got[k].value.cpu(), ref["val"] if ref["val"] is not None else torch.ones(ref["row"].numel()))
+        with torch.no_grad():
+            fill = float(fx["fill"] or 0.0) if fx["predictor"] == "cn7" else 0.0
+            xcn1, xcn2, xcn3, xij, _ = pred.cn_stage(x, G, e, fill)
+            scale = lambda t: 1.0 + t.abs().max().item()
+            assert (xcn1.cpu() - call["xcn1lin"]).abs().max().item() <= 2e-5 * scale(call["xcn1lin"])
+            assert (xcn2.cpu() - call["xcn2lin"]).abs().max().item() <= 1e-4 * scale(call["xcn2lin"])
+            if order == 3:
+                assert (xcn3.cpu() - call["xcn3lin"]).abs().max().item() <= 1e-4 * scale(call["xcn3lin"])
+            assert torch.equal(xij.cpu(), call["xijlin"])
+            out = pred._head(xcn1, xcn2, xcn3, xij)
+            assert torch.allclose(out.cpu(), call["out"], rtol=1e-3, atol=1e-4)
+        if fx["predictor"] != "cn7":
+            assert pred.n == call["n"]
+            assert abs(pred.innerprod.item() - call["innerprod"].item()) <= 1e-4 * (1 + abs(call["innerprod"].item()))
