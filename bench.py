@@ -257,7 +257,9 @@ def main():
         e = e_rank[:, s * T:(s + 1) * T]
         sess = ob.CNSession(G, e, a.batch, a.order).build(a.order, True)
         sess.stats(5, 0.0, ip3, 0)
-        return sess.aggregate(x, 5, 0.0, ip3)
+        out = sess.aggregate(x, 5, 0.0, ip3)
+        sess.release()
+        return out
 
     def step_e2e(s):
         e = e_host[:, s * T:(s + 1) * T].to(dev, non_blocking=True)
@@ -318,6 +320,7 @@ def main():
         sess.build(a.order, True)
         ev1.record()
         torch.cuda.synchronize()
+        sess.release()
         build_ms.append(ev0.elapsed_time(ev1))
     build_avg = sum(build_ms) / len(build_ms)
     bb = [algorithmic_bytes(G, e_rank[:, s * T:(s + 1) * T], a.order, a.feat, a.batch) for s in range(a.warmup, nsteps)]
@@ -343,7 +346,7 @@ def main():
             "e2e": {"value": links / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * T,
                     "d2h_bytes_per_step": 4 * T * (world if world > 1 else 1), "ms_per_step": ms_e2e / a.steps,
                     "api": "CNLinkPredictor*.forward(h, adj, CNSession, ..., edges) -> scores.cpu()"},
-            "gpu_launches": 10 * a.steps,
+            "gpu_launches": 12 * a.steps,  # per step: 5 plan + build + colstat + 3 stats + aggregate + release (CUB scans not counted)
             "roofline": {"bound": "hbm", "kernel": "k_cn_build", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": build_bytes, "kernel_ms": build_avg,

@@ -35,8 +35,8 @@ constexpr uint32_t kEmpty = 0xffffffffu;
 constexpr int kFilterBits = 18;                       // 262144-bit filter (32 KB)
 constexpr int kFilterWords = 1 << (kFilterBits - 5);
 constexpr int kQueue = 96;                            // per-warp queue of filter survivors
-constexpr int kLongRow = 4096;                        // rows longer than this are walked by the whole CTA
-constexpr int kMaxLong = 192;                         // deferred long rows per pass before an early flush
+constexpr int kLongRow = 1024;                        // rows longer than this are walked by the whole CTA
+constexpr int kMaxLong = 256;                         // deferred long rows per pass before an early flush
 
 struct BuildSmem {
     uint2 table[kSlots + 7];
