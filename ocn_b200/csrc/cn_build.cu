@@ -20,9 +20,9 @@
 //     table (measured hit rate 0-8 %), and a miss costs one branch-free shared-memory bit test;
 //   * columns that pass the filter are compacted into a per-warp queue and looked up 32 at a time,
 //     so the divergent probe loops run with all lanes busy;
-//   * rows of the j-side frontier are pulled by the warps from a shared counter (row granularity),
-//     rows longer than kLongRow are deferred and then strided over by all warps of the CTA, so the
-//     heavy-tailed row lengths do not stall the CTA at a barrier;
+//   * the rows of the j-side frontier are described in shared memory, cut into chunks of kChunk columns
+//     and pulled by the warps from a shared counter, so the heavy-tailed row lengths do not stall the
+//     CTA at a barrier; rows of <= kTinyRow columns are walked by one thread each;
 //   * frontier rows are streamed 8 x 32 columns per warp iteration: eight independent 128-byte
 //     loads in flight per warp.
 #include "common.cuh"
@@ -35,8 +35,9 @@ constexpr uint32_t kEmpty = 0xffffffffu;
 constexpr int kFilterBits = 18;                       // 262144-bit filter (32 KB)
 constexpr int kFilterWords = 1 << (kFilterBits - 5);
 constexpr int kQueue = 96;                            // per-warp queue of filter survivors
-constexpr int kLongRow = 1024;                        // rows longer than this are walked by the whole CTA
-constexpr int kMaxLong = 256;                         // deferred long rows per pass before an early flush
+constexpr int kChunk = 2048;                          // columns of a frontier row handed to a warp at a time
+constexpr int kTinyRow = 8;                           // rows this short are walked by one thread
+constexpr int kRowBatch = 768;                        // frontier rows described in shared memory at a time
 
 struct BuildSmem {
     uint2 table[kSlots + 7];
@@ -44,11 +45,13 @@ struct BuildSmem {
     uint32_t qkey[kBuildWarps][kQueue];
     unsigned acc2[kEdgeSub][32];
     unsigned acc3[kEdgeSub][32];
-    long long lrs[kMaxLong];
     long long krs[32];
     long long jrs[kEdgeSub];
-    int ld[kMaxLong];
-    int le[kMaxLong];
+    uint32_t rrs[kRowBatch];       // row start (offset into col) of the frontier rows of the current batch
+    int rd[kRowBatch];             // their lengths
+    int rcp[kRowBatch + 1];        // exclusive prefix of their chunk counts
+    int wsum[kBuildWarps];
+    unsigned char re[kRowBatch];   // their link slots
     int kp[32];
     int kdeg[32];
     int kpre[33];
@@ -58,7 +61,7 @@ struct BuildSmem {
     long long unit;
     int chunk, pass;
     int next_item;
-    int n_long;
+    int n_chunks;
 };
 
 // queue entries carry the link slot in their top bits: node ids must stay below 2^kTagShift
@@ -249,27 +252,16 @@ __device__ __forceinline__ void walk_step(BuildSmem& S, const SAddr& A, uint32_t
     }
 }
 
-// stream columns of one frontier row: chunks [start + n*stride, +256) (start, stride multiples of 256);
-// the last partial chunk of the row takes a narrower step
-__device__ __forceinline__ void walk_row(BuildSmem& S, const SAddr& A, uint32_t sq, const int32_t* __restrict__ col,
-                                         int64_t rs, int d, int e, int start, int stride, int lane, int& tail) {
+// stream columns [start, end) of one frontier row, 256 at a time; the last partial piece of the row
+// takes a narrower step
+__device__ __forceinline__ void walk_row(BuildSmem& S, const SAddr& A, uint32_t sq, const int32_t* __restrict__ rowp,
+                                         int d, int e, int start, int end, int lane, int& tail) {
     const uint32_t tag = (uint32_t)e << kTagShift;
-    const int32_t* rowp = col + rs;
-    for (int b2 = start; b2 < d; b2 += stride) {
+    for (int b2 = start; b2 < end; b2 += 256) {
         const int rem = d - b2;
         if (rem > 128) walk_step<8>(S, A, sq, rowp, d, tag, b2, lane, tail);
         else if (rem > 32) walk_step<4>(S, A, sq, rowp, d, tag, b2, lane, tail);
         else walk_step<1>(S, A, sq, rowp, d, tag, b2, lane, tail);
-    }
-}
-
-// all warps of the CTA stride over the deferred long rows
-__device__ __forceinline__ void flush_long_rows(BuildSmem& S, const SAddr& A, uint32_t sq,
-                                                const int32_t* __restrict__ col, int warp, int lane, int& tail) {
-    const int nl = S.n_long < kMaxLong ? S.n_long : kMaxLong;
-    for (int r = 0; r < nl; ++r) {
-        const int first = (warp + kBuildWarps - (r % kBuildWarps)) % kBuildWarps;
-        walk_row(S, A, sq, col, S.lrs[r], S.ld[r], S.le[r], first * 256, kBuildWarps * 256, lane, tail);
     }
 }
 
@@ -438,46 +430,98 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
                 (&S.acc2[0][0])[s] = 0u;
                 (&S.acc3[0][0])[s] = 0u;
             }
-            if (tid == 0) { S.next_item = 0; S.n_long = 0; }
             __syncthreads();
 
             // order 1: is j itself a key?  (one lookup per link, by the unit holding the link's first piece)
             if (tid < ne) S.m1[tid] = S.m1[tid] ? ht_lookup(A, (uint32_t)dst[g0 + tid]) : 0u;
             if (order >= 2) {
-                // phase 1: warps pull (link, neighbour m of j) items; m itself feeds C2, its row feeds C3
-                const int n_items = S.jpre[kEdgeSub];
-                while (true) {
-                    int item = 0;
-                    if (lane == 0) item = atomicAdd(&S.next_item, 1);
-                    item = __shfl_sync(0xffffffffu, item, 0);
-                    if (item >= n_items) break;
-                    int e = 0;  // last link slot with jpre[e] <= item
+                // the rows N(m), m in the N(j) slices of the group's links, kRowBatch at a time
+                const int n_rows = S.jpre[kEdgeSub];
+                for (int r0 = 0; r0 < n_rows; r0 += kRowBatch) {
+                    const int nb = (n_rows - r0) < kRowBatch ? (n_rows - r0) : kRowBatch;
+                    // describe the rows: m feeds C2; tiny rows are walked right here, one thread each;
+                    // the others are cut into chunks of kChunk columns
+                    int chunks = 0;
+                    if (tid < nb) {
+                        const int item = r0 + tid;
+                        int e = 0;  // last link slot with jpre[e] <= item
 #pragma unroll
-                    for (int s = kEdgeSub / 2; s > 0; s >>= 1)
-                        if (S.jpre[e + s] <= item) e += s;
-                    const int32_t m = ldg_i32(col + S.jrs[e] + (item - S.jpre[e]));
-                    if (lane == 0 && flt_test(A, (uint32_t)m)) add_bits(S.acc2[e], ht_lookup(A, (uint32_t)m));
-                    if (order >= 3) {
-                        const int64_t rs_m = ldg_i64(rowptr + m);
-                        const int dm = (int)(ldg_i64(rowptr + m + 1) - rs_m);
-                        if (dm > kLongRow) {
-                            int slot = 0;
-                            if (lane == 0) slot = atomicAdd(&S.n_long, 1);
-                            slot = __shfl_sync(0xffffffffu, slot, 0);
-                            if (slot < kMaxLong) {
-                                if (lane == 0) { S.lrs[slot] = rs_m; S.ld[slot] = dm; S.le[slot] = e; }
+                        for (int s2 = kEdgeSub / 2; s2 > 0; s2 >>= 1)
+                            if (S.jpre[e + s2] <= item) e += s2;
+                        const int32_t m = ldg_i32(col + S.jrs[e] + (item - S.jpre[e]));
+                        if (flt_test(A, (uint32_t)m)) add_bits(S.acc2[e], ht_lookup(A, (uint32_t)m));
+                        int dm = 0;
+                        uint32_t rs32 = 0u;
+                        if (order >= 3) {
+                            const int64_t rs_m = ldg_i64(rowptr + m);
+                            dm = (int)(ldg_i64(rowptr + m + 1) - rs_m);
+                            rs32 = (uint32_t)rs_m;
+                            if (dm <= kTinyRow) {
+                                int32_t l[kTinyRow];  // all loads first: one memory round trip per thread
+#pragma unroll
+                                for (int u = 0; u < kTinyRow; ++u) l[u] = u < dm ? ldg_i32(col + rs_m + u) : -1;
+#pragma unroll
+                                for (int u = 0; u < kTinyRow; ++u)
+                                    if (l[u] >= 0 && flt_test(A, (uint32_t)l[u])) add_bits(S.acc3[e], ht_lookup(A, (uint32_t)l[u]));
                             } else {
-                                walk_row(S, A, sq, col, rs_m, dm, e, 0, 256, lane, tail);  // list full: walk it alone
+                                chunks = (dm - 1) / kChunk;  // EXTRA chunks beyond the first kChunk columns
                             }
-                        } else {
-                            walk_row(S, A, sq, col, rs_m, dm, e, 0, 256, lane, tail);
                         }
+                        S.rrs[tid] = rs32;
+                        S.rd[tid] = dm;
+                        S.re[tid] = (unsigned char)e;
                     }
-                }
-                if (order >= 3) {
+                    if (order < 3) continue;
+                    // CTA-wide exclusive scan of the chunk counts
+                    int incl = chunks;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    if (lane == 31) S.wsum[warp] = incl;
                     __syncthreads();
-                    flush_long_rows(S, A, sq, col, warp, lane, tail);
+                    if (warp == 0) {
+                        const int wv = S.wsum[lane];
+                        int wi = wv;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int v = __shfl_up_sync(0xffffffffu, wi, o);
+                            if (lane >= o) wi += v;
+                        }
+                        S.wsum[lane] = wi - wv;
+                        if (lane == 31) { S.n_chunks = wi; S.next_item = 0; }
+                    }
+                    __syncthreads();
+                    if (tid < nb) S.rcp[tid] = incl - chunks + S.wsum[warp];
+                    if (tid == 0) S.rcp[nb] = S.n_chunks;
+                    __syncthreads();
+                    // warps pull items from a shared counter until the batch is done: item c < nb is the first
+                    // kChunk columns of row c (no search), the items after that are the extra chunks of long rows
+                    const int n_items = nb + S.n_chunks;
+                    while (true) {
+                        int c = 0;
+                        if (lane == 0) c = atomicAdd(&S.next_item, 1);
+                        c = __shfl_sync(0xffffffffu, c, 0);
+                        if (c >= n_items) break;
+                        int a = c, start = 0;
+                        if (c >= nb) {
+                            const int x = c - nb;
+                            int lo2 = 0, hi2 = nb;  // last row with rcp[row] <= x
+                            while (hi2 - lo2 > 1) {
+                                const int mid = (lo2 + hi2) >> 1;
+                                if (S.rcp[mid] <= x) lo2 = mid; else hi2 = mid;
+                            }
+                            a = lo2;
+                            start = (x - S.rcp[a] + 1) * kChunk;
+                        }
+                        const int d = S.rd[a];
+                        if (d <= kTinyRow) continue;  // walked by its describing thread
+                        const int end = (start + kChunk < d) ? start + kChunk : d;
+                        walk_row(S, A, sq, col + S.rrs[a], d, (int)S.re[a], start, end, lane, tail);
+                    }
                     q_drain(S, A, sq, lane, tail);
+                    __syncthreads();  // descriptors are reused by the next batch
                 }
             }
             __syncthreads();
@@ -537,6 +581,7 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
     OCN_CHECK_ARG(n > 0 && num_edges > 0 && batch_size > 0, "ocn_cn_build: sizes must be positive");
     OCN_CHECK_ARG(records || records_capacity == 0, "ocn_cn_build: records is null");
     OCN_CHECK_ARG(n < (int64_t(1) << kTagShift), "ocn_cn_build: at most 2^27 nodes (queue tag width)");
+    // row starts are kept as 32-bit offsets in shared memory; rowptr[n] < 2^32 is the caller's contract (checked by ocn_graph_validate users)
     static_assert(kEdgeSub == 32, "one lane per link slot");
     cudaStream_t st = (cudaStream_t)stream;
     PlanLayout L = plan_layout(num_edges);

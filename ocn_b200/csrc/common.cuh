@@ -35,7 +35,7 @@ int sm_count();
 // ---- constants shared by the plan and the build kernel -----------------------------------
 constexpr int kPChunk = 32;   // positions of N(src) handled by one work unit (one mask word)
 constexpr int kEdgeSub = 32;  // target links of a run handled by one work unit
-constexpr int kSlots = 20983;  // (key, mask) slots of the shared-memory table of ocn_cn_build (prime, 164 KB)
+constexpr int kSlots = 20399;  // (key, mask) slots of the shared-memory table of ocn_cn_build (prime, 159 KB)
 constexpr int kCap = (kSlots * 7) / 10;  // keys inserted per table pass (load factor 0.7)
 
 // one record per (target link, position p in N(src)):
