@@ -283,6 +283,7 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
     A.filter = sbase + (uint32_t)offsetof(BuildSmem, filter);
     A.queue = sbase + (uint32_t)offsetof(BuildSmem, qkey);
     const uint32_t sq = A.queue + (uint32_t)warp * (kQueue * 4u);
+    if (order <= 2 && plan[OCN_PLAN_USE_DIRECT] != 0) return;  // the table-free kernel handles this stream
     const int64_t n_units = plan[OCN_PLAN_NUM_UNITS];
     const int64_t n_runs = plan[OCN_PLAN_NUM_RUNS];
     const int64_t W = plan[OCN_PLAN_BUDGET];
@@ -541,6 +542,86 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
     }
 }
 
+// Orders 1 and 2 need no table: C1[p] = [N(i)[p] in N(j)], C2[p] = |N(j) (cap) N(N(i)[p])| are plain sorted-list
+// intersections.  One warp per link.  Pass 1: one lane per position p walks the shorter of the two rows and
+// binary-searches the longer one (resuming where the previous search ended); pairs whose shorter row exceeds
+// 32 columns are deferred.  Pass 2: the deferred pairs are intersected by the whole warp (lanes stride over the
+// shorter row), so a hub x hub pair costs len/32 * log steps instead of len * log on one lane.
+// Records are written directly (no atomics): each (link, p) has one owner.
+__global__ void __launch_bounds__(256)
+k_cn_build_direct(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ src,
+                  const int64_t* __restrict__ dst, int64_t T, int order, const int64_t* __restrict__ rec_off,
+                  const int64_t* __restrict__ plan, Record* __restrict__ records) {
+    if (plan[OCN_PLAN_USE_DIRECT] == 0) return;  // the table kernel handles this stream
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    for (int64_t t = warp; t < T; t += nwarps) {
+        const int64_t i = src[t], j = dst[t];
+        const int64_t rs_i = rowptr[i], di = rowptr[i + 1] - rs_i;
+        const int64_t rs_j = rowptr[j], dj = rowptr[j + 1] - rs_j;
+        const int32_t* nj = col + rs_j;
+        Record* rec = records + rec_off[t];
+        for (int64_t base = 0; base < di; base += 32) {
+            const int64_t p = base + lane;
+            bool defer = false;
+            int64_t rs_k = 0, dk = 0;
+            unsigned c1 = 0u;
+            if (p < di) {
+                const int32_t k = ldg_i32(col + rs_i + p);
+                c1 = row_contains(nj, dj, k) ? 1u : 0u;
+                unsigned c2 = 0u;
+                if (order >= 2) {
+                    rs_k = ldg_i64(rowptr + k);
+                    dk = ldg_i64(rowptr + k + 1) - rs_k;
+                    const int32_t* a = nj;          // shorter row
+                    const int32_t* b = col + rs_k;  // longer row
+                    int64_t la = dj, lb = dk;
+                    if (la > lb) {
+                        const int32_t* tp = a; a = b; b = tp;
+                        const int64_t tl = la; la = lb; lb = tl;
+                    }
+                    if (la > 32) {
+                        defer = true;
+                    } else {
+                        int64_t lo = 0;  // both rows ascend: every search resumes where the previous one ended
+                        for (int64_t u = 0; u < la && lo < lb; ++u) {
+                            const int32_t v = ldg_i32(a + u);
+                            int64_t hi = lb;
+                            while (lo < hi) {
+                                const int64_t mid = (lo + hi) >> 1;
+                                if (ldg_i32(b + mid) < v) lo = mid + 1; else hi = mid;
+                            }
+                            if (lo < lb && ldg_i32(b + lo) == v) { ++c2; ++lo; }
+                        }
+                    }
+                }
+                if (!defer) rec[p] = make_uint2(c2 | (c1 << 31), 0u);
+            }
+            unsigned pending = __ballot_sync(0xffffffffu, defer);
+            while (pending) {
+                const int sl = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const int64_t rk = __shfl_sync(0xffffffffu, rs_k, sl);
+                const int64_t dkk = __shfl_sync(0xffffffffu, dk, sl);
+                const unsigned cc1 = __shfl_sync(0xffffffffu, c1, sl);
+                const int32_t* a = nj;
+                const int32_t* b = col + rk;
+                int64_t la = dj, lb = dkk;
+                if (la > lb) {
+                    const int32_t* tp = a; a = b; b = tp;
+                    const int64_t tl = la; la = lb; lb = tl;
+                }
+                unsigned cnt = 0u;
+                for (int64_t u = lane; u < la; u += 32) cnt += row_contains(b, lb, ldg_i32(a + u)) ? 1u : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                if (lane == 0) rec[base + sl] = make_uint2(cnt | (cc1 << 31), 0u);
+            }
+        }
+    }
+}
+
 // per-batch column statistics from the finished records: one warp per link
 __global__ void k_cn_colstat(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
                              const int64_t* __restrict__ src, int64_t T, int64_t batch_size, int weighted,
@@ -589,11 +670,22 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
     const int64_t* rec_off = (const int64_t*)(base + L.rec_off);
     OCN_CUDA(cudaFuncSetAttribute(k_cn_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BuildSmem)));
     OCN_CUDA(cudaMemsetAsync((void*)(plan + OCN_PLAN_UNIT_COUNTER), 0, sizeof(int64_t), st));  // restart the dynamic unit counter
-    if (records_capacity > 0) OCN_CUDA(cudaMemsetAsync(records, 0, sizeof(Record) * (size_t)records_capacity, st));
-    const int blocks = sm_count() * kBuildCtasPerSm;
-    k_cn_build<<<blocks, kBuildThreads, sizeof(BuildSmem), st>>>(
-        rowptr, col, n, src, dst, order, rec_off, (const int32_t*)(base + L.run_start),
-        (const int64_t*)(base + L.run_unit_off), (const int64_t*)(base + L.cost_pre), (int64_t*)plan, (Record*)records);
+    if (records_capacity > 0)  // the table path accumulates with atomics
+        OCN_CUDA(cudaMemsetAsync(records, 0, sizeof(Record) * (size_t)records_capacity, st));
+    if (order <= 2) {  // the plan picked one of the two on the device (plan[OCN_PLAN_USE_DIRECT]); the other returns at once
+        int64_t want = (num_edges + 7) / 8;
+        int64_t cap = (int64_t)sm_count() * 16;
+        k_cn_build_direct<<<(int)(want < cap ? want : cap), 256, 0, st>>>(rowptr, col, src, dst, num_edges, order, rec_off,
+                                                                         plan, (Record*)records);
+        OCN_LAUNCH_CHECK();
+    }
+    {
+        const int blocks = sm_count() * kBuildCtasPerSm;
+        k_cn_build<<<blocks, kBuildThreads, sizeof(BuildSmem), st>>>(
+            rowptr, col, n, src, dst, order, rec_off, (const int32_t*)(base + L.run_start),
+            (const int64_t*)(base + L.run_unit_off), (const int64_t*)(base + L.cost_pre), (int64_t*)plan,
+            (Record*)records);
+    }
     OCN_LAUNCH_CHECK();
     if (colstat != nullptr) {
         int64_t want = (num_edges + 7) / 8;

@@ -130,7 +130,8 @@ __global__ void k_plan_finish(int64_t T, int64_t batch_size, int resident_ctas, 
     plan[OCN_PLAN_NUM_BATCHES] = (T + batch_size - 1) / batch_size;
     plan[OCN_PLAN_UNIT_COUNTER] = 0;  // dynamic unit counter of ocn_cn_build
     plan[OCN_PLAN_BUDGET] = unit_budget(plan[OCN_PLAN_TOTAL_COST], resident_ctas);
-    plan[7] = 0;
+    // orders <= 2: the table pays off only when several links share it (runs of >= 3 links on average)
+    plan[OCN_PLAN_USE_DIRECT] = (T <= 3 * plan[OCN_PLAN_NUM_RUNS]) ? 1 : 0;
 }
 
 }  // namespace ocn

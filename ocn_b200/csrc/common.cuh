@@ -70,9 +70,9 @@ PlanLayout plan_layout(int64_t num_edges);
 // cost window (in probed columns) one work unit of ocn_cn_build covers: about 8 units per resident CTA,
 // clamped so that a unit amortises its table build but a heavy link is still split over many CTAs
 __host__ __device__ inline long long unit_budget(long long total_cost, int resident_ctas) {
-    long long w = total_cost / (8ll * (resident_ctas > 0 ? resident_ctas : 1));
+    long long w = total_cost / (4ll * (resident_ctas > 0 ? resident_ctas : 1));
     if (w < 65536) w = 65536;
-    if (w > 524288) w = 524288;
+    if (w > 1048576) w = 1048576;
     return w;
 }
 constexpr int kBuildCtasPerSm = 1;  // one 1024-thread CTA per SM owns (almost) all shared memory
@@ -82,6 +82,7 @@ constexpr int kLinkCost = 64;  // fixed cost added to every link so that empty l
 #define OCN_PLAN_UNIT_COUNTER 4
 #define OCN_PLAN_BUDGET 5
 #define OCN_PLAN_TOTAL_COST 6
+#define OCN_PLAN_USE_DIRECT 7  /* orders <= 2 only: 1 = table-free kernel (short runs), 0 = table kernel */
 
 // ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

@@ -148,10 +148,12 @@ class CNLinkPredictorOringin(_OCNBase):
     variant, order = 5, 2
 
     def multidomainforward(self, x, adj, cn1, cn2, tar_ei, filled1: bool = False, cndropprobs: Iterable[float] = []):
+        if isinstance(cn1, SparseRows) and isinstance(cn2, SparseRows):
+            # the reference's own data flow: explicit adjoverlap outputs (incl. the folded adj2byblock matrix)
+            from .explicit import cn5_explicit
+            xcn1, xcn2, xij = cn5_explicit(self, x, cn1, cn2, tar_ei)
+            return self._head(xcn1, xcn2, None, xij)
         sess = cn1 if isinstance(cn1, CNSession) else None
-        if isinstance(cn1, SparseRows) or isinstance(cn2, SparseRows):
-            raise TypeError("pass cn1=cn2=None (or a CNSession): the fused path builds the CN sets itself; "
-                            "explicit matrices go through ocn_b200.explicit.cn5_explicit")
         xcn1, xcn2, _, xij, _ = self.cn_stage(x, adj, tar_ei, 0.0, sess)
         return self._head(xcn1, xcn2, None, xij)
 
@@ -181,8 +183,12 @@ class CNLinkPredictorbaselearn(_OCNBase):
 
     def multidomainforward(self, x, adj, cn1, cn2, tar_ei, args, filled1: bool = False,
                            cndropprobs: Iterable[float] = []):
-        sess = cn1 if isinstance(cn1, CNSession) else None
         fill = float(getattr(args, "sum", args if isinstance(args, (int, float)) else 0.0))
+        if isinstance(cn1, SparseRows) and isinstance(cn2, SparseRows):
+            from .explicit import cn7_explicit
+            xcn1, xcn2, xij = cn7_explicit(self, x, cn1, cn2, tar_ei, fill)
+            return self._head(xcn1, xcn2, None, xij)
+        sess = cn1 if isinstance(cn1, CNSession) else None
         xcn1, xcn2, _, xij, _ = self.cn_stage(x, adj, tar_ei, fill, sess)
         return self._head(xcn1, xcn2, None, xij)
 

@@ -328,3 +328,80 @@ def test_full_size_citation2_walk_counts():
             s, t = int(cns[k].rowptr[b]), int(cns[k].rowptr[b + 1])
             assert torch.equal(cns[k].col[s:t], ni[keep])
             assert torch.equal(cns[k].value[s:t].double(), vals[keep])
+
+
+def test_torch_custom_ops():
+    """torch.ops.ocn.* (north_star: the C ABI exposed as PyTorch custom ops), incl. autograd registration."""
+    g = GRAPHS["cora"]()
+    G, A = _graph(g), _sp(g)
+    e = g.query_edges(600, "mixed")
+    ed = e.to(DEV)
+    x = g.features(32)
+    rp, col = torch.ops.ocn.rows_intersect(G.rowptr, G.col, G.rowptr, G.col, ed)
+    ref = R.adjoverlap(A, A, e)
+    assert torch.equal(rp.cpu(), ref.rowptr()) and torch.equal(col.cpu(), ref.col)
+    # spmm with autograd
+    xr = x.clone().requires_grad_(True)
+    w = torch.randn(g.n, 32)
+    (R.pure_conv(xr, A, "sum") * w).sum().backward()
+    xg = x.to(DEV).requires_grad_(True)
+    out = torch.ops.ocn.spmm_csr(G.rowptr, G.col, None, xg, 0)
+    (out * w.to(DEV)).sum().backward()
+    ones = R.Sp(A.row, A.col, torch.ones(A.nnz), A.shape)
+    _close(out.detach(), R.pure_conv(x, A, "sum"), R.spmm_add(ones, x.abs()))
+    _close(xg.grad, xr.grad, R.spmm_add(ones, w.abs()), rtol=1e-4)
+    # gcn with autograd
+    norm = ob.gcn_norm(G)
+    xg2 = x.to(DEV).requires_grad_(True)
+    o2 = torch.ops.ocn.gcn_spmm(G.rowptr, G.col, norm, xg2, 3)
+    _close(o2.detach(), R.pure_conv(x, A, "gcn"), R.spmm_add(ones, x.abs()) + x.abs())
+    (o2 * w.to(DEV)).sum().backward()
+    xr2 = x.clone().requires_grad_(True)
+    (R.pure_conv(xr2, A, "gcn") * w).sum().backward()
+    _close(xg2.grad, xr2.grad, R.spmm_add(ones, w.abs()) + w.abs(), rtol=1e-4)
+    # A^2 and the fused stream op
+    rp2, c2, v2 = torch.ops.ocn.spgemm_a2(G.rowptr, G.col, 0, True)
+    a2 = R.adj2_true(A, keep_value=True)
+    assert torch.equal(rp2.cpu(), a2.rowptr()) and torch.equal(c2.cpu().long(), a2.col) and torch.equal(v2.cpu(), a2.values())
+    ip3 = torch.zeros(3, device=DEV)
+    x1, x2, x3, xij = torch.ops.ocn.cn_aggregate(G.rowptr, G.col, ed, x.to(DEV), ip3, 600, 2, True, 5, 0.0)
+    cns = R.get_cn(A, e, 2)
+    r1, r2, rij, n1, n2 = R.cn5_aggregate(cns[0], cns[1], x, e, R.InnerProdState(), training=False)
+    _close(x1, r1, _mass(n1, x))
+    _close(x2, r2, _mass(n2, x))
+    assert x3.shape[0] == 0 and torch.equal(xij.cpu(), rij)
+
+
+@pytest.mark.parametrize("name,fold", [("cora", 0), ("pubmed", 1024), ("ddi_s", 64)])
+def test_explicit_large_driver_flow(name, fold):
+    """NeighborOverlap_large.py:68-82 as written: adj2 = A@A (or the folded adj2byblock matrix), cn1/cn2 from
+    adjoverlap, then cn5 / cn7 on the explicit matrices -- against the oracle fed with the same matrices."""
+    g = GRAPHS[name]()
+    G, A = _graph(g), _sp(g)
+    F = 16
+    e = g.query_edges(512, "mixed")
+    ed, x = e.to(DEV), g.features(F)
+    G2 = ob.sparse_tensor_multiply(G, fold) if fold else ob.spgemm_a2(G)
+    a2 = R.adj2_folded(A, fold) if fold else R.adj2_true(A)
+    cn1, cn2 = ob.adjoverlap(G, G, ed), ob.adjoverlap(G, G2, ed)
+    r1, r2 = R.adjoverlap(A, A, e), R.adjoverlap(A, a2, e)
+    _assert_rows_equal(cn1, r1)
+    _assert_rows_equal(cn2, r2)
+    torch.manual_seed(3)
+    p5 = ob.CNLinkPredictorOringin(F, F, 1, 3, 0.0).to(DEV).train()
+    st = R.InnerProdState()
+    for _ in range(2):  # two training calls: the running inner product moves
+        with torch.no_grad():
+            out = p5.multidomainforward(x.to(DEV), G, cn1, cn2, ed)
+        o1, o2, oij, n1, n2 = R.cn5_aggregate(r1, r2, x, e, st, training=True)
+        ref = p5._head(o1.to(DEV), o2.to(DEV), None, oij.to(DEV))
+        assert torch.allclose(out, ref, rtol=1e-3, atol=1e-4)
+        assert abs(p5.innerprod.item() - st.innerprod.item()) <= 1e-4 * (1 + abs(st.innerprod.item()))
+    p7 = ob.CNLinkPredictorbaselearn(F, F, 1, 3, 0.0).to(DEV).eval()
+
+    class Args:
+        sum = 1
+    with torch.no_grad():
+        out7 = p7.multidomainforward(x.to(DEV), G, cn1, cn2, ed, Args())
+    o1, o2, oij, _ = R.cn7_aggregate(r1, r2, x, e, 1.0)
+    assert torch.allclose(out7, p7._head(o1.to(DEV), o2.to(DEV), None, oij.to(DEV)), rtol=1e-3, atol=1e-4)
