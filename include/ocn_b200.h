@@ -34,7 +34,7 @@ extern "C" {
 #define OCN_ECUDA (-2)    /* CUDA runtime / launch error */
 #define OCN_ENOSPACE (-3) /* caller-provided buffer too small */
 
-#define OCN_ABI_VERSION 1
+#define OCN_ABI_VERSION 2
 
 int ocn_abi_version(void);
 const char* ocn_last_error(void);
@@ -90,7 +90,12 @@ int ocn_rows_intersect_fill(const int64_t* rowptr1, const int32_t* col1,
 #define OCN_PLAN_NUM_RUNS 1    /* maximal runs of equal src inside a batch */
 #define OCN_PLAN_NUM_UNITS 2   /* work units of ocn_cn_build */
 #define OCN_PLAN_NUM_BATCHES 3
-#define OCN_PLAN_WORDS 8
+/* words 4..7 are internal to the library */
+#define OCN_PLAN_HUB_DEGREE 8    /* rows of >= this many columns go through the hub stage (0: stage off) */
+#define OCN_PLAN_HUB_PAIRS 9     /* (hub row, link) pairs of the stream */
+#define OCN_PLAN_HUB_ENTRIES 10  /* (key, run, position) entries of the stream */
+#define OCN_PLAN_HUB_POSITIONS 11 /* sum over runs of deg(src) */
+#define OCN_PLAN_WORDS 16
 
 /* bytes of plan scratch the caller must provide for a stream of num_edges links */
 size_t ocn_cn_plan_bytes(int64_t num_edges);
@@ -102,6 +107,7 @@ size_t ocn_cn_record_bytes(void);
 int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n,
                 const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t batch_size,
                 int order /* highest CN order that will be built: sizes the work units */,
+                int64_t hub_degree /* 0: automatic, -1: hub stage off, > 0: rows of at least this many columns */,
                 void* plan_scratch, size_t plan_scratch_bytes,
                 int64_t* out_plan /* device int64[OCN_PLAN_WORDS] */, void* stream);
 
@@ -114,7 +120,20 @@ int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n,
                  const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t batch_size,
                  int order, int weighted,
                  const void* plan_scratch, const int64_t* plan,
-                 void* records, int64_t records_capacity, void* colstat, void* stream);
+                 void* records, int64_t records_capacity, void* colstat,
+                 int64_t nnz /* rowptr[n]; only read by the hub stage */,
+                 const int64_t* plan_host /* HOST copy of plan[OCN_PLAN_WORDS] (the caller read it back to size
+                                             the buffers); NULL = hub stage off */,
+                 void* hub_scratch /* ocn_cn_hub_bytes(...) bytes, NULL = hub stage off */, size_t hub_scratch_bytes,
+                 void* node_scratch /* 16 bytes per node, ZERO on entry, zero again when the call has run */,
+                 void* stream);
+
+/* Hub stage of the order-3 walk (cn_hub.cu): a row N(m) that many links of the stream would walk
+ * is streamed once for all of them.  Scratch bytes for the sizes ocn_cn_plan reported. */
+size_t ocn_cn_hub_bytes(int64_t n, int64_t nnz, const int64_t* plan_host);
+/* Measurement hook: two cudaEvent_t recorded on the build's stream right before / after the
+ * dominant kernel of the indexed path (k_cn_hub_count).  NULL, NULL switches it off. */
+int ocn_cn_hub_timing_events(void* start_event, void* stop_event);
 
 /* variant: 5 = cn5/OCN (order 2) or its order-3 form (cn6 template), 7 = cn7/OCNP.
  * fill   : weight of a node that is CN1 of exactly one edge of the batch (cn5: 0, cn7: args.sum).

@@ -24,8 +24,11 @@ _SIGS = {
     "ocn_cn_plan_bytes": (c_size_t, [c_int64]),
     "ocn_cn_colstat_bytes": (c_size_t, [c_int64]),
     "ocn_cn_record_bytes": (c_size_t, []),
-    "ocn_cn_plan": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int, _P, c_size_t, _P, _P]),
-    "ocn_cn_build": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, c_int64, _P, _P]),
+    "ocn_cn_plan": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int64, _P, c_size_t, _P, _P]),
+    "ocn_cn_build": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, c_int64, _P,
+                             c_int64, _P, _P, c_size_t, _P, _P]),
+    "ocn_cn_hub_bytes": (c_size_t, [c_int64, c_int64, _P]),
+    "ocn_cn_hub_timing_events": (c_int, [_P, _P]),
     "ocn_cn_stats": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, c_int,
                              _P, _P, _P, _P, _P]),
     "ocn_cn_aggregate": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P,
@@ -72,7 +75,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.ocn_abi_version() != 1:
+        if L.ocn_abi_version() != 2:
             raise OcnError("libocn_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -13,6 +13,7 @@ computes on the CPU.
 """
 from __future__ import annotations
 
+import ctypes
 import dataclasses
 from typing import List, Optional, Tuple
 
@@ -22,7 +23,8 @@ from torch import Tensor
 from . import _lib
 from .graph import Graph, _require_cuda
 
-PLAN_WORDS = 8
+PLAN_WORDS = 16
+PLAN_HUB_DEGREE = 8  # include/ocn_b200.h OCN_PLAN_HUB_DEGREE
 COLSTAT_BUDGET_BYTES = 4 << 30  # per-wave cap for the per-batch column statistics
 
 
@@ -98,7 +100,10 @@ class CNSession:
     ``batch_size`` cuts the stream into the reference's link batches; every batch is
     normalised independently (the column sums of model.py:2261 run over one batch)."""
 
-    def __init__(self, graph: Graph, tarei: Tensor, batch_size: Optional[int] = None, order: int = 3):
+    def __init__(self, graph: Graph, tarei: Tensor, batch_size: Optional[int] = None, order: int = 3,
+                 hub_degree: int = 0):
+        """``hub_degree``: rows of at least this many columns are walked once per stream by the hub
+        stage of the order-3 build (0 = chosen from n and the stream length, -1 = stage off)."""
         _require_cuda(graph.col)
         _require_cuda(tarei)
         self.g = graph
@@ -116,11 +121,14 @@ class CNSession:
         self.plan = torch.zeros(PLAN_WORDS, dtype=torch.int64, device=self.dev)
         with torch.cuda.device(self.dev):
             _lib.check(L.ocn_cn_plan(_lib.ptr(graph.rowptr), _lib.ptr(graph.col), graph.n, _lib.ptr(self.src),
-                                     _lib.ptr(self.dst), self.T, self.batch_size, int(order),
+                                     _lib.ptr(self.dst), self.T, self.batch_size, int(order), int(hub_degree),
                                      _lib.ptr(self.plan_scratch), self.plan_bytes,
                                      _lib.ptr(self.plan), _stream(self.dev)), "ocn_cn_plan")
         host = self.plan.tolist()  # the one host sync of the session: buffer sizes
         self.num_records, self.num_runs, self.num_units = host[0], host[1], host[2]
+        self.plan_host = (ctypes.c_int64 * PLAN_WORDS)(*host)
+        self.hub_degree = host[PLAN_HUB_DEGREE]
+        self.hub_bytes = L.ocn_cn_hub_bytes(graph.n, graph.nnz, self.plan_host) if self.hub_degree > 0 else 0
         self.records = torch.empty(max(1, self.num_records) * L.ocn_cn_record_bytes(), dtype=torch.uint8,
                                    device=self.dev)
         self.colstat = None  # borrowed by build(with_stats=True)
@@ -134,12 +142,16 @@ class CNSession:
         g = self.g
         if with_stats and self.colstat is None:
             self.colstat = _borrow_colstat(g, self.nb * self.L.ocn_cn_colstat_bytes(g.n))
+        hub_scratch = node_scratch = None
+        if self.hub_bytes > 0 and order >= 3:
+            hub_scratch, node_scratch = _hub_workspace(g, self.hub_bytes)
         with torch.cuda.device(self.dev):
             _lib.check(self.L.ocn_cn_build(_lib.ptr(g.rowptr), _lib.ptr(g.col), g.n, _lib.ptr(self.src),
                                            _lib.ptr(self.dst), self.T, self.batch_size, int(order), int(bool(weighted)),
                                            _lib.ptr(self.plan_scratch), _lib.ptr(self.plan), _lib.ptr(self.records),
                                            self.num_records, _lib.ptr(self.colstat) if with_stats else None,
-                                           _stream(self.dev)), "ocn_cn_build")
+                                           g.nnz, self.plan_host, _lib.ptr(hub_scratch), self.hub_bytes,
+                                           _lib.ptr(node_scratch), _stream(self.dev)), "ocn_cn_build")
         self.order, self.weighted = int(order), bool(weighted)
         return self
 
@@ -221,6 +233,20 @@ class CNSession:
         _return_colstat(self.g, self.colstat)
 
 
+def _hub_workspace(g: Graph, nbytes: int):
+    """Scratch of the hub stage, kept with the graph: a byte buffer that only grows and the 16-byte-per-node
+    key index (all zero between calls; ocn_cn_build restores it).  Calls on one graph are ordered by the stream."""
+    buf = g._ws.get("hub")
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=g.device)
+        g._ws["hub"] = buf
+    node = g._ws.get("hub_node")
+    if node is None:
+        node = torch.zeros((g.n, 4), dtype=torch.int32, device=g.device)
+        g._ws["hub_node"] = node
+    return buf, node
+
+
 def _borrow_colstat(g: Graph, nbytes: int) -> Tensor:
     """A zeroed buffer for the per-batch column statistics.  Buffers handed back by
     ``CNSession.release`` (which re-zeroes exactly the touched entries) are reused, so a steady
@@ -248,11 +274,12 @@ def _check_x(x: Tensor, g: Graph) -> Tensor:
     return x.contiguous()
 
 
-def get_cn(adj: Graph, tedge: Tensor, order: int = 2, weighted: bool = True) -> List[SparseRows]:
+def get_cn(adj: Graph, tedge: Tensor, order: int = 2, weighted: bool = True, hub_degree: int = 0,
+           batch_size: Optional[int] = None) -> List[SparseRows]:
     """``get_cn1_cn2`` (NeighborOverlapCitation2.py:78-104) generalised to ``order`` sets.
     weighted=True keeps the pygho walk counts as values, False gives the 0/1 structure that
     ``adjoverlap(adj, adj2, e)`` yields in the _large drivers."""
-    s = CNSession(adj, tedge, None, order).build(order, weighted, with_stats=False)
+    s = CNSession(adj, tedge, batch_size, order, hub_degree).build(order, weighted, with_stats=False)
     return [s.extract(k) for k in range(1, order + 1)]
 
 

@@ -656,7 +656,8 @@ using namespace ocn;
 extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src,
                             const int64_t* dst, int64_t num_edges, int64_t batch_size, int order, int weighted,
                             const void* plan_scratch, const int64_t* plan, void* records, int64_t records_capacity,
-                            void* colstat, void* stream) {
+                            void* colstat, int64_t nnz, const int64_t* plan_host, void* hub_scratch,
+                            size_t hub_scratch_bytes, void* node_scratch, void* stream) {
     OCN_CHECK_ARG(rowptr && col && src && dst && plan_scratch && plan, "ocn_cn_build: null pointer");
     OCN_CHECK_ARG(order >= 1 && order <= 3, "ocn_cn_build: order must be 1, 2 or 3 (got %d)", order);
     OCN_CHECK_ARG(n > 0 && num_edges > 0 && batch_size > 0, "ocn_cn_build: sizes must be positive");
@@ -672,6 +673,16 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
     OCN_CUDA(cudaMemsetAsync((void*)(plan + OCN_PLAN_UNIT_COUNTER), 0, sizeof(int64_t), st));  // restart the dynamic unit counter
     if (records_capacity > 0)  // the table path accumulates with atomics
         OCN_CUDA(cudaMemsetAsync(records, 0, sizeof(Record) * (size_t)records_capacity, st));
+    // order 3 on a stream with few runs: inverted-index path (cn_hub.cu) instead of the per-run tables
+    bool indexed = false;
+    if (order >= 3 && plan_host != nullptr && hub_scratch != nullptr && plan_host[OCN_PLAN_HUB_DEGREE] > 0) {
+        OCN_CHECK_ARG(node_scratch != nullptr, "ocn_cn_build: hub stage needs node_scratch");
+        OCN_CHECK_ARG(nnz > 0, "ocn_cn_build: hub stage needs nnz");
+        int rc = run_hub_stage(rowptr, col, n, src, dst, num_edges, plan_scratch, plan, plan_host, hub_scratch,
+                               hub_scratch_bytes, node_scratch, (Record*)records, nnz, st);
+        if (rc != OCN_OK) return rc;
+        indexed = true;
+    }
     if (order <= 2) {  // the plan picked one of the two on the device (plan[OCN_PLAN_USE_DIRECT]); the other returns at once
         int64_t want = (num_edges + 7) / 8;
         int64_t cap = (int64_t)sm_count() * 16;
@@ -679,14 +690,14 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
                                                                          plan, (Record*)records);
         OCN_LAUNCH_CHECK();
     }
-    {
+    if (!indexed) {
         const int blocks = sm_count() * kBuildCtasPerSm;
         k_cn_build<<<blocks, kBuildThreads, sizeof(BuildSmem), st>>>(
             rowptr, col, n, src, dst, order, rec_off, (const int32_t*)(base + L.run_start),
             (const int64_t*)(base + L.run_unit_off), (const int64_t*)(base + L.cost_pre), (int64_t*)plan,
             (Record*)records);
+        OCN_LAUNCH_CHECK();
     }
-    OCN_LAUNCH_CHECK();
     if (colstat != nullptr) {
         int64_t want = (num_edges + 7) / 8;
         int64_t cap = (int64_t)sm_count() * 8;

@@ -1,0 +1,626 @@
+// Indexed path of ocn_cn_build for order 3: CN_1..3 of a stream of links through an inverted index
+// of the source side, with the rows shared by many links streamed once.
+//
+//     C1[t][p] = [ dst in N(k_p) ]
+//     C2[t][p] = #{ m in N(dst)              : m in N(k_p) }
+//     C3[t][p] = #{ m in N(dst), l in N(m)   : l in N(k_p) },          k_p = N(src[t])[p]
+//
+// cn_build.cu answers "l in N(k_p)?" from a shared-memory table per run of links with one source
+// and walks N(m) once per (link, m).  In a stream of T links with spread-out destinations a row
+// N(m) is walked by about T*d(m)/n links: for the citation2 evaluation stream
+// (NeighborOverlapCitation2.py:241-254, every source against 1000 uniform destinations) 87 % of
+// the walked columns sit in rows that several links of the same call walk, and a link's own part is
+// ~150 columns.  This path therefore
+//
+//   * builds ONE inverted index for the whole stream:  entries(l) = { position pi = (run r, p) :
+//     l in N(k_{r,p}) }, a list sorted by (l, pi); node_index[l] = (first, last+1, 64-bit signature
+//     of the runs in the list).  The positions of a run are contiguous (run_pos_off[r] + p);
+//   * k_cn_hub_count: every row N(m) with d(m) >= plan[OCN_PLAN_HUB_DEGREE] that some destination
+//     touches is streamed ONCE; the entries of its columns are counted per position in warp-private
+//     shared memory (U[pi] += 1: a shared-memory atomic costs about a load on sm_100a, a global RED
+//     15x more -- scripts/micro/atoms_bench.cu), then every link t next to m (the pair list L_m)
+//     adds U[positions of its run] into its records: one RED per non-zero counter, not per walk;
+//   * k_cn_link: per link, C1, C2 and the C3 part through the short rows, by looking (l, run of t)
+//     up in the same index (the run's entries are a contiguous piece of l's list).
+//
+// All sums are integer RED.ADDs into the zeroed records, so the result is exact and independent of
+// the order of execution.  Sizes come from the plan the caller read back (pairs, entries, positions).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace ocn {
+
+constexpr int kHubSeg = 2048;       // columns of a shared row per work item (16-bit counters: < 65536)
+constexpr int kHubThreads = 256;
+constexpr int kHubWarps = kHubThreads / 32;
+constexpr int kShortList = 4;       // entry lists up to this length are walked by their own lane
+constexpr int kMidList = 32;        // up to this length flattened over the lanes, longer ones by the whole warp
+static_assert(kHubSeg < 65536, "16-bit walk counters per item");
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+static int key_bits(int64_t n) {
+    int b = 1;
+    while (b < 32 && (int64_t(1) << b) < n) ++b;
+    return b;
+}
+
+HubLayout hub_layout(int64_t n, int64_t nnz, int64_t pairs, int64_t entries, int64_t positions) {
+    HubLayout L;
+    size_t off = 0;
+    const size_t P = (size_t)(pairs > 0 ? pairs : 1), E = (size_t)(entries > 0 ? entries : 1);
+    for (int k = 0; k < 2; ++k) { L.pkey[k] = off; off += align256(sizeof(uint32_t) * P); }
+    for (int k = 0; k < 2; ++k) { L.pval[k] = off; off += align256(sizeof(uint32_t) * P); }
+    for (int k = 0; k < 2; ++k) { L.ekey[k] = off; off += align256(sizeof(uint32_t) * E); }
+    for (int k = 0; k < 2; ++k) { L.eval[k] = off; off += align256(sizeof(uint32_t) * E); }
+    L.ent_off = off;   off += align256(sizeof(int64_t) * (size_t)(positions + 2));
+    L.max_items = (int64_t)P + nnz / kHubSeg + 2;
+    L.items = off;     off += align256(sizeof(uint2) * (size_t)L.max_items);
+    L.counters = off;  off += align256(sizeof(unsigned long long) * 4);
+    L.prun = off;      off += align256(sizeof(int32_t) * P);
+    L.prec = off;      off += align256(sizeof(unsigned long long) * P);
+    size_t b1 = 0, b2 = 0, b3 = 0;
+    {
+        cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
+        cub::DeviceRadixSort::SortPairs(nullptr, b1, k, v, (int)P, 0, key_bits(n));
+        cub::DeviceRadixSort::SortPairs(nullptr, b2, k, v, (int)E, 0, key_bits(n));
+        cub::DeviceScan::ExclusiveSum(nullptr, b3, (int64_t*)nullptr, (int64_t*)nullptr, (int)(positions + 2));
+    }
+    size_t b = b2 > b3 ? b2 : b3;
+    L.cub_temp = off;                      // entries: scan + sort
+    L.cub_temp_bytes = align256(b + 256);
+    off += L.cub_temp_bytes;
+    L.cub_temp2 = off;                     // pairs: sort (runs concurrently on the auxiliary stream)
+    L.cub_temp2_bytes = align256(b1 + 256);
+    off += L.cub_temp2_bytes;
+    L.total = off;
+    return L;
+}
+
+// ---- the inverted index ------------------------------------------------------------------------
+// position pi of the stream = (run r, position p of N(src of r)); run_pos_off is the exclusive
+// prefix of deg(src) over the runs
+__device__ __forceinline__ void locate_position(int64_t pi, const int64_t* __restrict__ run_pos_off, int64_t n_runs,
+                                                int64_t& r, int64_t& p) {
+    int64_t lo = 0, hi = n_runs;  // last r with run_pos_off[r] <= pi
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (run_pos_off[mid] <= pi) lo = mid; else hi = mid;
+    }
+    r = lo;
+    p = pi - run_pos_off[lo];
+}
+
+__global__ void k_hub_pos_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                const int64_t* __restrict__ src, const int32_t* __restrict__ run_start,
+                                const int64_t* __restrict__ run_pos_off, int64_t n_runs, int64_t n_pos,
+                                int64_t* __restrict__ ent_off) {
+    const int64_t pi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi > n_pos) return;
+    if (pi == n_pos) {
+        ent_off[pi] = 0;
+        return;
+    }
+    int64_t r, p;
+    locate_position(pi, run_pos_off, n_runs, r, p);
+    const int64_t i = src[run_start[r]];
+    const int32_t k = ldg_i32(col + rowptr[i] + p);
+    ent_off[pi] = rowptr[k + 1] - rowptr[k];
+}
+
+// one warp per position: the row N(k) of the position's node becomes entries (l, pi), emitted in
+// position order (the stable sort by l then leaves every list ascending in pi)
+__global__ void k_hub_emit_entries(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                   const int64_t* __restrict__ src, const int32_t* __restrict__ run_start,
+                                   const int64_t* __restrict__ run_pos_off, int64_t n_runs, int64_t n_pos,
+                                   const int64_t* __restrict__ ent_off, uint32_t* __restrict__ ekey,
+                                   uint32_t* __restrict__ eval) {
+    const int64_t pi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pi >= n_pos) return;
+    int64_t r, p;
+    locate_position(pi, run_pos_off, n_runs, r, p);
+    const int64_t i = src[run_start[r]];
+    const int32_t k = ldg_i32(col + rowptr[i] + p);
+    const int64_t rs = rowptr[k], d = rowptr[k + 1] - rs;
+    const int64_t off = ent_off[pi];
+    for (int64_t idx = lane; idx < d; idx += 32) {
+        ekey[off + idx] = (uint32_t)ldg_i32(col + rs + idx);
+        eval[off + idx] = (uint32_t)pi;
+    }
+}
+
+// run of a position: last r with run_pos_off[r] <= pi (runs are few: the search stays in L1)
+__device__ __forceinline__ uint32_t run_of_position(uint32_t pi, const int64_t* __restrict__ run_pos_off, int n_runs) {
+    int lo = 0, hi = n_runs;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((uint32_t)run_pos_off[mid] <= pi) lo = mid; else hi = mid;
+    }
+    return (uint32_t)lo;
+}
+
+// node_index[l] = (first entry of l, one past its last entry, signature of the runs of its entries:
+// bit (run mod 64)); all zero = l is no key.  set == 0 restores the zeros.
+__global__ void k_hub_entry_heads(const uint32_t* __restrict__ ekey, const uint32_t* __restrict__ eval,
+                                  const int64_t* __restrict__ run_pos_off, int n_runs, int64_t E, int set,
+                                  uint4* __restrict__ node_index) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const uint32_t k = ekey[e];
+    unsigned* ni = reinterpret_cast<unsigned*>(node_index + k);
+    const bool first = (e == 0 || ekey[e - 1] != k);
+    if (!set) {
+        if (first) node_index[k] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    if (first) ni[0] = (unsigned)e;
+    if (e == E - 1 || ekey[e + 1] != k) ni[1] = (unsigned)(e + 1);
+    const uint32_t r = run_of_position(eval[e], run_pos_off, n_runs);
+    atomicOr(ni + 2 + ((r >> 5) & 1u), 1u << (r & 31u));
+}
+
+// ---- (shared row, link) pairs, in link order ---------------------------------------------------
+__device__ __forceinline__ bool is_hub_row(const int64_t* __restrict__ rowptr, int32_t m, int64_t hub_d) {
+    return (ldg_i64(rowptr + m + 1) - ldg_i64(rowptr + m)) >= hub_d;
+}
+
+// one warp per link over the first kLongRow neighbours of dst (positions by ballot rank) ...
+__global__ void k_hub_emit_pairs(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                 const int64_t* __restrict__ dst, int64_t T, int64_t hub_d,
+                                 const int32_t* __restrict__ hub_off, uint32_t* __restrict__ pkey,
+                                 uint32_t* __restrict__ pval) {
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= T) return;
+    const int64_t j = dst[t];
+    const int64_t rs = rowptr[j];
+    int64_t d = rowptr[j + 1] - rs;
+    if (d > kLongRow) d = kLongRow;
+    int64_t base = hub_off[t];
+    for (int64_t o = 0; o < d; o += 32) {
+        const int64_t idx = o + lane;
+        int32_t m = -1;
+        bool hub = false;
+        if (idx < d) {
+            m = ldg_i32(col + rs + idx);
+            hub = is_hub_row(rowptr, m, hub_d);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hub);
+        if (hub) {
+            const int64_t pos = base + __popc(bal & ((1u << lane) - 1u));
+            pkey[pos] = (uint32_t)m;
+            pval[pos] = (uint32_t)t;
+        }
+        base += __popc(bal);
+    }
+}
+
+// ... and one CTA per link of the long-destination list for the rest (the order of a link's pairs is free:
+// its rows are distinct, and the sort by row keeps links in stream order)
+__global__ void __launch_bounds__(1024)
+k_hub_emit_pairs_long(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ dst,
+                      int64_t hub_d, const int32_t* __restrict__ hub_off, const int32_t* __restrict__ long_list,
+                      const int64_t* __restrict__ plan, uint32_t* __restrict__ pkey, uint32_t* __restrict__ pval) {
+    __shared__ int s_pos;
+    const int64_t n_long = plan[OCN_PLAN_LONG_COUNT];
+    for (int64_t i = blockIdx.x; i < n_long; i += gridDim.x) {
+        const int64_t t = long_list[i];
+        const int64_t j = dst[t];
+        const int64_t rs = rowptr[j], d = rowptr[j + 1] - rs;
+        if (threadIdx.x == 0) s_pos = 0;
+        __syncthreads();
+        if (threadIdx.x < kLongRow && is_hub_row(rowptr, ldg_i32(col + rs + threadIdx.x), hub_d)) atomicAdd(&s_pos, 1);
+        __syncthreads();
+        const int64_t base = hub_off[t];
+        for (int64_t o = kLongRow + threadIdx.x; o < d; o += blockDim.x) {
+            const int32_t m = ldg_i32(col + rs + o);
+            if (is_hub_row(rowptr, m, hub_d)) {
+                const int64_t pos = base + atomicAdd(&s_pos, 1);
+                pkey[pos] = (uint32_t)m;
+                pval[pos] = (uint32_t)t;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// work items (row, segment of kHubSeg columns), per-pair run and record offset
+__global__ void k_hub_items(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ run_id,
+                            const int64_t* __restrict__ rec_off, const uint32_t* __restrict__ pkey,
+                            const uint32_t* __restrict__ pval, int64_t P, int32_t* __restrict__ prun,
+                            unsigned long long* __restrict__ prec, uint2* __restrict__ items, int64_t max_items,
+                            unsigned long long* __restrict__ counters) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int nseg = 0;
+    if (q < P) {
+        const uint32_t t = pval[q];
+        prun[q] = run_id[t] - 1;
+        prec[q] = (unsigned long long)rec_off[t];
+        const uint32_t m = pkey[q];
+        if (q == 0 || pkey[q - 1] != m) nseg = (int)((rowptr[m + 1] - rowptr[m] + kHubSeg - 1) / kHubSeg);
+    }
+    // one atomic per warp: lane 0 reserves the warp's items, every head row takes its share
+    int incl = nseg;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 0 && total > 0) base = atomicAdd(&counters[0], (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 0) + (unsigned long long)(incl - nseg);
+    for (int s = 0; s < nseg; ++s)
+        if ((int64_t)(base + s) < max_items) items[base + s] = make_uint2((uint32_t)q, (uint32_t)s);
+}
+
+// ---- warp helpers --------------------------------------------------------------------------------
+// lane's owner in a flattened expansion: largest s with excl[s] <= j (excl = exclusive scan of the
+// per-lane counts, one value per lane)
+__device__ __forceinline__ int owner_lane(int excl, int j) {
+    int s = 0;
+#pragma unroll
+    for (int st = 16; st > 0; st >>= 1) {
+        const int ev = __shfl_sync(0xffffffffu, excl, s + st);
+        if (ev <= j) s += st;
+    }
+    return s;
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+
+// U holds 16-bit counters packed in pairs
+__device__ __forceinline__ void count_walk(uint32_t* U, uint32_t pos) { atomicAdd(U + (pos >> 1), 1u << ((pos & 1u) << 4)); }
+
+// ---- the walk through the shared rows ------------------------------------------------------------
+// One warp per item (row m, segment of its columns).  Entries of runs without a link next to m
+// only touch counters nobody reads; a column whose run signature misses every run of L_m is skipped.
+// Entry lists are walked by their own lane (<= kShortList entries), flattened over the lanes
+// (<= kMidList) or by the whole warp, so that neither the many short lists nor the few long ones
+// (54 % of the visits are in lists of > 32 entries at citation2 shape) leave lanes idle.
+__global__ void __launch_bounds__(kHubThreads, 6)
+k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint32_t* __restrict__ pkey,
+               const int32_t* __restrict__ prun, const unsigned long long* __restrict__ prec, int64_t P,
+               const uint32_t* __restrict__ eval, const uint4* __restrict__ node_index,
+               const int64_t* __restrict__ run_pos_off, int n_runs, int n_pos,
+               const uint2* __restrict__ items, int64_t max_items, unsigned long long* __restrict__ counters,
+               Record* __restrict__ records) {
+    extern __shared__ uint32_t hub_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rpad = (n_runs + 1 + 3) & ~3;
+    const int uwords = (((n_pos + 1) >> 1) + 3) & ~3;   // packed 16-bit counters, a multiple of 4 words
+    uint32_t* s_pos = hub_smem;                          // run -> first position (n_runs + 1 entries)
+    uint32_t* U = hub_smem + rpad + (size_t)warp * uwords;
+    for (int r = threadIdx.x; r <= n_runs; r += blockDim.x) s_pos[r] = (uint32_t)run_pos_off[r];
+    __syncthreads();
+    unsigned long long n_items = counters[0];
+    if (n_items > (unsigned long long)max_items) n_items = (unsigned long long)max_items;  // cannot happen with ocn_cn_hub_bytes
+    unsigned* rec32 = reinterpret_cast<unsigned*>(records);
+    while (true) {
+        unsigned long long it = 0;
+        if (lane == 0) it = atomicAdd(&counters[1], 1ull);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= n_items) break;
+        const uint2 item = items[it];
+        const int64_t q0 = item.x;
+        const uint32_t m = pkey[q0];
+        int64_t c = 0;  // |L_m|
+        unsigned act_lo = 0u, act_hi = 0u;  // signature of the runs that have a link next to m
+        while (true) {
+            const int64_t qi = q0 + c + lane;
+            const bool ok = qi < P && pkey[qi] == m;
+            if (ok) {
+                const int r = prun[qi];
+                if (r & 32) act_hi |= 1u << (r & 31); else act_lo |= 1u << (r & 31);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            c += __popc(bal);
+            if (bal != 0xffffffffu) break;
+        }
+        act_lo = __reduce_or_sync(0xffffffffu, act_lo);
+        act_hi = __reduce_or_sync(0xffffffffu, act_hi);
+        for (int s = lane * 4; s < uwords; s += 128) *reinterpret_cast<uint4*>(U + s) = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        const int64_t rs = rowptr[m];
+        const int64_t d = rowptr[m + 1] - rs;
+        const int64_t c0 = (int64_t)item.y * kHubSeg;
+        const int64_t c1 = (c0 + kHubSeg < d) ? c0 + kHubSeg : d;
+        // software pipeline: the (column -> index entry) loads of the next 32 columns are in flight while
+        // the lists of the current ones are walked
+        uint4 he_next = make_uint4(0u, 0u, 0u, 0u);
+        if (c0 + lane < c1) he_next = __ldg(node_index + ldg_i32(col + rs + c0 + lane));
+        for (int64_t b = c0; b < c1; b += 32) {
+            const uint4 he = he_next;
+            he_next = make_uint4(0u, 0u, 0u, 0u);
+            if (b + 32 + lane < c1) he_next = __ldg(node_index + ldg_i32(col + rs + b + 32 + lane));
+            const int cnt = ((he.z & act_lo) | (he.w & act_hi)) ? (int)(he.y - he.x) : 0;
+            if (!__any_sync(0xffffffffu, cnt != 0)) continue;
+            const uint32_t* list = eval + he.x;
+            // short lists: every lane walks its own
+            {
+                const int cs = cnt <= kShortList ? cnt : 0;
+                uint32_t pos[kShortList];
+#pragma unroll
+                for (int k = 0; k < kShortList; ++k) pos[k] = k < cs ? __ldg(list + k) : 0u;
+#pragma unroll
+                for (int k = 0; k < kShortList; ++k)
+                    if (k < cs) count_walk(U, pos[k]);
+            }
+            // middle lists: flattened over the lanes, 32 entries at a time
+            const int cm = (cnt > kShortList && cnt <= kMidList) ? cnt : 0;
+            if (__any_sync(0xffffffffu, cm != 0)) {
+                const int incl = warp_incl_scan(cm, lane);
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                const int excl = incl - cm;
+                for (int j0 = 0; j0 < total; j0 += 32) {
+                    const int j = j0 + lane;
+                    const int s = owner_lane(excl, j);
+                    const uint32_t ehead = __shfl_sync(0xffffffffu, he.x, s);
+                    const int eexcl = __shfl_sync(0xffffffffu, excl, s);
+                    if (j < total) count_walk(U, __ldg(eval + ehead + (uint32_t)(j - eexcl)));
+                }
+            }
+            // long lists: the whole warp per list
+            unsigned lg = __ballot_sync(0xffffffffu, cnt > kMidList);
+            while (lg) {
+                const int sl = __ffs(lg) - 1;
+                lg &= lg - 1;
+                const uint32_t ehead = __shfl_sync(0xffffffffu, he.x, sl);
+                const int n = __shfl_sync(0xffffffffu, cnt, sl);
+#pragma unroll 2
+                for (int e = lane; e < n; e += 32) count_walk(U, __ldg(eval + ehead + e));
+            }
+        }
+        __syncwarp();
+        // hand the counts to the links next to m
+        for (int64_t q = 0; q < c; ++q) {
+            const int r = prun[q0 + q];
+            const uint32_t pb = s_pos[r], np = s_pos[r + 1] - pb;
+            unsigned* rec = rec32 + 2 * prec[q0 + q] + 1;
+            for (uint32_t p = lane; p < np; p += 32) {
+                const uint32_t pos = pb + p;
+                const uint32_t u = (U[pos >> 1] >> ((pos & 1u) << 4)) & 0xffffu;
+                if (u) atomicAdd(rec + 2 * p, u);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- everything a link does not share ------------------------------------------------------------
+// One warp per item (link t, 32 consecutive rows of N(dst[t])): C1 (first item of the link), C2 for
+// its rows, C3 through those of its rows that have fewer than hub_d columns, their columns
+// flattened over the lanes.  lookup: the entries of l that belong to the run of t are the piece of
+// l's list with positions in [pos_lo, pos_hi).
+__device__ __forceinline__ void link_lookup(const uint4* __restrict__ node_index, const uint32_t* __restrict__ eval,
+                                            uint32_t l, uint32_t r, uint32_t pos_lo, uint32_t pos_hi,
+                                            unsigned* __restrict__ rec, unsigned inc) {
+    const uint4 he = __ldg(node_index + l);
+    if ((((r & 32u) ? he.w : he.z) >> (r & 31u) & 1u) == 0u) return;  // no entry of l in a run of this signature bit
+    uint32_t lo = he.x, hi = he.y;
+    while (lo < hi) {  // first entry of l with position >= pos_lo
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(eval + mid) < pos_lo) lo = mid + 1; else hi = mid;
+    }
+    for (; lo < he.y; ++lo) {
+        const uint32_t pos = __ldg(eval + lo);
+        if (pos >= pos_hi) break;
+        atomicAdd(rec + 2 * (pos - pos_lo), inc);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_cn_link(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ dst,
+          int64_t T, const int32_t* __restrict__ run_id, const int64_t* __restrict__ rec_off,
+          const int32_t* __restrict__ chunk_off, const int64_t* __restrict__ run_pos_off,
+          const uint32_t* __restrict__ eval, const uint4* __restrict__ node_index, int64_t hub_d,
+          Record* __restrict__ records) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_items = chunk_off[T];
+    unsigned* rec32 = reinterpret_cast<unsigned*>(records);
+    for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += nwarps) {
+        int64_t lo = 0, hi = T;  // last t with chunk_off[t] <= item
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (chunk_off[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int64_t t = lo;
+        const int64_t ch = item - chunk_off[t];
+        const int64_t j = dst[t];
+        const int64_t rs_j = rowptr[j], d_j = rowptr[j + 1] - rs_j;
+        const uint32_t r = (uint32_t)(run_id[t] - 1);
+        const uint32_t pos_lo = (uint32_t)run_pos_off[r], pos_hi = (uint32_t)run_pos_off[r + 1];
+        unsigned* rec = rec32 + 2 * rec_off[t];
+        if (ch == 0 && lane == 0) link_lookup(node_index, eval, (uint32_t)j, r, pos_lo, pos_hi, rec, 0x80000000u);  // C1
+        const int64_t oi = ch * 32 + lane;
+        int64_t rs_m = 0;
+        int cnt = 0;
+        if (oi < d_j) {
+            const int32_t m = ldg_i32(col + rs_j + oi);
+            link_lookup(node_index, eval, (uint32_t)m, r, pos_lo, pos_hi, rec, 1u);  // C2
+            rs_m = ldg_i64(rowptr + m);
+            const int64_t d_m = ldg_i64(rowptr + m + 1) - rs_m;
+            if (d_m < hub_d) cnt = (int)d_m;
+        }
+        const int incl = warp_incl_scan(cnt, lane);
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - cnt;
+        for (int j0 = 0; j0 < total; j0 += 32) {  // C3 through the rows this link does not share
+            const int jj = j0 + lane;
+            const int s = owner_lane(excl, jj);
+            const int64_t rs_o = __shfl_sync(0xffffffffu, rs_m, s);
+            const int eexcl = __shfl_sync(0xffffffffu, excl, s);
+            if (jj < total)
+                link_lookup(node_index, eval, (uint32_t)ldg_i32(col + rs_o + (jj - eexcl)), r, pos_lo, pos_hi, rec + 1, 1u);
+        }
+    }
+}
+
+static int grid_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// optional CUDA events around the dominant kernel (bench.py's roofline leg)
+static cudaEvent_t g_hub_events[2] = {nullptr, nullptr};
+static void hub_timing_record(int which, cudaStream_t st) {
+    if (g_hub_events[which] != nullptr) cudaEventRecord(g_hub_events[which], st);
+}
+
+// Auxiliary stream per device: the pair pipeline runs beside the entry pipeline and the per-link
+// kernel beside the shared-row walk (small latency-bound kernels; both only add into the records).
+// Every call forks from and joins back into the caller's stream, so the caller sees one ordered call.
+struct HubAux {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+static std::mutex g_aux_mutex;
+static HubAux g_aux[64];
+
+static int hub_aux(HubAux** out) {
+    int dev = 0;
+    OCN_CUDA(cudaGetDevice(&dev));
+    OCN_CHECK_ARG(dev >= 0 && dev < 64, "ocn_cn_build: device ordinal %d", dev);
+    std::lock_guard<std::mutex> lock(g_aux_mutex);
+    HubAux& a = g_aux[dev];
+    if (a.stream == nullptr) {
+        OCN_CUDA(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 4; ++k) OCN_CUDA(cudaEventCreateWithFlags(&a.ev[k], cudaEventDisableTiming));
+    }
+    *out = &a;
+    return OCN_OK;
+}
+
+// called by ocn_cn_build between the zeroing of the records and the column statistics
+int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst,
+                  int64_t T, const void* plan_scratch, const int64_t* plan_dev, const int64_t* plan_host, void* hub_scratch,
+                  size_t hub_scratch_bytes, void* node_scratch, Record* records, int64_t nnz, cudaStream_t st) {
+    const int64_t hub_d = plan_host[OCN_PLAN_HUB_DEGREE];
+    const int64_t P = plan_host[OCN_PLAN_HUB_PAIRS], E = plan_host[OCN_PLAN_HUB_ENTRIES];
+    const int64_t NP = plan_host[OCN_PLAN_HUB_POSITIONS], R = plan_host[OCN_PLAN_NUM_RUNS];
+    OCN_CHECK_ARG(hub_d > 0, "ocn_cn_build: the indexed path is off in this plan");
+    OCN_CHECK_ARG(P < (int64_t(1) << 31) && E < (int64_t(1) << 31), "ocn_cn_build: indexed path limited to 2^31 pairs / entries");
+    OCN_CHECK_ARG(R <= kHubMaxRuns && NP <= kHubMaxPositions, "ocn_cn_build: indexed path with %lld runs, %lld positions",
+                  (long long)R, (long long)NP);
+    if (NP <= 0 || E <= 0) return OCN_OK;  // no source has a neighbour: every record set is empty
+    HubLayout H = hub_layout(n, nnz, P, E, NP);
+    if (hub_scratch_bytes < H.total)
+        return fail(OCN_ENOSPACE, "ocn_cn_build: hub scratch %zu < %zu bytes", hub_scratch_bytes, H.total);
+    HubAux* aux = nullptr;
+    if (int rc = hub_aux(&aux)) return rc;
+    cudaStream_t sa = aux->stream;
+    PlanLayout L = plan_layout(T);
+    const char* pb = (const char*)plan_scratch;
+    const int64_t* rec_off = (const int64_t*)(pb + L.rec_off);
+    const int32_t* run_id = (const int32_t*)(pb + L.run_id);
+    const int32_t* run_start = (const int32_t*)(pb + L.run_start);
+    const int32_t* hub_off = (const int32_t*)(pb + L.hub_off);
+    const int32_t* chunk_off = (const int32_t*)(pb + L.chunk_off);
+    const int32_t* long_list = (const int32_t*)(pb + L.long_list);
+    const int64_t* run_pos_off = (const int64_t*)(pb + L.run_pos_off);
+    uint4* node_index = (uint4*)node_scratch;
+    char* hb = (char*)hub_scratch;
+    uint32_t* pkey[2] = {(uint32_t*)(hb + H.pkey[0]), (uint32_t*)(hb + H.pkey[1])};
+    uint32_t* pval[2] = {(uint32_t*)(hb + H.pval[0]), (uint32_t*)(hb + H.pval[1])};
+    uint32_t* ekey[2] = {(uint32_t*)(hb + H.ekey[0]), (uint32_t*)(hb + H.ekey[1])};
+    uint32_t* eval[2] = {(uint32_t*)(hb + H.eval[0]), (uint32_t*)(hb + H.eval[1])};
+    int64_t* ent_off = (int64_t*)(hb + H.ent_off);
+    uint2* items = (uint2*)(hb + H.items);
+    int32_t* prun = (int32_t*)(hb + H.prun);
+    unsigned long long* prec = (unsigned long long*)(hb + H.prec);
+    unsigned long long* counters = (unsigned long long*)(hb + H.counters);
+    const int bits = key_bits(n);
+    const int th = 256;
+
+    OCN_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * 4, st));
+    OCN_CUDA(cudaEventRecord(aux->ev[0], st));  // fork: everything before this call is visible to the auxiliary stream
+    OCN_CUDA(cudaStreamWaitEvent(sa, aux->ev[0], 0));
+
+    // auxiliary stream: (shared row, link) pairs, sorted by row, and the work items
+    cub::DoubleBuffer<uint32_t> dk(pkey[0], pkey[1]), dv(pval[0], pval[1]);
+    if (P > 0) {
+        k_hub_emit_pairs<<<grid_for(T * 32, th), th, 0, sa>>>(rowptr, col, dst, T, hub_d, hub_off, pkey[0], pval[0]);
+        OCN_LAUNCH_CHECK();
+        k_hub_emit_pairs_long<<<sm_count() * 2, 1024, 0, sa>>>(rowptr, col, dst, hub_d, hub_off, long_list, plan_dev,
+                                                              pkey[0], pval[0]);
+        OCN_LAUNCH_CHECK();
+        size_t tb2 = H.cub_temp2_bytes;
+        OCN_CUDA(cub::DeviceRadixSort::SortPairs(hb + H.cub_temp2, tb2, dk, dv, (int)P, 0, bits, sa));
+        k_hub_items<<<grid_for(P, th), th, 0, sa>>>(rowptr, run_id, rec_off, dk.Current(), dv.Current(), P, prun, prec,
+                                                    items, H.max_items, counters);
+        OCN_LAUNCH_CHECK();
+    }
+    OCN_CUDA(cudaEventRecord(aux->ev[1], sa));
+
+    // caller's stream: the inverted index of the source side
+    void* tmp = hb + H.cub_temp;
+    size_t tmp_bytes = H.cub_temp_bytes;
+    cub::DoubleBuffer<uint32_t> ek(ekey[0], ekey[1]), ev(eval[0], eval[1]);
+    k_hub_pos_count<<<grid_for(NP + 1, th), th, 0, st>>>(rowptr, col, src, run_start, run_pos_off, R, NP, ent_off);
+    OCN_LAUNCH_CHECK();
+    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, ent_off, ent_off, (int)(NP + 1), st));
+    k_hub_emit_entries<<<grid_for(NP * 32, th), th, 0, st>>>(rowptr, col, src, run_start, run_pos_off, R, NP, ent_off,
+                                                            ekey[0], eval[0]);
+    OCN_LAUNCH_CHECK();
+    OCN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ek, ev, (int)E, 0, bits, st));
+    k_hub_entry_heads<<<grid_for(E, th), th, 0, st>>>(ek.Current(), ev.Current(), run_pos_off, (int)R, E, 1, node_index);
+    OCN_LAUNCH_CHECK();
+    OCN_CUDA(cudaEventRecord(aux->ev[2], st));  // index complete
+
+    // auxiliary stream: per link, C1, C2 and C3 through the rows that are not shared (needs the index only)
+    OCN_CUDA(cudaStreamWaitEvent(sa, aux->ev[2], 0));
+    k_cn_link<<<sm_count() * 8, 256, 0, sa>>>(rowptr, col, dst, T, run_id, rec_off, chunk_off, run_pos_off, ev.Current(),
+                                              node_index, hub_d, records);
+    OCN_LAUNCH_CHECK();
+    OCN_CUDA(cudaEventRecord(aux->ev[3], sa));
+
+    // caller's stream: the walk through the shared rows (needs the pairs and the items)
+    OCN_CUDA(cudaStreamWaitEvent(st, aux->ev[1], 0));
+    if (P > 0) {
+        const int rpad = (int)((R + 1 + 3) & ~int64_t(3));
+        const int uwords = (int)((((NP + 1) >> 1) + 3) & ~int64_t(3));
+        const size_t smem = sizeof(uint32_t) * ((size_t)rpad + (size_t)uwords * kHubWarps);
+        OCN_CUDA(cudaFuncSetAttribute(k_cn_hub_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = (int)((200u * 1024u) / smem);
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) per_sm = 1;
+        hub_timing_record(0, st);
+        k_cn_hub_count<<<sm_count() * per_sm, kHubThreads, smem, st>>>(
+            rowptr, col, dk.Current(), prun, prec, P, ev.Current(), node_index, run_pos_off, (int)R, (int)NP, items,
+            H.max_items, counters, records);
+        OCN_LAUNCH_CHECK();
+        hub_timing_record(1, st);
+    }
+    OCN_CUDA(cudaStreamWaitEvent(st, aux->ev[3], 0));  // join
+    k_hub_entry_heads<<<grid_for(E, th), th, 0, st>>>(ek.Current(), ev.Current(), run_pos_off, (int)R, E, 0, node_index);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+}  // namespace ocn
+
+using namespace ocn;
+
+extern "C" size_t ocn_cn_hub_bytes(int64_t n, int64_t nnz, const int64_t* plan_host) {
+    if (n <= 0 || nnz < 0 || plan_host == nullptr) return 0;
+    if (plan_host[OCN_PLAN_HUB_DEGREE] <= 0) return 0;
+    return hub_layout(n, nnz, plan_host[OCN_PLAN_HUB_PAIRS], plan_host[OCN_PLAN_HUB_ENTRIES],
+                      plan_host[OCN_PLAN_HUB_POSITIONS]).total;
+}
+
+extern "C" int ocn_cn_hub_timing_events(void* start_event, void* stop_event) {
+    g_hub_events[0] = (cudaEvent_t)start_event;
+    g_hub_events[1] = (cudaEvent_t)stop_event;
+    return OCN_OK;
+}

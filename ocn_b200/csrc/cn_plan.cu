@@ -22,9 +22,15 @@ PlanLayout plan_layout(int64_t T) {
     L.run_unit_off = off;  off += align16(sizeof(int64_t) * (T + 2));
     L.cost_pre = off;      off += align16(sizeof(int64_t) * (T + 2));
     L.partial = off;       off += align16(sizeof(float) * 3 * (T + 1));
-    size_t b1 = 0, b2 = 0;
+    L.hub_off = off;       off += align16(sizeof(int32_t) * (T + 2));
+    L.run_pos_off = off;   off += align16(sizeof(int64_t) * (T + 2));
+    L.chunk_off = off;     off += align16(sizeof(int32_t) * (T + 2));
+    L.long_list = off;     off += align16(sizeof(int32_t) * (T + 2));
+    size_t b1 = 0, b2 = 0, b3 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, b1, (int64_t*)nullptr, (int64_t*)nullptr, (int)(T + 2));
     cub::DeviceScan::InclusiveSum(nullptr, b2, (int32_t*)nullptr, (int32_t*)nullptr, (int)(T + 2));
+    cub::DeviceScan::ExclusiveSum(nullptr, b3, (int32_t*)nullptr, (int32_t*)nullptr, (int)(T + 2));
+    if (b3 > b2) b2 = b3;
     L.cub_temp = off;
     L.cub_temp_bytes = align16((b1 > b2 ? b1 : b2) + 256);
     off += L.cub_temp_bytes;
@@ -47,14 +53,18 @@ __global__ void k_plan_edges(const int64_t* __restrict__ rowptr, const int64_t* 
 }
 
 // after the inclusive scan flag[t] = run index + 1
-__global__ void k_plan_runs(const int64_t* __restrict__ src, int64_t T, int64_t batch_size,
-                            const int32_t* __restrict__ run_incl, int32_t* __restrict__ run_start,
+__global__ void k_plan_runs(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ src, int64_t T,
+                            int64_t batch_size, const int32_t* __restrict__ run_incl, int32_t* __restrict__ run_start,
                             int64_t* __restrict__ plan) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     bool first = (t % batch_size == 0) || src[t - 1] != src[t];
     int32_t r = run_incl[t] - 1;
-    if (first) run_start[r] = (int32_t)t;
+    if (first) {
+        run_start[r] = (int32_t)t;
+        // positions of the stream = sum over runs of deg(src) (k_plan_hub_decide needs it before the run-level scan)
+        atomicAdd((unsigned long long*)&plan[OCN_PLAN_HUB_POSITIONS], (unsigned long long)(rowptr[src[t] + 1] - rowptr[src[t]]));
+    }
     if (t == T - 1) {
         run_start[r + 1] = (int32_t)T;
         plan[OCN_PLAN_NUM_RUNS] = r + 1;
@@ -62,50 +72,112 @@ __global__ void k_plan_runs(const int64_t* __restrict__ src, int64_t T, int64_t 
 }
 
 // one warp per link: walk cost = number of columns the j-side walk probes (+ a constant)
+// Rows N(m) of at least plan[OCN_PLAN_HUB_DEGREE] columns are not walked per link: the hub stage
+// (cn_hub.cu) streams each of them once for all links of the stream; they are counted into hub_cnt.
+// The warp covers the first kLongRow neighbours of dst; a destination with more is queued for
+// k_plan_cost_long (one CTA per such link), so that a hub destination is not a serial tail.
+__device__ __forceinline__ void cost_of_row(const int64_t* __restrict__ rowptr, int32_t m, int64_t hub_d, long long& w, int& hubs) {
+    const long long dm = ldg_i64(rowptr + m + 1) - ldg_i64(rowptr + m);
+    if (hub_d > 0 && dm >= hub_d) ++hubs; else w += dm;
+}
+
 __global__ void k_plan_cost(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                             const int64_t* __restrict__ dst, int64_t T, int order, int64_t* __restrict__ cost,
+                            int32_t* __restrict__ hub_cnt, int32_t* __restrict__ chunk_cnt, int32_t* __restrict__ long_list,
                             int64_t* __restrict__ plan) {
     const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t > T) return;
     if (t == T) {
-        if (lane == 0) cost[t] = 0;
+        if (lane == 0) { cost[t] = 0; hub_cnt[t] = 0; chunk_cnt[t] = 0; }
         return;
     }
+    const int64_t hub_d = plan[OCN_PLAN_HUB_DEGREE];
     const int64_t j = dst[t];
     const int64_t rs = rowptr[j], d = rowptr[j + 1] - rs;
     long long w = 0;
+    int hubs = 0;
     if (order >= 3) {
-        for (int64_t o = lane; o < d; o += 32) {
-            const int32_t m = col[rs + o];
-            w += rowptr[m + 1] - rowptr[m];
-        }
+        const int64_t dcap = d < kLongRow ? d : kLongRow;
+        for (int64_t o = lane; o < dcap; o += 32) cost_of_row(rowptr, ldg_i32(col + rs + o), hub_d, w, hubs);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            w += __shfl_xor_sync(0xffffffffu, w, o);
+            hubs += __shfl_xor_sync(0xffffffffu, hubs, o);
+        }
     }
     if (order >= 2) w += d;
     w += kLinkCost;
     if (lane == 0) {
         cost[t] = w;
+        hub_cnt[t] = hubs;
+        chunk_cnt[t] = (int32_t)((d + 31) >> 5);
         atomicAdd((unsigned long long*)&plan[OCN_PLAN_TOTAL_COST], (unsigned long long)w);
+        if (order >= 3 && d > kLongRow)
+            long_list[atomicAdd((unsigned long long*)&plan[OCN_PLAN_LONG_COUNT], 1ull)] = (int32_t)t;
     }
+}
+
+__global__ void __launch_bounds__(1024)
+k_plan_cost_long(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ dst,
+                 int64_t* __restrict__ cost, int32_t* __restrict__ hub_cnt, const int32_t* __restrict__ long_list,
+                 int64_t* __restrict__ plan) {
+    __shared__ unsigned long long s_w;
+    __shared__ int s_h;
+    const int64_t n_long = plan[OCN_PLAN_LONG_COUNT];
+    const int64_t hub_d = plan[OCN_PLAN_HUB_DEGREE];
+    for (int64_t i = blockIdx.x; i < n_long; i += gridDim.x) {
+        const int64_t t = long_list[i];
+        const int64_t j = dst[t];
+        const int64_t rs = rowptr[j], d = rowptr[j + 1] - rs;
+        if (threadIdx.x == 0) { s_w = 0ull; s_h = 0; }
+        __syncthreads();
+        long long w = 0;
+        int hubs = 0;
+        for (int64_t o = kLongRow + threadIdx.x; o < d; o += blockDim.x) cost_of_row(rowptr, ldg_i32(col + rs + o), hub_d, w, hubs);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            w += __shfl_xor_sync(0xffffffffu, w, o);
+            hubs += __shfl_xor_sync(0xffffffffu, hubs, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&s_w, (unsigned long long)w);
+            atomicAdd(&s_h, hubs);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {  // each long link is owned by one CTA: plain read-modify-write
+            cost[t] += (int64_t)s_w;
+            hub_cnt[t] += s_h;
+            atomicAdd((unsigned long long*)&plan[OCN_PLAN_TOTAL_COST], s_w);
+        }
+        __syncthreads();
+    }
+}
+
+// the indexed path (cn_hub.cu) is used for order 3 when the runs and positions of the stream fit its
+// per-warp shared-memory counters
+__global__ void k_plan_hub_decide(int order, int64_t hub_degree, int64_t* __restrict__ plan) {
+    const bool fits = plan[OCN_PLAN_NUM_RUNS] <= kHubMaxRuns && plan[OCN_PLAN_HUB_POSITIONS] <= kHubMaxPositions;
+    plan[OCN_PLAN_HUB_DEGREE] = (order >= 3 && hub_degree > 0 && fits) ? hub_degree : 0;
 }
 
 // one warp per run: (table passes over all 32-position chunks of N(src)) x (cost windows of the run)
 __global__ void k_plan_units(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                              const int64_t* __restrict__ src, int64_t T, const int32_t* __restrict__ run_start,
                              const int64_t* __restrict__ cost_pre, int resident_ctas,
-                             const int64_t* __restrict__ plan, int64_t* __restrict__ run_units) {
+                             int64_t* __restrict__ plan, int64_t* __restrict__ run_units,
+                             int64_t* __restrict__ run_pos) {
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r > T + 1) return;
     const int64_t n_runs = plan[OCN_PLAN_NUM_RUNS];
-    int64_t u = 0;
+    int64_t u = 0, npos = 0;
     if (r < n_runs) {
         const int64_t t0 = run_start[r], len = run_start[r + 1] - t0;
         const int64_t i = src[t0];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
         int64_t passes = 0;
+        long long keys = 0;
         for (int64_t c0 = 0; c0 < d; c0 += kPChunk) {
             long long f = 0;
             if (c0 + lane < d) {
@@ -115,16 +187,25 @@ __global__ void k_plan_units(const int64_t* __restrict__ rowptr, const int32_t* 
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
             passes += (f + kCap - 1) / kCap;
+            keys += f;
+        }
+        if (plan[OCN_PLAN_HUB_DEGREE] > 0) {  // the hub stage lists every (key, run, position) entry
+            npos = d;
+            if (lane == 0) atomicAdd((unsigned long long*)&plan[OCN_PLAN_HUB_ENTRIES], (unsigned long long)keys);
         }
         const long long W = unit_budget(plan[OCN_PLAN_TOTAL_COST], resident_ctas);
         const long long run_cost = cost_pre[t0 + len] - cost_pre[t0];
         u = passes * ((run_cost + W - 1) / W);
     }
-    if (lane == 0) run_units[r] = u;
+    if (lane == 0) {
+        run_units[r] = u;
+        run_pos[r] = npos;
+    }
 }
 
 __global__ void k_plan_finish(int64_t T, int64_t batch_size, int resident_ctas, const int64_t* __restrict__ rec_off,
-                              const int64_t* __restrict__ run_unit_off, int64_t* __restrict__ plan) {
+                              const int64_t* __restrict__ run_unit_off, const int32_t* __restrict__ hub_off,
+                              const int64_t* __restrict__ run_pos_off, int64_t* __restrict__ plan) {
     plan[OCN_PLAN_NUM_RECORDS] = rec_off[T];
     plan[OCN_PLAN_NUM_UNITS] = run_unit_off[plan[OCN_PLAN_NUM_RUNS]];
     plan[OCN_PLAN_NUM_BATCHES] = (T + batch_size - 1) / batch_size;
@@ -132,6 +213,8 @@ __global__ void k_plan_finish(int64_t T, int64_t batch_size, int resident_ctas, 
     plan[OCN_PLAN_BUDGET] = unit_budget(plan[OCN_PLAN_TOTAL_COST], resident_ctas);
     // orders <= 2: the table pays off only when several links share it (runs of >= 3 links on average)
     plan[OCN_PLAN_USE_DIRECT] = (T <= 3 * plan[OCN_PLAN_NUM_RUNS]) ? 1 : 0;
+    plan[OCN_PLAN_HUB_PAIRS] = hub_off[T];
+    plan[OCN_PLAN_HUB_POSITIONS] = run_pos_off[plan[OCN_PLAN_NUM_RUNS]];  // 0 when the indexed path is off
 }
 
 }  // namespace ocn
@@ -148,12 +231,14 @@ size_t ocn_cn_colstat_bytes(int64_t n) { return n < 0 ? 0 : sizeof(ColStat) * (s
 size_t ocn_cn_record_bytes(void) { return sizeof(Record); }
 
 int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst, int64_t num_edges,
-                int64_t batch_size, int order, void* plan_scratch, size_t plan_scratch_bytes, int64_t* out_plan, void* stream) {
+                int64_t batch_size, int order, int64_t hub_degree, void* plan_scratch, size_t plan_scratch_bytes,
+                int64_t* out_plan, void* stream) {
     OCN_CHECK_ARG(rowptr && col && out_plan && plan_scratch, "ocn_cn_plan: null pointer");
     OCN_CHECK_ARG(n > 0 && num_edges > 0 && batch_size > 0, "ocn_cn_plan: n, num_edges and batch_size must be positive");
     OCN_CHECK_ARG(num_edges < (int64_t(1) << 30), "ocn_cn_plan: at most 2^30 links per call");
     OCN_CHECK_ARG(src && dst, "ocn_cn_plan: null edge pointer");
     OCN_CHECK_ARG(order >= 1 && order <= 3, "ocn_cn_plan: order must be 1..3");
+    OCN_CHECK_ARG(hub_degree >= -1, "ocn_cn_plan: hub_degree must be -1 (off), 0 (auto) or a degree");
     PlanLayout L = plan_layout(num_edges);
     if (plan_scratch_bytes < L.total)
         return fail(OCN_ENOSPACE, "ocn_cn_plan: plan scratch %zu < %zu bytes", plan_scratch_bytes, L.total);
@@ -171,22 +256,39 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
     int threads = 256;
     int blocks = (int)((T + 1 + threads - 1) / threads);
     OCN_CUDA(cudaMemsetAsync(out_plan, 0, sizeof(int64_t) * OCN_PLAN_WORDS, st));
+    int32_t* hub_off = (int32_t*)(base + L.hub_off);
+    int64_t* run_pos_off = (int64_t*)(base + L.run_pos_off);
+    if (hub_degree == 0) {  // auto: share a row once about 1.5 links of the stream are expected to walk it
+        hub_degree = (3 * n + 2 * num_edges - 1) / (2 * num_edges);  // (measured optimum 64 at n/T = 45, flat from 32 to 128)
+        if (hub_degree < 32) hub_degree = 32;
+    }
     k_plan_edges<<<blocks, threads, 0, st>>>(rowptr, src, T, batch_size, rec_off, run_id);
     OCN_LAUNCH_CHECK();
-    int blocks_w = (int)(((T + 1) * 32 + threads - 1) / threads);
-    k_plan_cost<<<blocks_w, threads, 0, st>>>(rowptr, col, dst, T, order, cost_pre, out_plan);
-    OCN_LAUNCH_CHECK();
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, rec_off, rec_off, (int)(T + 1), st));
-    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cost_pre, cost_pre, (int)(T + 1), st));
     OCN_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, run_id, run_id, (int)(T + 1), st));
-    k_plan_runs<<<blocks, threads, 0, st>>>(src, T, batch_size, run_id, run_start, out_plan);
+    k_plan_runs<<<blocks, threads, 0, st>>>(rowptr, src, T, batch_size, run_id, run_start, out_plan);
     OCN_LAUNCH_CHECK();
+    k_plan_hub_decide<<<1, 1, 0, st>>>(order, hub_degree, out_plan);
+    OCN_LAUNCH_CHECK();
+    int blocks_w = (int)(((T + 1) * 32 + threads - 1) / threads);
+    int32_t* chunk_off = (int32_t*)(base + L.chunk_off);
+    int32_t* long_list = (int32_t*)(base + L.long_list);
+    k_plan_cost<<<blocks_w, threads, 0, st>>>(rowptr, col, dst, T, order, cost_pre, hub_off, chunk_off, long_list, out_plan);
+    OCN_LAUNCH_CHECK();
+    if (order >= 3) {
+        k_plan_cost_long<<<sm_count() * 2, 1024, 0, st>>>(rowptr, col, dst, cost_pre, hub_off, long_list, out_plan);
+        OCN_LAUNCH_CHECK();
+    }
+    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cost_pre, cost_pre, (int)(T + 1), st));
+    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, hub_off, hub_off, (int)(T + 1), st));
+    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, chunk_off, chunk_off, (int)(T + 1), st));
     int blocks2 = (int)(((T + 2) * 32 + threads - 1) / threads);
     k_plan_units<<<blocks2, threads, 0, st>>>(rowptr, col, src, T, run_start, cost_pre, resident_ctas, out_plan,
-                                              run_unit_off);
+                                              run_unit_off, run_pos_off);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, run_unit_off, run_unit_off, (int)(T + 2), st));
-    k_plan_finish<<<1, 1, 0, st>>>(T, batch_size, resident_ctas, rec_off, run_unit_off, out_plan);
+    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, run_pos_off, run_pos_off, (int)(T + 2), st));
+    k_plan_finish<<<1, 1, 0, st>>>(T, batch_size, resident_ctas, rec_off, run_unit_off, hub_off, run_pos_off, out_plan);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
 }

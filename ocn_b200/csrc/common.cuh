@@ -38,11 +38,6 @@ constexpr int kEdgeSub = 32;  // target links of a run handled by one work unit
 constexpr int kSlots = 20399;  // (key, mask) slots of the shared-memory table of ocn_cn_build (prime, 159 KB)
 constexpr int kCap = (kSlots * 7) / 10;  // keys inserted per table pass (load factor 0.7)
 
-// one record per (target link, position p in N(src)):
-//   x = C2 | (C1 << 31)   (C1 in {0,1}; C2 = #2-walks dst->..->N(src)[p], < 2^31)
-//   y = C3                (#3-walks)
-using Record = uint2;
-
 // per-batch, per-node column statistics (32 B = one L2 sector)
 struct __align__(32) ColStat {
     uint32_t c1;   // number of links of the batch that have this node in CN1
@@ -61,11 +56,38 @@ struct PlanLayout {
     size_t run_unit_off;   // int64[T+2]
     size_t cost_pre;       // int64[T+2]  exclusive prefix of the per-link walk cost
     size_t partial;        // float[3*T]
+    size_t hub_off;        // int32[T+2]  exclusive prefix of the per-link number of hub rows in N(dst)
+    size_t run_pos_off;    // int64[T+2]  exclusive prefix of deg(src) over the runs (hub stage positions)
+    size_t chunk_off;      // int32[T+2]  exclusive prefix of ceil(deg(dst)/32) (items of the per-link kernel)
+    size_t long_list;      // int32[T+2]  links whose destination has more than kLongRow neighbours
     size_t cub_temp;       // bytes
     size_t cub_temp_bytes;
     size_t total;
 };
 PlanLayout plan_layout(int64_t num_edges);
+
+// one record per (target link, position p in N(src)):
+//   x = C2 | (C1 << 31)   (C1 in {0,1}; C2 = #2-walks dst->..->N(src)[p], < 2^31)
+//   y = C3                (#3-walks)
+using Record = uint2;
+
+// hub stage scratch (cn_hub.cu), offsets in bytes
+struct HubLayout {
+    size_t pkey[2], pval[2];  // uint32[P] x2 each: (hub row, link) pairs, radix-sort double buffers
+    size_t ekey[2], eval[2];  // uint32[E] x2 each: (key, position of the stream) entries
+    size_t ent_off;           // int64[positions + 2]
+    size_t items;             // uint2[max_items]
+    int64_t max_items;
+    size_t counters;          // uint64[4]: number of items, next item
+    size_t prun, prec;        // int32[P] run / uint64[P] record offset of the link of every sorted pair
+    size_t cub_temp, cub_temp_bytes;    // entry pipeline (caller's stream)
+    size_t cub_temp2, cub_temp2_bytes;  // pair pipeline (auxiliary stream)
+    size_t total;
+};
+HubLayout hub_layout(int64_t n, int64_t nnz, int64_t pairs, int64_t entries, int64_t positions);
+int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst,
+                  int64_t T, const void* plan_scratch, const int64_t* plan_dev, const int64_t* plan_host, void* hub_scratch,
+                  size_t hub_scratch_bytes, void* node_scratch, Record* records, int64_t nnz, cudaStream_t st);
 
 // cost window (in probed columns) one work unit of ocn_cn_build covers: about 8 units per resident CTA,
 // clamped so that a unit amortises its table build but a heavy link is still split over many CTAs
@@ -83,6 +105,10 @@ constexpr int kLinkCost = 64;  // fixed cost added to every link so that empty l
 #define OCN_PLAN_BUDGET 5
 #define OCN_PLAN_TOTAL_COST 6
 #define OCN_PLAN_USE_DIRECT 7  /* orders <= 2 only: 1 = table-free kernel (short runs), 0 = table kernel */
+#define OCN_PLAN_LONG_COUNT 12 /* entries of the long-destination list */
+constexpr int kLongRow = 256;      // neighbours of dst a single warp walks in the plan / pair kernels; the rest goes to a CTA
+constexpr int kHubMaxRuns = 2048;       // indexed path: run -> first position table in shared memory
+constexpr int kHubMaxPositions = 8192;  // indexed path: warp-private 16-bit counters per position (16 KB per warp)
 
 // ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--kind", default="stream")
     ap.add_argument("--feat", type=int, default=32)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--hub", type=int, default=0, help="hub_degree: 0 auto, -1 off")
     a = ap.parse_args()
     dev = "cuda:0"
     t0 = time.time()
@@ -40,7 +41,7 @@ def main():
     for rep in range(a.reps):
         marks = [ev() for _ in range(6)]
         marks[0].record()
-        sess = ob.CNSession(G, e, a.batch, a.order)
+        sess = ob.CNSession(G, e, a.batch, a.order, a.hub)
         marks[1].record()
         sess.build(a.order, True)
         marks[2].record()
@@ -56,7 +57,7 @@ def main():
         tot = sum(ts)
         print(f"rep {rep}: " + "  ".join(f"{n} {t:.3f} ms" for n, t in zip(names, ts)) +
               f"  | total {tot:.3f} ms  {T / tot / 1e3:.3f} M links/s  units {sess.num_units} runs {sess.num_runs} "
-              f"records {sess.num_records}", flush=True)
+              f"records {sess.num_records} hub_d {sess.hub_degree} pairs {sess.plan_host[9]} entries {sess.plan_host[10]}", flush=True)
 
 
 if __name__ == "__main__":

@@ -18,14 +18,14 @@ def test_library_exports_every_header_symbol():
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/ocn_b200.h but not exported"
         assert s in _lib._SIGS, f"{s} has no ctypes signature"
-    assert L.ocn_abi_version() == 1
+    assert L.ocn_abi_version() == 2
 
 
 def test_argument_errors_do_not_need_a_gpu():
     L = _lib.lib()
     assert L.ocn_cn_plan_bytes(-1) == 0 and L.ocn_cn_plan_bytes(1000) > 1000 * 8
     assert L.ocn_cn_record_bytes() == 8 and L.ocn_cn_colstat_bytes(10) == 320
-    rc = L.ocn_cn_build(None, None, 0, None, None, 0, 0, 2, 1, None, None, None, 0, None, None)
+    rc = L.ocn_cn_build(None, None, 0, None, None, 0, 0, 2, 1, None, None, None, 0, None, 0, None, None, 0, None, None)
     assert rc == -1 and b"null pointer" in L.ocn_last_error()
     rc = L.ocn_spmm_csr(None, None, None, 4, None, 32, 0, None, None)
     assert rc == -1

@@ -330,6 +330,46 @@ def test_full_size_citation2_walk_counts():
             assert torch.equal(cns[k].value[s:t].double(), vals[keep])
 
 
+@pytest.mark.parametrize("name,B", [("tiny", 128), ("tiny_dense", 64), ("cora", 384), ("citation2_s", 2048)])
+@pytest.mark.parametrize("hub", [2, 7, 40])
+def test_hub_stage_bit_exact(name, B, hub):
+    """Order-3 walk counts with rows of >= hub columns routed through the hub stage (cn_hub.cu)
+    against the oracle; the per-link table kernel handles the rest."""
+    g = GRAPHS[name]()
+    G, A = _graph(g), _sp(g)
+    e = g.query_edges(B, "stream" if name.startswith("citation2") else "mixed")
+    ref = R.get_cn(A, e, 3)
+    sess = ob.CNSession(G, e.to(DEV), None, 3, hub_degree=hub)
+    assert sess.hub_degree == hub and sess.hub_bytes > 0
+    sess.build(3, True, with_stats=False)
+    for k in range(3):
+        _assert_rows_equal(sess.extract(k + 1), ref[k])
+    assert bool((G._ws["hub_node"] == 0).all()), "node index not restored"
+    # several batches in one stream (runs are cut at batch boundaries)
+    got = ob.get_cn(G, e.to(DEV), 3, True, hub_degree=hub, batch_size=max(8, B // 5))
+    for k in range(3):
+        _assert_rows_equal(got[k], ref[k])
+
+
+def test_hub_stage_matches_table_kernel_at_scale():
+    """citation2 shape at 5 % size, 16 batches of the evaluation stream: hub stage on (automatic
+    threshold and a low one) == hub stage off, bit for bit, for every record."""
+    g = synth.make_graph("citation2", scale=0.05, device=DEV)
+    G = ob.Graph(g.rowptr, g.col, g.n)
+    e = g.query_edges(16 * 2048, "stream", device=DEV)
+    off = ob.CNSession(G, e, 2048, 3, hub_degree=-1)
+    assert off.hub_degree == 0
+    off.build(3, True, with_stats=False)
+    for hub in (0, 24):
+        on = ob.CNSession(G, e, 2048, 3, hub_degree=hub)
+        assert on.hub_degree > 0
+        on.build(3, True, with_stats=False)
+        assert torch.equal(on.records, off.records)
+    # a stream with one run per link (training shape) keeps the stage off
+    many = ob.CNSession(G, g.query_edges(4096, "neg", device=DEV), 2048, 3)
+    assert many.hub_degree == 0
+
+
 def test_torch_custom_ops():
     """torch.ops.ocn.* (north_star: the C ABI exposed as PyTorch custom ops), incl. autograd registration."""
     g = GRAPHS["cora"]()
