@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--feat", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=48, help="links of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hub", type=int, default=0, help="hub_degree of the indexed order-3 path: 0 auto, -1 off (per-run tables)")
+    ap.add_argument("--no-plan-stream", action="store_true", help="plan on the main stream (no overlap with the previous step)")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed device steps (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -118,9 +122,11 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes(G, e, order, feat, batch):
+def algorithmic_bytes(G, e, order, feat, batch, hub_d=0):
     """Bytes the fused path must move for these links with no cache credit (DESIGN.md "Byte accounting").
-    Returns (build_kernel_bytes, whole_step_bytes, survey_formula_bytes)."""
+    Returns (build_stage_bytes, whole_step_bytes, survey_formula_bytes, shared_row_kernel_bytes); the last is the
+    part of SURVEY.md 8(d)'s per-link index term that runs through rows of >= hub_d columns -- the walk
+    k_cn_hub_count performs once per stream instead of once per link."""
     import ocn_b200 as ob  # noqa: F401
     deg = G.degree()
     colL = G.col.long()
@@ -147,7 +153,12 @@ def algorithmic_bytes(G, e, order, feat, batch):
     agg = int((3 * 8 + 4 + 32 + 4 * feat) * di.sum()) + T * (4 * feat * (order + 1) + 2 * 4 * feat + 32)
     survey = int((32 + 4 * (di + dj) + (8 * dj + 4 * Fj if order >= 2 else 0) + (8 * di + 4 * Fi if order >= 3 else 0)).sum()) \
         + T * 4 * feat * (order + 1 + 2)
-    return build, build + agg, survey
+    hub = 0
+    if hub_d > 0 and order >= 3:
+        big = deg >= hub_d
+        Fh = torch.zeros(G.n, dtype=torch.int64, device=G.device).index_add_(0, G.row(), (8 + 4 * deg[colL]) * big[colL])
+        hub = int(Fh[j].sum())
+    return build, build + agg, survey, hub
 
 
 def run_reference(a, rank, world):
@@ -253,18 +264,25 @@ def main():
     pred = cls(a.feat, a.feat, 1, 3, 0.0, weighted=True).to(dev).eval()
     ip3 = torch.zeros(3, device=dev)
 
+    # the plan of a step (and its size read-back) runs on its own stream: the host waits for the plan only,
+    # while the main stream is still executing the previous step
+    plan_stream = None if a.no_plan_stream else torch.cuda.Stream(device=dev)
+
     def step_device(s):
         e = e_rank[:, s * T:(s + 1) * T]
-        sess = ob.CNSession(G, e, a.batch, a.order).build(a.order, True)
+        sess = ob.CNSession(G, e, a.batch, a.order, a.hub, plan_stream=plan_stream).build(a.order, True)
         sess.stats(5, 0.0, ip3, 0)
         out = sess.aggregate(x, 5, 0.0, ip3)
         sess.release()
         return out
 
+    out_host = [torch.empty(world * T, dtype=torch.float32).pin_memory() for _ in range(nsteps)]
+
     def step_e2e(s):
-        e = e_host[:, s * T:(s + 1) * T].to(dev, non_blocking=True)
+        with torch.cuda.stream(plan_stream if plan_stream is not None else torch.cuda.current_stream()):
+            e = e_host[:, s * T:(s + 1) * T].to(dev, non_blocking=True)
         with torch.no_grad():
-            sess = ob.CNSession(G, e, a.batch, a.order).build(a.order, True)
+            sess = ob.CNSession(G, e, a.batch, a.order, a.hub, plan_stream=plan_stream).build(a.order, True)
             if a.order >= 3:
                 out = pred(x, G, sess, None, None, e)
             else:
@@ -275,7 +293,11 @@ def main():
             allsc = torch.empty(world * T, dtype=scores.dtype, device=dev)
             dist.all_gather_into_tensor(allsc, scores.contiguous())
             scores = allsc
-        return scores.cpu() if rank == 0 else scores[:1].cpu()
+        # device -> host read of the step's result: asynchronous copy into pinned memory (an evaluation loop
+        # collects the scores of every batch and ranks them at the end); the timed region ends with a full sync
+        n_out = scores.numel() if rank == 0 else 1
+        out_host[s][:n_out].copy_(scores[:n_out], non_blocking=True)
+        return out_host[s]
 
     def barrier():
         if world > 1:
@@ -283,10 +305,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn):
+    def timed(fn, profile=False):
         for s in range(a.warmup):
             fn(s)
         barrier()
+        if profile:
+            torch.cuda.cudart().cudaProfilerStart()
         sampler = ClockSampler(local)
         sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -296,6 +320,8 @@ def main():
             fn(s)
         ev1.record()
         barrier()
+        if profile:
+            torch.cuda.cudart().cudaProfilerStop()
         wall = time.perf_counter() - t0
         clocks = sampler.stop()
         ms = ev0.elapsed_time(ev1)
@@ -306,34 +332,51 @@ def main():
             ms, wall = float(t[0]), float(t[1]) / 1e3
         return ms, wall, clocks
 
-    ms_dev, _, clocks = timed(step_device)
+    ms_dev, _, clocks = timed(step_device, a.profile_range)
     ms_e2e_ev, wall_e2e, _ = timed(step_e2e)
     ms_e2e = max(ms_e2e_ev, wall_e2e * 1e3)  # the D2H read ends after the last event: use the host clock too
 
-    # roofline of the dominant kernel (k_cn_build): events around it on its stream, fresh links each launch
-    build_ms = []
+    # roofline of the dominant kernel: CUDA events recorded by the library on the build's stream right
+    # before / after k_cn_hub_count (indexed path) -- or around the whole build stage when the per-run
+    # table kernel k_cn_build is in use (--hub -1) -- fresh links each launch
+    L = ob._lib.lib()
+    build_ms, kern_ms, hub_ds = [], [], []
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record(); k1.record()
+    torch.cuda.synchronize()
     for s in range(a.warmup, nsteps):
         e = e_rank[:, s * T:(s + 1) * T]
-        sess = ob.CNSession(G, e, a.batch, a.order)
+        sess = ob.CNSession(G, e, a.batch, a.order, a.hub)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        indexed = sess.hub_degree > 0
+        if indexed:
+            L.ocn_cn_hub_timing_events(k0.cuda_event, k1.cuda_event)
         ev0.record()
         sess.build(a.order, True)
         ev1.record()
         torch.cuda.synchronize()
+        L.ocn_cn_hub_timing_events(None, None)
         sess.release()
         build_ms.append(ev0.elapsed_time(ev1))
+        kern_ms.append(k0.elapsed_time(k1) if indexed else build_ms[-1])
+        hub_ds.append(sess.hub_degree)
     build_avg = sum(build_ms) / len(build_ms)
-    bb = [algorithmic_bytes(G, e_rank[:, s * T:(s + 1) * T], a.order, a.feat, a.batch) for s in range(a.warmup, nsteps)]
+    kern_avg = sum(kern_ms) / len(kern_ms)
+    indexed = hub_ds[-1] > 0
+    bb = [algorithmic_bytes(G, e_rank[:, s * T:(s + 1) * T], a.order, a.feat, a.batch, hub_ds[s - a.warmup])
+          for s in range(a.warmup, nsteps)]
     build_bytes = sum(b[0] for b in bb) / len(bb)
     step_bytes = sum(b[1] for b in bb) / len(bb)
     survey_bytes = sum(b[2] for b in bb) / len(bb)
+    kern_bytes = (sum(b[3] for b in bb) / len(bb)) if indexed else build_bytes
+    kern_name = "k_cn_hub_count" if indexed else "k_cn_build"
     peak, peak_src = peaks()
-    achieved = build_bytes / (build_avg * 1e-3) / 1e9
+    achieved = kern_bytes / (kern_avg * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("k_cn_build_dram_bytes_per_launch")
+            traffic = json.load(f).get(kern_name + "_dram_bytes_per_launch")
 
     if rank == 0:
         links = world * T * a.steps
@@ -346,13 +389,19 @@ def main():
             "e2e": {"value": links / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * T,
                     "d2h_bytes_per_step": 4 * T * (world if world > 1 else 1), "ms_per_step": ms_e2e / a.steps,
                     "api": "CNLinkPredictor*.forward(h, adj, CNSession, ..., edges) -> scores.cpu()"},
-            "gpu_launches": 12 * a.steps,  # per step: 5 plan + build + colstat + 3 stats + aggregate + release (CUB scans not counted)
-            "roofline": {"bound": "hbm", "kernel": "k_cn_build", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            # own kernels per step (CUB scans / radix sorts not counted): 7 plan + 10 build (indexed path; 2 with
+            # the table kernel) + 3 stats + aggregate + release
+            "gpu_launches": ((22 if indexed else 14) * a.steps),
+            "roofline": {"bound": "hbm", "kernel": kern_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": build_bytes, "kernel_ms": build_avg,
-                         "kernel_share_of_step": build_avg / (ms_dev / a.steps),
-                         "whole_step_gbs": step_bytes / (ms_dev / a.steps * 1e-3) / 1e9,
-                         "survey_formula_gbs": survey_bytes / (ms_dev / a.steps * 1e-3) / 1e9},
+                         "algorithmic_bytes_per_launch": kern_bytes, "kernel_ms": kern_avg,
+                         "kernel_share_of_step": kern_avg / (ms_dev / a.steps),
+                         "build_stage_ms": build_avg, "hub_degree": hub_ds[-1],
+                         "whole_step_survey_gbs": survey_bytes / (ms_dev / a.steps * 1e-3) / 1e9,
+                         "whole_step_survey_frac": survey_bytes / (ms_dev / a.steps * 1e-3) / 1e9 / peak,
+                         "note": "achieved = SURVEY 8(d) per-link index bytes of the rows this kernel covers "
+                                 "(8 + 4 d(m) for every (link, m in N(dst)) with d(m) >= hub_degree) / its duration; the "
+                                 "kernel streams each such row once per stream, so the figure can exceed the DRAM traffic"},
         }
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a, g, g.rowptr.cpu(), g.col.cpu())

@@ -101,14 +101,20 @@ class CNSession:
     normalised independently (the column sums of model.py:2261 run over one batch)."""
 
     def __init__(self, graph: Graph, tarei: Tensor, batch_size: Optional[int] = None, order: int = 3,
-                 hub_degree: int = 0):
-        """``hub_degree``: rows of at least this many columns are walked once per stream by the hub
-        stage of the order-3 build (0 = chosen from n and the stream length, -1 = stage off)."""
+                 hub_degree: int = 0, plan_stream: Optional["torch.cuda.Stream"] = None):
+        """``hub_degree``: rows of at least this many columns are walked once per stream by the indexed
+        order-3 build (0 = chosen from n and the stream length, -1 = per-run tables instead).
+
+        ``plan_stream``: run the plan and its one size read-back on this CUDA stream instead of the
+        current one, so the host only waits for the plan while the current stream keeps executing the
+        previous session (``tarei`` must be ready on that stream).  Everything after the plan runs on
+        the current stream, which is made to wait for the plan."""
         _require_cuda(graph.col)
         _require_cuda(tarei)
         self.g = graph
-        self.src, self.dst = _edges(tarei)
-        self.T = int(self.src.numel())
+        if tarei.dim() != 2 or tarei.shape[0] != 2:
+            raise ValueError("target links must be an int64 tensor of shape [2, B]")
+        self.T = int(tarei.shape[1])
         if self.T == 0:
             raise ValueError("empty link batch")
         self.batch_size = int(batch_size or self.T)
@@ -117,14 +123,20 @@ class CNSession:
         L = _lib.lib()
         self.L = L
         self.plan_bytes = L.ocn_cn_plan_bytes(self.T)
-        self.plan_scratch = torch.empty(self.plan_bytes, dtype=torch.uint8, device=self.dev)
-        self.plan = torch.zeros(PLAN_WORDS, dtype=torch.int64, device=self.dev)
-        with torch.cuda.device(self.dev):
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.device(self.dev), torch.cuda.stream(plan_stream if plan_stream is not None else main):
+            self.src, self.dst = _edges(tarei)  # may copy: on the stream the plan reads it from
+            self.plan_scratch = torch.empty(self.plan_bytes, dtype=torch.uint8, device=self.dev)
+            self.plan = torch.zeros(PLAN_WORDS, dtype=torch.int64, device=self.dev)
             _lib.check(L.ocn_cn_plan(_lib.ptr(graph.rowptr), _lib.ptr(graph.col), graph.n, _lib.ptr(self.src),
                                      _lib.ptr(self.dst), self.T, self.batch_size, int(order), int(hub_degree),
                                      _lib.ptr(self.plan_scratch), self.plan_bytes,
                                      _lib.ptr(self.plan), _stream(self.dev)), "ocn_cn_plan")
-        host = self.plan.tolist()  # the one host sync of the session: buffer sizes
+            host = self.plan.tolist()  # the one host sync of the session (of the plan stream only): buffer sizes
+        if plan_stream is not None:
+            main.wait_stream(plan_stream)
+            for t in (self.plan_scratch, self.plan, self.src, self.dst):
+                t.record_stream(main)
         self.num_records, self.num_runs, self.num_units = host[0], host[1], host[2]
         self.plan_host = (ctypes.c_int64 * PLAN_WORDS)(*host)
         self.hub_degree = host[PLAN_HUB_DEGREE]

@@ -258,8 +258,8 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
     OCN_CUDA(cudaMemsetAsync(out_plan, 0, sizeof(int64_t) * OCN_PLAN_WORDS, st));
     int32_t* hub_off = (int32_t*)(base + L.hub_off);
     int64_t* run_pos_off = (int64_t*)(base + L.run_pos_off);
-    if (hub_degree == 0) {  // auto: share a row once about 1.5 links of the stream are expected to walk it
-        hub_degree = (3 * n + 2 * num_edges - 1) / (2 * num_edges);  // (measured optimum 64 at n/T = 45, flat from 32 to 128)
+    if (hub_degree == 0) {  // auto: share a row once about one link of the stream is expected to walk it
+        hub_degree = (n + num_edges - 1) / num_edges;  // (citation2 shape, n/T = 45: flat optimum between 24 and 64)
         if (hub_degree < 32) hub_degree = 32;
     }
     k_plan_edges<<<blocks, threads, 0, st>>>(rowptr, src, T, batch_size, rec_off, run_id);
