@@ -28,6 +28,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -39,6 +41,8 @@ constexpr int kHubThreads = 256;
 constexpr int kHubWarps = kHubThreads / 32;
 constexpr int kShortList = 4;       // entry lists up to this length are walked by their own lane
 constexpr int kMidList = 32;        // up to this length flattened over the lanes, longer ones by the whole warp
+constexpr int kHubWindow = 4096;      // positions a warp-private counter array holds (8 KB of packed counters per warp)
+constexpr int kHubCtaWindow = 32768;  // positions per pass of the CTA-per-item variant (64 KB of packed counters per CTA)
 static_assert(kHubSeg < 65536, "16-bit walk counters per item");
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -282,37 +286,54 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
     return v;
 }
 
-// U holds 16-bit counters packed in pairs
-__device__ __forceinline__ void count_walk(uint32_t* U, uint32_t pos) { atomicAdd(U + (pos >> 1), 1u << ((pos & 1u) << 4)); }
+// U holds 16-bit counters packed in pairs, for the positions [win_lo, win_lo + win_n) of this pass
+__device__ __forceinline__ void count_walk(uint32_t* U, uint32_t pos, uint32_t win_lo, uint32_t win_n) {
+    const uint32_t rel = pos - win_lo;
+    if (rel < win_n) atomicAdd(U + (rel >> 1), 1u << ((rel & 1u) << 4));
+}
 
 // ---- the walk through the shared rows ------------------------------------------------------------
-// One warp per item (row m, segment of its columns).  Entries of runs without a link next to m
-// only touch counters nobody reads; a column whose run signature misses every run of L_m is skipped.
-// Entry lists are walked by their own lane (<= kShortList entries), flattened over the lanes
-// (<= kMidList) or by the whole warp, so that neither the many short lists nor the few long ones
-// (54 % of the visits are in lists of > 32 entries at citation2 shape) leave lanes idle.
-__global__ void __launch_bounds__(kHubThreads, 6)
+// One warp (kCta == false: streams with up to kHubWindow positions, counters private to the warp) or one
+// CTA (kCta == true: more positions -- a hub source -- counters shared by the CTA's warps) per item
+// (row m, segment of its columns).  Entries of runs without a link next to m only touch counters
+// nobody reads; a column whose run signature misses every run of L_m is skipped.  Entry lists are
+// walked by their own lane (<= kShortList entries), flattened over the lanes (<= kMidList) or by the
+// whole warp, so that neither the many short lists nor the few long ones (54 % of the visits are in
+// lists of > 32 entries at citation2 shape) leave lanes idle.  Positions beyond the counter window are
+// handled by further passes over the items ([win_lo, win_lo + win_n) per launch).
+template <bool kCta>
+__global__ void __launch_bounds__(kHubThreads, kCta ? 3 : 6)
 k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint32_t* __restrict__ pkey,
                const int32_t* __restrict__ prun, const unsigned long long* __restrict__ prec, int64_t P,
                const uint32_t* __restrict__ eval, const uint4* __restrict__ node_index,
-               const int64_t* __restrict__ run_pos_off, int n_runs, int n_pos,
+               const int64_t* __restrict__ run_pos_off, int n_runs, uint32_t win_lo, uint32_t win_n,
                const uint2* __restrict__ items, int64_t max_items, unsigned long long* __restrict__ counters,
                Record* __restrict__ records) {
     extern __shared__ uint32_t hub_smem[];
+    __shared__ unsigned long long s_item;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nw = kCta ? kHubWarps : 1;   // warps sharing an item
+    const int wi = kCta ? warp : 0;        // this warp's index among them
     const int rpad = (n_runs + 1 + 3) & ~3;
-    const int uwords = (((n_pos + 1) >> 1) + 3) & ~3;   // packed 16-bit counters, a multiple of 4 words
-    uint32_t* s_pos = hub_smem;                          // run -> first position (n_runs + 1 entries)
-    uint32_t* U = hub_smem + rpad + (size_t)warp * uwords;
+    const int uwords = (int)((((win_n + 1) >> 1) + 3) & ~3u);   // packed 16-bit counters, a multiple of 4 words
+    uint32_t* s_pos = hub_smem;                                  // run -> first position (n_runs + 1 entries)
+    uint32_t* U = hub_smem + rpad + (kCta ? (size_t)0 : (size_t)warp * uwords);
     for (int r = threadIdx.x; r <= n_runs; r += blockDim.x) s_pos[r] = (uint32_t)run_pos_off[r];
     __syncthreads();
     unsigned long long n_items = counters[0];
     if (n_items > (unsigned long long)max_items) n_items = (unsigned long long)max_items;  // cannot happen with ocn_cn_hub_bytes
     unsigned* rec32 = reinterpret_cast<unsigned*>(records);
+    auto item_sync = [&]() { if (kCta) __syncthreads(); else __syncwarp(); };
     while (true) {
         unsigned long long it = 0;
-        if (lane == 0) it = atomicAdd(&counters[1], 1ull);
-        it = __shfl_sync(0xffffffffu, it, 0);
+        if (kCta) {
+            if (threadIdx.x == 0) s_item = atomicAdd(&counters[1], 1ull);
+            __syncthreads();
+            it = s_item;
+        } else {
+            if (lane == 0) it = atomicAdd(&counters[1], 1ull);
+            it = __shfl_sync(0xffffffffu, it, 0);
+        }
         if (it >= n_items) break;
         const uint2 item = items[it];
         const int64_t q0 = item.x;
@@ -332,22 +353,25 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
         }
         act_lo = __reduce_or_sync(0xffffffffu, act_lo);
         act_hi = __reduce_or_sync(0xffffffffu, act_hi);
-        for (int s = lane * 4; s < uwords; s += 128) *reinterpret_cast<uint4*>(U + s) = make_uint4(0u, 0u, 0u, 0u);
-        __syncwarp();
+        for (int s = (kCta ? threadIdx.x : lane) * 4; s < uwords; s += (kCta ? kHubThreads : 32) * 4)
+            *reinterpret_cast<uint4*>(U + s) = make_uint4(0u, 0u, 0u, 0u);
+        item_sync();
         const int64_t rs = rowptr[m];
         const int64_t d = rowptr[m + 1] - rs;
         const int64_t c0 = (int64_t)item.y * kHubSeg;
         const int64_t c1 = (c0 + kHubSeg < d) ? c0 + kHubSeg : d;
         // software pipeline: the column of step b+2 and the index entry of step b+1 are in flight while
         // the lists of step b are walked
+        const int64_t stride = 32 * nw;
         auto load_col = [&](int64_t bb) -> int32_t { return (bb + lane < c1) ? ldg_i32(col + rs + bb + lane) : -1; };
         auto load_entry = [&](int32_t l) -> uint4 { return l >= 0 ? __ldg(node_index + l) : make_uint4(0u, 0u, 0u, 0u); };
-        uint4 he_next = load_entry(load_col(c0));
-        int32_t col_next = load_col(c0 + 32);
-        for (int64_t b = c0; b < c1; b += 32) {
+        const int64_t b0 = c0 + 32 * wi;
+        uint4 he_next = load_entry(load_col(b0));
+        int32_t col_next = load_col(b0 + stride);
+        for (int64_t b = b0; b < c1; b += stride) {
             const uint4 he = he_next;
             he_next = load_entry(col_next);
-            col_next = load_col(b + 64);
+            col_next = load_col(b + 2 * stride);
             const int cnt = ((he.z & act_lo) | (he.w & act_hi)) ? (int)(he.y - he.x) : 0;
             if (!__any_sync(0xffffffffu, cnt != 0)) continue;
             const uint32_t* list = eval + he.x;
@@ -359,7 +383,7 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
                 for (int k = 0; k < kShortList; ++k) pos[k] = k < cs ? __ldg(list + k) : 0u;
 #pragma unroll
                 for (int k = 0; k < kShortList; ++k)
-                    if (k < cs) count_walk(U, pos[k]);
+                    if (k < cs) count_walk(U, pos[k], win_lo, win_n);
             }
             // middle lists: flattened over the lanes, 32 entries at a time
             const int cm = (cnt > kShortList && cnt <= kMidList) ? cnt : 0;
@@ -372,33 +396,46 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
                     const int s = owner_lane(excl, j);
                     const uint32_t ehead = __shfl_sync(0xffffffffu, he.x, s);
                     const int eexcl = __shfl_sync(0xffffffffu, excl, s);
-                    if (j < total) count_walk(U, __ldg(eval + ehead + (uint32_t)(j - eexcl)));
+                    if (j < total) count_walk(U, __ldg(eval + ehead + (uint32_t)(j - eexcl)), win_lo, win_n);
                 }
             }
-            // long lists: the whole warp per list
+            // long lists: the whole warp per list (ascending positions: only the window's piece is read when the
+            // stream needs several passes)
             unsigned lg = __ballot_sync(0xffffffffu, cnt > kMidList);
             while (lg) {
                 const int sl = __ffs(lg) - 1;
                 lg &= lg - 1;
-                const uint32_t ehead = __shfl_sync(0xffffffffu, he.x, sl);
-                const int n = __shfl_sync(0xffffffffu, cnt, sl);
-#pragma unroll 2
-                for (int e = lane; e < n; e += 32) count_walk(U, __ldg(eval + ehead + e));
+                uint32_t e0 = __shfl_sync(0xffffffffu, he.x, sl);
+                uint32_t e1 = __shfl_sync(0xffffffffu, he.y, sl);
+                if (win_lo > 0u) {  // first entry with position >= win_lo
+                    uint32_t lo = e0, hi = e1;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (__ldg(eval + mid) < win_lo) lo = mid + 1; else hi = mid;
+                    }
+                    e0 = lo;
+                }
+                for (uint32_t e = e0 + lane; e0 < e1; e0 += 32, e += 32) {
+                    const uint32_t pos = e < e1 ? __ldg(eval + e) : 0xffffffffu;
+                    count_walk(U, pos, win_lo, win_n);
+                    if (__any_sync(0xffffffffu, pos - win_lo >= win_n)) break;  // past the window (or the list)
+                }
             }
         }
-        __syncwarp();
+        item_sync();
         // hand the counts to the links next to m
-        for (int64_t q = 0; q < c; ++q) {
+        for (int64_t q = wi; q < c; q += nw) {
             const int r = prun[q0 + q];
-            const uint32_t pb = s_pos[r], np = s_pos[r + 1] - pb;
+            const uint32_t pb = s_pos[r], pe = s_pos[r + 1];
+            const uint32_t lo = pb > win_lo ? pb : win_lo, hi = pe < win_lo + win_n ? pe : win_lo + win_n;
             unsigned* rec = rec32 + 2 * prec[q0 + q] + 1;
-            for (uint32_t p = lane; p < np; p += 32) {
-                const uint32_t pos = pb + p;
-                const uint32_t u = (U[pos >> 1] >> ((pos & 1u) << 4)) & 0xffffu;
-                if (u) atomicAdd(rec + 2 * p, u);
+            for (uint32_t pos = lo + lane; pos < hi; pos += 32) {
+                const uint32_t rel = pos - win_lo;
+                const uint32_t u = (U[rel >> 1] >> ((rel & 1u) << 4)) & 0xffffu;
+                if (u) atomicAdd(rec + 2 * (pos - pb), u);
             }
         }
-        __syncwarp();
+        item_sync();
     }
 }
 
@@ -513,7 +550,7 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
     const int64_t NP = plan_host[OCN_PLAN_HUB_POSITIONS], R = plan_host[OCN_PLAN_NUM_RUNS];
     OCN_CHECK_ARG(hub_d > 0, "ocn_cn_build: the indexed path is off in this plan");
     OCN_CHECK_ARG(P < (int64_t(1) << 31) && E < (int64_t(1) << 31), "ocn_cn_build: indexed path limited to 2^31 pairs / entries");
-    OCN_CHECK_ARG(R <= kHubMaxRuns && NP <= kHubMaxPositions, "ocn_cn_build: indexed path with %lld runs, %lld positions",
+    OCN_CHECK_ARG(R <= kHubMaxRuns && NP < (int64_t(1) << 31), "ocn_cn_build: indexed path with %lld runs, %lld positions",
                   (long long)R, (long long)NP);
     if (NP <= 0 || E <= 0) return OCN_OK;  // no source has a neighbour: every record set is empty
     HubLayout H = hub_layout(n, nnz, P, E, NP);
@@ -594,18 +631,30 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
     // caller's stream: the walk through the shared rows (needs the pairs and the items)
     OCN_CUDA(cudaStreamWaitEvent(st, aux->ev[1], 0));
     if (P > 0) {
+        // positions are counted a window at a time: one pass of warp-per-item for the usual stream; a stream with
+        // more positions (a hub source) uses the CTA-per-item variant with a CTA-wide window
+        int64_t warp_win = kHubWindow, cta_win = kHubCtaWindow;
+        if (const char* v = getenv("OCN_HUB_WINDOW")) warp_win = atoll(v) > 0 ? atoll(v) : warp_win;        // test hooks
+        if (const char* v = getenv("OCN_HUB_CTA_WINDOW")) cta_win = atoll(v) > 0 ? atoll(v) : cta_win;
+        const bool cta = NP > warp_win;
+        const int64_t win = cta ? (NP < cta_win ? NP : cta_win) : NP;
         const int rpad = (int)((R + 1 + 3) & ~int64_t(3));
-        const int uwords = (int)((((NP + 1) >> 1) + 3) & ~int64_t(3));
-        const size_t smem = sizeof(uint32_t) * ((size_t)rpad + (size_t)uwords * kHubWarps);
-        OCN_CUDA(cudaFuncSetAttribute(k_cn_hub_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int uwords = (int)((((win + 1) >> 1) + 3) & ~int64_t(3));
+        const size_t smem = sizeof(uint32_t) * ((size_t)rpad + (size_t)uwords * (cta ? 1 : kHubWarps));
+        auto kern = cta ? k_cn_hub_count<true> : k_cn_hub_count<false>;
+        OCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = (int)((200u * 1024u) / smem);
-        if (per_sm > 8) per_sm = 8;
+        if (per_sm > (cta ? 3 : 8)) per_sm = cta ? 3 : 8;
         if (per_sm < 1) per_sm = 1;
         hub_timing_record(0, st);
-        k_cn_hub_count<<<sm_count() * per_sm, kHubThreads, smem, st>>>(
-            rowptr, col, dk.Current(), prun, prec, P, ev.Current(), node_index, run_pos_off, (int)R, (int)NP, items,
-            H.max_items, counters, records);
-        OCN_LAUNCH_CHECK();
+        for (int64_t w0 = 0; w0 < NP; w0 += win) {
+            if (w0 > 0) OCN_CUDA(cudaMemsetAsync(counters + 1, 0, sizeof(unsigned long long), st));  // restart the item counter
+            const int64_t wn = (NP - w0) < win ? (NP - w0) : win;
+            kern<<<sm_count() * per_sm, kHubThreads, smem, st>>>(
+                rowptr, col, dk.Current(), prun, prec, P, ev.Current(), node_index, run_pos_off, (int)R, (uint32_t)w0,
+                (uint32_t)wn, items, H.max_items, counters, records);
+            OCN_LAUNCH_CHECK();
+        }
         hub_timing_record(1, st);
     }
     if (timed_alone) {

@@ -24,6 +24,9 @@ PlanLayout plan_layout(int64_t T) {
     L.partial = off;       off += align16(sizeof(float) * 3 * (T + 1));
     L.hub_off = off;       off += align16(sizeof(int32_t) * (T + 2));
     L.run_pos_off = off;   off += align16(sizeof(int64_t) * (T + 2));
+    L.run_pos_heavy = off; off += align16(sizeof(int64_t) * (T + 2));
+    L.pos_start = off;     off += align16(sizeof(int64_t) * (T + 2));
+    L.pos_scanN = off;     off += align16(sizeof(int64_t) * (T + 2));
     L.chunk_off = off;     off += align16(sizeof(int32_t) * (T + 2));
     L.long_list = off;     off += align16(sizeof(int32_t) * (T + 2));
     size_t b1 = 0, b2 = 0, b3 = 0;
@@ -154,10 +157,10 @@ k_plan_cost_long(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
     }
 }
 
-// the indexed path (cn_hub.cu) is used for order 3 when the runs and positions of the stream fit its
-// per-warp shared-memory counters
+// the indexed path (cn_hub.cu) is used for order 3 when the stream has few runs (its run -> position table
+// lives in shared memory, and its index holds one entry per (position, neighbour of the position's node))
 __global__ void k_plan_hub_decide(int order, int64_t hub_degree, int64_t* __restrict__ plan) {
-    const bool fits = plan[OCN_PLAN_NUM_RUNS] <= kHubMaxRuns && plan[OCN_PLAN_HUB_POSITIONS] <= kHubMaxPositions;
+    const bool fits = plan[OCN_PLAN_NUM_RUNS] <= kHubMaxRuns;
     plan[OCN_PLAN_HUB_DEGREE] = (order >= 3 && hub_degree > 0 && fits) ? hub_degree : 0;
 }
 
@@ -166,7 +169,7 @@ __global__ void k_plan_units(const int64_t* __restrict__ rowptr, const int32_t* 
                              const int64_t* __restrict__ src, int64_t T, const int32_t* __restrict__ run_start,
                              const int64_t* __restrict__ cost_pre, int resident_ctas,
                              int64_t* __restrict__ plan, int64_t* __restrict__ run_units,
-                             int64_t* __restrict__ run_pos) {
+                             int64_t* __restrict__ run_pos_light, int64_t* __restrict__ run_pos_heavy) {
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r > T + 1) return;
@@ -199,13 +202,36 @@ __global__ void k_plan_units(const int64_t* __restrict__ rowptr, const int32_t* 
     }
     if (lane == 0) {
         run_units[r] = u;
-        run_pos[r] = npos;
+        // positions of the stream: the runs of light sources first, those of heavy sources (long rows N(src)) last,
+        // so that the entry lists of the index end with the heavy sources' entries (cn_hub.cu)
+        const bool heavy = npos > kHeavyRun;
+        run_pos_light[r] = heavy ? 0 : npos;
+        run_pos_heavy[r] = heavy ? npos : 0;
+    }
+}
+
+// after the two run-level scans: origin[r] = first position of run r in run order (ascending in r),
+// start[r] = first position of run r in the stream's position numbering (light runs first, heavy runs last)
+__global__ void k_plan_positions(const int64_t* __restrict__ plan, const int64_t* __restrict__ scan_light,
+                                 const int64_t* __restrict__ scan_heavy, int64_t* __restrict__ origin,
+                                 int64_t* __restrict__ start) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n_runs = plan[OCN_PLAN_NUM_RUNS];
+    if (r > n_runs) return;
+    const int64_t total_light = scan_light[n_runs];
+    origin[r] = scan_light[r] + scan_heavy[r];
+    if (r < n_runs) {
+        const bool heavy = scan_heavy[r + 1] != scan_heavy[r];
+        start[r] = heavy ? total_light + scan_heavy[r] : scan_light[r];
+    } else {
+        start[r] = total_light + scan_heavy[r];
     }
 }
 
 __global__ void k_plan_finish(int64_t T, int64_t batch_size, int resident_ctas, const int64_t* __restrict__ rec_off,
                               const int64_t* __restrict__ run_unit_off, const int32_t* __restrict__ hub_off,
-                              const int64_t* __restrict__ run_pos_off, int64_t* __restrict__ plan) {
+                              const int64_t* __restrict__ run_pos_off, const int64_t* __restrict__ run_pos_heavy_off,
+                              int64_t* __restrict__ plan) {
     plan[OCN_PLAN_NUM_RECORDS] = rec_off[T];
     plan[OCN_PLAN_NUM_UNITS] = run_unit_off[plan[OCN_PLAN_NUM_RUNS]];
     plan[OCN_PLAN_NUM_BATCHES] = (T + batch_size - 1) / batch_size;
@@ -214,7 +240,8 @@ __global__ void k_plan_finish(int64_t T, int64_t batch_size, int resident_ctas, 
     // orders <= 2: the table pays off only when several links share it (runs of >= 3 links on average)
     plan[OCN_PLAN_USE_DIRECT] = (T <= 3 * plan[OCN_PLAN_NUM_RUNS]) ? 1 : 0;
     plan[OCN_PLAN_HUB_PAIRS] = hub_off[T];
-    plan[OCN_PLAN_HUB_POSITIONS] = run_pos_off[plan[OCN_PLAN_NUM_RUNS]];  // 0 when the indexed path is off
+    const int64_t n_runs = plan[OCN_PLAN_NUM_RUNS];
+    plan[OCN_PLAN_HUB_POSITIONS] = run_pos_off[n_runs] + run_pos_heavy_off[n_runs];  // 0 when the indexed path is off
 }
 
 }  // namespace ocn
@@ -258,6 +285,9 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
     OCN_CUDA(cudaMemsetAsync(out_plan, 0, sizeof(int64_t) * OCN_PLAN_WORDS, st));
     int32_t* hub_off = (int32_t*)(base + L.hub_off);
     int64_t* run_pos_off = (int64_t*)(base + L.run_pos_off);
+    int64_t* run_pos_heavy = (int64_t*)(base + L.run_pos_heavy);
+    int64_t* pos_start = (int64_t*)(base + L.pos_start);
+    int64_t* pos_scanN = (int64_t*)(base + L.pos_scanN);
     if (hub_degree == 0) {  // auto: share a row once about one link of the stream is expected to walk it
         hub_degree = (n + num_edges - 1) / num_edges;  // (citation2 shape, n/T = 45: flat optimum between 24 and 64)
         if (hub_degree < 32) hub_degree = 32;
@@ -284,11 +314,15 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, chunk_off, chunk_off, (int)(T + 1), st));
     int blocks2 = (int)(((T + 2) * 32 + threads - 1) / threads);
     k_plan_units<<<blocks2, threads, 0, st>>>(rowptr, col, src, T, run_start, cost_pre, resident_ctas, out_plan,
-                                              run_unit_off, run_pos_off);
+                                              run_unit_off, pos_scanN, run_pos_heavy);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, run_unit_off, run_unit_off, (int)(T + 2), st));
-    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, run_pos_off, run_pos_off, (int)(T + 2), st));
-    k_plan_finish<<<1, 1, 0, st>>>(T, batch_size, resident_ctas, rec_off, run_unit_off, hub_off, run_pos_off, out_plan);
+    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pos_scanN, pos_scanN, (int)(T + 2), st));
+    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, run_pos_heavy, run_pos_heavy, (int)(T + 2), st));
+    k_plan_positions<<<(int)((T + 2 + threads - 1) / threads), threads, 0, st>>>(out_plan, pos_scanN, run_pos_heavy, run_pos_off,
+                                                                                pos_start);
+    OCN_LAUNCH_CHECK();
+    k_plan_finish<<<1, 1, 0, st>>>(T, batch_size, resident_ctas, rec_off, run_unit_off, hub_off, pos_scanN, run_pos_heavy, out_plan);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
 }

@@ -57,7 +57,10 @@ struct PlanLayout {
     size_t cost_pre;       // int64[T+2]  exclusive prefix of the per-link walk cost
     size_t partial;        // float[3*T]
     size_t hub_off;        // int32[T+2]  exclusive prefix of the per-link number of hub rows in N(dst)
-    size_t run_pos_off;    // int64[T+2]  exclusive prefix of deg(src) over the runs (hub stage positions)
+    size_t run_pos_off;    // int64[T+2]  exclusive prefix of deg(src) over the runs, in run order (ascending)
+    size_t run_pos_heavy;  // int64[T+2]  the same prefix over the heavy runs only
+    size_t pos_start;      // int64[T+2]  first position of every run in the index numbering (light runs first, heavy last)
+    size_t pos_scanN;      // int64[T+2]  the prefix over the light runs only
     size_t chunk_off;      // int32[T+2]  exclusive prefix of ceil(deg(dst)/32) (items of the per-link kernel)
     size_t long_list;      // int32[T+2]  links whose destination has more than kLongRow neighbours
     size_t cub_temp;       // bytes
@@ -106,9 +109,9 @@ constexpr int kLinkCost = 64;  // fixed cost added to every link so that empty l
 #define OCN_PLAN_TOTAL_COST 6
 #define OCN_PLAN_USE_DIRECT 7  /* orders <= 2 only: 1 = table-free kernel (short runs), 0 = table kernel */
 #define OCN_PLAN_LONG_COUNT 12 /* entries of the long-destination list */
+constexpr int kHeavyRun = 64;      // a run whose source has more neighbours than this is "heavy": its positions are numbered last
 constexpr int kLongRow = 256;      // neighbours of dst a single warp walks in the plan / pair kernels; the rest goes to a CTA
 constexpr int kHubMaxRuns = 2048;       // indexed path: run -> first position table in shared memory
-constexpr int kHubMaxPositions = 8192;  // indexed path: warp-private 16-bit counters per position (16 KB per warp)
 
 // ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
