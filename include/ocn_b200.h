@@ -50,6 +50,36 @@ int ocn_device_sm_count(void);
 int ocn_graph_validate(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t nnz,
                        int32_t* out_flags, void* stream);
 
+/* ---- the step before the path: building / masking the adjacency on the device ----
+ * SparseTensor.from_edge_index(tei, sparse_sizes=(n, n))[.to_symmetric()] (ogbdataset.py:44-45,
+ * NeighborOverlap_large.py:56-63, NeighborOverlapCitation2.py:135-143): edge list (int64 src/dst, optional
+ * keep mask uint8[num_edges] = the reference's `adjmask`) -> CSR with ascending duplicate-free rows.
+ * count: fills out_rowptr[n+1]; out_info[0] = nnz, out_info[1] = kept edges with an endpoint outside [0, n)
+ * (they are dropped; the host mirror raises).  The caller reads nnz, allocates col int32[nnz] (and
+ * optionally mult int32[nnz]: how many list edges map onto each entry) and calls fill with the same scratch. */
+size_t ocn_graph_build_bytes(int64_t num_edges, int symmetric);
+int ocn_graph_build_count(const int64_t* src, const int64_t* dst, const uint8_t* keep, int64_t num_edges,
+                          int64_t n, int symmetric, void* scratch, size_t scratch_bytes,
+                          int64_t* out_rowptr, int64_t* out_info, void* stream);
+int ocn_graph_build_fill(const void* scratch, int64_t num_edges, int symmetric, int64_t n, int64_t nnz,
+                         int32_t* out_col, int32_t* out_mult, void* stream);
+
+/* Per-batch target-link masking under --maskinput (NeighborOverlap_large.py:56-63: adjmask[perm] = 0, rebuild,
+ * to_symmetric) WITHOUT re-sorting the edge list: (rowptr, col, mult) is the full graph from ocn_graph_build_*
+ * (mult NULL = every entry comes from exactly one list edge), (src, dst)[num_masked] the masked links.  An
+ * entry survives while an unmasked list edge still maps onto it -- the result equals a rebuild from the
+ * remaining list.  dec is an int32[nnz] work array, all zero on entry and on return of fill.
+ * count: out_rowptr[n+1] of the masked graph, out_info[0] = its nnz, out_info[1] = masked links not found in
+ * the graph; fill: out_col int32[nnz'] (and out_mult).  fill must follow count (it restores dec). */
+size_t ocn_graph_mask_bytes(int64_t n);
+int ocn_graph_mask_count(const int64_t* rowptr, const int32_t* col, const int32_t* mult, int64_t n,
+                         const int64_t* src, const int64_t* dst, int64_t num_masked, int symmetric,
+                         int32_t* dec, void* scratch, size_t scratch_bytes,
+                         int64_t* out_rowptr, int64_t* out_info, void* stream);
+int ocn_graph_mask_fill(const int64_t* rowptr, const int32_t* col, const int32_t* mult, int64_t n,
+                        const int64_t* src, const int64_t* dst, int64_t num_masked, int symmetric,
+                        int32_t* dec, const int64_t* out_rowptr, int32_t* out_col, int32_t* out_mult, void* stream);
+
 /* ---- piece 1: generic per-target-edge row intersection ----------------------------------
  * adjoverlap(adj1, adj2, tarei) with calresadj=False (utils.py:248-285 -> spmoverlap_
  * utils.py:163-183): out row b = adj1[src[b]] (cap) adj2[dst[b]], columns ascending, value 1.
@@ -190,6 +220,10 @@ int ocn_spmm_csr(const int64_t* rowptr, const int32_t* col, const float* val, in
 /* grad_x[col] += val * grad_out[row]  (transpose SpMM by scatter; reduce sum/mean only) */
 int ocn_spmm_csr_bwd(const int64_t* rowptr, const int32_t* col, const float* val, int64_t num_rows,
                      const float* grad_out, int64_t feat, int reduce, float* grad_x, void* stream);
+/* spmm_max backward (PureConv aggr="max", model.py:47): grad_x[argmax col of (row, f)] += val * grad_out[row, f];
+ * the first maximum in row order wins, as in torch_sparse's running strict comparison; x is the forward input */
+int ocn_spmm_csr_max_bwd(const int64_t* rowptr, const int32_t* col, const float* val, int64_t num_rows,
+                         const float* x, const float* grad_out, int64_t feat, float* grad_x, void* stream);
 
 /* GCN-style aggregation fused with its degree normalisation.
  * mode 3: PureConv "gcn" (model.py:51-54)   out = nrm * (A (nrm*x) + nrm*x), nrm = rsqrt(1 + rowsum)
@@ -212,6 +246,18 @@ int ocn_spgemm_a2_symbolic(const int64_t* rowptr, const int32_t* col, int64_t n,
 int ocn_spgemm_a2_numeric(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t fold,
                           void* scratch, const int64_t* out_rowptr, int32_t* out_col, float* out_val,
                           void* stream);
+
+/* ---- the step after the path: ranking metrics on the device --------------------------
+ * ogb Evaluator.eval as the drivers call it (NeighborOverlap_large.py:162-179: Hits@K over all positive /
+ * negative scores of a split; NeighborOverlapCitation2.py:256-259: MRR of every source against its own
+ * 1000 negatives), so that scores stay on the device.
+ * ocn_mrr: out_mrr[b] = 1 / (0.5 * (#{neg[b,:] > pos[b]} + #{neg[b,:] >= pos[b]}) + 1)   (ogb >= 1.3.3)
+ * ocn_hits_at_k: out_hits[0] = mean(pos > k-th largest neg), 1.0 when num_neg < k. */
+int ocn_mrr(const float* pos, const float* neg, int64_t num_sources, int64_t negs_per_source,
+            float* out_mrr, void* stream);
+size_t ocn_hits_bytes(int64_t num_neg);
+int ocn_hits_at_k(const float* pos, int64_t num_pos, const float* neg, int64_t num_neg, int64_t k,
+                  void* scratch, size_t scratch_bytes, float* out_hits, void* stream);
 
 #ifdef __cplusplus
 }

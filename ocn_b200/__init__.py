@@ -9,6 +9,7 @@ from .cn import CNSession, SparseRows, adjoverlap, cn_aggregate_eval, get_cn, ge
 from .sparse_ops import (gcn_norm, gcnconv_propagate, pure_conv, pure_conv3_gcn, sparse_tensor_multiply,  # noqa: F401
                          spgemm_a2, spmm, spmm_add, spmm_max, spmm_mean)
 from . import ops  # noqa: F401  (registers torch.ops.ocn.*)
+from . import dist, metrics  # noqa: F401
 from .predictor import (CNLinkPredictor3hopCNs, CNLinkPredictorbaselearn, CNLinkPredictorOringin,  # noqa: F401
                         predictor_dict)
 

@@ -19,6 +19,12 @@ _SIGS = {
     "ocn_last_error": (ctypes.c_char_p, []),
     "ocn_device_sm_count": (c_int, []),
     "ocn_graph_validate": (c_int, [_P, _P, c_int64, c_int64, _P, _P]),
+    "ocn_graph_build_bytes": (c_size_t, [c_int64, c_int]),
+    "ocn_graph_build_count": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, c_size_t, _P, _P, _P]),
+    "ocn_graph_build_fill": (c_int, [_P, c_int64, c_int, c_int64, c_int64, _P, _P, _P]),
+    "ocn_graph_mask_bytes": (c_size_t, [c_int64]),
+    "ocn_graph_mask_count": (c_int, [_P, _P, _P, c_int64, _P, _P, c_int64, c_int, _P, _P, c_size_t, _P, _P, _P]),
+    "ocn_graph_mask_fill": (c_int, [_P, _P, _P, c_int64, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P]),
     "ocn_rows_intersect_count": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, _P, _P]),
     "ocn_rows_intersect_fill": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P]),
     "ocn_cn_plan_bytes": (c_size_t, [c_int64]),
@@ -41,11 +47,15 @@ _SIGS = {
     "ocn_cn_release": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, _P, _P, _P, _P]),
     "ocn_spmm_csr": (c_int, [_P, _P, _P, c_int64, _P, c_int64, c_int, _P, _P]),
     "ocn_spmm_csr_bwd": (c_int, [_P, _P, _P, c_int64, _P, c_int64, c_int, _P, _P]),
+    "ocn_spmm_csr_max_bwd": (c_int, [_P, _P, _P, c_int64, _P, _P, c_int64, _P, _P]),
     "ocn_gcn_norm": (c_int, [_P, _P, c_int64, _P, _P]),
     "ocn_gcn_spmm": (c_int, [_P, _P, _P, c_int64, _P, c_int, _P, c_int64, _P, _P]),
     "ocn_spgemm_scratch_bytes": (c_size_t, [c_int64]),
     "ocn_spgemm_a2_symbolic": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P]),
     "ocn_spgemm_a2_numeric": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "ocn_mrr": (c_int, [_P, _P, c_int64, c_int64, _P, _P]),
+    "ocn_hits_bytes": (c_size_t, [c_int64]),
+    "ocn_hits_at_k": (c_int, [_P, c_int64, _P, c_int64, c_int64, _P, c_size_t, _P, _P]),
 }
 
 _lib = None

@@ -147,6 +147,32 @@ __global__ void k_spmm_bwd(const int64_t* __restrict__ rowptr, const int32_t* __
     }
 }
 
+// spmm_max backward: the gradient of out[r, f] goes to the FIRST column (in row order) that attains the
+// maximum (torch_sparse keeps the first arg-max: its running comparison is a strict ">"); empty rows
+// receive nothing.  One warp per row, lanes over the features; the forward value is recomputed.
+__global__ void k_spmm_max_bwd(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                               const float* __restrict__ val, int64_t num_rows, const float* __restrict__ x,
+                               const float* __restrict__ g, int64_t F, float* __restrict__ grad_x) {
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    for (int64_t r = warp; r < num_rows; r += nwarps) {
+        const int64_t s = rowptr[r], e = rowptr[r + 1];
+        if (e == s) continue;
+        for (int64_t f = lane; f < F; f += 32) {
+            float best = -FLT_MAX;
+            int64_t arg = s;
+            for (int64_t o = s; o < e; ++o) {
+                const float w = val ? __ldg(val + o) : 1.0f;
+                const float v = w * __ldg(x + (int64_t)ldg_i32(col + o) * F + f);
+                if (v > best) { best = v; arg = o; }
+            }
+            const float w = val ? __ldg(val + arg) : 1.0f;
+            atomicAdd(grad_x + (int64_t)ldg_i32(col + arg) * F + f, w * g[r * F + f]);
+        }
+    }
+}
+
 __global__ void k_gcn_norm(const int64_t* __restrict__ rowptr, const float* __restrict__ ew, int64_t n,
                            float* __restrict__ out) {
     int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -212,6 +238,19 @@ int ocn_spmm_csr_bwd(const int64_t* rowptr, const int32_t* col, const float* val
     int64_t cap = (int64_t)sm_count() * 16;
     const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
     k_spmm_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, col, val, num_rows, grad_out, feat, reduce, grad_x);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+int ocn_spmm_csr_max_bwd(const int64_t* rowptr, const int32_t* col, const float* val, int64_t num_rows, const float* x,
+                         const float* grad_out, int64_t feat, float* grad_x, void* stream) {
+    OCN_CHECK_ARG(rowptr && x && grad_out && grad_x, "ocn_spmm_csr_max_bwd: null pointer");
+    OCN_CHECK_ARG(num_rows >= 0 && feat > 0, "ocn_spmm_csr_max_bwd: bad sizes");
+    if (num_rows == 0) return OCN_OK;
+    int64_t want = (num_rows + 7) / 8;
+    int64_t cap = (int64_t)sm_count() * 16;
+    const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    k_spmm_max_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, col, val, num_rows, x, grad_out, feat, grad_x);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
 }

@@ -5,7 +5,7 @@ to rank t mod world -- and every rank runs the full fused path on its batches.  
 The only collective is the gather of fp32 scores."""
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import Iterable, List, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -24,6 +24,120 @@ def gather_scores(local_scores: Sequence[torch.Tensor], owned: Sequence[Tuple[in
     full = torch.zeros(num_links, dtype=torch.float32, device=dev)
     for sc, (s, e) in zip(local_scores, owned):
         full[s:e] = sc.reshape(-1).float()
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(full, op=dist.ReduceOp.SUM)  # disjoint supports: a sum is a gather in link order
+    _all_reduce_sum(full)  # disjoint supports: a sum is a gather in link order
     return full
+
+
+# ---- training step ---------------------------------------------------------------
+# NeighborOverlapCitation2.py:131-209: one optimiser step = the positive sub-batches then the negative
+# sub-batches of one permutation batch (16 384 links in sub-batches of 2048), every sub-batch calling
+# backward() on its share of the loss, gradients accumulating until optimizer.step().  The sub-batches are
+# independent given (A, h, weights) EXCEPT for cn5's running mean of inner products, which every training
+# forward updates (model.py:2241-2250): sub-batch u uses ip_u = mean(s_1 .. s_u).  s_u depends only on the
+# CN sets and column sums of sub-batch u, so the ranks compute their s_u first, exchange the scalars,
+# replay the running mean in sequence order and only then run the weighted aggregation -- one scalar
+# exchange plus the gradient all-reduce per step, results independent of the world size.
+
+def _world() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _all_reduce_sum(t: torch.Tensor) -> None:
+    """In-place sum over the ranks: NCCL on device memory; the gloo backend (CPU tests, or two ranks sharing one
+    GPU in the parity test) goes through a host copy."""
+    if _world() <= 1:
+        return
+    if t.is_cuda and dist.get_backend() == "gloo":
+        c = t.cpu()
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        t.copy_(c)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+def exchange_batch_scalars(local: torch.Tensor, owned_ids: Sequence[int], num_batches: int) -> torch.Tensor:
+    """``local[k]`` is the scalar of sub-batch ``owned_ids[k]``; returns all ``num_batches`` scalars in
+    sequence order on every rank (disjoint supports: the sum is a gather)."""
+    full = torch.zeros(num_batches, dtype=torch.float32, device=local.device)
+    if len(owned_ids):
+        full[torch.as_tensor(list(owned_ids), device=local.device, dtype=torch.long)] = local.float().reshape(-1)
+    _all_reduce_sum(full)
+    return full
+
+
+def replay_running_mean(s_all: torch.Tensor, ip0: torch.Tensor, n0: int) -> Tuple[torch.Tensor, int]:
+    """``innerprod1`` in training mode (model.py:2245-2248) replayed over the sub-batches in sequence:
+    n += 1; ip = ip * (1 - 1/n) + s / n, in fp32 exactly as the module does it.  Returns the coefficient every
+    sub-batch sees (``[num_batches]``; the last one is the buffer's value after the step) and the final n."""
+    ip = ip0.detach().float().reshape(-1)[:1].clone()
+    out = torch.empty(s_all.numel(), dtype=torch.float32, device=s_all.device)
+    n = int(n0)
+    for u in range(s_all.numel()):
+        n += 1
+        beta = n ** -1
+        ip *= (1 - beta)
+        ip += beta * s_all[u]
+        out[u] = ip[0]
+    return out, n
+
+
+def allreduce_gradients(tensors: Iterable[torch.Tensor]) -> None:
+    """Sum the gradients of ``tensors`` (parameters, or leaves such as the detached ``h`` of
+    NeighborOverlapCitation2.py:155) over the ranks in ONE flat bucket.  The reference scales every sub-batch
+    loss by 1/len(step) before backward (:177, :200), so the plain sum is the step's gradient; tensors without
+    a gradient on this rank contribute zeros (and receive the sum)."""
+    ts = [t for t in tensors if t.requires_grad]
+    if _world() <= 1 or not ts:
+        return
+    for t in ts:
+        if t.grad is None:
+            t.grad = torch.zeros_like(t)
+    flat = torch.cat([t.grad.reshape(-1).float() for t in ts])
+    _all_reduce_sum(flat)
+    o = 0
+    for t in ts:
+        k = t.numel()
+        t.grad.copy_(flat[o:o + k].view_as(t.grad))
+        o += k
+
+
+def sharded_train_step(pred, h: torch.Tensor, graph, sub_batches: Sequence[torch.Tensor], signs: Sequence[float],
+                       total_len: int, rank: int, world: int, fill: float = 0.0, args=None):
+    """The predictor part of one optimiser step of the citation2 / ppa drivers with its sub-batches dealt to
+    ranks (sub-batch u -> rank u mod world).  ``sub_batches[u]`` is ``[2, b]`` links, ``signs[u]`` is +1 for a
+    positive and -1 for a negative sub-batch (loss = -(1/total_len) * sum(logsigmoid(sign * out)),
+    NeighborOverlapCitation2.py:177,200).  ``h`` is the detached node embedding with requires_grad.  After the
+    call every rank holds the summed gradients of the predictor parameters and of ``h``, and the predictor's
+    inner-product buffer / counter in the state the sequential loop leaves them in.  Returns the step loss."""
+    import torch.nn.functional as F
+    from .cn import CNSession
+    U = len(sub_batches)
+    mine = list(range(rank, U, world))
+    ocn5 = getattr(pred, "variant", 5) == 5
+    sess, s_local = {}, []
+    for u in mine:  # phase 1: CN sets + column statistics of the owned sub-batches, their inner products
+        sess[u] = CNSession(graph, sub_batches[u], None, pred.order).build(pred.order, pred.weighted)
+        if ocn5:
+            s_local.append(pred.batch_inner_product(sess[u], fill))
+    dev = h.device
+    if ocn5:  # phase 2: one scalar exchange, running mean replayed in sequence order
+        s_all = exchange_batch_scalars(torch.stack(s_local) if s_local else torch.zeros(0, device=dev), mine, U)
+        ips, n_end = replay_running_mean(s_all, pred.innerprod, pred.n)
+    loss = torch.zeros((), device=dev)
+    for u in mine:  # phase 3: weighted aggregation, heads, loss, backward
+        e = sub_batches[u]
+        if ocn5:
+            xcn1, xcn2, xcn3, xij, _ = pred.cn_stage(h, graph, e, fill, sess[u], ip=ips[u:u + 1])
+        else:
+            xcn1, xcn2, xcn3, xij, _ = pred.cn_stage(h, graph, e, fill, sess[u])
+        out = pred._head(xcn1, xcn2, xcn3, xij)
+        l = -(1.0 / total_len) * F.logsigmoid(signs[u] * out).sum()
+        l.backward()
+        loss += l.detach()
+    if ocn5:
+        with torch.no_grad():
+            pred.innerprod.copy_(ips[-1:].to(pred.innerprod.dtype))
+        pred.n = n_end
+    allreduce_gradients(list(pred.parameters()) + [h])  # phase 4
+    _all_reduce_sum(loss)
+    return loss

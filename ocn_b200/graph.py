@@ -19,7 +19,7 @@ class Graph:
     """
 
     def __init__(self, rowptr: Tensor, col: Tensor, n: Optional[int] = None, value: Optional[Tensor] = None,
-                 n_cols: Optional[int] = None):
+                 n_cols: Optional[int] = None, mult: Optional[Tensor] = None):
         if rowptr.dtype != torch.int64:
             rowptr = rowptr.to(torch.int64)
         if col.dtype != torch.int32:
@@ -31,13 +31,22 @@ class Graph:
         self.value = None if value is None else value.to(torch.float32).contiguous()
         if self.rowptr.numel() != self.n + 1:
             raise ValueError(f"rowptr has {self.rowptr.numel()} entries, expected n+1 = {self.n + 1}")
+        self.mult = mult  # int32[nnz]: list edges per entry (from_edge_index(..., with_multiplicity=True)); for masked()
         self._ws = {}
 
     # -- construction ------------------------------------------------------------------------
     @staticmethod
-    def from_edge_index(edge_index: Tensor, n: int, symmetric: bool = True) -> "Graph":
-        """Sort by (row, col), drop duplicates (and, like to_symmetric(), union both directions)."""
+    def from_edge_index(edge_index: Tensor, n: int, symmetric: bool = True, keep: Optional[Tensor] = None,
+                        with_multiplicity: bool = False) -> "Graph":
+        """Sort by (row, col), drop duplicates (and, like to_symmetric(), union both directions).
+        ``keep`` is the reference's ``adjmask`` (bool [E]).  CUDA edge lists go through ``ocn_graph_build_*``
+        (one radix sort + run-length encode in libocn_b200); a CPU edge list is only host-side data
+        preparation (synthetic generators, tests) and yields a host graph no op accepts until it is moved."""
+        if edge_index.is_cuda:
+            return _build_on_device(edge_index, n, symmetric, keep, with_multiplicity)
         src, dst = edge_index[0].to(torch.int64), edge_index[1].to(torch.int64)
+        if keep is not None:
+            src, dst = src[keep], dst[keep]
         if symmetric:
             src, dst = torch.cat((src, dst)), torch.cat((dst, src))
         key = torch.unique(src * n + dst)
@@ -47,9 +56,45 @@ class Graph:
         torch.cumsum(torch.bincount(row, minlength=n), 0, out=rowptr[1:])
         return Graph(rowptr, col, n)
 
+    def masked(self, links: Tensor, symmetric: bool = True) -> "Graph":
+        """The adjacency of one --maskinput training batch (NeighborOverlap_large.py:56-63): this graph rebuilt
+        without the list edges ``links`` [2, M] -- by decrementing entry multiplicities and compacting the rows
+        (``ocn_graph_mask_*``), not by re-sorting the edge list."""
+        _require_cuda(self.col)
+        _require_cuda(links)
+        L = _lib.lib()
+        dev = self.device
+        src, dst = links[0].to(torch.int64).contiguous(), links[1].to(torch.int64).contiguous()
+        M = int(src.numel())
+        dec = self._ws.get("mask_dec")
+        if dec is None:
+            dec = torch.zeros(max(1, self.nnz), dtype=torch.int32, device=dev)
+            self._ws["mask_dec"] = dec
+        nb = L.ocn_graph_mask_bytes(self.n)
+        scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+        rowptr = torch.empty(self.n + 1, dtype=torch.int64, device=dev)
+        info = torch.zeros(2, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(L.ocn_graph_mask_count(_lib.ptr(self.rowptr), _lib.ptr(self.col), _lib.ptr(self.mult), self.n,
+                                              _lib.ptr(src), _lib.ptr(dst), M, int(symmetric), _lib.ptr(dec),
+                                              _lib.ptr(scratch), nb, _lib.ptr(rowptr), _lib.ptr(info), st),
+                       "ocn_graph_mask_count")
+            nnz, missing = info.tolist()
+            col = torch.empty(nnz, dtype=torch.int32, device=dev)
+            mult = torch.empty(nnz, dtype=torch.int32, device=dev) if self.mult is not None else None
+            _lib.check(L.ocn_graph_mask_fill(_lib.ptr(self.rowptr), _lib.ptr(self.col), _lib.ptr(self.mult), self.n,
+                                             _lib.ptr(src), _lib.ptr(dst), M, int(symmetric), _lib.ptr(dec),
+                                             _lib.ptr(rowptr), _lib.ptr(col) if nnz else None, _lib.ptr(mult), st),
+                       "ocn_graph_mask_fill")
+        if missing:
+            raise ValueError(f"{missing} masked links are not edges of this graph")
+        return Graph(rowptr, col, self.n, None, self.n_cols, mult)
+
     def to(self, device) -> "Graph":
         return Graph(self.rowptr.to(device), self.col.to(device), self.n,
-                     None if self.value is None else self.value.to(device), self.n_cols)
+                     None if self.value is None else self.value.to(device), self.n_cols,
+                     None if self.mult is None else self.mult.to(device))
 
     # -- accessors mirroring what the reference reads ------------------------------------------
     @property
@@ -86,6 +131,34 @@ class Graph:
             _lib.check(_lib.lib().ocn_graph_validate(_lib.ptr(self.rowptr), _lib.ptr(self.col), self.n, self.nnz,
                                                      _lib.ptr(flags), st), "ocn_graph_validate")
         return int(flags.item())
+
+
+def _build_on_device(edge_index: Tensor, n: int, symmetric: bool, keep: Optional[Tensor], with_mult: bool) -> Graph:
+    L = _lib.lib()
+    dev = edge_index.device
+    src, dst = edge_index[0].to(torch.int64).contiguous(), edge_index[1].to(torch.int64).contiguous()
+    E = int(src.numel())
+    if keep is not None:
+        keep = keep.to(device=dev, dtype=torch.uint8).contiguous()
+        if keep.numel() != E:
+            raise ValueError("keep mask must have one entry per edge")
+    nb = L.ocn_graph_build_bytes(E, int(symmetric))
+    scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+    rowptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    info = torch.zeros(2, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(L.ocn_graph_build_count(_lib.ptr(src), _lib.ptr(dst), _lib.ptr(keep), E, n, int(symmetric),
+                                           _lib.ptr(scratch), nb, _lib.ptr(rowptr), _lib.ptr(info), st),
+                   "ocn_graph_build_count")
+        nnz, bad = info.tolist()
+        if bad:
+            raise ValueError(f"{bad} edges have an endpoint outside [0, {n})")
+        col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        mult = torch.empty(nnz, dtype=torch.int32, device=dev) if with_mult else None
+        _lib.check(L.ocn_graph_build_fill(_lib.ptr(scratch), E, int(symmetric), n, nnz, _lib.ptr(col), _lib.ptr(mult), st),
+                   "ocn_graph_build_fill")
+    return Graph(rowptr, col, n, None, None, mult)
 
 
 def _require_cuda(t: Tensor):

@@ -67,16 +67,35 @@ def _(rowptr, col, val, grad_out, n_cols, reduce):
     return grad_out.new_empty(n_cols, grad_out.shape[1], dtype=torch.float32)
 
 
+@torch.library.custom_op("ocn::spmm_csr_max_bwd", mutates_args=(), device_types="cuda")
+def spmm_csr_max_bwd(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, grad_out: Tensor) -> Tensor:
+    from . import _lib
+    g, xf = grad_out.contiguous().float(), x.contiguous().float()
+    gx = torch.zeros_like(xf)
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.lib().ocn_spmm_csr_max_bwd(_lib.ptr(rowptr), _lib.ptr(col.to(torch.int32)), _lib.ptr(val),
+                                                   rowptr.numel() - 1, _lib.ptr(xf), _lib.ptr(g), g.shape[1],
+                                                   _lib.ptr(gx), _cn._stream(g.device)), "ocn_spmm_csr_max_bwd")
+    return gx
+
+
+@spmm_csr_max_bwd.register_fake
+def _(rowptr, col, val, x, grad_out):
+    return x.new_empty(x.shape, dtype=torch.float32)
+
+
 def _spmm_setup(ctx, inputs, output):
     rowptr, col, val, x, reduce = inputs
-    ctx.save_for_backward(rowptr, col, val if val is not None else rowptr.new_empty(0))
+    ctx.save_for_backward(rowptr, col, val if val is not None else rowptr.new_empty(0),
+                          x if reduce == 2 else rowptr.new_empty(0))
     ctx.has_val, ctx.reduce, ctx.n_cols = val is not None, reduce, x.shape[0]
 
 
 def _spmm_backward(ctx, g):
-    rowptr, col, val = ctx.saved_tensors
+    rowptr, col, val, x = ctx.saved_tensors
     if ctx.reduce == 2:
-        raise NotImplementedError("spmm max backward is not on the hot path")
+        gx = torch.ops.ocn.spmm_csr_max_bwd(rowptr, col, val if ctx.has_val else None, x, g)
+        return None, None, None, gx, None
     gx = torch.ops.ocn.spmm_csr_bwd(rowptr, col, val if ctx.has_val else None, g, ctx.n_cols, ctx.reduce)
     return None, None, None, gx, None
 

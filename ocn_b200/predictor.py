@@ -105,12 +105,27 @@ class _OCNBase(nn.Module):
         self.innerprod *= (1 - beta)
         self.innerprod += beta * s
 
-    def cn_stage(self, x: Tensor, adj: Graph, tar_ei: Tensor, fill: float = 0.0, sess: Optional[CNSession] = None):
+    def batch_inner_product(self, sess: CNSession, fill: float = 0.0) -> Tensor:
+        """``s`` of ``innerprod1`` (model.py:2244) for a one-batch session: sum(C2 * C1-hat).  It depends on the
+        CN sets and the column statistics only, not on the running mean -- which is what lets the sub-batches
+        of one optimiser step run on different ranks (``ocn_b200.dist.sharded_train_step``)."""
+        ip3 = self.innerprod.detach().float().repeat(3).contiguous()
+        return sess.stats(5, fill, ip3, 0)[0, 1].detach().clone()
+
+    def cn_stage(self, x: Tensor, adj: Graph, tar_ei: Tensor, fill: float = 0.0, sess: Optional[CNSession] = None,
+                 ip: Optional[Tensor] = None):
+        """``ip``: use this inner-product coefficient (shape [1]) instead of reading / updating the module's
+        running mean -- the caller has already folded this batch's ``s`` into it."""
         if sess is None:
             sess = CNSession(adj, tar_ei, None, self.order)
             sess.build(self.order, self.weighted)
-        ip3 = self.innerprod.detach().float().repeat(3).contiguous()
-        if self.variant == 5:
+        ip3 = (self.innerprod if ip is None else ip).detach().float().reshape(-1)[:1].repeat(3).contiguous()
+        if self.variant == 5 and ip is not None:
+            if self.order >= 3:
+                raise ValueError("an explicit coefficient is supported for order 2 (cn5); the order-3 template chains "
+                                 "three updates per batch through the buffer (SURVEY Q9)")
+            sess.stats(5, fill, ip3, 0)
+        elif self.variant == 5:
             if self.training and sess.nb != 1:
                 raise ValueError("training updates the inner-product running mean once per link batch; "
                                  "pass one batch per call (the reference does, NeighborOverlapCitation2.py:162-179)")

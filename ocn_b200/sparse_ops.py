@@ -40,18 +40,22 @@ def _spmm_raw(rowptr, col, val, rows, x, reduce: int) -> Tensor:
 class _SpmmFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, rowptr, col, val, rows, reduce):
-        ctx.save_for_backward(rowptr, col, val)
+        xf = x.float().contiguous()
+        ctx.save_for_backward(rowptr, col, val, xf if reduce == 2 else None)
         ctx.rows, ctx.reduce, ctx.xshape = rows, reduce, x.shape
-        return _spmm_raw(rowptr, col, val, rows, x.float(), reduce)
+        return _spmm_raw(rowptr, col, val, rows, xf, reduce)
 
     @staticmethod
     def backward(ctx, g):
-        rowptr, col, val = ctx.saved_tensors
-        if ctx.reduce == 2:
-            raise NotImplementedError("spmm_max backward is not on the hot path (the reference's README configs use sum/gcn)")
+        rowptr, col, val, xf = ctx.saved_tensors
         g = g.contiguous().float()
         gx = torch.zeros(ctx.xshape, dtype=torch.float32, device=g.device)
         with torch.cuda.device(g.device):
+            if ctx.reduce == 2:
+                _lib.check(_lib.lib().ocn_spmm_csr_max_bwd(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), ctx.rows,
+                                                           _lib.ptr(xf), _lib.ptr(g), g.shape[1], _lib.ptr(gx),
+                                                           _stream(g.device)), "ocn_spmm_csr_max_bwd")
+                return gx, None, None, None, None, None
             _lib.check(_lib.lib().ocn_spmm_csr_bwd(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), ctx.rows,
                                                    _lib.ptr(g), g.shape[1], ctx.reduce, _lib.ptr(gx),
                                                    _stream(g.device)), "ocn_spmm_csr_bwd")

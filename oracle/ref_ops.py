@@ -75,6 +75,21 @@ def sp_coalesce(row: Tensor, col: Tensor, val: Optional[Tensor], shape, reduce_s
 # piece 1: per-target-edge row intersection  (utils.py:146-183, 248-285)
 # ----------------------------------------------------------------------------------------------
 
+def masked_adjacency(edge_list: Tensor, n: int, perm: Optional[Tensor] = None, symmetric: bool = True) -> Sp:
+    """The adjacency of one training batch under --maskinput, as the driver builds it
+    (NeighborOverlap_large.py:49,56-63; NeighborOverlapCitation2.py:129,135-143): ``adjmask[perm] = 0``,
+    ``from_edge_index(edge_list[:, adjmask])`` (sorted by (row, col), duplicates kept), ``to_symmetric()``
+    (union with the transpose, coalesced).  ``perm=None`` is the unmasked ``data.adj_t``."""
+    adjmask = torch.ones(edge_list.shape[1], dtype=torch.bool)
+    if perm is not None:
+        adjmask[perm] = 0
+    tei = edge_list[:, adjmask]
+    row, col = tei[0], tei[1]
+    if symmetric:
+        row, col = torch.cat((row, col)), torch.cat((col, row))
+    return sp_coalesce(row, col, None, (n, n))
+
+
 def index_select_rows(adj: Sp, idx: Tensor) -> Sp:
     """``adj[idx]`` (utils.py:256-257): torch_sparse row gather -- output row r is input row
     idx[r], columns keep their ascending order [recalled]."""
@@ -373,6 +388,23 @@ def cn7_aggregate(cn1: Sp, cn2: Sp, x: Tensor, tar_ei: Tensor, args_sum: float):
 # ----------------------------------------------------------------------------------------------
 # piece 3a: GNN neighbour aggregation
 # ----------------------------------------------------------------------------------------------
+
+def spmm_max_backward(adj: Sp, x: Tensor, grad_out: Tensor) -> Tensor:
+    """Backward of ``spmm_max`` (torch_sparse.matmul, model.py:47): the gradient of out[r, f] goes to the
+    first entry of row r (in column order) that attains the maximum [recalled: torch_sparse's spmm keeps
+    the arg-max with a strict ">" while scanning the row]; empty rows pass nothing."""
+    prod = adj.values().unsqueeze(1) * x[adj.col]                                    # [nnz, F]
+    best = torch.full((adj.shape[0], x.shape[1]), float("-inf")).index_reduce_(0, adj.row, prod, "amax")
+    pos = torch.arange(adj.nnz).unsqueeze(1).expand_as(prod)
+    cand = torch.where(prod == best[adj.row], pos, torch.full_like(pos, adj.nnz))
+    first = torch.full((adj.shape[0], x.shape[1]), adj.nnz, dtype=torch.long).scatter_reduce_(
+        0, adj.row.unsqueeze(1).expand_as(cand), cand, "amin")
+    gx = torch.zeros_like(x)
+    r, f = torch.nonzero(first < adj.nnz, as_tuple=True)
+    e = first[r, f]
+    gx.index_put_((adj.col[e], f), adj.values()[e] * grad_out[r, f], accumulate=True)
+    return gx
+
 
 def pure_conv(x: Tensor, adj: Sp, aggr: str) -> Tensor:
     """``PureConv.forward`` (model.py:42-55)."""

@@ -293,6 +293,14 @@ def test_gnn_aggregation(name, F):
     xg = xd.clone().requires_grad_(True)
     (ob.pure_conv(xg, G, "mean") * w.to(DEV)).sum().backward()
     _close(xg.grad, xr.grad, R.spmm_add(ones, w.abs()), rtol=1e-4)
+    # backward of the max aggregation: the first arg-max of every (row, feature) receives the gradient
+    xg = xd.clone().requires_grad_(True)
+    (ob.pure_conv(xg, G, "max") * w.to(DEV)).sum().backward()
+    _close(xg.grad, R.spmm_max_backward(A, x, w), R.spmm_add(ones, w.abs()), rtol=1e-5)
+    xt = torch.round(x * 2) / 2  # many ties
+    xg = xt.to(DEV).requires_grad_(True)
+    (ob.pure_conv(xg, G, "max") * w.to(DEV)).sum().backward()
+    _close(xg.grad, R.spmm_max_backward(A, xt, w), R.spmm_add(ones, w.abs()), rtol=1e-5)
 
 
 def test_spmm_on_cn_matrix_with_values():

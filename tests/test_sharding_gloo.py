@@ -56,3 +56,57 @@ def test_batches_dealt_and_scores_gathered():
         p.join(120)
         assert p.exitcode == 0
     assert out.get(timeout=10) is True
+
+
+def _train_worker(rank, world, port, out):
+    """Scalar exchange + running-mean replay + flat gradient all-reduce, against the sequential loop."""
+    from ocn_b200.dist import allreduce_gradients, exchange_batch_scalars, replay_running_mean
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    U = 7
+    s_seq = torch.randn(U).abs() * 3  # the inner products of the 7 sub-batches of a step
+    mine = list(range(rank, U, world))
+    s_all = exchange_batch_scalars(s_seq[mine], mine, U)
+    ips, n_end = replay_running_mean(s_all, torch.tensor([0.25]), 3)
+    # sequential module behaviour (model.py:2245-2248)
+    ip, n, want = torch.tensor([0.25]), 3, []
+    for u in range(U):
+        n += 1
+        beta = n ** -1
+        ip *= (1 - beta)
+        ip += beta * s_seq[u]
+        want.append(ip.clone())
+    ok = torch.equal(s_all, s_seq) and torch.equal(ips, torch.cat(want)) and n_end == n
+    # gradients: every rank back-propagates its sub-batches' share of the loss; the sum is the step gradient
+    lin = torch.nn.Linear(5, 3)
+    frozen = torch.nn.Parameter(torch.ones(2), requires_grad=False)
+    unused = torch.nn.Parameter(torch.ones(4))  # never touched on any rank: stays zero
+    x = torch.randn(U, 11, 5)
+    for u in mine:
+        (lin(x[u]).sigmoid().sum() / U).backward()
+    allreduce_gradients(list(lin.parameters()) + [frozen, unused])
+    ref = torch.nn.Linear(5, 3)
+    ref.load_state_dict(lin.state_dict())
+    for u in range(U):
+        (ref(x[u]).sigmoid().sum() / U).backward()
+    ok = ok and torch.allclose(lin.weight.grad, ref.weight.grad, rtol=1e-5, atol=1e-6) \
+        and torch.allclose(lin.bias.grad, ref.bias.grad, rtol=1e-5, atol=1e-6) \
+        and frozen.grad is None and bool((unused.grad == 0).all())
+    if rank == 0:
+        out.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_training_step_exchange_and_gradient_allreduce():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get(timeout=10) is True
