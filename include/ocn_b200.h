@@ -247,6 +247,18 @@ int ocn_spgemm_a2_numeric(const int64_t* rowptr, const int32_t* col, int64_t n, 
                           void* scratch, const int64_t* out_rowptr, int32_t* out_col, float* out_val,
                           void* stream);
 
+/* ---- the step after the aggregation: fused inference-mode MLP head --------------------
+ * out[b, :] = lin(mix[0]*xcn1lin(xcn1[b]) + mix[1]*xcn2lin(xcn2[b]) [+ mix[2]*xcn3lin(xcn3[b])] + mix[3]*xijlin(xij[b]))
+ * (model.py:2192-2235 modules, :2429-2437 combination; mix = sigmoid(alpha).cumprod and beta).  Served for
+ * in_ch, hid in {32, 64} with <= 200 KB of parameters (they live in shared memory); ocn_cn_head_params returns
+ * the length of the packed fp32 parameter buffer (layout documented in csrc/head.cu) or -1 when the head is
+ * not served (the caller keeps its GEMMs).  flags: bit0 LayerNorm, bit1 tailact, bit2 twolayerlin.
+ * xcn3 NULL = two CN branches (cn5 / cn7). */
+int64_t ocn_cn_head_params(int in_ch, int hid, int out_ch, int flags, int branches);
+int ocn_cn_head(const float* xcn1, const float* xcn2, const float* xcn3, const float* xij, int64_t num_links,
+                int in_ch, int hid, int out_ch, int flags, const float* params, int64_t params_len,
+                const float* mix, float* out, void* stream);
+
 /* ---- the step after the path: ranking metrics on the device --------------------------
  * ogb Evaluator.eval as the drivers call it (NeighborOverlap_large.py:162-179: Hits@K over all positive /
  * negative scores of a split; NeighborOverlapCitation2.py:256-259: MRR of every source against its own

@@ -53,6 +53,8 @@ _SIGS = {
     "ocn_spgemm_scratch_bytes": (c_size_t, [c_int64]),
     "ocn_spgemm_a2_symbolic": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P]),
     "ocn_spgemm_a2_numeric": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "ocn_cn_head_params": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
+    "ocn_cn_head": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int64, _P, _P, _P]),
     "ocn_mrr": (c_int, [_P, _P, c_int64, c_int64, _P, _P]),
     "ocn_hits_bytes": (c_size_t, [c_int64]),
     "ocn_hits_at_k": (c_int, [_P, c_int64, _P, c_int64, c_int64, _P, c_size_t, _P, _P]),

@@ -146,7 +146,13 @@ class _OCNBase(nn.Module):
             sess.release()  # nothing will run backward through this session: hand the statistics buffer back
         return xcn1, xcn2, (xcn3 if xcn3.numel() else None), xij, sess
 
+    fuse_head = True  # inference: one fused kernel for hidden widths 32 / 64 (csrc/head.cu); else the torch modules
+
     def _head(self, xcn1, xcn2, xcn3, xij):
+        if self.fuse_head and not self.training and not torch.is_grad_enabled() and xcn1.is_cuda:
+            from . import head
+            if head.supported(self, xcn1.shape[1]) > 0:
+                return head.fused_head(self, xcn1, xcn2, xcn3, xij)
         xij = self.xijlin(xij)
         xcn1 = self.xcn1lin(xcn1)
         xcn2 = self.xcn2lin(xcn2)

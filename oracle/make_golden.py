@@ -135,7 +135,14 @@ def run_case(name, graph, F, batches, predictor, mode, style, fill=None, ln=Fals
 
 
 def main():
-    argparse.ArgumentParser().parse_args()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="", help="regex: write only the fixtures whose name matches")
+    only = re.compile(ap.parse_args().only)
+    write_case = globals()["run_case"]
+
+    def run_case(name, *a, **k):
+        if only.search(name):
+            write_case(name, *a, **k)
     tiny = synth.tiny_graph(60, 260, 3)
     cora = synth.make_graph("cora", scale=0.12)
     cit = synth.make_graph("citation2", scale=0.0002)
@@ -158,6 +165,10 @@ def main():
     run_case("cn5_pygho_train_cit", cit, 8, links(cit, 64, 3), "cn5", "train", "pygho")
     run_case("cn6_pygho_eval_cit", cit, 8, [cit.query_edges(64, "stream")], "cn6", "eval", "pygho")
     run_case("cn6_pygho_train_tiny", tiny, 8, links(tiny, 48, 3), "cn6", "train", "pygho")
+    # widths served by the fused inference head (csrc/head.cu): 32 (the citation2 config) and 64
+    run_case("cn6_pygho_eval_cit_f32", cit, 32, [cit.query_edges(64, "stream")], "cn6", "eval", "pygho", seed=1)
+    run_case("cn5_large_eval_ln_cora_f32", cora, 32, links(cora, 96, 1), "cn5", "eval", "large", ln=True, seed=2)
+    run_case("cn7_large_sum1_tiny_f64", tiny, 64, links(tiny, 48, 1), "cn7", "eval", "large", fill=1, seed=3)
 
 
 if __name__ == "__main__":

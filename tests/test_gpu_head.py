@@ -1,0 +1,60 @@
+"""Fused inference head (csrc/head.cu) against the torch modules that mirror the reference's
+nn.Sequential heads (model.py:2192-2235), for every flag combination and served width; the golden fixtures
+of tests/test_golden_reference.py (*_f32 / *_f64) pin the same kernel to the reference's own scores."""
+import itertools
+
+import pytest
+import torch
+
+import ocn_b200 as ob
+from ocn_b200 import head
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("in_ch,hid", [(32, 32), (64, 32), (32, 64), (64, 64)])
+@pytest.mark.parametrize("ln,tailact,two", list(itertools.product([False, True], repeat=3)))
+@pytest.mark.parametrize("cls", ["cn5", "cn6"])
+def test_fused_head_matches_modules(in_ch, hid, ln, tailact, two, cls):
+    torch.manual_seed(in_ch + hid + 2 * ln + 4 * tailact + 8 * two)
+    P = ob.predictor_dict[cls]
+    pred = P(in_ch, hid, 2 if two else 1, 3, 0.0, ln=ln, tailact=tailact, twolayerlin=two).to(DEV).eval()
+    with torch.no_grad():
+        pred.alpha.copy_(torch.tensor([0.3, -0.2, 1.1]))
+        pred.beta.fill_(0.7)
+    B = 1000 + 3  # not a multiple of the links a warp carries
+    xs = [torch.randn(B, in_ch, device=DEV) * s for s in (1.0, 3.0, 0.5, 2.0)]
+    x3 = xs[2] if cls == "cn6" else None
+    assert head.supported(pred, in_ch) > 0
+    with torch.no_grad():
+        got = pred._head(xs[0], xs[1], x3, xs[3])
+        pred.fuse_head = False
+        want = pred._head(xs[0], xs[1], x3, xs[3])
+    assert got.shape == want.shape
+    # fp32 fma chains in a different order than cuBLAS; compare in float64 against the modules' own result
+    err = (got.double() - want.double()).abs().max().item()
+    assert err <= 2e-5 * (1.0 + want.abs().max().item()), err
+
+
+def test_unserved_widths_and_training_keep_the_modules():
+    pred = ob.CNLinkPredictorOringin(256, 256, 1, 3, 0.0).to(DEV).eval()
+    assert head.supported(pred, 256) == -1
+    x = torch.randn(10, 256, device=DEV)
+    with torch.no_grad():
+        assert pred._head(x, x, None, x).shape == (10, 1)
+    pred = ob.CNLinkPredictorOringin(32, 32, 1, 3, 0.0).to(DEV).train()
+    x = torch.randn(10, 32, device=DEV, requires_grad=True)
+    out = pred._head(x, x, None, x)
+    out.sum().backward()  # autograd through the torch modules
+    assert x.grad is not None
+
+
+def test_parameter_cache_follows_updates():
+    pred = ob.CNLinkPredictorOringin(32, 32, 1, 3, 0.0).to(DEV).eval()
+    x = torch.randn(64, 32, device=DEV)
+    with torch.no_grad():
+        a = pred._head(x, x, None, x)
+        pred.lin[-1].bias.add_(1.0)
+        b = pred._head(x, x, None, x)
+    assert torch.allclose(b - a, torch.ones_like(a), atol=1e-5)

@@ -49,7 +49,7 @@ def _sequential(variant):
             out = pred.multidomainforward(h, G, None, None, e, 1.0)
         l = -(1.0 / total) * F.logsigmoid(sg * out).sum()
         l.backward()
-        loss += float(l)
+        loss += float(l.detach())
     return pred, h, loss
 
 
@@ -61,8 +61,10 @@ def _worker(rank, world, port, variant, out):
     loss = sharded_train_step(pred, h, G, subs, signs, total, rank, world, fill=1.0 if variant == 7 else 0.0)
     torch.cuda.synchronize()
     if rank == 0:
-        out.put(({k: v.grad.cpu() for k, v in pred.named_parameters() if v.grad is not None}, h.grad.cpu(),
-                 float(loss), pred.innerprod.cpu(), pred.n))
+        # numpy arrays are pickled by value (tensors would be shared through file descriptors of a process
+        # that may already have exited)
+        out.put(({k: v.grad.cpu().numpy() for k, v in pred.named_parameters() if v.grad is not None},
+                 h.grad.cpu().numpy(), float(loss), pred.innerprod.cpu().numpy(), pred.n))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -77,6 +79,8 @@ def test_sharded_train_step_matches_sequential(variant):
     for p in procs:
         p.start()
     grads, hgrad, loss, ip, n = out.get(timeout=300)
+    grads = {k: torch.from_numpy(v) for k, v in grads.items()}
+    hgrad, ip = torch.from_numpy(hgrad), torch.from_numpy(ip)
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
