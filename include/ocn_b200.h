@@ -95,6 +95,18 @@ int ocn_rows_intersect_fill(const int64_t* rowptr1, const int32_t* col1,
                             const int64_t* src, const int64_t* dst, int64_t num_edges,
                             const int64_t* out_rowptr, int64_t* out_col, void* stream);
 
+/* calresadj=True branch of adjoverlap (utils.py:260-274 -> spmoverlap_notoverlap_ utils.py:210-244), used by the
+ * completion predictors: out row b = adj1[src[b]] \ adj2[dst[b]] (columns ascending).  The second residual,
+ * adj2[dst] \ adj1[src], is the same call with the matrices and link ends swapped. */
+int ocn_rows_difference_count(const int64_t* rowptr1, const int32_t* col1,
+                              const int64_t* rowptr2, const int32_t* col2,
+                              const int64_t* src, const int64_t* dst, int64_t num_edges,
+                              int64_t* out_counts, void* stream);
+int ocn_rows_difference_fill(const int64_t* rowptr1, const int32_t* col1,
+                             const int64_t* rowptr2, const int32_t* col2,
+                             const int64_t* src, const int64_t* dst, int64_t num_edges,
+                             const int64_t* out_rowptr, int64_t* out_col, void* stream);
+
 /* ---- pieces 1 + 1b + 2, fused: higher-order CN sets over A, A^2, A^3 ------------------------
  * Replaces get_cn1_cn2 (NeighborOverlapCitation2.py:78-104, NeighborOverlap_large_ppa.py:147-173)
  * and adjoverlap(adj, adj, e) / adjoverlap(adj, adj2, e) (NeighborOverlap_large.py:78-79)

@@ -63,34 +63,43 @@ def _edges(tarei: Tensor) -> Tuple[Tensor, Tensor]:
 
 
 def adjoverlap(adj1: Graph, adj2: Graph, tarei: Tensor, filled1: bool = False, calresadj: bool = False,
-               cnsampledeg: int = -1, ressampledeg: int = -1) -> SparseRows:
+               cnsampledeg: int = -1, ressampledeg: int = -1):
     """``utils.adjoverlap``: row b = adj1[tarei[0,b]] (cap) adj2[tarei[1,b]], value 1.0.
 
     ``adj2`` may be any matrix over the same columns (A itself, an explicit A^2 from
     ``spgemm_a2`` or the folded adj2byblock matrix)."""
-    if calresadj or cnsampledeg > 0 or ressampledeg > 0:
-        raise NotImplementedError("only the calresadj=False, cnsampledeg=-1 branch used by cn5/cn7 is on the hot path")
+    if cnsampledeg > 0 or ressampledeg > 0:
+        raise NotImplementedError("the random samplers (sparsesample_reweight, utils.py:109-143) are not on the hot path: "
+                                  "no README command sets cndeg > 0")
     _require_cuda(tarei)
     if adj1.sizes() != adj2.sizes():
         raise AssertionError("adj1.sizes() == adj2.sizes()")  # utils.py:165
     src, dst = _edges(tarei)
+    overlap = _rows_setop("intersect", adj1, adj2, src, dst)
+    if not calresadj:
+        return overlap
+    # utils.py:260-274: (overlap, adj1[src] minus adj2[dst], adj2[dst] minus adj1[src])
+    return overlap, _rows_setop("difference", adj1, adj2, src, dst), _rows_setop("difference", adj2, adj1, dst, src)
+
+
+def _rows_setop(op: str, adj1: Graph, adj2: Graph, src: Tensor, dst: Tensor) -> SparseRows:
     B = src.numel()
     dev = adj1.device
     counts = torch.zeros(B + 1, dtype=torch.int64, device=dev)
     L = _lib.lib()
+    count_fn, fill_fn = getattr(L, f"ocn_rows_{op}_count"), getattr(L, f"ocn_rows_{op}_fill")
     with torch.cuda.device(dev):
         st = _stream(dev)
-        _lib.check(L.ocn_rows_intersect_count(_lib.ptr(adj1.rowptr), _lib.ptr(adj1.col), _lib.ptr(adj2.rowptr),
-                                              _lib.ptr(adj2.col), _lib.ptr(src), _lib.ptr(dst), B,
-                                              _lib.ptr(counts), st), "ocn_rows_intersect_count")
+        _lib.check(count_fn(_lib.ptr(adj1.rowptr), _lib.ptr(adj1.col), _lib.ptr(adj2.rowptr), _lib.ptr(adj2.col),
+                            _lib.ptr(src), _lib.ptr(dst), B, _lib.ptr(counts), st), f"ocn_rows_{op}_count")
         rowptr = torch.zeros(B + 1, dtype=torch.int64, device=dev)
         torch.cumsum(counts[:B], 0, out=rowptr[1:])
         nnz = int(rowptr[-1].item())
         col = torch.empty(nnz, dtype=torch.int64, device=dev)
         if nnz:
-            _lib.check(L.ocn_rows_intersect_fill(_lib.ptr(adj1.rowptr), _lib.ptr(adj1.col), _lib.ptr(adj2.rowptr),
-                                                 _lib.ptr(adj2.col), _lib.ptr(src), _lib.ptr(dst), B,
-                                                 _lib.ptr(rowptr), _lib.ptr(col), st), "ocn_rows_intersect_fill")
+            _lib.check(fill_fn(_lib.ptr(adj1.rowptr), _lib.ptr(adj1.col), _lib.ptr(adj2.rowptr), _lib.ptr(adj2.col),
+                               _lib.ptr(src), _lib.ptr(dst), B, _lib.ptr(rowptr), _lib.ptr(col), st),
+                       f"ocn_rows_{op}_fill")
     return SparseRows(rowptr, col, torch.ones(nnz, dtype=torch.float32, device=dev), (B, adj1.n_cols))
 
 

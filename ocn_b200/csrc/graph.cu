@@ -99,6 +99,43 @@ __global__ void k_rows_intersect(const int64_t* __restrict__ rowptr1, const int3
     }
 }
 
+// Set difference for the completion predictors' calresadj=True branch (utils.py:260-274 ->
+// spmoverlap_notoverlap_ :210-244): out row b = adj1[src[b]] \ adj2[dst[b]], columns ascending.  One warp
+// per link walks row 1 and binary-searches row 2 (the other difference is the same call with the
+// matrices and the link ends swapped).
+template <bool FILL>
+__global__ void k_rows_difference(const int64_t* __restrict__ rowptr1, const int32_t* __restrict__ col1,
+                                  const int64_t* __restrict__ rowptr2, const int32_t* __restrict__ col2,
+                                  const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                  int64_t num_edges, int64_t* __restrict__ out_counts,
+                                  const int64_t* __restrict__ out_rowptr, int64_t* __restrict__ out_col) {
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int lane = lane_id();
+    for (int64_t t = warp; t < num_edges; t += nwarps) {
+        const int64_t i = src[t], j = dst[t];
+        const int64_t s1 = rowptr1[i], l1 = rowptr1[i + 1] - s1;
+        const int64_t s2 = rowptr2[j], l2 = rowptr2[j + 1] - s2;
+        const int32_t* a = col1 + s1;
+        const int32_t* b = col2 + s2;
+        int64_t count = 0;
+        const int64_t obase = FILL ? out_rowptr[t] : 0;
+        for (int64_t base = 0; base < l1; base += 32) {
+            const int64_t o = base + lane;
+            bool keep = false;
+            int32_t c = 0;
+            if (o < l1) {
+                c = __ldg(a + o);
+                keep = !row_contains(b, l2, c);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (FILL && keep) out_col[obase + count + __popc(m & ((1u << lane) - 1))] = c;
+            count += __popc(m);
+        }
+        if (!FILL && lane == 0) out_counts[t] = count;
+    }
+}
+
 }  // namespace ocn
 
 using namespace ocn;
@@ -146,6 +183,34 @@ int ocn_rows_intersect_fill(const int64_t* rowptr1, const int32_t* col1, const i
     int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
     k_rows_intersect<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr1, col1, rowptr2, col2, src, dst,
                                                                       num_edges, nullptr, out_rowptr, out_col);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+int ocn_rows_difference_count(const int64_t* rowptr1, const int32_t* col1, const int64_t* rowptr2,
+                              const int32_t* col2, const int64_t* src, const int64_t* dst, int64_t num_edges,
+                              int64_t* out_counts, void* stream) {
+    OCN_CHECK_ARG(rowptr1 && rowptr2 && num_edges >= 0, "ocn_rows_difference_count: bad arguments");
+    if (num_edges == 0) return OCN_OK;
+    OCN_CHECK_ARG(src && dst && out_counts, "ocn_rows_difference_count: null edge/out pointer");
+    int64_t want = (num_edges + 7) / 8;
+    int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
+    k_rows_difference<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr1, col1, rowptr2, col2, src, dst,
+                                                                        num_edges, out_counts, nullptr, nullptr);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+int ocn_rows_difference_fill(const int64_t* rowptr1, const int32_t* col1, const int64_t* rowptr2,
+                             const int32_t* col2, const int64_t* src, const int64_t* dst, int64_t num_edges,
+                             const int64_t* out_rowptr, int64_t* out_col, void* stream) {
+    OCN_CHECK_ARG(rowptr1 && rowptr2 && num_edges >= 0, "ocn_rows_difference_fill: bad arguments");
+    if (num_edges == 0) return OCN_OK;
+    OCN_CHECK_ARG(src && dst && out_rowptr, "ocn_rows_difference_fill: null edge/out pointer");
+    int64_t want = (num_edges + 7) / 8;
+    int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
+    k_rows_difference<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr1, col1, rowptr2, col2, src, dst,
+                                                                       num_edges, nullptr, out_rowptr, out_col);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
 }

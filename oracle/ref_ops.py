@@ -155,9 +155,13 @@ def spmoverlap_notoverlap_(adj1: Sp, adj2: Sp) -> Tuple[Sp, Sp, Sp]:
             elem2spm(element2[~matchedmask], adj1.shape))
 
 
-def adjoverlap(adj1: Sp, adj2: Sp, tarei: Tensor) -> Sp:
-    """utils.py:248-285, ``calresadj=False, cnsampledeg=-1`` branch (the only one cn5/cn7 reach)."""
-    return spmoverlap_(index_select_rows(adj1, tarei[0]), index_select_rows(adj2, tarei[1]))
+def adjoverlap(adj1: Sp, adj2: Sp, tarei: Tensor, calresadj: bool = False):
+    """utils.py:248-285 with ``cnsampledeg=-1``: the ``calresadj=False`` branch (the only one cn5/cn7 reach)
+    or, with ``calresadj=True`` (:260-274, completion predictors), (overlap, only-in-1, only-in-2)."""
+    a1, a2 = index_select_rows(adj1, tarei[0]), index_select_rows(adj2, tarei[1])
+    if calresadj:
+        return spmoverlap_notoverlap_(a1, a2)
+    return spmoverlap_(a1, a2)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -26,7 +26,12 @@ def test_fused_head_matches_modules(in_ch, hid, ln, tailact, two, cls):
     B = 1000 + 3  # not a multiple of the links a warp carries
     xs = [torch.randn(B, in_ch, device=DEV) * s for s in (1.0, 3.0, 0.5, 2.0)]
     x3 = xs[2] if cls == "cn6" else None
-    assert head.supported(pred, in_ch) > 0
+    n_params = sum(p.numel() for n, p in pred.named_parameters()
+                   if n.split(".")[0] in ("xcn1lin", "xcn2lin", "xijlin", "lin") or (cls == "cn6" and n.startswith("xcn3lin")))
+    if 4 * n_params > 200 * 1024:  # does not fit the shared-memory budget: the torch modules serve it
+        assert head.supported(pred, in_ch) == -1
+        return
+    assert head.supported(pred, in_ch) == n_params
     with torch.no_grad():
         got = pred._head(xs[0], xs[1], x3, xs[3])
         pred.fuse_head = False

@@ -76,6 +76,9 @@ def test_adjoverlap_generic_and_spgemm(name):
     e = g.query_edges(512, "mixed")
     ed = e.to(DEV)
     _assert_rows_equal(ob.adjoverlap(G, G, ed), R.adjoverlap(A, A, e))
+    # calresadj=True (utils.py:260-274): overlap and the two residual sets
+    for got, ref in zip(ob.adjoverlap(G, G, ed, calresadj=True), R.adjoverlap(A, A, e, calresadj=True)):
+        _assert_rows_equal(got, ref)
     # true A^2 (structure and 2-walk counts), then adjoverlap(adj, adj2, e) as NeighborOverlap_large.py:78-79
     a2 = R.adj2_true(A, keep_value=True)
     G2 = ob.spgemm_a2(G, with_value=True)
