@@ -40,28 +40,45 @@ k_spmm(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, cons
                 w = val ? __ldg(val + o) : 1.0f;
             }
             const int cnt = (int)((e - base) < 32 ? (e - base) : 32);
-            for (int q = 0; q < cnt; q += rpw) {
-                const int sl = q + grp;
-                const int srcl = sl < cnt ? sl : 0;
-                const int32_t cc = __shfl_sync(0xffffffffu, c, srcl);
-                float ww = __shfl_sync(0xffffffffu, w, srcl);
-                if (sl < cnt) {
-                    float pre = 1.0f;
-                    if (mode == kGcnSelf) pre = norm[cc];
-                    else if (mode == kGcnNoSelf) ww = ww * (nr * norm[cc]);
+            // kGather neighbour rows per lane group are requested before any of them is consumed: a lane keeps
+            // kGather * VPL independent 16-byte loads in flight (one per iteration left the gather latency-bound)
+            constexpr int kGather = VPL <= 2 ? 4 : 2;
+            for (int q = 0; q < cnt; q += rpw * kGather) {
+                float4 xv[kGather][VPL];
+                float ww[kGather], pre[kGather];
+                bool on[kGather];
+#pragma unroll
+                for (int u = 0; u < kGather; ++u) {
+                    const int sl = q + u * rpw + grp;
+                    on[u] = sl < cnt;
+                    const int srcl = on[u] ? sl : 0;
+                    const int32_t cc = __shfl_sync(0xffffffffu, c, srcl);
+                    ww[u] = __shfl_sync(0xffffffffu, w, srcl);
+                    pre[u] = 1.0f;
+                    if (on[u]) {
+                        if (mode == kGcnSelf) pre[u] = norm[cc];
+                        else if (mode == kGcnNoSelf) ww[u] = ww[u] * (nr * norm[cc]);
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) {
+                            const int k = sub + v * lpr;
+                            xv[u][v] = (k < nvec) ? __ldg(x4 + (int64_t)cc * nvec + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kGather; ++u) {
+                    if (!on[u]) continue;
 #pragma unroll
                     for (int v = 0; v < VPL; ++v) {
-                        const int k = sub + v * lpr;
-                        if (k < nvec) {
-                            float4 xv = __ldg(x4 + (int64_t)cc * nvec + k);
-                            if (mode == kGcnSelf) { xv.x *= pre; xv.y *= pre; xv.z *= pre; xv.w *= pre; }
-                            if (is_max) {
-                                acc[v].x = fmaxf(acc[v].x, ww * xv.x); acc[v].y = fmaxf(acc[v].y, ww * xv.y);
-                                acc[v].z = fmaxf(acc[v].z, ww * xv.z); acc[v].w = fmaxf(acc[v].w, ww * xv.w);
-                            } else {
-                                acc[v].x = fmaf(ww, xv.x, acc[v].x); acc[v].y = fmaf(ww, xv.y, acc[v].y);
-                                acc[v].z = fmaf(ww, xv.z, acc[v].z); acc[v].w = fmaf(ww, xv.w, acc[v].w);
-                            }
+                        if (sub + v * lpr >= nvec) continue;
+                        float4 t = xv[u][v];
+                        if (mode == kGcnSelf) { t.x *= pre[u]; t.y *= pre[u]; t.z *= pre[u]; t.w *= pre[u]; }
+                        if (is_max) {
+                            acc[v].x = fmaxf(acc[v].x, ww[u] * t.x); acc[v].y = fmaxf(acc[v].y, ww[u] * t.y);
+                            acc[v].z = fmaxf(acc[v].z, ww[u] * t.z); acc[v].w = fmaxf(acc[v].w, ww[u] * t.w);
+                        } else {
+                            acc[v].x = fmaf(ww[u], t.x, acc[v].x); acc[v].y = fmaf(ww[u], t.y, acc[v].y);
+                            acc[v].z = fmaf(ww[u], t.z, acc[v].z); acc[v].w = fmaf(ww[u], t.w, acc[v].w);
                         }
                     }
                 }

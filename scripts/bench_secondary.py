@@ -30,9 +30,72 @@ def timeit(fn, reps=5, warm=2):
     return ts[len(ts) // 2]
 
 
+def before_after(out):
+    """The steps either side of the path at citation2 shape: device CSR build, per-batch
+    --maskinput adjacency (vs rebuilding with torch sort/unique on the same GPU, the reference's op sequence),
+    the fused inference head (vs the torch modules) and the ranking metrics."""
+    g = synth.make_graph("citation2", device=DEV)
+    n = g.n
+    el = torch.stack((g.raw_src, g.raw_dst)).to(DEV)
+    E = el.shape[1]
+    ms = timeit(lambda: ob.Graph.from_edge_index(el, n, with_multiplicity=True), reps=3, warm=1)
+    out.append({"op": "graph_build (from_edge_index + to_symmetric)", "edges": E, "ms": ms, "Medges_per_s": E / ms / 1e3})
+    print(out[-1], flush=True)
+    G = ob.Graph.from_edge_index(el, n, with_multiplicity=True)
+    perm = torch.randperm(E, device=DEV)[:16384]
+    links = el[:, perm].contiguous()
+    ms = timeit(lambda: G.masked(links), reps=5, warm=2)
+    byt = 2 * 8 * (n + 1) + 3 * 4 * G.nnz + 4 * G.nnz  # rowptr in/out, col + mult + dec read twice-ish, col written
+    out.append({"op": "graph_mask (adjmask[perm]=0 rebuild) by multiplicity decrement", "masked_links": 16384, "nnz": G.nnz,
+                "ms": ms, "alg_GBs": byt / ms / 1e6, "frac_of_measured_hbm": byt / ms / 1e6 / PEAK})
+    print(out[-1], flush=True)
+
+    def torch_rebuild():  # the reference's per-batch op sequence on the same GPU (sort-based)
+        keep = torch.ones(E, dtype=torch.bool, device=DEV)
+        keep[perm] = False
+        s, d = el[0][keep], el[1][keep]
+        key = torch.unique(torch.cat((s, d)) * n + torch.cat((d, s)))
+        return key
+    ms2 = timeit(torch_rebuild, reps=3, warm=1)
+    out.append({"op": "graph_mask reference op sequence (torch.unique of the remaining list, same GPU)", "ms": ms2,
+                "speedup_of_graph_mask": ms2 / ms})
+    print(out[-1], flush=True)
+    del G, el
+    torch.cuda.empty_cache()
+    for F in (32, 64):
+        torch.manual_seed(0)
+        pred = ob.CNLinkPredictor3hopCNs(F, F, 1, 3, 0.0).to(DEV).eval()
+        xs = [torch.randn(65536, F, device=DEV) for _ in range(4)]
+        with torch.no_grad():
+            pred.fuse_head = True
+            ms = timeit(lambda: pred._head(*xs))
+            pred.fuse_head = False
+            ms2 = timeit(lambda: pred._head(*xs))
+        out.append({"op": "predictor head, 65536 links", "F": F, "fused_ms": ms, "torch_modules_ms": ms2,
+                    "Mlinks_per_s": 65536 / ms / 1e3, "speedup": ms2 / ms})
+        print(out[-1], flush=True)
+    pos, neg = torch.randn(86596, device=DEV), torch.randn(86596, 1000, device=DEV)
+    ms = timeit(lambda: ob.metrics.mrr_list(pos, neg))
+    out.append({"op": "mrr (86596 sources x 1000 negatives)", "ms": ms, "alg_GBs": 4 * neg.numel() / ms / 1e6,
+                "frac_of_measured_hbm": 4 * neg.numel() / ms / 1e6 / PEAK})
+    print(out[-1], flush=True)
+    negf = torch.randn(3_000_000, device=DEV)
+    ms = timeit(lambda: ob.metrics.hits_at_k(pos, negf, 100))
+    out.append({"op": "hits@100 (3M negatives)", "ms": ms})
+    print(out[-1], flush=True)
+
+
 def main():
     out = []
-    for name, feats in (("citation2", (32, 128)), ("collab", (256,)), ("pubmed", (256,)), ("ddi", (64,))):
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only in ("", "steps"):
+        before_after(out)
+    graphs = (("citation2", (32, 128)), ("collab", (256,)), ("pubmed", (256,)), ("ddi", (64,)))
+    if only == "steps":
+        graphs = ()
+    elif only:
+        graphs = tuple(gf for gf in graphs if gf[0] == only)
+    for name, feats in graphs:
         g = synth.make_graph(name, device=DEV)
         G = ob.Graph(g.rowptr, g.col, g.n)
         norm = ob.gcn_norm(G)
@@ -72,7 +135,7 @@ def main():
         del G, g
         torch.cuda.empty_cache()
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/secondary.json", "w") as f:
+    with open(f"gpurun_out/secondary{('_' + only) if only else ''}.json", "w") as f:
         json.dump(out, f, indent=1)
 
 
