@@ -24,25 +24,43 @@ k_spmm(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, cons
     const int rpw = 32 / lpr, grp = lane / lpr, sub = lane - grp * lpr;
     const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
     const bool is_max = mode == kMax;
+    // Software pipeline over the rows of this warp: the row pointers of the row after next and the first 32
+    // columns of the next row are in flight while the current row's neighbour rows are gathered, so a row costs
+    // one exposed memory latency (the gather) instead of three dependent ones (rowptr -> col -> x).
+    auto load_ptr = [&](int64_t rr, int64_t& s, int64_t& e) {
+        s = 0; e = 0;
+        if (rr < num_rows) { s = ldg_i64(rowptr + rr); e = ldg_i64(rowptr + rr + 1); }
+    };
+    auto load_cols = [&](int64_t at, int64_t e, int32_t& c, float& w) {
+        c = 0; w = 0.f;
+        if (at + lane < e) { c = ldg_i32(col + at + lane); w = val ? __ldg(val + at + lane) : 1.0f; }
+    };
+    int64_t s1, e1, s2, e2;
+    int32_t c1;
+    float w1;
+    load_ptr(warp, s1, e1);
+    load_ptr(warp + nwarps, s2, e2);
+    load_cols(s1, e1, c1, w1);
     for (int64_t r = warp; r < num_rows; r += nwarps) {
-        const int64_t s = rowptr[r], e = rowptr[r + 1];
+        int64_t s3, e3;
+        load_ptr(r + 2 * nwarps, s3, e3);
+        int32_t c2;
+        float w2;
+        load_cols(s2, e2, c2, w2);
+        const int64_t s = s1, e = e1;
         const float nr = (mode >= kGcnSelf) ? norm[r] : 1.0f;
         float4 acc[VPL];
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
             acc[v] = is_max ? make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX) : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int64_t base = s; base < e; base += 32) {
-            const int64_t o = base + lane;
-            int32_t c = 0;
-            float w = 0.f;
-            if (o < e) {
-                c = ldg_i32(col + o);
-                w = val ? __ldg(val + o) : 1.0f;
-            }
+            int32_t c = c1;
+            float w = w1;
+            if (base != s) load_cols(base, e, c, w);
             const int cnt = (int)((e - base) < 32 ? (e - base) : 32);
             // kGather neighbour rows per lane group are requested before any of them is consumed: a lane keeps
             // kGather * VPL independent 16-byte loads in flight (one per iteration left the gather latency-bound)
-            constexpr int kGather = VPL <= 2 ? 4 : 2;
+            constexpr int kGather = 2;
             for (int q = 0; q < cnt; q += rpw * kGather) {
                 float4 xv[kGather][VPL];
                 float ww[kGather], pre[kGather];
@@ -116,6 +134,8 @@ k_spmm(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, cons
                 }
             }
         }
+        s1 = s2; e1 = e2; c1 = c2; w1 = w2;
+        s2 = s3; e2 = e3;
     }
 }
 

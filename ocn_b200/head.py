@@ -31,13 +31,28 @@ def _pack_seq(seq: nn.Sequential, last_plain: bool = False) -> List[Tensor]:
     return out
 
 
+_HEAD_MODULES = ("xcn1lin", "xcn2lin", "xcn3lin", "xijlin", "lin")
+
+
+def _static(pred, in_ch: int):
+    """Per-module facts that do not change after construction (flags, widths, parameter list, served or not)."""
+    st = pred.__dict__.get("_ocn_head_static")
+    if st is None or st["in_ch"] != in_ch:
+        three = pred.order >= 3 and hasattr(pred, "xcn3lin")
+        hid, out_ch = pred.lin[0].in_features, pred.lin[-1].out_features
+        flags = _flags(pred)
+        names = [m for m in _HEAD_MODULES if m != "xcn3lin" or three]
+        ps = [p for m in names for p in getattr(pred, m).parameters()]
+        n = _lib.lib().ocn_cn_head_params(int(in_ch), int(hid), int(out_ch), flags, 3 if three else 2)
+        st = {"in_ch": in_ch, "hid": hid, "out_ch": out_ch, "flags": flags, "three": three, "params": ps, "n": int(n)}
+        pred.__dict__["_ocn_head_static"] = st
+    return st
+
+
 def supported(pred, in_ch: int) -> int:
-    """Number of floats of the packed parameter buffer, or -1 when this head is not served by the fused kernel."""
-    lin0 = pred.lin[0]
-    hid, out_ch = lin0.in_features, pred.lin[-1].out_features
-    if any(isinstance(m, nn.Dropout) and m.p > 0 and pred.training for m in pred.modules()):
-        return -1
-    return _lib.lib().ocn_cn_head_params(int(in_ch), int(hid), int(out_ch), _flags(pred), 3 if hasattr(pred, "xcn3lin") and pred.order >= 3 else 2)
+    """Number of floats of the packed parameter buffer, or -1 when this head is not served by the fused kernel
+    (widths other than 32 / 64, more than 200 KB of parameters)."""
+    return _static(pred, in_ch)["n"]
 
 
 def _flags(pred) -> int:
@@ -47,35 +62,36 @@ def _flags(pred) -> int:
     return (1 if ln else 0) | (2 if tailact else 0) | (4 if two else 0)
 
 
-def packed_params(pred) -> Tensor:
-    """The head's parameters in the order csrc/head.cu documents; cached until a parameter changes."""
-    ps = [p for n, p in pred.named_parameters() if n.split(".")[0] in ("xcn1lin", "xcn2lin", "xcn3lin", "xijlin", "lin")]
-    key = tuple((p.data_ptr(), p._version) for p in ps)
-    cache = getattr(pred, "_ocn_head_cache", None)
+def packed_params(pred, in_ch: int) -> Tensor:
+    """The head's parameters in the order csrc/head.cu documents; repacked only when a parameter changed
+    (in-place update -> version counter, or a new tensor -> data pointer)."""
+    st = _static(pred, in_ch)
+    key = tuple(p._version for p in st["params"]) + (st["params"][0].data_ptr(), pred.alpha._version, pred.beta._version)
+    cache = pred.__dict__.get("_ocn_head_cache")
     if cache is not None and cache[0] == key:
-        return cache[1]
+        return cache[1], cache[2]
     pieces = _pack_seq(pred.xcn1lin) + _pack_seq(pred.xcn2lin)
-    if pred.order >= 3 and hasattr(pred, "xcn3lin"):
+    if st["three"]:
         pieces += _pack_seq(pred.xcn3lin)
     pieces += _pack_seq(pred.xijlin) + _pack_seq(pred.lin, last_plain=True)
     with torch.no_grad():
         flat = torch.cat([t.detach().float().reshape(-1) for t in pieces]).contiguous()
-    pred._ocn_head_cache = (key, flat)
-    return flat
+        alpha = torch.sigmoid(pred.alpha).cumprod(-1)
+        mix = torch.cat((alpha[:3].float(), pred.beta.detach().float().reshape(1))).contiguous()
+    pred.__dict__["_ocn_head_cache"] = (key, flat, mix)
+    return flat, mix
 
 
 def fused_head(pred, xcn1: Tensor, xcn2: Tensor, xcn3: Optional[Tensor], xij: Tensor) -> Tensor:
     L = _lib.lib()
     B, in_ch = xcn1.shape
-    hid, out_ch = pred.lin[0].in_features, pred.lin[-1].out_features
-    params = packed_params(pred)
-    with torch.no_grad():
-        alpha = torch.sigmoid(pred.alpha).cumprod(-1)
-        mix = torch.cat((alpha[:3].float(), pred.beta.detach().float().reshape(1))).contiguous()
+    st = _static(pred, in_ch)
+    hid, out_ch = st["hid"], st["out_ch"]
+    params, mix = packed_params(pred, in_ch)
     out = torch.empty(B, out_ch, dtype=torch.float32, device=xcn1.device)
     with torch.cuda.device(xcn1.device):
         _lib.check(L.ocn_cn_head(_lib.ptr(xcn1.contiguous()), _lib.ptr(xcn2.contiguous()),
                                  _lib.ptr(None if xcn3 is None else xcn3.contiguous()), _lib.ptr(xij.contiguous()), B,
-                                 in_ch, hid, out_ch, _flags(pred), _lib.ptr(params), params.numel(), _lib.ptr(mix),
+                                 in_ch, hid, out_ch, st["flags"], _lib.ptr(params), params.numel(), _lib.ptr(mix),
                                  _lib.ptr(out), _stream(xcn1.device)), "ocn_cn_head")
     return out
