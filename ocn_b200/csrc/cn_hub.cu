@@ -41,6 +41,7 @@ constexpr int kHubThreads = 256;
 constexpr int kHubWarps = kHubThreads / 32;
 constexpr int kShortList = 4;       // entry lists up to this length are walked by their own lane
 constexpr int kMidList = 32;        // up to this length flattened over the lanes, longer ones by the whole warp
+constexpr int kHubQueue = 64;         // queued entry lists per warp (8 bytes each)
 constexpr int kHubWindow = 4096;      // positions a warp-private counter array holds (8 KB of packed counters per warp)
 constexpr int kHubCtaWindow = 32768;  // positions per pass of the CTA-per-item variant (64 KB of packed counters per CTA)
 static_assert(kHubSeg < 65536, "16-bit walk counters per item");
@@ -287,9 +288,10 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 }
 
 // U holds 16-bit counters packed in pairs, for the positions [win_lo, win_lo + win_n) of this pass
+template <bool kWin>
 __device__ __forceinline__ void count_walk(uint32_t* U, uint32_t pos, uint32_t win_lo, uint32_t win_n) {
-    const uint32_t rel = pos - win_lo;
-    if (rel < win_n) atomicAdd(U + (rel >> 1), 1u << ((rel & 1u) << 4));
+    const uint32_t rel = kWin ? pos - win_lo : pos;  // kWin == false: one window holds every position, no test
+    if (!kWin || rel < win_n) atomicAdd(U + (rel >> 1), 1u << ((rel & 1u) << 4));
 }
 
 // ---- the walk through the shared rows ------------------------------------------------------------
@@ -301,7 +303,7 @@ __device__ __forceinline__ void count_walk(uint32_t* U, uint32_t pos, uint32_t w
 // whole warp, so that neither the many short lists nor the few long ones (54 % of the visits are in
 // lists of > 32 entries at citation2 shape) leave lanes idle.  Positions beyond the counter window are
 // handled by further passes over the items ([win_lo, win_lo + win_n) per launch).
-template <bool kCta>
+template <bool kCta, bool kWin>
 __global__ void __launch_bounds__(kHubThreads, kCta ? 3 : 6)
 k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint32_t* __restrict__ pkey,
                const int32_t* __restrict__ prun, const unsigned long long* __restrict__ prec, int64_t P,
@@ -318,6 +320,9 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
     const int uwords = (int)((((win_n + 1) >> 1) + 3) & ~3u);   // packed 16-bit counters, a multiple of 4 words
     uint32_t* s_pos = hub_smem;                                  // run -> first position (n_runs + 1 entries)
     uint32_t* U = hub_smem + rpad + (kCta ? (size_t)0 : (size_t)warp * uwords);
+    // warp-private queue of the entry lists that passed the signature test (head, length): lists are walked 32 at a
+    // time, one per lane, instead of by the few lanes of a 32-column step that happen to hold one
+    uint2* Q = reinterpret_cast<uint2*>(hub_smem + rpad + (size_t)uwords * (kCta ? 1 : kHubWarps)) + (size_t)warp * kHubQueue;
     for (int r = threadIdx.x; r <= n_runs; r += blockDim.x) s_pos[r] = (uint32_t)run_pos_off[r];
     __syncthreads();
     unsigned long long n_items = counters[0];
@@ -365,6 +370,34 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
         const int64_t stride = 32 * nw;
         auto load_col = [&](int64_t bb) -> int32_t { return (bb + lane < c1) ? ldg_i32(col + rs + bb + lane) : -1; };
         auto load_entry = [&](int32_t l) -> uint4 { return l >= 0 ? __ldg(node_index + l) : make_uint4(0u, 0u, 0u, 0u); };
+        // one queued list per lane (length 0 = none): the first kShortList entries by the lane itself, the rest of
+        // the middle lists flattened over the lanes, 32 entries at a time
+        auto drain = [&](uint2 ql) {
+            const int cnt = (int)ql.y;
+            {
+                const uint32_t* list = eval + ql.x;
+                uint32_t pos[kShortList];
+#pragma unroll
+                for (int k = 0; k < kShortList; ++k) pos[k] = k < cnt ? __ldg(list + k) : 0u;
+#pragma unroll
+                for (int k = 0; k < kShortList; ++k)
+                    if (k < cnt) count_walk<kWin>(U, pos[k], win_lo, win_n);
+            }
+            const int cm = cnt > kShortList ? cnt - kShortList : 0;
+            if (__any_sync(0xffffffffu, cm != 0)) {
+                const int incl = warp_incl_scan(cm, lane);
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                const int excl = incl - cm;
+                for (int j0 = 0; j0 < total; j0 += 32) {
+                    const int j = j0 + lane;
+                    const int s = owner_lane(excl, j);
+                    const uint32_t ehead = __shfl_sync(0xffffffffu, ql.x, s) + kShortList;
+                    const int eexcl = __shfl_sync(0xffffffffu, excl, s);
+                    if (j < total) count_walk<kWin>(U, __ldg(eval + ehead + (uint32_t)(j - eexcl)), win_lo, win_n);
+                }
+            }
+        };
+        int qn = 0;  // queued lists (warp-uniform)
         const int64_t b0 = c0 + 32 * wi;
         uint4 he_next = load_entry(load_col(b0));
         int32_t col_next = load_col(b0 + stride);
@@ -374,29 +407,17 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
             col_next = load_col(b + 2 * stride);
             const int cnt = ((he.z & act_lo) | (he.w & act_hi)) ? (int)(he.y - he.x) : 0;
             if (!__any_sync(0xffffffffu, cnt != 0)) continue;
-            const uint32_t* list = eval + he.x;
-            // short lists: every lane walks its own
+            // short and middle lists go to the queue; a full batch of 32 is walked as soon as there is one
             {
-                const int cs = cnt <= kShortList ? cnt : 0;
-                uint32_t pos[kShortList];
-#pragma unroll
-                for (int k = 0; k < kShortList; ++k) pos[k] = k < cs ? __ldg(list + k) : 0u;
-#pragma unroll
-                for (int k = 0; k < kShortList; ++k)
-                    if (k < cs) count_walk(U, pos[k], win_lo, win_n);
-            }
-            // middle lists: flattened over the lanes, 32 entries at a time
-            const int cm = (cnt > kShortList && cnt <= kMidList) ? cnt : 0;
-            if (__any_sync(0xffffffffu, cm != 0)) {
-                const int incl = warp_incl_scan(cm, lane);
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                const int excl = incl - cm;
-                for (int j0 = 0; j0 < total; j0 += 32) {
-                    const int j = j0 + lane;
-                    const int s = owner_lane(excl, j);
-                    const uint32_t ehead = __shfl_sync(0xffffffffu, he.x, s);
-                    const int eexcl = __shfl_sync(0xffffffffu, excl, s);
-                    if (j < total) count_walk(U, __ldg(eval + ehead + (uint32_t)(j - eexcl)), win_lo, win_n);
+                const bool push = cnt > 0 && cnt <= kMidList;
+                const unsigned pm = __ballot_sync(0xffffffffu, push);
+                if (push) Q[qn + __popc(pm & ((1u << lane) - 1u))] = make_uint2(he.x, (uint32_t)cnt);
+                qn += __popc(pm);
+                __syncwarp();
+                if (qn >= 32) {
+                    qn -= 32;
+                    drain(Q[qn + lane]);
+                    __syncwarp();
                 }
             }
             // long lists: the whole warp per list (ascending positions: only the window's piece is read when the
@@ -407,7 +428,7 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
                 lg &= lg - 1;
                 uint32_t e0 = __shfl_sync(0xffffffffu, he.x, sl);
                 uint32_t e1 = __shfl_sync(0xffffffffu, he.y, sl);
-                if (win_lo > 0u) {  // first entry with position >= win_lo
+                if (kWin && win_lo > 0u) {  // first entry with position >= win_lo
                     uint32_t lo = e0, hi = e1;
                     while (lo < hi) {
                         const uint32_t mid = (lo + hi) >> 1;
@@ -415,22 +436,28 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
                     }
                     e0 = lo;
                 }
-                for (uint32_t e = e0 + lane; e0 < e1; e0 += 32, e += 32) {
-                    const uint32_t pos = e < e1 ? __ldg(eval + e) : 0xffffffffu;
-                    count_walk(U, pos, win_lo, win_n);
-                    if (__any_sync(0xffffffffu, pos - win_lo >= win_n)) break;  // past the window (or the list)
+                if (kWin) {
+                    for (uint32_t e = e0 + lane; e0 < e1; e0 += 32, e += 32) {
+                        const uint32_t pos = e < e1 ? __ldg(eval + e) : 0xffffffffu;
+                        count_walk<true>(U, pos, win_lo, win_n);
+                        if (__any_sync(0xffffffffu, pos - win_lo >= win_n)) break;  // past the window (or the list)
+                    }
+                } else {
+#pragma unroll 2
+                    for (uint32_t e = e0 + lane; e < e1; e += 32) count_walk<false>(U, __ldg(eval + e), 0u, 0u);
                 }
             }
         }
+        if (qn > 0) drain(lane < qn ? Q[lane] : make_uint2(0u, 0u));
         item_sync();
         // hand the counts to the links next to m
         for (int64_t q = wi; q < c; q += nw) {
             const int r = prun[q0 + q];
             const uint32_t pb = s_pos[r], pe = s_pos[r + 1];
-            const uint32_t lo = pb > win_lo ? pb : win_lo, hi = pe < win_lo + win_n ? pe : win_lo + win_n;
+            const uint32_t lo = (kWin && pb < win_lo) ? win_lo : pb, hi = (kWin && pe > win_lo + win_n) ? win_lo + win_n : pe;
             unsigned* rec = rec32 + 2 * prec[q0 + q] + 1;
             for (uint32_t pos = lo + lane; pos < hi; pos += 32) {
-                const uint32_t rel = pos - win_lo;
+                const uint32_t rel = kWin ? pos - win_lo : pos;
                 const uint32_t u = (U[rel >> 1] >> ((rel & 1u) << 4)) & 0xffffu;
                 if (u) atomicAdd(rec + 2 * (pos - pb), u);
             }
@@ -640,8 +667,11 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
         const int64_t win = cta ? (NP < cta_win ? NP : cta_win) : NP;
         const int rpad = (int)((R + 1 + 3) & ~int64_t(3));
         const int uwords = (int)((((win + 1) >> 1) + 3) & ~int64_t(3));
-        const size_t smem = sizeof(uint32_t) * ((size_t)rpad + (size_t)uwords * (cta ? 1 : kHubWarps));
-        auto kern = cta ? k_cn_hub_count<true> : k_cn_hub_count<false>;
+        const size_t smem = sizeof(uint32_t) * ((size_t)rpad + (size_t)uwords * (cta ? 1 : kHubWarps)) +
+                            sizeof(uint2) * (size_t)kHubQueue * kHubWarps;
+        const bool windowed = NP > win;  // several passes: every visit is tested against the window
+        auto kern = cta ? (windowed ? k_cn_hub_count<true, true> : k_cn_hub_count<true, false>)
+                        : (windowed ? k_cn_hub_count<false, true> : k_cn_hub_count<false, false>);
         OCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = (int)((200u * 1024u) / smem);
         if (per_sm > (cta ? 3 : 8)) per_sm = cta ? 3 : 8;
