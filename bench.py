@@ -32,6 +32,16 @@ METRIC = "higher-order CN aggregation edges/sec (citation2 shape)"
 UNIT = "edges/s"
 
 
+# The ONE JSON line goes to the real stdout; everything else a library may print there (e.g. "NCCL version ..."
+# from the communicator init when NCCL_DEBUG is set) is diverted to stderr.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -200,7 +210,7 @@ def run_reference(a, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(a, g):
@@ -405,7 +415,7 @@ def main():
         }
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a, g, g.rowptr.cpu(), g.col.cpu())
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -48,9 +48,9 @@ static_assert(kHubSeg < 65536, "16-bit walk counters per item");
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-static int key_bits(int64_t n) {
+static int key_bits(int64_t n) {  // bits of the keys 0 .. n (n itself is the "no pair" sentinel of the pair sort)
     int b = 1;
-    while (b < 32 && (int64_t(1) << b) < n) ++b;
+    while (b < 32 && (int64_t(1) << b) <= n) ++b;
     return b;
 }
 
@@ -175,13 +175,23 @@ __device__ __forceinline__ bool is_hub_row(const int64_t* __restrict__ rowptr, i
 }
 
 // one warp per link over the first kLongRow neighbours of dst (positions by ballot rank) ...
-__global__ void k_hub_emit_pairs(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+// A link whose run has no positions in this pass (it belongs to the other class of runs) still owns its slots of
+// the pair arrays; they are filled with the sentinel row n, which sorts last and yields no work item.
+__device__ __forceinline__ bool link_in_pass(const int32_t* __restrict__ run_id, const int64_t* __restrict__ run_pos_off,
+                                             int64_t t) {
+    const int r = run_id[t] - 1;
+    return run_pos_off[r + 1] > run_pos_off[r];
+}
+
+__global__ void k_hub_emit_pairs(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
                                  const int64_t* __restrict__ dst, int64_t T, int64_t hub_d,
-                                 const int32_t* __restrict__ hub_off, uint32_t* __restrict__ pkey,
+                                 const int32_t* __restrict__ hub_off, const int32_t* __restrict__ run_id,
+                                 const int64_t* __restrict__ run_pos_off, uint32_t* __restrict__ pkey,
                                  uint32_t* __restrict__ pval) {
     const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t >= T) return;
+    const bool in_pass = link_in_pass(run_id, run_pos_off, t);
     const int64_t j = dst[t];
     const int64_t rs = rowptr[j];
     int64_t d = rowptr[j + 1] - rs;
@@ -198,7 +208,7 @@ __global__ void k_hub_emit_pairs(const int64_t* __restrict__ rowptr, const int32
         const unsigned bal = __ballot_sync(0xffffffffu, hub);
         if (hub) {
             const int64_t pos = base + __popc(bal & ((1u << lane) - 1u));
-            pkey[pos] = (uint32_t)m;
+            pkey[pos] = in_pass ? (uint32_t)m : (uint32_t)n;
             pval[pos] = (uint32_t)t;
         }
         base += __popc(bal);
@@ -208,13 +218,16 @@ __global__ void k_hub_emit_pairs(const int64_t* __restrict__ rowptr, const int32
 // ... and one CTA per link of the long-destination list for the rest (the order of a link's pairs is free:
 // its rows are distinct, and the sort by row keeps links in stream order)
 __global__ void __launch_bounds__(1024)
-k_hub_emit_pairs_long(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ dst,
-                      int64_t hub_d, const int32_t* __restrict__ hub_off, const int32_t* __restrict__ long_list,
-                      const int64_t* __restrict__ plan, uint32_t* __restrict__ pkey, uint32_t* __restrict__ pval) {
+k_hub_emit_pairs_long(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
+                      const int64_t* __restrict__ dst, int64_t hub_d, const int32_t* __restrict__ hub_off,
+                      const int32_t* __restrict__ long_list, const int64_t* __restrict__ plan,
+                      const int32_t* __restrict__ run_id, const int64_t* __restrict__ run_pos_off,
+                      uint32_t* __restrict__ pkey, uint32_t* __restrict__ pval) {
     __shared__ int s_pos;
     const int64_t n_long = plan[OCN_PLAN_LONG_COUNT];
     for (int64_t i = blockIdx.x; i < n_long; i += gridDim.x) {
         const int64_t t = long_list[i];
+        const bool in_pass = link_in_pass(run_id, run_pos_off, t);
         const int64_t j = dst[t];
         const int64_t rs = rowptr[j], d = rowptr[j + 1] - rs;
         if (threadIdx.x == 0) s_pos = 0;
@@ -226,7 +239,7 @@ k_hub_emit_pairs_long(const int64_t* __restrict__ rowptr, const int32_t* __restr
             const int32_t m = ldg_i32(col + rs + o);
             if (is_hub_row(rowptr, m, hub_d)) {
                 const int64_t pos = base + atomicAdd(&s_pos, 1);
-                pkey[pos] = (uint32_t)m;
+                pkey[pos] = in_pass ? (uint32_t)m : (uint32_t)n;
                 pval[pos] = (uint32_t)t;
             }
         }
@@ -235,7 +248,7 @@ k_hub_emit_pairs_long(const int64_t* __restrict__ rowptr, const int32_t* __restr
 }
 
 // work items (row, segment of kHubSeg columns), per-pair run and record offset
-__global__ void k_hub_items(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ run_id,
+__global__ void k_hub_items(const int64_t* __restrict__ rowptr, int64_t n, const int32_t* __restrict__ run_id,
                             const int64_t* __restrict__ rec_off, const uint32_t* __restrict__ pkey,
                             const uint32_t* __restrict__ pval, int64_t P, int32_t* __restrict__ prun,
                             unsigned long long* __restrict__ prec, uint2* __restrict__ items, int64_t max_items,
@@ -248,7 +261,7 @@ __global__ void k_hub_items(const int64_t* __restrict__ rowptr, const int32_t* _
         prun[q] = run_id[t] - 1;
         prec[q] = (unsigned long long)rec_off[t];
         const uint32_t m = pkey[q];
-        if (q == 0 || pkey[q - 1] != m) nseg = (int)((rowptr[m + 1] - rowptr[m] + kHubSeg - 1) / kHubSeg);
+        if (m < (uint32_t)n && (q == 0 || pkey[q - 1] != m)) nseg = (int)((rowptr[m + 1] - rowptr[m] + kHubSeg - 1) / kHubSeg);
     }
     // one atomic per warp: lane 0 reserves the warp's items, every head row takes its share
     int incl = nseg;
@@ -510,6 +523,7 @@ k_cn_link(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, c
         const int64_t rs_j = rowptr[j], d_j = rowptr[j + 1] - rs_j;
         const uint32_t r = (uint32_t)(run_id[t] - 1);
         const uint32_t pos_lo = (uint32_t)run_pos_off[r], pos_hi = (uint32_t)run_pos_off[r + 1];
+        if (pos_lo == pos_hi) continue;  // the run has no positions in this pass (other class of runs, or an isolated source)
         unsigned* rec = rec32 + 2 * rec_off[t];
         if (ch == 0 && lane == 0) link_lookup(node_index, eval, (uint32_t)j, r, pos_lo, pos_hi, rec, 0x80000000u);  // C1
         const int64_t oi = ch * 32 + lane;
@@ -568,23 +582,14 @@ static int hub_aux(HubAux** out) {
     return OCN_OK;
 }
 
-// called by ocn_cn_build between the zeroing of the records and the column statistics
-int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst,
-                  int64_t T, const void* plan_scratch, const int64_t* plan_dev, const int64_t* plan_host, void* hub_scratch,
-                  size_t hub_scratch_bytes, void* node_scratch, Record* records, int64_t nnz, cudaStream_t st) {
-    const int64_t hub_d = plan_host[OCN_PLAN_HUB_DEGREE];
-    const int64_t P = plan_host[OCN_PLAN_HUB_PAIRS], E = plan_host[OCN_PLAN_HUB_ENTRIES];
-    const int64_t NP = plan_host[OCN_PLAN_HUB_POSITIONS], R = plan_host[OCN_PLAN_NUM_RUNS];
-    OCN_CHECK_ARG(hub_d > 0, "ocn_cn_build: the indexed path is off in this plan");
-    OCN_CHECK_ARG(P < (int64_t(1) << 31) && E < (int64_t(1) << 31), "ocn_cn_build: indexed path limited to 2^31 pairs / entries");
-    OCN_CHECK_ARG(R <= kHubMaxRuns && NP < (int64_t(1) << 31), "ocn_cn_build: indexed path with %lld runs, %lld positions",
-                  (long long)R, (long long)NP);
-    if (NP <= 0 || E <= 0) return OCN_OK;  // no source has a neighbour: every record set is empty
-    HubLayout H = hub_layout(n, nnz, P, E, NP);
-    if (hub_scratch_bytes < H.total)
-        return fail(OCN_ENOSPACE, "ocn_cn_build: hub scratch %zu < %zu bytes", hub_scratch_bytes, H.total);
-    HubAux* aux = nullptr;
-    if (int rc = hub_aux(&aux)) return rc;
+// One pass of the indexed stage over the runs that have positions in `run_pos_off` (an exclusive prefix over ALL
+// runs in which the runs of the other class contribute nothing): inverted index, pairs, shared-row walk, per-link
+// kernel.  Records of links outside the pass are not touched.
+static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst, int64_t T,
+                    const void* plan_scratch, const int64_t* plan_dev, const int64_t* run_pos_off, int64_t hub_d, int64_t P,
+                    int64_t E, int64_t NP, int64_t R, const HubLayout& H, void* hub_scratch, void* node_scratch,
+                    Record* records, HubAux* aux, bool first_pass, cudaStream_t st) {
+    if (NP <= 0 || E <= 0) return OCN_OK;  // no source of this pass has a neighbour: its record sets are empty
     cudaStream_t sa = aux->stream;
     PlanLayout L = plan_layout(T);
     const char* pb = (const char*)plan_scratch;
@@ -594,7 +599,6 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
     const int32_t* hub_off = (const int32_t*)(pb + L.hub_off);
     const int32_t* chunk_off = (const int32_t*)(pb + L.chunk_off);
     const int32_t* long_list = (const int32_t*)(pb + L.long_list);
-    const int64_t* run_pos_off = (const int64_t*)(pb + L.run_pos_off);
     uint4* node_index = (uint4*)node_scratch;
     char* hb = (char*)hub_scratch;
     uint32_t* pkey[2] = {(uint32_t*)(hb + H.pkey[0]), (uint32_t*)(hb + H.pkey[1])};
@@ -616,14 +620,15 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
     // auxiliary stream: (shared row, link) pairs, sorted by row, and the work items
     cub::DoubleBuffer<uint32_t> dk(pkey[0], pkey[1]), dv(pval[0], pval[1]);
     if (P > 0) {
-        k_hub_emit_pairs<<<grid_for(T * 32, th), th, 0, sa>>>(rowptr, col, dst, T, hub_d, hub_off, pkey[0], pval[0]);
+        k_hub_emit_pairs<<<grid_for(T * 32, th), th, 0, sa>>>(rowptr, col, n, dst, T, hub_d, hub_off, run_id, run_pos_off,
+                                                             pkey[0], pval[0]);
         OCN_LAUNCH_CHECK();
-        k_hub_emit_pairs_long<<<sm_count() * 2, 1024, 0, sa>>>(rowptr, col, dst, hub_d, hub_off, long_list, plan_dev,
-                                                              pkey[0], pval[0]);
+        k_hub_emit_pairs_long<<<sm_count() * 2, 1024, 0, sa>>>(rowptr, col, n, dst, hub_d, hub_off, long_list, plan_dev,
+                                                              run_id, run_pos_off, pkey[0], pval[0]);
         OCN_LAUNCH_CHECK();
         size_t tb2 = H.cub_temp2_bytes;
         OCN_CUDA(cub::DeviceRadixSort::SortPairs(hb + H.cub_temp2, tb2, dk, dv, (int)P, 0, bits, sa));
-        k_hub_items<<<grid_for(P, th), th, 0, sa>>>(rowptr, run_id, rec_off, dk.Current(), dv.Current(), P, prun, prec,
+        k_hub_items<<<grid_for(P, th), th, 0, sa>>>(rowptr, n, run_id, rec_off, dk.Current(), dv.Current(), P, prun, prec,
                                                     items, H.max_items, counters);
         OCN_LAUNCH_CHECK();
     }
@@ -658,8 +663,8 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
     // caller's stream: the walk through the shared rows (needs the pairs and the items)
     OCN_CUDA(cudaStreamWaitEvent(st, aux->ev[1], 0));
     if (P > 0) {
-        // positions are counted a window at a time: one pass of warp-per-item for the usual stream; a stream with
-        // more positions (a hub source) uses the CTA-per-item variant with a CTA-wide window
+        // positions are counted a window at a time: one pass of warp-per-item for the usual stream; a pass with
+        // more positions (hub sources) uses the CTA-per-item variant with a CTA-wide window
         int64_t warp_win = kHubWindow, cta_win = kHubCtaWindow;
         if (const char* v = getenv("OCN_HUB_WINDOW")) warp_win = atoll(v) > 0 ? atoll(v) : warp_win;        // test hooks
         if (const char* v = getenv("OCN_HUB_CTA_WINDOW")) cta_win = atoll(v) > 0 ? atoll(v) : cta_win;
@@ -676,7 +681,7 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
         int per_sm = (int)((200u * 1024u) / smem);
         if (per_sm > (cta ? 3 : 8)) per_sm = cta ? 3 : 8;
         if (per_sm < 1) per_sm = 1;
-        hub_timing_record(0, st);
+        if (first_pass) hub_timing_record(0, st);
         for (int64_t w0 = 0; w0 < NP; w0 += win) {
             if (w0 > 0) OCN_CUDA(cudaMemsetAsync(counters + 1, 0, sizeof(unsigned long long), st));  // restart the item counter
             const int64_t wn = (NP - w0) < win ? (NP - w0) : win;
@@ -696,6 +701,41 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
     k_hub_entry_heads<<<grid_for(E, th), th, 0, st>>>(ek.Current(), ev.Current(), run_pos_off, (int)R, E, 0, node_index);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
+}
+
+// called by ocn_cn_build between the zeroing of the records and the column statistics.
+// Runs of heavy sources (more than kHeavyRun neighbours; ocn_cn_plan) are indexed in a pass of their own: such a
+// source alone contributes thousands of positions and millions of index entries, and in a common index every
+// shared row of the stream would walk them (measured: a 65 536-link slice with one source of 5 637 neighbours took
+// 9.2 ms instead of 1.2 ms).  In its own pass only the rows next to ITS links are walked.
+int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst,
+                  int64_t T, const void* plan_scratch, const int64_t* plan_dev, const int64_t* plan_host, void* hub_scratch,
+                  size_t hub_scratch_bytes, void* node_scratch, Record* records, int64_t nnz, cudaStream_t st) {
+    const int64_t hub_d = plan_host[OCN_PLAN_HUB_DEGREE];
+    const int64_t P = plan_host[OCN_PLAN_HUB_PAIRS], E = plan_host[OCN_PLAN_HUB_ENTRIES];
+    const int64_t NP = plan_host[OCN_PLAN_HUB_POSITIONS], R = plan_host[OCN_PLAN_NUM_RUNS];
+    const int64_t E_heavy = plan_host[OCN_PLAN_HUB_ENTRIES_HEAVY], NP_heavy = plan_host[OCN_PLAN_HUB_POSITIONS_HEAVY];
+    OCN_CHECK_ARG(hub_d > 0, "ocn_cn_build: the indexed path is off in this plan");
+    OCN_CHECK_ARG(P < (int64_t(1) << 31) && E < (int64_t(1) << 31), "ocn_cn_build: indexed path limited to 2^31 pairs / entries");
+    OCN_CHECK_ARG(R <= kHubMaxRuns && NP < (int64_t(1) << 31), "ocn_cn_build: indexed path with %lld runs, %lld positions",
+                  (long long)R, (long long)NP);
+    OCN_CHECK_ARG(E_heavy >= 0 && E_heavy <= E && NP_heavy >= 0 && NP_heavy <= NP, "ocn_cn_build: inconsistent plan");
+    if (NP <= 0 || E <= 0) return OCN_OK;  // no source has a neighbour: every record set is empty
+    HubLayout H = hub_layout(n, nnz, P, E, NP);
+    if (hub_scratch_bytes < H.total)
+        return fail(OCN_ENOSPACE, "ocn_cn_build: hub scratch %zu < %zu bytes", hub_scratch_bytes, H.total);
+    HubAux* aux = nullptr;
+    if (int rc = hub_aux(&aux)) return rc;
+    PlanLayout L = plan_layout(T);
+    const char* pb = (const char*)plan_scratch;
+    if (NP_heavy == 0)  // the usual stream: one pass over the plain prefix
+        return hub_pass(rowptr, col, n, src, dst, T, plan_scratch, plan_dev, (const int64_t*)(pb + L.run_pos_off), hub_d, P, E,
+                        NP, R, H, hub_scratch, node_scratch, records, aux, true, st);
+    if (int rc = hub_pass(rowptr, col, n, src, dst, T, plan_scratch, plan_dev, (const int64_t*)(pb + L.pos_scanN), hub_d, P,
+                          E - E_heavy, NP - NP_heavy, R, H, hub_scratch, node_scratch, records, aux, true, st))
+        return rc;
+    return hub_pass(rowptr, col, n, src, dst, T, plan_scratch, plan_dev, (const int64_t*)(pb + L.run_pos_heavy), hub_d, P,
+                    E_heavy, NP_heavy, R, H, hub_scratch, node_scratch, records, aux, false, st);
 }
 
 }  // namespace ocn

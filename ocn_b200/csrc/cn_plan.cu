@@ -7,6 +7,8 @@
 // (run, chunk of kPChunk positions of N(src), sub-list of kEdgeSub links of the run).
 #include <cub/device/device_scan.cuh>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ocn {
@@ -168,7 +170,7 @@ __global__ void k_plan_hub_decide(int order, int64_t hub_degree, int64_t* __rest
 __global__ void k_plan_units(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                              const int64_t* __restrict__ src, int64_t T, const int32_t* __restrict__ run_start,
                              const int64_t* __restrict__ cost_pre, int resident_ctas,
-                             int64_t* __restrict__ plan, int64_t* __restrict__ run_units,
+                             int64_t heavy_run, int64_t* __restrict__ plan, int64_t* __restrict__ run_units,
                              int64_t* __restrict__ run_pos_light, int64_t* __restrict__ run_pos_heavy) {
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -194,7 +196,10 @@ __global__ void k_plan_units(const int64_t* __restrict__ rowptr, const int32_t* 
         }
         if (plan[OCN_PLAN_HUB_DEGREE] > 0) {  // the hub stage lists every (key, run, position) entry
             npos = d;
-            if (lane == 0) atomicAdd((unsigned long long*)&plan[OCN_PLAN_HUB_ENTRIES], (unsigned long long)keys);
+            if (lane == 0) {
+                atomicAdd((unsigned long long*)&plan[OCN_PLAN_HUB_ENTRIES], (unsigned long long)keys);
+                if (d > heavy_run) atomicAdd((unsigned long long*)&plan[OCN_PLAN_HUB_ENTRIES_HEAVY], (unsigned long long)keys);
+            }
         }
         const long long W = unit_budget(plan[OCN_PLAN_TOTAL_COST], resident_ctas);
         const long long run_cost = cost_pre[t0 + len] - cost_pre[t0];
@@ -202,9 +207,9 @@ __global__ void k_plan_units(const int64_t* __restrict__ rowptr, const int32_t* 
     }
     if (lane == 0) {
         run_units[r] = u;
-        // positions of the stream: the runs of light sources first, those of heavy sources (long rows N(src)) last,
-        // so that the entry lists of the index end with the heavy sources' entries (cn_hub.cu)
-        const bool heavy = npos > kHeavyRun;
+        // the runs of heavy sources (long rows N(src)) get an index of their own (cn_hub.cu): two position
+        // numberings, one over the light runs and one over the heavy runs (a run of the other class has no positions)
+        const bool heavy = npos > heavy_run;
         run_pos_light[r] = heavy ? 0 : npos;
         run_pos_heavy[r] = heavy ? npos : 0;
     }
@@ -242,6 +247,7 @@ __global__ void k_plan_finish(int64_t T, int64_t batch_size, int resident_ctas, 
     plan[OCN_PLAN_HUB_PAIRS] = hub_off[T];
     const int64_t n_runs = plan[OCN_PLAN_NUM_RUNS];
     plan[OCN_PLAN_HUB_POSITIONS] = run_pos_off[n_runs] + run_pos_heavy_off[n_runs];  // 0 when the indexed path is off
+    plan[OCN_PLAN_HUB_POSITIONS_HEAVY] = run_pos_heavy_off[n_runs];
 }
 
 }  // namespace ocn
@@ -313,7 +319,9 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, hub_off, hub_off, (int)(T + 1), st));
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, chunk_off, chunk_off, (int)(T + 1), st));
     int blocks2 = (int)(((T + 2) * 32 + threads - 1) / threads);
-    k_plan_units<<<blocks2, threads, 0, st>>>(rowptr, col, src, T, run_start, cost_pre, resident_ctas, out_plan,
+    int64_t heavy_run = kHeavyRun;
+    if (const char* v = getenv("OCN_HUB_HEAVY_RUN")) heavy_run = atoll(v) > 0 ? atoll(v) : heavy_run;  // test hook
+    k_plan_units<<<blocks2, threads, 0, st>>>(rowptr, col, src, T, run_start, cost_pre, resident_ctas, heavy_run, out_plan,
                                               run_unit_off, pos_scanN, run_pos_heavy);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, run_unit_off, run_unit_off, (int)(T + 2), st));

@@ -109,7 +109,9 @@ constexpr int kLinkCost = 64;  // fixed cost added to every link so that empty l
 #define OCN_PLAN_TOTAL_COST 6
 #define OCN_PLAN_USE_DIRECT 7  /* orders <= 2 only: 1 = table-free kernel (short runs), 0 = table kernel */
 #define OCN_PLAN_LONG_COUNT 12 /* entries of the long-destination list */
-constexpr int kHeavyRun = 64;      // a run whose source has more neighbours than this is "heavy": its positions are numbered last
+#define OCN_PLAN_HUB_ENTRIES_HEAVY 13   /* the part of OCN_PLAN_HUB_ENTRIES that belongs to runs of heavy sources */
+#define OCN_PLAN_HUB_POSITIONS_HEAVY 14 /* the part of OCN_PLAN_HUB_POSITIONS that belongs to runs of heavy sources */
+constexpr int kHeavyRun = 1024;    // a run whose source has more neighbours than this is "heavy": indexed in a pass of its own
 constexpr int kLongRow = 256;      // neighbours of dst a single warp walks in the plan / pair kernels; the rest goes to a CTA
 constexpr int kHubMaxRuns = 2048;       // indexed path: run -> first position table in shared memory
 

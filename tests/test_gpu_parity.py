@@ -379,6 +379,33 @@ def test_hub_stage_position_windows(monkeypatch, warp_win, cta_win):
         _assert_rows_equal(got[k], ref[k])
 
 
+@pytest.mark.parametrize("name,B,kind", [("tiny_dense", 200, "mixed"), ("cora", 1500, "mixed"), ("citation2_s", 4096, "stream")])
+@pytest.mark.parametrize("heavy_run", [1, 6, 20])
+def test_hub_stage_heavy_sources_get_their_own_pass(monkeypatch, name, B, kind, heavy_run):
+    """Runs whose source has more than `heavy_run` neighbours are indexed in a second pass (forced on small graphs
+    through the plan's test hook; 1024 in production): every record must still equal the oracle's, for streams
+    that are all light, mixed, and (heavy_run = 1) almost all heavy."""
+    g = GRAPHS[name]()
+    G, A = _graph(g), _sp(g)
+    e = g.query_edges(B, kind)
+    ref = R.get_cn(A, e, 3)
+    monkeypatch.setenv("OCN_HUB_HEAVY_RUN", str(heavy_run))
+    sess = ob.CNSession(G, e.to(DEV), 512, 3, hub_degree=3)
+    assert sess.hub_degree == 3
+    deg = (g.rowptr[1:] - g.rowptr[:-1])
+    if bool((deg[e[0]] > heavy_run).any()):
+        assert sess.plan_host[14] > 0 and sess.plan_host[13] > 0, "expected a heavy pass"
+    sess.build(3, True, with_stats=False)
+    for k in range(3):
+        _assert_rows_equal(sess.extract(k + 1), ref[k])
+    # and with the CTA-wide counter window forced small in the same run (several window launches per pass)
+    monkeypatch.setenv("OCN_HUB_WINDOW", "64")
+    monkeypatch.setenv("OCN_HUB_CTA_WINDOW", "160")
+    got = ob.get_cn(G, e.to(DEV), 3, True, hub_degree=3, batch_size=512)
+    for k in range(3):
+        _assert_rows_equal(got[k], ref[k])
+
+
 def test_hub_stage_matches_table_kernel_at_scale():
     """citation2 shape at 5 % size, 16 batches of the evaluation stream: hub stage on (automatic
     threshold and a low one) == hub stage off, bit for bit, for every record."""
