@@ -13,22 +13,19 @@ namespace ocn {
 
 enum { kSum = 0, kMean = 1, kMax = 2, kGcnSelf = 3, kGcnNoSelf = 4 };
 
-// MODE is a compile-time constant (the five modes share the loop, not the branches); kExact: the feature row is
-// covered exactly by lpr lanes x VPL float4 (nvec == lpr * VPL, e.g. every power-of-two width), no bounds tests.
-template <int VPL, int MODE, bool kExact>
+template <int VPL>
 __global__ void __launch_bounds__(256)
 k_spmm(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
-       const float* __restrict__ norm, int64_t num_rows, const float* __restrict__ x, int nvec, int lpr,
+       const float* __restrict__ norm, int64_t num_rows, const float* __restrict__ x, int nvec, int lpr, int mode,
        float* __restrict__ out) {
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int lane = lane_id();
     const int rpw = 32 / lpr, grp = lane / lpr, sub = lane - grp * lpr;
     const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
-    constexpr bool is_max = MODE == kMax;
-    constexpr int kGather = 2;  // neighbour rows per lane group requested before any is consumed
-    // Software pipeline: the row pointers of the row after next and the first 32 columns of the next row (or the
-    // next 32 columns of a long row) are in flight while the current neighbour rows are gathered, so a row costs
+    const bool is_max = mode == kMax;
+    // Software pipeline over the rows of this warp: the row pointers of the row after next and the first 32
+    // columns of the next row are in flight while the current row's neighbour rows are gathered, so a row costs
     // one exposed memory latency (the gather) instead of three dependent ones (rowptr -> col -> x).
     auto load_ptr = [&](int64_t rr, int64_t& s, int64_t& e) {
         s = 0; e = 0;
@@ -47,20 +44,23 @@ k_spmm(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, cons
     for (int64_t r = warp; r < num_rows; r += nwarps) {
         int64_t s3, e3;
         load_ptr(r + 2 * nwarps, s3, e3);
+        int32_t c2;
+        float w2;
+        load_cols(s2, e2, c2, w2);
         const int64_t s = s1, e = e1;
-        const float nr = (MODE >= kGcnSelf) ? norm[r] : 1.0f;
+        const float nr = (mode >= kGcnSelf) ? norm[r] : 1.0f;
         float4 acc[VPL];
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
             acc[v] = is_max ? make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX) : make_float4(0.f, 0.f, 0.f, 0.f);
-        int32_t c = c1;
-        float w = w1;
         for (int64_t base = s; base < e; base += 32) {
-            // prefetch: the next 32 columns of this row, or the first 32 of the next row
-            int32_t cn;
-            float wn;
-            if (base + 32 < e) load_cols(base + 32, e, cn, wn); else load_cols(s2, e2, cn, wn);
+            int32_t c = c1;
+            float w = w1;
+            if (base != s) load_cols(base, e, c, w);
             const int cnt = (int)((e - base) < 32 ? (e - base) : 32);
+            // kGather neighbour rows per lane group are requested before any of them is consumed: a lane keeps
+            // kGather * VPL independent 16-byte loads in flight (one per iteration left the gather latency-bound)
+            constexpr int kGather = 2;
             for (int q = 0; q < cnt; q += rpw * kGather) {
                 float4 xv[kGather][VPL];
                 float ww[kGather], pre[kGather];
@@ -74,12 +74,13 @@ k_spmm(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, cons
                     ww[u] = __shfl_sync(0xffffffffu, w, srcl);
                     pre[u] = 1.0f;
                     if (on[u]) {
-                        if (MODE == kGcnSelf) pre[u] = __ldg(norm + cc);
-                        else if (MODE == kGcnNoSelf) ww[u] = ww[u] * (nr * __ldg(norm + cc));
-                        const float4* __restrict__ xr = x4 + (int64_t)cc * nvec + sub;
+                        if (mode == kGcnSelf) pre[u] = norm[cc];
+                        else if (mode == kGcnNoSelf) ww[u] = ww[u] * (nr * norm[cc]);
 #pragma unroll
-                        for (int v = 0; v < VPL; ++v)
-                            xv[u][v] = (kExact || sub + v * lpr < nvec) ? __ldg(xr + v * lpr) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int v = 0; v < VPL; ++v) {
+                            const int k = sub + v * lpr;
+                            xv[u][v] = (k < nvec) ? __ldg(x4 + (int64_t)cc * nvec + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
                     }
                 }
 #pragma unroll
@@ -87,9 +88,9 @@ k_spmm(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, cons
                     if (!on[u]) continue;
 #pragma unroll
                     for (int v = 0; v < VPL; ++v) {
-                        if (!kExact && sub + v * lpr >= nvec) continue;
+                        if (sub + v * lpr >= nvec) continue;
                         float4 t = xv[u][v];
-                        if (MODE == kGcnSelf) { t.x *= pre[u]; t.y *= pre[u]; t.z *= pre[u]; t.w *= pre[u]; }
+                        if (mode == kGcnSelf) { t.x *= pre[u]; t.y *= pre[u]; t.z *= pre[u]; t.w *= pre[u]; }
                         if (is_max) {
                             acc[v].x = fmaxf(acc[v].x, ww[u] * t.x); acc[v].y = fmaxf(acc[v].y, ww[u] * t.y);
                             acc[v].z = fmaxf(acc[v].z, ww[u] * t.z); acc[v].w = fmaxf(acc[v].w, ww[u] * t.w);
@@ -100,10 +101,7 @@ k_spmm(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, cons
                     }
                 }
             }
-            c = cn;
-            w = wn;
         }
-        if (e <= s) load_cols(s2, e2, c, w);  // empty row: nothing was prefetched inside the loop
         for (int o = lpr; o < 32; o <<= 1) {
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
@@ -121,13 +119,13 @@ k_spmm(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, cons
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
                 const int k = sub + v * lpr;
-                if (kExact || k < nvec) {
+                if (k < nvec) {
                     float4 a = acc[v];
                     if (is_max && e == s) a = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (MODE == kMean) {
+                    if (mode == kMean) {
                         const float inv = 1.0f / (float)((e - s) > 0 ? (e - s) : 1);
                         a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
-                    } else if (MODE == kGcnSelf) {
+                    } else if (mode == kGcnSelf) {
                         float4 xs = __ldg(x4 + r * nvec + k);
                         a.x = nr * (a.x + nr * xs.x); a.y = nr * (a.y + nr * xs.y);
                         a.z = nr * (a.z + nr * xs.z); a.w = nr * (a.w + nr * xs.w);
@@ -136,7 +134,7 @@ k_spmm(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, cons
                 }
             }
         }
-        s1 = s2; e1 = e2; c1 = c; w1 = w;
+        s1 = s2; e1 = e2; c1 = c2; w1 = w2;
         s2 = s3; e2 = e3;
     }
 }
@@ -231,54 +229,25 @@ __global__ void k_gcn_norm(const int64_t* __restrict__ rowptr, const float* __re
     }
 }
 
-template <int VPL, int MODE, bool kExact>
-static int launch_spmm_t(const int64_t* rowptr, const int32_t* col, const float* val, const float* norm, int64_t num_rows,
-                         const float* x, int nvec, int lpr, float* out, cudaStream_t st) {
-    // several waves of CTAs (about 4x the resident set), rows dealt round-robin over all warps: with power-law rows
-    // a single resident wave ends in a long tail (measured: 4.2 ms instead of 3.7 ms at citation2 shape, F = 32)
-    const int64_t want = (num_rows + 7) / 8;
-    const int64_t cap = (int64_t)sm_count() * 16;
-    const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-    k_spmm<VPL, MODE, kExact><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, nvec, lpr, out);
-    OCN_LAUNCH_CHECK();
-    return OCN_OK;
-}
-
-template <int VPL, bool kExact>
-static int launch_spmm_m(int mode, const int64_t* rowptr, const int32_t* col, const float* val, const float* norm,
-                         int64_t num_rows, const float* x, int nvec, int lpr, float* out, cudaStream_t st) {
-    switch (mode) {
-        case kSum: return launch_spmm_t<VPL, kSum, kExact>(rowptr, col, val, norm, num_rows, x, nvec, lpr, out, st);
-        case kMean: return launch_spmm_t<VPL, kMean, kExact>(rowptr, col, val, norm, num_rows, x, nvec, lpr, out, st);
-        case kMax: return launch_spmm_t<VPL, kMax, kExact>(rowptr, col, val, norm, num_rows, x, nvec, lpr, out, st);
-        case kGcnSelf: return launch_spmm_t<VPL, kGcnSelf, kExact>(rowptr, col, val, norm, num_rows, x, nvec, lpr, out, st);
-        default: return launch_spmm_t<VPL, kGcnNoSelf, kExact>(rowptr, col, val, norm, num_rows, x, nvec, lpr, out, st);
-    }
-}
-
 static int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* val, const float* norm,
                        int64_t num_rows, const float* x, int64_t feat, int mode, float* out, cudaStream_t st) {
+    int64_t want = (num_rows + 7) / 8;
+    int64_t cap = (int64_t)sm_count() * 16;
+    const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
     if (feat % 4 != 0 || feat > 1024) {
-        int64_t want = (num_rows + 7) / 8;
-        int64_t cap = (int64_t)sm_count() * 16;
-        const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
         k_spmm_scalar<<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, feat, mode, out);
-        OCN_LAUNCH_CHECK();
-        return OCN_OK;
+    } else {
+        const int nvec = (int)(feat / 4);
+        int lpr = 1;
+        while (lpr < nvec && lpr < 32) lpr <<= 1;
+        const int vpl = (nvec + 31) / 32;
+        if (vpl <= 1) k_spmm<1><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, nvec, lpr, mode, out);
+        else if (vpl <= 2) k_spmm<2><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, nvec, lpr, mode, out);
+        else if (vpl <= 4) k_spmm<4><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, nvec, lpr, mode, out);
+        else k_spmm<8><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, nvec, lpr, mode, out);
     }
-    const int nvec = (int)(feat / 4);
-    int lpr = 1;
-    while (lpr < nvec && lpr < 32) lpr <<= 1;
-    const int vpl = (nvec + 31) / 32;
-    const bool exact = nvec == lpr * vpl;
-#define OCN_SPMM(V)                                                                                          \
-    (exact ? launch_spmm_m<V, true>(mode, rowptr, col, val, norm, num_rows, x, nvec, lpr, out, st)          \
-           : launch_spmm_m<V, false>(mode, rowptr, col, val, norm, num_rows, x, nvec, lpr, out, st))
-    if (vpl <= 1) return OCN_SPMM(1);
-    if (vpl <= 2) return OCN_SPMM(2);
-    if (vpl <= 4) return OCN_SPMM(4);
-    return OCN_SPMM(8);
-#undef OCN_SPMM
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
 }
 
 }  // namespace ocn
