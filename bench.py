@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hub", type=int, default=0, help="hub_degree of the indexed order-3 path: 0 auto, -1 off (per-run tables)")
     ap.add_argument("--no-plan-stream", action="store_true", help="plan on the main stream (no overlap with the previous step)")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="sessions in flight: consecutive steps alternate between this many CUDA streams, so the "
+                         "latency-bound stages of one step (sorts, small kernels) overlap the walks of the other")
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed device steps (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -279,12 +282,23 @@ def main():
     # while the main stream is still executing the previous step
     plan_stream = None if a.no_plan_stream else torch.cuda.Stream(device=dev)
 
+    streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, a.streams))]
+
+    def fork():  # the work streams start after everything already queued on the default stream ...
+        for st in streams:
+            st.wait_stream(torch.cuda.current_stream())
+
+    def join():  # ... and the default stream (where the timing events are recorded) waits for all of them
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
+
     def step_device(s):
-        e = e_rank[:, s * T:(s + 1) * T]
-        sess = ob.CNSession(G, e, a.batch, a.order, a.hub, plan_stream=plan_stream).build(a.order, True)
-        sess.stats(5, 0.0, ip3, 0)
-        out = sess.aggregate(x, 5, 0.0, ip3)
-        sess.release()
+        with torch.cuda.stream(streams[s % len(streams)]):
+            e = e_rank[:, s * T:(s + 1) * T]
+            sess = ob.CNSession(G, e, a.batch, a.order, a.hub, plan_stream=plan_stream).build(a.order, True)
+            sess.stats(5, 0.0, ip3, 0)
+            out = sess.aggregate(x, 5, 0.0, ip3)
+            sess.release()
         return out
 
     out_host = [torch.empty(world * T, dtype=torch.float32).pin_memory() for _ in range(nsteps)]
@@ -292,22 +306,22 @@ def main():
     def step_e2e(s):
         with torch.cuda.stream(plan_stream if plan_stream is not None else torch.cuda.current_stream()):
             e = e_host[:, s * T:(s + 1) * T].to(dev, non_blocking=True)
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.stream(streams[s % len(streams)]):
             sess = ob.CNSession(G, e, a.batch, a.order, a.hub, plan_stream=plan_stream).build(a.order, True)
             if a.order >= 3:
                 out = pred(x, G, sess, None, None, e)
             else:
                 out = pred(x, G, sess, None, e)
-        scores = out.squeeze(-1)
-        if world > 1:
-            import torch.distributed as dist
-            allsc = torch.empty(world * T, dtype=scores.dtype, device=dev)
-            dist.all_gather_into_tensor(allsc, scores.contiguous())
-            scores = allsc
-        # device -> host read of the step's result: asynchronous copy into pinned memory (an evaluation loop
-        # collects the scores of every batch and ranks them at the end); the timed region ends with a full sync
-        n_out = scores.numel() if rank == 0 else 1
-        out_host[s][:n_out].copy_(scores[:n_out], non_blocking=True)
+            scores = out.squeeze(-1)
+            if world > 1:
+                import torch.distributed as dist
+                allsc = torch.empty(world * T, dtype=scores.dtype, device=dev)
+                dist.all_gather_into_tensor(allsc, scores.contiguous())
+                scores = allsc
+            # device -> host read of the step's result: asynchronous copy into pinned memory (an evaluation loop
+            # collects the scores of every batch and ranks them at the end); the timed region ends with a full sync
+            n_out = scores.numel() if rank == 0 else 1
+            out_host[s][:n_out].copy_(scores[:n_out], non_blocking=True)
         return out_host[s]
 
     def barrier():
@@ -334,8 +348,10 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ev0.record()
+        fork()
         for s in range(a.warmup, nsteps):
             fn(s)
+        join()
         ev1.record()
         barrier()
         if profile:

@@ -256,15 +256,17 @@ class CNSession:
 
 def _hub_workspace(g: Graph, nbytes: int):
     """Scratch of the hub stage, kept with the graph: a byte buffer that only grows and the 16-byte-per-node
-    key index (all zero between calls; ocn_cn_build restores it).  Calls on one graph are ordered by the stream."""
-    buf = g._ws.get("hub")
+    key index (all zero between calls; ocn_cn_build restores it).  Calls on one stream are ordered by the stream;
+    every stream has its own pair of buffers, so that two sessions may be in flight on two streams."""
+    sid = torch.cuda.current_stream(g.device).cuda_stream  # one workspace per stream: sessions on different streams overlap
+    buf = g._ws.get(("hub", sid))
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=g.device)
-        g._ws["hub"] = buf
-    node = g._ws.get("hub_node")
+        g._ws[("hub", sid)] = buf
+    node = g._ws.get(("hub_node", sid))
     if node is None:
         node = torch.zeros((g.n, 4), dtype=torch.int32, device=g.device)
-        g._ws["hub_node"] = node
+        g._ws[("hub_node", sid)] = node
     return buf, node
 
 
@@ -272,7 +274,7 @@ def _borrow_colstat(g: Graph, nbytes: int) -> Tensor:
     """A zeroed buffer for the per-batch column statistics.  Buffers handed back by
     ``CNSession.release`` (which re-zeroes exactly the touched entries) are reused, so a steady
     stream of sessions does not pay a multi-GB memset per call."""
-    pool = g._ws.setdefault("colstat", [])
+    pool = g._ws.setdefault(("colstat", torch.cuda.current_stream(g.device).cuda_stream), [])
     for k, buf in enumerate(pool):
         if buf.numel() >= nbytes:
             pool.pop(k)
@@ -281,7 +283,8 @@ def _borrow_colstat(g: Graph, nbytes: int) -> Tensor:
 
 
 def _return_colstat(g: Graph, buf: Tensor):
-    pool = g._ws.setdefault("colstat", [])
+    # the pool is per stream: the re-zeroing enqueued by release() is ordered before the next borrower's kernels
+    pool = g._ws.setdefault(("colstat", torch.cuda.current_stream(g.device).cuda_stream), [])
     if len(pool) < 2:
         pool.append(buf)
 

@@ -30,7 +30,9 @@
 
 #include <stdlib.h>
 
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -566,14 +568,13 @@ struct HubAux {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 static std::mutex g_aux_mutex;
-static HubAux g_aux[64];
+static std::map<std::pair<int, cudaStream_t>, HubAux> g_aux;  // one auxiliary stream per (device, caller stream)
 
-static int hub_aux(HubAux** out) {
+static int hub_aux(cudaStream_t caller, HubAux** out) {
     int dev = 0;
     OCN_CUDA(cudaGetDevice(&dev));
-    OCN_CHECK_ARG(dev >= 0 && dev < 64, "ocn_cn_build: device ordinal %d", dev);
     std::lock_guard<std::mutex> lock(g_aux_mutex);
-    HubAux& a = g_aux[dev];
+    HubAux& a = g_aux[std::make_pair(dev, caller)];  // calls on different caller streams (two sessions in flight) do not share one
     if (a.stream == nullptr) {
         OCN_CUDA(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
         for (int k = 0; k < 4; ++k) OCN_CUDA(cudaEventCreateWithFlags(&a.ev[k], cudaEventDisableTiming));
@@ -725,7 +726,7 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
     if (hub_scratch_bytes < H.total)
         return fail(OCN_ENOSPACE, "ocn_cn_build: hub scratch %zu < %zu bytes", hub_scratch_bytes, H.total);
     HubAux* aux = nullptr;
-    if (int rc = hub_aux(&aux)) return rc;
+    if (int rc = hub_aux(st, &aux)) return rc;
     PlanLayout L = plan_layout(T);
     const char* pb = (const char*)plan_scratch;
     if (NP_heavy == 0)  // the usual stream: one pass over the plain prefix
