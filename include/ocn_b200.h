@@ -70,15 +70,18 @@ int ocn_graph_build_fill(const void* scratch, int64_t num_edges, int symmetric, 
  * entry survives while an unmasked list edge still maps onto it -- the result equals a rebuild from the
  * remaining list.  dec is an int32[nnz] work array, all zero on entry and on return of fill.
  * count: out_rowptr[n+1] of the masked graph, out_info[0] = its nnz, out_info[1] = masked links not found in
- * the graph; fill: out_col int32[nnz'] (and out_mult).  fill must follow count (it restores dec). */
-size_t ocn_graph_mask_bytes(int64_t n);
-int ocn_graph_mask_count(const int64_t* rowptr, const int32_t* col, const int32_t* mult, int64_t n,
+ * the graph; fill: out_col int32[nnz'] (and out_mult).  fill must follow count with the same scratch (count
+ * leaves the sorted positions of the dead entries there; fill restores dec).  The survivors move in one flat
+ * coalesced copy: entry p goes to p - #{dead positions < p}. */
+size_t ocn_graph_mask_bytes(int64_t n, int64_t num_masked);
+int ocn_graph_mask_count(const int64_t* rowptr, const int32_t* col, const int32_t* mult, int64_t n, int64_t nnz,
                          const int64_t* src, const int64_t* dst, int64_t num_masked, int symmetric,
                          int32_t* dec, void* scratch, size_t scratch_bytes,
                          int64_t* out_rowptr, int64_t* out_info, void* stream);
-int ocn_graph_mask_fill(const int64_t* rowptr, const int32_t* col, const int32_t* mult, int64_t n,
+int ocn_graph_mask_fill(const int64_t* rowptr, const int32_t* col, const int32_t* mult, int64_t n, int64_t nnz,
                         const int64_t* src, const int64_t* dst, int64_t num_masked, int symmetric,
-                        int32_t* dec, const int64_t* out_rowptr, int32_t* out_col, int32_t* out_mult, void* stream);
+                        int32_t* dec, const void* scratch /* as left by count */,
+                        int32_t* out_col, int32_t* out_mult, void* stream);
 
 /* ---- piece 1: generic per-target-edge row intersection ----------------------------------
  * adjoverlap(adj1, adj2, tarei) with calresadj=False (utils.py:248-285 -> spmoverlap_

@@ -13,9 +13,9 @@
 // * ocn_graph_mask_*: the per-batch masked adjacency WITHOUT a sort.  Every masked link decrements the
 //   multiplicity of its (two) entries -- a binary search in one row each -- an entry survives while some
 //   unmasked list edge still maps onto it (exactly what rebuilding from the remaining list yields, also
-//   when the list holds duplicates or both directions of a link); rows are compacted by one warp each.
-//   Traffic: one streaming pass over col/mult (read) and the new col (write) instead of ~6 sort passes
-//   over 16-byte pairs.
+//   when the list holds duplicates or both directions of a link); the few dead positions are sorted and
+//   the survivors move in one flat coalesced copy.  Traffic: one streaming pass over col/mult/dec (read)
+//   and the new col/mult (write) instead of ~6 sort passes over 16-byte pairs.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
 #include <cub/device/device_scan.cuh>
@@ -106,6 +106,31 @@ __global__ void k_graph_fill(const unsigned long long* __restrict__ uniq, const 
 }
 
 // ---- per-batch masking ---------------------------------------------------------------------------
+// The masked adjacency is the full one minus a FEW dead entries (at most two per masked link), so it is built by
+// a flat, fully coalesced copy: the dead entry positions are collected while the multiplicities are decremented,
+// sorted (a few thousand keys), and every surviving entry p moves to p - #{dead positions < p}; the new row
+// pointers are the old ones minus the same count.  No per-row work, no scan over the entries.
+struct MaskLayout {
+    size_t rem_a, rem_b, counter, cub_temp, cub_bytes, total;
+    int64_t cap;
+};
+
+static MaskLayout mask_layout(int64_t num_masked) {
+    MaskLayout L;
+    L.cap = 2 * (num_masked > 0 ? num_masked : 0) + 1;
+    size_t off = 0;
+    L.rem_a = off;   off += align256(sizeof(int64_t) * (size_t)L.cap);
+    L.rem_b = off;   off += align256(sizeof(int64_t) * (size_t)L.cap);
+    L.counter = off; off += 256;
+    size_t b = 0;
+    cub::DoubleBuffer<int64_t> db(nullptr, nullptr);
+    cub::DeviceRadixSort::SortKeys(nullptr, b, db, (int)L.cap, 0, 64);
+    L.cub_bytes = b + 256;
+    L.cub_temp = off; off += align256(L.cub_bytes);
+    L.total = off;
+    return L;
+}
+
 __device__ __forceinline__ int64_t entry_of(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                             int64_t u, int64_t v) {
     int64_t lo = rowptr[u], hi = rowptr[u + 1];
@@ -117,60 +142,105 @@ __device__ __forceinline__ int64_t entry_of(const int64_t* __restrict__ rowptr, 
     return (lo < end && __ldg(col + lo) == (int32_t)v) ? lo : -1;
 }
 
+__global__ void k_mask_init(int64_t* __restrict__ rem, int64_t cap, int64_t nnz, unsigned long long* __restrict__ counter) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x) rem[i] = nnz;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0ull;
+}
+
+// kReset == false: dec[p]++ for the (two) entries of every masked link; the decrement that uses up an entry's
+// multiplicity records its position as dead.  kReset == true: dec back to zero.
 template <bool kReset>
-__global__ void k_mask_mark(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
-                            const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t M, int symmetric,
-                            int32_t* __restrict__ dec, int64_t* __restrict__ info) {
+__global__ void k_mask_mark(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                            const int32_t* __restrict__ mult, int64_t n, const int64_t* __restrict__ src,
+                            const int64_t* __restrict__ dst, int64_t M, int symmetric, int32_t* __restrict__ dec,
+                            int64_t* __restrict__ rem, unsigned long long* __restrict__ counter, int64_t* __restrict__ info) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t u = src[t], v = dst[t];
         if (u < 0 || u >= n || v < 0 || v >= n) {
             if (!kReset) atomicAdd(reinterpret_cast<unsigned long long*>(info + 1), 1ull);
             continue;
         }
-        const int64_t p = entry_of(rowptr, col, u, v);
-        if (p >= 0) { if (kReset) dec[p] = 0; else atomicAdd(dec + p, 1); }
-        else if (!kReset) atomicAdd(reinterpret_cast<unsigned long long*>(info + 1), 1ull);
-        if (symmetric) {
-            const int64_t q = entry_of(rowptr, col, v, u);
-            if (q >= 0) { if (kReset) dec[q] = 0; else atomicAdd(dec + q, 1); }
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            if (side == 1 && !symmetric) break;
+            const int64_t p = side == 0 ? entry_of(rowptr, col, u, v) : entry_of(rowptr, col, v, u);
+            if (p < 0) {
+                if (!kReset && side == 0) atomicAdd(reinterpret_cast<unsigned long long*>(info + 1), 1ull);
+                continue;
+            }
+            if (kReset) {
+                dec[p] = 0;
+            } else {
+                const int32_t old = atomicAdd(dec + p, 1);
+                if (old + 1 == (mult ? __ldg(mult + p) : 1)) rem[atomicAdd(counter, 1ull)] = p;
+            }
         }
     }
 }
 
-// one warp per row: survivors = entries whose multiplicity exceeds the number of masked links on them
-template <bool kFill>
+// number of dead positions < key (the list is ascending and padded with the sentinel nnz)
+__device__ __forceinline__ int64_t dead_before(const int64_t* __restrict__ rem, int64_t cap, int64_t key) {
+    int64_t lo = 0, hi = cap;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(rem + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void k_mask_rowptr(const int64_t* __restrict__ rowptr, int64_t n, const int64_t* __restrict__ rem, int64_t cap,
+                              int64_t* __restrict__ out_rowptr, int64_t* __restrict__ info) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = rowptr[r];
+        const int64_t v = s - dead_before(rem, cap, s);
+        out_rowptr[r] = v;
+        if (r == n) info[0] = v;
+    }
+}
+
+constexpr int kMaskChunk = 4096;  // entries per CTA of the flat copy
+
 __global__ void __launch_bounds__(256)
-k_mask_rows(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ mult,
-            const int32_t* __restrict__ dec, int64_t n, int64_t* __restrict__ out_rowptr, int32_t* __restrict__ out_col,
-            int32_t* __restrict__ out_mult) {
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const int lane = lane_id();
-    for (int64_t r = warp; r < n; r += nwarps) {
-        const int64_t s = rowptr[r], e = rowptr[r + 1];
-        int64_t w = kFill ? out_rowptr[r] : 0;
-        for (int64_t b = s; b < e; b += 32) {
-            const int64_t o = b + lane;
-            int32_t left = 0, c = 0;
-            if (o < e) {
-                left = (mult ? __ldg(mult + o) : 1) - __ldg(dec + o);
-                c = ldg_i32(col + o);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, left > 0);
-            if (kFill && left > 0) {
-                const int64_t at = w + __popc(m & ((1u << lane) - 1u));
-                out_col[at] = c;
-                if (out_mult) out_mult[at] = left;
-            }
-            w += __popc(m);
+k_mask_copy(const int32_t* __restrict__ col, const int32_t* __restrict__ mult, const int32_t* __restrict__ dec, int64_t nnz,
+            const int64_t* __restrict__ rem, int64_t cap, int32_t* __restrict__ out_col, int32_t* __restrict__ out_mult) {
+    __shared__ int64_t s_base, s_cnt;
+    __shared__ int64_t s_dead[64];
+    for (int64_t p0 = (int64_t)blockIdx.x * kMaskChunk; p0 < nnz; p0 += (int64_t)gridDim.x * kMaskChunk) {
+        const int64_t p1 = (p0 + kMaskChunk < nnz) ? p0 + kMaskChunk : nnz;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_base = dead_before(rem, cap, p0);
+            s_cnt = dead_before(rem, cap, p1) - s_base;
         }
-        if (!kFill && lane == 0) out_rowptr[r] = w;
+        __syncthreads();
+        const int64_t base = s_base, cnt = s_cnt;
+        if (cnt > 0 && cnt <= 64 && (int64_t)threadIdx.x < cnt) s_dead[threadIdx.x] = rem[base + threadIdx.x];
+        __syncthreads();
+        for (int64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+            int64_t shift = base;
+            bool dead = false;
+            if (cnt > 64) {  // many dead entries in one chunk (a masked hub): search the list
+                shift = dead_before(rem, cap, p);
+                dead = shift < cap && __ldg(rem + shift) == p;
+            } else {
+                for (int k = 0; k < (int)cnt; ++k) {
+                    const int64_t q = s_dead[k];
+                    shift += q < p;
+                    dead |= q == p;
+                }
+            }
+            if (!dead) {
+                out_col[p - shift] = ldg_i32(col + p);
+                if (out_mult) out_mult[p - shift] = (mult ? __ldg(mult + p) : 1) - __ldg(dec + p);
+            }
+        }
     }
-    if (!kFill && warp == 0 && lane == 0) out_rowptr[n] = 0;
 }
 
-__global__ void k_mask_info(const int64_t* __restrict__ out_rowptr, int64_t n, int64_t* __restrict__ info) {
-    info[0] = out_rowptr[n];
+static int nnz_bits(int64_t nnz) {  // bits of the keys 0 .. nnz (nnz itself is the padding sentinel)
+    int b = 1;
+    while (b < 63 && (int64_t(1) << b) <= nnz) ++b;
+    return b;
 }
 
 static int grid_for(int64_t items, int per_block) {
@@ -234,48 +304,58 @@ int ocn_graph_build_fill(const void* scratch, int64_t num_edges, int symmetric, 
     return OCN_OK;
 }
 
-size_t ocn_graph_mask_bytes(int64_t n) {
-    size_t b = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, b, (int64_t*)nullptr, (int64_t*)nullptr, (int)(n + 1));
-    return align256(b + 256);
+size_t ocn_graph_mask_bytes(int64_t n, int64_t num_masked) {
+    (void)n;
+    return mask_layout(num_masked).total;
 }
 
-int ocn_graph_mask_count(const int64_t* rowptr, const int32_t* col, const int32_t* mult, int64_t n, const int64_t* src,
-                         const int64_t* dst, int64_t num_masked, int symmetric, int32_t* dec, void* scratch,
-                         size_t scratch_bytes, int64_t* out_rowptr, int64_t* out_info, void* stream) {
-    OCN_CHECK_ARG(rowptr && col && dec && scratch && out_rowptr && out_info, "ocn_graph_mask_count: null pointer");
-    OCN_CHECK_ARG(n > 0 && num_masked >= 0 && (num_masked == 0 || (src && dst)), "ocn_graph_mask_count: bad arguments");
-    OCN_CHECK_ARG(scratch_bytes >= ocn_graph_mask_bytes(n), "ocn_graph_mask_count: scratch too small");
+int ocn_graph_mask_count(const int64_t* rowptr, const int32_t* col, const int32_t* mult, int64_t n, int64_t nnz,
+                         const int64_t* src, const int64_t* dst, int64_t num_masked, int symmetric, int32_t* dec,
+                         void* scratch, size_t scratch_bytes, int64_t* out_rowptr, int64_t* out_info, void* stream) {
+    OCN_CHECK_ARG(rowptr && dec && scratch && out_rowptr && out_info && (col || nnz == 0), "ocn_graph_mask_count: null pointer");
+    OCN_CHECK_ARG(n > 0 && nnz >= 0 && num_masked >= 0 && (num_masked == 0 || (src && dst)), "ocn_graph_mask_count: bad arguments");
+    OCN_CHECK_ARG(num_masked < (int64_t(1) << 30), "ocn_graph_mask_count: too many masked links");
+    const MaskLayout L = mask_layout(num_masked);
+    OCN_CHECK_ARG(scratch_bytes >= L.total, "ocn_graph_mask_count: scratch too small (%zu < %zu)", scratch_bytes, L.total);
     cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)scratch;
+    int64_t* rem_a = (int64_t*)(base + L.rem_a);
+    int64_t* rem_b = (int64_t*)(base + L.rem_b);
+    unsigned long long* counter = (unsigned long long*)(base + L.counter);
     OCN_CUDA(cudaMemsetAsync(out_info, 0, 2 * sizeof(int64_t), st));
-    if (num_masked > 0) {
-        k_mask_mark<false><<<grid_for(num_masked, 256), 256, 0, st>>>(rowptr, col, n, src, dst, num_masked, symmetric, dec,
-                                                                     out_info);
-        OCN_LAUNCH_CHECK();
-    }
-    k_mask_rows<false><<<grid_for(n, 8), 256, 0, st>>>(rowptr, col, mult, dec, n, out_rowptr, nullptr, nullptr);
+    k_mask_init<<<grid_for(L.cap, 256), 256, 0, st>>>(rem_a, L.cap, nnz, counter);
     OCN_LAUNCH_CHECK();
-    size_t tb = scratch_bytes;
-    OCN_CUDA(cub::DeviceScan::ExclusiveSum(scratch, tb, out_rowptr, out_rowptr, (int)(n + 1), st));
-    k_mask_info<<<1, 1, 0, st>>>(out_rowptr, n, out_info);
+    const int64_t* rem = rem_a;
+    if (num_masked > 0) {
+        k_mask_mark<false><<<grid_for(num_masked, 256), 256, 0, st>>>(rowptr, col, mult, n, src, dst, num_masked, symmetric, dec,
+                                                                     rem_a, counter, out_info);
+        OCN_LAUNCH_CHECK();
+        cub::DoubleBuffer<int64_t> db(rem_a, rem_b);
+        size_t tb = L.cub_bytes;
+        OCN_CUDA(cub::DeviceRadixSort::SortKeys(base + L.cub_temp, tb, db, (int)L.cap, 0, nnz_bits(nnz), st));
+        if (db.Current() != rem_a)  // fill() reads the sorted list from the first buffer
+            OCN_CUDA(cudaMemcpyAsync(rem_a, db.Current(), sizeof(int64_t) * (size_t)L.cap, cudaMemcpyDeviceToDevice, st));
+    }
+    k_mask_rowptr<<<grid_for(n + 1, 256), 256, 0, st>>>(rowptr, n, rem, L.cap, out_rowptr, out_info);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
 }
 
-int ocn_graph_mask_fill(const int64_t* rowptr, const int32_t* col, const int32_t* mult, int64_t n, const int64_t* src,
-                        const int64_t* dst, int64_t num_masked, int symmetric, int32_t* dec, const int64_t* out_rowptr,
-                        int32_t* out_col, int32_t* out_mult, void* stream) {
-    OCN_CHECK_ARG(rowptr && col && dec && out_rowptr, "ocn_graph_mask_fill: null pointer");
-    OCN_CHECK_ARG(n > 0 && num_masked >= 0, "ocn_graph_mask_fill: bad arguments");
+int ocn_graph_mask_fill(const int64_t* rowptr, const int32_t* col, const int32_t* mult, int64_t n, int64_t nnz,
+                        const int64_t* src, const int64_t* dst, int64_t num_masked, int symmetric, int32_t* dec,
+                        const void* scratch, int32_t* out_col, int32_t* out_mult, void* stream) {
+    OCN_CHECK_ARG(rowptr && dec && scratch && (col || nnz == 0), "ocn_graph_mask_fill: null pointer");
+    OCN_CHECK_ARG(n > 0 && nnz >= 0 && num_masked >= 0, "ocn_graph_mask_fill: bad arguments");
+    const MaskLayout L = mask_layout(num_masked);
     cudaStream_t st = (cudaStream_t)stream;
-    if (out_col) {
-        k_mask_rows<true><<<grid_for(n, 8), 256, 0, st>>>(rowptr, col, mult, dec, n, const_cast<int64_t*>(out_rowptr), out_col,
-                                                         out_mult);
+    const int64_t* rem = (const int64_t*)((const char*)scratch + L.rem_a);
+    if (out_col && nnz > 0) {
+        k_mask_copy<<<grid_for(nnz, kMaskChunk), 256, 0, st>>>(col, mult, dec, nnz, rem, L.cap, out_col, out_mult);
         OCN_LAUNCH_CHECK();
     }
     if (num_masked > 0) {  // hand the decrement array back all zero
-        k_mask_mark<true><<<grid_for(num_masked, 256), 256, 0, st>>>(rowptr, col, n, src, dst, num_masked, symmetric, dec,
-                                                                    nullptr);
+        k_mask_mark<true><<<grid_for(num_masked, 256), 256, 0, st>>>(rowptr, col, mult, n, src, dst, num_masked, symmetric, dec,
+                                                                    nullptr, nullptr, nullptr);
         OCN_LAUNCH_CHECK();
     }
     return OCN_OK;

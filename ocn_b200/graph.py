@@ -70,22 +70,22 @@ class Graph:
         if dec is None:
             dec = torch.zeros(max(1, self.nnz), dtype=torch.int32, device=dev)
             self._ws["mask_dec"] = dec
-        nb = L.ocn_graph_mask_bytes(self.n)
+        nb = L.ocn_graph_mask_bytes(self.n, M)
         scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
         rowptr = torch.empty(self.n + 1, dtype=torch.int64, device=dev)
         info = torch.zeros(2, dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(L.ocn_graph_mask_count(_lib.ptr(self.rowptr), _lib.ptr(self.col), _lib.ptr(self.mult), self.n,
-                                              _lib.ptr(src), _lib.ptr(dst), M, int(symmetric), _lib.ptr(dec),
+                                              self.nnz, _lib.ptr(src), _lib.ptr(dst), M, int(symmetric), _lib.ptr(dec),
                                               _lib.ptr(scratch), nb, _lib.ptr(rowptr), _lib.ptr(info), st),
                        "ocn_graph_mask_count")
             nnz, missing = info.tolist()
             col = torch.empty(nnz, dtype=torch.int32, device=dev)
             mult = torch.empty(nnz, dtype=torch.int32, device=dev) if self.mult is not None else None
             _lib.check(L.ocn_graph_mask_fill(_lib.ptr(self.rowptr), _lib.ptr(self.col), _lib.ptr(self.mult), self.n,
-                                             _lib.ptr(src), _lib.ptr(dst), M, int(symmetric), _lib.ptr(dec),
-                                             _lib.ptr(rowptr), _lib.ptr(col) if nnz else None, _lib.ptr(mult), st),
+                                             self.nnz, _lib.ptr(src), _lib.ptr(dst), M, int(symmetric), _lib.ptr(dec),
+                                             _lib.ptr(scratch), _lib.ptr(col) if nnz else None, _lib.ptr(mult), st),
                        "ocn_graph_mask_fill")
         if missing:
             raise ValueError(f"{missing} masked links are not edges of this graph")

@@ -85,13 +85,41 @@ def before_after(out):
     print(out[-1], flush=True)
 
 
+def training(out):
+    """One optimiser step of the citation2 driver's predictor loop (NeighborOverlapCitation2.py:131-209): 16 384
+    positive links + 16 384 negatives in sub-batches of 2048 (one source per link: the per-run table path),
+    forward (CN sets, statistics, aggregation, heads) + backward, through ocn_b200.dist.sharded_train_step."""
+    from ocn_b200.dist import sharded_train_step
+    g = synth.make_graph("citation2", device=DEV)
+    G = ob.Graph(g.rowptr, g.col, g.n)
+    for order, cls in ((2, ob.CNLinkPredictorOringin),):
+        torch.manual_seed(0)
+        pred = cls(32, 32, 1, 3, 0.0, weighted=True).to(DEV).train()
+        h = g.features(32, device=DEV).requires_grad_(True)
+        pos = g.query_edges(16384, "pos", device=DEV)
+        neg = torch.stack((pos[0], synth.hash_randint(16384, g.n, 5, 9, DEV)))
+        subs = [pos[:, k:k + 2048] for k in range(0, 16384, 2048)] + [neg[:, k:k + 2048] for k in range(0, 16384, 2048)]
+        signs = [1.0] * 8 + [-1.0] * 8
+
+        def step():
+            pred.zero_grad(set_to_none=True)
+            h.grad = None
+            return sharded_train_step(pred, h, G, subs, signs, 16384, 0, 1)
+        ms = timeit(step, reps=3, warm=1)
+        out.append({"op": f"training step, cn5 order {order}, 32768 links in 16 sub-batches (fwd + bwd)", "ms": ms,
+                    "Mlinks_per_s": 32768 / ms / 1e3})
+        print(out[-1], flush=True)
+
+
 def main():
     out = []
     only = sys.argv[1] if len(sys.argv) > 1 else ""
     if only in ("", "steps"):
         before_after(out)
+    if only in ("", "train"):
+        training(out)
     graphs = (("citation2", (32, 128)), ("collab", (256,)), ("pubmed", (256,)), ("ddi", (64,)))
-    if only == "steps":
+    if only in ("steps", "train"):
         graphs = ()
     elif only:
         graphs = tuple(gf for gf in graphs if gf[0] == only)
