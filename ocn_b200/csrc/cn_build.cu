@@ -543,81 +543,88 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
 }
 
 // Orders 1 and 2 need no table: C1[p] = [N(i)[p] in N(j)], C2[p] = |N(j) (cap) N(N(i)[p])| are plain sorted-list
-// intersections.  One warp per link.  Pass 1: one lane per position p walks the shorter of the two rows and
-// binary-searches the longer one (resuming where the previous search ended); pairs whose shorter row exceeds
-// 32 columns are deferred.  Pass 2: the deferred pairs are intersected by the whole warp (lanes stride over the
-// shorter row), so a hub x hub pair costs len/32 * log steps instead of len * log on one lane.
-// Records are written directly (no atomics): each (link, p) has one owner.
+// intersections.  The work is flattened over the RECORDS: a warp takes 32 consecutive (link, position) pairs of
+// the stream -- one per lane, whichever links they belong to -- so that a link with a 5 000-neighbour source is
+// spread over 157 warps instead of being walked by one (training batches draw their links from the edges, i.e.
+// degree-biased: one warp per link left a tail of tens of milliseconds per 2048-link batch).  Pass 1: the lane
+// walks the shorter of N(j) and N(k_p) and binary-searches the longer one (resuming where the previous search
+// ended); pairs whose shorter row exceeds 32 columns are deferred.  Pass 2: the deferred pairs are intersected by
+// the whole warp (lanes stride over the shorter row), so a hub x hub pair costs len/32 * log steps instead of
+// len * log on one lane.  Records are written directly (no atomics): each (link, p) has one owner.
 __global__ void __launch_bounds__(256)
 k_cn_build_direct(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ src,
                   const int64_t* __restrict__ dst, int64_t T, int order, const int64_t* __restrict__ rec_off,
                   const int64_t* __restrict__ plan, Record* __restrict__ records) {
     if (plan[OCN_PLAN_USE_DIRECT] == 0) return;  // the table kernel handles this stream
-    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int lane = lane_id();
-    for (int64_t t = warp; t < T; t += nwarps) {
-        const int64_t i = src[t], j = dst[t];
-        const int64_t rs_i = rowptr[i], di = rowptr[i + 1] - rs_i;
-        const int64_t rs_j = rowptr[j], dj = rowptr[j + 1] - rs_j;
-        const int32_t* nj = col + rs_j;
-        Record* rec = records + rec_off[t];
-        for (int64_t base = 0; base < di; base += 32) {
-            const int64_t p = base + lane;
-            bool defer = false;
-            int64_t rs_k = 0, dk = 0;
-            unsigned c1 = 0u;
-            if (p < di) {
-                const int32_t k = ldg_i32(col + rs_i + p);
-                c1 = row_contains(nj, dj, k) ? 1u : 0u;
-                unsigned c2 = 0u;
-                if (order >= 2) {
-                    rs_k = ldg_i64(rowptr + k);
-                    dk = ldg_i64(rowptr + k + 1) - rs_k;
-                    const int32_t* a = nj;          // shorter row
-                    const int32_t* b = col + rs_k;  // longer row
-                    int64_t la = dj, lb = dk;
-                    if (la > lb) {
-                        const int32_t* tp = a; a = b; b = tp;
-                        const int64_t tl = la; la = lb; lb = tl;
-                    }
-                    if (la > 32) {
-                        defer = true;
-                    } else {
-                        int64_t lo = 0;  // both rows ascend: every search resumes where the previous one ended
-                        for (int64_t u = 0; u < la && lo < lb; ++u) {
-                            const int32_t v = ldg_i32(a + u);
-                            int64_t hi = lb;
-                            while (lo < hi) {
-                                const int64_t mid = (lo + hi) >> 1;
-                                if (ldg_i32(b + mid) < v) lo = mid + 1; else hi = mid;
-                            }
-                            if (lo < lb && ldg_i32(b + lo) == v) { ++c2; ++lo; }
-                        }
-                    }
-                }
-                if (!defer) rec[p] = make_uint2(c2 | (c1 << 31), 0u);
+    const int64_t total = rec_off[T];
+    for (int64_t g0 = warp * 32; g0 < total; g0 += nwarps * 32) {
+        const int64_t g = g0 + lane;
+        bool defer = false;
+        int64_t rs_k = 0, dk = 0, rs_j = 0, dj = 0;
+        unsigned c1 = 0u;
+        if (g < total) {
+            int64_t lo_t = 0, hi_t = T;  // link of record g: the last t with rec_off[t] <= g (links without records share offsets)
+            while (hi_t - lo_t > 1) {
+                const int64_t mid = (lo_t + hi_t) >> 1;
+                if (ldg_i64(rec_off + mid) <= g) lo_t = mid; else hi_t = mid;
             }
-            unsigned pending = __ballot_sync(0xffffffffu, defer);
-            while (pending) {
-                const int sl = __ffs(pending) - 1;
-                pending &= pending - 1;
-                const int64_t rk = __shfl_sync(0xffffffffu, rs_k, sl);
-                const int64_t dkk = __shfl_sync(0xffffffffu, dk, sl);
-                const unsigned cc1 = __shfl_sync(0xffffffffu, c1, sl);
-                const int32_t* a = nj;
-                const int32_t* b = col + rk;
-                int64_t la = dj, lb = dkk;
+            const int64_t t = lo_t, p = g - ldg_i64(rec_off + t);
+            const int64_t i = src[t], j = dst[t];
+            rs_j = ldg_i64(rowptr + j);
+            dj = ldg_i64(rowptr + j + 1) - rs_j;
+            const int32_t* nj = col + rs_j;
+            const int32_t k = ldg_i32(col + ldg_i64(rowptr + i) + p);
+            c1 = row_contains(nj, dj, k) ? 1u : 0u;
+            unsigned c2 = 0u;
+            if (order >= 2) {
+                rs_k = ldg_i64(rowptr + k);
+                dk = ldg_i64(rowptr + k + 1) - rs_k;
+                const int32_t* a = nj;          // shorter row
+                const int32_t* b = col + rs_k;  // longer row
+                int64_t la = dj, lb = dk;
                 if (la > lb) {
                     const int32_t* tp = a; a = b; b = tp;
                     const int64_t tl = la; la = lb; lb = tl;
                 }
-                unsigned cnt = 0u;
-                for (int64_t u = lane; u < la; u += 32) cnt += row_contains(b, lb, ldg_i32(a + u)) ? 1u : 0u;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-                if (lane == 0) rec[base + sl] = make_uint2(cnt | (cc1 << 31), 0u);
+                if (la > 32) {
+                    defer = true;
+                } else {
+                    int64_t lo = 0;  // both rows ascend: every search resumes where the previous one ended
+                    for (int64_t u = 0; u < la && lo < lb; ++u) {
+                        const int32_t v = ldg_i32(a + u);
+                        int64_t hi = lb;
+                        while (lo < hi) {
+                            const int64_t mid = (lo + hi) >> 1;
+                            if (ldg_i32(b + mid) < v) lo = mid + 1; else hi = mid;
+                        }
+                        if (lo < lb && ldg_i32(b + lo) == v) { ++c2; ++lo; }
+                    }
+                }
             }
+            if (!defer) records[g] = make_uint2(c2 | (c1 << 31), 0u);
+        }
+        unsigned pending = __ballot_sync(0xffffffffu, defer);
+        while (pending) {
+            const int sl = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const int64_t rk = __shfl_sync(0xffffffffu, rs_k, sl), dkk = __shfl_sync(0xffffffffu, dk, sl);
+            const int64_t rj = __shfl_sync(0xffffffffu, rs_j, sl), djj = __shfl_sync(0xffffffffu, dj, sl);
+            const unsigned cc1 = __shfl_sync(0xffffffffu, c1, sl);
+            const int32_t* a = col + rj;
+            const int32_t* b = col + rk;
+            int64_t la = djj, lb = dkk;
+            if (la > lb) {
+                const int32_t* tp = a; a = b; b = tp;
+                const int64_t tl = la; la = lb; lb = tl;
+            }
+            unsigned cnt = 0u;
+            for (int64_t u = lane; u < la; u += 32) cnt += row_contains(b, lb, ldg_i32(a + u)) ? 1u : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if (lane == 0) records[g0 + sl] = make_uint2(cnt | (cc1 << 31), 0u);
         }
     }
 }
@@ -684,7 +691,7 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
         indexed = true;
     }
     if (order <= 2) {  // the plan picked one of the two on the device (plan[OCN_PLAN_USE_DIRECT]); the other returns at once
-        int64_t want = (num_edges + 7) / 8;
+        int64_t want = (records_capacity / 32 + 7) / 8 + 1;  // a warp per 32 records
         int64_t cap = (int64_t)sm_count() * 16;
         k_cn_build_direct<<<(int)(want < cap ? want : cap), 256, 0, st>>>(rowptr, col, src, dst, num_edges, order, rec_off,
                                                                          plan, (Record*)records);
