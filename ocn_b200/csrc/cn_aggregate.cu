@@ -107,24 +107,28 @@ __global__ void k_stats_init(float* __restrict__ bscal, int64_t num_batches, int
     }
 }
 
-// one warp per link: min over CN1 members of the column count, and the link's partial sums
+// one warp per link (a whole CTA per link with a heavy source: per-warp sums combined in warp order, so the
+// result stays run-to-run deterministic): min over CN1 members of the column count, and the link's partial sums
 __global__ void k_stats(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
                         const int64_t* __restrict__ src, int64_t T, int64_t batch_size, int order, int weighted,
                         int variant, float fill, const float* __restrict__ ip, int stage,
                         const int64_t* __restrict__ rec_off, const Record* __restrict__ records,
                         const ColStat* __restrict__ colstat, float* __restrict__ bscal, float* __restrict__ partial) {
-    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    __shared__ float sh_a[32], sh_b[32];
+    __shared__ uint32_t sh_m[32];
+    const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    int64_t warp = (int64_t)blockIdx.x * wpb + wib;
+    int64_t nwarps = (int64_t)gridDim.x * wpb;
     int lane = lane_id();
-    for (int64_t t = warp; t < T; t += nwarps) {
-        const int64_t b = t / batch_size;
-        const int64_t i = src[t];
-        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs, ro = rec_off[t];
+    // warp-level sums over the 32-position chunks base0, base0 + stride, ... of link t
+    auto walk = [&](int64_t t, int64_t rs, int64_t d, int64_t base0, int64_t stride, float& s_a, float& s_b, uint32_t& minc) {
+        const int64_t b = t / batch_size, ro = rec_off[t];
         const ColStat* cs = colstat + b * n;
         WeightParams P = make_params(order, weighted, variant, fill, ip, stage == 0 ? nullptr : bscal + b * 8);
-        uint32_t minc = 0xffffffffu;
-        float s_a = 0.0f, s_b = 0.0f;
-        for (int64_t base = 0; base < d; base += 32) {
+        minc = 0xffffffffu;
+        s_a = 0.0f;
+        s_b = 0.0f;
+        for (int64_t base = base0; base < d; base += stride) {
             const int64_t p = base + lane;
             if (p < d) {
                 const Record rec = records[ro + p];
@@ -148,25 +152,49 @@ __global__ void k_stats(const int64_t* __restrict__ rowptr, const int32_t* __res
                 }
             }
         }
-        if (stage == 0) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                uint32_t other = __shfl_xor_sync(0xffffffffu, minc, o);
-                minc = other < minc ? other : minc;
-            }
-            s_a = warp_sum(s_a);
-            if (lane == 0) {
-                if (minc != 0xffffffffu) atomicMin(reinterpret_cast<uint32_t*>(bscal) + b * 8 + 4, minc);
-                partial[t] = s_a;
-            }
-        } else {
-            s_a = warp_sum(s_a);
-            s_b = warp_sum(s_b);
-            if (lane == 0) {
-                partial[T + 1 + t] = s_a;
-                partial[2 * (T + 1) + t] = s_b;
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, minc, o);
+            minc = other < minc ? other : minc;
         }
+        s_a = warp_sum(s_a);
+        s_b = warp_sum(s_b);
+    };
+    auto store = [&](int64_t t, float s_a, float s_b, uint32_t minc) {
+        const int64_t b = t / batch_size;
+        if (stage == 0) {
+            if (minc != 0xffffffffu) atomicMin(reinterpret_cast<uint32_t*>(bscal) + b * 8 + 4, minc);
+            partial[t] = s_a;
+        } else {
+            partial[T + 1 + t] = s_a;
+            partial[2 * (T + 1) + t] = s_b;
+        }
+    };
+    for (int64_t t = warp; t < T; t += nwarps) {
+        const int64_t i = src[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
+        if (d > kHeavyLink) continue;
+        float s_a, s_b;
+        uint32_t minc;
+        walk(t, rs, d, 0, 32, s_a, s_b, minc);
+        if (lane == 0) store(t, s_a, s_b, minc);
+    }
+    for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
+        const int64_t i = src[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
+        if (d <= kHeavyLink) continue;  // uniform over the CTA
+        float s_a, s_b;
+        uint32_t minc;
+        walk(t, rs, d, 32 * (int64_t)wib, 32 * (int64_t)wpb, s_a, s_b, minc);
+        if (lane == 0) { sh_a[wib] = s_a; sh_b[wib] = s_b; sh_m[wib] = minc; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float a = 0.0f, c = 0.0f;
+            uint32_t m = 0xffffffffu;
+            for (int w = 0; w < wpb; ++w) { a += sh_a[w]; c += sh_b[w]; m = sh_m[w] < m ? sh_m[w] : m; }
+            store(t, a, c, m);
+        }
+        __syncthreads();
     }
 }
 
@@ -225,16 +253,17 @@ k_cn_aggregate(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
     const int sub = lane - grp * lpr;  // position inside the row
     const int64_t F = (int64_t)nvec * 4;
     const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
-    for (int64_t t = warp; t < T; t += nwarps) {
-        const int64_t b = t / batch_size;
-        const int64_t i = src[t], j = dst[t];
-        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs, ro = rec_off[t];
+    const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    // weighted sums over the 32-position chunks base0, base0 + stride, ... of link t; afterwards the lanes of row
+    // group 0 hold the sums (fixed butterfly order)
+    auto walk = [&](int64_t t, int64_t rs, int64_t d, int64_t base0, int64_t stride, float4 (&a1)[VPL], float4 (&a2)[VPL],
+                    float4 (&a3)[VPL]) {
+        const int64_t b = t / batch_size, ro = rec_off[t];
         const ColStat* cs = colstat + b * n;
         const WeightParams P = make_params(order, weighted, variant, fill, ip, bscal + b * 8);
-        float4 a1[VPL], a2[VPL], a3[VPL];
 #pragma unroll
         for (int v = 0; v < VPL; ++v) a1[v] = a2[v] = a3[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int64_t base = 0; base < d; base += 32) {
+        for (int64_t base = base0; base < d; base += stride) {
             const int64_t p = base + lane;
             int32_t k = 0;
             float w1 = 0.f, w2 = 0.f, w3 = 0.f;
@@ -291,23 +320,59 @@ k_cn_aggregate(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
                 a3[v].z += __shfl_xor_sync(0xffffffffu, a3[v].z, o); a3[v].w += __shfl_xor_sync(0xffffffffu, a3[v].w, o);
             }
         }
-        if (grp == 0) {
+    };
+    // accumulate == false: the sums become the output rows; true: they are added to them (same lane, same address)
+    auto emit = [&](int64_t t, const float4 (&a1)[VPL], const float4 (&a2)[VPL], const float4 (&a3)[VPL], bool accumulate) {
+        if (grp != 0) return;
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                const int c = sub + v * lpr;
-                if (c < nvec) {
-                    reinterpret_cast<float4*>(xcn1 + t * F)[c] = a1[v];
-                    if (xcn2) reinterpret_cast<float4*>(xcn2 + t * F)[c] = a2[v];
-                    if (xcn3) reinterpret_cast<float4*>(xcn3 + t * F)[c] = a3[v];
+        for (int v = 0; v < VPL; ++v) {
+            const int c = sub + v * lpr;
+            if (c < nvec) {
+                float4* o1 = reinterpret_cast<float4*>(xcn1 + t * F) + c;
+                float4* o2 = xcn2 ? reinterpret_cast<float4*>(xcn2 + t * F) + c : nullptr;
+                float4* o3 = xcn3 ? reinterpret_cast<float4*>(xcn3 + t * F) + c : nullptr;
+                float4 r1 = a1[v], r2 = a2[v], r3 = a3[v];
+                if (accumulate) {
+                    const float4 p1 = *o1;
+                    r1 = make_float4(p1.x + r1.x, p1.y + r1.y, p1.z + r1.z, p1.w + r1.w);
+                    if (o2) { const float4 p2 = *o2; r2 = make_float4(p2.x + r2.x, p2.y + r2.y, p2.z + r2.z, p2.w + r2.w); }
+                    if (o3) { const float4 p3 = *o3; r3 = make_float4(p3.x + r3.x, p3.y + r3.y, p3.z + r3.z, p3.w + r3.w); }
                 }
+                *o1 = r1;
+                if (o2) *o2 = r2;
+                if (o3) *o3 = r3;
             }
         }
-        if (xij) {
-            for (int c = lane; c < nvec; c += 32) {
-                const float4 xa = __ldg(x4 + i * nvec + c), xb = __ldg(x4 + j * nvec + c);
-                reinterpret_cast<float4*>(xij + t * F)[c] = make_float4(xa.x * xb.x, xa.y * xb.y, xa.z * xb.z, xa.w * xb.w);
-            }
+    };
+    auto pair_term = [&](int64_t t, int64_t i, int64_t j) {
+        if (!xij) return;
+        for (int c = lane; c < nvec; c += 32) {
+            const float4 xa = __ldg(x4 + i * nvec + c), xb = __ldg(x4 + j * nvec + c);
+            reinterpret_cast<float4*>(xij + t * F)[c] = make_float4(xa.x * xb.x, xa.y * xb.y, xa.z * xb.z, xa.w * xb.w);
         }
+    };
+    for (int64_t t = warp; t < T; t += nwarps) {  // one warp per link ...
+        const int64_t i = src[t], j = dst[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
+        if (d > kHeavyLink) continue;
+        float4 a1[VPL], a2[VPL], a3[VPL];
+        walk(t, rs, d, 0, 32, a1, a2, a3);
+        emit(t, a1, a2, a3, false);
+        pair_term(t, i, j);
+    }
+    // ... a whole CTA per link with a heavy source: every warp sums its share of the chunks, the shares are added to
+    // the output rows one warp after the other (warp order: run-to-run deterministic)
+    for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
+        const int64_t i = src[t], j = dst[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
+        if (d <= kHeavyLink) continue;  // uniform over the CTA
+        float4 a1[VPL], a2[VPL], a3[VPL];
+        walk(t, rs, d, 32 * (int64_t)wib, 32 * (int64_t)wpb, a1, a2, a3);
+        for (int w = 0; w < wpb; ++w) {
+            if (wib == w) emit(t, a1, a2, a3, w != 0);
+            __syncthreads();
+        }
+        if (wib == 0) pair_term(t, i, j);
     }
 }
 
@@ -321,16 +386,16 @@ k_cn_aggregate_bwd(const int64_t* __restrict__ rowptr, const int32_t* __restrict
                    const float* __restrict__ x, int64_t F,
                    const float* __restrict__ g1, const float* __restrict__ g2, const float* __restrict__ g3,
                    const float* __restrict__ gij, float* __restrict__ grad_x) {
-    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    int64_t warp = (int64_t)blockIdx.x * wpb + wib;
+    int64_t nwarps = (int64_t)gridDim.x * wpb;
     const int lane = lane_id();
-    for (int64_t t = warp; t < T; t += nwarps) {
-        const int64_t b = t / batch_size;
-        const int64_t i = src[t], j = dst[t];
-        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs, ro = rec_off[t];
+    // 32-position chunks base0, base0 + stride, ... of link t (all sums are atomic: any split of the chunks is fine)
+    auto walk = [&](int64_t t, int64_t i, int64_t j, int64_t rs, int64_t d, int64_t base0, int64_t stride, bool pair_term) {
+        const int64_t b = t / batch_size, ro = rec_off[t];
         const ColStat* cs = colstat + b * n;
         const WeightParams P = make_params(order, weighted, variant, fill, ip, bscal + b * 8);
-        for (int64_t base = 0; base < d; base += 32) {
+        for (int64_t base = base0; base < d; base += stride) {
             const int64_t p = base + lane;
             int32_t k = 0;
             float w1 = 0.f, w2 = 0.f, w3 = 0.f;
@@ -364,13 +429,23 @@ k_cn_aggregate_bwd(const int64_t* __restrict__ rowptr, const int32_t* __restrict
                 }
             }
         }
-        if (gij) {
+        if (gij && pair_term) {
             for (int64_t c = lane; c < F; c += 32) {
                 const float g = gij[t * F + c];
                 atomicAdd(grad_x + i * F + c, g * x[j * F + c]);
                 atomicAdd(grad_x + j * F + c, g * x[i * F + c]);
             }
         }
+    };
+    for (int64_t t = warp; t < T; t += nwarps) {  // one warp per link ...
+        const int64_t i = src[t], j = dst[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
+        if (d <= kHeavyLink) walk(t, i, j, rs, d, 0, 32, true);
+    }
+    for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {  // ... a whole CTA per link with a heavy source
+        const int64_t i = src[t], j = dst[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
+        if (d > kHeavyLink) walk(t, i, j, rs, d, 32 * (int64_t)wib, 32 * (int64_t)wpb, wib == 0);
     }
 }
 
@@ -443,14 +518,13 @@ __global__ void k_cn_release(const int64_t* __restrict__ rowptr, const int32_t* 
                              const int64_t* __restrict__ src, int64_t T, int64_t batch_size,
                              const int64_t* __restrict__ rec_off, const Record* __restrict__ records,
                              ColStat* __restrict__ colstat) {
-    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int wpb = blockDim.x >> 5;
+    int64_t warp = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * wpb;
     const int lane = lane_id();
-    for (int64_t t = warp; t < T; t += nwarps) {
-        const int64_t b = t / batch_size;
-        const int64_t i = src[t];
-        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs, ro = rec_off[t];
-        for (int64_t p = lane; p < d; p += 32) {
+    auto walk = [&](int64_t t, int64_t rs, int64_t d, int64_t p0, int64_t stride) {
+        const int64_t b = t / batch_size, ro = rec_off[t];
+        for (int64_t p = p0; p < d; p += stride) {
             const Record rec = records[ro + p];
             if (rec.x | rec.y) {
                 uint4* c = reinterpret_cast<uint4*>(colstat + b * n + ldg_i32(col + rs + p));
@@ -458,6 +532,16 @@ __global__ void k_cn_release(const int64_t* __restrict__ rowptr, const int32_t* 
                 c[1] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
+    };
+    for (int64_t t = warp; t < T; t += nwarps) {  // one warp per link ...
+        const int64_t i = src[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
+        if (d <= kHeavyLink) walk(t, rs, d, lane, 32);
+    }
+    for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {  // ... a whole CTA per link with a heavy source
+        const int64_t i = src[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
+        if (d > kHeavyLink) walk(t, rs, d, threadIdx.x, blockDim.x);
     }
 }
 

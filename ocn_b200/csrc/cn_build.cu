@@ -634,14 +634,15 @@ __global__ void k_cn_colstat(const int64_t* __restrict__ rowptr, const int32_t* 
                              const int64_t* __restrict__ src, int64_t T, int64_t batch_size, int weighted,
                              const int64_t* __restrict__ rec_off, const Record* __restrict__ records,
                              ColStat* __restrict__ colstat) {
-    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    int64_t warp = (int64_t)blockIdx.x * wpb + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * wpb;
     const int lane = lane_id();
-    for (int64_t t = warp; t < T; t += nwarps) {
-        const int64_t i = src[t];
-        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs, ro = rec_off[t];
+    // positions p0, p0 + stride, ... of link t
+    auto walk = [&](int64_t t, int64_t rs, int64_t d, int64_t p0, int64_t stride) {
+        const int64_t ro = rec_off[t];
         ColStat* cs = colstat + (t / batch_size) * n;
-        for (int64_t p = lane; p < d; p += 32) {
+        for (int64_t p = p0; p < d; p += stride) {
             const Record rec = records[ro + p];
             if (rec.x | rec.y) {
                 ColStat* c = cs + ldg_i32(col + rs + p);
@@ -653,6 +654,16 @@ __global__ void k_cn_colstat(const int64_t* __restrict__ rowptr, const int32_t* 
                 if (v3) atomicAdd(&c->s3, v3);
             }
         }
+    };
+    for (int64_t t = warp; t < T; t += nwarps) {  // one warp per link ...
+        const int64_t i = src[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
+        if (d <= kHeavyLink) walk(t, rs, d, lane, 32);
+    }
+    for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {  // ... a whole CTA per link with a heavy source
+        const int64_t i = src[t];
+        const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
+        if (d > kHeavyLink) walk(t, rs, d, threadIdx.x, blockDim.x);
     }
 }
 

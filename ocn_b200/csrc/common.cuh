@@ -112,6 +112,7 @@ constexpr int kLinkCost = 64;  // fixed cost added to every link so that empty l
 #define OCN_PLAN_HUB_ENTRIES_HEAVY 13   /* the part of OCN_PLAN_HUB_ENTRIES that belongs to runs of heavy sources */
 #define OCN_PLAN_HUB_POSITIONS_HEAVY 14 /* the part of OCN_PLAN_HUB_POSITIONS that belongs to runs of heavy sources */
 constexpr int kHeavyRun = 1024;    // a run whose source has more neighbours than this is "heavy": indexed in a pass of its own
+constexpr int kHeavyLink = 1024;   // a link whose source has more neighbours is walked by a whole CTA in the per-link kernels
 constexpr int kLongRow = 256;      // neighbours of dst a single warp walks in the plan / pair kernels; the rest goes to a CTA
 constexpr int kHubMaxRuns = 2048;       // indexed path: run -> first position table in shared memory
 
