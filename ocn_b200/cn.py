@@ -26,6 +26,8 @@ from .graph import Graph, _require_cuda
 PLAN_WORDS = 16
 PLAN_HUB_DEGREE = 8  # include/ocn_b200.h OCN_PLAN_HUB_DEGREE
 COLSTAT_BUDGET_BYTES = 4 << 30  # per-wave cap for the per-batch column statistics
+HUB_WORKSPACE_FLOOR = 512 << 20  # first size of the per-stream scratch of the indexed order-3 path
+RECORDS_BUCKET = 16 << 20        # record buffers are sized in these steps, so that the caching allocator re-serves them
 
 
 @dataclasses.dataclass
@@ -150,8 +152,8 @@ class CNSession:
         self.plan_host = (ctypes.c_int64 * PLAN_WORDS)(*host)
         self.hub_degree = host[PLAN_HUB_DEGREE]
         self.hub_bytes = L.ocn_cn_hub_bytes(graph.n, graph.nnz, self.plan_host) if self.hub_degree > 0 else 0
-        self.records = torch.empty(max(1, self.num_records) * L.ocn_cn_record_bytes(), dtype=torch.uint8,
-                                   device=self.dev)
+        rec_bytes = max(1, self.num_records) * L.ocn_cn_record_bytes()
+        self.records = torch.empty(-(-rec_bytes // RECORDS_BUCKET) * RECORDS_BUCKET, dtype=torch.uint8, device=self.dev)
         self.colstat = None  # borrowed by build(with_stats=True)
         self.bscal = torch.zeros(self.nb * 8, dtype=torch.float32, device=self.dev)
         self.order = 0
@@ -261,7 +263,10 @@ def _hub_workspace(g: Graph, nbytes: int):
     sid = torch.cuda.current_stream(g.device).cuda_stream  # one workspace per stream: sessions on different streams overlap
     buf = g._ws.get(("hub", sid))
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=g.device)
+        # grow rarely: a cudaMalloc in the middle of a stream of sessions costs 1 - 40 ms (measured), the scratch of a
+        # 65 536-link call is ~40 MB
+        g._ws.pop(("hub", sid), None)
+        buf = torch.empty(max(2 * int(nbytes), HUB_WORKSPACE_FLOOR), dtype=torch.uint8, device=g.device)
         g._ws[("hub", sid)] = buf
     node = g._ws.get(("hub_node", sid))
     if node is None:
