@@ -284,6 +284,12 @@ def main():
     plan_stream = None if a.no_plan_stream else torch.cuda.Stream(device=dev)
 
     streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, a.streams))]
+    # one cached block per stream (and one for the default stream of the roofline leg): the per-session buffers are
+    # carved out of it, no cudaMalloc (1 - 40 ms when it happens) inside a timed region
+    ob.reserve_stream_pool(2 << 30, dev)
+    for st_ in streams:
+        with torch.cuda.stream(st_):
+            ob.reserve_stream_pool(4 << 30, dev)
 
     def fork():  # the work streams start after everything already queued on the default stream ...
         for st in streams:

@@ -5,7 +5,8 @@ Importing the package does not load the CUDA library; the first op does, and rai
 """
 from . import synth  # noqa: F401
 from .graph import Graph  # noqa: F401
-from .cn import CNSession, SparseRows, adjoverlap, cn_aggregate_eval, get_cn, get_cn1_cn2  # noqa: F401
+from .cn import (CNSession, SparseRows, adjoverlap, cn_aggregate_eval, get_cn, get_cn1_cn2,  # noqa: F401
+                 reserve_stream_pool)
 from .sparse_ops import (gcn_norm, gcnconv_propagate, pure_conv, pure_conv3_gcn, sparse_tensor_multiply,  # noqa: F401
                          spgemm_a2, spmm, spmm_add, spmm_max, spmm_mean)
 from . import ops  # noqa: F401  (registers torch.ops.ocn.*)

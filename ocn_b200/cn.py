@@ -256,6 +256,16 @@ class CNSession:
         _return_colstat(self.g, self.colstat)
 
 
+def reserve_stream_pool(nbytes: int = 4 << 30, device=None) -> None:
+    """Seed torch's caching allocator for the CURRENT stream with one block of ``nbytes``: the per-session buffers
+    (plan scratch, records, outputs; a few tens of MB each, sizes varying from call to call) are then carved out of
+    it instead of reaching cudaMalloc, whose latency in the middle of a stream of sessions was measured at 1 - 40 ms.
+    Call once per stream before a latency-sensitive loop."""
+    dev = torch.device(device if device is not None else torch.cuda.current_device())
+    block = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+    del block
+
+
 def _hub_workspace(g: Graph, nbytes: int):
     """Scratch of the hub stage, kept with the graph: a byte buffer that only grows and the 16-byte-per-node
     key index (all zero between calls; ocn_cn_build restores it).  Calls on one stream are ordered by the stream;
