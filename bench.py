@@ -16,6 +16,7 @@ Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the byte account
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -287,9 +288,9 @@ def main():
     # one cached block per stream (and one for the default stream of the roofline leg): the per-session buffers are
     # carved out of it, no cudaMalloc (1 - 40 ms when it happens) inside a timed region
     ob.reserve_stream_pool(2 << 30, dev)
-    for st_ in streams:
+    for st_ in streams + ([plan_stream] if plan_stream is not None else []):
         with torch.cuda.stream(st_):
-            ob.reserve_stream_pool(4 << 30, dev)
+            ob.reserve_stream_pool(4 << 30 if st_ is not plan_stream else 1 << 30, dev)
 
     def fork():  # the work streams start after everything already queued on the default stream ...
         for st in streams:
@@ -353,6 +354,8 @@ def main():
             torch.cuda.cudart().cudaProfilerStart()
         sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gc.collect()
+        gc.disable()  # a generation-2 collection in the middle of the loop stalls the launches for 10+ ms
         t0 = time.perf_counter()
         ev0.record()
         fork()
@@ -361,6 +364,7 @@ def main():
         join()
         ev1.record()
         barrier()
+        gc.enable()
         if profile:
             torch.cuda.cudart().cudaProfilerStop()
         wall = time.perf_counter() - t0
