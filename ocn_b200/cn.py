@@ -263,7 +263,10 @@ def reserve_stream_pool(nbytes: int = 4 << 30, device=None) -> None:
     Call once per stream before a latency-sensitive loop."""
     dev = torch.device(device if device is not None else torch.cuda.current_device())
     block = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
-    del block
+    # the allocator serves requests of up to 1 MB (plan words, batch scalars, counts) from a separate pool of 2 MB
+    # segments: seed that one too
+    small = [torch.empty(1 << 20, dtype=torch.uint8, device=dev) for _ in range(64)]
+    del block, small
 
 
 def _hub_workspace(g: Graph, nbytes: int):

@@ -45,6 +45,7 @@ with torch.cuda.stream(plan_stream):
     ob.reserve_stream_pool(1 << 30, dev)
 import gc
 gc.collect(); gc.disable()
+NA = torch.cuda.memory_stats()["num_device_alloc"]
 for rep in range(3):
     torch.cuda.synchronize()
     t_all = time.perf_counter()
@@ -59,6 +60,10 @@ for rep in range(3):
             out = sess.aggregate(x, 5, 0.0, ip3)
             sess.release()
         dt = 1e3 * (time.perf_counter() - t0)
+        na = torch.cuda.memory_stats()["num_device_alloc"]
+        if na != globals().get("NA", na):
+            LOG.append(("cudaMalloc calls", na - NA, "reserved GB", round(torch.cuda.memory_reserved() / 2**30, 2)))
+        NA = na
         if dt > 3.0 or LOG:
             print(f"rep {rep} step {s}: host {dt:.2f} ms  slow calls: {LOG}", flush=True)
     torch.cuda.synchronize()
