@@ -179,7 +179,7 @@ __global__ void k_stats(const int64_t* __restrict__ rowptr, const int32_t* __res
         walk(t, rs, d, 0, 32, s_a, s_b, minc);
         if (lane == 0) store(t, s_a, s_b, minc);
     }
-    for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
+    for (int64_t t = blockIdx.x; t < (rec_off[T + 1] != 0 ? T : 0); t += gridDim.x) {
         const int64_t i = src[t];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
         if (d <= kHeavyLink) continue;  // uniform over the CTA
@@ -362,7 +362,7 @@ k_cn_aggregate(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
     }
     // ... a whole CTA per link with a heavy source: every warp sums its share of the chunks, the shares are added to
     // the output rows one warp after the other (warp order: run-to-run deterministic)
-    for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
+    for (int64_t t = blockIdx.x; t < (rec_off[T + 1] != 0 ? T : 0); t += gridDim.x) {
         const int64_t i = src[t], j = dst[t];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
         if (d <= kHeavyLink) continue;  // uniform over the CTA
@@ -442,7 +442,7 @@ k_cn_aggregate_bwd(const int64_t* __restrict__ rowptr, const int32_t* __restrict
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
         if (d <= kHeavyLink) walk(t, i, j, rs, d, 0, 32, true);
     }
-    for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {  // ... a whole CTA per link with a heavy source
+    for (int64_t t = blockIdx.x; t < (rec_off[T + 1] != 0 ? T : 0); t += gridDim.x) {  // ... a whole CTA per link with a heavy source
         const int64_t i = src[t], j = dst[t];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
         if (d > kHeavyLink) walk(t, i, j, rs, d, 32 * (int64_t)wib, 32 * (int64_t)wpb, wib == 0);
@@ -538,7 +538,7 @@ __global__ void k_cn_release(const int64_t* __restrict__ rowptr, const int32_t* 
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
         if (d <= kHeavyLink) walk(t, rs, d, lane, 32);
     }
-    for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {  // ... a whole CTA per link with a heavy source
+    for (int64_t t = blockIdx.x; t < (rec_off[T + 1] != 0 ? T : 0); t += gridDim.x) {  // ... a whole CTA per link with a heavy source
         const int64_t i = src[t];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
         if (d > kHeavyLink) walk(t, rs, d, threadIdx.x, blockDim.x);

@@ -18,7 +18,7 @@ static size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 PlanLayout plan_layout(int64_t T) {
     PlanLayout L;
     size_t off = 0;
-    L.rec_off = off;       off += align16(sizeof(int64_t) * (T + 1));
+    L.rec_off = off;       off += align16(sizeof(int64_t) * (T + 2));  // [T + 1]: number of links with a heavy source
     L.run_id = off;        off += align16(sizeof(int32_t) * (T + 1));
     L.run_start = off;     off += align16(sizeof(int32_t) * (T + 2));
     L.run_unit_off = off;  off += align16(sizeof(int64_t) * (T + 2));
@@ -53,8 +53,11 @@ __global__ void k_plan_edges(const int64_t* __restrict__ rowptr, const int64_t* 
         return;
     }
     int64_t i = src[t];
-    rec_off[t] = rowptr[i + 1] - rowptr[i];
+    const int64_t d = rowptr[i + 1] - rowptr[i];
+    rec_off[t] = d;
     flag[t] = (t % batch_size == 0 || src[t - 1] != i) ? 1 : 0;
+    // the per-link kernels walk such a link with a whole CTA; they skip that phase when the count is zero
+    if (d > kHeavyLink) atomicAdd(reinterpret_cast<unsigned long long*>(rec_off + T + 1), 1ull);
 }
 
 // after the inclusive scan flag[t] = run index + 1
@@ -298,6 +301,7 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
         hub_degree = (n + num_edges - 1) / num_edges;  // (citation2 shape, n/T = 45: flat optimum between 24 and 64)
         if (hub_degree < 32) hub_degree = 32;
     }
+    OCN_CUDA(cudaMemsetAsync(rec_off + T + 1, 0, sizeof(int64_t), st));
     k_plan_edges<<<blocks, threads, 0, st>>>(rowptr, src, T, batch_size, rec_off, run_id);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, rec_off, rec_off, (int)(T + 1), st));

@@ -50,7 +50,7 @@ static_assert(sizeof(ColStat) == 32, "ColStat must be one sector");
 
 // plan scratch layout (offsets in bytes, all 16-B aligned)
 struct PlanLayout {
-    size_t rec_off;        // int64[T+1]
+    size_t rec_off;        // int64[T+2]: exclusive prefix of deg(src) over the links; [T+1] = number of links with a heavy source
     size_t run_id;         // int32[T+1]
     size_t run_start;      // int32[T+2]
     size_t run_unit_off;   // int64[T+2]
