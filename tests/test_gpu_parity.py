@@ -420,7 +420,8 @@ def test_hub_stage_matches_table_kernel_at_scale():
         on = ob.CNSession(G, e, 2048, 3, hub_degree=hub)
         assert on.hub_degree > 0
         on.build(3, True, with_stats=False)
-        assert torch.equal(on.records, off.records)
+        nb = on.num_records * 8  # the buffers are sized in buckets: compare the records, not the slack behind them
+        assert on.num_records == off.num_records and torch.equal(on.records[:nb], off.records[:nb])
     # a stream with one run per link (training shape) keeps the stage off
     many = ob.CNSession(G, g.query_edges(4096, "neg", device=DEV), 2048, 3)
     assert many.hub_degree == 0
