@@ -592,14 +592,10 @@ k_cn_build_direct(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
                 if (la > 32) {
                     defer = true;
                 } else {
-                    // both rows ascend: every search resumes where the previous one ended and gallops forward
-                    // (1, 2, 4, ... columns) before it bisects -- the expected gap is lb / la columns, not lb
-                    int64_t lo = 0;
+                    int64_t lo = 0;  // both rows ascend: every search resumes where the previous one ended
                     for (int64_t u = 0; u < la && lo < lb; ++u) {
                         const int32_t v = ldg_i32(a + u);
-                        int64_t step = 1, hi = lo;
-                        while (hi < lb && ldg_i32(b + hi) < v) { lo = hi + 1; hi += step; step <<= 1; }
-                        if (hi > lb) hi = lb;
+                        int64_t hi = lb;
                         while (lo < hi) {
                             const int64_t mid = (lo + hi) >> 1;
                             if (ldg_i32(b + mid) < v) lo = mid + 1; else hi = mid;
