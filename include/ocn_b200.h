@@ -170,7 +170,7 @@ int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n,
                  const int64_t* plan_host /* HOST copy of plan[OCN_PLAN_WORDS] (the caller read it back to size
                                              the buffers); NULL = hub stage off */,
                  void* hub_scratch /* ocn_cn_hub_bytes(...) bytes, NULL = hub stage off */, size_t hub_scratch_bytes,
-                 void* node_scratch /* 16 bytes per node, ZERO on entry, zero again when the call has run */,
+                 void* node_scratch /* 2 x 16 bytes per node (uint4[2n]), ZERO on entry, zero again when the call has run */,
                  void* stream);
 
 /* Hub stage of the order-3 walk (cn_hub.cu): a row N(m) that many links of the stream would walk

@@ -283,7 +283,7 @@ def _hub_workspace(g: Graph, nbytes: int):
         g._ws[("hub", sid)] = buf
     node = g._ws.get(("hub_node", sid))
     if node is None:
-        node = torch.zeros((g.n, 4), dtype=torch.int32, device=g.device)
+        node = torch.zeros((2 * g.n, 4), dtype=torch.int32, device=g.device)  # second half: the pass over heavy sources
         g._ws[("hub_node", sid)] = node
     return buf, node
 

@@ -566,6 +566,8 @@ static void hub_timing_record(int which, cudaStream_t st) {
 struct HubAux {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t heavy_stream = nullptr;  // the pass over the runs of heavy sources runs beside the light pass
+    cudaEvent_t hev[2] = {nullptr, nullptr};
 };
 static std::mutex g_aux_mutex;
 static std::map<std::pair<int, cudaStream_t>, HubAux> g_aux;  // one auxiliary stream per (device, caller stream)
@@ -578,6 +580,8 @@ static int hub_aux(cudaStream_t caller, HubAux** out) {
     if (a.stream == nullptr) {
         OCN_CUDA(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
         for (int k = 0; k < 4; ++k) OCN_CUDA(cudaEventCreateWithFlags(&a.ev[k], cudaEventDisableTiming));
+        OCN_CUDA(cudaStreamCreateWithFlags(&a.heavy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) OCN_CUDA(cudaEventCreateWithFlags(&a.hev[k], cudaEventDisableTiming));
     }
     *out = &a;
     return OCN_OK;
@@ -682,7 +686,7 @@ static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const 
         int per_sm = (int)((200u * 1024u) / smem);
         if (per_sm > (cta ? 3 : 8)) per_sm = cta ? 3 : 8;
         if (per_sm < 1) per_sm = 1;
-        if (first_pass) hub_timing_record(0, st);
+        if (first_pass) hub_timing_record(0, st);  // (the heavy pass, if any, runs on another stream: not part of the timing)
         for (int64_t w0 = 0; w0 < NP; w0 += win) {
             if (w0 > 0) OCN_CUDA(cudaMemsetAsync(counters + 1, 0, sizeof(unsigned long long), st));  // restart the item counter
             const int64_t wn = (NP - w0) < win ? (NP - w0) : win;
@@ -691,7 +695,7 @@ static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const 
                 (uint32_t)wn, items, H.max_items, counters, records);
             OCN_LAUNCH_CHECK();
         }
-        hub_timing_record(1, st);
+        if (first_pass) hub_timing_record(1, st);
     }
     if (timed_alone) {
         k_cn_link<<<sm_count() * 8, 256, 0, st>>>(rowptr, col, dst, T, run_id, rec_off, chunk_off, run_pos_off, ev.Current(),
@@ -723,8 +727,9 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
     OCN_CHECK_ARG(E_heavy >= 0 && E_heavy <= E && NP_heavy >= 0 && NP_heavy <= NP, "ocn_cn_build: inconsistent plan");
     if (NP <= 0 || E <= 0) return OCN_OK;  // no source has a neighbour: every record set is empty
     HubLayout H = hub_layout(n, nnz, P, E, NP);
-    if (hub_scratch_bytes < H.total)
-        return fail(OCN_ENOSPACE, "ocn_cn_build: hub scratch %zu < %zu bytes", hub_scratch_bytes, H.total);
+    const size_t need = NP_heavy > 0 ? 2 * H.total : H.total;  // a heavy pass works in a second copy of the layout
+    if (hub_scratch_bytes < need)
+        return fail(OCN_ENOSPACE, "ocn_cn_build: hub scratch %zu < %zu bytes", hub_scratch_bytes, need);
     HubAux* aux = nullptr;
     if (int rc = hub_aux(st, &aux)) return rc;
     PlanLayout L = plan_layout(T);
@@ -732,11 +737,23 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
     if (NP_heavy == 0)  // the usual stream: one pass over the plain prefix
         return hub_pass(rowptr, col, n, src, dst, T, plan_scratch, plan_dev, (const int64_t*)(pb + L.run_pos_off), hub_d, P, E,
                         NP, R, H, hub_scratch, node_scratch, records, aux, true, st);
+    // two passes side by side (disjoint records): the heavy one on its own stream with the second half of the
+    // scratch and of the node index -- its kernels are short of parallelism (few links, long rows) and hide behind
+    // the light pass
+    OCN_CUDA(cudaEventRecord(aux->hev[0], st));
+    OCN_CUDA(cudaStreamWaitEvent(aux->heavy_stream, aux->hev[0], 0));
+    HubAux* aux_h = nullptr;
+    if (int rc = hub_aux(aux->heavy_stream, &aux_h)) return rc;
+    if (int rc = hub_pass(rowptr, col, n, src, dst, T, plan_scratch, plan_dev, (const int64_t*)(pb + L.run_pos_heavy), hub_d, P,
+                          E_heavy, NP_heavy, R, H, (char*)hub_scratch + H.total, (uint4*)node_scratch + n, records, aux_h, false,
+                          aux->heavy_stream))
+        return rc;
+    OCN_CUDA(cudaEventRecord(aux->hev[1], aux->heavy_stream));
     if (int rc = hub_pass(rowptr, col, n, src, dst, T, plan_scratch, plan_dev, (const int64_t*)(pb + L.pos_scanN), hub_d, P,
                           E - E_heavy, NP - NP_heavy, R, H, hub_scratch, node_scratch, records, aux, true, st))
         return rc;
-    return hub_pass(rowptr, col, n, src, dst, T, plan_scratch, plan_dev, (const int64_t*)(pb + L.run_pos_heavy), hub_d, P,
-                    E_heavy, NP_heavy, R, H, hub_scratch, node_scratch, records, aux, false, st);
+    OCN_CUDA(cudaStreamWaitEvent(st, aux->hev[1], 0));
+    return OCN_OK;
 }
 
 }  // namespace ocn
@@ -746,8 +763,9 @@ using namespace ocn;
 extern "C" size_t ocn_cn_hub_bytes(int64_t n, int64_t nnz, const int64_t* plan_host) {
     if (n <= 0 || nnz < 0 || plan_host == nullptr) return 0;
     if (plan_host[OCN_PLAN_HUB_DEGREE] <= 0) return 0;
-    return hub_layout(n, nnz, plan_host[OCN_PLAN_HUB_PAIRS], plan_host[OCN_PLAN_HUB_ENTRIES],
-                      plan_host[OCN_PLAN_HUB_POSITIONS]).total;
+    const size_t one = hub_layout(n, nnz, plan_host[OCN_PLAN_HUB_PAIRS], plan_host[OCN_PLAN_HUB_ENTRIES],
+                                  plan_host[OCN_PLAN_HUB_POSITIONS]).total;
+    return plan_host[OCN_PLAN_HUB_POSITIONS_HEAVY] > 0 ? 2 * one : one;
 }
 
 extern "C" int ocn_cn_hub_timing_events(void* start_event, void* stop_event) {
