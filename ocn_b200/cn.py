@@ -157,12 +157,15 @@ class CNSession:
         self.colstat = None  # borrowed by build(with_stats=True)
         self.bscal = torch.zeros(self.nb * 8, dtype=torch.float32, device=self.dev)
         self.order = 0
+        self.plan_order = int(order)
         self.weighted = True
         self._released = False
 
     # -- steps ------------------------------------------------------------------------------
     def build(self, order: int, weighted: bool, with_stats: bool = True) -> "CNSession":
         g = self.g
+        if order > self.plan_order:
+            raise ValueError(f"the session was planned for order {self.plan_order}; cannot build order {order}")
         if with_stats and self.colstat is None:
             self.colstat = _borrow_colstat(g, self.nb * self.L.ocn_cn_colstat_bytes(g.n))
         hub_scratch = node_scratch = None

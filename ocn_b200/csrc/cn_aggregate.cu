@@ -390,11 +390,22 @@ k_cn_aggregate_bwd(const int64_t* __restrict__ rowptr, const int32_t* __restrict
     int64_t warp = (int64_t)blockIdx.x * wpb + wib;
     int64_t nwarps = (int64_t)gridDim.x * wpb;
     const int lane = lane_id();
+    const bool vec = (F % 4 == 0) && F <= 128;  // 16-byte vector reductions (rows of grad_x and of g1..g3 are 16-byte aligned)
+    const int nvec = (int)(F / 4);
+    int lpr = 1;
+    while (lpr < nvec && lpr < 32) lpr <<= 1;
+    const int rpw = 32 / lpr, grp = lane / lpr, sub = lane - grp * lpr;
     // 32-position chunks base0, base0 + stride, ... of link t (all sums are atomic: any split of the chunks is fine)
     auto walk = [&](int64_t t, int64_t i, int64_t j, int64_t rs, int64_t d, int64_t base0, int64_t stride, bool pair_term) {
         const int64_t b = t / batch_size, ro = rec_off[t];
         const ColStat* cs = colstat + b * n;
         const WeightParams P = make_params(order, weighted, variant, fill, ip, bscal + b * 8);
+        float4 G1 = make_float4(0.f, 0.f, 0.f, 0.f), G2 = G1, G3 = G1;  // this lane's slice of the link's output gradients
+        if (vec && sub < nvec) {
+            if (g1) G1 = __ldg(reinterpret_cast<const float4*>(g1) + t * nvec + sub);
+            if (g2) G2 = __ldg(reinterpret_cast<const float4*>(g2) + t * nvec + sub);
+            if (g3) G3 = __ldg(reinterpret_cast<const float4*>(g3) + t * nvec + sub);
+        }
         for (int64_t base = base0; base < d; base += stride) {
             const int64_t p = base + lane;
             int32_t k = 0;
@@ -413,6 +424,31 @@ k_cn_aggregate_bwd(const int64_t* __restrict__ rowptr, const int32_t* __restrict
                 }
             }
             unsigned active = __ballot_sync(0xffffffffu, nz);
+            if (vec) {
+                // F / 4 <= 32: a row of grad_x is covered by lpr lanes with one 16-byte vector reduction each, and
+                // 32 / lpr records are scattered at once (4x fewer reductions than one float per lane)
+                while (active) {
+                    unsigned tmp = active;
+                    for (int q = 0; q < grp; ++q) tmp &= tmp - 1;
+                    const int sl = tmp ? (__ffs(tmp) - 1) : -1;
+                    for (int q = 0; q < rpw && active; ++q) active &= active - 1;
+                    const int srcl = sl < 0 ? 0 : sl;
+                    const int32_t kk = __shfl_sync(0xffffffffu, k, srcl);
+                    const float u1 = __shfl_sync(0xffffffffu, w1, srcl);
+                    const float u2 = __shfl_sync(0xffffffffu, w2, srcl);
+                    const float u3 = __shfl_sync(0xffffffffu, w3, srcl);
+                    if (sl >= 0 && sub < nvec) {
+                        float4 g;
+                        g.x = fmaf(u1, G1.x, fmaf(u2, G2.x, u3 * G3.x));
+                        g.y = fmaf(u1, G1.y, fmaf(u2, G2.y, u3 * G3.y));
+                        g.z = fmaf(u1, G1.z, fmaf(u2, G2.z, u3 * G3.z));
+                        g.w = fmaf(u1, G1.w, fmaf(u2, G2.w, u3 * G3.w));
+                        if (g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f)
+                            atomicAdd(reinterpret_cast<float4*>(grad_x) + (int64_t)kk * nvec + sub, g);
+                    }
+                }
+                continue;
+            }
             while (active) {
                 const int sl = __ffs(active) - 1;
                 active &= active - 1;

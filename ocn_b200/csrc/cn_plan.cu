@@ -173,14 +173,16 @@ __global__ void k_plan_hub_decide(int order, int64_t hub_degree, int64_t* __rest
 __global__ void k_plan_units(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                              const int64_t* __restrict__ src, int64_t T, const int32_t* __restrict__ run_start,
                              const int64_t* __restrict__ cost_pre, int resident_ctas,
-                             int64_t heavy_run, int64_t* __restrict__ plan, int64_t* __restrict__ run_units,
+                             int64_t heavy_run, int order, int64_t* __restrict__ plan, int64_t* __restrict__ run_units,
                              int64_t* __restrict__ run_pos_light, int64_t* __restrict__ run_pos_heavy) {
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r > T + 1) return;
     const int64_t n_runs = plan[OCN_PLAN_NUM_RUNS];
     int64_t u = 0, npos = 0;
-    if (r < n_runs) {
+    // orders <= 2 on short runs go to the table-free kernel (k_plan_finish: OCN_PLAN_USE_DIRECT): no table units to plan
+    const bool direct = order <= 2 && T <= 3 * n_runs;
+    if (r < n_runs && !direct) {
         const int64_t t0 = run_start[r], len = run_start[r + 1] - t0;
         const int64_t i = src[t0];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
@@ -325,8 +327,8 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
     int blocks2 = (int)(((T + 2) * 32 + threads - 1) / threads);
     int64_t heavy_run = kHeavyRun;
     if (const char* v = getenv("OCN_HUB_HEAVY_RUN")) heavy_run = atoll(v) > 0 ? atoll(v) : heavy_run;  // test hook
-    k_plan_units<<<blocks2, threads, 0, st>>>(rowptr, col, src, T, run_start, cost_pre, resident_ctas, heavy_run, out_plan,
-                                              run_unit_off, pos_scanN, run_pos_heavy);
+    k_plan_units<<<blocks2, threads, 0, st>>>(rowptr, col, src, T, run_start, cost_pre, resident_ctas, heavy_run, order,
+                                              out_plan, run_unit_off, pos_scanN, run_pos_heavy);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, run_unit_off, run_unit_off, (int)(T + 2), st));
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pos_scanN, pos_scanN, (int)(T + 2), st));
