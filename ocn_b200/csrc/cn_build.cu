@@ -542,124 +542,6 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
     }
 }
 
-// ---- order 2 on training-shape batches: links with a long destination row --------------------------
-// For a link (i, j) whose N(j) has 64 .. 8192 columns the intersections |N(j) (cap) N(k_p)|, p over N(i), all test
-// membership in the SAME set N(j): one CTA puts N(j) into a shared-memory hash set once and every N(k_p) is streamed
-// against it (one shared-memory probe per column instead of a ~log2 |N(j)|-step binary search in global memory per
-// column of the shorter row).  Links are pulled from the build's dynamic counter.  The record-flattened kernel
-// below skips these links.
-constexpr int kSetMinDst = 64, kSetMaxDst = 8192, kSetMinSrc = 32;
-constexpr int kSetSlots = 16384;  // 64 KB of uint32 slots
-constexpr int kSetThreads = 256;
-
-__device__ __forceinline__ bool set_link(int64_t di, int64_t dj) { return dj >= kSetMinDst && dj <= kSetMaxDst && di >= kSetMinSrc; }
-
-__device__ __forceinline__ bool set_contains(const uint32_t* __restrict__ slots, uint32_t mask, int shift, uint32_t key) {
-    uint32_t h = (key * 2654435761u) >> shift;
-    while (true) {
-        const uint32_t v = slots[h];
-        if (v == key) return true;
-        if (v == 0xffffffffu) return false;
-        h = (h + 1u) & mask;
-    }
-}
-
-constexpr int kSetWindow = 1024;  // records per work item
-
-__global__ void __launch_bounds__(kSetThreads)
-k_cn_build_set(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ src,
-               const int64_t* __restrict__ dst, int64_t T, const int64_t* __restrict__ rec_off, int64_t* __restrict__ plan,
-               Record* __restrict__ records) {
-    if (plan[OCN_PLAN_USE_DIRECT] == 0) return;
-    extern __shared__ uint32_t set_slots[];
-    __shared__ long long s_w, s_t;
-    const int lane = threadIdx.x & 31;
-    const int64_t total = rec_off[T];
-    const int64_t n_win = (total + kSetWindow - 1) / kSetWindow;
-    // work item = a window of kSetWindow consecutive records of the stream (pulled from the build's dynamic counter): a
-    // link with thousands of positions is spread over many CTAs (each builds the set again: |N(j)| inserts against
-    // up to 1024 x |N(k)| probes), windows of short links cost next to nothing
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const long long w = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(plan + OCN_PLAN_UNIT_COUNTER), 1ull);
-            s_w = w;
-            if (w < n_win) {  // first link of the window: the last t with rec_off[t] <= w * kSetWindow
-                const int64_t g = w * kSetWindow;
-                int64_t lo = 0, hi = T;
-                while (hi - lo > 1) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (rec_off[mid] <= g) lo = mid; else hi = mid;
-                }
-                s_t = lo;
-            }
-        }
-        __syncthreads();
-        if (s_w >= n_win) break;
-        const int64_t g_lo = s_w * kSetWindow, g_hi = (g_lo + kSetWindow < total) ? g_lo + kSetWindow : total;
-        for (int64_t t = s_t; t < T && rec_off[t] < g_hi; ++t) {  // the links that overlap the window (uniform over the CTA)
-            const int64_t ro = rec_off[t], re = rec_off[t + 1];
-            const int64_t p_lo = (g_lo > ro ? g_lo : ro) - ro, p_hi = (g_hi < re ? g_hi : re) - ro;
-            if (p_hi <= p_lo) continue;
-            const int64_t i = src[t], j = dst[t];
-            const int64_t rs_i = rowptr[i], di = re - ro;
-            const int64_t rs_j = rowptr[j], dj = rowptr[j + 1] - rs_j;
-            if (!set_link(di, dj)) continue;
-            int bits = 7;
-            while ((int64_t(1) << bits) < 2 * dj) ++bits;  // load factor <= 0.5
-            const uint32_t size = 1u << bits, mask = size - 1u;
-            const int shift = 32 - bits;
-            __syncthreads();  // the previous link's probes are done
-            for (uint32_t s = threadIdx.x; s < size; s += kSetThreads) set_slots[s] = 0xffffffffu;
-            __syncthreads();
-            for (int64_t q = threadIdx.x; q < dj; q += kSetThreads) {
-                const uint32_t key = (uint32_t)ldg_i32(col + rs_j + q);
-                uint32_t h = (key * 2654435761u) >> shift;
-                while (atomicCAS(set_slots + h, 0xffffffffu, key) != 0xffffffffu) h = (h + 1u) & mask;  // keys of a row are distinct
-            }
-            __syncthreads();
-            Record* rec = records + ro;
-            const int64_t rounds = (p_hi - p_lo + kSetThreads - 1) / kSetThreads;
-            for (int64_t rd = 0; rd < rounds; ++rd) {
-                const int64_t p = p_lo + rd * kSetThreads + threadIdx.x;
-                int mode = 0;  // 0 done / idle, 1: stream N(k) against the set with the whole warp, 2: N(k) is far longer than N(j): search it
-                int64_t rs_k = 0, dk = 0;
-                unsigned c1 = 0u;
-                if (p < p_hi) {
-                    const int32_t k = ldg_i32(col + rs_i + p);
-                    c1 = set_contains(set_slots, mask, shift, (uint32_t)k) ? 1u : 0u;
-                    rs_k = ldg_i64(rowptr + k);
-                    dk = ldg_i64(rowptr + k + 1) - rs_k;
-                    if (dk > 16 * dj) mode = 2;
-                    else if (dk > 32) mode = 1;
-                    else {
-                        unsigned c2 = 0u;
-                        for (int64_t u = 0; u < dk; ++u) c2 += set_contains(set_slots, mask, shift, (uint32_t)ldg_i32(col + rs_k + u)) ? 1u : 0u;
-                        rec[p] = make_uint2(c2 | (c1 << 31), 0u);
-                    }
-                }
-                unsigned pending = __ballot_sync(0xffffffffu, mode != 0);
-                while (pending) {
-                    const int sl = __ffs(pending) - 1;
-                    pending &= pending - 1;
-                    const int64_t rk = __shfl_sync(0xffffffffu, rs_k, sl), dkk = __shfl_sync(0xffffffffu, dk, sl);
-                    const int md = __shfl_sync(0xffffffffu, mode, sl);
-                    const unsigned cc1 = __shfl_sync(0xffffffffu, c1, sl);
-                    unsigned cnt = 0u;
-                    if (md == 1) {
-                        for (int64_t u = lane; u < dkk; u += 32) cnt += set_contains(set_slots, mask, shift, (uint32_t)ldg_i32(col + rk + u)) ? 1u : 0u;
-                    } else {
-                        for (int64_t u = lane; u < dj; u += 32) cnt += row_contains(col + rk, dkk, ldg_i32(col + rs_j + u)) ? 1u : 0u;
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-                    if (lane == 0) rec[p_lo + rd * kSetThreads + (threadIdx.x & ~31) + sl] = make_uint2(cnt | (cc1 << 31), 0u);
-                }
-            }
-        }
-    }
-}
-
 // Orders 1 and 2 need no table: C1[p] = [N(i)[p] in N(j)], C2[p] = |N(j) (cap) N(N(i)[p])| are plain sorted-list
 // intersections.  The work is flattened over the RECORDS: a warp takes 32 consecutive (link, position) pairs of
 // the stream -- one per lane, whichever links they belong to -- so that a link with a 5 000-neighbour source is
@@ -693,40 +575,36 @@ k_cn_build_direct(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
             const int64_t i = src[t], j = dst[t];
             rs_j = ldg_i64(rowptr + j);
             dj = ldg_i64(rowptr + j + 1) - rs_j;
-            const int64_t rs_i = ldg_i64(rowptr + i);
-            const bool by_set = order >= 2 && set_link(ldg_i64(rowptr + i + 1) - rs_i, dj);  // k_cn_build_set has this link
             const int32_t* nj = col + rs_j;
-            const int32_t k = ldg_i32(col + rs_i + p);
-            if (!by_set) {
-                c1 = row_contains(nj, dj, k) ? 1u : 0u;
-                unsigned c2 = 0u;
-                if (order >= 2) {
-                    rs_k = ldg_i64(rowptr + k);
-                    dk = ldg_i64(rowptr + k + 1) - rs_k;
-                    const int32_t* a = nj;          // shorter row
-                    const int32_t* b = col + rs_k;  // longer row
-                    int64_t la = dj, lb = dk;
-                    if (la > lb) {
-                        const int32_t* tp = a; a = b; b = tp;
-                        const int64_t tl = la; la = lb; lb = tl;
-                    }
-                    if (la > 32) {
-                        defer = true;
-                    } else {
-                        int64_t lo = 0;  // both rows ascend: every search resumes where the previous one ended
-                        for (int64_t u = 0; u < la && lo < lb; ++u) {
-                            const int32_t v = ldg_i32(a + u);
-                            int64_t hi = lb;
-                            while (lo < hi) {
-                                const int64_t mid = (lo + hi) >> 1;
-                                if (ldg_i32(b + mid) < v) lo = mid + 1; else hi = mid;
-                            }
-                            if (lo < lb && ldg_i32(b + lo) == v) { ++c2; ++lo; }
+            const int32_t k = ldg_i32(col + ldg_i64(rowptr + i) + p);
+            c1 = row_contains(nj, dj, k) ? 1u : 0u;
+            unsigned c2 = 0u;
+            if (order >= 2) {
+                rs_k = ldg_i64(rowptr + k);
+                dk = ldg_i64(rowptr + k + 1) - rs_k;
+                const int32_t* a = nj;          // shorter row
+                const int32_t* b = col + rs_k;  // longer row
+                int64_t la = dj, lb = dk;
+                if (la > lb) {
+                    const int32_t* tp = a; a = b; b = tp;
+                    const int64_t tl = la; la = lb; lb = tl;
+                }
+                if (la > 32) {
+                    defer = true;
+                } else {
+                    int64_t lo = 0;  // both rows ascend: every search resumes where the previous one ended
+                    for (int64_t u = 0; u < la && lo < lb; ++u) {
+                        const int32_t v = ldg_i32(a + u);
+                        int64_t hi = lb;
+                        while (lo < hi) {
+                            const int64_t mid = (lo + hi) >> 1;
+                            if (ldg_i32(b + mid) < v) lo = mid + 1; else hi = mid;
                         }
+                        if (lo < lb && ldg_i32(b + lo) == v) { ++c2; ++lo; }
                     }
                 }
-                if (!defer) records[g] = make_uint2(c2 | (c1 << 31), 0u);
             }
+            if (!defer) records[g] = make_uint2(c2 | (c1 << 31), 0u);
         }
         unsigned pending = __ballot_sync(0xffffffffu, defer);
         while (pending) {
@@ -824,16 +702,6 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
         indexed = true;
     }
     if (order <= 2) {  // the plan picked one of the two on the device (plan[OCN_PLAN_USE_DIRECT]); the other returns at once
-        if (order >= 2) {  // links with a long destination row: one CTA per link, N(j) as a shared-memory set
-            const size_t smem = sizeof(uint32_t) * kSetSlots;
-            OCN_CUDA(cudaFuncSetAttribute(k_cn_build_set, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int64_t ctas = (int64_t)sm_count() * 3;
-            const int64_t windows = records_capacity / kSetWindow + 1;
-            if (ctas > windows) ctas = windows;
-            k_cn_build_set<<<(int)ctas, kSetThreads, smem, st>>>(rowptr, col, src, dst, num_edges, rec_off, (int64_t*)plan,
-                                                               (Record*)records);
-            OCN_LAUNCH_CHECK();
-        }
         int64_t want = (records_capacity / 32 + 7) / 8 + 1;  // a warp per 32 records
         int64_t cap = (int64_t)sm_count() * 16;
         k_cn_build_direct<<<(int)(want < cap ? want : cap), 256, 0, st>>>(rowptr, col, src, dst, num_edges, order, rec_off,
