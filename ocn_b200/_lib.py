@@ -10,7 +10,7 @@ import re
 from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libocn_b200.so")
+LIB_PATH = os.environ.get("OCN_B200_LIB") or os.path.join(HERE, "libocn_b200.so")  # override: A/B of kernel variants
 HEADER = os.path.join(HERE, "..", "include", "ocn_b200.h")
 
 _P = c_void_p
