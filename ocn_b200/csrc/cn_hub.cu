@@ -70,6 +70,7 @@ HubLayout hub_layout(int64_t n, int64_t nnz, int64_t pairs, int64_t entries, int
     L.counters = off;  off += align256(sizeof(unsigned long long) * 4);
     L.prun = off;      off += align256(sizeof(int32_t) * P);
     L.prec = off;      off += align256(sizeof(unsigned long long) * P);
+    L.key_bits = off;  off += align256(sizeof(uint32_t) * (size_t)((n + 32) / 32));
     size_t b1 = 0, b2 = 0, b3 = 0;
     {
         cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
@@ -155,7 +156,7 @@ __device__ __forceinline__ uint32_t run_of_position(uint32_t pi, const int64_t* 
 // bit (run mod 64)); all zero = l is no key.  set == 0 restores the zeros.
 __global__ void k_hub_entry_heads(const uint32_t* __restrict__ ekey, const uint32_t* __restrict__ eval,
                                   const int64_t* __restrict__ run_pos_off, int n_runs, int64_t E, int set,
-                                  uint4* __restrict__ node_index) {
+                                  uint4* __restrict__ node_index, uint32_t* __restrict__ key_bits) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     const uint32_t k = ekey[e];
@@ -165,7 +166,10 @@ __global__ void k_hub_entry_heads(const uint32_t* __restrict__ ekey, const uint3
         if (first) node_index[k] = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
-    if (first) ni[0] = (unsigned)e;
+    if (first) {
+        ni[0] = (unsigned)e;
+        atomicOr(key_bits + (k >> 5), 1u << (k & 31u));  // 1 bit per node: 8 MB of index entries are filtered by 366 KB
+    }
     if (e == E - 1 || ekey[e + 1] != k) ni[1] = (unsigned)(e + 1);
     const uint32_t r = run_of_position(eval[e], run_pos_off, n_runs);
     atomicOr(ni + 2 + ((r >> 5) & 1u), 1u << (r & 31u));
@@ -323,6 +327,7 @@ __global__ void __launch_bounds__(kHubThreads, kCta ? 3 : 6)
 k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint32_t* __restrict__ pkey,
                const int32_t* __restrict__ prun, const unsigned long long* __restrict__ prec, int64_t P,
                const uint32_t* __restrict__ eval, const uint4* __restrict__ node_index,
+               const uint32_t* __restrict__ key_bits,
                const int64_t* __restrict__ run_pos_off, int n_runs, uint32_t win_lo, uint32_t win_n,
                const uint2* __restrict__ items, int64_t max_items, unsigned long long* __restrict__ counters,
                Record* __restrict__ records) {
@@ -380,11 +385,13 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
         const int64_t d = rowptr[m + 1] - rs;
         const int64_t c0 = (int64_t)item.y * kHubSeg;
         const int64_t c1 = (c0 + kHubSeg < d) ? c0 + kHubSeg : d;
-        // software pipeline: the column of step b+2 and the index entry of step b+1 are in flight while
-        // the lists of step b are walked
+        // software pipeline: the column of step b+3, the key bit of step b+2 and the index entry of step b+1 are in
+        // flight while the lists of step b are walked
         const int64_t stride = 32 * nw;
         auto load_col = [&](int64_t bb) -> int32_t { return (bb + lane < c1) ? ldg_i32(col + rs + bb + lane) : -1; };
-        auto load_entry = [&](int32_t l) -> uint4 { return l >= 0 ? __ldg(node_index + l) : make_uint4(0u, 0u, 0u, 0u); };
+        // a column is a key of the index only if its bit is set: the 16-byte entry is fetched for those alone
+        auto load_bit = [&](int32_t l) -> bool { return l >= 0 && ((__ldg(key_bits + (l >> 5)) >> (l & 31)) & 1u) != 0u; };
+        auto load_entry = [&](int32_t l, bool key) -> uint4 { return key ? __ldg(node_index + l) : make_uint4(0u, 0u, 0u, 0u); };
         // one queued list per lane (length 0 = none): the first kShortList entries by the lane itself, the rest of
         // the middle lists flattened over the lanes, 32 entries at a time
         auto drain = [&](uint2 ql) {
@@ -414,12 +421,19 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
         };
         int qn = 0;  // queued lists (warp-uniform)
         const int64_t b0 = c0 + 32 * wi;
-        uint4 he_next = load_entry(load_col(b0));
-        int32_t col_next = load_col(b0 + stride);
+        uint4 he_next;
+        int32_t col_n1 = load_col(b0 + stride), col_n2 = load_col(b0 + 2 * stride);
+        {
+            const int32_t l0 = load_col(b0);
+            he_next = load_entry(l0, load_bit(l0));
+        }
+        bool bit_n1 = load_bit(col_n1);
         for (int64_t b = b0; b < c1; b += stride) {
             const uint4 he = he_next;
-            he_next = load_entry(col_next);
-            col_next = load_col(b + 2 * stride);
+            he_next = load_entry(col_n1, bit_n1);
+            col_n1 = col_n2;
+            bit_n1 = load_bit(col_n1);
+            col_n2 = load_col(b + 3 * stride);
             const int cnt = ((he.z & act_lo) | (he.w & act_hi)) ? (int)(he.y - he.x) : 0;
             if (!__any_sync(0xffffffffu, cnt != 0)) continue;
             // short and middle lists go to the queue; a full batch of 32 is walked as soon as there is one
@@ -466,15 +480,27 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
         if (qn > 0) drain(lane < qn ? Q[lane] : make_uint2(0u, 0u));
         item_sync();
         // hand the counts to the links next to m
-        for (int64_t q = wi; q < c; q += nw) {
-            const int r = prun[q0 + q];
-            const uint32_t pb = s_pos[r], pe = s_pos[r + 1];
-            const uint32_t lo = (kWin && pb < win_lo) ? win_lo : pb, hi = (kWin && pe > win_lo + win_n) ? win_lo + win_n : pe;
-            unsigned* rec = rec32 + 2 * prec[q0 + q] + 1;
-            for (uint32_t pos = lo + lane; pos < hi; pos += 32) {
-                const uint32_t rel = kWin ? pos - win_lo : pos;
-                const uint32_t u = (U[rel >> 1] >> ((rel & 1u) << 4)) & 0xffffu;
-                if (u) atomicAdd(rec + 2 * (pos - pb), u);
+        // (the run and the record offset of 32 links at a time are fetched by the lanes up front: no dependent
+        // global load between two links)
+        for (int64_t qb = 0; qb < c; qb += 32) {
+            int r_l = 0;
+            unsigned long long prec_l = 0ull;
+            if (qb + lane < c) {
+                r_l = prun[q0 + qb + lane];
+                prec_l = prec[q0 + qb + lane];
+            }
+            const int cnt = (int)((c - qb) < 32 ? (c - qb) : 32);
+            for (int qq = wi; qq < cnt; qq += nw) {
+                const int r = __shfl_sync(0xffffffffu, r_l, qq);
+                const unsigned long long pr = __shfl_sync(0xffffffffu, prec_l, qq);
+                const uint32_t pb = s_pos[r], pe = s_pos[r + 1];
+                const uint32_t lo = (kWin && pb < win_lo) ? win_lo : pb, hi = (kWin && pe > win_lo + win_n) ? win_lo + win_n : pe;
+                unsigned* rec = rec32 + 2 * pr + 1;
+                for (uint32_t pos = lo + lane; pos < hi; pos += 32) {
+                    const uint32_t rel = kWin ? pos - win_lo : pos;
+                    const uint32_t u = (U[rel >> 1] >> ((rel & 1u) << 4)) & 0xffffu;
+                    if (u) atomicAdd(rec + 2 * (pos - pb), u);
+                }
             }
         }
         item_sync();
@@ -486,9 +512,11 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
 // its rows, C3 through those of its rows that have fewer than hub_d columns, their columns
 // flattened over the lanes.  lookup: the entries of l that belong to the run of t are the piece of
 // l's list with positions in [pos_lo, pos_hi).
-__device__ __forceinline__ void link_lookup(const uint4* __restrict__ node_index, const uint32_t* __restrict__ eval,
+__device__ __forceinline__ void link_lookup(const uint4* __restrict__ node_index, const uint32_t* __restrict__ key_bits,
+                                            const uint32_t* __restrict__ eval,
                                             uint32_t l, uint32_t r, uint32_t pos_lo, uint32_t pos_hi,
                                             unsigned* __restrict__ rec, unsigned inc) {
+    if (((__ldg(key_bits + (l >> 5)) >> (l & 31u)) & 1u) == 0u) return;  // l has no entry list (most nodes)
     const uint4 he = __ldg(node_index + l);
     if ((((r & 32u) ? he.w : he.z) >> (r & 31u) & 1u) == 0u) return;  // no entry of l in a run of this signature bit
     uint32_t lo = he.x, hi = he.y;
@@ -507,8 +535,8 @@ __global__ void __launch_bounds__(256)
 k_cn_link(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ dst,
           int64_t T, const int32_t* __restrict__ run_id, const int64_t* __restrict__ rec_off,
           const int32_t* __restrict__ chunk_off, const int64_t* __restrict__ run_pos_off,
-          const uint32_t* __restrict__ eval, const uint4* __restrict__ node_index, int64_t hub_d,
-          Record* __restrict__ records) {
+          const uint32_t* __restrict__ eval, const uint4* __restrict__ node_index,
+          const uint32_t* __restrict__ key_bits, int64_t hub_d, Record* __restrict__ records) {
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_items = chunk_off[T];
@@ -527,13 +555,13 @@ k_cn_link(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, c
         const uint32_t pos_lo = (uint32_t)run_pos_off[r], pos_hi = (uint32_t)run_pos_off[r + 1];
         if (pos_lo == pos_hi) continue;  // the run has no positions in this pass (other class of runs, or an isolated source)
         unsigned* rec = rec32 + 2 * rec_off[t];
-        if (ch == 0 && lane == 0) link_lookup(node_index, eval, (uint32_t)j, r, pos_lo, pos_hi, rec, 0x80000000u);  // C1
+        if (ch == 0 && lane == 0) link_lookup(node_index, key_bits, eval, (uint32_t)j, r, pos_lo, pos_hi, rec, 0x80000000u);  // C1
         const int64_t oi = ch * 32 + lane;
         int64_t rs_m = 0;
         int cnt = 0;
         if (oi < d_j) {
             const int32_t m = ldg_i32(col + rs_j + oi);
-            link_lookup(node_index, eval, (uint32_t)m, r, pos_lo, pos_hi, rec, 1u);  // C2
+            link_lookup(node_index, key_bits, eval, (uint32_t)m, r, pos_lo, pos_hi, rec, 1u);  // C2
             rs_m = ldg_i64(rowptr + m);
             const int64_t d_m = ldg_i64(rowptr + m + 1) - rs_m;
             if (d_m < hub_d) cnt = (int)d_m;
@@ -547,7 +575,7 @@ k_cn_link(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, c
             const int64_t rs_o = __shfl_sync(0xffffffffu, rs_m, s);
             const int eexcl = __shfl_sync(0xffffffffu, excl, s);
             if (jj < total)
-                link_lookup(node_index, eval, (uint32_t)ldg_i32(col + rs_o + (jj - eexcl)), r, pos_lo, pos_hi, rec + 1, 1u);
+                link_lookup(node_index, key_bits, eval, (uint32_t)ldg_i32(col + rs_o + (jj - eexcl)), r, pos_lo, pos_hi, rec + 1, 1u);
         }
     }
 }
@@ -615,10 +643,12 @@ static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const 
     int32_t* prun = (int32_t*)(hb + H.prun);
     unsigned long long* prec = (unsigned long long*)(hb + H.prec);
     unsigned long long* counters = (unsigned long long*)(hb + H.counters);
+    uint32_t* key_bitmap = (uint32_t*)(hb + H.key_bits);
     const int bits = key_bits(n);
     const int th = 256;
 
     OCN_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * 4, st));
+    OCN_CUDA(cudaMemsetAsync(key_bitmap, 0, sizeof(uint32_t) * (size_t)((n + 32) / 32), st));
     OCN_CUDA(cudaEventRecord(aux->ev[0], st));  // fork: everything before this call is visible to the auxiliary stream
     OCN_CUDA(cudaStreamWaitEvent(sa, aux->ev[0], 0));
 
@@ -650,7 +680,7 @@ static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const 
                                                             ekey[0], eval[0]);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ek, ev, (int)E, 0, bits, st));
-    k_hub_entry_heads<<<grid_for(E, th), th, 0, st>>>(ek.Current(), ev.Current(), run_pos_off, (int)R, E, 1, node_index);
+    k_hub_entry_heads<<<grid_for(E, th), th, 0, st>>>(ek.Current(), ev.Current(), run_pos_off, (int)R, E, 1, node_index, key_bitmap);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cudaEventRecord(aux->ev[2], st));  // index complete
 
@@ -661,7 +691,7 @@ static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const 
     OCN_CUDA(cudaStreamWaitEvent(sa, aux->ev[2], 0));
     if (!timed_alone)
         k_cn_link<<<sm_count() * 8, 256, 0, sa>>>(rowptr, col, dst, T, run_id, rec_off, chunk_off, run_pos_off, ev.Current(),
-                                              node_index, hub_d, records);
+                                              node_index, key_bitmap, hub_d, records);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cudaEventRecord(aux->ev[3], sa));
 
@@ -691,7 +721,7 @@ static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const 
             if (w0 > 0) OCN_CUDA(cudaMemsetAsync(counters + 1, 0, sizeof(unsigned long long), st));  // restart the item counter
             const int64_t wn = (NP - w0) < win ? (NP - w0) : win;
             kern<<<sm_count() * per_sm, kHubThreads, smem, st>>>(
-                rowptr, col, dk.Current(), prun, prec, P, ev.Current(), node_index, run_pos_off, (int)R, (uint32_t)w0,
+                rowptr, col, dk.Current(), prun, prec, P, ev.Current(), node_index, key_bitmap, run_pos_off, (int)R, (uint32_t)w0,
                 (uint32_t)wn, items, H.max_items, counters, records);
             OCN_LAUNCH_CHECK();
         }
@@ -699,11 +729,11 @@ static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const 
     }
     if (timed_alone) {
         k_cn_link<<<sm_count() * 8, 256, 0, st>>>(rowptr, col, dst, T, run_id, rec_off, chunk_off, run_pos_off, ev.Current(),
-                                                  node_index, hub_d, records);
+                                                  node_index, key_bitmap, hub_d, records);
         OCN_LAUNCH_CHECK();
     }
     OCN_CUDA(cudaStreamWaitEvent(st, aux->ev[3], 0));  // join
-    k_hub_entry_heads<<<grid_for(E, th), th, 0, st>>>(ek.Current(), ev.Current(), run_pos_off, (int)R, E, 0, node_index);
+    k_hub_entry_heads<<<grid_for(E, th), th, 0, st>>>(ek.Current(), ev.Current(), run_pos_off, (int)R, E, 0, node_index, key_bitmap);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
 }

@@ -83,6 +83,7 @@ struct HubLayout {
     int64_t max_items;
     size_t counters;          // uint64[4]: number of items, next item
     size_t prun, prec;        // int32[P] run / uint64[P] record offset of the link of every sorted pair
+    size_t key_bits;          // uint32[ceil((n + 1) / 32)]: bit l = node l is a key of the index (has an entry list)
     size_t cub_temp, cub_temp_bytes;    // entry pipeline (caller's stream)
     size_t cub_temp2, cub_temp2_bytes;  // pair pipeline (auxiliary stream)
     size_t total;
