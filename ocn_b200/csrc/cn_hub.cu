@@ -56,7 +56,7 @@ static int key_bits(int64_t n) {  // bits of the keys 0 .. n (n itself is the "n
     return b;
 }
 
-HubLayout hub_layout(int64_t n, int64_t nnz, int64_t pairs, int64_t entries, int64_t positions) {
+HubLayout hub_layout(int64_t n, int64_t nnz, int64_t pairs, int64_t entries, int64_t positions, int64_t chunks) {
     HubLayout L;
     size_t off = 0;
     const size_t P = (size_t)(pairs > 0 ? pairs : 1), E = (size_t)(entries > 0 ? entries : 1);
@@ -71,6 +71,7 @@ HubLayout hub_layout(int64_t n, int64_t nnz, int64_t pairs, int64_t entries, int
     L.prun = off;      off += align256(sizeof(int32_t) * P);
     L.prec = off;      off += align256(sizeof(unsigned long long) * P);
     L.key_bits = off;  off += align256(sizeof(uint32_t) * (size_t)((n + 32) / 32));
+    L.item_link = off; off += align256(sizeof(int32_t) * (size_t)((chunks > 0 ? chunks : 0) + 1));
     size_t b1 = 0, b2 = 0, b3 = 0;
     {
         cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
@@ -531,23 +532,27 @@ __device__ __forceinline__ void link_lookup(const uint4* __restrict__ node_index
     }
 }
 
+// link of every work item (chunk_off is the exclusive prefix of the per-link item counts): one warp per link
+__global__ void k_hub_item_links(const int32_t* __restrict__ chunk_off, int64_t T, int32_t* __restrict__ item_link) {
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= T) return;
+    const int32_t a = chunk_off[t], b = chunk_off[t + 1];
+    for (int32_t it = a + (threadIdx.x & 31); it < b; it += 32) item_link[it] = (int32_t)t;
+}
+
 __global__ void __launch_bounds__(256)
 k_cn_link(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ dst,
           int64_t T, const int32_t* __restrict__ run_id, const int64_t* __restrict__ rec_off,
           const int32_t* __restrict__ chunk_off, const int64_t* __restrict__ run_pos_off,
           const uint32_t* __restrict__ eval, const uint4* __restrict__ node_index,
-          const uint32_t* __restrict__ key_bits, int64_t hub_d, Record* __restrict__ records) {
+          const uint32_t* __restrict__ key_bits, const int32_t* __restrict__ item_link, int64_t hub_d,
+          Record* __restrict__ records) {
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_items = chunk_off[T];
     unsigned* rec32 = reinterpret_cast<unsigned*>(records);
     for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += nwarps) {
-        int64_t lo = 0, hi = T;  // last t with chunk_off[t] <= item
-        while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (chunk_off[mid] <= item) lo = mid; else hi = mid;
-        }
-        const int64_t t = lo;
+        const int64_t t = item_link[item];
         const int64_t ch = item - chunk_off[t];
         const int64_t j = dst[t];
         const int64_t rs_j = rowptr[j], d_j = rowptr[j + 1] - rs_j;
@@ -644,6 +649,7 @@ static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const 
     unsigned long long* prec = (unsigned long long*)(hb + H.prec);
     unsigned long long* counters = (unsigned long long*)(hb + H.counters);
     uint32_t* key_bitmap = (uint32_t*)(hb + H.key_bits);
+    int32_t* item_link = (int32_t*)(hb + H.item_link);
     const int bits = key_bits(n);
     const int th = 256;
 
@@ -653,6 +659,8 @@ static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const 
     OCN_CUDA(cudaStreamWaitEvent(sa, aux->ev[0], 0));
 
     // auxiliary stream: (shared row, link) pairs, sorted by row, and the work items
+    k_hub_item_links<<<grid_for(T * 32, th), th, 0, sa>>>(chunk_off, T, item_link);
+    OCN_LAUNCH_CHECK();
     cub::DoubleBuffer<uint32_t> dk(pkey[0], pkey[1]), dv(pval[0], pval[1]);
     if (P > 0) {
         k_hub_emit_pairs<<<grid_for(T * 32, th), th, 0, sa>>>(rowptr, col, n, dst, T, hub_d, hub_off, run_id, run_pos_off,
@@ -691,7 +699,7 @@ static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const 
     OCN_CUDA(cudaStreamWaitEvent(sa, aux->ev[2], 0));
     if (!timed_alone)
         k_cn_link<<<sm_count() * 8, 256, 0, sa>>>(rowptr, col, dst, T, run_id, rec_off, chunk_off, run_pos_off, ev.Current(),
-                                              node_index, key_bitmap, hub_d, records);
+                                              node_index, key_bitmap, item_link, hub_d, records);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cudaEventRecord(aux->ev[3], sa));
 
@@ -729,7 +737,7 @@ static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const 
     }
     if (timed_alone) {
         k_cn_link<<<sm_count() * 8, 256, 0, st>>>(rowptr, col, dst, T, run_id, rec_off, chunk_off, run_pos_off, ev.Current(),
-                                                  node_index, key_bitmap, hub_d, records);
+                                                  node_index, key_bitmap, item_link, hub_d, records);
         OCN_LAUNCH_CHECK();
     }
     OCN_CUDA(cudaStreamWaitEvent(st, aux->ev[3], 0));  // join
@@ -756,7 +764,7 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
                   (long long)R, (long long)NP);
     OCN_CHECK_ARG(E_heavy >= 0 && E_heavy <= E && NP_heavy >= 0 && NP_heavy <= NP, "ocn_cn_build: inconsistent plan");
     if (NP <= 0 || E <= 0) return OCN_OK;  // no source has a neighbour: every record set is empty
-    HubLayout H = hub_layout(n, nnz, P, E, NP);
+    HubLayout H = hub_layout(n, nnz, P, E, NP, plan_host[OCN_PLAN_NUM_CHUNKS]);
     const size_t need = NP_heavy > 0 ? 2 * H.total : H.total;  // a heavy pass works in a second copy of the layout
     if (hub_scratch_bytes < need)
         return fail(OCN_ENOSPACE, "ocn_cn_build: hub scratch %zu < %zu bytes", hub_scratch_bytes, need);
@@ -794,7 +802,7 @@ extern "C" size_t ocn_cn_hub_bytes(int64_t n, int64_t nnz, const int64_t* plan_h
     if (n <= 0 || nnz < 0 || plan_host == nullptr) return 0;
     if (plan_host[OCN_PLAN_HUB_DEGREE] <= 0) return 0;
     const size_t one = hub_layout(n, nnz, plan_host[OCN_PLAN_HUB_PAIRS], plan_host[OCN_PLAN_HUB_ENTRIES],
-                                  plan_host[OCN_PLAN_HUB_POSITIONS]).total;
+                                  plan_host[OCN_PLAN_HUB_POSITIONS], plan_host[OCN_PLAN_NUM_CHUNKS]).total;
     return plan_host[OCN_PLAN_HUB_POSITIONS_HEAVY] > 0 ? 2 * one : one;
 }
 

@@ -241,7 +241,7 @@ __global__ void k_plan_positions(const int64_t* __restrict__ plan, const int64_t
 __global__ void k_plan_finish(int64_t T, int64_t batch_size, int resident_ctas, const int64_t* __restrict__ rec_off,
                               const int64_t* __restrict__ run_unit_off, const int32_t* __restrict__ hub_off,
                               const int64_t* __restrict__ run_pos_off, const int64_t* __restrict__ run_pos_heavy_off,
-                              int64_t* __restrict__ plan) {
+                              const int32_t* __restrict__ chunk_off, int64_t* __restrict__ plan) {
     plan[OCN_PLAN_NUM_RECORDS] = rec_off[T];
     plan[OCN_PLAN_NUM_UNITS] = run_unit_off[plan[OCN_PLAN_NUM_RUNS]];
     plan[OCN_PLAN_NUM_BATCHES] = (T + batch_size - 1) / batch_size;
@@ -253,6 +253,7 @@ __global__ void k_plan_finish(int64_t T, int64_t batch_size, int resident_ctas, 
     const int64_t n_runs = plan[OCN_PLAN_NUM_RUNS];
     plan[OCN_PLAN_HUB_POSITIONS] = run_pos_off[n_runs] + run_pos_heavy_off[n_runs];  // 0 when the indexed path is off
     plan[OCN_PLAN_HUB_POSITIONS_HEAVY] = run_pos_heavy_off[n_runs];
+    plan[OCN_PLAN_NUM_CHUNKS] = chunk_off[T];
 }
 
 }  // namespace ocn
@@ -336,7 +337,7 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
     k_plan_positions<<<(int)((T + 2 + threads - 1) / threads), threads, 0, st>>>(out_plan, pos_scanN, run_pos_heavy, run_pos_off,
                                                                                 pos_start);
     OCN_LAUNCH_CHECK();
-    k_plan_finish<<<1, 1, 0, st>>>(T, batch_size, resident_ctas, rec_off, run_unit_off, hub_off, pos_scanN, run_pos_heavy, out_plan);
+    k_plan_finish<<<1, 1, 0, st>>>(T, batch_size, resident_ctas, rec_off, run_unit_off, hub_off, pos_scanN, run_pos_heavy, chunk_off, out_plan);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
 }

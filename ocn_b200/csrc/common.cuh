@@ -84,11 +84,12 @@ struct HubLayout {
     size_t counters;          // uint64[4]: number of items, next item
     size_t prun, prec;        // int32[P] run / uint64[P] record offset of the link of every sorted pair
     size_t key_bits;          // uint32[ceil((n + 1) / 32)]: bit l = node l is a key of the index (has an entry list)
+    size_t item_link;         // int32[chunks + 1]: link of every work item of the per-link kernel
     size_t cub_temp, cub_temp_bytes;    // entry pipeline (caller's stream)
     size_t cub_temp2, cub_temp2_bytes;  // pair pipeline (auxiliary stream)
     size_t total;
 };
-HubLayout hub_layout(int64_t n, int64_t nnz, int64_t pairs, int64_t entries, int64_t positions);
+HubLayout hub_layout(int64_t n, int64_t nnz, int64_t pairs, int64_t entries, int64_t positions, int64_t chunks);
 int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst,
                   int64_t T, const void* plan_scratch, const int64_t* plan_dev, const int64_t* plan_host, void* hub_scratch,
                   size_t hub_scratch_bytes, void* node_scratch, Record* records, int64_t nnz, cudaStream_t st);
@@ -111,6 +112,7 @@ constexpr int kLinkCost = 64;  // fixed cost added to every link so that empty l
 #define OCN_PLAN_USE_DIRECT 7  /* orders <= 2 only: 1 = table-free kernel (short runs), 0 = table kernel */
 #define OCN_PLAN_LONG_COUNT 12 /* entries of the long-destination list */
 #define OCN_PLAN_HUB_ENTRIES_HEAVY 13   /* the part of OCN_PLAN_HUB_ENTRIES that belongs to runs of heavy sources */
+#define OCN_PLAN_NUM_CHUNKS 15           /* work items (link, 32 rows of N(dst)) of the per-link kernel of the indexed path */
 #define OCN_PLAN_HUB_POSITIONS_HEAVY 14 /* the part of OCN_PLAN_HUB_POSITIONS that belongs to runs of heavy sources */
 constexpr int kHeavyRun = 1024;    // a run whose source has more neighbours than this is "heavy": indexed in a pass of its own
 constexpr int kHeavyLink = 1024;   // a link whose source has more neighbours is walked by a whole CTA in the per-link kernels
