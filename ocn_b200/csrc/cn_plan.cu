@@ -93,37 +93,40 @@ __global__ void k_plan_cost(const int64_t* __restrict__ rowptr, const int32_t* _
                             const int64_t* __restrict__ dst, int64_t T, int order, int64_t* __restrict__ cost,
                             int32_t* __restrict__ hub_cnt, int32_t* __restrict__ chunk_cnt, int32_t* __restrict__ long_list,
                             int64_t* __restrict__ plan) {
+    __shared__ unsigned long long s_cost;  // one global reduction per CTA, not one per link on a single address
+    if (threadIdx.x == 0) s_cost = 0ull;
+    __syncthreads();
     const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (t > T) return;
-    if (t == T) {
-        if (lane == 0) { cost[t] = 0; hub_cnt[t] = 0; chunk_cnt[t] = 0; }
-        return;
-    }
-    const int64_t hub_d = plan[OCN_PLAN_HUB_DEGREE];
-    const int64_t j = dst[t];
-    const int64_t rs = rowptr[j], d = rowptr[j + 1] - rs;
-    long long w = 0;
-    int hubs = 0;
-    if (order >= 3) {
-        const int64_t dcap = d < kLongRow ? d : kLongRow;
-        for (int64_t o = lane; o < dcap; o += 32) cost_of_row(rowptr, ldg_i32(col + rs + o), hub_d, w, hubs);
+    if (t == T && lane == 0) { cost[t] = 0; hub_cnt[t] = 0; chunk_cnt[t] = 0; }
+    if (t < T) {
+        const int64_t hub_d = plan[OCN_PLAN_HUB_DEGREE];
+        const int64_t j = dst[t];
+        const int64_t rs = rowptr[j], d = rowptr[j + 1] - rs;
+        long long w = 0;
+        int hubs = 0;
+        if (order >= 3) {
+            const int64_t dcap = d < kLongRow ? d : kLongRow;
+            for (int64_t o = lane; o < dcap; o += 32) cost_of_row(rowptr, ldg_i32(col + rs + o), hub_d, w, hubs);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            w += __shfl_xor_sync(0xffffffffu, w, o);
-            hubs += __shfl_xor_sync(0xffffffffu, hubs, o);
+            for (int o = 16; o > 0; o >>= 1) {
+                w += __shfl_xor_sync(0xffffffffu, w, o);
+                hubs += __shfl_xor_sync(0xffffffffu, hubs, o);
+            }
+        }
+        if (order >= 2) w += d;
+        w += kLinkCost;
+        if (lane == 0) {
+            cost[t] = w;
+            hub_cnt[t] = hubs;
+            chunk_cnt[t] = (int32_t)((d + 31) >> 5);
+            atomicAdd(&s_cost, (unsigned long long)w);
+            if (order >= 3 && d > kLongRow)
+                long_list[atomicAdd((unsigned long long*)&plan[OCN_PLAN_LONG_COUNT], 1ull)] = (int32_t)t;
         }
     }
-    if (order >= 2) w += d;
-    w += kLinkCost;
-    if (lane == 0) {
-        cost[t] = w;
-        hub_cnt[t] = hubs;
-        chunk_cnt[t] = (int32_t)((d + 31) >> 5);
-        atomicAdd((unsigned long long*)&plan[OCN_PLAN_TOTAL_COST], (unsigned long long)w);
-        if (order >= 3 && d > kLongRow)
-            long_list[atomicAdd((unsigned long long*)&plan[OCN_PLAN_LONG_COUNT], 1ull)] = (int32_t)t;
-    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cost) atomicAdd((unsigned long long*)&plan[OCN_PLAN_TOTAL_COST], s_cost);
 }
 
 __global__ void __launch_bounds__(1024)
