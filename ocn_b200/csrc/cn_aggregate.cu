@@ -179,10 +179,9 @@ __global__ void k_stats(const int64_t* __restrict__ rowptr, const int32_t* __res
         walk(t, rs, d, 0, 32, s_a, s_b, minc);
         if (lane == 0) store(t, s_a, s_b, minc);
     }
-    for (int64_t t = blockIdx.x; t < (rec_off[T + 1] != 0 ? T : 0); t += gridDim.x) {
+    for_each_heavy_link(rowptr, src, T, rec_off, [&](int64_t t) {
         const int64_t i = src[t];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
-        if (d <= kHeavyLink) continue;  // uniform over the CTA
         float s_a, s_b;
         uint32_t minc;
         walk(t, rs, d, 32 * (int64_t)wib, 32 * (int64_t)wpb, s_a, s_b, minc);
@@ -195,7 +194,7 @@ __global__ void k_stats(const int64_t* __restrict__ rowptr, const int32_t* __res
             store(t, a, c, m);
         }
         __syncthreads();
-    }
+    });
 }
 
 // one CTA per batch: fixed-order tree sum of the link partials (run-to-run deterministic)
@@ -362,10 +361,9 @@ k_cn_aggregate(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
     }
     // ... a whole CTA per link with a heavy source: every warp sums its share of the chunks, the shares are added to
     // the output rows one warp after the other (warp order: run-to-run deterministic)
-    for (int64_t t = blockIdx.x; t < (rec_off[T + 1] != 0 ? T : 0); t += gridDim.x) {
+    for_each_heavy_link(rowptr, src, T, rec_off, [&](int64_t t) {
         const int64_t i = src[t], j = dst[t];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
-        if (d <= kHeavyLink) continue;  // uniform over the CTA
         float4 a1[VPL], a2[VPL], a3[VPL];
         walk(t, rs, d, 32 * (int64_t)wib, 32 * (int64_t)wpb, a1, a2, a3);
         for (int w = 0; w < wpb; ++w) {
@@ -373,7 +371,7 @@ k_cn_aggregate(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
             __syncthreads();
         }
         if (wib == 0) pair_term(t, i, j);
-    }
+    });
 }
 
 // backward: grad_x[k,:] += w1*g1[t,:] + w2*g2[t,:] + w3*g3[t,:]; pair term by the product rule.
@@ -478,11 +476,11 @@ k_cn_aggregate_bwd(const int64_t* __restrict__ rowptr, const int32_t* __restrict
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
         if (d <= kHeavyLink) walk(t, i, j, rs, d, 0, 32, true);
     }
-    for (int64_t t = blockIdx.x; t < (rec_off[T + 1] != 0 ? T : 0); t += gridDim.x) {  // ... a whole CTA per link with a heavy source
+    for_each_heavy_link(rowptr, src, T, rec_off, [&](int64_t t) {  // ... a whole CTA per link with a heavy source
         const int64_t i = src[t], j = dst[t];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
-        if (d > kHeavyLink) walk(t, i, j, rs, d, 32 * (int64_t)wib, 32 * (int64_t)wpb, wib == 0);
-    }
+        walk(t, i, j, rs, d, 32 * (int64_t)wib, 32 * (int64_t)wpb, wib == 0);
+    });
 }
 
 // ---- sparse extraction ---------------------------------------------------------------------
@@ -574,11 +572,11 @@ __global__ void k_cn_release(const int64_t* __restrict__ rowptr, const int32_t* 
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
         if (d <= kHeavyLink) walk(t, rs, d, lane, 32);
     }
-    for (int64_t t = blockIdx.x; t < (rec_off[T + 1] != 0 ? T : 0); t += gridDim.x) {  // ... a whole CTA per link with a heavy source
+    for_each_heavy_link(rowptr, src, T, rec_off, [&](int64_t t) {  // ... a whole CTA per link with a heavy source
         const int64_t i = src[t];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
-        if (d > kHeavyLink) walk(t, rs, d, threadIdx.x, blockDim.x);
-    }
+        walk(t, rs, d, threadIdx.x, blockDim.x);
+    });
 }
 
 static int grid_for_warps(int64_t items) {

@@ -660,11 +660,11 @@ __global__ void k_cn_colstat(const int64_t* __restrict__ rowptr, const int32_t* 
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
         if (d <= kHeavyLink) walk(t, rs, d, lane, 32);
     }
-    for (int64_t t = blockIdx.x; t < (rec_off[T + 1] != 0 ? T : 0); t += gridDim.x) {  // ... a whole CTA per link with a heavy source
+    for_each_heavy_link(rowptr, src, T, rec_off, [&](int64_t t) {  // ... a whole CTA per link with a heavy source
         const int64_t i = src[t];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
-        if (d > kHeavyLink) walk(t, rs, d, threadIdx.x, blockDim.x);
-    }
+        walk(t, rs, d, threadIdx.x, blockDim.x);
+    });
 }
 
 }  // namespace ocn

@@ -142,4 +142,29 @@ __device__ __forceinline__ bool row_contains(const int32_t* __restrict__ row, in
     return lo < len && __ldg(row + lo) == key;
 }
 
+// The links with a heavy source (more than kHeavyLink neighbours) among t = blockIdx.x, blockIdx.x + gridDim.x, ...:
+// the CTA tests blockDim.x candidates at a time (two dependent loads in all, not two per candidate in turn), collects
+// the heavy ones in shared memory and calls body(t) for each with ALL its threads.  rec_off[T + 1] is the plan's count
+// of such links in the stream (0: nothing to do).
+template <typename Body>
+__device__ __forceinline__ void for_each_heavy_link(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ src,
+                                                    int64_t T, const int64_t* __restrict__ rec_off, Body&& body) {
+    __shared__ int s_n;
+    __shared__ long long s_list[1024];
+    if (rec_off[T + 1] == 0) return;
+    for (int64_t c0 = 0; (int64_t)blockIdx.x + c0 * gridDim.x < T; c0 += blockDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        const int64_t t = (int64_t)blockIdx.x + (c0 + threadIdx.x) * gridDim.x;
+        if (t < T) {
+            const int64_t i = src[t];
+            if (rowptr[i + 1] - rowptr[i] > kHeavyLink) s_list[atomicAdd(&s_n, 1)] = t;
+        }
+        __syncthreads();
+        const int n = s_n;
+        for (int k = 0; k < n; ++k) body((int64_t)s_list[k]);
+    }
+}
+
 }  // namespace ocn
