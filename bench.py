@@ -63,6 +63,8 @@ def parse():
                     help="end-to-end leg: consecutive steps alternate between this many CUDA streams, so that the copies, "
                          "the small head / gather kernels and the D2H read of one step overlap the walks of the next "
                          "(measured 41.0 -> 43.2 M links/s); the device-resident leg always uses one stream")
+    ap.add_argument("--device-streams", type=int, default=1,
+                    help="device-resident leg: consecutive steps alternate between this many of the --streams streams")
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed device steps (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -300,8 +302,8 @@ def main():
         for st in streams:
             torch.cuda.current_stream().wait_stream(st)
 
-    def step_device(s):  # device-resident leg: one stream (measured: a second stream does not raise its throughput)
-        with torch.cuda.stream(streams[0]):
+    def step_device(s):  # device-resident leg
+        with torch.cuda.stream(streams[s % max(1, min(a.device_streams, len(streams)))]):
             e = e_rank[:, s * T:(s + 1) * T]
             sess = ob.CNSession(G, e, a.batch, a.order, a.hub, plan_stream=plan_stream).build(a.order, True)
             sess.stats(5, 0.0, ip3, 0)
@@ -434,9 +436,10 @@ def main():
             "e2e": {"value": links / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * T,
                     "d2h_bytes_per_step": 4 * T * (world if world > 1 else 1), "ms_per_step": ms_e2e / a.steps,
                     "api": "CNLinkPredictor*.forward(h, adj, CNSession, ..., edges) -> scores.cpu()"},
-            # own kernels per step (CUB scans / radix sorts not counted): 7 plan + 10 build (indexed path; 2 with
-            # the table kernel) + 3 stats + aggregate + release
-            "gpu_launches": ((22 if indexed else 14) * a.steps),
+            # own kernels per device-resident step, counted in profiles/r01_launches_v24.txt (CUB scans / radix sorts
+            # not counted): 8 plan + 11 build (indexed path; the table path has k_cn_build + k_cn_colstat, plus
+            # k_cn_build_direct for orders <= 2) + 3 stats + aggregate + release
+            "gpu_launches": ((24 if indexed else (15 + (1 if a.order <= 2 else 0))) * a.steps),
             "roofline": {"bound": "hbm", "kernel": kern_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kern_bytes, "kernel_ms": kern_avg,
