@@ -473,8 +473,16 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
                         if (__any_sync(0xffffffffu, pos - win_lo >= win_n)) break;  // past the window (or the list)
                     }
                 } else {
-#pragma unroll 2
-                    for (uint32_t e = e0 + lane; e < e1; e += 32) count_walk<false>(U, __ldg(eval + e), 0u, 0u);
+                    // the lists are 33 .. ~230 entries long: 128 entries per round, all loads issued before the first
+                    // counter is touched
+                    for (uint32_t e = e0 + lane; e < e1; e += 128) {
+                        uint32_t pv[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) pv[k] = (e + 32u * k < e1) ? __ldg(eval + e + 32u * k) : 0xffffffffu;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (pv[k] != 0xffffffffu) count_walk<false>(U, pv[k], 0u, 0u);
+                    }
                 }
             }
         }
