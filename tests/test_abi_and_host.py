@@ -91,3 +91,71 @@ def test_predictor_state_dict_keys_match_reference_layout():
         assert k in keys, k
     p6 = ob.CNLinkPredictor3hopCNs(32, 32, 1, 3, 0.0)
     assert "xcn3lin.7.weight" in p6.state_dict() and "xcn4lin.0.weight" not in p6.state_dict()
+
+
+def test_head_parameter_packing_layout():
+    """Host logic of the fused head (ocn_b200/head.py): the flat parameter buffer read back in the order csrc/head.cu
+    documents reproduces the module's own forward (CPU, no kernel involved)."""
+    import torch.nn.functional as F
+    from ocn_b200 import head
+    from ocn_b200.predictor import CNLinkPredictor3hopCNs
+
+    for ln, tailact, two in ((False, False, False), (True, False, True), (True, True, False)):
+        torch.manual_seed(3)
+        I, H, O = 32, 64, 2
+        pred = CNLinkPredictor3hopCNs(I, H, O, 3, 0.0, ln=ln, tailact=tailact, twolayerlin=two).eval()
+        st = {"three": True}
+        pieces = head._pack_seq(pred.xcn1lin) + head._pack_seq(pred.xcn2lin) + head._pack_seq(pred.xcn3lin) \
+            + head._pack_seq(pred.xijlin) + head._pack_seq(pred.lin, last_plain=True)
+        flat = torch.cat([p.detach().reshape(-1) for p in pieces])
+        assert head._flags(pred) == (1 if ln else 0) | (2 if tailact else 0) | (4 if two else 0)
+        off = 0
+
+        def take(n):
+            nonlocal off
+            v = flat[off:off + n]
+            off += n
+            return v
+
+        def lin_t(x, i, o):  # weights are stored transposed: [in, out]
+            w, b = take(i * o).view(i, o), take(o)
+            return x @ w + b
+
+        def norm(x):
+            g, b = take(H), take(H)
+            return F.layer_norm(x, (H,), g, b, 1e-5)
+
+        xs = [torch.randn(7, I) for _ in range(4)]
+        with torch.no_grad():
+            alpha = torch.sigmoid(pred.alpha).cumprod(-1)
+            mix = [float(alpha[0]), float(alpha[1]), float(alpha[2]), float(pred.beta)]
+            z = 0
+            for br in range(3):
+                a = torch.relu(lin_t(xs[br], I, H))
+                a = lin_t(a, H, H)
+                if ln:
+                    a = norm(a)
+                a = lin_t(torch.relu(a), H, H)
+                z = z + mix[br] * a
+            a = lin_t(xs[3], I, H)
+            if ln:
+                a = norm(a)
+            a = torch.relu(a)
+            if not tailact:
+                a = lin_t(a, H, H)
+            z = z + mix[3] * a
+            a = lin_t(z, H, H)
+            if ln:
+                a = norm(a)
+            a = torch.relu(a)
+            if two:
+                a = lin_t(a, H, H)
+                if ln:
+                    a = norm(a)
+                a = torch.relu(a)
+            wo, bo = take(O * H).view(O, H), take(O)  # the last Linear keeps its [out, in] layout
+            out = a @ wo.t() + bo
+            assert off == flat.numel()
+            pred.fuse_head = False
+            ref = pred._head(xs[0], xs[1], xs[2], xs[3])
+        assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)
