@@ -18,5 +18,5 @@ __all__ = [
     "Graph", "CNSession", "SparseRows", "adjoverlap", "cn_aggregate_eval", "get_cn", "get_cn1_cn2",
     "gcn_norm", "gcnconv_propagate", "pure_conv", "pure_conv3_gcn", "sparse_tensor_multiply", "spgemm_a2",
     "spmm", "spmm_add", "spmm_max", "spmm_mean", "CNLinkPredictorOringin", "CNLinkPredictor3hopCNs",
-    "CNLinkPredictorbaselearn", "predictor_dict", "synth",
+    "CNLinkPredictorbaselearn", "predictor_dict", "synth", "reserve_stream_pool", "metrics", "dist",
 ]
