@@ -525,7 +525,7 @@ __device__ __forceinline__ void link_lookup(const uint4* __restrict__ node_index
                                             const uint32_t* __restrict__ eval,
                                             uint32_t l, uint32_t r, uint32_t pos_lo, uint32_t pos_hi,
                                             unsigned* __restrict__ rec, unsigned inc) {
-    if (((__ldg(key_bits + (l >> 5)) >> (l & 31u)) & 1u) == 0u) return;  // l has no entry list (most nodes)
+    if (key_bits != nullptr && ((__ldg(key_bits + (l >> 5)) >> (l & 31u)) & 1u) == 0u) return;  // l has no entry list (most nodes)
     const uint4 he = __ldg(node_index + l);
     if ((((r & 32u) ? he.w : he.z) >> (r & 31u) & 1u) == 0u) return;  // no entry of l in a run of this signature bit
     uint32_t lo = he.x, hi = he.y;
@@ -582,13 +582,24 @@ k_cn_link(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, c
         const int incl = warp_incl_scan(cnt, lane);
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         const int excl = incl - cnt;
-        for (int j0 = 0; j0 < total; j0 += 32) {  // C3 through the rows this link does not share
-            const int jj = j0 + lane;
-            const int s = owner_lane(excl, jj);
-            const int64_t rs_o = __shfl_sync(0xffffffffu, rs_m, s);
-            const int eexcl = __shfl_sync(0xffffffffu, excl, s);
-            if (jj < total)
-                link_lookup(node_index, key_bits, eval, (uint32_t)ldg_i32(col + rs_o + (jj - eexcl)), r, pos_lo, pos_hi, rec + 1, 1u);
+        // C3 through the rows this link does not share: 128 columns per round -- the four column loads, then the four
+        // key-map words are in flight together; the few columns that are keys go on to the index
+        for (int j0 = 0; j0 < total; j0 += 128) {
+            int32_t lc[4];
+            uint32_t bw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int jj = j0 + 32 * k + lane;
+                const int s = owner_lane(excl, jj);
+                const int64_t rs_o = __shfl_sync(0xffffffffu, rs_m, s);
+                const int eexcl = __shfl_sync(0xffffffffu, excl, s);
+                lc[k] = (jj < total) ? ldg_i32(col + rs_o + (jj - eexcl)) : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bw[k] = lc[k] >= 0 ? __ldg(key_bits + (lc[k] >> 5)) : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((bw[k] >> (lc[k] & 31)) & 1u) link_lookup(node_index, nullptr, eval, (uint32_t)lc[k], r, pos_lo, pos_hi, rec + 1, 1u);
         }
     }
 }
