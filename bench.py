@@ -436,7 +436,7 @@ def main():
             "e2e": {"value": links / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * T,
                     "d2h_bytes_per_step": 4 * T * (world if world > 1 else 1), "ms_per_step": ms_e2e / a.steps,
                     "api": "CNLinkPredictor*.forward(h, adj, CNSession, ..., edges) -> scores.cpu()"},
-            # own kernels per device-resident step, counted in profiles/r01_launches_v25.txt (CUB scans / radix sorts
+            # own kernels per device-resident step, counted in profiles/r01_launches_v26.txt (CUB scans / radix sorts
             # not counted): 8 plan + 11 build (indexed path; the table path has k_cn_build + k_cn_colstat, plus
             # k_cn_build_direct for orders <= 2) + 3 stats + aggregate + release
             "gpu_launches": ((24 if indexed else (15 + (1 if a.order <= 2 else 0))) * a.steps),

@@ -78,6 +78,8 @@ def packed_params(pred, in_ch: int) -> Tensor:
         flat = torch.cat([t.detach().float().reshape(-1) for t in pieces]).contiguous()
         alpha = torch.sigmoid(pred.alpha).cumprod(-1)
         mix = torch.cat((alpha[:3].float(), pred.beta.detach().float().reshape(1))).contiguous()
+    if flat.is_cuda:  # rare (a parameter changed): finished before any other stream may read the cached buffers
+        torch.cuda.current_stream(flat.device).synchronize()
     pred.__dict__["_ocn_head_cache"] = (key, flat, mix)
     return flat, mix
 

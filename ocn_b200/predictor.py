@@ -112,6 +112,18 @@ class _OCNBase(nn.Module):
         ip3 = self.innerprod.detach().float().repeat(3).contiguous()
         return sess.stats(5, fill, ip3, 0)[0, 1].detach().clone()
 
+    def _ip3(self) -> Tensor:
+        """The inner-product buffer broadcast to the three coefficient slots of the kernels; rebuilt only when the
+        buffer changed (three tiny launches per call otherwise, in an evaluation loop that never updates it)."""
+        key = (self.innerprod.data_ptr(), self.innerprod._version)
+        c = self.__dict__.get("_ip3_cache")
+        if c is None or c[0] != key:
+            c = (key, self.innerprod.detach().float().reshape(-1)[:1].repeat(3).contiguous())
+            if c[1].is_cuda:  # rare: finished before any other stream may read the cached tensor
+                torch.cuda.current_stream(c[1].device).synchronize()
+            self.__dict__["_ip3_cache"] = c
+        return c[1]
+
     def cn_stage(self, x: Tensor, adj: Graph, tar_ei: Tensor, fill: float = 0.0, sess: Optional[CNSession] = None,
                  ip: Optional[Tensor] = None):
         """``ip``: use this inner-product coefficient (shape [1]) instead of reading / updating the module's
@@ -119,7 +131,7 @@ class _OCNBase(nn.Module):
         if sess is None:
             sess = CNSession(adj, tar_ei, None, self.order)
             sess.build(self.order, self.weighted)
-        ip3 = (self.innerprod if ip is None else ip).detach().float().reshape(-1)[:1].repeat(3).contiguous()
+        ip3 = self._ip3() if ip is None else ip.detach().float().reshape(-1)[:1].repeat(3).contiguous()
         if self.variant == 5 and ip is not None:
             if self.order >= 3:
                 raise ValueError("an explicit coefficient is supported for order 2 (cn5); the order-3 template chains "
