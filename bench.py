@@ -287,19 +287,20 @@ def main():
     plan_stream = None if a.no_plan_stream else torch.cuda.Stream(device=dev)
 
     streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, a.streams))]
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     # one cached block per stream (and one for the default stream of the roofline leg): the per-session buffers are
     # carved out of it, no cudaMalloc (1 - 40 ms when it happens) inside a timed region
     ob.reserve_stream_pool(2 << 30, dev)
-    for st_ in streams + ([plan_stream] if plan_stream is not None else []):
+    for st_ in streams + [st2 for st2 in (plan_stream, comm_stream) if st2 is not None]:
         with torch.cuda.stream(st_):
-            ob.reserve_stream_pool(4 << 30 if st_ is not plan_stream else 1 << 30, dev)
+            ob.reserve_stream_pool(4 << 30 if st_ in streams else 1 << 30, dev)
 
     def fork():  # the work streams start after everything already queued on the default stream ...
         for st in streams:
             st.wait_stream(torch.cuda.current_stream())
 
     def join():  # ... and the default stream (where the timing events are recorded) waits for all of them
-        for st in streams:
+        for st in streams + ([comm_stream] if comm_stream is not None else []):
             torch.cuda.current_stream().wait_stream(st)
 
     def step_device(s):  # device-resident leg
@@ -322,16 +323,24 @@ def main():
                 out = pred(x, G, sess, None, None, e)
             else:
                 out = pred(x, G, sess, None, e)
-            scores = out.squeeze(-1)
+            scores = out.squeeze(-1).contiguous()
             if world > 1:
+                # the gather runs on ONE communication stream: issued from the two alternating work streams, NCCL
+                # would order the streams against each other and undo their overlap
                 import torch.distributed as dist
-                allsc = torch.empty(world * T, dtype=scores.dtype, device=dev)
-                dist.all_gather_into_tensor(allsc, scores.contiguous())
-                scores = allsc
-            # device -> host read of the step's result: asynchronous copy into pinned memory (an evaluation loop
-            # collects the scores of every batch and ranks them at the end); the timed region ends with a full sync
-            n_out = scores.numel() if rank == 0 else 1
-            out_host[s][:n_out].copy_(scores[:n_out], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()
+                with torch.cuda.stream(comm_stream):
+                    comm_stream.wait_event(done)
+                    scores.record_stream(comm_stream)
+                    allsc = torch.empty(world * T, dtype=scores.dtype, device=dev)
+                    dist.all_gather_into_tensor(allsc, scores)
+                    n_out = allsc.numel() if rank == 0 else 1
+                    out_host[s][:n_out].copy_(allsc[:n_out], non_blocking=True)
+            else:
+                # device -> host read of the step's result: asynchronous copy into pinned memory (an evaluation loop
+                # collects the scores of every batch and ranks them at the end); the timed region ends with a full sync
+                out_host[s][:scores.numel()].copy_(scores, non_blocking=True)
         return out_host[s]
 
     def barrier():
