@@ -8,8 +8,8 @@ One *step* = one pass of the hot path (CN sets of orders 1..3 -> batch normalisa
 orthogonalisation -> CN-indicator SpMM + pair term) over ``--batches`` consecutive link batches of
 2048 links in the shape of the citation2 evaluation stream (NeighborOverlapCitation2.py:241-254:
 every source against 1000 uniform destinations).  Under torchrun every rank holds a replica of
-the graph and features and scores its own batches (weak scaling, no data-path collective); the
-end-to-end arm gathers the fp32 scores with NCCL.
+the graph and features and scores its own batches (weak scaling, no data-path collective); in the
+end-to-end arm every rank reads its scores back per step and the ranks gather all fp32 scores once at the end (NCCL).
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the byte accounting.
 """
@@ -24,7 +24,11 @@ import sys
 import threading
 import time
 
-import torch
+# every kernel is loaded at start-up: with CUDA's default lazy loading the first launch of a kernel variant that the
+# warm-up steps did not reach (e.g. the CTA-wide counter variant a hub source needs) stalls a timed step for milliseconds
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -63,6 +67,8 @@ def parse():
                     help="end-to-end leg: consecutive steps alternate between this many CUDA streams, so that the copies, "
                          "the small head / gather kernels and the D2H read of one step overlap the walks of the next "
                          "(measured 41.0 -> 43.2 M links/s); the device-resident leg always uses one stream")
+    ap.add_argument("--slice-offset", type=int, default=0,
+                    help="skip this many steps' worth of links of the stream (one GPU re-enacts the slices another rank gets)")
     ap.add_argument("--device-streams", type=int, default=1,
                     help="device-resident leg: consecutive steps alternate between this many of the --streams streams")
     ap.add_argument("--profile-range", action="store_true",
@@ -274,7 +280,7 @@ def main():
     T = a.batch * a.batches
     nsteps = a.steps + a.warmup
     # every rank scores its own slice of the stream; every step gets fresh links
-    e_all = g.query_edges(world * nsteps * T, "stream", device=dev)
+    e_all = g.query_edges((world * nsteps + a.slice_offset) * T, "stream", device=dev)[:, a.slice_offset * T:]
     e_rank = e_all[:, rank * nsteps * T:(rank + 1) * nsteps * T].contiguous()
     e_host = e_rank.cpu().pin_memory()
     torch.manual_seed(0)
@@ -324,24 +330,31 @@ def main():
             else:
                 out = pred(x, G, sess, None, e)
             scores = out.squeeze(-1).contiguous()
+            # device -> host read of the step's result: asynchronous copy into pinned memory (an evaluation loop
+            # collects the scores of every batch and ranks them at the end); the timed region ends with a full sync.
+            # With several ranks every rank reads back its own scores; the ranks meet ONCE, in the final gather
+            # (north_star: "the final gather of scores") -- a gather per step would couple the ranks step by step.
+            out_host[s][:T].copy_(scores, non_blocking=True)
             if world > 1:
-                # the gather runs on ONE communication stream: issued from the two alternating work streams, NCCL
-                # would order the streams against each other and undo their overlap
-                import torch.distributed as dist
-                done = torch.cuda.Event()
-                done.record()
-                with torch.cuda.stream(comm_stream):
-                    comm_stream.wait_event(done)
-                    scores.record_stream(comm_stream)
-                    allsc = torch.empty(world * T, dtype=scores.dtype, device=dev)
-                    dist.all_gather_into_tensor(allsc, scores)
-                    n_out = allsc.numel() if rank == 0 else 1
-                    out_host[s][:n_out].copy_(allsc[:n_out], non_blocking=True)
-            else:
-                # device -> host read of the step's result: asynchronous copy into pinned memory (an evaluation loop
-                # collects the scores of every batch and ranks them at the end); the timed region ends with a full sync
-                out_host[s][:scores.numel()].copy_(scores, non_blocking=True)
+                rank_scores[s].copy_(scores)
         return out_host[s]
+
+    rank_scores = torch.empty(nsteps, T, dtype=torch.float32, device=dev) if world > 1 else None
+    gathered_host = torch.empty(world * a.steps * T, dtype=torch.float32).pin_memory() if world > 1 else None
+
+    def final_gather():
+        """All ranks' scores of the timed steps, gathered once on the communication stream and read by rank 0."""
+        if world <= 1:
+            return
+        import torch.distributed as dist
+        for st in streams:
+            comm_stream.wait_stream(st)
+        with torch.cuda.stream(comm_stream):
+            mine = rank_scores[a.warmup:].reshape(-1)
+            allsc = torch.empty(world * mine.numel(), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(allsc, mine)
+            if rank == 0:
+                gathered_host.copy_(allsc, non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -357,7 +370,7 @@ def main():
     except Exception:
         pass
 
-    def timed(fn, profile=False):
+    def timed(fn, profile=False, finalize=None):
         for s in range(a.warmup):
             fn(s)
         barrier()
@@ -372,6 +385,8 @@ def main():
         fork()
         for s in range(a.warmup, nsteps):
             fn(s)
+        if finalize is not None:
+            finalize()
         join()
         ev1.record()
         barrier()
@@ -389,7 +404,7 @@ def main():
         return ms, wall, clocks
 
     ms_dev, _, clocks = timed(step_device, a.profile_range)
-    ms_e2e_ev, wall_e2e, _ = timed(step_e2e)
+    ms_e2e_ev, wall_e2e, _ = timed(step_e2e, finalize=final_gather)
     ms_e2e = max(ms_e2e_ev, wall_e2e * 1e3)  # the D2H read ends after the last event: use the host clock too
 
     # roofline of the dominant kernel: CUDA events recorded by the library on the build's stream right
@@ -442,8 +457,9 @@ def main():
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 walk counts / f32 features", "data": "synthetic", "config": workload_config(a, g),
             "clocks": clocks,
-            "e2e": {"value": links / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * T,
-                    "d2h_bytes_per_step": 4 * T * (world if world > 1 else 1), "ms_per_step": ms_e2e / a.steps,
+            "e2e": {"value": links / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * T * world,
+                    "d2h_bytes_per_step": 4 * T * world, "ms_per_step": ms_e2e / a.steps,
+                    "final_gather_bytes": (4 * T * a.steps * world * world) if world > 1 else 0,
                     "api": "CNLinkPredictor*.forward(h, adj, CNSession, ..., edges) -> scores.cpu()"},
             # own kernels per device-resident step, counted in profiles/r01_launches_v26.txt (CUB scans / radix sorts
             # not counted): 8 plan + 11 build (indexed path; the table path has k_cn_build + k_cn_colstat, plus

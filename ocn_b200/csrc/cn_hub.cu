@@ -789,6 +789,8 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
         return fail(OCN_ENOSPACE, "ocn_cn_build: hub scratch %zu < %zu bytes", hub_scratch_bytes, need);
     HubAux* aux = nullptr;
     if (int rc = hub_aux(st, &aux)) return rc;
+    HubAux* aux_h = nullptr;  // created with the first call on this stream, not with the first hub source
+    if (int rc = hub_aux(aux->heavy_stream, &aux_h)) return rc;
     PlanLayout L = plan_layout(T);
     const char* pb = (const char*)plan_scratch;
     if (NP_heavy == 0)  // the usual stream: one pass over the plain prefix
@@ -799,8 +801,6 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
     // the light pass
     OCN_CUDA(cudaEventRecord(aux->hev[0], st));
     OCN_CUDA(cudaStreamWaitEvent(aux->heavy_stream, aux->hev[0], 0));
-    HubAux* aux_h = nullptr;
-    if (int rc = hub_aux(aux->heavy_stream, &aux_h)) return rc;
     if (int rc = hub_pass(rowptr, col, n, src, dst, T, plan_scratch, plan_dev, (const int64_t*)(pb + L.run_pos_heavy), hub_d, P,
                           E_heavy, NP_heavy, R, H, (char*)hub_scratch + H.total, (uint4*)node_scratch + n, records, aux_h, false,
                           aux->heavy_stream))
