@@ -84,13 +84,14 @@ def dist_env():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (NVML, ~2 ms period; nvidia-smi
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, 2 ms period, 5 ms with several ranks; nvidia-smi
     as a fallback).  A daemon thread polls while the steps run."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period: float = 0.002):
         self.index, self.sm, self.bits, self.stop_flag, self.thread = index, [], 0, False, None
+        self.period = period
         self.max_mhz, self.h = None, None
         try:
             import pynvml
@@ -121,7 +122,7 @@ class ClockSampler:
                 self._sample()
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def start(self):
         self.sm, self.bits, self.stop_flag = [], 0, False
@@ -364,7 +365,7 @@ def main():
 
     # NVML is initialised (and queried once) before any timed region: its first calls take driver locks for
     # milliseconds and would otherwise stall the launches of the first timed steps
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, 0.002 if world == 1 else 0.005)  # N ranks share the host cores: poll less often
     try:
         sampler._sample()
     except Exception:
