@@ -31,6 +31,15 @@ def test_argument_errors_do_not_need_a_gpu():
     assert rc == -1
     rc = L.ocn_spgemm_a2_symbolic(None, None, 4, 0, None, None, None)
     assert rc == -1
+    # the entry points either side of the path (graph build / mask, fused head, metrics)
+    assert L.ocn_graph_build_bytes(1000, 1) > 2 * 1000 * (8 + 8 + 8 + 4) and L.ocn_graph_mask_bytes(100, 10) > 0
+    assert L.ocn_graph_build_count(None, None, None, 5, 10, 1, None, 0, None, None, None) == -1
+    assert L.ocn_graph_mask_count(None, None, None, 10, 0, None, None, 0, 1, None, None, 0, None, None, None) == -1
+    assert L.ocn_cn_head_params(32, 32, 1, 0, 2) == 2 * (32 * 32 * 3 + 32 * 3) + (32 * 32 * 2 + 64) + (32 * 32 + 32 + 32 + 1)
+    assert L.ocn_cn_head_params(256, 256, 1, 0, 2) == -1 and L.ocn_cn_head_params(64, 64, 1, 4, 3) == -1  # beyond 200 KB
+    assert L.ocn_cn_head(None, None, None, None, 5, 32, 32, 1, 0, None, 0, None, None, None) == -1
+    assert L.ocn_hits_bytes(1000) >= 4000 and L.ocn_mrr(None, None, 3, 4, None, None) == -1
+    assert L.ocn_rows_difference_count(None, None, None, None, None, None, 3, None, None) == -1
 
 
 def test_no_cpu_fallback():
@@ -45,6 +54,14 @@ def test_no_cpu_fallback():
         ob.spmm_add(G, torch.zeros(30, 4))
     with pytest.raises(_lib.OcnError):
         ob.pure_conv(torch.zeros(30, 4), G, "gcn")
+    with pytest.raises(_lib.OcnError):
+        G.masked(e)
+    with pytest.raises(_lib.OcnError):
+        ob.metrics.mrr_list(torch.zeros(4), torch.zeros(4, 10))
+    with pytest.raises(_lib.OcnError):
+        ob.metrics.hits_at_k(torch.zeros(4), torch.zeros(40), 3)
+    with pytest.raises(_lib.OcnError):
+        ob.adjoverlap(G, G, e, calresadj=True)
 
 
 def test_product_never_imports_oracle():
