@@ -176,3 +176,22 @@ def test_head_parameter_packing_layout():
             pred.fuse_head = False
             ref = pred._head(xs[0], xs[1], xs[2], xs[3])
         assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_header_is_plain_c():
+    """include/ocn_b200.h is what a cgo / ctypes / JNI maintainer binds: it must compile as C99 on its own."""
+    import shutil
+    import subprocess
+    import tempfile
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
+        f.write('#include "include/ocn_b200.h"\nint main(void) { return ocn_abi_version() == OCN_ABI_VERSION ? 0 : 1; }\n')
+        path = f.name
+    try:
+        res = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", root, path], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+    finally:
+        os.unlink(path)
