@@ -168,3 +168,44 @@ def test_pure_conv_gcn_dense():
     dd = ahat.sum(1).pow(-0.5)
     assert torch.allclose(R.gcnconv_propagate(x, A, True, True), (dd[:, None] * ahat * dd[None, :]) @ x, atol=1e-5)
     assert torch.allclose(R.pure_conv3_gcn(x, A), (d * a * d.t()) @ x, atol=1e-5)
+
+
+def test_adjoverlap_calresadj_and_masked_adjacency_vs_sets():
+    """The oracle restatements of the steps either side of the path against python sets: adjoverlap(calresadj=True)
+    (utils.py:260-274) and the --maskinput adjacency (NeighborOverlap_large.py:49-63)."""
+    g = synth.tiny_graph(60, 300, 9)
+    A = R.sp_from_csr(g.rowptr, g.col)
+    nbr = [set(g.col[int(g.rowptr[v]):int(g.rowptr[v + 1])].tolist()) for v in range(g.n)]
+    e = g.query_edges(40, "mixed")
+    ov, r1, r2 = R.adjoverlap(A, A, e, calresadj=True)
+    for b in range(e.shape[1]):
+        i, j = int(e[0, b]), int(e[1, b])
+        got = [set(s.col[s.row == b].tolist()) for s in (ov, r1, r2)]
+        assert got == [nbr[i] & nbr[j], nbr[i] - nbr[j], nbr[j] - nbr[i]]
+    # masked adjacency: duplicates and reversed copies of an edge keep it alive until every copy is masked
+    el = torch.tensor([[0, 0, 1, 2, 3, 3], [1, 1, 0, 3, 2, 4]])
+    full = R.masked_adjacency(el, 5)
+    assert _pairs(full) == [(0, 1), (1, 0), (2, 3), (3, 2), (3, 4), (4, 3)]
+    assert _pairs(R.masked_adjacency(el, 5, torch.tensor([0, 1]))) == _pairs(full)          # (1, 0) still lists the pair
+    assert _pairs(R.masked_adjacency(el, 5, torch.tensor([0, 1, 2]))) == [(2, 3), (3, 2), (3, 4), (4, 3)]
+    assert _pairs(R.masked_adjacency(el, 5, torch.tensor([5]), symmetric=False)) == [(0, 1), (1, 0), (2, 3), (3, 2)]
+
+
+def test_spmm_max_backward_matches_autograd():
+    """First-arg-max gradient routing of spmm_max (no ties in random data: equals torch's amax backward)."""
+    g = synth.make_graph("cora")
+    A = R.sp_from_csr(g.rowptr, g.col)
+    x = g.features(6)
+    w = torch.randn(g.n, 6, generator=torch.Generator().manual_seed(4))
+    xr = x.clone().requires_grad_(True)
+    out = torch.full((g.n, 6), float("-inf")).index_reduce(0, A.row, A.values().unsqueeze(1) * xr[A.col], "amax", include_self=True)
+    out = torch.where(torch.isinf(out), torch.zeros_like(out), out)
+    (out * w).sum().backward()
+    assert torch.allclose(R.spmm_max_backward(A, x, w), xr.grad, rtol=1e-5, atol=1e-5)
+    # ties: the first maximum in row order takes the whole gradient
+    xt = torch.zeros(g.n, 1)
+    gx = R.spmm_max_backward(A, xt, torch.ones(g.n, 1))
+    deg = g.rowptr[1:] - g.rowptr[:-1]
+    first = g.col[g.rowptr[:-1][deg > 0]].long()
+    ref = torch.zeros(g.n, 1).index_add_(0, first, torch.ones(first.numel(), 1))
+    assert torch.equal(gx, ref)
