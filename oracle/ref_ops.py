@@ -43,8 +43,12 @@ class Sp:
         return self.val if self.val is not None else torch.ones(self.nnz, dtype=torch.float32)
 
     def rowptr(self) -> Tensor:
-        rp = torch.zeros(self.shape[0] + 1, dtype=torch.int64)
-        torch.cumsum(torch.bincount(self.row, minlength=self.shape[0]), 0, out=rp[1:])
+        # cached like torch_sparse's SparseStorage._rowptr (an Sp is never mutated after construction)
+        rp = getattr(self, "_rowptr_cache", None)
+        if rp is None:
+            rp = torch.zeros(self.shape[0] + 1, dtype=torch.int64)
+            torch.cumsum(torch.bincount(self.row, minlength=self.shape[0]), 0, out=rp[1:])
+            self._rowptr_cache = rp
         return rp
 
     def to_dense(self) -> Tensor:
@@ -182,10 +186,7 @@ def spspmm_expand(a: Sp, b: Sp) -> Sp:
     """pygho ``spspmm(A, 1, B, 0)`` the way pygho computes it [recalled]: every nonzero (r, k) of A is
     expanded against row k of B (searchsorted/cumsum bookkeeping), the products are keyed by (r, c),
     sorted/uniqued and scatter-summed.  Pure index arithmetic -- no library SpGEMM."""
-    rp = getattr(b, "_rowptr_cache", None)
-    if rp is None:
-        rp = b.rowptr()
-        b._rowptr_cache = rp
+    rp = b.rowptr()
     start = rp[a.col]
     cnt = rp[a.col + 1] - start
     total = int(cnt.sum())
