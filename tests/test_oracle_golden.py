@@ -209,3 +209,47 @@ def test_spmm_max_backward_matches_autograd():
     first = g.col[g.rowptr[:-1][deg > 0]].long()
     ref = torch.zeros(g.n, 1).index_add_(0, first, torch.ones(first.numel(), 1))
     assert torch.equal(gx, ref)
+
+
+def test_oracle_edge_cases_vs_bruteforce():
+    """Empty batch, endpoints without neighbours, i == j, a link repeated inside one batch (its CN columns
+    count twice in the column statistics, model.py:2261) -- the cases the driver loops can produce
+    (utils.py:218 is the reference's own empty-input guard; negative sampling draws isolated nodes and repeats)."""
+    n = 30
+    g = synth.tiny_graph(n, 60, 11)
+    rp, col = g.rowptr.numpy(), g.col.numpy()
+    deg = np.diff(rp)
+    A = R.sp_from_csr(g.rowptr, g.col)
+    a = brute.dense_adj(rp, col, n)
+    # empty batch: every CN matrix is [0 x n] with no entries, aggregates are [0 x F]
+    e0 = torch.zeros(2, 0, dtype=torch.int64)
+    cns = R.get_cn(A, e0, 3)
+    assert [c.nnz for c in cns] == [0, 0, 0] and all(c.shape == (0, n) for c in cns)
+    assert R.adjoverlap(A, A, e0).nnz == 0
+    x = g.features(4)
+    out = R.cn6_aggregate(cns[0], cns[1], cns[2], x, e0, R.InnerProdState(), training=False)
+    assert all(o.shape == (0, 4) for o in out[:4])
+    # isolated endpoints (made by removing a node's row and column), self link, repeated link
+    iso = int(np.argmax(deg))
+    keep = (A.row != iso) & (A.col != iso)
+    A2 = R.Sp(A.row[keep], A.col[keep], None, A.shape)
+    a2 = a.copy()
+    a2[iso, :] = 0
+    a2[:, iso] = 0
+    other = int(np.argsort(deg)[-2])
+    e = torch.tensor([[iso, other, other, 3, 3, 5], [other, iso, other, 7, 7, 5]], dtype=torch.int64)
+    cns = R.get_cn(A2, e, 3)
+    for k in (1, 2, 3):
+        ref = brute.cn_sets(a2, e.numpy(), k)
+        rows = _rows(cns[k - 1], e.shape[1])
+        for b in range(e.shape[1]):
+            assert sorted(rows[b]) == ref[b][0].tolist()
+            assert [rows[b][c] for c in sorted(rows[b])] == ref[b][1].astype(float).tolist()
+        assert rows[0] == {} and rows[1] == {}          # no neighbours on one side: empty set at every order
+        assert rows[3] == rows[4]                       # the repeated link
+    # i == j at order 1 is the whole row
+    assert sorted(_rows(cns[0], 6)[2]) == np.nonzero(a2[other])[0].tolist()
+    outs = R.cn6_aggregate(cns[0], cns[1], cns[2], x, e, R.InnerProdState(0.25), training=False)[:3]
+    ref = brute.cn5_dense(a2, e.numpy(), x.double().numpy(), float(np.float32(0.25)), 3, True)
+    for o, r in zip(outs, ref):
+        assert np.abs(o.double().numpy() - r).max() <= 2e-4 * (1.0 + np.abs(r).max())
