@@ -69,6 +69,10 @@ def parse():
                          "(measured 41.0 -> 43.2 M links/s); the device-resident leg always uses one stream")
     ap.add_argument("--slice-offset", type=int, default=0,
                     help="skip this many steps' worth of links of the stream (one GPU re-enacts the slices another rank gets)")
+    ap.add_argument("--deal", choices=("cost", "contiguous"), default="cost",
+                    help="several ranks: 'cost' deals the timed slices of the stream so that every rank gets the same "
+                         "number of slices and a balanced predicted cost (ocn_b200.dist.predicted_walk_cost / "
+                         "deal_by_cost); 'contiguous' gives rank r the r-th run of consecutive slices")
     ap.add_argument("--device-streams", type=int, default=1,
                     help="device-resident leg: consecutive steps alternate between this many of the --streams streams")
     ap.add_argument("--profile-range", action="store_true",
@@ -283,6 +287,22 @@ def main():
     # every rank scores its own slice of the stream; every step gets fresh links
     e_all = g.query_edges((world * nsteps + a.slice_offset) * T, "stream", device=dev)[:, a.slice_offset * T:]
     e_rank = e_all[:, rank * nsteps * T:(rank + 1) * nsteps * T].contiguous()
+    dealing = "contiguous slices per rank"
+    if world > 1 and a.deal == "cost":
+        # slices differ in cost (0.56 ms + 0.82 ms per million index entries; one slice in 26 holds a hub source):
+        # the timed slices of all ranks are dealt by predicted cost, same count per rank, no slice split.  The
+        # prediction is exact integer arithmetic on the replicated graph, so the ranks agree without a collective.
+        try:
+            from ocn_b200 import dist as obdist
+            cost = obdist.predicted_walk_cost(g.rowptr, g.col, e_all[0, :world * nsteps * T], T, a.batch).tolist()
+            pool = [r * nsteps + a.warmup + k for r in range(world) for k in range(a.steps)]
+            mine = obdist.deal_by_cost([cost[i] for i in pool], world, a.steps)[rank]
+            ids = list(range(rank * nsteps, rank * nsteps + a.warmup)) + [pool[i] for i in mine]
+            e_rank = torch.cat([e_all[:, i * T:(i + 1) * T] for i in ids], dim=1).contiguous()
+            dealing = "timed slices dealt by predicted index entries (longest first, equal count per rank)"
+        except Exception as ex:  # never lose a measurement to the dealing: fall back to the contiguous slices
+            dealing = f"contiguous slices per rank (cost dealing failed: {type(ex).__name__}: {ex})"
+    del e_all
     e_host = e_rank.cpu().pin_memory()
     torch.manual_seed(0)
     cls = ob.CNLinkPredictor3hopCNs if a.order >= 3 else ob.CNLinkPredictorOringin
@@ -477,6 +497,8 @@ def main():
                                  "(8 + 4 d(m) for every (link, m in N(dst)) with d(m) >= hub_degree) / its duration; the "
                                  "kernel streams each such row once per stream, so the figure can exceed the DRAM traffic"},
         }
+        if world > 1:
+            line["dealing"] = dealing
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a, g, g.rowptr.cpu(), g.col.cpu())
         emit(line)

@@ -1,7 +1,9 @@
 """Multi-GPU plumbing: the graph and features are replicated on every rank, the
 reference's own batch sequence (PermIterator order, utils.py:8-36) is dealt round-robin -- batch t goes
-to rank t mod world -- and every rank runs the full fused path on its batches.  A batch is never split
-(its links are coupled through the column statistics), so scores are identical for any world size.
+to rank t mod world -- and every rank runs the full fused path on its batches (``deal_batches``); for long streams whose pieces differ in
+cost, ``predicted_walk_cost`` + ``deal_by_cost`` deal equal numbers of slices with balanced predicted work instead.
+A batch is never split (its links are coupled through the column statistics), so scores are identical for any
+world size and any dealing.
 The only collective is the gather of fp32 scores."""
 from __future__ import annotations
 
@@ -15,6 +17,47 @@ def deal_batches(num_links: int, batch_size: int, rank: int, world: int) -> List
     """[start, end) link ranges of the batches owned by ``rank``."""
     nb = (num_links + batch_size - 1) // batch_size
     return [(b * batch_size, min(num_links, (b + 1) * batch_size)) for b in range(rank, nb, world)]
+
+
+def predicted_walk_cost(rowptr: torch.Tensor, col: torch.Tensor, src: torch.Tensor, slice_links: int,
+                        batch_size: int) -> torch.Tensor:
+    """int64 [ceil(T / slice_links)]: for every slice of ``slice_links`` consecutive links of the stream, the number
+    of index entries its order-3 build writes -- sum over the runs (maximal pieces of one source inside one link
+    batch, as ocn_cn_plan cuts them) of sum_{k in N(src)} d(k).  The time of a slice follows this count
+    (profiles/r01_step_times_v22.txt: 0.56 ms + 0.82 ms per million entries at 65 536 links), which makes it the
+    weight for dealing slices to ranks.  Pure integer torch ops on whatever device the graph is on; exact, so every
+    rank computes the same numbers without talking to the others."""
+    T = src.numel()
+    deg = rowptr[1:] - rowptr[:-1]
+    t = torch.arange(T, device=src.device)
+    first = (t % batch_size == 0)
+    first[1:] |= src[1:] != src[:-1]
+    heads = src[first]
+    # F[i] = sum of the degrees of i's neighbours, for the run heads only (rows gathered, not the whole matrix)
+    uniq, inv = torch.unique(heads, return_inverse=True)
+    cnt = deg[uniq]
+    owner = torch.repeat_interleave(torch.arange(uniq.numel(), device=src.device), cnt)
+    pos = torch.arange(int(cnt.sum()), device=src.device) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt) \
+        + torch.repeat_interleave(rowptr[uniq], cnt)
+    F = torch.zeros(uniq.numel(), dtype=torch.int64, device=src.device).index_add_(0, owner, deg[col[pos].long()])
+    num_slices = (T + slice_links - 1) // slice_links
+    slice_of_head = torch.div(t[first], slice_links, rounding_mode="floor")
+    return torch.zeros(num_slices, dtype=torch.int64, device=src.device).index_add_(0, slice_of_head, F[inv])
+
+
+def deal_by_cost(costs: Sequence[int], world: int, per_rank: int) -> List[List[int]]:
+    """Slices -> ranks, ``per_rank`` slices each, total predicted cost balanced: longest-processing-time greedy
+    (heaviest slice first, to the least loaded rank that still has room; ties by lower index, so the result is the
+    same on every rank).  Every rank returns its slices in ascending stream order.  A slice is a whole number of
+    link batches, so scores do not depend on the dealing."""
+    if len(costs) != world * per_rank:
+        raise ValueError(f"{len(costs)} slices cannot be dealt as {per_rank} to each of {world} ranks")
+    load, owned = [0] * world, [[] for _ in range(world)]
+    for sl in sorted(range(len(costs)), key=lambda i: (-int(costs[i]), i)):
+        r = min((r for r in range(world) if len(owned[r]) < per_rank), key=lambda r: (load[r], r))
+        owned[r].append(sl)
+        load[r] += int(costs[sl])
+    return [sorted(o) for o in owned]
 
 
 def gather_scores(local_scores: Sequence[torch.Tensor], owned: Sequence[Tuple[int, int]], num_links: int) -> torch.Tensor:
