@@ -195,3 +195,39 @@ def test_header_is_plain_c():
         assert res.returncode == 0, res.stderr
     finally:
         os.unlink(path)
+
+
+def test_cost_dealing_of_stream_slices():
+    """ocn_b200.dist.predicted_walk_cost / deal_by_cost (host logic of the multi-GPU bench and evaluation loop):
+    the predicted cost is the exact index-entry count of a slice, the dealing is a partition with equal counts that
+    is identical on every rank and never worse balanced than contiguous chunks."""
+    from ocn_b200 import dist as obdist
+    g = synth.tiny_graph(300, 2400, 7)
+    rp, col = g.rowptr, g.col
+    deg = (rp[1:] - rp[:-1]).numpy()
+    slice_links, batch, world, per_rank = 64, 16, 4, 3
+    T = slice_links * world * per_rank
+    srcs = torch.randint(0, g.n, (T // 10 + 1,), generator=torch.Generator().manual_seed(3))
+    src = srcs.repeat_interleave(10)[:T]                      # runs of 10 links, cut again at the batch boundaries
+    cost = obdist.predicted_walk_cost(rp, col, src, slice_links, batch).tolist()
+    # brute force: runs = maximal pieces of one source inside one batch; entries = sum over runs, over k in N(src), of d(k)
+    ref = [0] * (T // slice_links)
+    cn, rpn, s = col.numpy(), rp.numpy(), src.numpy()
+    for t in range(T):
+        if t % batch == 0 or s[t] != s[t - 1]:
+            ref[t // slice_links] += int(sum(deg[k] for k in cn[rpn[s[t]]:rpn[s[t] + 1]]))
+    assert cost == ref
+    owned = obdist.deal_by_cost(cost, world, per_rank)
+    assert sorted(i for o in owned for i in o) == list(range(world * per_rank))
+    assert all(len(o) == per_rank and o == sorted(o) for o in owned)
+    assert owned == obdist.deal_by_cost(list(cost), world, per_rank)   # deterministic: same on every rank
+    load = lambda ids: sum(cost[i] for i in ids)
+    contiguous = max(load(range(r * per_rank, (r + 1) * per_rank)) for r in range(world))
+    assert max(load(o) for o in owned) <= contiguous
+    # one very heavy slice: it ends up with the lightest companions
+    skew = [100, 1, 2, 3, 4, 5, 6, 7]
+    o = obdist.deal_by_cost(skew, 2, 4)
+    heavy = o[0] if 0 in o[0] else o[1]
+    assert sorted(heavy) == [0, 1, 2, 3]
+    with pytest.raises(ValueError):
+        obdist.deal_by_cost([1, 2, 3], 2, 2)
