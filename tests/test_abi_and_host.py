@@ -231,3 +231,30 @@ def test_cost_dealing_of_stream_slices():
     assert sorted(heavy) == [0, 1, 2, 3]
     with pytest.raises(ValueError):
         obdist.deal_by_cost([1, 2, 3], 2, 2)
+
+
+def test_bench_algorithmic_bytes_follow_the_survey_formula():
+    """bench.algorithmic_bytes: the SURVEY.md 8(d) per-link figure (index terms, the x[i] / x[j] gathers and the
+    outputs; the gathers over the CN sets themselves are left out, which only lowers the figure) and the part
+    of its order-3 index term that runs through rows of >= hub_degree columns (numerator of roofline.achieved),
+    against a per-link python count."""
+    import bench
+    g = synth.tiny_graph(80, 400, 2)
+    G = ob.Graph(g.rowptr, g.col, g.n)
+    e = g.query_edges(64, "mixed")
+    rp, col = g.rowptr.tolist(), g.col.tolist()
+    d = lambda v: rp[v + 1] - rp[v]
+    N = lambda v: col[rp[v]:rp[v + 1]]
+    feat, hub_d = 8, 6
+    for order in (1, 2, 3):
+        _, _, survey, hub = bench.algorithmic_bytes(G, e, order, feat, 16, hub_d=hub_d)
+        want, want_hub = 0, 0
+        for i, j in e.t().tolist():
+            want += 32 + 4 * (d(i) + d(j)) + 4 * feat * (order + 1 + 2)
+            if order >= 2:
+                want += 8 * d(j) + 4 * sum(d(m) for m in N(j))
+            if order >= 3:
+                want += 8 * d(i) + 4 * sum(d(k) for k in N(i))
+                want_hub += sum(8 + 4 * d(m) for m in N(j) if d(m) >= hub_d)
+        assert survey == want
+        assert hub == want_hub
