@@ -488,6 +488,9 @@ def main():
             "gpu_launches": ((24 if indexed else (15 + (1 if a.order <= 2 else 0))) * a.steps),
             "roofline": {"bound": "hbm", "kernel": kern_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         # the same launch at DRAM level (ncu bytes / live duration): far below the peak -- the kernel is
+                         # bound by issue slots and shared-memory counter updates, not by HBM
+                         "dram_gbs": (traffic / (kern_avg * 1e-3) / 1e9) if traffic else None,
                          "algorithmic_bytes_per_launch": kern_bytes, "kernel_ms": kern_avg,
                          "kernel_share_of_step": kern_avg / (ms_dev / a.steps),
                          "build_stage_ms": build_avg, "hub_degree": hub_ds[-1],
