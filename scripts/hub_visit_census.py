@@ -79,6 +79,10 @@ def main():
     pairs = int(L.sum())
     print(f"runs {R}  positions {P}  entries {entries}  pairs {pairs}  shared rows {M.size}  "
           f"columns of the shared rows {int(deg[M].sum())}")
+    # the other side of hub_degree: rows below it are walked by every link next to them (k_cn_link)
+    small_cols = A @ np.where(big, 0, deg).astype(np.float64)          # per node j: columns of its rows below hub_degree
+    print(f"per-link walk (k_cn_link): {small_cols[dst].sum() / 1e6:.1f} M column look-ups through rows below hub_degree, "
+          f"{(A @ (~big).astype(np.float64))[dst].sum() / 1e6:.2f} M such (link, row) pairs")
 
     # W[m, r] = entries of run r met while streaming N(m)  = sum_{l in N(m)} E[r, l]
     W = np.asarray((A[M] @ E.T).todense(), dtype=np.float64)      # [|M| x R]
