@@ -110,3 +110,45 @@ def test_training_step_exchange_and_gradient_allreduce():
         p.join(120)
         assert p.exitcode == 0
     assert out.get(timeout=10) is True
+
+
+def _cost_worker(rank, world, port, out):
+    """Slices of a stream dealt by predicted cost: every rank computes the dealing on its own replica of the graph
+    (no collective), scores its slices batch by batch, and the one gather returns the stream in link order."""
+    from ocn_b200 import synth
+    from ocn_b200.dist import deal_by_cost, predicted_walk_cost
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = synth.tiny_graph(200, 1500, 9)
+    slice_links, bs, per_rank = 96, 32, 3
+    T = slice_links * world * per_rank
+    edges = g.query_edges(T, "stream")
+    cost = predicted_walk_cost(g.rowptr, g.col, edges[0], slice_links, bs).tolist()
+    dealt = deal_by_cost(cost, world, per_rank)
+    # the ranks agree without talking: compare through one all_gather of the flattened dealing
+    mine_flat = torch.tensor([i for o in dealt for i in o])
+    seen = [torch.empty_like(mine_flat) for _ in range(world)]
+    dist.all_gather(seen, mine_flat)
+    ok = all(torch.equal(s, mine_flat) for s in seen)
+    owned = [(sl * slice_links + b, sl * slice_links + b + bs) for sl in dealt[rank] for b in range(0, slice_links, bs)]
+    score = lambda b: b[0].float() * 2 + b[1].float().sum()      # batch-coupled stand-in for the CUDA path
+    scores = gather_scores([score(edges[:, s:e]) for (s, e) in owned], owned, T)
+    ref = torch.cat([score(edges[:, s:s + bs]) for s in range(0, T, bs)])
+    ok = ok and torch.equal(scores, ref)
+    if rank == 0:
+        out.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_slices_dealt_by_cost_and_scores_gathered():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cost_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert out.get(timeout=10) is True
