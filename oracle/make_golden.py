@@ -134,6 +134,28 @@ def run_case(name, graph, F, batches, predictor, mode, style, fill=None, ln=Fals
     print(f"wrote {path}: {len(calls)} call(s), {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def run_utils_case(graphs):
+    """The reference's own ``utils.py`` on the two remaining callers of the path: ``sparse_tensor_multiply``
+    (--adj2byblock, NeighborOverlap_large.py:68-71; block sizes that do and do not divide n) followed by the driver's
+    ``adjoverlap(adj, adj2, edge)`` (:79), and ``adjoverlap(..., calresadj=True)`` (utils.py:260-274)."""
+    cases = []
+    for name, graph, block, e in graphs:
+        n = graph.n
+        rowptr, col = graph.rowptr, graph.col.long()
+        row = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
+        adj = SparseTensor(row=row, col=col, sparse_sizes=(n, n), is_sorted=True)
+        spadj = SparseTensor.from_torch_sparse_coo_tensor(adj.to_torch_sparse_coo_tensor())   # NeighborOverlap_large.py:67-70
+        adj2 = ref_utils.sparse_tensor_multiply(spadj, block_size=block)                       # :71
+        cn2 = ref_utils.adjoverlap(adj, adj2, e, False)                                        # :79
+        ov, r1, r2 = ref_utils.adjoverlap(adj, adj, e, False, calresadj=True)                  # utils.py:260-274
+        cases.append({"name": name, "n": n, "rowptr": rowptr.clone(), "col": graph.col.clone(), "block": block,
+                      "edges": e.clone(), "adj2": _sp_dump(adj2), "cn2": _sp_dump(cn2),
+                      "overlap": _sp_dump(ov), "res1": _sp_dump(r1), "res2": _sp_dump(r2)})
+    path = os.path.join(ROOT, "tests", "golden", "ref_utils_adj2byblock_calresadj.pt")
+    torch.save(cases, path)
+    print(f"wrote {path}: {len(cases)} case(s), {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="", help="regex: write only the fixtures whose name matches")
@@ -156,6 +178,10 @@ def main():
             out.append(torch.cat((g.query_edges(B // 2, "pos"), neg), 1))
         return out
 
+    if only.search("utils_adj2byblock_calresadj"):
+        mid = synth.tiny_graph(150, 700, 8)
+        run_utils_case([("tiny_b16", tiny, 16, links(tiny, 48, 1)[0]), ("tiny_b60", tiny, 60, links(tiny, 48, 1)[0]),
+                        ("tiny_b1024", tiny, 1024, links(tiny, 48, 1)[0]), ("mid_b64", mid, 64, links(mid, 64, 1)[0])])
     run_case("cn5_large_eval_tiny", tiny, 8, links(tiny, 48, 1), "cn5", "eval", "large")
     run_case("cn5_large_train_cora", cora, 16, links(cora, 96, 3), "cn5", "train", "large")
     run_case("cn5_large_eval_ln_cora", cora, 16, links(cora, 96, 1), "cn5", "eval", "large", ln=True)

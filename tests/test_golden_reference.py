@@ -105,3 +105,29 @@ def test_cuda_path_reproduces_reference_execution(path):
         if fx["predictor"] != "cn7":
             assert pred.n == call["n"]
             assert abs(pred.innerprod.item() - call["innerprod"].item()) <= 1e-4 * (1 + abs(call["innerprod"].item()))
+
+
+UTILS_FIXTURE = os.path.join(os.path.dirname(__file__), "golden", "ref_utils_adj2byblock_calresadj.pt")
+
+
+def test_oracle_reproduces_reference_adj2byblock_and_calresadj():
+    """The reference's own ``sparse_tensor_multiply`` (--adj2byblock, utils.py:287-329), the ``adjoverlap(adj, adj2,
+    edge)`` that follows it in the driver (NeighborOverlap_large.py:79) and ``adjoverlap(..., calresadj=True)``
+    (utils.py:260-274), executed by oracle/make_golden.py: pins ``adj2_folded`` (every block product lands
+    in the top-left corner), and the residual sets.  The CUDA path is compared with the same oracle functions in
+    tests/test_gpu_parity.py::test_adjoverlap_generic_and_spgemm."""
+    cases = _load(UTILS_FIXTURE)
+    assert len(cases) >= 4
+    for c in cases:
+        A = R.sp_from_csr(c["rowptr"], c["col"])
+        f = R.adj2_folded(A, c["block"])
+        want = c["adj2"]
+        assert tuple(want["shape"]) == (c["n"], c["n"])
+        assert torch.equal(f.row, want["row"]) and torch.equal(f.col, want["col"]), c["name"]
+        assert torch.equal(f.values(), want["val"].float()), c["name"]
+        if c["block"] < c["n"]:   # the fold is visible: nothing outside the top-left block
+            assert int(f.row.max()) < c["block"] and int(f.col.max()) < c["block"]
+        e = c["edges"]
+        _same_sparse(R.adjoverlap(A, f, e), c["cn2"])
+        for got, key in zip(R.adjoverlap(A, A, e, calresadj=True), ("overlap", "res1", "res2")):
+            _same_sparse(got, c[key])
