@@ -75,6 +75,8 @@ def parse():
                          "deal_by_cost); 'contiguous' gives rank r the r-th run of consecutive slices")
     ap.add_argument("--device-streams", type=int, default=1,
                     help="device-resident leg: consecutive steps alternate between this many of the --streams streams")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="library tuning option (ocn_b200._lib.OPTIONS), e.g. --opt hub_exact=1 for an A/B run")
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed device steps (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -169,7 +171,7 @@ def algorithmic_bytes(G, e, order, feat, batch, hub_d=0):
     j_bytes = int((per_link_j * chunks.clamp(min=1)).sum())
     # i side, once per work unit (run x chunk x 32-link sub-list): N(i) chunk, its rowptr pairs, its rows
     t = torch.arange(T, device=e.device)
-    first = (t % batch == 0) | (torch.cat((i[:1] - 1, i[:-1])) != i)
+    first = (t == 0) | (torch.cat((i[:1] - 1, i[:-1])) != i)   # runs cross batch boundaries (ocn_cn_plan)
     run_id = torch.cumsum(first.long(), 0) - 1
     run_len = torch.bincount(run_id)
     run_src = i[first]
@@ -275,6 +277,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (ocn_b200 has no CPU path)")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    for kv in a.opt:
+        k, v = kv.split("=")
+        ob._lib.set_option(k, int(v))
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(dev))

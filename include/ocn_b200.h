@@ -34,12 +34,27 @@ extern "C" {
 #define OCN_ECUDA (-2)    /* CUDA runtime / launch error */
 #define OCN_ENOSPACE (-3) /* caller-provided buffer too small */
 
-#define OCN_ABI_VERSION 2
+#define OCN_ABI_VERSION 3
 
 int ocn_abi_version(void);
 const char* ocn_last_error(void);
 /* number of SMs of the current device (grid sizing is done inside; exposed for bench.py) */
 int ocn_device_sm_count(void);
+
+/* Tuning / test options of the library (process-wide; not part of the data path's contract).  The parity tests use
+ * them to force, on small graphs, the code paths that production sizes reach on their own (position windows,
+ * heavy-source passes), and bench.py / scripts/ab.py use them for one-process A/B runs of kernel variants.
+ * value 0 always means "the built-in default".  Returns OCN_EINVAL for an unknown key. */
+#define OCN_OPT_HUB_WINDOW 0      /* positions a warp-private counter window of k_cn_hub_count holds (default 4096) */
+#define OCN_OPT_HUB_CTA_WINDOW 1  /* positions of the CTA-wide counter window (default 32768) */
+#define OCN_OPT_HUB_HEAVY_RUN 2   /* a run whose source has more neighbours is indexed in its own pass (default 1024) */
+#define OCN_OPT_HUB_WALKER 3      /* 1: the shared pass walks run segments (k_cn_hub_count_seg; measured slower), 0: whole lists */
+#define OCN_OPT_HUB_SEG_CTAS 4    /* resident CTAs per SM of k_cn_hub_count_seg (default 5) */
+#define OCN_OPT_HUB_EXACT 5       /* 1: 32-byte node entries with exact run sets + run-segment starts for streams of <= 128 runs
+                                     (measured slower than the folded 64-bit sets on the bench workload; implied by WALKER = 1) */
+#define OCN_OPT_COUNT 16
+int ocn_set_option(int key, int64_t value);
+int64_t ocn_get_option(int key);
 
 /* ---- graph ------------------------------------------------------------------------------ */
 
@@ -170,12 +185,16 @@ int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n,
                  const int64_t* plan_host /* HOST copy of plan[OCN_PLAN_WORDS] (the caller read it back to size
                                              the buffers); NULL = hub stage off */,
                  void* hub_scratch /* ocn_cn_hub_bytes(...) bytes, NULL = hub stage off */, size_t hub_scratch_bytes,
-                 void* node_scratch /* 2 x 16 bytes per node (uint4[2n]), ZERO on entry, zero again when the call has run */,
+                 void* node_scratch /* 2 x 32 bytes per node (uint4[4n]), ZERO on entry, zero again when the call has run */,
                  void* stream);
 
 /* Hub stage of the order-3 walk (cn_hub.cu): a row N(m) that many links of the stream would walk
  * is streamed once for all of them.  Scratch bytes for the sizes ocn_cn_plan reported. */
 size_t ocn_cn_hub_bytes(int64_t n, int64_t nnz, const int64_t* plan_host);
+/* A build that fails half way restores node_scratch to zero itself; if even that fails (a sticky CUDA error) the
+ * buffer is remembered as dirty and every later ocn_cn_build on it is refused until the caller has zeroed it and
+ * called this. */
+int ocn_cn_hub_scratch_reset(const void* node_scratch);
 /* Measurement hook: two cudaEvent_t recorded on the build's stream right before / after the
  * dominant kernel of the indexed path (k_cn_hub_count).  NULL, NULL switches it off. */
 int ocn_cn_hub_timing_events(void* start_event, void* stop_event);

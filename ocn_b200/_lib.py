@@ -37,6 +37,9 @@ _SIGS = {
                              c_int64, _P, _P, c_size_t, _P, _P]),
     "ocn_cn_hub_bytes": (c_size_t, [c_int64, c_int64, _P]),
     "ocn_cn_hub_timing_events": (c_int, [_P, _P]),
+    "ocn_cn_hub_scratch_reset": (c_int, [_P]),
+    "ocn_set_option": (c_int, [c_int, c_int64]),
+    "ocn_get_option": (c_int64, [c_int]),
     "ocn_cn_stats": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, c_int,
                              _P, _P, _P, _P, _P]),
     "ocn_cn_aggregate": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P,
@@ -89,10 +92,23 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.ocn_abi_version() != 2:
+        if L.ocn_abi_version() != 3:
             raise OcnError("libocn_b200.so ABI version mismatch")
         _lib = L
     return _lib
+
+
+OPTIONS = {"hub_window": 0, "hub_cta_window": 1, "hub_heavy_run": 2, "hub_walker": 3, "hub_seg_ctas": 4, "hub_exact": 5}
+
+
+def set_option(name: str, value: int) -> None:
+    """Tuning / test option of the library (include/ocn_b200.h OCN_OPT_*); 0 restores the default."""
+    check(lib().ocn_set_option(OPTIONS[name], int(value)), "ocn_set_option")
+
+
+def reset_options() -> None:
+    for k in OPTIONS.values():
+        lib().ocn_set_option(k, 0)
 
 
 def check(status: int, what: str):

@@ -172,12 +172,19 @@ class CNSession:
         if self.hub_bytes > 0 and order >= 3:
             hub_scratch, node_scratch = _hub_workspace(g, self.hub_bytes)
         with torch.cuda.device(self.dev):
-            _lib.check(self.L.ocn_cn_build(_lib.ptr(g.rowptr), _lib.ptr(g.col), g.n, _lib.ptr(self.src),
-                                           _lib.ptr(self.dst), self.T, self.batch_size, int(order), int(bool(weighted)),
-                                           _lib.ptr(self.plan_scratch), _lib.ptr(self.plan), _lib.ptr(self.records),
-                                           self.num_records, _lib.ptr(self.colstat) if with_stats else None,
-                                           g.nnz, self.plan_host, _lib.ptr(hub_scratch), self.hub_bytes,
-                                           _lib.ptr(node_scratch), _stream(self.dev)), "ocn_cn_build")
+            try:
+                _lib.check(self.L.ocn_cn_build(_lib.ptr(g.rowptr), _lib.ptr(g.col), g.n, _lib.ptr(self.src),
+                                               _lib.ptr(self.dst), self.T, self.batch_size, int(order), int(bool(weighted)),
+                                               _lib.ptr(self.plan_scratch), _lib.ptr(self.plan), _lib.ptr(self.records),
+                                               self.num_records, _lib.ptr(self.colstat) if with_stats else None,
+                                               g.nnz, self.plan_host, _lib.ptr(hub_scratch), self.hub_bytes,
+                                               _lib.ptr(node_scratch), _stream(self.dev)), "ocn_cn_build")
+            except _lib.OcnError:
+                # the zero-on-entry scratch of a failed build is not trusted again: drop it (the next session on
+                # this stream allocates fresh, zeroed buffers) together with the borrowed column statistics
+                _drop_workspace(g, node_scratch)
+                self.colstat = None
+                raise
         self.order, self.weighted = int(order), bool(weighted)
         return self
 
@@ -273,7 +280,7 @@ def reserve_stream_pool(nbytes: int = 4 << 30, device=None) -> None:
 
 
 def _hub_workspace(g: Graph, nbytes: int):
-    """Scratch of the hub stage, kept with the graph: a byte buffer that only grows and the 16-byte-per-node
+    """Scratch of the hub stage, kept with the graph: a byte buffer that only grows and the 32-byte-per-node
     key index (all zero between calls; ocn_cn_build restores it).  Calls on one stream are ordered by the stream;
     every stream has its own pair of buffers, so that two sessions may be in flight on two streams."""
     sid = torch.cuda.current_stream(g.device).cuda_stream  # one workspace per stream: sessions on different streams overlap
@@ -286,9 +293,17 @@ def _hub_workspace(g: Graph, nbytes: int):
         g._ws[("hub", sid)] = buf
     node = g._ws.get(("hub_node", sid))
     if node is None:
-        node = torch.zeros((2 * g.n, 4), dtype=torch.int32, device=g.device)  # second half: the pass over heavy sources
+        node = torch.zeros((4 * g.n, 4), dtype=torch.int32, device=g.device)  # 32 B per node; second half: the pass over heavy sources
         g._ws[("hub_node", sid)] = node
     return buf, node
+
+
+def _drop_workspace(g: Graph, node_scratch) -> None:
+    sid = torch.cuda.current_stream(g.device).cuda_stream
+    g._ws.pop(("hub", sid), None)
+    g._ws.pop(("hub_node", sid), None)
+    if node_scratch is not None:
+        _lib.lib().ocn_cn_hub_scratch_reset(_lib.ptr(node_scratch))  # the address may be handed out again, zeroed
 
 
 def _borrow_colstat(g: Graph, nbytes: int) -> Tensor:

@@ -28,10 +28,10 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
-#include <stdlib.h>
-
 #include <map>
 #include <mutex>
+#include <set>
+#include <string>
 #include <utility>
 
 #include "common.cuh"
@@ -72,6 +72,7 @@ HubLayout hub_layout(int64_t n, int64_t nnz, int64_t pairs, int64_t entries, int
     L.prec = off;      off += align256(sizeof(unsigned long long) * P);
     L.key_bits = off;  off += align256(sizeof(uint32_t) * (size_t)((n + 32) / 32));
     L.item_link = off; off += align256(sizeof(int32_t) * (size_t)((chunks > 0 ? chunks : 0) + 1));
+    L.sidx = off;      off += align256(sizeof(uint16_t) * E);
     size_t b1 = 0, b2 = 0, b3 = 0;
     {
         cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
@@ -323,7 +324,7 @@ __device__ __forceinline__ void count_walk(uint32_t* U, uint32_t pos, uint32_t w
 // whole warp, so that neither the many short lists nor the few long ones (54 % of the visits are in
 // lists of > 32 entries at citation2 shape) leave lanes idle.  Positions beyond the counter window are
 // handled by further passes over the items ([win_lo, win_lo + win_n) per launch).
-template <bool kCta, bool kWin>
+template <bool kCta, bool kWin, bool kExact>
 __global__ void __launch_bounds__(kHubThreads, kCta ? 3 : 6)
 k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint32_t* __restrict__ pkey,
                const int32_t* __restrict__ prun, const unsigned long long* __restrict__ prec, int64_t P,
@@ -365,13 +366,21 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
         const int64_t q0 = item.x;
         const uint32_t m = pkey[q0];
         int64_t c = 0;  // |L_m|
-        unsigned act_lo = 0u, act_hi = 0u;  // signature of the runs that have a link next to m
+        // the runs that have a link next to m: exact set (kExact: up to 128 runs, 32-byte node entries whose second
+        // half is the exact run set of the list) or folded into 64 bits
+        unsigned act_lo = 0u, act_hi = 0u, act_2 = 0u, act_3 = 0u;
         while (true) {
             const int64_t qi = q0 + c + lane;
             const bool ok = qi < P && pkey[qi] == m;
             if (ok) {
                 const int r = prun[qi];
-                if (r & 32) act_hi |= 1u << (r & 31); else act_lo |= 1u << (r & 31);
+                if (kExact) {
+                    const unsigned bit = 1u << (r & 31), w = (unsigned)r >> 5;
+                    act_lo |= w == 0 ? bit : 0u;
+                    act_hi |= w == 1 ? bit : 0u;
+                    act_2 |= w == 2 ? bit : 0u;
+                    act_3 |= w == 3 ? bit : 0u;
+                } else if (r & 32) act_hi |= 1u << (r & 31); else act_lo |= 1u << (r & 31);
             }
             const unsigned bal = __ballot_sync(0xffffffffu, ok);
             c += __popc(bal);
@@ -379,6 +388,10 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
         }
         act_lo = __reduce_or_sync(0xffffffffu, act_lo);
         act_hi = __reduce_or_sync(0xffffffffu, act_hi);
+        if (kExact) {
+            act_2 = __reduce_or_sync(0xffffffffu, act_2);
+            act_3 = __reduce_or_sync(0xffffffffu, act_3);
+        }
         for (int s = (kCta ? threadIdx.x : lane) * 4; s < uwords; s += (kCta ? kHubThreads : 32) * 4)
             *reinterpret_cast<uint4*>(U + s) = make_uint4(0u, 0u, 0u, 0u);
         item_sync();
@@ -392,7 +405,27 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
         auto load_col = [&](int64_t bb) -> int32_t { return (bb + lane < c1) ? ldg_i32(col + rs + bb + lane) : -1; };
         // a column is a key of the index only if its bit is set: the 16-byte entry is fetched for those alone
         auto load_bit = [&](int32_t l) -> bool { return l >= 0 && ((__ldg(key_bits + (l >> 5)) >> (l & 31)) & 1u) != 0u; };
-        auto load_entry = [&](int32_t l, bool key) -> uint4 { return key ? __ldg(node_index + l) : make_uint4(0u, 0u, 0u, 0u); };
+        // node entry -> (first entry, length of the list if it holds a run of an active link, else 0); the loads of step
+        // b+1 are issued here, the test runs when the values are used
+        uint4 he_raw = make_uint4(0u, 0u, 0u, 0u);
+        uint2 he_fe = make_uint2(0u, 0u);
+        auto load_entry = [&](int32_t l, bool key) {
+            if (kExact) {
+                if (key) {
+                    he_fe = __ldg(reinterpret_cast<const uint2*>(node_index + 2 * (size_t)l));
+                    he_raw = __ldg(node_index + 2 * (size_t)l + 1);
+                } else {
+                    he_raw = make_uint4(0u, 0u, 0u, 0u);
+                }
+            } else {
+                he_raw = key ? __ldg(node_index + l) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        };
+        auto entry_first = [&]() -> uint32_t { return kExact ? he_fe.x : he_raw.x; };
+        auto entry_count = [&]() -> int {
+            if (kExact) return ((he_raw.x & act_lo) | (he_raw.y & act_hi) | (he_raw.z & act_2) | (he_raw.w & act_3)) ? (int)(he_fe.y - he_fe.x) : 0;
+            return ((he_raw.z & act_lo) | (he_raw.w & act_hi)) ? (int)(he_raw.y - he_raw.x) : 0;
+        };
         // one queued list per lane (length 0 = none): the first kShortList entries by the lane itself, the rest of
         // the middle lists flattened over the lanes, 32 entries at a time
         auto drain = [&](uint2 ql) {
@@ -422,26 +455,25 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
         };
         int qn = 0;  // queued lists (warp-uniform)
         const int64_t b0 = c0 + 32 * wi;
-        uint4 he_next;
         int32_t col_n1 = load_col(b0 + stride), col_n2 = load_col(b0 + 2 * stride);
         {
             const int32_t l0 = load_col(b0);
-            he_next = load_entry(l0, load_bit(l0));
+            load_entry(l0, load_bit(l0));
         }
         bool bit_n1 = load_bit(col_n1);
         for (int64_t b = b0; b < c1; b += stride) {
-            const uint4 he = he_next;
-            he_next = load_entry(col_n1, bit_n1);
+            const int cnt = entry_count();
+            const uint32_t he_x = entry_first(), he_y = he_x + (uint32_t)cnt;
+            load_entry(col_n1, bit_n1);
             col_n1 = col_n2;
             bit_n1 = load_bit(col_n1);
             col_n2 = load_col(b + 3 * stride);
-            const int cnt = ((he.z & act_lo) | (he.w & act_hi)) ? (int)(he.y - he.x) : 0;
             if (!__any_sync(0xffffffffu, cnt != 0)) continue;
             // short and middle lists go to the queue; a full batch of 32 is walked as soon as there is one
             {
                 const bool push = cnt > 0 && cnt <= kMidList;
                 const unsigned pm = __ballot_sync(0xffffffffu, push);
-                if (push) Q[qn + __popc(pm & ((1u << lane) - 1u))] = make_uint2(he.x, (uint32_t)cnt);
+                if (push) Q[qn + __popc(pm & ((1u << lane) - 1u))] = make_uint2(he_x, (uint32_t)cnt);
                 qn += __popc(pm);
                 __syncwarp();
                 if (qn >= 32) {
@@ -456,8 +488,8 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
             while (lg) {
                 const int sl = __ffs(lg) - 1;
                 lg &= lg - 1;
-                uint32_t e0 = __shfl_sync(0xffffffffu, he.x, sl);
-                uint32_t e1 = __shfl_sync(0xffffffffu, he.y, sl);
+                uint32_t e0 = __shfl_sync(0xffffffffu, he_x, sl);
+                uint32_t e1 = __shfl_sync(0xffffffffu, he_y, sl);
                 if (kWin && win_lo > 0u) {  // first entry with position >= win_lo
                     uint32_t lo = e0, hi = e1;
                     while (lo < hi) {
@@ -516,6 +548,311 @@ k_cn_hub_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
     }
 }
 
+// ---- run-segment index (streams of up to kSegRuns runs, positions in one warp-private window) -------------
+// The census of the walk above (scripts/hub_visit_census2.py, bench slice 0) says: of the 104 M entries it visits
+// per launch only 19.6 M belong to a run that has a link next to the streamed row -- a list that holds one active
+// run is walked whole.  With at most 128 runs the node entry can carry the EXACT set of runs of its list
+// (128 bits), and because a list is sorted by position, i.e. by run, the entries of run r are the segment number
+// rank(r) = popc(runs(l) & below(r)) of the list.  Node entry (32 bytes, one sector):
+//     a = (first entry, one past the last, -, -)      b = run set (bit r = the list holds an entry of run r)
+// Lists with one entry per run ("simple": popc(b) == length; 97 % of the keys) need nothing else -- segment s is
+// entry first + s.  The others store the start of segment s (relative to first) in sidx[first + s]: a list has no
+// more segments than entries, so the array parallel to the entries has room.  A streamed column then costs its
+// hit segments only (13.7 M per launch, 19.6 M entries) instead of its whole list, and the per-link look-up
+// (k_cn_link) finds a run's piece of a list without a search.
+constexpr int kSegRuns = 128;
+
+__device__ __forceinline__ int popc4(uint4 s) { return __popc(s.x) + __popc(s.y) + __popc(s.z) + __popc(s.w); }
+
+// number of runs of the set `s` below run r, and whether r itself is in the set
+__device__ __forceinline__ int seg_rank(uint4 s, uint32_t r, bool& present) {
+    const uint32_t w = r >> 5, b = r & 31u;
+    const uint32_t sw = w == 0 ? s.x : (w == 1 ? s.y : (w == 2 ? s.z : s.w));
+    present = ((sw >> b) & 1u) != 0u;
+    int rank = __popc(sw & ((1u << b) - 1u));
+    if (w > 0) rank += __popc(s.x);
+    if (w > 1) rank += __popc(s.y);
+    if (w > 2) rank += __popc(s.z);
+    return rank;
+}
+
+// position (0..31) of the j-th (0-based) set bit of w; j < popc(w)
+__device__ __forceinline__ int nth_set_bit(uint32_t w, int j) {
+    int pos = 0, t;
+    t = __popc(w & 0xffffu); if (j >= t) { j -= t; w >>= 16; pos = 16; }
+    t = __popc(w & 0xffu);   if (j >= t) { j -= t; w >>= 8;  pos += 8; }
+    t = __popc(w & 0xfu);    if (j >= t) { j -= t; w >>= 4;  pos += 4; }
+    t = __popc(w & 0x3u);    if (j >= t) { j -= t; w >>= 2;  pos += 2; }
+    if (j >= (int)(w & 1u)) pos += 1;
+    return pos;
+}
+
+__global__ void k_hub_entry_heads_seg(const uint32_t* __restrict__ ekey, const uint32_t* __restrict__ eval,
+                                      const int64_t* __restrict__ run_pos_off, int n_runs, int64_t E, int set,
+                                      uint4* __restrict__ node_index, uint32_t* __restrict__ key_bits) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const uint32_t k = ekey[e];
+    unsigned* ni = reinterpret_cast<unsigned*>(node_index + 2 * (size_t)k);
+    const bool first = (e == 0 || ekey[e - 1] != k);
+    if (!set) {
+        if (first) {
+            node_index[2 * (size_t)k] = make_uint4(0u, 0u, 0u, 0u);
+            node_index[2 * (size_t)k + 1] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        return;
+    }
+    if (first) {
+        ni[0] = (unsigned)e;
+        atomicOr(key_bits + (k >> 5), 1u << (k & 31u));
+    }
+    if (e == E - 1 || ekey[e + 1] != k) ni[1] = (unsigned)(e + 1);
+    const uint32_t r = run_of_position(eval[e], run_pos_off, n_runs);
+    atomicOr(ni + 4 + (r >> 5), 1u << (r & 31u));
+}
+
+// segment starts of the lists that hold several entries of one run (after the run sets are complete)
+__global__ void k_hub_segments(const uint32_t* __restrict__ ekey, const uint32_t* __restrict__ eval,
+                               const int64_t* __restrict__ run_pos_off, int n_runs, int64_t E,
+                               const uint4* __restrict__ node_index, uint16_t* __restrict__ sidx) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const uint32_t k = ekey[e];
+    const uint4 a = node_index[2 * (size_t)k], s = node_index[2 * (size_t)k + 1];
+    if ((uint32_t)popc4(s) == a.y - a.x) return;  // one entry per run: segment s is entry first + s
+    const uint32_t r = run_of_position(eval[e], run_pos_off, n_runs);
+    if (e != (int64_t)a.x && run_of_position(eval[e - 1], run_pos_off, n_runs) == r) return;  // inside a segment
+    bool present;
+    const int j = seg_rank(s, r, present);
+    sidx[a.x + (uint32_t)j] = (uint16_t)(e - a.x);
+}
+
+// the entries [e0, e1) of run r in the list of node entry (a, s); e0 == e1 when the list holds none
+__device__ __forceinline__ void seg_bounds(uint4 s, uint32_t first, uint32_t end, int rank,
+                                           const uint16_t* __restrict__ sidx, uint32_t& e0, uint32_t& e1) {
+    const int k = popc4(s);
+    const uint32_t cnt = end - first;
+    if ((uint32_t)k == cnt) {
+        e0 = first + (uint32_t)rank;
+        e1 = e0 + 1u;
+    } else {
+        e0 = first + (uint32_t)__ldg(sidx + first + rank);
+        e1 = (rank + 1 < k) ? first + (uint32_t)__ldg(sidx + first + rank + 1) : end;
+    }
+}
+
+// k_cn_hub_count with the run-segment index (opt-in: ocn_set_option(OCN_OPT_HUB_WALKER, 1)): one warp per item (row m,
+// segment of its columns), counters private to the warp.  Columns whose run set meets the active runs of m are queued
+// (node entry, 24 bytes) in warp-private shared memory; every 32 queued columns -- and at the end of the item --
+// their (column, active run) hits are flattened over the lanes: slot j finds its column (owner) and the j-th set bit
+// of that column's hit set, then counts the entries of that run segment.
+// MEASURED SLOWER than the whole-list walk above and therefore not the default (bench slices, kernel alone, B200):
+// whole lists 0.58 ms (104 M entry visits, 359 M warp instructions, 73 % issue slots) against 0.74 - 0.89 ms for three
+// versions of this kernel (22 M visits, 330 - 395 M warp instructions, 57 - 65 % issue slots, 5 CTAs/SM at 48 registers):
+// finding a hit's segment costs ~12 warp instructions per useful visit where walking a list costs 2.6 per visit, useful
+// or not, and the per-segment entry loops run with 3 - 4 lanes active (profiles/r02_seg_v1_*, r02_seg_v2_*).
+// Kept as a tested alternative walker for streams whose lists are much longer than the bench's.
+constexpr int kSegQueue = 64;        // queued node entries per warp
+constexpr int kSegLanePairs = 8;     // rows with at least this many links hand their counters out one lane per link
+#ifndef OCN_SEG_MINB
+#define OCN_SEG_MINB 5
+#endif
+
+__global__ void __launch_bounds__(kHubThreads, OCN_SEG_MINB)
+k_cn_hub_count_seg(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint32_t* __restrict__ pkey,
+                   const int32_t* __restrict__ prun, const unsigned long long* __restrict__ prec, int64_t P,
+                   const uint32_t* __restrict__ eval, const uint16_t* __restrict__ sidx,
+                   const uint4* __restrict__ node_index, const uint32_t* __restrict__ key_bits,
+                   const int64_t* __restrict__ run_pos_off, int n_runs, uint32_t n_pos,
+                   const uint2* __restrict__ items, int64_t max_items, unsigned long long* __restrict__ counters,
+                   Record* __restrict__ records) {
+    extern __shared__ uint32_t hub_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rpad = (n_runs + 1 + 3) & ~3;
+    const int uwords = (int)((((n_pos + 1) >> 1) + 3) & ~3u);
+    uint32_t* s_pos = hub_smem;
+    uint32_t* U = hub_smem + rpad + (size_t)warp * uwords;
+    uint4* Qs = reinterpret_cast<uint4*>(hub_smem + rpad + (size_t)kHubWarps * uwords) + (size_t)warp * kSegQueue;          // run sets
+    uint2* Qa = reinterpret_cast<uint2*>(hub_smem + rpad + (size_t)kHubWarps * uwords + 4 * kSegQueue * kHubWarps) +
+                (size_t)warp * kSegQueue;                                                                                    // (first, end)
+    for (int r = threadIdx.x; r <= n_runs; r += blockDim.x) s_pos[r] = (uint32_t)run_pos_off[r];
+    __syncthreads();
+    unsigned long long n_items = counters[0];
+    if (n_items > (unsigned long long)max_items) n_items = (unsigned long long)max_items;
+    unsigned* rec32 = reinterpret_cast<unsigned*>(records);
+    while (true) {
+        unsigned long long it = 0;
+        if (lane == 0) it = atomicAdd(&counters[1], 1ull);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= n_items) break;
+        const uint2 item = items[it];
+        const int64_t q0 = item.x;
+        const uint32_t m = pkey[q0];
+        int64_t c = 0;  // |L_m|
+        uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;  // the runs that have a link next to m
+        while (true) {
+            const int64_t qi = q0 + c + lane;
+            const bool ok = qi < P && pkey[qi] == m;
+            if (ok) {
+                const uint32_t r = (uint32_t)prun[qi];
+                const uint32_t bit = 1u << (r & 31u), w = r >> 5;
+                a0 |= w == 0 ? bit : 0u;
+                a1 |= w == 1 ? bit : 0u;
+                a2 |= w == 2 ? bit : 0u;
+                a3 |= w == 3 ? bit : 0u;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            c += __popc(bal);
+            if (bal != 0xffffffffu) break;
+        }
+        a0 = __reduce_or_sync(0xffffffffu, a0);
+        a1 = __reduce_or_sync(0xffffffffu, a1);
+        a2 = __reduce_or_sync(0xffffffffu, a2);
+        a3 = __reduce_or_sync(0xffffffffu, a3);
+        for (int s = lane * 4; s < uwords; s += 128) *reinterpret_cast<uint4*>(U + s) = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        const int64_t rs = rowptr[m];
+        const int64_t d = rowptr[m + 1] - rs;
+        const int64_t c0 = (int64_t)item.y * kHubSeg;
+        const int64_t c1 = (c0 + kHubSeg < d) ? c0 + kHubSeg : d;
+        auto load_col = [&](int64_t bb) -> int32_t { return (bb + lane < c1) ? ldg_i32(col + rs + bb + lane) : -1; };
+        auto load_bit = [&](int32_t l) -> bool { return l >= 0 && ((__ldg(key_bits + (l >> 5)) >> (l & 31)) & 1u) != 0u; };
+        // the hits of the queued columns [base, base + count), flattened over the lanes
+        auto drain = [&](int base, int count) {
+            int h = 0;
+            if (lane < count) {
+                const uint4 g = Qs[base + lane];
+                h = __popc(g.x & a0) + __popc(g.y & a1) + __popc(g.z & a2) + __popc(g.w & a3);
+            }
+            const int incl = warp_incl_scan(h, lane);
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int excl = incl - h;
+            for (int j0 = 0; j0 < total; j0 += 32) {
+                const int j = j0 + lane;
+                const int sl = owner_lane(excl, j);
+                const int jl = j - __shfl_sync(0xffffffffu, excl, sl);
+                if (j < total) {
+                    const uint4 g = Qs[base + sl];
+                    const uint2 fe = Qa[base + sl];
+                    // the jl-th active run of the column: word, then bit
+                    const uint32_t x0 = g.x & a0, x1 = g.y & a1, x2 = g.z & a2, x3 = g.w & a3;
+                    const int p0 = __popc(x0), p1 = p0 + __popc(x1), p2 = p1 + __popc(x2);
+                    const int s0 = __popc(g.x), s1 = s0 + __popc(g.y), s2 = s1 + __popc(g.z), k = s2 + __popc(g.w);
+                    uint32_t xw, sw;
+                    int jj, below;
+                    if (jl < p0)      { xw = x0; sw = g.x; jj = jl;      below = 0; }
+                    else if (jl < p1) { xw = x1; sw = g.y; jj = jl - p0; below = s0; }
+                    else if (jl < p2) { xw = x2; sw = g.z; jj = jl - p1; below = s1; }
+                    else              { xw = x3; sw = g.w; jj = jl - p2; below = s2; }
+                    const int bit = nth_set_bit(xw, jj);
+                    const int rank = below + __popc(sw & ((1u << bit) - 1u));
+                    if ((uint32_t)k == fe.y - fe.x) {   // one entry per run
+                        count_walk<false>(U, __ldg(eval + fe.x + rank), 0u, 0u);
+                    } else {
+                        uint32_t e = fe.x + (uint32_t)__ldg(sidx + fe.x + rank);
+                        const uint32_t e1 = (rank + 1 < k) ? fe.x + (uint32_t)__ldg(sidx + fe.x + rank + 1) : fe.y;
+                        for (; e < e1; ++e) count_walk<false>(U, __ldg(eval + e), 0u, 0u);
+                    }
+                }
+            }
+        };
+        // software pipeline as in k_cn_hub_count: column of step b+3, key bit of step b+2, node entry of step b+1
+        uint2 ha_next = make_uint2(0u, 0u);
+        uint4 hs_next = make_uint4(0u, 0u, 0u, 0u);
+        auto load_entry = [&](int32_t l, bool key) {
+            if (key) {
+                ha_next = __ldg(reinterpret_cast<const uint2*>(node_index + 2 * (size_t)l));
+                hs_next = __ldg(node_index + 2 * (size_t)l + 1);
+            } else {
+                hs_next = make_uint4(0u, 0u, 0u, 0u);
+            }
+        };
+        int32_t col_n1 = load_col(c0 + 32), col_n2 = load_col(c0 + 64);
+        {
+            const int32_t l0 = load_col(c0);
+            load_entry(l0, load_bit(l0));
+        }
+        bool bit_n1 = load_bit(col_n1);
+        int qn = 0;  // queued columns (warp-uniform)
+        for (int64_t b = c0; b < c1; b += 32) {
+            const uint2 ha = ha_next;
+            const uint4 hs = hs_next;
+            load_entry(col_n1, bit_n1);
+            col_n1 = col_n2;
+            bit_n1 = load_bit(col_n1);
+            col_n2 = load_col(b + 96);
+            const bool push = ((hs.x & a0) | (hs.y & a1) | (hs.z & a2) | (hs.w & a3)) != 0u;
+            const unsigned pm = __ballot_sync(0xffffffffu, push);
+            if (pm == 0u) continue;
+            if (push) {
+                const int qi = qn + __popc(pm & ((1u << lane) - 1u));
+                Qs[qi] = hs;
+                Qa[qi] = ha;
+            }
+            qn += __popc(pm);
+            __syncwarp();
+            if (qn >= 32) {
+                qn -= 32;
+                drain(qn, 32);
+                __syncwarp();
+            }
+        }
+        if (qn > 0) drain(0, qn);
+        __syncwarp();
+        // hand the counts to the links next to m
+        if (c >= kSegLanePairs) {
+            // many links: one lane per link walks the positions of its run (links of one run read the same counters)
+            for (int64_t qb = 0; qb < c; qb += 32) {
+                uint32_t pb = 0u, pe = 0u;
+                unsigned* rec = rec32;
+                if (qb + lane < c) {
+                    const int r = prun[q0 + qb + lane];
+                    pb = s_pos[r];
+                    pe = s_pos[r + 1];
+                    rec = rec32 + 2 * prec[q0 + qb + lane] + 1;
+                }
+                for (uint32_t pos = pb; pos < pe; ++pos, rec += 2) {
+                    const uint32_t u = (U[pos >> 1] >> ((pos & 1u) << 4)) & 0xffffu;
+                    if (u) atomicAdd(rec, u);
+                }
+            }
+        } else {
+            int r_l = 0;
+            unsigned long long prec_l = 0ull;
+            if (lane < c) {
+                r_l = prun[q0 + lane];
+                prec_l = prec[q0 + lane];
+            }
+            for (int qq = 0; qq < (int)c; ++qq) {
+                const int r = __shfl_sync(0xffffffffu, r_l, qq);
+                const unsigned long long pr = __shfl_sync(0xffffffffu, prec_l, qq);
+                const uint32_t pb = s_pos[r], pe = s_pos[r + 1];
+                unsigned* rec = rec32 + 2 * pr + 1;
+                for (uint32_t pos = pb + lane; pos < pe; pos += 32) {
+                    const uint32_t u = (U[pos >> 1] >> ((pos & 1u) << 4)) & 0xffffu;
+                    if (u) atomicAdd(rec + 2 * (pos - pb), u);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// per-link look-up in the run-segment index: the entries of run r in l's list, without a search
+__device__ __forceinline__ void link_lookup_seg(const uint4* __restrict__ node_index, const uint32_t* __restrict__ key_bits,
+                                                const uint32_t* __restrict__ eval, const uint16_t* __restrict__ sidx,
+                                                uint32_t l, uint32_t r, uint32_t pos_lo, unsigned* __restrict__ rec, unsigned inc) {
+    if (key_bits != nullptr && ((__ldg(key_bits + (l >> 5)) >> (l & 31u)) & 1u) == 0u) return;
+    const uint4 s = __ldg(node_index + 2 * (size_t)l + 1);
+    bool present;
+    const int rank = seg_rank(s, r, present);
+    if (!present) return;
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(node_index + 2 * (size_t)l));
+    uint32_t e0, e1;
+    seg_bounds(s, a.x, a.y, rank, sidx, e0, e1);
+    for (uint32_t e = e0; e < e1; ++e) atomicAdd(rec + 2 * (__ldg(eval + e) - pos_lo), inc);
+}
+
 // ---- everything a link does not share ------------------------------------------------------------
 // One warp per item (link t, 32 consecutive rows of N(dst[t])): C1 (first item of the link), C2 for
 // its rows, C3 through those of its rows that have fewer than hub_d columns, their columns
@@ -548,13 +885,19 @@ __global__ void k_hub_item_links(const int32_t* __restrict__ chunk_off, int64_t 
     for (int32_t it = a + (threadIdx.x & 31); it < b; it += 32) item_link[it] = (int32_t)t;
 }
 
+template <bool kSeg>
 __global__ void __launch_bounds__(256)
 k_cn_link(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ dst,
           int64_t T, const int32_t* __restrict__ run_id, const int64_t* __restrict__ rec_off,
           const int32_t* __restrict__ chunk_off, const int64_t* __restrict__ run_pos_off,
-          const uint32_t* __restrict__ eval, const uint4* __restrict__ node_index,
+          const uint32_t* __restrict__ eval, const uint16_t* __restrict__ sidx, const uint4* __restrict__ node_index,
           const uint32_t* __restrict__ key_bits, const int32_t* __restrict__ item_link, int64_t hub_d,
           Record* __restrict__ records) {
+    // (l, run r of the link) -> the entries of r in l's list: by rank in the run-segment index, by search otherwise
+    auto lookup = [&](const uint32_t* kb, uint32_t l, uint32_t r, uint32_t pos_lo, uint32_t pos_hi, unsigned* rec, unsigned inc) {
+        if (kSeg) link_lookup_seg(node_index, kb, eval, sidx, l, r, pos_lo, rec, inc);
+        else link_lookup(node_index, kb, eval, l, r, pos_lo, pos_hi, rec, inc);
+    };
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_items = chunk_off[T];
@@ -568,13 +911,13 @@ k_cn_link(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, c
         const uint32_t pos_lo = (uint32_t)run_pos_off[r], pos_hi = (uint32_t)run_pos_off[r + 1];
         if (pos_lo == pos_hi) continue;  // the run has no positions in this pass (other class of runs, or an isolated source)
         unsigned* rec = rec32 + 2 * rec_off[t];
-        if (ch == 0 && lane == 0) link_lookup(node_index, key_bits, eval, (uint32_t)j, r, pos_lo, pos_hi, rec, 0x80000000u);  // C1
+        if (ch == 0 && lane == 0) lookup(key_bits, (uint32_t)j, r, pos_lo, pos_hi, rec, 0x80000000u);  // C1
         const int64_t oi = ch * 32 + lane;
         int64_t rs_m = 0;
         int cnt = 0;
         if (oi < d_j) {
             const int32_t m = ldg_i32(col + rs_j + oi);
-            link_lookup(node_index, key_bits, eval, (uint32_t)m, r, pos_lo, pos_hi, rec, 1u);  // C2
+            lookup(key_bits, (uint32_t)m, r, pos_lo, pos_hi, rec, 1u);  // C2
             rs_m = ldg_i64(rowptr + m);
             const int64_t d_m = ldg_i64(rowptr + m + 1) - rs_m;
             if (d_m < hub_d) cnt = (int)d_m;
@@ -599,10 +942,11 @@ k_cn_link(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, c
             for (int k = 0; k < 4; ++k) bw[k] = lc[k] >= 0 ? __ldg(key_bits + (lc[k] >> 5)) : 0u;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if ((bw[k] >> (lc[k] & 31)) & 1u) link_lookup(node_index, nullptr, eval, (uint32_t)lc[k], r, pos_lo, pos_hi, rec + 1, 1u);
+                if ((bw[k] >> (lc[k] & 31)) & 1u) lookup(nullptr, (uint32_t)lc[k], r, pos_lo, pos_hi, rec + 1, 1u);
         }
     }
 }
+
 
 static int grid_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
@@ -642,11 +986,18 @@ static int hub_aux(cudaStream_t caller, HubAux** out) {
 // One pass of the indexed stage over the runs that have positions in `run_pos_off` (an exclusive prefix over ALL
 // runs in which the runs of the other class contribute nothing): inverted index, pairs, shared-row walk, per-link
 // kernel.  Records of links outside the pass are not touched.
-static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst, int64_t T,
-                    const void* plan_scratch, const int64_t* plan_dev, const int64_t* run_pos_off, int64_t hub_d, int64_t P,
-                    int64_t E, int64_t NP, int64_t R, const HubLayout& H, void* hub_scratch, void* node_scratch,
-                    Record* records, HubAux* aux, bool first_pass, cudaStream_t st) {
-    if (NP <= 0 || E <= 0) return OCN_OK;  // no source of this pass has a neighbour: its record sets are empty
+struct PassState {            // what a failing pass has to undo (hub_pass_cleanup)
+    bool forked = false;      // the auxiliary stream holds work of this call
+    bool index_set = false;   // node_index / key_bitmap hold the index of this call
+    bool seg = false;
+    const uint32_t* ekey = nullptr;
+    const uint32_t* eval = nullptr;
+};
+
+static int hub_pass_body(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst, int64_t T,
+                         const void* plan_scratch, const int64_t* plan_dev, const int64_t* run_pos_off, int64_t hub_d, int64_t P,
+                         int64_t E, int64_t NP, int64_t R, const HubLayout& H, void* hub_scratch, uint4* node_index,
+                         Record* records, HubAux* aux, bool first_pass, cudaStream_t st, PassState& ps) {
     cudaStream_t sa = aux->stream;
     PlanLayout L = plan_layout(T);
     const char* pb = (const char*)plan_scratch;
@@ -656,7 +1007,6 @@ static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const 
     const int32_t* hub_off = (const int32_t*)(pb + L.hub_off);
     const int32_t* chunk_off = (const int32_t*)(pb + L.chunk_off);
     const int32_t* long_list = (const int32_t*)(pb + L.long_list);
-    uint4* node_index = (uint4*)node_scratch;
     char* hb = (char*)hub_scratch;
     uint32_t* pkey[2] = {(uint32_t*)(hb + H.pkey[0]), (uint32_t*)(hb + H.pkey[1])};
     uint32_t* pval[2] = {(uint32_t*)(hb + H.pval[0]), (uint32_t*)(hb + H.pval[1])};
@@ -669,13 +1019,31 @@ static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const 
     unsigned long long* counters = (unsigned long long*)(hb + H.counters);
     uint32_t* key_bitmap = (uint32_t*)(hb + H.key_bits);
     int32_t* item_link = (int32_t*)(hb + H.item_link);
+    uint16_t* sidx = (uint16_t*)(hb + H.sidx);
     const int bits = key_bits(n);
     const int th = 256;
+
+    // positions are counted a window at a time: one pass of warp-per-item for the usual stream; a pass with
+    // more positions (hub sources) uses the CTA-per-item variant with a CTA-wide window
+    const int64_t warp_win = option(OCN_OPT_HUB_WINDOW, kHubWindow), cta_win = option(OCN_OPT_HUB_CTA_WINDOW, kHubCtaWindow);
+    const bool cta = NP > warp_win;
+    const int64_t win = cta ? (NP < cta_win ? NP : cta_win) : NP;
+    const bool windowed = NP > win;  // several passes: every visit is tested against the window
+    // exact index layout: 32-byte node entries with the exact run set of every list (<= 128 runs) and the run-segment
+    // starts -- the shared pass skips the lists without an active run, the per-link kernel finds a run's entries by rank.
+    // `seg`: the opt-in segment walker of the shared pass (measured slower than the whole-list walk, see above)
+    // Both are opt-in (ocn_set_option): on the bench workload the 32-byte entries cost more than the 10 % of entry visits
+    // the exact sets save (kernel 0.587 ms against 0.571 ms with the folded sets).
+    const bool want_seg = option(OCN_OPT_HUB_WALKER, 0) == 1;
+    const bool exact = !cta && !windowed && R <= kSegRuns && NP < 65536 && (want_seg || option(OCN_OPT_HUB_EXACT, 0) == 1);
+    const bool seg = exact && want_seg;
+    ps.seg = exact;
 
     OCN_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * 4, st));
     OCN_CUDA(cudaMemsetAsync(key_bitmap, 0, sizeof(uint32_t) * (size_t)((n + 32) / 32), st));
     OCN_CUDA(cudaEventRecord(aux->ev[0], st));  // fork: everything before this call is visible to the auxiliary stream
     OCN_CUDA(cudaStreamWaitEvent(sa, aux->ev[0], 0));
+    ps.forked = true;
 
     // auxiliary stream: (shared row, link) pairs, sorted by row, and the work items
     k_hub_item_links<<<grid_for(T * 32, th), th, 0, sa>>>(chunk_off, T, item_link);
@@ -707,62 +1075,129 @@ static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const 
                                                             ekey[0], eval[0]);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ek, ev, (int)E, 0, bits, st));
-    k_hub_entry_heads<<<grid_for(E, th), th, 0, st>>>(ek.Current(), ev.Current(), run_pos_off, (int)R, E, 1, node_index, key_bitmap);
+    ps.ekey = ek.Current();
+    ps.eval = ev.Current();
+    ps.index_set = true;
+    if (exact) {
+        k_hub_entry_heads_seg<<<grid_for(E, th), th, 0, st>>>(ek.Current(), ev.Current(), run_pos_off, (int)R, E, 1, node_index, key_bitmap);
+        OCN_LAUNCH_CHECK();
+        k_hub_segments<<<grid_for(E, th), th, 0, st>>>(ek.Current(), ev.Current(), run_pos_off, (int)R, E, node_index, sidx);
+    } else {
+        k_hub_entry_heads<<<grid_for(E, th), th, 0, st>>>(ek.Current(), ev.Current(), run_pos_off, (int)R, E, 1, node_index, key_bitmap);
+    }
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cudaEventRecord(aux->ev[2], st));  // index complete
 
     // auxiliary stream: per link, C1, C2 and C3 through the rows that are not shared (needs the index only).
     // With the measurement hook set the two kernels run one after the other, so that k_cn_hub_count is timed alone.
+    auto launch_link = [&](cudaStream_t s_) {
+        if (exact)
+            k_cn_link<true><<<sm_count() * 8, 256, 0, s_>>>(rowptr, col, dst, T, run_id, rec_off, chunk_off, run_pos_off, ev.Current(),
+                                                            sidx, node_index, key_bitmap, item_link, hub_d, records);
+        else
+            k_cn_link<false><<<sm_count() * 8, 256, 0, s_>>>(rowptr, col, dst, T, run_id, rec_off, chunk_off, run_pos_off, ev.Current(),
+                                                             sidx, node_index, key_bitmap, item_link, hub_d, records);
+    };
     const bool timed_alone = g_hub_events[0] != nullptr;
     if (timed_alone) OCN_CUDA(cudaStreamWaitEvent(sa, aux->ev[1], 0));
     OCN_CUDA(cudaStreamWaitEvent(sa, aux->ev[2], 0));
-    if (!timed_alone)
-        k_cn_link<<<sm_count() * 8, 256, 0, sa>>>(rowptr, col, dst, T, run_id, rec_off, chunk_off, run_pos_off, ev.Current(),
-                                              node_index, key_bitmap, item_link, hub_d, records);
+    if (!timed_alone) launch_link(sa);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cudaEventRecord(aux->ev[3], sa));
 
     // caller's stream: the walk through the shared rows (needs the pairs and the items)
     OCN_CUDA(cudaStreamWaitEvent(st, aux->ev[1], 0));
     if (P > 0) {
-        // positions are counted a window at a time: one pass of warp-per-item for the usual stream; a pass with
-        // more positions (hub sources) uses the CTA-per-item variant with a CTA-wide window
-        int64_t warp_win = kHubWindow, cta_win = kHubCtaWindow;
-        if (const char* v = getenv("OCN_HUB_WINDOW")) warp_win = atoll(v) > 0 ? atoll(v) : warp_win;        // test hooks
-        if (const char* v = getenv("OCN_HUB_CTA_WINDOW")) cta_win = atoll(v) > 0 ? atoll(v) : cta_win;
-        const bool cta = NP > warp_win;
-        const int64_t win = cta ? (NP < cta_win ? NP : cta_win) : NP;
         const int rpad = (int)((R + 1 + 3) & ~int64_t(3));
         const int uwords = (int)((((win + 1) >> 1) + 3) & ~int64_t(3));
-        const size_t smem = sizeof(uint32_t) * ((size_t)rpad + (size_t)uwords * (cta ? 1 : kHubWarps)) +
-                            sizeof(uint2) * (size_t)kHubQueue * kHubWarps;
-        const bool windowed = NP > win;  // several passes: every visit is tested against the window
-        auto kern = cta ? (windowed ? k_cn_hub_count<true, true> : k_cn_hub_count<true, false>)
-                        : (windowed ? k_cn_hub_count<false, true> : k_cn_hub_count<false, false>);
-        OCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = (int)((200u * 1024u) / smem);
-        if (per_sm > (cta ? 3 : 8)) per_sm = cta ? 3 : 8;
-        if (per_sm < 1) per_sm = 1;
-        if (first_pass) hub_timing_record(0, st);  // (the heavy pass, if any, runs on another stream: not part of the timing)
-        for (int64_t w0 = 0; w0 < NP; w0 += win) {
-            if (w0 > 0) OCN_CUDA(cudaMemsetAsync(counters + 1, 0, sizeof(unsigned long long), st));  // restart the item counter
-            const int64_t wn = (NP - w0) < win ? (NP - w0) : win;
-            kern<<<sm_count() * per_sm, kHubThreads, smem, st>>>(
-                rowptr, col, dk.Current(), prun, prec, P, ev.Current(), node_index, key_bitmap, run_pos_off, (int)R, (uint32_t)w0,
-                (uint32_t)wn, items, H.max_items, counters, records);
+        if (seg) {
+            const size_t smem = sizeof(uint32_t) * ((size_t)rpad + (size_t)uwords * kHubWarps) + (size_t)24 * kSegQueue * kHubWarps;
+            OCN_CUDA(cudaFuncSetAttribute(k_cn_hub_count_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = (int)((200u * 1024u) / (smem + 1024));
+            const int cap = (int)option(OCN_OPT_HUB_SEG_CTAS, OCN_SEG_MINB);
+            if (per_sm > cap) per_sm = cap;
+            if (per_sm < 1) per_sm = 1;
+            if (first_pass) hub_timing_record(0, st);
+            k_cn_hub_count_seg<<<sm_count() * per_sm, kHubThreads, smem, st>>>(
+                rowptr, col, dk.Current(), prun, prec, P, ev.Current(), sidx, node_index, key_bitmap, run_pos_off, (int)R,
+                (uint32_t)NP, items, H.max_items, counters, records);
             OCN_LAUNCH_CHECK();
+            if (first_pass) hub_timing_record(1, st);
+        } else {
+            const size_t smem = sizeof(uint32_t) * ((size_t)rpad + (size_t)uwords * (cta ? 1 : kHubWarps)) +
+                                sizeof(uint2) * (size_t)kHubQueue * kHubWarps;
+            auto kern = cta ? (windowed ? k_cn_hub_count<true, true, false> : k_cn_hub_count<true, false, false>)
+                            : (windowed ? k_cn_hub_count<false, true, false>
+                                        : (exact ? k_cn_hub_count<false, false, true> : k_cn_hub_count<false, false, false>));
+            OCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = (int)((200u * 1024u) / smem);
+            if (per_sm > (cta ? 3 : 8)) per_sm = cta ? 3 : 8;
+            if (per_sm < 1) per_sm = 1;
+            if (first_pass) hub_timing_record(0, st);  // (the heavy pass, if any, runs on another stream: not part of the timing)
+            for (int64_t w0 = 0; w0 < NP; w0 += win) {
+                if (w0 > 0) OCN_CUDA(cudaMemsetAsync(counters + 1, 0, sizeof(unsigned long long), st));  // restart the item counter
+                const int64_t wn = (NP - w0) < win ? (NP - w0) : win;
+                kern<<<sm_count() * per_sm, kHubThreads, smem, st>>>(
+                    rowptr, col, dk.Current(), prun, prec, P, ev.Current(), node_index, key_bitmap, run_pos_off, (int)R, (uint32_t)w0,
+                    (uint32_t)wn, items, H.max_items, counters, records);
+                OCN_LAUNCH_CHECK();
+            }
+            if (first_pass) hub_timing_record(1, st);
         }
-        if (first_pass) hub_timing_record(1, st);
     }
     if (timed_alone) {
-        k_cn_link<<<sm_count() * 8, 256, 0, st>>>(rowptr, col, dst, T, run_id, rec_off, chunk_off, run_pos_off, ev.Current(),
-                                                  node_index, key_bitmap, item_link, hub_d, records);
+        launch_link(st);
         OCN_LAUNCH_CHECK();
     }
     OCN_CUDA(cudaStreamWaitEvent(st, aux->ev[3], 0));  // join
-    k_hub_entry_heads<<<grid_for(E, th), th, 0, st>>>(ek.Current(), ev.Current(), run_pos_off, (int)R, E, 0, node_index, key_bitmap);
+    ps.forked = false;
+    if (exact)
+        k_hub_entry_heads_seg<<<grid_for(E, th), th, 0, st>>>(ek.Current(), ev.Current(), run_pos_off, (int)R, E, 0, node_index, key_bitmap);
+    else
+        k_hub_entry_heads<<<grid_for(E, th), th, 0, st>>>(ek.Current(), ev.Current(), run_pos_off, (int)R, E, 0, node_index, key_bitmap);
     OCN_LAUNCH_CHECK();
+    ps.index_set = false;
     return OCN_OK;
+}
+
+// node_scratch buffers a failed call could not restore to zero: the next build on one of them is refused (the caller
+// has to hand in a zeroed buffer) instead of computing from a dirty index
+static std::mutex g_poison_mutex;
+static std::set<const void*> g_poisoned;
+
+static int hub_pass(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst, int64_t T,
+                    const void* plan_scratch, const int64_t* plan_dev, const int64_t* run_pos_off, int64_t hub_d, int64_t P,
+                    int64_t E, int64_t NP, int64_t R, const HubLayout& H, void* hub_scratch, void* node_scratch,
+                    Record* records, HubAux* aux, bool first_pass, cudaStream_t st, const void* poison_key) {
+    if (NP <= 0 || E <= 0) return OCN_OK;  // no source of this pass has a neighbour: its record sets are empty
+    PassState ps;
+    uint4* node_index = (uint4*)node_scratch;
+    const int rc = hub_pass_body(rowptr, col, n, src, dst, T, plan_scratch, plan_dev, run_pos_off, hub_d, P, E, NP, R, H, hub_scratch,
+                                 node_index, records, aux, first_pass, st, ps);
+    if (rc == OCN_OK) return rc;
+    // a launch or a runtime call failed half way: join the auxiliary stream and put the index back to zero, so that the
+    // caller's stream sees one ordered (failed) call and the next call starts from the contract's all-zero state
+    const std::string msg = last_error();
+    bool clean = true;
+    if (ps.forked) {
+        clean = cudaEventRecord(aux->ev[3], aux->stream) == cudaSuccess && cudaStreamWaitEvent(st, aux->ev[3], 0) == cudaSuccess;
+    }
+    if (ps.index_set && clean) {
+        const int th = 256;
+        PlanLayout L = plan_layout(T);
+        (void)L;
+        if (ps.seg)
+            k_hub_entry_heads_seg<<<grid_for(E, th), th, 0, st>>>(ps.ekey, ps.eval, run_pos_off, (int)R, E, 0, node_index, nullptr);
+        else
+            k_hub_entry_heads<<<grid_for(E, th), th, 0, st>>>(ps.ekey, ps.eval, run_pos_off, (int)R, E, 0, node_index, nullptr);
+        clean = cudaGetLastError() == cudaSuccess;
+    }
+    if (!clean) {
+        std::lock_guard<std::mutex> lock(g_poison_mutex);
+        g_poisoned.insert(poison_key);
+    }
+    last_error() = msg + (clean ? " [index restored]" : " [node_scratch left dirty: hand in a zeroed buffer]");
+    return rc;
 }
 
 // called by ocn_cn_build between the zeroing of the records and the column statistics.
@@ -783,6 +1218,12 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
                   (long long)R, (long long)NP);
     OCN_CHECK_ARG(E_heavy >= 0 && E_heavy <= E && NP_heavy >= 0 && NP_heavy <= NP, "ocn_cn_build: inconsistent plan");
     if (NP <= 0 || E <= 0) return OCN_OK;  // no source has a neighbour: every record set is empty
+    {
+        std::lock_guard<std::mutex> lock(g_poison_mutex);
+        if (g_poisoned.count(node_scratch))
+            return fail(OCN_EINVAL, "ocn_cn_build: node_scratch was left dirty by a failed call; pass a zeroed buffer "
+                                    "(ocn_cn_hub_scratch_reset after zeroing this one)");
+    }
     HubLayout H = hub_layout(n, nnz, P, E, NP, plan_host[OCN_PLAN_NUM_CHUNKS]);
     const size_t need = NP_heavy > 0 ? 2 * H.total : H.total;  // a heavy pass works in a second copy of the layout
     if (hub_scratch_bytes < need)
@@ -795,19 +1236,19 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
     const char* pb = (const char*)plan_scratch;
     if (NP_heavy == 0)  // the usual stream: one pass over the plain prefix
         return hub_pass(rowptr, col, n, src, dst, T, plan_scratch, plan_dev, (const int64_t*)(pb + L.run_pos_off), hub_d, P, E,
-                        NP, R, H, hub_scratch, node_scratch, records, aux, true, st);
+                        NP, R, H, hub_scratch, node_scratch, records, aux, true, st, node_scratch);
     // two passes side by side (disjoint records): the heavy one on its own stream with the second half of the
     // scratch and of the node index -- its kernels are short of parallelism (few links, long rows) and hide behind
     // the light pass
     OCN_CUDA(cudaEventRecord(aux->hev[0], st));
     OCN_CUDA(cudaStreamWaitEvent(aux->heavy_stream, aux->hev[0], 0));
     if (int rc = hub_pass(rowptr, col, n, src, dst, T, plan_scratch, plan_dev, (const int64_t*)(pb + L.run_pos_heavy), hub_d, P,
-                          E_heavy, NP_heavy, R, H, (char*)hub_scratch + H.total, (uint4*)node_scratch + n, records, aux_h, false,
-                          aux->heavy_stream))
+                          E_heavy, NP_heavy, R, H, (char*)hub_scratch + H.total, (uint4*)node_scratch + 2 * n, records, aux_h, false,
+                          aux->heavy_stream, node_scratch))
         return rc;
     OCN_CUDA(cudaEventRecord(aux->hev[1], aux->heavy_stream));
     if (int rc = hub_pass(rowptr, col, n, src, dst, T, plan_scratch, plan_dev, (const int64_t*)(pb + L.pos_scanN), hub_d, P,
-                          E - E_heavy, NP - NP_heavy, R, H, hub_scratch, node_scratch, records, aux, true, st))
+                          E - E_heavy, NP - NP_heavy, R, H, hub_scratch, node_scratch, records, aux, true, st, node_scratch))
         return rc;
     OCN_CUDA(cudaStreamWaitEvent(st, aux->hev[1], 0));
     return OCN_OK;
@@ -823,6 +1264,12 @@ extern "C" size_t ocn_cn_hub_bytes(int64_t n, int64_t nnz, const int64_t* plan_h
     const size_t one = hub_layout(n, nnz, plan_host[OCN_PLAN_HUB_PAIRS], plan_host[OCN_PLAN_HUB_ENTRIES],
                                   plan_host[OCN_PLAN_HUB_POSITIONS], plan_host[OCN_PLAN_NUM_CHUNKS]).total;
     return plan_host[OCN_PLAN_HUB_POSITIONS_HEAVY] > 0 ? 2 * one : one;
+}
+
+extern "C" int ocn_cn_hub_scratch_reset(const void* node_scratch) {
+    std::lock_guard<std::mutex> lock(g_poison_mutex);
+    g_poisoned.erase(node_scratch);
+    return OCN_OK;
 }
 
 extern "C" int ocn_cn_hub_timing_events(void* start_event, void* stop_event) {

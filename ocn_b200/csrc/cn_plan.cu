@@ -1,13 +1,15 @@
 // ocn_cn_plan: device-side schedule for a stream of target links.
 //
-// The stream is cut into batches of batch_size links (utils.py:8-36 PermIterator).  Inside a
-// batch, maximal runs of consecutive links with the same source node share everything that
-// depends on N(src) -- in the citation2 evaluation stream every source is repeated against
-// 1000 destinations (NeighborOverlapCitation2.py:248-252).  A work unit of ocn_cn_build is
+// The stream is cut into batches of batch_size links (utils.py:8-36 PermIterator).  Maximal runs of
+// consecutive links with the same source node share everything that depends on N(src) -- in the
+// citation2 evaluation stream every source is repeated against 1000 destinations
+// (NeighborOverlapCitation2.py:248-252).  A run may cross a batch boundary: the records of a link do not
+// depend on its batch, only the column statistics do (k_cn_colstat takes the batch from the link's
+// position in the stream).  Round 1 cut the runs at the batch boundaries: 97 runs for the 66 sources of a
+// 65 536-link session, i.e. a third of the index entries (and of the entry visits of the shared pass)
+// were duplicates of another run of the same source.  A work unit of ocn_cn_build is
 // (run, chunk of kPChunk positions of N(src), sub-list of kEdgeSub links of the run).
 #include <cub/device/device_scan.cuh>
-
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -55,7 +57,7 @@ __global__ void k_plan_edges(const int64_t* __restrict__ rowptr, const int64_t* 
     int64_t i = src[t];
     const int64_t d = rowptr[i + 1] - rowptr[i];
     rec_off[t] = d;
-    flag[t] = (t % batch_size == 0 || src[t - 1] != i) ? 1 : 0;
+    flag[t] = (t == 0 || src[t - 1] != i) ? 1 : 0;  // runs ignore batch boundaries (see the header)
     // the per-link kernels walk such a link with a whole CTA; they skip that phase when the count is zero
     if (d > kHeavyLink) atomicAdd(reinterpret_cast<unsigned long long*>(rec_off + T + 1), 1ull);
 }
@@ -66,7 +68,7 @@ __global__ void k_plan_runs(const int64_t* __restrict__ rowptr, const int64_t* _
                             int64_t* __restrict__ plan) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
-    bool first = (t % batch_size == 0) || src[t - 1] != src[t];
+    bool first = (t == 0) || src[t - 1] != src[t];
     int32_t r = run_incl[t] - 1;
     if (first) {
         run_start[r] = (int32_t)t;
@@ -329,8 +331,7 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, hub_off, hub_off, (int)(T + 1), st));
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, chunk_off, chunk_off, (int)(T + 1), st));
     int blocks2 = (int)(((T + 2) * 32 + threads - 1) / threads);
-    int64_t heavy_run = kHeavyRun;
-    if (const char* v = getenv("OCN_HUB_HEAVY_RUN")) heavy_run = atoll(v) > 0 ? atoll(v) : heavy_run;  // test hook
+    const int64_t heavy_run = option(OCN_OPT_HUB_HEAVY_RUN, kHeavyRun);
     k_plan_units<<<blocks2, threads, 0, st>>>(rowptr, col, src, T, run_start, cost_pre, resident_ctas, heavy_run, order,
                                               out_plan, run_unit_off, pos_scanN, run_pos_heavy);
     OCN_LAUNCH_CHECK();

@@ -31,6 +31,8 @@ int fail(int code, const char* fmt, ...);
 #define OCN_LAUNCH_CHECK() OCN_CUDA(cudaGetLastError())
 
 int sm_count();
+int64_t option(int key, int64_t dflt);  // ocn_set_option value, or dflt when unset (0)
+int set_option(int key, int64_t value);
 
 // ---- constants shared by the plan and the build kernel -----------------------------------
 constexpr int kPChunk = 32;   // positions of N(src) handled by one work unit (one mask word)
@@ -85,6 +87,7 @@ struct HubLayout {
     size_t prun, prec;        // int32[P] run / uint64[P] record offset of the link of every sorted pair
     size_t key_bits;          // uint32[ceil((n + 1) / 32)]: bit l = node l is a key of the index (has an entry list)
     size_t item_link;         // int32[chunks + 1]: link of every work item of the per-link kernel
+    size_t sidx;              // uint16[E]: run-segment starts of the lists with several entries per run (k_hub_segments)
     size_t cub_temp, cub_temp_bytes;    // entry pipeline (caller's stream)
     size_t cub_temp2, cub_temp2_bytes;  // pair pipeline (auxiliary stream)
     size_t total;

@@ -20,6 +20,17 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+static int64_t g_options[OCN_OPT_COUNT] = {0};
+int64_t option(int key, int64_t dflt) {
+    const int64_t v = (key >= 0 && key < OCN_OPT_COUNT) ? g_options[key] : 0;
+    return v != 0 ? v : dflt;
+}
+int set_option(int key, int64_t value) {
+    if (key < 0 || key >= OCN_OPT_COUNT) return fail(OCN_EINVAL, "ocn_set_option: unknown key %d", key);
+    g_options[key] = value;
+    return OCN_OK;
+}
+
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
     int dev = 0;
@@ -145,6 +156,8 @@ extern "C" {
 int ocn_abi_version(void) { return OCN_ABI_VERSION; }
 const char* ocn_last_error(void) { return last_error().c_str(); }
 int ocn_device_sm_count(void) { return sm_count(); }
+int ocn_set_option(int key, int64_t value) { return set_option(key, value); }
+int64_t ocn_get_option(int key) { return option(key, 0); }
 
 int ocn_graph_validate(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t nnz, int32_t* out_flags,
                        void* stream) {

@@ -22,15 +22,16 @@ def deal_batches(num_links: int, batch_size: int, rank: int, world: int) -> List
 def predicted_walk_cost(rowptr: torch.Tensor, col: torch.Tensor, src: torch.Tensor, slice_links: int,
                         batch_size: int) -> torch.Tensor:
     """int64 [ceil(T / slice_links)]: for every slice of ``slice_links`` consecutive links of the stream, the number
-    of index entries its order-3 build writes -- sum over the runs (maximal pieces of one source inside one link
-    batch, as ocn_cn_plan cuts them) of sum_{k in N(src)} d(k).  The time of a slice follows this count
+    of index entries its order-3 build writes when the slice is scored as one session -- sum over the runs (maximal
+    pieces of one source inside the slice, as ocn_cn_plan cuts them; a run may cross a link-batch boundary, so
+    ``batch_size`` no longer enters) of sum_{k in N(src)} d(k).  The time of a slice follows this count
     (profiles/r01_step_times_v22.txt: 0.56 ms + 0.82 ms per million entries at 65 536 links), which makes it the
     weight for dealing slices to ranks.  Pure integer torch ops on whatever device the graph is on; exact, so every
     rank computes the same numbers without talking to the others."""
     T = src.numel()
     deg = rowptr[1:] - rowptr[:-1]
     t = torch.arange(T, device=src.device)
-    first = (t % batch_size == 0)
+    first = (t % slice_links == 0)
     first[1:] |= src[1:] != src[:-1]
     heads = src[first]
     # F[i] = sum of the degrees of i's neighbours, for the run heads only (rows gathered, not the whole matrix)

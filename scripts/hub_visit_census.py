@@ -55,7 +55,7 @@ def main():
 
     # runs: maximal pieces of one source inside one link batch (k_plan_edges)
     t = np.arange(T)
-    first = (t % a.batch == 0) | (np.r_[-1, src[:-1]] != src)
+    first = (t == 0) | (np.r_[-1, src[:-1]] != src)   # runs cross batch boundaries (round 2; round 1 cut them: t % batch == 0)
     run_of_link = np.cumsum(first) - 1
     run_src = src[first]
     R = run_src.size

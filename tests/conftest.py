@@ -20,3 +20,16 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def lib_options():
+    """Set tuning / test options of libocn_b200 (ocn_set_option) for one test; defaults are restored afterwards."""
+    from ocn_b200 import _lib
+
+    def setter(**kw):
+        for k, v in kw.items():
+            _lib.set_option(k, v)
+
+    yield setter
+    _lib.reset_options()

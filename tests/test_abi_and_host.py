@@ -18,7 +18,7 @@ def test_library_exports_every_header_symbol():
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/ocn_b200.h but not exported"
         assert s in _lib._SIGS, f"{s} has no ctypes signature"
-    assert L.ocn_abi_version() == 2
+    assert L.ocn_abi_version() == 3
 
 
 def test_argument_errors_do_not_need_a_gpu():
@@ -208,13 +208,13 @@ def test_cost_dealing_of_stream_slices():
     slice_links, batch, world, per_rank = 64, 16, 4, 3
     T = slice_links * world * per_rank
     srcs = torch.randint(0, g.n, (T // 10 + 1,), generator=torch.Generator().manual_seed(3))
-    src = srcs.repeat_interleave(10)[:T]                      # runs of 10 links, cut again at the batch boundaries
+    src = srcs.repeat_interleave(10)[:T]                      # runs of 10 links, cut again at the slice boundaries
     cost = obdist.predicted_walk_cost(rp, col, src, slice_links, batch).tolist()
-    # brute force: runs = maximal pieces of one source inside one batch; entries = sum over runs, over k in N(src), of d(k)
+    # brute force: runs = maximal pieces of one source inside one slice (= one session); entries = sum over runs, over k in N(src), of d(k)
     ref = [0] * (T // slice_links)
     cn, rpn, s = col.numpy(), rp.numpy(), src.numpy()
     for t in range(T):
-        if t % batch == 0 or s[t] != s[t - 1]:
+        if t % slice_links == 0 or s[t] != s[t - 1]:
             ref[t // slice_links] += int(sum(deg[k] for k in cn[rpn[s[t]]:rpn[s[t] + 1]]))
     assert cost == ref
     owned = obdist.deal_by_cost(cost, world, per_rank)

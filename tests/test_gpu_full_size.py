@@ -87,3 +87,49 @@ def test_folded_a2_definition_at_ddi_shape():
     fkey = folded.row() * g.n + folded.col.long()
     assert torch.equal(fkey, ukey)
     assert torch.equal(folded.value.double(), vals)
+
+
+def _bench_slice(g, k, T=65536):
+    return g.query_edges((k + 1) * T, "stream", device=DEV)[:, k * T:(k + 1) * T].contiguous()
+
+
+def test_bench_slices_indexed_equals_tables_at_full_size(lib_options):
+    """The benchmarked workload itself (bench.py: citation2 shape, 65 536 links = 32 batches of the evaluation stream,
+    order 3): on slice 0 and on the first slice that holds a hub source (> 1024 neighbours: heavy pass, CTA-wide
+    counter windows) the indexed path -- folded 64-bit run sets (default), exact run sets, and the segment walker -- gives the records of the per-run
+    table path (hub_degree = -1) bit for bit, and the aggregates xcn1..3 / xij of the two paths agree."""
+    g = synth.make_graph("citation2", device=DEV)
+    G = ob.Graph(g.rowptr, g.col, g.n)
+    deg = g.rowptr[1:] - g.rowptr[:-1]
+    x = g.features(32, device=DEV)
+    ip3 = torch.zeros(3, device=DEV)
+    T = 65536
+    hub_slice = None
+    all_e = g.query_edges(40 * T, "stream", device=DEV)
+    for k in range(1, 40):
+        if int(deg[all_e[0, k * T:(k + 1) * T]].max()) > 1024:
+            hub_slice = k
+            break
+    assert hub_slice is not None, "the synthetic stream is expected to hold a hub source within 40 slices"
+    del all_e
+    for k in (0, hub_slice):
+        e = _bench_slice(g, k)
+        off = ob.CNSession(G, e, 2048, 3, hub_degree=-1).build(3, True)
+        assert off.hub_degree == 0
+        off.stats(5, 0.0, ip3, 0)
+        ref = off.aggregate(x, 5, 0.0, ip3)
+        nb = off.num_records * 8
+        for mode in ({}, {"hub_exact": 1}, {"hub_walker": 1}):   # folded run sets (default), exact sets, segment walker
+            lib_options(hub_walker=0, hub_exact=0)
+            lib_options(**mode)
+            on = ob.CNSession(G, e, 2048, 3).build(3, True)
+            assert on.hub_degree > 0 and on.num_records == off.num_records
+            if k == hub_slice:
+                assert on.plan_host[14] > 0, "expected a heavy-source pass on this slice"
+            assert torch.equal(on.records[:nb], off.records[:nb]), (k, mode)
+            on.stats(5, 0.0, ip3, 0)
+            got = on.aggregate(x, 5, 0.0, ip3)
+            for a, b in zip(got, ref):
+                assert torch.equal(a, b), "same records, same kernels: the aggregates must be identical"
+            on.release()
+        off.release()

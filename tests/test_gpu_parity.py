@@ -366,15 +366,14 @@ def test_hub_stage_bit_exact(name, B, hub):
 
 
 @pytest.mark.parametrize("warp_win,cta_win", [(64, 100000), (64, 96), (100000, 100000)])
-def test_hub_stage_position_windows(monkeypatch, warp_win, cta_win):
+def test_hub_stage_position_windows(lib_options, warp_win, cta_win):
     """Streams with more positions than a counter window holds: CTA-per-item counters and several passes
     (forced on a small graph through the library's test hooks) give the same records."""
     g = GRAPHS["cora"]()
     G, A = _graph(g), _sp(g)
     e = g.query_edges(300, "mixed")
     ref = R.get_cn(A, e, 3)
-    monkeypatch.setenv("OCN_HUB_WINDOW", str(warp_win))
-    monkeypatch.setenv("OCN_HUB_CTA_WINDOW", str(cta_win))
+    lib_options(hub_window=warp_win, hub_cta_window=cta_win)
     got = ob.get_cn(G, e.to(DEV), 3, True, hub_degree=3, batch_size=128)
     for k in range(3):
         _assert_rows_equal(got[k], ref[k])
@@ -382,7 +381,7 @@ def test_hub_stage_position_windows(monkeypatch, warp_win, cta_win):
 
 @pytest.mark.parametrize("name,B,kind", [("tiny_dense", 200, "mixed"), ("cora", 1500, "mixed"), ("citation2_s", 4096, "stream")])
 @pytest.mark.parametrize("heavy_run", [1, 6, 20])
-def test_hub_stage_heavy_sources_get_their_own_pass(monkeypatch, name, B, kind, heavy_run):
+def test_hub_stage_heavy_sources_get_their_own_pass(lib_options, name, B, kind, heavy_run):
     """Runs whose source has more than `heavy_run` neighbours are indexed in a second pass (forced on small graphs
     through the plan's test hook; 1024 in production): every record must still equal the oracle's, for streams
     that are all light, mixed, and (heavy_run = 1) almost all heavy."""
@@ -390,7 +389,7 @@ def test_hub_stage_heavy_sources_get_their_own_pass(monkeypatch, name, B, kind, 
     G, A = _graph(g), _sp(g)
     e = g.query_edges(B, kind)
     ref = R.get_cn(A, e, 3)
-    monkeypatch.setenv("OCN_HUB_HEAVY_RUN", str(heavy_run))
+    lib_options(hub_heavy_run=heavy_run)
     sess = ob.CNSession(G, e.to(DEV), 512, 3, hub_degree=3)
     assert sess.hub_degree == 3
     deg = (g.rowptr[1:] - g.rowptr[:-1])
@@ -400,8 +399,7 @@ def test_hub_stage_heavy_sources_get_their_own_pass(monkeypatch, name, B, kind, 
     for k in range(3):
         _assert_rows_equal(sess.extract(k + 1), ref[k])
     # and with the CTA-wide counter window forced small in the same run (several window launches per pass)
-    monkeypatch.setenv("OCN_HUB_WINDOW", "64")
-    monkeypatch.setenv("OCN_HUB_CTA_WINDOW", "160")
+    lib_options(hub_window=64, hub_cta_window=160)
     got = ob.get_cn(G, e.to(DEV), 3, True, hub_degree=3, batch_size=512)
     for k in range(3):
         _assert_rows_equal(got[k], ref[k])
@@ -425,6 +423,46 @@ def test_hub_stage_matches_table_kernel_at_scale():
     # a stream with one run per link (training shape) keeps the stage off
     many = ob.CNSession(G, g.query_edges(4096, "neg", device=DEV), 2048, 3)
     assert many.hub_degree == 0
+
+
+def _grouped_stream(g, nsrc, per_src, seed=0):
+    """nsrc random sources with neighbours, each against per_src uniform destinations (the evaluation-stream shape)."""
+    deg = g.rowptr[1:] - g.rowptr[:-1]
+    cand = torch.nonzero(deg > 0).flatten()
+    gen = torch.Generator().manual_seed(seed)
+    srcs = cand[torch.randint(0, cand.numel(), (nsrc,), generator=gen)]
+    src = srcs.repeat_interleave(per_src)
+    dst = torch.randint(0, g.n, (nsrc * per_src,), generator=gen)
+    return torch.stack((src, dst))
+
+
+@pytest.mark.parametrize("name,nsrc,per_src,hub", [("tiny_dense", 30, 12, 2), ("tiny", 100, 6, 2), ("cora", 90, 30, 3),
+                                                   ("cora", 128, 8, 8), ("citation2_s", 60, 50, 4), ("tiny_dense", 129, 3, 2)])
+def test_hub_run_segment_index(lib_options, name, nsrc, per_src, hub):
+    """Opt-in index layout for streams of up to 128 runs: 32-byte node entries with exact run sets and run-segment
+    starts (search-free per-link look-ups), with the whole-list walk of the shared rows or k_cn_hub_count_seg as
+    walker.  The records equal the oracle's under the default (folded 64-bit sets) and equal it bit for bit under
+    both options.  tiny_dense gives lists with several entries per run (the sidx path); 129 sources fall back to
+    the folded layout."""
+    g = GRAPHS[name]()
+    G, A = _graph(g), _sp(g)
+    e = _grouped_stream(g, nsrc, per_src, seed=nsrc)
+    ref = R.get_cn(A, e, 3)
+    sess = ob.CNSession(G, e.to(DEV), None, 3, hub_degree=hub)
+    assert sess.hub_degree == hub
+    if nsrc <= 128 and sess.plan_host[11] <= 4096:
+        assert sess.num_runs <= 128
+    sess.build(3, True, with_stats=False)
+    for k in range(3):
+        _assert_rows_equal(sess.extract(k + 1), ref[k])
+    nodes = [v for k, v in G._ws.items() if isinstance(k, tuple) and k[0] == "hub_node"]
+    assert nodes and all(bool((v == 0).all()) for v in nodes), "node index not restored"
+    nb = sess.num_records * 8
+    for mode in ({"hub_exact": 1}, {"hub_walker": 1}):
+        lib_options(hub_walker=0, hub_exact=0)
+        lib_options(**mode)
+        other = ob.CNSession(G, e.to(DEV), None, 3, hub_degree=hub).build(3, True, with_stats=False)
+        assert torch.equal(sess.records[:nb], other.records[:nb]), mode
 
 
 def test_torch_custom_ops():
