@@ -52,6 +52,7 @@ int ocn_device_sm_count(void);
 #define OCN_OPT_HUB_SEG_CTAS 4    /* resident CTAs per SM of k_cn_hub_count_seg (default 5) */
 #define OCN_OPT_HUB_EXACT 5       /* 1: 32-byte node entries with exact run sets + run-segment starts for streams of <= 128 runs
                                      (measured slower than the folded 64-bit sets on the bench workload; implied by WALKER = 1) */
+#define OCN_OPT_GROUPED_OFF 6     /* 1: never use the run-grouped statistics / aggregation kernels (cn_grouped.cu) */
 #define OCN_OPT_COUNT 16
 int ocn_set_option(int key, int64_t value);
 int64_t ocn_get_option(int key);
@@ -147,7 +148,7 @@ int ocn_rows_difference_fill(const int64_t* rowptr1, const int32_t* col1,
 
 /* plan[] int64 layout written by ocn_cn_plan (device): */
 #define OCN_PLAN_NUM_RECORDS 0 /* sum over edges of deg(src) */
-#define OCN_PLAN_NUM_RUNS 1    /* maximal runs of equal src inside a batch */
+#define OCN_PLAN_NUM_RUNS 1    /* maximal runs of consecutive links with one source */
 #define OCN_PLAN_NUM_UNITS 2   /* work units of ocn_cn_build */
 #define OCN_PLAN_NUM_BATCHES 3
 /* words 4..7 are internal to the library */
@@ -155,7 +156,8 @@ int ocn_rows_difference_fill(const int64_t* rowptr1, const int32_t* col1,
 #define OCN_PLAN_HUB_PAIRS 9     /* (hub row, link) pairs of the stream */
 #define OCN_PLAN_HUB_ENTRIES 10  /* (key, run, position) entries of the stream */
 #define OCN_PLAN_HUB_POSITIONS 11 /* sum over runs of deg(src) */
-#define OCN_PLAN_WORDS 16
+#define OCN_PLAN_WIDE_LINKS 16   /* links whose source has more than 64 neighbours (they stay with the per-link kernels) */
+#define OCN_PLAN_WORDS 24
 
 /* bytes of plan scratch the caller must provide for a stream of num_edges links */
 size_t ocn_cn_plan_bytes(int64_t num_edges);
@@ -210,7 +212,11 @@ int ocn_cn_stats(const int64_t* rowptr, const int32_t* col, int64_t n,
                  int order, int weighted, int variant, float fill, const float* ip,
                  int stage /* 0: scale + s12, 1: s13 + s23 (needs stage 0 and final ip[0]) */,
                  const void* plan_scratch, const void* records, const void* colstat,
-                 float* batch_scalars, void* stream);
+                 float* batch_scalars,
+                 const int64_t* plan_host /* HOST copy of plan[OCN_PLAN_WORDS] as the caller read it back, or NULL.
+                                             Streams of long runs (>= 16 links per run on average) use the run-grouped
+                                             kernels of cn_grouped.cu; NULL keeps the per-link kernels */,
+                 void* stream);
 
 int ocn_cn_aggregate(const int64_t* rowptr, const int32_t* col, int64_t n,
                      const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t batch_size,
@@ -219,7 +225,7 @@ int ocn_cn_aggregate(const int64_t* rowptr, const int32_t* col, int64_t n,
                      const float* batch_scalars,
                      const float* x, int64_t feat,
                      float* xcn1, float* xcn2, float* xcn3 /* NULL unless order 3 */,
-                     float* xij /* x[src]*x[dst], may be NULL */, void* stream);
+                     float* xij /* x[src]*x[dst], may be NULL */, const int64_t* plan_host /* as for ocn_cn_stats */, void* stream);
 
 int ocn_cn_aggregate_bwd(const int64_t* rowptr, const int32_t* col, int64_t n,
                          const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t batch_size,
@@ -244,7 +250,8 @@ int ocn_cn_extract_fill(const int64_t* rowptr, const int32_t* col, int64_t n,
 
 int ocn_cn_release(const int64_t* rowptr, const int32_t* col, int64_t n,
                    const int64_t* src, int64_t num_edges, int64_t batch_size,
-                   const void* plan_scratch, const void* records, void* colstat, void* stream);
+                   const void* plan_scratch, const void* records, void* colstat, const int64_t* plan_host /* as for ocn_cn_stats */,
+                   void* stream);
 
 /* ---- piece 2 / 3a: CSR SpMM ---------------------------------------------------------------
  * spmm_add / spmm_mean / spmm_max(src, other) (torch_sparse.matmul; model.py:6,45-53,2426-2427).

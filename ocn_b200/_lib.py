@@ -41,15 +41,15 @@ _SIGS = {
     "ocn_set_option": (c_int, [c_int, c_int64]),
     "ocn_get_option": (c_int64, [c_int]),
     "ocn_cn_stats": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, c_int,
-                             _P, _P, _P, _P, _P]),
+                             _P, _P, _P, _P, _P, _P]),
     "ocn_cn_aggregate": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P,
-                                 _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P]),
+                                 _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P]),
     "ocn_cn_aggregate_bwd": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P,
                                      _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P]),
     "ocn_cn_extract_count": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, _P, _P, _P, _P]),
     "ocn_cn_extract_fill": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P,
                                     _P, _P, _P, _P, _P, _P, _P, _P]),
-    "ocn_cn_release": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, _P, _P, _P, _P]),
+    "ocn_cn_release": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
     "ocn_spmm_csr": (c_int, [_P, _P, _P, c_int64, _P, c_int64, c_int, _P, _P]),
     "ocn_spmm_csr_bwd": (c_int, [_P, _P, _P, c_int64, _P, c_int64, c_int, _P, _P]),
     "ocn_spmm_csr_max_bwd": (c_int, [_P, _P, _P, c_int64, _P, _P, c_int64, _P, _P]),
@@ -98,7 +98,7 @@ def lib():
     return _lib
 
 
-OPTIONS = {"hub_window": 0, "hub_cta_window": 1, "hub_heavy_run": 2, "hub_walker": 3, "hub_seg_ctas": 4, "hub_exact": 5}
+OPTIONS = {"hub_window": 0, "hub_cta_window": 1, "hub_heavy_run": 2, "hub_walker": 3, "hub_seg_ctas": 4, "hub_exact": 5, "grouped_off": 6}
 
 
 def set_option(name: str, value: int) -> None:

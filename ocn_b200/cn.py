@@ -23,7 +23,7 @@ from torch import Tensor
 from . import _lib
 from .graph import Graph, _require_cuda
 
-PLAN_WORDS = 16
+PLAN_WORDS = 24
 PLAN_HUB_DEGREE = 8  # include/ocn_b200.h OCN_PLAN_HUB_DEGREE
 COLSTAT_BUDGET_BYTES = 4 << 30  # per-wave cap for the per-batch column statistics
 HUB_WORKSPACE_FLOOR = 512 << 20  # first size of the per-stream scratch of the indexed order-3 path
@@ -195,7 +195,7 @@ class CNSession:
                                            self.batch_size, self.order, int(self.weighted), int(variant), float(fill),
                                            _lib.ptr(ip), int(stage), _lib.ptr(self.plan_scratch),
                                            _lib.ptr(self.records), _lib.ptr(self.colstat), _lib.ptr(self.bscal),
-                                           _stream(self.dev)), "ocn_cn_stats")
+                                           self.plan_host, _stream(self.dev)), "ocn_cn_stats")
         return self.bscal.view(self.nb, 8)
 
     def aggregate(self, x: Tensor, variant: int, fill: float, ip: Tensor, want_xij: bool = True):
@@ -211,8 +211,8 @@ class CNSession:
                 _lib.ptr(g.rowptr), _lib.ptr(g.col), g.n, _lib.ptr(self.src), _lib.ptr(self.dst), self.T,
                 self.batch_size, self.order, int(self.weighted), int(variant), float(fill), _lib.ptr(ip),
                 _lib.ptr(self.plan_scratch), _lib.ptr(self.records), _lib.ptr(self.colstat), _lib.ptr(self.bscal),
-                _lib.ptr(x), F, _lib.ptr(xcn1), _lib.ptr(xcn2), _lib.ptr(xcn3), _lib.ptr(xij), _stream(self.dev)),
-                "ocn_cn_aggregate")
+                _lib.ptr(x), F, _lib.ptr(xcn1), _lib.ptr(xcn2), _lib.ptr(xcn3), _lib.ptr(xij), self.plan_host,
+                _stream(self.dev)), "ocn_cn_aggregate")
         return xcn1, xcn2, xcn3, xij
 
     def aggregate_bwd(self, x: Tensor, variant: int, fill: float, ip: Tensor, g1, g2, g3, gij, grad_x: Tensor):
@@ -261,7 +261,7 @@ class CNSession:
         with torch.cuda.device(self.dev):
             _lib.check(self.L.ocn_cn_release(_lib.ptr(g.rowptr), _lib.ptr(g.col), g.n, _lib.ptr(self.src), self.T,
                                              self.batch_size, _lib.ptr(self.plan_scratch), _lib.ptr(self.records),
-                                             _lib.ptr(self.colstat), _stream(self.dev)), "ocn_cn_release")
+                                             _lib.ptr(self.colstat), self.plan_host, _stream(self.dev)), "ocn_cn_release")
         self._released = True
         _return_colstat(self.g, self.colstat)
 

@@ -16,82 +16,9 @@
 //   c3(k)      = S3 - (ipn_b * w1) * c1 - ipn_c * (c2raw * (1/c2))          ; 0 -> 1
 //   C3h        = C3' * (1 / c3(k))
 #include "common.cuh"
+#include "cn_weights.cuh"
 
 namespace ocn {
-
-struct WeightParams {
-    int order, weighted, variant;
-    float fill, ipn_a, ipn_b, ipn_c;
-};
-
-struct EntryWeights {
-    float w1, w2, w3;   // C1h, C2h (cn7: raw C2), C3h values of this (link, node)
-    bool in1, in2, in3; // membership in the three patterns
-};
-
-__device__ __forceinline__ EntryWeights entry_weights(Record rec, uint32_t c1cnt, unsigned long long s2,
-                                                      unsigned long long s3, const WeightParams& P) {
-    EntryWeights W;
-    const bool has1 = (rec.x >> 31) != 0u;
-    const uint32_t C2 = rec.x & 0x7fffffffu, C3 = rec.y;
-    const float c2v = P.weighted ? (float)C2 : (C2 ? 1.0f : 0.0f);
-    const float c3v = P.weighted ? (float)C3 : (C3 ? 1.0f : 0.0f);
-    const float w1k = (c1cnt >= 2u) ? __fdiv_rn(1.0f, (float)c1cnt) : P.fill;
-    const float h1 = has1 ? w1k : 0.0f;
-    W.in1 = has1;
-    W.w1 = h1;
-    W.in2 = has1 || (P.order >= 2 && C2 != 0u);
-    W.in3 = W.in2 || (P.order >= 3 && C3 != 0u);
-    W.w2 = 0.0f;
-    W.w3 = 0.0f;
-    if (P.variant == 7) {
-        W.in2 = (P.order >= 2 && C2 != 0u);
-        W.w2 = c2v;
-        W.in3 = false;
-        return W;
-    }
-    if (P.order < 2) return W;
-    const float c1f = (float)c1cnt;
-    const float corr1a = (c1cnt >= 2u) ? __fmul_rn(__fmul_rn(P.ipn_a, w1k), c1f) : 0.0f;
-    const float c2raw = __fsub_rn((float)s2, corr1a);
-    const float c2sum = (c2raw == 0.0f) ? 1.0f : c2raw;
-    const float inv2 = __fdiv_rn(1.0f, c2sum);
-    const float v2 = __fsub_rn(c2v, __fmul_rn(P.ipn_a, h1));
-    W.w2 = W.in2 ? __fmul_rn(v2, inv2) : 0.0f;
-    if (P.order < 3) return W;
-    const float corr1b = (c1cnt >= 2u) ? __fmul_rn(__fmul_rn(P.ipn_b, w1k), c1f) : 0.0f;
-    const float t2 = (c2raw == 0.0f) ? 0.0f : __fmul_rn(c2raw, inv2);
-    const float c3raw = __fsub_rn(__fsub_rn((float)s3, corr1b), __fmul_rn(P.ipn_c, t2));
-    const float c3sum = (c3raw == 0.0f) ? 1.0f : c3raw;
-    const float inv3 = __fdiv_rn(1.0f, c3sum);
-    const float v3 = __fsub_rn(__fsub_rn(c3v, __fmul_rn(P.ipn_b, h1)), __fmul_rn(P.ipn_c, W.w2));
-    W.w3 = W.in3 ? __fmul_rn(v3, inv3) : 0.0f;
-    return W;
-}
-
-__device__ __forceinline__ WeightParams make_params(int order, int weighted, int variant, float fill,
-                                                    const float* __restrict__ ip, const float* __restrict__ bscal) {
-    WeightParams P;
-    P.order = order;
-    P.weighted = weighted;
-    P.variant = variant;
-    P.fill = fill;
-    const float scale = bscal ? bscal[0] : 0.0f;
-    const float a = ip ? ip[0] : 0.0f, b = ip ? ip[1] : 0.0f, c = ip ? ip[2] : 0.0f;
-    P.ipn_a = scale > 0.0f ? __fdiv_rn(a, scale) : a;
-    P.ipn_b = scale > 0.0f ? __fdiv_rn(b, scale) : b;
-    P.ipn_c = scale > 0.0f ? __fdiv_rn(c, scale) : c;
-    return P;
-}
-
-__device__ __forceinline__ void load_colstat(const ColStat* cs, uint32_t& c1, unsigned long long& s2,
-                                             unsigned long long& s3) {
-    const uint4 a = __ldcg(reinterpret_cast<const uint4*>(cs));
-    c1 = a.x;
-    s2 = ((unsigned long long)a.w << 32) | a.z;
-    const uint2 b = __ldcg(reinterpret_cast<const uint2*>(cs) + 2);
-    s3 = ((unsigned long long)b.y << 32) | b.x;
-}
 
 // ---- batch scalars -------------------------------------------------------------------------
 // batch_scalars[b*8 + {0: scale, 1: s12, 2: s13, 3: s23, 4: (u32) min c1>=2}]
@@ -113,7 +40,8 @@ __global__ void k_stats(const int64_t* __restrict__ rowptr, const int32_t* __res
                         const int64_t* __restrict__ src, int64_t T, int64_t batch_size, int order, int weighted,
                         int variant, float fill, const float* __restrict__ ip, int stage,
                         const int64_t* __restrict__ rec_off, const Record* __restrict__ records,
-                        const ColStat* __restrict__ colstat, float* __restrict__ bscal, float* __restrict__ partial) {
+                        const ColStat* __restrict__ colstat, float* __restrict__ bscal, float* __restrict__ partial,
+                        int64_t min_deg /* links whose source has at most this many neighbours were done by cn_grouped.cu */) {
     __shared__ float sh_a[32], sh_b[32];
     __shared__ uint32_t sh_m[32];
     const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -173,7 +101,7 @@ __global__ void k_stats(const int64_t* __restrict__ rowptr, const int32_t* __res
     for (int64_t t = warp; t < T; t += nwarps) {
         const int64_t i = src[t];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
-        if (d > kHeavyLink) continue;
+        if (d > kHeavyLink || d <= min_deg) continue;
         float s_a, s_b;
         uint32_t minc;
         walk(t, rs, d, 0, 32, s_a, s_b, minc);
@@ -243,7 +171,8 @@ k_cn_aggregate(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
                const int64_t* __restrict__ rec_off, const Record* __restrict__ records,
                const ColStat* __restrict__ colstat, const float* __restrict__ bscal,
                const float* __restrict__ x, int nvec, int lpr,
-               float* __restrict__ xcn1, float* __restrict__ xcn2, float* __restrict__ xcn3, float* __restrict__ xij) {
+               float* __restrict__ xcn1, float* __restrict__ xcn2, float* __restrict__ xcn3, float* __restrict__ xij,
+               int64_t min_deg) {
     int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int lane = lane_id();
@@ -353,7 +282,7 @@ k_cn_aggregate(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
     for (int64_t t = warp; t < T; t += nwarps) {  // one warp per link ...
         const int64_t i = src[t], j = dst[t];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
-        if (d > kHeavyLink) continue;
+        if (d > kHeavyLink || d <= min_deg) continue;
         float4 a1[VPL], a2[VPL], a3[VPL];
         walk(t, rs, d, 0, 32, a1, a2, a3);
         emit(t, a1, a2, a3, false);
@@ -601,7 +530,7 @@ extern "C" {
 int ocn_cn_stats(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, int64_t num_edges,
                  int64_t batch_size, int order, int weighted, int variant, float fill, const float* ip, int stage,
                  const void* plan_scratch, const void* records, const void* colstat, float* batch_scalars,
-                 void* stream) {
+                 const int64_t* plan_host, void* stream) {
     OCN_CHECK_ARG(rowptr && col && src && plan_scratch && colstat && batch_scalars, "ocn_cn_stats: null pointer");
     OCN_CHECK_ARG(num_edges > 0 && batch_size > 0 && n > 0, "ocn_cn_stats: sizes must be positive");
     OCN_CHECK_ARG(stage == 0 || stage == 1, "ocn_cn_stats: stage must be 0 or 1");
@@ -611,10 +540,18 @@ int ocn_cn_stats(const int64_t* rowptr, const int32_t* col, int64_t n, const int
     const int64_t nb = (num_edges + batch_size - 1) / batch_size;
     k_stats_init<<<(int)((nb + 255) / 256), 256, 0, st>>>(batch_scalars, nb, stage);
     OCN_LAUNCH_CHECK();
-    k_stats<<<grid_for_warps(num_edges), 256, 0, st>>>(rowptr, col, n, src, num_edges, batch_size, order, weighted,
-                                                       variant, fill, ip, stage, rec_off, (const Record*)records,
-                                                       (const ColStat*)colstat, batch_scalars, partial);
-    OCN_LAUNCH_CHECK();
+    const bool grouped = use_grouped(num_edges, plan_host);
+    if (grouped)
+        if (int rc = grouped_stats(rowptr, col, n, src, num_edges, batch_size, order, weighted, variant, fill, ip, stage,
+                                   plan_scratch, (const Record*)records, (const ColStat*)colstat, batch_scalars, partial, st))
+            return rc;
+    if (!grouped || plan_host[OCN_PLAN_WIDE_LINKS] > 0) {  // every link, or the ones the grouped kernel left out
+        k_stats<<<grid_for_warps(num_edges), 256, 0, st>>>(rowptr, col, n, src, num_edges, batch_size, order, weighted,
+                                                           variant, fill, ip, stage, rec_off, (const Record*)records,
+                                                           (const ColStat*)colstat, batch_scalars, partial,
+                                                           grouped ? (int64_t)kGroupedMaxDeg : (int64_t)-1);
+        OCN_LAUNCH_CHECK();
+    }
     k_stats_finalize<<<(int)nb, 256, 0, st>>>(num_edges, batch_size, stage, partial, batch_scalars);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
@@ -624,7 +561,7 @@ int ocn_cn_aggregate(const int64_t* rowptr, const int32_t* col, int64_t n, const
                      int64_t num_edges, int64_t batch_size, int order, int weighted, int variant, float fill,
                      const float* ip, const void* plan_scratch, const void* records, const void* colstat,
                      const float* batch_scalars, const float* x, int64_t feat, float* xcn1, float* xcn2, float* xcn3,
-                     float* xij, void* stream) {
+                     float* xij, const int64_t* plan_host, void* stream) {
     OCN_CHECK_ARG(rowptr && col && src && dst && plan_scratch && colstat && batch_scalars && x && xcn1,
                   "ocn_cn_aggregate: null pointer");
     OCN_CHECK_ARG(num_edges > 0 && batch_size > 0 && n > 0, "ocn_cn_aggregate: sizes must be positive");
@@ -635,6 +572,15 @@ int ocn_cn_aggregate(const int64_t* rowptr, const int32_t* col, int64_t n, const
     cudaStream_t st = (cudaStream_t)stream;
     PLAN_PTRS();
     const int nvec = (int)(feat / 4);
+    const bool grouped = use_grouped(num_edges, plan_host) && grouped_aggregate_smem(nvec) <= 96 * 1024;
+    if (grouped) {
+        if (int rc = grouped_aggregate(rowptr, col, n, src, dst, num_edges, batch_size, order, weighted, variant, fill, ip,
+                                       plan_scratch, (const Record*)records, (const ColStat*)colstat, batch_scalars, x, nvec,
+                                       xcn1, xcn2, xcn3, xij, st))
+            return rc;
+        if (plan_host[OCN_PLAN_WIDE_LINKS] == 0) return OCN_OK;
+    }
+    const int64_t min_deg = grouped ? kGroupedMaxDeg : -1;  // grouped: only the links the grouped kernel left out
     int lpr = 1;
     while (lpr < nvec && lpr < 32) lpr <<= 1;
     const int vpl = (nvec + 31) / 32;
@@ -642,7 +588,7 @@ int ocn_cn_aggregate(const int64_t* rowptr, const int32_t* col, int64_t n, const
 #define AGG(V)                                                                                                       \
     k_cn_aggregate<V><<<grid, 256, 0, st>>>(rowptr, col, n, src, dst, num_edges, batch_size, order, weighted, variant, \
                                             fill, ip, rec_off, (const Record*)records, (const ColStat*)colstat,      \
-                                            batch_scalars, x, nvec, lpr, xcn1, xcn2, xcn3, xij)
+                                            batch_scalars, x, nvec, lpr, xcn1, xcn2, xcn3, xij, min_deg)
     if (vpl <= 1) AGG(1);
     else if (vpl <= 2) AGG(2);
     else if (vpl <= 4) AGG(4);
@@ -710,11 +656,14 @@ int ocn_cn_extract_fill(const int64_t* rowptr, const int32_t* col, int64_t n, co
 }
 
 int ocn_cn_release(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, int64_t num_edges,
-                   int64_t batch_size, const void* plan_scratch, const void* records, void* colstat, void* stream) {
+                   int64_t batch_size, const void* plan_scratch, const void* records, void* colstat,
+                   const int64_t* plan_host, void* stream) {
     OCN_CHECK_ARG(rowptr && col && src && plan_scratch && records && colstat, "ocn_cn_release: null pointer");
     OCN_CHECK_ARG(num_edges > 0 && batch_size > 0, "ocn_cn_release: sizes must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     PLAN_PTRS();
+    if (use_grouped(num_edges, plan_host))
+        return grouped_release(rowptr, col, n, src, num_edges, batch_size, plan_scratch, (ColStat*)colstat, st);
     k_cn_release<<<grid_for_warps(num_edges), 256, 0, st>>>(rowptr, col, n, src, num_edges, batch_size, rec_off,
                                                              (const Record*)records, (ColStat*)colstat);
     OCN_LAUNCH_CHECK();

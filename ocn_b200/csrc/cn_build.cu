@@ -633,7 +633,7 @@ k_cn_build_direct(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
 __global__ void k_cn_colstat(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
                              const int64_t* __restrict__ src, int64_t T, int64_t batch_size, int weighted,
                              const int64_t* __restrict__ rec_off, const Record* __restrict__ records,
-                             ColStat* __restrict__ colstat) {
+                             ColStat* __restrict__ colstat, int64_t min_deg) {
     const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     int64_t warp = (int64_t)blockIdx.x * wpb + wib;
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
@@ -658,7 +658,7 @@ __global__ void k_cn_colstat(const int64_t* __restrict__ rowptr, const int32_t* 
     for (int64_t t = warp; t < T; t += nwarps) {  // one warp per link ...
         const int64_t i = src[t];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
-        if (d <= kHeavyLink) walk(t, rs, d, lane, 32);
+        if (d <= kHeavyLink && d > min_deg) walk(t, rs, d, lane, 32);
     }
     for_each_heavy_link(rowptr, src, T, rec_off, [&](int64_t t) {  // ... a whole CTA per link with a heavy source
         const int64_t i = src[t];
@@ -716,11 +716,17 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
             (Record*)records);
         OCN_LAUNCH_CHECK();
     }
-    if (colstat != nullptr) {
+    const bool grouped = colstat != nullptr && use_grouped(num_edges, plan_host);
+    if (grouped)
+        if (int rc = grouped_colstat(rowptr, col, n, src, num_edges, batch_size, weighted, plan_scratch, (const Record*)records,
+                                     (ColStat*)colstat, st))
+            return rc;
+    if (colstat != nullptr && (!grouped || plan_host[OCN_PLAN_WIDE_LINKS] > 0)) {
         int64_t want = (num_edges + 7) / 8;
         int64_t cap = (int64_t)sm_count() * 8;
         k_cn_colstat<<<(int)(want < cap ? want : cap), 256, 0, st>>>(rowptr, col, n, src, num_edges, batch_size, weighted,
-                                                                    rec_off, (const Record*)records, (ColStat*)colstat);
+                                                                    rec_off, (const Record*)records, (ColStat*)colstat,
+                                                                    grouped ? (int64_t)kGroupedMaxDeg : (int64_t)-1);
         OCN_LAUNCH_CHECK();
     }
     return OCN_OK;

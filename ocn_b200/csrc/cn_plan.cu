@@ -46,7 +46,8 @@ PlanLayout plan_layout(int64_t T) {
 }
 
 __global__ void k_plan_edges(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ src, int64_t T,
-                             int64_t batch_size, int64_t* __restrict__ rec_off, int32_t* __restrict__ flag) {
+                             int64_t batch_size, int64_t* __restrict__ rec_off, int32_t* __restrict__ flag,
+                             int64_t* __restrict__ plan) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t > T) return;
     if (t == T) {
@@ -60,6 +61,9 @@ __global__ void k_plan_edges(const int64_t* __restrict__ rowptr, const int64_t* 
     flag[t] = (t == 0 || src[t - 1] != i) ? 1 : 0;  // runs ignore batch boundaries (see the header)
     // the per-link kernels walk such a link with a whole CTA; they skip that phase when the count is zero
     if (d > kHeavyLink) atomicAdd(reinterpret_cast<unsigned long long*>(rec_off + T + 1), 1ull);
+    // ... and the run-grouped kernels leave links with a source of more than kGroupedMaxDeg neighbours to them (rare in
+    // a stream of uniformly drawn sources: one atomic per such link)
+    if (d > kGroupedMaxDeg) atomicAdd(reinterpret_cast<unsigned long long*>(plan + OCN_PLAN_WIDE_LINKS), 1ull);
 }
 
 // after the inclusive scan flag[t] = run index + 1
@@ -310,7 +314,7 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
         if (hub_degree < 32) hub_degree = 32;
     }
     OCN_CUDA(cudaMemsetAsync(rec_off + T + 1, 0, sizeof(int64_t), st));
-    k_plan_edges<<<blocks, threads, 0, st>>>(rowptr, src, T, batch_size, rec_off, run_id);
+    k_plan_edges<<<blocks, threads, 0, st>>>(rowptr, src, T, batch_size, rec_off, run_id, out_plan);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, rec_off, rec_off, (int)(T + 1), st));
     OCN_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, run_id, run_id, (int)(T + 1), st));

@@ -97,6 +97,23 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
                   int64_t T, const void* plan_scratch, const int64_t* plan_dev, const int64_t* plan_host, void* hub_scratch,
                   size_t hub_scratch_bytes, void* node_scratch, Record* records, int64_t nnz, cudaStream_t st);
 
+// run-grouped kernels after the build (cn_grouped.cu): used when the stream averages >= kGroupedMinRun links per run
+constexpr int kGroupedMinRun = 16;
+constexpr int kGroupedMaxDeg = 64;   // sources with more neighbours (more than two position tiles) stay with the per-link kernels
+bool use_grouped(int64_t T, const int64_t* plan_host);
+int grouped_colstat(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, int64_t T, int64_t batch_size,
+                    int weighted, const void* plan_scratch, const Record* records, ColStat* colstat, cudaStream_t st);
+int grouped_stats(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, int64_t T, int64_t batch_size,
+                  int order, int weighted, int variant, float fill, const float* ip, int stage, const void* plan_scratch,
+                  const Record* records, const ColStat* colstat, float* bscal, float* partial, cudaStream_t st);
+size_t grouped_aggregate_smem(int nvec);
+int grouped_aggregate(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst, int64_t T,
+                      int64_t batch_size, int order, int weighted, int variant, float fill, const float* ip,
+                      const void* plan_scratch, const Record* records, const ColStat* colstat, const float* bscal,
+                      const float* x, int nvec, float* xcn1, float* xcn2, float* xcn3, float* xij, cudaStream_t st);
+int grouped_release(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, int64_t T, int64_t batch_size,
+                    const void* plan_scratch, ColStat* colstat, cudaStream_t st);
+
 // cost window (in probed columns) one work unit of ocn_cn_build covers: about 8 units per resident CTA,
 // clamped so that a unit amortises its table build but a heavy link is still split over many CTAs
 __host__ __device__ inline long long unit_budget(long long total_cost, int resident_ctas) {

@@ -465,6 +465,59 @@ def test_hub_run_segment_index(lib_options, name, nsrc, per_src, hub):
         assert torch.equal(sess.records[:nb], other.records[:nb]), mode
 
 
+@pytest.mark.parametrize("name,nsrc,per_src,batch,F", [("cora", 20, 40, 64, 32), ("tiny_dense", 12, 50, 100, 8), ("citation2_s", 9, 300, 512, 64),
+                                                       ("cora", 6, 200, 2048, 256), ("pubmed", 30, 17, 96, 32)])
+@pytest.mark.parametrize("order,variant,weighted", [(3, 5, True), (2, 5, False), (2, 7, True)])
+def test_run_grouped_kernels(lib_options, name, nsrc, per_src, batch, F, order, variant, weighted):
+    """Streams of long runs (>= 16 links per source) take the run-grouped kernels of cn_grouped.cu for the column
+    statistics, batch scalars, aggregation and release: integer statistics and batch scalars equal the per-link
+    kernels' bit for bit (=> identical normalised matrices), the aggregates agree within the fp32 tolerance (the
+    sums run in a different order) and with the oracle; batches that cut runs, position tiles (> 32 neighbours) and
+    windows that hold several runs are all in the cases."""
+    g = GRAPHS[name]()
+    G, A = _graph(g), _sp(g)
+    e = _grouped_stream(g, nsrc, per_src, seed=per_src)
+    ed, x = e.to(DEV), g.features(F)
+    ip = 0.37
+    ip3 = torch.full((3,), ip, dtype=torch.float32, device=DEV)
+    fill = 1.0 if variant == 7 else 0.0
+    res = {}
+    for off in (0, 1):
+        lib_options(grouped_off=off)
+        sess = ob.CNSession(G, ed, batch, order).build(order, weighted)
+        assert sess.T >= 16 * sess.num_runs
+        if variant == 5:
+            sess.stats(5, fill, ip3, 0)
+        outs = sess.aggregate(x.to(DEV), variant, fill, ip3)
+        mats = [sess.extract(10 + k, variant, fill, ip3) for k in range(1, (order if variant == 5 else 1) + 1)]
+        res[off] = (sess.bscal.clone(), outs, mats)
+        sess.release()
+        assert int(sess.colstat.count_nonzero()) == 0, "release left statistics behind"
+    assert torch.equal(res[0][0].view(torch.int32), res[1][0].view(torch.int32)), "batch scalars differ between the grouped and the per-link kernels"
+    for a, b in zip(res[0][2], res[1][2]):
+        assert torch.equal(a.col, b.col) and torch.equal(a.value, b.value)
+    for a, b in zip(res[0][1], res[1][1]):
+        if a is not None:
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), (a - b).abs().max()
+    assert torch.equal(res[0][1][3], res[1][1][3])   # pair term
+    # against the oracle, batch by batch (every batch is normalised on its own)
+    T = e.shape[1]
+    for s in range(0, T, batch):
+        eb = e[:, s:s + batch]
+        cns = _oracle_cns(A, eb, order, weighted)
+        if variant == 7:
+            r = R.cn7_aggregate(cns[0], cns[1], x, eb, fill)
+            refs, masses = [r[0], r[1]], [_mass(r[3], x), _mass(cns[1], x)]
+        elif order == 3:
+            r = R.cn6_aggregate(cns[0], cns[1], cns[2], x, eb, R.InnerProdState(ip), training=False)
+            refs, masses = [r[0], r[1], r[2]], [_mass(r[4], x), _mass(r[5], x), _mass(r[6], x)]
+        else:
+            r = R.cn5_aggregate(cns[0], cns[1], x, eb, R.InnerProdState(ip), training=False)
+            refs, masses = [r[0], r[1]], [_mass(r[3], x), _mass(r[4], x)]
+        for k, (ref, mass) in enumerate(zip(refs, masses)):
+            _close(res[0][1][k][s:s + batch], ref, mass, rtol=1e-4)
+
+
 def test_torch_custom_ops():
     """torch.ops.ocn.* (north_star: the C ABI exposed as PyTorch custom ops), incl. autograd registration."""
     g = GRAPHS["cora"]()
