@@ -4,12 +4,14 @@
     python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU op sequence (oracle port)
 
-One *step* = one pass of the hot path (CN sets of orders 1..3 -> batch normalisation /
+One *session* = one pass of the hot path (CN sets of orders 1..3 -> batch normalisation /
 orthogonalisation -> CN-indicator SpMM + pair term) over ``--batches`` consecutive link batches of
 2048 links in the shape of the citation2 evaluation stream (NeighborOverlapCitation2.py:241-254:
-every source against 1000 uniform destinations).  Under torchrun every rank holds a replica of
-the graph and features and scores its own batches (weak scaling, no data-path collective); in the
-end-to-end arm every rank reads its scores back per step and the ranks gather all fp32 scores once at the end (NCCL).
+every source against 1000 uniform destinations).  One *step* = ``--sessions`` consecutive sessions
+(default 48: 3.1 M links, ~50 ms, so that 20 steps time about a second; round 1 timed 25 ms in all).
+Under torchrun every rank holds a replica of the graph and features and scores its own sessions
+(weak scaling, no data-path collective); in the end-to-end arm every rank reads its scores back per
+session and the ranks gather all fp32 scores once at the end (NCCL).
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the byte accounting.
 """
@@ -57,7 +59,9 @@ def parse():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--order", type=int, default=3)
     ap.add_argument("--batch", type=int, default=2048)
-    ap.add_argument("--batches", type=int, default=32, help="link batches per step")
+    ap.add_argument("--batches", type=int, default=32, help="link batches per session (one plan / build / aggregate pass)")
+    ap.add_argument("--sessions", type=int, default=48, help="sessions per step")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the `secondary` measurements (SURVEY 8(d))")
     ap.add_argument("--feat", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=48, help="links of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -68,7 +72,7 @@ def parse():
                          "the small head / gather kernels and the D2H read of one step overlap the walks of the next "
                          "(measured 41.0 -> 43.2 M links/s); the device-resident leg always uses one stream")
     ap.add_argument("--slice-offset", type=int, default=0,
-                    help="skip this many steps' worth of links of the stream (one GPU re-enacts the slices another rank gets)")
+                    help="skip this many sessions' worth of links of the stream (one GPU re-enacts the sessions another rank gets)")
     ap.add_argument("--deal", choices=("cost", "contiguous"), default="cost",
                     help="several ranks: 'cost' deals the timed slices of the stream so that every rank gets the same "
                          "number of slices and a balanced predicted cost (ocn_b200.dist.predicted_walk_cost / "
@@ -235,11 +239,13 @@ def run_reference(a, rank, world):
 
 
 def workload_config(a, g):
+    T = a.batch * a.batches
     return {"workload": f"{a.graph}-shape synthetic graph (N={g.n}, nnz={g.nnz}), cn5 order {a.order} (cn6 template) "
                         f"scoring, F={a.feat}, evaluation link stream (each source x 1000 uniform destinations)",
-            "link_batch": a.batch, "batches_per_step": a.batches, "links_per_step_per_gpu": a.batch * a.batches,
-            "weighted": True, "l2": "inputs larger than L2 (CSR col 244 MB + fresh links every step)",
-            "parallelism": f"graph replicated, link batches sharded over {a.gpus} GPU(s)"}
+            "link_batch": a.batch, "batches_per_session": a.batches, "links_per_session": T,
+            "sessions_per_step": a.sessions, "links_per_step_per_gpu": T * a.sessions,
+            "weighted": True, "l2": "inputs larger than L2 (CSR col 244 MB + fresh links every session)",
+            "parallelism": f"graph replicated, sessions of {a.batches} link batches sharded over {a.gpus} GPU(s)"}
 
 
 def cpu_baseline(a, g, rowptr, col):
@@ -262,7 +268,114 @@ def cpu_baseline(a, g, rowptr, col):
         best = dt if best is None else min(best, dt)
     return {"value": S / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{S} links of the same stream (order {a.order}, F={a.feat}); oracle/ref_ops.py get_cn + "
-                      f"cn6_aggregate, best of 2"}
+                      f"cn6_aggregate, best of 2; the GPU arm's steps are {a.batch * a.batches * a.sessions} links each"}
+
+
+def kernel_source_sha():
+    """sha1 over the sources of the dominant kernel: profiles/traffic.json carries the one its ncu capture was taken
+    from, and `roofline.traffic` is only reported when the two agree."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in ("cn_hub.cu", "common.cuh"):
+        with open(os.path.join(ROOT, "ocn_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def percentile(xs, q):
+    xs = sorted(xs)
+    return xs[min(len(xs) - 1, int(q * len(xs)))] if xs else None
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def secondary(a, ob, synth, G, g, x, sampler, peak, dev):
+    """The other measurements SURVEY.md 8(d) lists, each CUDA-event timed (median of 5 after 2 warm-ups) with the SM
+    clock sampled while it runs: GNN SpMM GB/s, A^2 SpGEMM products/s, order 2 (the reference-pinned K = 2), one
+    optimiser step, and configs 1-4 through the fused path.  Kept under ~20 s."""
+    out = {}
+
+    def measure(name, fn, extra, reps=5, warm=2):
+        sampler.start()
+        ms = timeit(fn, reps, warm)
+        clk = sampler.stop()
+        rec = {"ms": ms, "sm_mhz": clk["sm_mhz"], "reasons": clk["reasons"]}
+        rec.update(extra(ms))
+        out[name] = rec
+
+    # (1) GNN neighbour aggregation at citation2 shape (PureConv3 / GCNConv propagate, model.py:128-142)
+    norm = ob.gcn_norm(G)
+    for F in (32, 128):
+        xf = x if F == a.feat else g.features(F, device=dev)
+        byt = 8 * (g.n + 1) + 4 * g.nnz + 4 * F * g.nnz + 4 * F * g.n
+        measure(f"gnn_spmm_gcn_citation2_F{F}", lambda: ob.pure_conv(xf, G, "gcn", norm),
+                lambda ms: {"alg_GBs": byt / ms / 1e6, "frac_of_measured_hbm": byt / ms / 1e6 / peak})
+    # (2) order 2 on the same stream (get_cn1_cn2 as the reference's citation2 driver calls it)
+    T = a.batch * a.batches
+    e2 = g.stream_links(7 * T, 4 * T, device=dev)
+    ip3 = torch.zeros(3, device=dev)
+
+    def order2():
+        for k in range(4):
+            s = ob.CNSession(G, e2[:, k * T:(k + 1) * T], a.batch, 2).build(2, True)
+            s.stats(5, 0.0, ip3, 0)
+            s.aggregate(x, 5, 0.0, ip3)
+            s.release()
+    measure("cn5_order2_citation2_stream", order2, lambda ms: {"links": 4 * T, "Mlinks_per_s": 4 * T / ms / 1e3}, reps=3, warm=1)
+    # (3) one optimiser step of the citation2 driver's predictor loop (NeighborOverlapCitation2.py:131-209)
+    from ocn_b200.dist import sharded_train_step
+    torch.manual_seed(0)
+    pred = ob.CNLinkPredictorOringin(a.feat, a.feat, 1, 3, 0.0, weighted=True).to(dev).train()
+    h = x.clone().requires_grad_(True)
+    pos = g.query_edges(16384, "pos", device=dev)
+    neg = torch.stack((pos[0], synth.hash_randint(16384, g.n, 5, 9, dev)))
+    subs = [pos[:, k:k + 2048] for k in range(0, 16384, 2048)] + [neg[:, k:k + 2048] for k in range(0, 16384, 2048)]
+    signs = [1.0] * 8 + [-1.0] * 8
+
+    def train_step():
+        pred.zero_grad(set_to_none=True)
+        h.grad = None
+        return sharded_train_step(pred, h, G, subs, signs, 16384, 0, 1)
+    measure("training_step_cn5_order2_32768_links", train_step, lambda ms: {"Mlinks_per_s": 32768 / ms / 1e3}, reps=3, warm=1)
+    del pred, h
+    # (4) configs 1-4 of BASELINE.json: A^2 (true) and the fused order-2 path at each config's batch and width
+    for name in ("cora", "pubmed", "collab", "ddi"):
+        gg = synth.make_graph(name, device=dev)
+        GG = ob.Graph(gg.rowptr, gg.col, gg.n)
+        deg = GG.degree()
+        prods = int(deg[gg.col.long()].sum())
+        if name in ("collab", "ddi"):
+            measure(f"spgemm_a2_{name}", lambda: ob.spgemm_a2(GG, 0, True),
+                    lambda ms: {"products": prods, "Gproducts_per_s": prods / ms / 1e6}, reps=3, warm=1)
+        e = gg.query_edges(gg.batch, "mixed", device=dev)
+        xx = gg.features(gg.hidden, device=dev)
+        variant = 5 if gg.predictor == "cn5" else 7
+
+        def fused():
+            s = ob.CNSession(GG, e, gg.batch, 2).build(2, False)
+            if variant == 5:
+                s.stats(5, 0.0, ip3, 0)
+            r = s.aggregate(xx, variant, 1.0 if variant == 7 else 0.0, ip3)
+            s.release()
+            return r
+        measure(f"fused_{gg.predictor}_order2_{name}", fused,
+                lambda ms: {"B": gg.batch, "F": gg.hidden, "Mlinks_per_s": gg.batch / ms / 1e3}, reps=3, warm=1)
+        del GG, gg
+    return out
 
 
 def main():
@@ -287,37 +400,38 @@ def main():
     g = synth.make_graph(a.graph, device=dev, scale=a.scale)
     G = ob.Graph(g.rowptr, g.col, g.n)
     x = g.features(a.feat, device=dev)
-    T = a.batch * a.batches
+    T = a.batch * a.batches          # links per session
+    S = a.sessions                   # sessions per step
     nsteps = a.steps + a.warmup
-    # every rank scores its own slice of the stream; every step gets fresh links
-    e_all = g.query_edges((world * nsteps + a.slice_offset) * T, "stream", device=dev)[:, a.slice_offset * T:]
-    e_rank = e_all[:, rank * nsteps * T:(rank + 1) * nsteps * T].contiguous()
-    dealing = "contiguous slices per rank"
+    nsess = nsteps * S               # sessions of this rank; session q of rank r covers stream sessions r * nsess + q
+    base = a.slice_offset + rank * nsess
+    ids = list(range(base, base + nsess))  # stream session of every local session
+    dealing = "contiguous sessions per rank"
     if world > 1 and a.deal == "cost":
-        # slices differ in cost (0.56 ms + 0.82 ms per million index entries; one slice in 26 holds a hub source):
-        # the timed slices of all ranks are dealt by predicted cost, same count per rank, no slice split.  The
+        # sessions differ in cost (the time follows the index entries a session writes; one in ~26 holds a hub source):
+        # the timed sessions of all ranks are dealt by predicted cost, same count per rank, no session split.  The
         # prediction is exact integer arithmetic on the replicated graph, so the ranks agree without a collective.
         try:
             from ocn_b200 import dist as obdist
-            cost = obdist.predicted_walk_cost(g.rowptr, g.col, e_all[0, :world * nsteps * T], T, a.batch).tolist()
-            pool = [r * nsteps + a.warmup + k for r in range(world) for k in range(a.steps)]
-            mine = obdist.deal_by_cost([cost[i] for i in pool], world, a.steps)[rank]
-            ids = list(range(rank * nsteps, rank * nsteps + a.warmup)) + [pool[i] for i in mine]
-            e_rank = torch.cat([e_all[:, i * T:(i + 1) * T] for i in ids], dim=1).contiguous()
-            dealing = "timed slices dealt by predicted index entries (longest first, equal count per rank)"
-        except Exception as ex:  # never lose a measurement to the dealing: fall back to the contiguous slices
-            dealing = f"contiguous slices per rank (cost dealing failed: {type(ex).__name__}: {ex})"
-    del e_all
+            src_all = g.stream_links(a.slice_offset * T, world * nsess * T, device=dev)[0]
+            cost = obdist.predicted_walk_cost(g.rowptr, g.col, src_all, T, a.batch).tolist()
+            del src_all
+            pool = [r * nsess + a.warmup * S + k for r in range(world) for k in range(a.steps * S)]
+            mine = obdist.deal_by_cost([cost[i] for i in pool], world, a.steps * S)[rank]
+            ids = ids[:a.warmup * S] + [a.slice_offset + pool[i] for i in mine]
+            dealing = "timed sessions dealt by predicted index entries (longest first, equal count per rank)"
+        except Exception as ex:  # never lose a measurement to the dealing: fall back to the contiguous sessions
+            dealing = f"contiguous sessions per rank (cost dealing failed: {type(ex).__name__}: {ex})"
+    e_rank = torch.cat([g.stream_links(i * T, T, device=dev) for i in ids], dim=1).contiguous()
     e_host = e_rank.cpu().pin_memory()
     torch.manual_seed(0)
     cls = ob.CNLinkPredictor3hopCNs if a.order >= 3 else ob.CNLinkPredictorOringin
     pred = cls(a.feat, a.feat, 1, 3, 0.0, weighted=True).to(dev).eval()
     ip3 = torch.zeros(3, device=dev)
 
-    # the plan of a step (and its size read-back) runs on its own stream: the host waits for the plan only,
-    # while the main stream is still executing the previous step
+    # the plan of a session (and its size read-back) runs on its own stream: the host waits for the plan only,
+    # while the main stream is still executing the previous session
     plan_stream = None if a.no_plan_stream else torch.cuda.Stream(device=dev)
-
     streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, a.streams))]
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     # one cached block per stream (and one for the default stream of the roofline leg): the per-session buffers are
@@ -335,48 +449,60 @@ def main():
         for st in streams + ([comm_stream] if comm_stream is not None else []):
             torch.cuda.current_stream().wait_stream(st)
 
-    def step_device(s):  # device-resident leg
-        with torch.cuda.stream(streams[s % max(1, min(a.device_streams, len(streams)))]):
-            e = e_rank[:, s * T:(s + 1) * T]
+    L = ob._lib.lib()
+    sess_events = []  # (start, end) CUDA events of every timed session of the device-resident leg
+
+    def session_device(q, timed):
+        st = streams[q % max(1, min(a.device_streams, len(streams)))]
+        with torch.cuda.stream(st):
+            ev = None
+            if timed:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            e = e_rank[:, q * T:(q + 1) * T]
             sess = ob.CNSession(G, e, a.batch, a.order, a.hub, plan_stream=plan_stream).build(a.order, True)
             sess.stats(5, 0.0, ip3, 0)
             out = sess.aggregate(x, 5, 0.0, ip3)
             sess.release()
+            if timed:
+                ev[1].record()
+                sess_events.append(ev)
         return out
 
-    out_host = [torch.empty(world * T, dtype=torch.float32).pin_memory() for _ in range(nsteps)]
+    out_host = torch.empty(a.steps * S * T, dtype=torch.float32).pin_memory()
+    rank_scores = torch.empty(a.steps * S, T, dtype=torch.float32, device=dev) if world > 1 else None
+    gathered_host = torch.empty(world * a.steps * S * T, dtype=torch.float32).pin_memory() if world > 1 else None
 
-    def step_e2e(s):
+    def session_e2e(q, timed):
         with torch.cuda.stream(plan_stream if plan_stream is not None else torch.cuda.current_stream()):
-            e = e_host[:, s * T:(s + 1) * T].to(dev, non_blocking=True)
-        with torch.no_grad(), torch.cuda.stream(streams[s % len(streams)]):
+            e = e_host[:, q * T:(q + 1) * T].to(dev, non_blocking=True)
+        with torch.no_grad(), torch.cuda.stream(streams[q % len(streams)]):
             sess = ob.CNSession(G, e, a.batch, a.order, a.hub, plan_stream=plan_stream).build(a.order, True)
             if a.order >= 3:
                 out = pred(x, G, sess, None, None, e)
             else:
                 out = pred(x, G, sess, None, e)
             scores = out.squeeze(-1).contiguous()
-            # device -> host read of the step's result: asynchronous copy into pinned memory (an evaluation loop
+            # device -> host read of the session's result: asynchronous copy into pinned memory (an evaluation loop
             # collects the scores of every batch and ranks them at the end); the timed region ends with a full sync.
             # With several ranks every rank reads back its own scores; the ranks meet ONCE, in the final gather
-            # (north_star: "the final gather of scores") -- a gather per step would couple the ranks step by step.
-            out_host[s][:T].copy_(scores, non_blocking=True)
-            if world > 1:
-                rank_scores[s].copy_(scores)
-        return out_host[s]
-
-    rank_scores = torch.empty(nsteps, T, dtype=torch.float32, device=dev) if world > 1 else None
-    gathered_host = torch.empty(world * a.steps * T, dtype=torch.float32).pin_memory() if world > 1 else None
+            # (north_star: "the final gather of scores") -- a gather per session would couple the ranks.
+            if timed:
+                k = q - a.warmup * S
+                out_host[k * T:(k + 1) * T].copy_(scores, non_blocking=True)
+                if world > 1:
+                    rank_scores[k].copy_(scores)
+        return scores
 
     def final_gather():
-        """All ranks' scores of the timed steps, gathered once on the communication stream and read by rank 0."""
+        """All ranks' scores of the timed sessions, gathered once on the communication stream and read by rank 0."""
         if world <= 1:
             return
         import torch.distributed as dist
         for st in streams:
             comm_stream.wait_stream(st)
         with torch.cuda.stream(comm_stream):
-            mine = rank_scores[a.warmup:].reshape(-1)
+            mine = rank_scores.reshape(-1)
             allsc = torch.empty(world * mine.numel(), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(allsc, mine)
             if rank == 0:
@@ -389,7 +515,7 @@ def main():
         torch.cuda.synchronize()
 
     # NVML is initialised (and queried once) before any timed region: its first calls take driver locks for
-    # milliseconds and would otherwise stall the launches of the first timed steps
+    # milliseconds and would otherwise stall the launches of the first timed sessions
     sampler = ClockSampler(local, 0.002 if world == 1 else 0.005)  # N ranks share the host cores: poll less often
     try:
         sampler._sample()
@@ -397,8 +523,8 @@ def main():
         pass
 
     def timed(fn, profile=False, finalize=None):
-        for s in range(a.warmup):
-            fn(s)
+        for q in range(a.warmup * S):
+            fn(q, False)
         barrier()
         if profile:
             torch.cuda.cudart().cudaProfilerStart()
@@ -406,11 +532,12 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         gc.collect()
         gc.disable()  # a generation-2 collection in the middle of the loop stalls the launches for 10+ ms
+        launches0 = L.ocn_launch_count()
         t0 = time.perf_counter()
         ev0.record()
         fork()
-        for s in range(a.warmup, nsteps):
-            fn(s)
+        for q in range(a.warmup * S, nsess):
+            fn(q, True)
         if finalize is not None:
             finalize()
         join()
@@ -420,6 +547,7 @@ def main():
         if profile:
             torch.cuda.cudart().cudaProfilerStop()
         wall = time.perf_counter() - t0
+        launches = L.ocn_launch_count() - launches0
         clocks = sampler.stop()
         ms = ev0.elapsed_time(ev1)
         if world > 1:
@@ -427,22 +555,23 @@ def main():
             t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1e3
-        return ms, wall, clocks
+        return ms, wall, clocks, launches
 
-    ms_dev, _, clocks = timed(step_device, a.profile_range)
-    ms_e2e_ev, wall_e2e, _ = timed(step_e2e, finalize=final_gather)
+    ms_dev, _, clocks, launches_dev = timed(session_device, a.profile_range)
+    sess_ms = [e0.elapsed_time(e1) for e0, e1 in sess_events]
+    ms_e2e_ev, wall_e2e, _, _ = timed(session_e2e, finalize=final_gather)
     ms_e2e = max(ms_e2e_ev, wall_e2e * 1e3)  # the D2H read ends after the last event: use the host clock too
 
     # roofline of the dominant kernel: CUDA events recorded by the library on the build's stream right
     # before / after k_cn_hub_count (indexed path) -- or around the whole build stage when the per-run
-    # table kernel k_cn_build is in use (--hub -1) -- fresh links each launch
-    L = ob._lib.lib()
-    build_ms, kern_ms, hub_ds = [], [], []
+    # table kernel k_cn_build is in use (--hub -1) -- fresh links each launch, over a sample of the timed sessions
+    build_ms, kern_ms, hub_ds, sample_q = [], [], [], []
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record(); k1.record()
     torch.cuda.synchronize()
-    for s in range(a.warmup, nsteps):
-        e = e_rank[:, s * T:(s + 1) * T]
+    stride = max(1, (nsess - a.warmup * S) // 24)
+    for q in range(a.warmup * S, nsess, stride):
+        e = e_rank[:, q * T:(q + 1) * T]
         sess = ob.CNSession(G, e, a.batch, a.order, a.hub)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         indexed = sess.hub_degree > 0
@@ -457,56 +586,79 @@ def main():
         build_ms.append(ev0.elapsed_time(ev1))
         kern_ms.append(k0.elapsed_time(k1) if indexed else build_ms[-1])
         hub_ds.append(sess.hub_degree)
+        sample_q.append(q)
     build_avg = sum(build_ms) / len(build_ms)
     kern_avg = sum(kern_ms) / len(kern_ms)
     indexed = hub_ds[-1] > 0
-    bb = [algorithmic_bytes(G, e_rank[:, s * T:(s + 1) * T], a.order, a.feat, a.batch, hub_ds[s - a.warmup])
-          for s in range(a.warmup, nsteps)]
+    bb = [algorithmic_bytes(G, e_rank[:, q * T:(q + 1) * T], a.order, a.feat, a.batch, hd) for q, hd in zip(sample_q, hub_ds)]
     build_bytes = sum(b[0] for b in bb) / len(bb)
-    step_bytes = sum(b[1] for b in bb) / len(bb)
     survey_bytes = sum(b[2] for b in bb) / len(bb)
     kern_bytes = (sum(b[3] for b in bb) / len(bb)) if indexed else build_bytes
     kern_name = "k_cn_hub_count" if indexed else "k_cn_build"
     peak, peak_src = peaks()
     achieved = kern_bytes / (kern_avg * 1e-3) / 1e9
-    traffic = None
+    # DRAM traffic and issue-slot use of that kernel from the committed ncu capture -- only if it was taken from the
+    # kernel source this library was built from
+    traffic, ncu_facts, traffic_note = None, {}, "profiles/traffic.json missing"
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get(kern_name + "_dram_bytes_per_launch")
+            tj = json.load(f)
+        if tj.get("kernel_source_sha") == kernel_source_sha():
+            traffic = tj.get(kern_name + "_dram_bytes_per_launch")
+            ncu_facts = tj.get(kern_name + "_ncu", {})
+            traffic_note = tj.get("source", "")
+        else:
+            traffic_note = (f"profiles/traffic.json was captured from kernel source {tj.get('kernel_source_sha')}, this "
+                            f"tree is {kernel_source_sha()}: not reported")
 
     if rank == 0:
-        links = world * T * a.steps
+        ms_session = ms_dev / (a.steps * S)
+        links = world * T * S * a.steps
         value = links / (ms_dev * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 walk counts / f32 features", "data": "synthetic", "config": workload_config(a, g),
             "clocks": clocks,
-            "e2e": {"value": links / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * T * world,
-                    "d2h_bytes_per_step": 4 * T * world, "ms_per_step": ms_e2e / a.steps,
-                    "final_gather_bytes": (4 * T * a.steps * world * world) if world > 1 else 0,
+            "timed_region_ms": ms_dev,
+            "session_ms": {"mean": ms_session, "p50": percentile(sess_ms, 0.5), "p95": percentile(sess_ms, 0.95),
+                           "max": max(sess_ms) if sess_ms else None, "n": len(sess_ms),
+                           "note": "per-session figures are event pairs on the work stream of rank 0 (plan excluded: it runs "
+                                   "a session ahead on its own stream)"},
+            "e2e": {"value": links / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * T * S * world,
+                    "d2h_bytes_per_step": 4 * T * S * world, "ms_per_step": ms_e2e / a.steps,
+                    "final_gather_bytes": (4 * T * S * a.steps * world * world) if world > 1 else 0,
                     "api": "CNLinkPredictor*.forward(h, adj, CNSession, ..., edges) -> scores.cpu()"},
-            # own kernels per device-resident step, counted in profiles/r01_launches_v26.txt (CUB scans / radix sorts
-            # not counted): 8 plan + 11 build (indexed path; the table path has k_cn_build + k_cn_colstat, plus
-            # k_cn_build_direct for orders <= 2) + 3 stats + aggregate + release
-            "gpu_launches": ((24 if indexed else (15 + (1 if a.order <= 2 else 0))) * a.steps),
-            "roofline": {"bound": "hbm", "kernel": kern_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            # launches of the library's own kernels inside the timed region of the device-resident leg, counted by the
+            # library (ocn_launch_count; the CUB scans / radix sorts it calls are not in the figure), this rank
+            "gpu_launches": int(launches_dev),
+            "gpu_launches_per_session": launches_dev / (a.steps * S),
+            "roofline": {"bound": "hbm" if not indexed else "issue",
+                         "bound_note": ("the contract's roofline is the HBM one (frac = algorithmic bytes / time / measured copy "
+                                        "bandwidth); ncu shows this kernel bound by instruction issue and L2 latency, not by "
+                                        "DRAM: see dram_frac and ncu below") if indexed else "",
+                         "kernel": kern_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         # the same launch at DRAM level (ncu bytes / live duration): far below the peak -- the kernel is
-                         # bound by issue slots and shared-memory counter updates, not by HBM
                          "dram_gbs": (traffic / (kern_avg * 1e-3) / 1e9) if traffic else None,
+                         "dram_frac": (traffic / (kern_avg * 1e-3) / 1e9 / peak) if traffic else None,
+                         "ncu": ncu_facts, "traffic_source": traffic_note,
                          "algorithmic_bytes_per_launch": kern_bytes, "kernel_ms": kern_avg,
-                         "kernel_share_of_step": kern_avg / (ms_dev / a.steps),
-                         "build_stage_ms": build_avg, "hub_degree": hub_ds[-1],
-                         "whole_step_survey_gbs": survey_bytes / (ms_dev / a.steps * 1e-3) / 1e9,
-                         "whole_step_survey_frac": survey_bytes / (ms_dev / a.steps * 1e-3) / 1e9 / peak,
+                         "kernel_share_of_session": kern_avg / ms_session,
+                         "build_stage_ms": build_avg, "hub_degree": hub_ds[-1], "sessions_sampled": len(kern_ms),
+                         "whole_session_survey_gbs": survey_bytes / (ms_session * 1e-3) / 1e9,
+                         "whole_session_survey_frac": survey_bytes / (ms_session * 1e-3) / 1e9 / peak,
                          "note": "achieved = SURVEY 8(d) per-link index bytes of the rows this kernel covers "
                                  "(8 + 4 d(m) for every (link, m in N(dst)) with d(m) >= hub_degree) / its duration; the "
-                                 "kernel streams each such row once per stream, so the figure can exceed the DRAM traffic"},
+                                 "kernel streams each such row once per session, so the figure exceeds the DRAM traffic"},
         }
         if world > 1:
             line["dealing"] = dealing
+        if world == 1 and not a.no_secondary:
+            try:
+                line["secondary"] = secondary(a, ob, synth, G, g, x, sampler, peak, dev)
+            except Exception as ex:  # the headline line is never lost to a secondary measurement
+                line["secondary"] = {"error": f"{type(ex).__name__}: {ex}"}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a, g, g.rowptr.cpu(), g.col.cpu())
         emit(line)

@@ -54,6 +54,8 @@ int ocn_device_sm_count(void);
                                      (measured slower than the folded 64-bit sets on the bench workload; implied by WALKER = 1) */
 #define OCN_OPT_GROUPED_OFF 6     /* 1: never use the run-grouped statistics / aggregation kernels (cn_grouped.cu) */
 #define OCN_OPT_COUNT 16
+/* launches of the library's own kernels since the process started (CUB scans / sorts it calls are not counted) */
+long long ocn_launch_count(void);
 int ocn_set_option(int key, int64_t value);
 int64_t ocn_get_option(int key);
 

@@ -40,6 +40,7 @@ _SIGS = {
     "ocn_cn_hub_scratch_reset": (c_int, [_P]),
     "ocn_set_option": (c_int, [c_int, c_int64]),
     "ocn_get_option": (c_int64, [c_int]),
+    "ocn_launch_count": (ctypes.c_longlong, []),
     "ocn_cn_stats": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, c_int,
                              _P, _P, _P, _P, _P, _P]),
     "ocn_cn_aggregate": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P,

@@ -28,7 +28,15 @@ int fail(int code, const char* fmt, ...);
                                __FILE__, __LINE__);                                         \
     } while (0)
 
-#define OCN_LAUNCH_CHECK() OCN_CUDA(cudaGetLastError())
+// every launch of one of the library's own kernels is followed by this: the error check, and the count bench.py reports
+// as gpu_launches (ocn_launch_count)
+void count_launch();
+long long launch_count();
+#define OCN_LAUNCH_CHECK()            \
+    do {                              \
+        ::ocn::count_launch();        \
+        OCN_CUDA(cudaGetLastError()); \
+    } while (0)
 
 int sm_count();
 int64_t option(int key, int64_t dflt);  // ocn_set_option value, or dflt when unset (0)

@@ -1,6 +1,8 @@
 // ABI basics, graph validation and the generic two-matrix row intersection.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace ocn {
@@ -19,6 +21,10 @@ int fail(int code, const char* fmt, ...) {
     last_error() = buf;
     return code;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 static int64_t g_options[OCN_OPT_COUNT] = {0};
 int64_t option(int key, int64_t dflt) {
@@ -158,6 +164,7 @@ const char* ocn_last_error(void) { return last_error().c_str(); }
 int ocn_device_sm_count(void) { return sm_count(); }
 int ocn_set_option(int key, int64_t value) { return set_option(key, value); }
 int64_t ocn_get_option(int key) { return option(key, 0); }
+long long ocn_launch_count(void) { return launch_count(); }
 
 int ocn_graph_validate(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t nnz, int32_t* out_flags,
                        void* stream) {

@@ -34,16 +34,16 @@ def mix64(x: torch.Tensor) -> torch.Tensor:
     return z ^ _lsr(z, 31)
 
 
-def hash_u01(n: int, seed: int, stream: int, device) -> torch.Tensor:
-    """n uniform doubles in [0,1), element t = f(seed, stream, t)."""
-    idx = torch.arange(n, dtype=torch.int64, device=device)
+def hash_u01(n: int, seed: int, stream: int, device, start: int = 0) -> torch.Tensor:
+    """n uniform doubles in [0,1), element t = f(seed, stream, start + t)."""
+    idx = torch.arange(start, start + n, dtype=torch.int64, device=device)
     z = mix64(idx + mix64(torch.tensor(seed * 1000003 + stream, dtype=torch.int64, device=device)))
     return _lsr(z, 11).to(torch.float64) * (2.0 ** -53)
 
 
-def hash_randint(n: int, high: int, seed: int, stream: int, device) -> torch.Tensor:
-    """n integers uniform in [0, high)."""
-    u = hash_u01(n, seed, stream, device)
+def hash_randint(n: int, high: int, seed: int, stream: int, device, start: int = 0) -> torch.Tensor:
+    """n integers uniform in [0, high): elements start .. start + n - 1 of the sequence."""
+    u = hash_u01(n, seed, stream, device, start)
     return (u * high).to(torch.int64).clamp_(max=high - 1)
 
 
@@ -138,6 +138,19 @@ class SynthGraph:
     def features(self, width: Optional[int] = None, device=None) -> torch.Tensor:
         device = device if device is not None else self.col.device
         return hash_normal((self.n, width or self.hidden), self.seed, 101, device)
+
+    def stream_links(self, start: int, num: int, device=None) -> torch.Tensor:
+        """Links start .. start + num - 1 of the 'stream' kind of ``query_edges`` without generating the ones before
+        them (element t of the stream depends on t only)."""
+        device = device if device is not None else self.col.device
+        rp = self.rowptr.to(device)
+        deg = rp[1:] - rp[:-1]
+        cand = torch.nonzero(deg > 0).flatten()
+        s0, s1 = start // 1000, (start + num + 999) // 1000
+        srcs = cand[hash_randint(s1 - s0, cand.numel(), self.seed, 205, device, start=s0)]
+        src = srcs.repeat_interleave(1000)[start - s0 * 1000:start - s0 * 1000 + num]
+        dst = hash_randint(num, self.n, self.seed, 204, device, start=start)
+        return torch.stack((src, dst))
 
     def query_edges(self, num: int, kind: str = "mixed", device=None) -> torch.Tensor:
         """[2,num] int64 target links: 'pos' = edges of the graph, 'neg' = uniform pairs,
