@@ -101,30 +101,43 @@ int ocn_graph_mask_fill(const int64_t* rowptr, const int32_t* col, const int32_t
                         int32_t* dec, const void* scratch /* as left by count */,
                         int32_t* out_col, int32_t* out_mult, void* stream);
 
+/* DropAdj (model.py:211-229: mask = rand_like(col) > dp; torch_sparse.masked_select_nnz(adj, mask); value * 1/(1-dp)),
+ * applied to the GNN's adjacency in every layer of a training forward (model.py:312): the entries with keep[e] != 0
+ * move, in order, into a new CSR whose values are (val or 1) * scale.  The mask comes from the caller's RNG (torch), so
+ * that a seeded run drops the same entries as the reference.  count: kept entries per row; the caller scans them into
+ * out_rowptr and calls fill. */
+int ocn_graph_select_count(const int64_t* rowptr, const uint8_t* keep, int64_t n, int64_t* out_counts, void* stream);
+int ocn_graph_select_fill(const int64_t* rowptr, const int32_t* col, const float* val /* NULL = ones */,
+                          const uint8_t* keep, int64_t n, float scale, const int64_t* out_rowptr, int32_t* out_col,
+                          float* out_val /* NULL = structure only */, void* stream);
+
 /* ---- piece 1: generic per-target-edge row intersection ----------------------------------
  * adjoverlap(adj1, adj2, tarei) with calresadj=False (utils.py:248-285 -> spmoverlap_
  * utils.py:163-183): out row b = adj1[src[b]] (cap) adj2[dst[b]], columns ascending, value 1.
  * adj1/adj2 may be different matrices with the same column space (e.g. A and an explicit A^2,
  * NeighborOverlap_large.py:78-79). */
-int ocn_rows_intersect_count(const int64_t* rowptr1, const int32_t* col1,
-                             const int64_t* rowptr2, const int32_t* col2,
+int ocn_rows_intersect_count(const int64_t* rowptr1, const int32_t* col1, int64_t n1 /* rows of matrix 1 */,
+                             const int64_t* rowptr2, const int32_t* col2, int64_t n2 /* rows of matrix 2 */,
                              const int64_t* src, const int64_t* dst, int64_t num_edges,
-                             int64_t* out_counts, void* stream);
+                             int64_t* out_counts /* [num_edges + 1], the last word ZERO on entry: it receives the number
+                                                    of links with src outside [0, n1) or dst outside [0, n2) -- the
+                                                    reference raises IndexError there; their rows stay empty */,
+                             void* stream);
 /* out_rowptr = exclusive scan of out_counts (int64[num_edges+1]), computed by the caller. */
-int ocn_rows_intersect_fill(const int64_t* rowptr1, const int32_t* col1,
-                            const int64_t* rowptr2, const int32_t* col2,
+int ocn_rows_intersect_fill(const int64_t* rowptr1, const int32_t* col1, int64_t n1,
+                            const int64_t* rowptr2, const int32_t* col2, int64_t n2,
                             const int64_t* src, const int64_t* dst, int64_t num_edges,
                             const int64_t* out_rowptr, int64_t* out_col, void* stream);
 
 /* calresadj=True branch of adjoverlap (utils.py:260-274 -> spmoverlap_notoverlap_ utils.py:210-244), used by the
  * completion predictors: out row b = adj1[src[b]] \ adj2[dst[b]] (columns ascending).  The second residual,
  * adj2[dst] \ adj1[src], is the same call with the matrices and link ends swapped. */
-int ocn_rows_difference_count(const int64_t* rowptr1, const int32_t* col1,
-                              const int64_t* rowptr2, const int32_t* col2,
+int ocn_rows_difference_count(const int64_t* rowptr1, const int32_t* col1, int64_t n1,
+                              const int64_t* rowptr2, const int32_t* col2, int64_t n2,
                               const int64_t* src, const int64_t* dst, int64_t num_edges,
                               int64_t* out_counts, void* stream);
-int ocn_rows_difference_fill(const int64_t* rowptr1, const int32_t* col1,
-                             const int64_t* rowptr2, const int32_t* col2,
+int ocn_rows_difference_fill(const int64_t* rowptr1, const int32_t* col1, int64_t n1,
+                             const int64_t* rowptr2, const int32_t* col2, int64_t n2,
                              const int64_t* src, const int64_t* dst, int64_t num_edges,
                              const int64_t* out_rowptr, int64_t* out_col, void* stream);
 
@@ -158,6 +171,7 @@ int ocn_rows_difference_fill(const int64_t* rowptr1, const int32_t* col1,
 #define OCN_PLAN_HUB_PAIRS 9     /* (hub row, link) pairs of the stream */
 #define OCN_PLAN_HUB_ENTRIES 10  /* (key, run, position) entries of the stream */
 #define OCN_PLAN_HUB_POSITIONS 11 /* sum over runs of deg(src) */
+#define OCN_PLAN_BAD_LINKS 17    /* links with an endpoint outside [0, n): the plan stops, the caller must not build */
 #define OCN_PLAN_WIDE_LINKS 16   /* links whose source has more than 64 neighbours (they stay with the per-link kernels) */
 #define OCN_PLAN_WORDS 24
 

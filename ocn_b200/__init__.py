@@ -7,7 +7,7 @@ from . import synth  # noqa: F401
 from .graph import Graph  # noqa: F401
 from .cn import (CNSession, SparseRows, adjoverlap, cn_aggregate_eval, get_cn, get_cn1_cn2,  # noqa: F401
                  reserve_stream_pool)
-from .sparse_ops import (gcn_norm, gcnconv_propagate, pure_conv, pure_conv3_gcn, sparse_tensor_multiply,  # noqa: F401
+from .sparse_ops import (drop_adj, gcn_norm, gcnconv_propagate, pure_conv, pure_conv3_gcn, sparse_tensor_multiply,  # noqa: F401
                          spgemm_a2, spmm, spmm_add, spmm_max, spmm_mean)
 from . import ops  # noqa: F401  (registers torch.ops.ocn.*)
 from . import dist, metrics  # noqa: F401
@@ -16,7 +16,7 @@ from .predictor import (CNLinkPredictor3hopCNs, CNLinkPredictorbaselearn, CNLink
 
 __all__ = [
     "Graph", "CNSession", "SparseRows", "adjoverlap", "cn_aggregate_eval", "get_cn", "get_cn1_cn2",
-    "gcn_norm", "gcnconv_propagate", "pure_conv", "pure_conv3_gcn", "sparse_tensor_multiply", "spgemm_a2",
+    "drop_adj", "gcn_norm", "gcnconv_propagate", "pure_conv", "pure_conv3_gcn", "sparse_tensor_multiply", "spgemm_a2",
     "spmm", "spmm_add", "spmm_max", "spmm_mean", "CNLinkPredictorOringin", "CNLinkPredictor3hopCNs",
     "CNLinkPredictorbaselearn", "predictor_dict", "synth", "reserve_stream_pool", "metrics", "dist",
 ]

@@ -25,10 +25,12 @@ _SIGS = {
     "ocn_graph_mask_bytes": (c_size_t, [c_int64, c_int64]),
     "ocn_graph_mask_count": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int, _P, _P, c_size_t, _P, _P, _P]),
     "ocn_graph_mask_fill": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P]),
-    "ocn_rows_intersect_count": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, _P, _P]),
-    "ocn_rows_intersect_fill": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P]),
-    "ocn_rows_difference_count": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, _P, _P]),
-    "ocn_rows_difference_fill": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P]),
+    "ocn_graph_select_count": (c_int, [_P, _P, c_int64, _P, _P]),
+    "ocn_graph_select_fill": (c_int, [_P, _P, _P, _P, c_int64, c_float, _P, _P, _P, _P]),
+    "ocn_rows_intersect_count": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, c_int64, _P, _P]),
+    "ocn_rows_intersect_fill": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, c_int64, _P, _P, _P]),
+    "ocn_rows_difference_count": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, c_int64, _P, _P]),
+    "ocn_rows_difference_fill": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, c_int64, _P, _P, _P]),
     "ocn_cn_plan_bytes": (c_size_t, [c_int64]),
     "ocn_cn_colstat_bytes": (c_size_t, [c_int64]),
     "ocn_cn_record_bytes": (c_size_t, []),

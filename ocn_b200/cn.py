@@ -25,6 +25,7 @@ from .graph import Graph, _require_cuda
 
 PLAN_WORDS = 24
 PLAN_HUB_DEGREE = 8  # include/ocn_b200.h OCN_PLAN_HUB_DEGREE
+PLAN_BAD_LINKS = 17  # OCN_PLAN_BAD_LINKS
 COLSTAT_BUDGET_BYTES = 4 << 30  # per-wave cap for the per-batch column statistics
 HUB_WORKSPACE_FLOOR = 512 << 20  # first size of the per-stream scratch of the indexed order-3 path
 RECORDS_BUCKET = 16 << 20        # record buffers are sized in these steps, so that the caching allocator re-serves them
@@ -92,15 +93,18 @@ def _rows_setop(op: str, adj1: Graph, adj2: Graph, src: Tensor, dst: Tensor) -> 
     count_fn, fill_fn = getattr(L, f"ocn_rows_{op}_count"), getattr(L, f"ocn_rows_{op}_fill")
     with torch.cuda.device(dev):
         st = _stream(dev)
-        _lib.check(count_fn(_lib.ptr(adj1.rowptr), _lib.ptr(adj1.col), _lib.ptr(adj2.rowptr), _lib.ptr(adj2.col),
-                            _lib.ptr(src), _lib.ptr(dst), B, _lib.ptr(counts), st), f"ocn_rows_{op}_count")
+        _lib.check(count_fn(_lib.ptr(adj1.rowptr), _lib.ptr(adj1.col), adj1.n, _lib.ptr(adj2.rowptr), _lib.ptr(adj2.col),
+                            adj2.n, _lib.ptr(src), _lib.ptr(dst), B, _lib.ptr(counts), st), f"ocn_rows_{op}_count")
         rowptr = torch.zeros(B + 1, dtype=torch.int64, device=dev)
         torch.cumsum(counts[:B], 0, out=rowptr[1:])
-        nnz = int(rowptr[-1].item())
+        nnz, bad = torch.stack((rowptr[-1], counts[B])).tolist()  # one read-back: output size + out-of-range endpoints
+        if bad:
+            raise IndexError(f"{bad} target links have an endpoint outside the matrices' rows "
+                             f"([0, {adj1.n}) for the first, [0, {adj2.n}) for the second end)")
         col = torch.empty(nnz, dtype=torch.int64, device=dev)
         if nnz:
-            _lib.check(fill_fn(_lib.ptr(adj1.rowptr), _lib.ptr(adj1.col), _lib.ptr(adj2.rowptr), _lib.ptr(adj2.col),
-                               _lib.ptr(src), _lib.ptr(dst), B, _lib.ptr(rowptr), _lib.ptr(col), st),
+            _lib.check(fill_fn(_lib.ptr(adj1.rowptr), _lib.ptr(adj1.col), adj1.n, _lib.ptr(adj2.rowptr), _lib.ptr(adj2.col),
+                               adj2.n, _lib.ptr(src), _lib.ptr(dst), B, _lib.ptr(rowptr), _lib.ptr(col), st),
                        f"ocn_rows_{op}_fill")
     return SparseRows(rowptr, col, torch.ones(nnz, dtype=torch.float32, device=dev), (B, adj1.n_cols))
 
@@ -148,6 +152,8 @@ class CNSession:
             main.wait_stream(plan_stream)
             for t in (self.plan_scratch, self.plan, self.src, self.dst):
                 t.record_stream(main)
+        if host[PLAN_BAD_LINKS]:
+            raise IndexError(f"{host[PLAN_BAD_LINKS]} target links have an endpoint outside [0, {graph.n})")
         self.num_records, self.num_runs, self.num_units = host[0], host[1], host[2]
         self.plan_host = (ctypes.c_int64 * PLAN_WORDS)(*host)
         self.hub_degree = host[PLAN_HUB_DEGREE]
@@ -166,8 +172,13 @@ class CNSession:
         g = self.g
         if order > self.plan_order:
             raise ValueError(f"the session was planned for order {self.plan_order}; cannot build order {order}")
-        if with_stats and self.colstat is None:
+        if with_stats and self.colstat is not None and not self._released and self.order > 0:
+            # a second build (another order or weighting) would add its counts on top of the first one's: hand the
+            # statistics back (release re-zeroes exactly the touched entries) and start from a zeroed buffer
+            self.release()
+        if with_stats and (self.colstat is None or self._released):
             self.colstat = _borrow_colstat(g, self.nb * self.L.ocn_cn_colstat_bytes(g.n))
+            self._released = False
         hub_scratch = node_scratch = None
         if self.hub_bytes > 0 and order >= 3:
             hub_scratch, node_scratch = _hub_workspace(g, self.hub_bytes)
@@ -216,6 +227,10 @@ class CNSession:
         return xcn1, xcn2, xcn3, xij
 
     def aggregate_bwd(self, x: Tensor, variant: int, fill: float, ip: Tensor, g1, g2, g3, gij, grad_x: Tensor):
+        if self._released:
+            raise RuntimeError("the column statistics of this session were released (a backward through it has run, or "
+                               "release() was called): the weights cannot be rebuilt -- build the session again, as "
+                               "autograd asks for retain_graph on a second backward")
         g = self.g
         c = lambda t: None if t is None else t.contiguous()
         g1, g2, g3, gij = c(g1), c(g2), c(g3), c(gij)
@@ -263,7 +278,7 @@ class CNSession:
                                              self.batch_size, _lib.ptr(self.plan_scratch), _lib.ptr(self.records),
                                              _lib.ptr(self.colstat), self.plan_host, _stream(self.dev)), "ocn_cn_release")
         self._released = True
-        _return_colstat(self.g, self.colstat)
+        _return_colstat(self.g, self.colstat)  # (the reference is kept for inspection; _released guards its further use)
 
 
 def reserve_stream_pool(nbytes: int = 4 << 30, device=None) -> None:

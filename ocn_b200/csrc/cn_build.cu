@@ -680,6 +680,9 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
     OCN_CHECK_ARG(order >= 1 && order <= 3, "ocn_cn_build: order must be 1, 2 or 3 (got %d)", order);
     OCN_CHECK_ARG(n > 0 && num_edges > 0 && batch_size > 0, "ocn_cn_build: sizes must be positive");
     OCN_CHECK_ARG(records || records_capacity == 0, "ocn_cn_build: records is null");
+    OCN_CHECK_ARG(plan_host == nullptr || plan_host[OCN_PLAN_BAD_LINKS] == 0,
+                  "ocn_cn_build: the plan found %lld links with an endpoint outside [0, n)",
+                  (long long)(plan_host ? plan_host[OCN_PLAN_BAD_LINKS] : 0));
     OCN_CHECK_ARG(n < (int64_t(1) << kTagShift), "ocn_cn_build: at most 2^27 nodes (queue tag width)");
     // row starts are kept as 32-bit offsets in shared memory; rowptr[n] < 2^32 is the caller's contract (checked by ocn_graph_validate users)
     static_assert(kEdgeSub == 32, "one lane per link slot");

@@ -45,7 +45,8 @@ PlanLayout plan_layout(int64_t T) {
     return L;
 }
 
-__global__ void k_plan_edges(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ src, int64_t T,
+__global__ void k_plan_edges(const int64_t* __restrict__ rowptr, int64_t n, const int64_t* __restrict__ src,
+                             const int64_t* __restrict__ dst, int64_t T,
                              int64_t batch_size, int64_t* __restrict__ rec_off, int32_t* __restrict__ flag,
                              int64_t* __restrict__ plan) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,6 +57,11 @@ __global__ void k_plan_edges(const int64_t* __restrict__ rowptr, const int64_t* 
         return;
     }
     int64_t i = src[t];
+    // the reference raises IndexError for a link outside the graph; here such links are counted (the count rides on the
+    // plan's read-back) and every later kernel of the plan returns at once, so nothing indexes rowptr with them
+    const bool bad = (uint64_t)i >= (uint64_t)n || (uint64_t)dst[t] >= (uint64_t)n;
+    if (bad) atomicAdd(reinterpret_cast<unsigned long long*>(plan + OCN_PLAN_BAD_LINKS), 1ull);
+    if ((uint64_t)i >= (uint64_t)n) i = 0;
     const int64_t d = rowptr[i + 1] - rowptr[i];
     rec_off[t] = d;
     flag[t] = (t == 0 || src[t - 1] != i) ? 1 : 0;  // runs ignore batch boundaries (see the header)
@@ -71,7 +77,7 @@ __global__ void k_plan_runs(const int64_t* __restrict__ rowptr, const int64_t* _
                             int64_t batch_size, const int32_t* __restrict__ run_incl, int32_t* __restrict__ run_start,
                             int64_t* __restrict__ plan) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
+    if (t >= T || plan[OCN_PLAN_BAD_LINKS] != 0) return;
     bool first = (t == 0) || src[t - 1] != src[t];
     int32_t r = run_incl[t] - 1;
     if (first) {
@@ -100,6 +106,7 @@ __global__ void k_plan_cost(const int64_t* __restrict__ rowptr, const int32_t* _
                             int32_t* __restrict__ hub_cnt, int32_t* __restrict__ chunk_cnt, int32_t* __restrict__ long_list,
                             int64_t* __restrict__ plan) {
     __shared__ unsigned long long s_cost;  // one global reduction per CTA, not one per link on a single address
+    if (plan[OCN_PLAN_BAD_LINKS] != 0) return;
     if (threadIdx.x == 0) s_cost = 0ull;
     __syncthreads();
     const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -141,6 +148,7 @@ k_plan_cost_long(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
                  int64_t* __restrict__ plan) {
     __shared__ unsigned long long s_w;
     __shared__ int s_h;
+    if (plan[OCN_PLAN_BAD_LINKS] != 0) return;
     const int64_t n_long = plan[OCN_PLAN_LONG_COUNT];
     const int64_t hub_d = plan[OCN_PLAN_HUB_DEGREE];
     for (int64_t i = blockIdx.x; i < n_long; i += gridDim.x) {
@@ -186,7 +194,7 @@ __global__ void k_plan_units(const int64_t* __restrict__ rowptr, const int32_t* 
                              int64_t* __restrict__ run_pos_light, int64_t* __restrict__ run_pos_heavy) {
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (r > T + 1) return;
+    if (r > T + 1 || plan[OCN_PLAN_BAD_LINKS] != 0) return;
     const int64_t n_runs = plan[OCN_PLAN_NUM_RUNS];
     int64_t u = 0, npos = 0;
     // orders <= 2 on short runs go to the table-free kernel (k_plan_finish: OCN_PLAN_USE_DIRECT): no table units to plan
@@ -314,7 +322,7 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
         if (hub_degree < 32) hub_degree = 32;
     }
     OCN_CUDA(cudaMemsetAsync(rec_off + T + 1, 0, sizeof(int64_t), st));
-    k_plan_edges<<<blocks, threads, 0, st>>>(rowptr, src, T, batch_size, rec_off, run_id, out_plan);
+    k_plan_edges<<<blocks, threads, 0, st>>>(rowptr, n, src, dst, T, batch_size, rec_off, run_id, out_plan);
     OCN_LAUNCH_CHECK();
     OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, rec_off, rec_off, (int)(T + 1), st));
     OCN_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, run_id, run_id, (int)(T + 1), st));

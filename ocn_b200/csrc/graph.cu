@@ -80,8 +80,8 @@ __global__ void k_validate(const int64_t* __restrict__ rowptr, const int32_t* __
 // searches its column in the longer row; matches are emitted in ascending column order with a
 // ballot (both rows are ascending, so walking either one keeps the output ascending).
 template <bool FILL>
-__global__ void k_rows_intersect(const int64_t* __restrict__ rowptr1, const int32_t* __restrict__ col1,
-                                 const int64_t* __restrict__ rowptr2, const int32_t* __restrict__ col2,
+__global__ void k_rows_intersect(const int64_t* __restrict__ rowptr1, const int32_t* __restrict__ col1, int64_t n1,
+                                 const int64_t* __restrict__ rowptr2, const int32_t* __restrict__ col2, int64_t n2,
                                  const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                  int64_t num_edges, int64_t* __restrict__ out_counts,
                                  const int64_t* __restrict__ out_rowptr, int64_t* __restrict__ out_col) {
@@ -90,6 +90,10 @@ __global__ void k_rows_intersect(const int64_t* __restrict__ rowptr1, const int3
     int lane = lane_id();
     for (int64_t t = warp; t < num_edges; t += nwarps) {
         int64_t i = src[t], j = dst[t];
+        if ((uint64_t)i >= (uint64_t)n1 || (uint64_t)j >= (uint64_t)n2) {  // reference: IndexError; here: counted, row left empty
+            if (!FILL && lane == 0) { out_counts[t] = 0; atomicAdd(reinterpret_cast<unsigned long long*>(out_counts + num_edges), 1ull); }
+            continue;
+        }
         int64_t s1 = rowptr1[i], l1 = rowptr1[i + 1] - s1;
         int64_t s2 = rowptr2[j], l2 = rowptr2[j + 1] - s2;
         const int32_t* a = col1 + s1;
@@ -121,8 +125,8 @@ __global__ void k_rows_intersect(const int64_t* __restrict__ rowptr1, const int3
 // per link walks row 1 and binary-searches row 2 (the other difference is the same call with the
 // matrices and the link ends swapped).
 template <bool FILL>
-__global__ void k_rows_difference(const int64_t* __restrict__ rowptr1, const int32_t* __restrict__ col1,
-                                  const int64_t* __restrict__ rowptr2, const int32_t* __restrict__ col2,
+__global__ void k_rows_difference(const int64_t* __restrict__ rowptr1, const int32_t* __restrict__ col1, int64_t n1,
+                                  const int64_t* __restrict__ rowptr2, const int32_t* __restrict__ col2, int64_t n2,
                                   const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                   int64_t num_edges, int64_t* __restrict__ out_counts,
                                   const int64_t* __restrict__ out_rowptr, int64_t* __restrict__ out_col) {
@@ -131,6 +135,10 @@ __global__ void k_rows_difference(const int64_t* __restrict__ rowptr1, const int
     int lane = lane_id();
     for (int64_t t = warp; t < num_edges; t += nwarps) {
         const int64_t i = src[t], j = dst[t];
+        if ((uint64_t)i >= (uint64_t)n1 || (uint64_t)j >= (uint64_t)n2) {
+            if (!FILL && lane == 0) { out_counts[t] = 0; atomicAdd(reinterpret_cast<unsigned long long*>(out_counts + num_edges), 1ull); }
+            continue;
+        }
         const int64_t s1 = rowptr1[i], l1 = rowptr1[i + 1] - s1;
         const int64_t s2 = rowptr2[j], l2 = rowptr2[j + 1] - s2;
         const int32_t* a = col1 + s1;
@@ -153,6 +161,43 @@ __global__ void k_rows_difference(const int64_t* __restrict__ rowptr1, const int
     }
 }
 
+// ---- per-entry selection (DropAdj, model.py:219-229: torch_sparse.masked_select_nnz + value * ratio) -------------
+// one warp per row: kept entries counted / compacted by ballot, order preserved
+__global__ void k_select_count(const int64_t* __restrict__ rowptr, const uint8_t* __restrict__ keep, int64_t n,
+                               int64_t* __restrict__ out_counts) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = lane_id();
+    if (warp >= n) return;
+    const int64_t s = rowptr[warp], e = rowptr[warp + 1];
+    int64_t c = 0;
+    for (int64_t o = s; o < e; o += 32) {
+        const bool k = (o + lane < e) && keep[o + lane] != 0;
+        c += __popc(__ballot_sync(0xffffffffu, k));
+    }
+    if (lane == 0) out_counts[warp] = c;
+}
+
+__global__ void k_select_fill(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                              const float* __restrict__ val, const uint8_t* __restrict__ keep, int64_t n, float scale,
+                              const int64_t* __restrict__ out_rowptr, int32_t* __restrict__ out_col,
+                              float* __restrict__ out_val) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = lane_id();
+    if (warp >= n) return;
+    const int64_t s = rowptr[warp], e = rowptr[warp + 1];
+    int64_t w = out_rowptr[warp];
+    for (int64_t o = s; o < e; o += 32) {
+        const bool k = (o + lane < e) && keep[o + lane] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, k);
+        if (k) {
+            const int64_t q = w + __popc(m & ((1u << lane) - 1u));
+            out_col[q] = col[o + lane];
+            if (out_val) out_val[q] = (val ? val[o + lane] : 1.0f) * scale;
+        }
+        w += __popc(m);
+    }
+}
+
 }  // namespace ocn
 
 using namespace ocn;
@@ -165,6 +210,24 @@ int ocn_device_sm_count(void) { return sm_count(); }
 int ocn_set_option(int key, int64_t value) { return set_option(key, value); }
 int64_t ocn_get_option(int key) { return option(key, 0); }
 long long ocn_launch_count(void) { return launch_count(); }
+
+int ocn_graph_select_count(const int64_t* rowptr, const uint8_t* keep, int64_t n, int64_t* out_counts, void* stream) {
+    OCN_CHECK_ARG(rowptr && keep && out_counts, "ocn_graph_select_count: null pointer");
+    OCN_CHECK_ARG(n > 0, "ocn_graph_select_count: n must be positive");
+    k_select_count<<<(int)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rowptr, keep, n, out_counts);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
+int ocn_graph_select_fill(const int64_t* rowptr, const int32_t* col, const float* val, const uint8_t* keep, int64_t n,
+                          float scale, const int64_t* out_rowptr, int32_t* out_col, float* out_val, void* stream) {
+    OCN_CHECK_ARG(rowptr && col && keep && out_rowptr && out_col, "ocn_graph_select_fill: null pointer");
+    OCN_CHECK_ARG(n > 0, "ocn_graph_select_fill: n must be positive");
+    k_select_fill<<<(int)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rowptr, col, val, keep, n, scale, out_rowptr,
+                                                                                  out_col, out_val);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
 
 int ocn_graph_validate(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t nnz, int32_t* out_flags,
                        void* stream) {
@@ -179,57 +242,57 @@ int ocn_graph_validate(const int64_t* rowptr, const int32_t* col, int64_t n, int
     return OCN_OK;
 }
 
-int ocn_rows_intersect_count(const int64_t* rowptr1, const int32_t* col1, const int64_t* rowptr2,
-                             const int32_t* col2, const int64_t* src, const int64_t* dst, int64_t num_edges,
+int ocn_rows_intersect_count(const int64_t* rowptr1, const int32_t* col1, int64_t n1, const int64_t* rowptr2,
+                             const int32_t* col2, int64_t n2, const int64_t* src, const int64_t* dst, int64_t num_edges,
                              int64_t* out_counts, void* stream) {
     OCN_CHECK_ARG(rowptr1 && rowptr2 && num_edges >= 0, "ocn_rows_intersect_count: bad arguments");
     if (num_edges == 0) return OCN_OK;
     OCN_CHECK_ARG(src && dst && out_counts, "ocn_rows_intersect_count: null edge/out pointer");
     int64_t want = (num_edges + 7) / 8;
     int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
-    k_rows_intersect<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr1, col1, rowptr2, col2, src, dst,
+    k_rows_intersect<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr1, col1, n1, rowptr2, col2, n2, src, dst,
                                                                        num_edges, out_counts, nullptr, nullptr);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
 }
 
-int ocn_rows_intersect_fill(const int64_t* rowptr1, const int32_t* col1, const int64_t* rowptr2,
-                            const int32_t* col2, const int64_t* src, const int64_t* dst, int64_t num_edges,
+int ocn_rows_intersect_fill(const int64_t* rowptr1, const int32_t* col1, int64_t n1, const int64_t* rowptr2,
+                            const int32_t* col2, int64_t n2, const int64_t* src, const int64_t* dst, int64_t num_edges,
                             const int64_t* out_rowptr, int64_t* out_col, void* stream) {
     OCN_CHECK_ARG(rowptr1 && rowptr2 && num_edges >= 0, "ocn_rows_intersect_fill: bad arguments");
     if (num_edges == 0) return OCN_OK;
     OCN_CHECK_ARG(src && dst && out_rowptr, "ocn_rows_intersect_fill: null edge/out pointer");
     int64_t want = (num_edges + 7) / 8;
     int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
-    k_rows_intersect<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr1, col1, rowptr2, col2, src, dst,
+    k_rows_intersect<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr1, col1, n1, rowptr2, col2, n2, src, dst,
                                                                       num_edges, nullptr, out_rowptr, out_col);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
 }
 
-int ocn_rows_difference_count(const int64_t* rowptr1, const int32_t* col1, const int64_t* rowptr2,
-                              const int32_t* col2, const int64_t* src, const int64_t* dst, int64_t num_edges,
+int ocn_rows_difference_count(const int64_t* rowptr1, const int32_t* col1, int64_t n1, const int64_t* rowptr2,
+                              const int32_t* col2, int64_t n2, const int64_t* src, const int64_t* dst, int64_t num_edges,
                               int64_t* out_counts, void* stream) {
     OCN_CHECK_ARG(rowptr1 && rowptr2 && num_edges >= 0, "ocn_rows_difference_count: bad arguments");
     if (num_edges == 0) return OCN_OK;
     OCN_CHECK_ARG(src && dst && out_counts, "ocn_rows_difference_count: null edge/out pointer");
     int64_t want = (num_edges + 7) / 8;
     int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
-    k_rows_difference<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr1, col1, rowptr2, col2, src, dst,
+    k_rows_difference<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr1, col1, n1, rowptr2, col2, n2, src, dst,
                                                                         num_edges, out_counts, nullptr, nullptr);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
 }
 
-int ocn_rows_difference_fill(const int64_t* rowptr1, const int32_t* col1, const int64_t* rowptr2,
-                             const int32_t* col2, const int64_t* src, const int64_t* dst, int64_t num_edges,
+int ocn_rows_difference_fill(const int64_t* rowptr1, const int32_t* col1, int64_t n1, const int64_t* rowptr2,
+                             const int32_t* col2, int64_t n2, const int64_t* src, const int64_t* dst, int64_t num_edges,
                              const int64_t* out_rowptr, int64_t* out_col, void* stream) {
     OCN_CHECK_ARG(rowptr1 && rowptr2 && num_edges >= 0, "ocn_rows_difference_fill: bad arguments");
     if (num_edges == 0) return OCN_OK;
     OCN_CHECK_ARG(src && dst && out_rowptr, "ocn_rows_difference_fill: null edge/out pointer");
     int64_t want = (num_edges + 7) / 8;
     int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
-    k_rows_difference<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr1, col1, rowptr2, col2, src, dst,
+    k_rows_difference<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr1, col1, n1, rowptr2, col2, n2, src, dst,
                                                                        num_edges, nullptr, out_rowptr, out_col);
     OCN_LAUNCH_CHECK();
     return OCN_OK;

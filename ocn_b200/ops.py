@@ -104,25 +104,30 @@ spmm_csr.register_autograd(_spmm_backward, setup_context=_spmm_setup)
 
 
 @torch.library.custom_op("ocn::gcn_spmm", mutates_args=(), device_types="cuda")
-def gcn_spmm(rowptr: Tensor, col: Tensor, norm: Tensor, x: Tensor, mode: int) -> Tensor:
-    return _sp._gcn_raw(_g(rowptr, col), None, norm, mode, x.float())
+def gcn_spmm(rowptr: Tensor, col: Tensor, norm: Tensor, x: Tensor, mode: int, edge_w: Optional[Tensor] = None,
+             self_adjoint: bool = True) -> Tensor:
+    """``self_adjoint``: the matrix is a symmetric unit-weight adjacency (what to_symmetric() yields), so its
+    backward is the same product; pass False for a directed graph or with ``edge_w`` (DropAdj values)."""
+    return _sp._gcn_raw(_g(rowptr, col), edge_w, norm, mode, x.float())
 
 
 @gcn_spmm.register_fake
-def _(rowptr, col, norm, x, mode):
+def _(rowptr, col, norm, x, mode, edge_w=None, self_adjoint=True):
     return x.new_empty(rowptr.numel() - 1, x.shape[1], dtype=torch.float32)
 
 
 def _gcn_setup(ctx, inputs, output):
-    rowptr, col, norm, x, mode = inputs
-    ctx.save_for_backward(rowptr, col, norm)
-    ctx.mode = mode
+    rowptr, col, norm, x, mode, edge_w, self_adjoint = inputs
+    ctx.save_for_backward(rowptr, col, norm, edge_w if edge_w is not None else rowptr.new_empty(0))
+    ctx.mode, ctx.has_w, ctx.self_adjoint = mode, edge_w is not None, bool(self_adjoint) and edge_w is None
 
 
 def _gcn_backward(ctx, g):
-    rowptr, col, norm = ctx.saved_tensors
-    # A-hat is symmetric for both modes (unit edge weights): grad_x = A-hat grad_out
-    return None, None, None, torch.ops.ocn.gcn_spmm(rowptr, col, norm, g.contiguous(), ctx.mode), None
+    rowptr, col, norm, edge_w = ctx.saved_tensors
+    if ctx.self_adjoint:  # A-hat == A-hat^T: grad_x = A-hat grad_out
+        return None, None, None, torch.ops.ocn.gcn_spmm(rowptr, col, norm, g.contiguous(), ctx.mode), None, None, None
+    gx = _sp._gcn_transpose_raw(_g(rowptr, col), edge_w if ctx.has_w else None, norm, ctx.mode, g)
+    return None, None, None, gx, None, None, None
 
 
 gcn_spmm.register_autograd(_gcn_backward, setup_context=_gcn_setup)

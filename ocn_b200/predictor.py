@@ -23,13 +23,18 @@ from .graph import Graph
 
 
 class DropAdj(nn.Module):
-    """Only the buffer of model.py:211-229 (kept for state_dict parity); cn5/cn6/cn7 never apply it."""
+    """model.py:211-229.  cn5 / cn6 / cn7 build one but never apply it; the GNN applies its own to the
+    adjacency of every layer in a training forward (model.py:312) -- ``forward`` does that on a ``Graph``."""
 
     def __init__(self, dp: float = 0.0, doscale=True):
         super().__init__()
         self.dp = dp
         self.register_buffer("ratio", torch.tensor(1 / (1 - dp)))
         self.doscale = doscale
+
+    def forward(self, adj: Graph) -> Graph:
+        from .sparse_ops import drop_adj
+        return drop_adj(adj, self.dp, self.training, self.doscale)
 
 
 def _mlp3(i, h, dropout, ln, last=True):

@@ -82,7 +82,9 @@ def spmm_max(src, other: Tensor):
 # ---- GCN-normalised aggregation ---------------------------------------------------------------
 
 def gcn_norm(g: Graph, edge_w: Optional[Tensor] = None) -> Tensor:
-    """rsqrt(1 + rowsum(A)) (model.py:51, :136)."""
+    """rsqrt(1 + rowsum(A)) (model.py:51, :136); the row sums run over ``edge_w`` (default: the graph's own values,
+    e.g. the rescaled survivors of DropAdj, or ones)."""
+    edge_w = edge_w if edge_w is not None else g.value
     out = torch.empty(g.n, dtype=torch.float32, device=g.device)
     with torch.cuda.device(g.device):
         _lib.check(_lib.lib().ocn_gcn_norm(_lib.ptr(g.rowptr), _lib.ptr(edge_w), g.n, _lib.ptr(out), _stream(g.device)),
@@ -100,23 +102,60 @@ def _gcn_raw(g: Graph, edge_w, norm, mode: int, x: Tensor) -> Tensor:
     return out
 
 
+def _gcn_transpose_raw(g: Graph, edge_w, norm, mode: int, grad: Tensor) -> Tensor:
+    """grad_x = A-hat^T grad for a matrix that is not its own transpose (a directed graph, or the adjacency after
+    DropAdj, whose two directions of an edge are dropped independently, model.py:222):
+        mode 3: A-hat = D (A_w + I) D   ->  D (A_w^T (D g)) + D^2 g
+        mode 4: A-hat = D A_w D         ->  D (A_w^T (D g))
+    with the transpose product as a scatter (ocn_spmm_csr_bwd: vector reductions into the rows of grad_x)."""
+    grad = grad.contiguous().float()
+    t = grad * norm.unsqueeze(1)
+    u = torch.zeros_like(t)
+    with torch.cuda.device(grad.device):
+        _lib.check(_lib.lib().ocn_spmm_csr_bwd(_lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(edge_w), g.n, _lib.ptr(t),
+                                               t.shape[1], 0, _lib.ptr(u), _stream(grad.device)), "ocn_spmm_csr_bwd")
+    u = u * norm.unsqueeze(1)
+    if mode == 3:
+        u = u + grad * (norm * norm).unsqueeze(1)
+    return u
+
+
 class _GcnFn(torch.autograd.Function):
-    """out = A-hat x with a symmetric A-hat (unit or symmetric edge weights), so grad_x = A-hat grad_out."""
+    """out = A-hat x.  A symmetric unit-weight adjacency (what the reference's to_symmetric() graphs are) is its own
+    transpose: grad_x = A-hat grad_out by the same gather kernel, run-to-run deterministic.  Anything else -- explicit
+    edge values, a directed graph -- takes the transpose scatter."""
 
     @staticmethod
     def forward(ctx, x, graph, norm, mode):
         ctx.graph, ctx.mode = graph, mode
+        ctx.self_adjoint = graph.value is None and graph.is_symmetric()
         ctx.save_for_backward(norm)
-        return _gcn_raw(graph, None, norm, mode, x.float())
+        return _gcn_raw(graph, graph.value, norm, mode, x.float())
 
     @staticmethod
     def backward(ctx, g):
         (norm,) = ctx.saved_tensors
-        return _gcn_raw(ctx.graph, None, norm, ctx.mode, g.contiguous().float()), None, None, None
+        if ctx.self_adjoint:
+            return _gcn_raw(ctx.graph, None, norm, ctx.mode, g.contiguous().float()), None, None, None
+        return _gcn_transpose_raw(ctx.graph, ctx.graph.value, norm, ctx.mode, g), None, None, None
+
+
+def drop_adj(adj: Graph, dp: float, training: bool = True, doscale: bool = True,
+             generator: Optional[torch.Generator] = None) -> Graph:
+    """``DropAdj.forward`` (model.py:219-229): in training mode every stored entry survives with probability 1 - dp
+    (``torch.rand_like(col) > dp``: the mask comes from torch's generator on the graph's device, as in the reference)
+    and the survivors carry 1 / (1 - dp) (times their value).  The two directions of an edge are dropped
+    independently, so the result is not symmetric."""
+    if dp < 1e-6 or not training:
+        return adj
+    _require_cuda(adj.col)
+    mask = torch.rand(adj.nnz, dtype=torch.float32, device=adj.device, generator=generator) > dp
+    return adj.drop_entries(mask, 1.0 / (1.0 - dp) if doscale else 1.0)
 
 
 def pure_conv(x: Tensor, adj: Graph, aggr: str = "gcn", norm: Optional[Tensor] = None) -> Tensor:
-    """``PureConv.forward`` (model.py:42-55)."""
+    """``PureConv.forward`` (model.py:42-55).  ``adj`` may carry values (DropAdj): they weigh the sums and the
+    degree normalisation exactly as ``spmm_*`` / ``adj_t.sum(dim=-1)`` do on a valued SparseTensor."""
     _require_cuda(x)
     if aggr == "gcn":
         return _GcnFn.apply(x, adj, norm if norm is not None else gcn_norm(adj), 3)
@@ -135,6 +174,9 @@ def gcnconv_propagate(x: Tensor, adj: Graph, normalize: bool, add_self_loops: bo
         return spmm(adj, x, aggr)
     if not add_self_loops:
         raise NotImplementedError("convdict never builds GCNConv(normalize=True, add_self_loops=False)")
+    if adj.value is not None:
+        # gcn_norm of PyG on a valued matrix adds unit self loops and normalises by the weighted degree: D (A_w + I) D
+        return _GcnFn.apply(x, adj, gcn_norm(adj), 3)
     return _GcnFn.apply(x, adj, gcn_norm(adj), 3)
 
 

@@ -39,7 +39,7 @@ def test_argument_errors_do_not_need_a_gpu():
     assert L.ocn_cn_head_params(256, 256, 1, 0, 2) == -1 and L.ocn_cn_head_params(64, 64, 1, 4, 3) == -1  # beyond 200 KB
     assert L.ocn_cn_head(None, None, None, None, 5, 32, 32, 1, 0, None, 0, None, None, None) == -1
     assert L.ocn_hits_bytes(1000) >= 4000 and L.ocn_mrr(None, None, 3, 4, None, None) == -1
-    assert L.ocn_rows_difference_count(None, None, None, None, None, None, 3, None, None) == -1
+    assert L.ocn_rows_difference_count(None, None, 4, None, None, 4, None, None, 3, None, None) == -1
 
 
 def test_no_cpu_fallback():

@@ -593,3 +593,101 @@ def test_explicit_large_driver_flow(name, fold):
         out7 = p7.multidomainforward(x.to(DEV), G, cn1, cn2, ed, Args())
     o1, o2, oij, _ = R.cn7_aggregate(r1, r2, x, e, 1.0)
     assert torch.allclose(out7, p7._head(o1.to(DEV), o2.to(DEV), None, oij.to(DEV)), rtol=1e-3, atol=1e-4)
+
+
+def _sp_of_graph(G):
+    row, col, val = G.coo()
+    v = val.cpu() if val is not None else torch.ones(col.numel())
+    return R.Sp(row.cpu(), col.cpu(), v, (G.n, G.n_cols))
+
+
+@pytest.mark.parametrize("name,F,dp", [("cora", 32, 0.51), ("pubmed", 64, 0.25), ("citation2_s", 32, 0.2), ("tiny_dense", 8, 0.07)])
+def test_dropadj_weighted_aggregation_and_transpose_backward(name, F, dp):
+    """DropAdj (model.py:211-229) on the GNN's adjacency as GCN.forward applies it per layer (model.py:312): a torch
+    Bernoulli mask over the stored entries, survivors rescaled by 1/(1-dp).  The dropped matrix is NOT symmetric (the
+    two directions of an edge are dropped independently), so forward AND backward of every aggregation the convs
+    use (puregcn with its self term, PureConv3's gcn, sum = gin, mean, max) are checked against autograd through the
+    oracle on the very same mask."""
+    g = GRAPHS[name]()
+    G = ob.Graph.from_edge_index(torch.stack((g.raw_src, g.raw_dst)).to(DEV), g.n)
+    assert G.is_symmetric()
+    torch.manual_seed(5)
+    drop = ob.predictor.DropAdj(dp).to(DEV).train()
+    Gd = drop(G)
+    assert Gd.nnz < G.nnz and Gd.value is not None and not Gd.is_symmetric()
+    assert abs(Gd.nnz / G.nnz - (1 - dp)) < 0.05
+    assert torch.allclose(Gd.value, torch.full_like(Gd.value, 1 / (1 - dp)))
+    assert drop.eval()(G) is G                        # no drop outside training
+    # the kept entries are a subset of the original rows, in order
+    key_all = G.row() * G.n + G.col.long()
+    key_kept = Gd.row() * G.n + Gd.col.long()
+    assert bool(torch.isin(key_kept, key_all).all()) and bool((key_kept[1:] > key_kept[:-1]).all())
+    A = _sp_of_graph(Gd)
+    x = g.features(F)
+    w = torch.randn(g.n, F, generator=torch.Generator().manual_seed(1))
+    ones = R.Sp(A.row, A.col, A.values().abs(), A.shape)
+    # gradient mass: |w| pushed back through |A|^T
+    At = R.Sp(A.col, A.row, A.values().abs(), (A.shape[1], A.shape[0]))
+    order = torch.argsort(At.row * At.shape[1] + At.col)
+    At = R.Sp(At.row[order], At.col[order], At.values()[order], At.shape)
+    gmass = R.spmm_add(At, w.abs()) + w.abs()
+    mass = R.spmm_add(ones, x.abs()) + x.abs()
+    for aggr in ("gcn", "gcn3", "sum", "mean", "max"):
+        xg = x.to(DEV).requires_grad_(True)
+        out = ob.pure_conv3_gcn(xg, Gd) if aggr == "gcn3" else ob.pure_conv(xg, Gd, aggr)
+        (out * w.to(DEV)).sum().backward()
+        if aggr == "max":   # the oracle's max is not differentiable by autograd: its backward is restated separately
+            _close(out.detach(), R.pure_conv(x, A, "max"), mass, rtol=1e-5)
+            _close(xg.grad, R.spmm_max_backward(A, x, w), gmass, rtol=1e-5)
+            continue
+        xr = x.clone().requires_grad_(True)
+        ref = R.pure_conv3_gcn(xr, A) if aggr == "gcn3" else R.pure_conv(xr, A, aggr)
+        (ref * w).sum().backward()
+        _close(out.detach(), ref.detach(), mass, rtol=1e-4)
+        _close(xg.grad, xr.grad, gmass, rtol=1e-4)
+
+
+def test_directed_graph_gcn_backward_uses_the_transpose():
+    """a directed (non-symmetric) unit-weight adjacency must not take the self-adjoint backward."""
+    g = GRAPHS["cora"]()
+    G = ob.Graph.from_edge_index(torch.stack((g.raw_src, g.raw_dst)).to(DEV), g.n, symmetric=False)
+    assert not G.is_symmetric()
+    A = _sp_of_graph(G)
+    x = g.features(16)
+    w = torch.randn(g.n, 16, generator=torch.Generator().manual_seed(2))
+    for mode, ref_fn in ((3, lambda t: R.pure_conv(t, A, "gcn")), (4, lambda t: R.pure_conv3_gcn(t, A))):
+        xr = x.clone().requires_grad_(True)
+        (ref_fn(xr) * w).sum().backward()
+        xg = x.to(DEV).requires_grad_(True)
+        out = ob.pure_conv(xg, G, "gcn") if mode == 3 else ob.pure_conv3_gcn(xg, G)
+        (out * w.to(DEV)).sum().backward()
+        assert torch.allclose(xg.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-5)
+        # the custom op with the flag
+        xo = x.to(DEV).requires_grad_(True)
+        o2 = torch.ops.ocn.gcn_spmm(G.rowptr, G.col, ob.gcn_norm(G), xo, mode, None, False)
+        (o2 * w.to(DEV)).sum().backward()
+        assert torch.allclose(xo.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-5)
+
+
+def test_out_of_range_links_raise():
+    """a target link outside [0, n) raises (the reference: IndexError) instead of reading out of bounds,
+    on the fused path (the plan counts them and stops) and on the generic set operations; the next call works."""
+    g = GRAPHS["cora"]()
+    G = _graph(g)
+    e = g.query_edges(64, "mixed").to(DEV)
+    for bad_val, end in ((g.n, 0), (-1, 1), (g.n + 12345, 1)):
+        bad = e.clone()
+        bad[end, 7] = bad_val
+        with pytest.raises(IndexError):
+            ob.CNSession(G, bad, None, 3)
+        with pytest.raises(IndexError):
+            ob.get_cn(G, bad, 2)
+        with pytest.raises(IndexError):
+            ob.adjoverlap(G, G, bad)
+        with pytest.raises(IndexError):
+            ob.adjoverlap(G, G, bad, calresadj=True)
+    A = _sp(g)
+    ref = R.get_cn(A, e.cpu(), 2)
+    got = ob.get_cn(G, e, 2)
+    for k in range(2):
+        _assert_rows_equal(got[k], ref[k])
