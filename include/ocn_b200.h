@@ -53,6 +53,7 @@ int ocn_device_sm_count(void);
 #define OCN_OPT_HUB_EXACT 5       /* 1: 32-byte node entries with exact run sets + run-segment starts for streams of <= 128 runs
                                      (measured slower than the folded 64-bit sets on the bench workload; implied by WALKER = 1) */
 #define OCN_OPT_GROUPED_OFF 6     /* 1: never use the run-grouped statistics / aggregation kernels (cn_grouped.cu) */
+#define OCN_OPT_SPGEMM_MODE 7     /* A^2 kernel: 0 automatic, 1 global scratch, 2 shared-memory rows, 3 dense bit matrix */
 #define OCN_OPT_COUNT 16
 /* launches of the library's own kernels since the process started (CUB scans / sorts it calls are not counted) */
 long long ocn_launch_count(void);
@@ -296,11 +297,14 @@ int ocn_gcn_spmm(const int64_t* rowptr, const int32_t* col, const float* edge_w,
  * fold == 0: the true A^2.  fold == bs > 0: the reference's adj2byblock result, every bs x bs
  * block summed into the top-left corner.  Two phase: symbolic writes the nnz of
  * every output row, numeric fills ascending columns (+ fp32 2-walk counts if out_val != NULL).
- * scratch: ocn_spgemm_scratch_bytes(n) bytes, zero on first use (left zero on return). */
-size_t ocn_spgemm_scratch_bytes(int64_t n);
-int ocn_spgemm_a2_symbolic(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t fold,
+ * scratch: ocn_spgemm_scratch_bytes(n, nnz, fold) bytes, zero on first use (left zero on return).  The library
+ * picks one of three kernels from (n, nnz, fold) -- dense bit-matrix rows (ddi), a shared-memory row accumulator
+ * (collab, Planetoid), a global-scratch accumulator (column spaces beyond shared memory); OCN_OPT_SPGEMM_MODE forces
+ * one for tests. */
+size_t ocn_spgemm_scratch_bytes(int64_t n, int64_t nnz, int64_t fold);
+int ocn_spgemm_a2_symbolic(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t nnz, int64_t fold,
                            void* scratch, int64_t* out_row_nnz, void* stream);
-int ocn_spgemm_a2_numeric(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t fold,
+int ocn_spgemm_a2_numeric(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t nnz, int64_t fold,
                           void* scratch, const int64_t* out_rowptr, int32_t* out_col, float* out_val,
                           void* stream);
 

@@ -58,9 +58,9 @@ _SIGS = {
     "ocn_spmm_csr_max_bwd": (c_int, [_P, _P, _P, c_int64, _P, _P, c_int64, _P, _P]),
     "ocn_gcn_norm": (c_int, [_P, _P, c_int64, _P, _P]),
     "ocn_gcn_spmm": (c_int, [_P, _P, _P, c_int64, _P, c_int, _P, c_int64, _P, _P]),
-    "ocn_spgemm_scratch_bytes": (c_size_t, [c_int64]),
-    "ocn_spgemm_a2_symbolic": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P]),
-    "ocn_spgemm_a2_numeric": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "ocn_spgemm_scratch_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "ocn_spgemm_a2_symbolic": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, _P]),
+    "ocn_spgemm_a2_numeric": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P]),
     "ocn_cn_head_params": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "ocn_cn_head": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int64, _P, _P, _P]),
     "ocn_mrr": (c_int, [_P, _P, c_int64, c_int64, _P, _P]),
@@ -101,7 +101,7 @@ def lib():
     return _lib
 
 
-OPTIONS = {"hub_window": 0, "hub_cta_window": 1, "hub_heavy_run": 2, "hub_walker": 3, "hub_seg_ctas": 4, "hub_exact": 5, "grouped_off": 6}
+OPTIONS = {"hub_window": 0, "hub_cta_window": 1, "hub_heavy_run": 2, "hub_walker": 3, "hub_seg_ctas": 4, "hub_exact": 5, "grouped_off": 6, "spgemm_mode": 7}
 
 
 def set_option(name: str, value: int) -> None:

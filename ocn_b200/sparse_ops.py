@@ -189,9 +189,9 @@ def spgemm_a2(adj: Graph, fold: int = 0, with_value: bool = False) -> Graph:
     dev = adj.device
     with torch.cuda.device(dev):
         st = _stream(dev)
-        scratch = torch.zeros(L.ocn_spgemm_scratch_bytes(adj.n), dtype=torch.uint8, device=dev)
+        scratch = torch.zeros(L.ocn_spgemm_scratch_bytes(adj.n, adj.nnz, int(fold)), dtype=torch.uint8, device=dev)
         row_nnz = torch.zeros(adj.n, dtype=torch.int64, device=dev)
-        _lib.check(L.ocn_spgemm_a2_symbolic(_lib.ptr(adj.rowptr), _lib.ptr(adj.col), adj.n, int(fold),
+        _lib.check(L.ocn_spgemm_a2_symbolic(_lib.ptr(adj.rowptr), _lib.ptr(adj.col), adj.n, adj.nnz, int(fold),
                                             _lib.ptr(scratch), _lib.ptr(row_nnz), st), "ocn_spgemm_a2_symbolic")
         rowptr = torch.zeros(adj.n + 1, dtype=torch.int64, device=dev)
         torch.cumsum(row_nnz, 0, out=rowptr[1:])
@@ -199,7 +199,7 @@ def spgemm_a2(adj: Graph, fold: int = 0, with_value: bool = False) -> Graph:
         col = torch.empty(nnz, dtype=torch.int32, device=dev)
         val = torch.empty(nnz, dtype=torch.float32, device=dev) if with_value else None
         if nnz:
-            _lib.check(L.ocn_spgemm_a2_numeric(_lib.ptr(adj.rowptr), _lib.ptr(adj.col), adj.n, int(fold),
+            _lib.check(L.ocn_spgemm_a2_numeric(_lib.ptr(adj.rowptr), _lib.ptr(adj.col), adj.n, adj.nnz, int(fold),
                                                _lib.ptr(scratch), _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), st),
                        "ocn_spgemm_a2_numeric")
     return Graph(rowptr, col, adj.n, val)

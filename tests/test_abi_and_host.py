@@ -29,7 +29,7 @@ def test_argument_errors_do_not_need_a_gpu():
     assert rc == -1 and b"null pointer" in L.ocn_last_error()
     rc = L.ocn_spmm_csr(None, None, None, 4, None, 32, 0, None, None)
     assert rc == -1
-    rc = L.ocn_spgemm_a2_symbolic(None, None, 4, 0, None, None, None)
+    rc = L.ocn_spgemm_a2_symbolic(None, None, 4, 8, 0, None, None, None)
     assert rc == -1
     # the entry points either side of the path (graph build / mask, fused head, metrics)
     assert L.ocn_graph_build_bytes(1000, 1) > 2 * 1000 * (8 + 8 + 8 + 4) and L.ocn_graph_mask_bytes(100, 10) > 0

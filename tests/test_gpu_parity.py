@@ -691,3 +691,22 @@ def test_out_of_range_links_raise():
     got = ob.get_cn(G, e, 2)
     for k in range(2):
         _assert_rows_equal(got[k], ref[k])
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("name,fold", [("tiny", 0), ("tiny", 32), ("tiny_dense", 0), ("tiny_dense", 16), ("cora", 0), ("cora", 1024),
+                                       ("ddi_s", 0), ("ddi_s", 64), ("ddi_s", 96), ("pubmed", 0), ("pubmed", 1024)])
+def test_spgemm_kernels_agree_with_the_oracle(lib_options, name, fold, mode):
+    """The three A^2 kernels -- global-scratch accumulator (1), shared-memory row accumulator (2), dense bit-matrix
+    rows (3) -- forced in turn: structure and 2-walk counts bit-exact against torch.sparse on the CPU, true and folded
+    (a fold that is no multiple of 32 leaves the dense kernel and falls back), structure-only too."""
+    g = GRAPHS[name]()
+    G, A = _graph(g), _sp(g)
+    lib_options(spgemm_mode=mode)
+    ref = R.adj2_folded(A, fold) if fold else R.adj2_true(A, keep_value=True)
+    got = ob.spgemm_a2(G, fold, True)
+    assert torch.equal(got.rowptr.cpu(), ref.rowptr())
+    assert torch.equal(got.col.cpu().long(), ref.col)
+    assert torch.equal(got.value.cpu(), ref.values())
+    s = ob.spgemm_a2(G, fold, False)
+    assert s.value is None and torch.equal(s.rowptr, got.rowptr) and torch.equal(s.col, got.col)
