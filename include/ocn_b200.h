@@ -174,6 +174,8 @@ int ocn_rows_difference_fill(const int64_t* rowptr1, const int32_t* col1, int64_
 #define OCN_PLAN_HUB_POSITIONS 11 /* sum over runs of deg(src) */
 #define OCN_PLAN_BAD_LINKS 17    /* links with an endpoint outside [0, n): the plan stops, the caller must not build */
 #define OCN_PLAN_WIDE_LINKS 16   /* links whose source has more than 64 neighbours (they stay with the per-link kernels) */
+#define OCN_PLAN_DENSE 18        /* 1: orders <= 2 on a dense graph (mean degree >= n / 64, n <= 32768) are built from bit-vector
+                                    rows (AND + popcount per record); ocn_cn_hub_bytes then sizes the bit matrix */
 #define OCN_PLAN_WORDS 24
 
 /* bytes of plan scratch the caller must provide for a stream of num_edges links */
@@ -208,7 +210,8 @@ int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n,
                  void* stream);
 
 /* Hub stage of the order-3 walk (cn_hub.cu): a row N(m) that many links of the stream would walk
- * is streamed once for all of them.  Scratch bytes for the sizes ocn_cn_plan reported. */
+ * is streamed once for all of them.  Scratch bytes for the sizes ocn_cn_plan reported.  When the plan chose the
+ * dense build for orders <= 2 (plan[OCN_PLAN_DENSE]) the same scratch holds the graph's rows as bit vectors. */
 size_t ocn_cn_hub_bytes(int64_t n, int64_t nnz, const int64_t* plan_host);
 /* A build that fails half way restores node_scratch to zero itself; if even that fails (a sticky CUDA error) the
  * buffer is remembered as dirty and every later ocn_cn_build on it is refused until the caller has zeroed it and

@@ -26,6 +26,7 @@ from .graph import Graph, _require_cuda
 PLAN_WORDS = 24
 PLAN_HUB_DEGREE = 8  # include/ocn_b200.h OCN_PLAN_HUB_DEGREE
 PLAN_BAD_LINKS = 17  # OCN_PLAN_BAD_LINKS
+PLAN_DENSE = 18      # OCN_PLAN_DENSE
 COLSTAT_BUDGET_BYTES = 4 << 30  # per-wave cap for the per-batch column statistics
 HUB_WORKSPACE_FLOOR = 512 << 20  # first size of the per-stream scratch of the indexed order-3 path
 RECORDS_BUCKET = 16 << 20        # record buffers are sized in these steps, so that the caching allocator re-serves them
@@ -157,7 +158,8 @@ class CNSession:
         self.num_records, self.num_runs, self.num_units = host[0], host[1], host[2]
         self.plan_host = (ctypes.c_int64 * PLAN_WORDS)(*host)
         self.hub_degree = host[PLAN_HUB_DEGREE]
-        self.hub_bytes = L.ocn_cn_hub_bytes(graph.n, graph.nnz, self.plan_host) if self.hub_degree > 0 else 0
+        self.dense = bool(host[PLAN_DENSE])
+        self.hub_bytes = L.ocn_cn_hub_bytes(graph.n, graph.nnz, self.plan_host) if (self.hub_degree > 0 or self.dense) else 0
         rec_bytes = max(1, self.num_records) * L.ocn_cn_record_bytes()
         self.records = torch.empty(-(-rec_bytes // RECORDS_BUCKET) * RECORDS_BUCKET, dtype=torch.uint8, device=self.dev)
         self.colstat = None  # borrowed by build(with_stats=True)
@@ -180,7 +182,7 @@ class CNSession:
             self.colstat = _borrow_colstat(g, self.nb * self.L.ocn_cn_colstat_bytes(g.n))
             self._released = False
         hub_scratch = node_scratch = None
-        if self.hub_bytes > 0 and order >= 3:
+        if self.hub_bytes > 0 and (order >= 3 or self.dense):
             hub_scratch, node_scratch = _hub_workspace(g, self.hub_bytes)
         with torch.cuda.device(self.dev):
             try:

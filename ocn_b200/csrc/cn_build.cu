@@ -629,6 +629,48 @@ k_cn_build_direct(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
     }
 }
 
+// Orders 1-2 on a dense graph: a warp takes 32 consecutive records (link, position p), finds their links with one
+// search per lane, then computes one record at a time with the lanes spread over the W words of the two bit-vector
+// rows: C2 = popc(row(dst) & row(k_p)) summed over the words, C1 = bit dst of row(k_p).
+__global__ void __launch_bounds__(256)
+k_cn_build_dense(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ src,
+                 const int64_t* __restrict__ dst, int64_t T, int order, const int64_t* __restrict__ rec_off,
+                 const uint32_t* __restrict__ bits, int W, Record* __restrict__ records) {
+    const int lane = lane_id();
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t total = rec_off[T];
+    for (int64_t g0 = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * 32; g0 < total; g0 += nwarps * 32) {
+        const int64_t g = g0 + lane;
+        int64_t j = -1;
+        int32_t k = 0;
+        if (g < total) {
+            int64_t lo_t = 0, hi_t = T;  // link of record g: the last t with rec_off[t] <= g
+            while (hi_t - lo_t > 1) {
+                const int64_t mid = (lo_t + hi_t) >> 1;
+                if (ldg_i64(rec_off + mid) <= g) lo_t = mid; else hi_t = mid;
+            }
+            j = dst[lo_t];
+            k = ldg_i32(col + ldg_i64(rowptr + src[lo_t]) + (g - ldg_i64(rec_off + lo_t)));
+        }
+        const int cnt = (int)((total - g0) < 32 ? (total - g0) : 32);
+        unsigned mine = 0u;
+        for (int q = 0; q < cnt; ++q) {
+            const int64_t jq = __shfl_sync(0xffffffffu, j, q);
+            const int32_t kq = __shfl_sync(0xffffffffu, k, q);
+            const uint32_t* rj = bits + jq * W;
+            const uint32_t* rk = bits + (int64_t)kq * W;
+            unsigned c2 = 0u;
+            if (order >= 2)
+                for (int w = lane; w < W; w += 32) c2 += __popc(__ldg(rj + w) & __ldg(rk + w));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+            const unsigned c1 = (__ldg(rk + (jq >> 5)) >> (jq & 31)) & 1u;
+            if (lane == q) mine = c2 | (c1 << 31);
+        }
+        if (g < total) records[g] = make_uint2(mine, 0u);
+    }
+}
+
 // per-batch column statistics from the finished records: one warp per link
 __global__ void k_cn_colstat(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
                              const int64_t* __restrict__ src, int64_t T, int64_t batch_size, int weighted,
@@ -704,7 +746,21 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
         if (rc != OCN_OK) return rc;
         indexed = true;
     }
-    if (order <= 2) {  // the plan picked one of the two on the device (plan[OCN_PLAN_USE_DIRECT]); the other returns at once
+    const bool dense = order <= 2 && plan_host != nullptr && plan_host[OCN_PLAN_DENSE] != 0 && hub_scratch != nullptr;
+    if (dense) {
+        const int W = dense_words(n);
+        const size_t need = sizeof(uint32_t) * (size_t)n * (size_t)W;
+        if (hub_scratch_bytes < need) return fail(OCN_ENOSPACE, "ocn_cn_build: dense scratch %zu < %zu bytes", hub_scratch_bytes, need);
+        uint32_t* bits = (uint32_t*)hub_scratch;
+        k_dense_bits<<<(int)((n * 32 + 255) / 256), 256, 0, st>>>(rowptr, col, n, W, bits);
+        OCN_LAUNCH_CHECK();
+        int64_t want = (records_capacity / 32 + 7) / 8 + 1;
+        int64_t cap = (int64_t)sm_count() * 16;
+        k_cn_build_dense<<<(int)(want < cap ? want : cap), 256, 0, st>>>(rowptr, col, src, dst, num_edges, order, rec_off, bits, W,
+                                                                        (Record*)records);
+        OCN_LAUNCH_CHECK();
+        indexed = true;  // (skips the table kernel below)
+    } else if (order <= 2) {  // the plan picked one of the two on the device (plan[OCN_PLAN_USE_DIRECT]); the other returns at once
         int64_t want = (records_capacity / 32 + 7) / 8 + 1;  // a warp per 32 records
         int64_t cap = (int64_t)sm_count() * 16;
         k_cn_build_direct<<<(int)(want < cap ? want : cap), 256, 0, st>>>(rowptr, col, src, dst, num_edges, order, rec_off,

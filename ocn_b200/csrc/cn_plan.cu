@@ -255,7 +255,8 @@ __global__ void k_plan_positions(const int64_t* __restrict__ plan, const int64_t
     }
 }
 
-__global__ void k_plan_finish(int64_t T, int64_t batch_size, int resident_ctas, const int64_t* __restrict__ rec_off,
+__global__ void k_plan_finish(int64_t T, int64_t batch_size, int resident_ctas, int order, int64_t n, const int64_t* __restrict__ rowptr,
+                              const int64_t* __restrict__ rec_off,
                               const int64_t* __restrict__ run_unit_off, const int32_t* __restrict__ hub_off,
                               const int64_t* __restrict__ run_pos_off, const int64_t* __restrict__ run_pos_heavy_off,
                               const int32_t* __restrict__ chunk_off, int64_t* __restrict__ plan) {
@@ -266,6 +267,10 @@ __global__ void k_plan_finish(int64_t T, int64_t batch_size, int resident_ctas, 
     plan[OCN_PLAN_BUDGET] = unit_budget(plan[OCN_PLAN_TOTAL_COST], resident_ctas);
     // orders <= 2: the table pays off only when several links share it (runs of >= 3 links on average)
     plan[OCN_PLAN_USE_DIRECT] = (T <= 3 * plan[OCN_PLAN_NUM_RUNS]) ? 1 : 0;
+    // dense graphs (ddi: density 0.147, the 2-hop frontier of a link is the whole graph several times over): C2 of a record
+    // is popc(row(dst) & row(k_p)) on bit-vector rows -- 0.3 M links/s through the walk kernels, ~30 M/s this way
+    const int64_t nnz = rowptr[n];
+    plan[OCN_PLAN_DENSE] = (order <= 2 && n <= 32768 && nnz >= n * (n / 64 + 1) && plan[OCN_PLAN_BAD_LINKS] == 0) ? 1 : 0;
     plan[OCN_PLAN_HUB_PAIRS] = hub_off[T];
     const int64_t n_runs = plan[OCN_PLAN_NUM_RUNS];
     plan[OCN_PLAN_HUB_POSITIONS] = run_pos_off[n_runs] + run_pos_heavy_off[n_runs];  // 0 when the indexed path is off
@@ -353,7 +358,7 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
     k_plan_positions<<<(int)((T + 2 + threads - 1) / threads), threads, 0, st>>>(out_plan, pos_scanN, run_pos_heavy, run_pos_off,
                                                                                 pos_start);
     OCN_LAUNCH_CHECK();
-    k_plan_finish<<<1, 1, 0, st>>>(T, batch_size, resident_ctas, rec_off, run_unit_off, hub_off, pos_scanN, run_pos_heavy, chunk_off, out_plan);
+    k_plan_finish<<<1, 1, 0, st>>>(T, batch_size, resident_ctas, order, n, rowptr, rec_off, run_unit_off, hub_off, pos_scanN, run_pos_heavy, chunk_off, out_plan);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
 }

@@ -105,6 +105,11 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
                   int64_t T, const void* plan_scratch, const int64_t* plan_dev, const int64_t* plan_host, void* hub_scratch,
                   size_t hub_scratch_bytes, void* node_scratch, Record* records, int64_t nnz, cudaStream_t st);
 
+// rows of the graph as bit vectors, W words each (spgemm.cu; also the dense order-2 build of cn_build.cu)
+__global__ void k_dense_bits(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n, int W,
+                             uint32_t* __restrict__ bits);
+inline int dense_words(int64_t n) { return (int)(((n + 31) / 32 + 3) & ~int64_t(3)); }
+
 // run-grouped kernels after the build (cn_grouped.cu): used when the stream averages >= kGroupedMinRun links per run
 constexpr int kGroupedMinRun = 16;
 constexpr int kGroupedMaxDeg = 64;   // sources with more neighbours (more than two position tiles) stay with the per-link kernels

@@ -439,7 +439,7 @@ static GemmMode gemm_mode(int64_t n, int64_t nnz, int64_t fold) {
 struct DenseLayout { int W, Wf; size_t bits, S, Sp, total; };
 static DenseLayout dense_layout(int64_t n, int64_t fold) {
     DenseLayout d;
-    d.W = (int)(((n + 31) / 32 + 3) & ~int64_t(3));
+    d.W = dense_words(n);
     const int64_t out = fold > 0 ? (fold < n ? fold : n) : n;
     d.Wf = fold > 0 ? (int)((out + 31) / 32) : d.W;
     size_t off = 0;
