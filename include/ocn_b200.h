@@ -224,7 +224,10 @@ int ocn_cn_hub_timing_events(void* start_event, void* stop_event);
 /* variant: 5 = cn5/OCN (order 2) or its order-3 form (cn6 template), 7 = cn7/OCNP.
  * fill   : weight of a node that is CN1 of exactly one edge of the batch (cn5: 0, cn7: args.sum).
  * ip     : device fp32[3] = inner-product buffer value used for (C2|C1-hat), (C3|C1-hat), (C3|C2-hat);
- *          eval mode passes the stored buffer three times (model.py:2241-2250, Q9).
+ *          eval mode passes the stored buffer three times (model.py:2241-2250, Q9).  NULL (aggregate / aggregate_bwd /
+ *          extract / stats stage 1): every batch reads its own three coefficients from batch_scalars[b*8 + 5..7], which
+ *          the caller wrote after stage 0 -- the sub-batches of one optimiser step as ONE session, each with the running
+ *          mean it would have seen in sequence.
  * out_batch_scalars: device fp32[num_batches * 8]:
  *          [0] scale = max|C1-hat|, [1] s12 = sum(C2 * C1-hat), [2] s13, [3] s23 (training only). */
 int ocn_cn_stats(const int64_t* rowptr, const int32_t* col, int64_t n,

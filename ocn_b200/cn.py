@@ -211,7 +211,15 @@ class CNSession:
                                            self.plan_host, _stream(self.dev)), "ocn_cn_stats")
         return self.bscal.view(self.nb, 8)
 
-    def aggregate(self, x: Tensor, variant: int, fill: float, ip: Tensor, want_xij: bool = True):
+    def set_batch_ip(self, ips: Tensor) -> None:
+        """Per-batch inner-product coefficients (``[num_batches]`` or ``[num_batches, 3]``) into the batches' scalar
+        slots 5..7; ``aggregate`` / ``aggregate_bwd`` / ``extract`` called with ``ip=None`` read them from there."""
+        v = ips.detach().float().reshape(self.nb, -1)
+        if v.shape[1] == 1:
+            v = v.expand(self.nb, 3)
+        self.bscal.view(self.nb, 8)[:, 5:8] = v
+
+    def aggregate(self, x: Tensor, variant: int, fill: float, ip: Optional[Tensor], want_xij: bool = True):
         g = self.g
         x = _check_x(x, g)
         F = x.shape[1]

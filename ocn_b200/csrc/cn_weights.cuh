@@ -87,7 +87,10 @@ __device__ __forceinline__ WeightParams make_params(int order, int weighted, int
     P.variant = variant;
     P.fill = fill;
     const float scale = bscal ? bscal[0] : 0.0f;
-    const float a = ip ? ip[0] : 0.0f, b = ip ? ip[1] : 0.0f, c = ip ? ip[2] : 0.0f;
+    // ip == NULL: every batch carries its own coefficients in its scalar slots 5..7 (a training step whose sub-batches run
+    // as one session: sub-batch u sees the running mean after u updates, model.py:2245-2248)
+    const float a = ip ? ip[0] : (bscal ? bscal[5] : 0.0f), b = ip ? ip[1] : (bscal ? bscal[6] : 0.0f),
+                c = ip ? ip[2] : (bscal ? bscal[7] : 0.0f);
     P.ipn_a = scale > 0.0f ? __fdiv_rn(a, scale) : a;
     P.ipn_b = scale > 0.0f ? __fdiv_rn(b, scale) : b;
     P.ipn_c = scale > 0.0f ? __fdiv_rn(c, scale) : c;

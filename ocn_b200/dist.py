@@ -146,38 +146,66 @@ def allreduce_gradients(tensors: Iterable[torch.Tensor]) -> None:
 
 
 def sharded_train_step(pred, h: torch.Tensor, graph, sub_batches: Sequence[torch.Tensor], signs: Sequence[float],
-                       total_len: int, rank: int, world: int, fill: float = 0.0, args=None):
+                       total_len: int, rank: int, world: int, fill: float = 0.0, args=None,
+                       fuse_sub_batches: bool = True):
     """The predictor part of one optimiser step of the citation2 / ppa drivers with its sub-batches dealt to
     ranks (sub-batch u -> rank u mod world).  ``sub_batches[u]`` is ``[2, b]`` links, ``signs[u]`` is +1 for a
     positive and -1 for a negative sub-batch (loss = -(1/total_len) * sum(logsigmoid(sign * out)),
     NeighborOverlapCitation2.py:177,200).  ``h`` is the detached node embedding with requires_grad.  After the
     call every rank holds the summed gradients of the predictor parameters and of ``h``, and the predictor's
-    inner-product buffer / counter in the state the sequential loop leaves them in.  Returns the step loss."""
+    inner-product buffer / counter in the state the sequential loop leaves them in.  Returns the step loss.
+
+    ``fuse_sub_batches``: the owned sub-batches (equal width) run as ONE session of several link batches instead of
+    one session each -- same column statistics per batch, same coefficients, same gradients up to fp32 summation
+    order (and up to the order in which dropout draws its masks, when the heads use dropout)."""
     import torch.nn.functional as F
     from .cn import CNSession
     U = len(sub_batches)
     mine = list(range(rank, U, world))
     ocn5 = getattr(pred, "variant", 5) == 5
-    sess, s_local = {}, []
-    for u in mine:  # phase 1: CN sets + column statistics of the owned sub-batches, their inner products
-        sess[u] = CNSession(graph, sub_batches[u], None, pred.order).build(pred.order, pred.weighted)
-        if ocn5:
-            s_local.append(pred.batch_inner_product(sess[u], fill))
     dev = h.device
-    if ocn5:  # phase 2: one scalar exchange, running mean replayed in sequence order
-        s_all = exchange_batch_scalars(torch.stack(s_local) if s_local else torch.zeros(0, device=dev), mine, U)
-        ips, n_end = replay_running_mean(s_all, pred.innerprod, pred.n)
+    widths = {int(sub_batches[u].shape[1]) for u in mine}
+    fused = fuse_sub_batches and len(mine) > 1 and len(widths) == 1 and not (ocn5 and pred.order >= 3)
     loss = torch.zeros((), device=dev)
-    for u in mine:  # phase 3: weighted aggregation, heads, loss, backward
-        e = sub_batches[u]
+    if fused:
+        # The owned sub-batches as ONE session of len(mine) link batches: one plan, one build, one aggregation forward
+        # and backward for all of them (16 x fewer launches, kernels 16 x larger); every batch still has its own column
+        # statistics, and its own inner-product coefficient through the batches' scalar slots.
+        b = widths.pop()
+        e_all = torch.cat([sub_batches[u] for u in mine], dim=1)
+        sess_all = CNSession(graph, e_all, b, pred.order).build(pred.order, pred.weighted)
+        ips, n_end = None, pred.n
         if ocn5:
-            xcn1, xcn2, xcn3, xij, _ = pred.cn_stage(h, graph, e, fill, sess[u], ip=ips[u:u + 1])
-        else:
-            xcn1, xcn2, xcn3, xij, _ = pred.cn_stage(h, graph, e, fill, sess[u])
-        out = pred._head(xcn1, xcn2, xcn3, xij)
-        l = -(1.0 / total_len) * F.logsigmoid(signs[u] * out).sum()
+            ip3 = pred.innerprod.detach().float().reshape(-1)[:1].repeat(3).contiguous()
+            s_local = sess_all.stats(5, fill, ip3, 0)[:, 1].detach().clone()        # s of every owned sub-batch
+            s_all = exchange_batch_scalars(s_local, mine, U)
+            ips, n_end = replay_running_mean(s_all, pred.innerprod, pred.n)
+            sess_all.set_batch_ip(ips[torch.as_tensor(mine, device=dev)])
+        xcn1, xcn2, xcn3, xij, _ = pred.cn_stage(h, graph, e_all, fill, sess_all, per_batch_ip=ocn5)
+        out = pred._head(xcn1, xcn2, xcn3, xij).reshape(len(mine), b)
+        sg = torch.as_tensor([signs[u] for u in mine], dtype=out.dtype, device=dev).unsqueeze(1)
+        l = -(1.0 / total_len) * F.logsigmoid(sg * out).sum()
         l.backward()
         loss += l.detach()
+    else:
+        sess, s_local = {}, []
+        for u in mine:  # phase 1: CN sets + column statistics of the owned sub-batches, their inner products
+            sess[u] = CNSession(graph, sub_batches[u], None, pred.order).build(pred.order, pred.weighted)
+            if ocn5:
+                s_local.append(pred.batch_inner_product(sess[u], fill))
+        if ocn5:  # phase 2: one scalar exchange, running mean replayed in sequence order
+            s_all = exchange_batch_scalars(torch.stack(s_local) if s_local else torch.zeros(0, device=dev), mine, U)
+            ips, n_end = replay_running_mean(s_all, pred.innerprod, pred.n)
+        for u in mine:  # phase 3: weighted aggregation, heads, loss, backward
+            e = sub_batches[u]
+            if ocn5:
+                xcn1, xcn2, xcn3, xij, _ = pred.cn_stage(h, graph, e, fill, sess[u], ip=ips[u:u + 1])
+            else:
+                xcn1, xcn2, xcn3, xij, _ = pred.cn_stage(h, graph, e, fill, sess[u])
+            out = pred._head(xcn1, xcn2, xcn3, xij)
+            l = -(1.0 / total_len) * F.logsigmoid(signs[u] * out).sum()
+            l.backward()
+            loss += l.detach()
     if ocn5:
         with torch.no_grad():
             pred.innerprod.copy_(ips[-1:].to(pred.innerprod.dtype))

@@ -48,10 +48,12 @@ class _CNAggregateFn(torch.autograd.Function):
     """xcn_k = C-hat_k @ x and x_i * x_j; the weights do not depend on x or on any parameter."""
 
     @staticmethod
-    def forward(ctx, x, sess: CNSession, variant: int, fill: float, ip3: Tensor):
+    def forward(ctx, x, sess: CNSession, variant: int, fill: float, ip3: Optional[Tensor]):
+        # ip3 None: every batch of the session reads its own coefficients from its scalar slots (CNSession.set_batch_ip)
         xcn1, xcn2, xcn3, xij = sess.aggregate(x, variant, fill, ip3, want_xij=True)
         ctx.sess, ctx.variant, ctx.fill = sess, variant, fill
-        ctx.save_for_backward(x, ip3)
+        ctx.per_batch = ip3 is None
+        ctx.save_for_backward(x, ip3 if ip3 is not None else x.new_empty(0))
         ctx.has = (xcn2 is not None, xcn3 is not None)
         z = lambda t: t if t is not None else x.new_zeros(0)
         return xcn1, z(xcn2), z(xcn3), xij
@@ -59,6 +61,8 @@ class _CNAggregateFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g1, g2, g3, gij):
         x, ip3 = ctx.saved_tensors
+        if ctx.per_batch:
+            ip3 = None
         gx = torch.zeros_like(x)
         ctx.sess.aggregate_bwd(x, ctx.variant, ctx.fill, ip3, g1, g2 if ctx.has[0] else None,
                                g3 if ctx.has[1] else None, gij, gx)
@@ -130,9 +134,19 @@ class _OCNBase(nn.Module):
         return c[1]
 
     def cn_stage(self, x: Tensor, adj: Graph, tar_ei: Tensor, fill: float = 0.0, sess: Optional[CNSession] = None,
-                 ip: Optional[Tensor] = None):
+                 ip: Optional[Tensor] = None, per_batch_ip: bool = False):
         """``ip``: use this inner-product coefficient (shape [1]) instead of reading / updating the module's
-        running mean -- the caller has already folded this batch's ``s`` into it."""
+        running mean -- the caller has already folded this batch's ``s`` into it.  ``per_batch_ip``: the session
+        holds several batches and the caller has stored every batch's coefficient with ``sess.set_batch_ip`` (after
+        ``sess.stats(..., stage 0)``): nothing is read from or written to the module's buffer."""
+        if per_batch_ip:
+            if self.variant == 5 and self.order >= 3:
+                raise ValueError("per-batch coefficients are supported for order 2 (SURVEY Q9: the order-3 template chains "
+                                 "three buffer updates per batch)")
+            xcn1, xcn2, xcn3, xij = _CNAggregateFn.apply(x, sess, self.variant, float(fill), None)
+            if not (torch.is_grad_enabled() and x.requires_grad):
+                sess.release()
+            return xcn1, xcn2, (xcn3 if xcn3.numel() else None), xij, sess
         if sess is None:
             sess = CNSession(adj, tar_ei, None, self.order)
             sess.build(self.order, self.weighted)
