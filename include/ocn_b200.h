@@ -142,6 +142,26 @@ int ocn_rows_difference_fill(const int64_t* rowptr1, const int32_t* col1, int64_
                              const int64_t* src, const int64_t* dst, int64_t num_edges,
                              const int64_t* out_rowptr, int64_t* out_col, void* stream);
 
+/* ---- container methods behind the import shims (ocn_b200/shim: torch_sparse / pygho stand-ins on CUDA) -----------
+ * adj[idx] / SparseTensor.index_select(0, idx) / pygho index_select([0], idx) (utils.py:256-257,
+ * NeighborOverlapCitation2.py:79-81): out row b = row idx[b] of the matrix, columns (and values) in order.
+ * out_counts has num_rows + 1 words, the last ZERO on entry: it receives the number of idx outside [0, n). */
+int ocn_rows_gather_count(const int64_t* rowptr, int64_t n, const int64_t* idx, int64_t num_rows, int64_t* out_counts,
+                          void* stream);
+int ocn_rows_gather_fill(const int64_t* rowptr, const int32_t* col, const float* val /* NULL = ones */, int64_t n,
+                         const int64_t* idx, int64_t num_rows, const int64_t* out_rowptr, int32_t* out_col,
+                         float* out_val /* NULL = structure only */, void* stream);
+/* pygho.backend.Spspmm.spsphadamard(A, B) on two explicit [num_rows x N] matrices (model.py:2243 innerprod1; the
+ * general case of NeighborOverlapCitation2.py:82-85): entries present in both, value va * vb (NULL values = ones),
+ * columns ascending. */
+int ocn_rows_hadamard_count(const int64_t* rowptr_a, const int32_t* col_a, const int64_t* rowptr_b, const int32_t* col_b,
+                            int64_t num_rows, int64_t* out_counts /* [num_rows] */, void* stream);
+int ocn_rows_hadamard_fill(const int64_t* rowptr_a, const int32_t* col_a, const float* val_a, const int64_t* rowptr_b,
+                           const int32_t* col_b, const float* val_b, int64_t num_rows, const int64_t* out_rowptr,
+                           int32_t* out_col, float* out_val, void* stream);
+/* SparseTensor.sum(dim=0) (model.py:2261, 3114): out[col[e]] += val[e] (NULL = 1) into the caller's ZEROED out[n_cols]. */
+int ocn_csr_colsum(const int32_t* col, const float* val, int64_t nnz, int64_t n_cols, float* out, void* stream);
+
 /* ---- pieces 1 + 1b + 2, fused: higher-order CN sets over A, A^2, A^3 ------------------------
  * Replaces get_cn1_cn2 (NeighborOverlapCitation2.py:78-104, NeighborOverlap_large_ppa.py:147-173)
  * and adjoverlap(adj, adj, e) / adjoverlap(adj, adj2, e) (NeighborOverlap_large.py:78-79)

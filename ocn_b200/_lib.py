@@ -31,6 +31,11 @@ _SIGS = {
     "ocn_rows_intersect_fill": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, c_int64, _P, _P, _P]),
     "ocn_rows_difference_count": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, c_int64, _P, _P]),
     "ocn_rows_difference_fill": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, c_int64, _P, _P, _P]),
+    "ocn_rows_gather_count": (c_int, [_P, c_int64, _P, c_int64, _P, _P]),
+    "ocn_rows_gather_fill": (c_int, [_P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, _P]),
+    "ocn_rows_hadamard_count": (c_int, [_P, _P, _P, _P, c_int64, _P, _P]),
+    "ocn_rows_hadamard_fill": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P]),
+    "ocn_csr_colsum": (c_int, [_P, _P, c_int64, c_int64, _P, _P]),
     "ocn_cn_plan_bytes": (c_size_t, [c_int64]),
     "ocn_cn_colstat_bytes": (c_size_t, [c_int64]),
     "ocn_cn_record_bytes": (c_size_t, []),
