@@ -156,6 +156,45 @@ def run_utils_case(graphs):
     print(f"wrote {path}: {len(cases)} case(s), {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def run_completion_case(name, graph, B, mode, ncalls, trainresdeg, testresdeg, seed):
+    """cn2 = IncompleteCN1Predictor (model.py:843-1146) at depth 1, in = hidden = 64 (its xijlin is a Linear(64, .)
+    applied twice).  The draws of sparsesample_reweight's torch.rand are recorded so that a replay is deterministic."""
+    torch.manual_seed(seed)
+    n = graph.n
+    rowptr, col = graph.rowptr, graph.col.long()
+    row = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
+    adj = SparseTensor(row=row, col=col, sparse_sizes=(n, n), is_sorted=True)
+    x = graph.features(64)
+    pred = ref_model.IncompleteCN1Predictor(64, 64, 1, 3, 0.0, trainresdeg=trainresdeg, testresdeg=testresdeg, depth=1)
+    pred.train() if mode == "train" else pred.eval()
+    draws = []
+    real_rand = torch.rand
+
+    def rand(*a, **k):
+        out = real_rand(*a, **k)
+        draws.append(out.clone())
+        return out
+    calls = []
+    torch.rand = rand
+    try:
+        with torch.no_grad():
+            for s in range(ncalls):
+                neg = torch.stack((synth.hash_randint(B - B // 2, n, 270 + s, 1, "cpu"), synth.hash_randint(B - B // 2, n, 270 + s, 2, "cpu")))
+                e = torch.cat((graph.query_edges(B // 2, "pos"), neg), 1)
+                first = len(draws)
+                out = pred(x, adj, e)
+                calls.append({"edges": e.clone(), "out": out.detach().clone(), "innerprod": pred.innerprod.detach().clone(),
+                              "n": pred.n, "draws": draws[first:]})
+    finally:
+        torch.rand = real_rand
+    fx = {"name": name, "n": n, "rowptr": rowptr.clone(), "col": graph.col.clone(), "x": x, "mode": mode,
+          "trainresdeg": trainresdeg, "testresdeg": testresdeg,
+          "state_dict": {k: v.clone() for k, v in pred.state_dict().items()}, "calls": calls}
+    path = os.path.join(ROOT, "tests", "golden", f"ref_{name}.pt")
+    torch.save(fx, path)
+    print(f"wrote {path}: {len(calls)} call(s), {sum(len(c['draws']) for c in calls)} recorded draws, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="", help="regex: write only the fixtures whose name matches")
@@ -182,6 +221,10 @@ def main():
         mid = synth.tiny_graph(150, 700, 8)
         run_utils_case([("tiny_b16", tiny, 16, links(tiny, 48, 1)[0]), ("tiny_b60", tiny, 60, links(tiny, 48, 1)[0]),
                         ("tiny_b1024", tiny, 1024, links(tiny, 48, 1)[0]), ("mid_b64", mid, 64, links(mid, 64, 1)[0])])
+    if only.search("cn2_eval_cora"):
+        run_completion_case("cn2_eval_cora", synth.make_graph("cora", scale=0.06), 32, "eval", 1, 8, 6, 11)
+    if only.search("cn2_train_tiny"):
+        run_completion_case("cn2_train_tiny", tiny, 24, "train", 3, 3, 128, 12)
     run_case("cn5_large_eval_tiny", tiny, 8, links(tiny, 48, 1), "cn5", "eval", "large")
     run_case("cn5_large_train_cora", cora, 16, links(cora, 96, 3), "cn5", "train", "large")
     run_case("cn5_large_eval_ln_cora", cora, 16, links(cora, 96, 1), "cn5", "eval", "large", ln=True)

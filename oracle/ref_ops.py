@@ -168,6 +168,66 @@ def adjoverlap(adj1: Sp, adj2: Sp, tarei: Tensor, calresadj: bool = False):
     return spmoverlap_(a1, a2)
 
 
+def sparsesample_reweight(adj: Sp, deg: int, rand_fn=None) -> Sp:
+    """utils.py:109-143: rows longer than ``deg`` are replaced by ``deg`` draws with replacement worth
+    ``rowcount / deg`` each, the others keep their entries with value 1; ``coalesce`` sums repeated draws.
+    ``rand_fn(shape)`` stands for ``torch.rand`` (the golden fixtures replay the reference's draws through it)."""
+    rowptr, col = adj.rowptr(), adj.col
+    rowcount = rowptr[1:] - rowptr[:-1]
+    mask = rowcount > deg
+    rowcount_m = rowcount[mask]
+    rowptr_m = rowptr[:-1][mask]
+    rand = (rand_fn or torch.rand)((rowcount_m.size(0), deg))
+    rand = rand.clone().mul_(rowcount_m.to(rand.dtype).reshape(-1, 1))
+    rand = rand.to(torch.long)
+    rand.add_(rowptr_m.reshape(-1, 1))
+    samplecol = col[rand].flatten()
+    samplerow = torch.arange(adj.shape[0])[mask].reshape(-1, 1).expand(-1, deg).flatten()
+    samplevalue = (rowcount_m * (1 / deg)).reshape(-1, 1).expand(-1, deg).flatten()
+    mask = torch.logical_not(mask)
+    rest = index_select_rows(adj, torch.nonzero(mask).flatten())
+    nosamplerow = torch.arange(adj.shape[0])[mask][rest.row]
+    return sp_coalesce(torch.cat((samplerow, nosamplerow)), torch.cat((samplecol, rest.col)),
+                       torch.cat((samplevalue, torch.ones_like(nosamplerow))).float(), adj.shape)
+
+
+def cn2_forward(mod, x: Tensor, adj: Sp, tar_ei: Tensor, state: "InnerProdState", training: bool, depth: int,
+                rand_fn=None) -> Tensor:
+    """``IncompleteCN1Predictor.multidomainforward`` (model.py:888-1131; edrop = 0, cndeg <= 0, use_xlin False).
+    ``mod`` supplies the dense heads (xijlin, xcnlin, lin, ptlin), buffers (beta, alpha2, pt, scale, offset) and the
+    sampling degrees; the sparse part is restated here."""
+    xij = mod.xijlin(x[tar_ei[0]] * x[tar_ei[1]])
+    resdeg = mod.trainresdeg if training else mod.testresdeg
+    if depth > 0.5:
+        cn, cnres1, cnres2 = adjoverlap(adj, adj, tar_ei, calresadj=True)
+        if resdeg > 0:
+            cnres1 = sparsesample_reweight(cnres1, resdeg, rand_fn)
+            cnres2 = sparsesample_reweight(cnres2, resdeg, rand_fn)
+    else:
+        cn = adjoverlap(adj, adj, tar_ei)
+    xcn = spmm_add(cn, x)
+    if depth > 0.5:
+        def clampprob(prob, pt):
+            p0 = torch.sigmoid(mod.scale * (prob - mod.offset))
+            return mod.alpha2 * pt * p0 / (pt * p0 + 1 - p0)
+        with torch.no_grad():
+            probcn1 = cn2_forward(mod, x, adj, torch.stack((tar_ei[1][cnres1.row], cnres1.col)), state, training,
+                                  depth - 1, rand_fn).flatten()
+            probcn2 = cn2_forward(mod, x, adj, torch.stack((tar_ei[0][cnres2.row], cnres2.col)), state, training,
+                                  depth - 1, rand_fn).flatten()
+        if mod.learnablept:
+            pt = mod.ptlin(xij)
+            probcn1, probcn2 = clampprob(probcn1, pt[cnres1.row]), clampprob(probcn2, pt[cnres2.row])
+        else:
+            probcn1, probcn2 = clampprob(probcn1, mod.pt), clampprob(probcn2, mod.pt)
+        cnres1 = Sp(cnres1.row, cnres1.col, (probcn1 * cnres1.values()).detach(), cnres1.shape)
+        cnres2 = Sp(cnres2.row, cnres2.col, (probcn2 * cnres2.values()).detach(), cnres2.shape)
+        xcn1, xcn2, _, _, _ = cn5_aggregate(cnres1, cnres2, x, tar_ei, state, training)     # model.py:960-1123
+        xcn = xcn + xcn2 + xcn1
+    xij = mod.xijlin(xij)
+    return mod.lin(mod.xcnlin(xcn) * mod.beta + xij)
+
+
 # ----------------------------------------------------------------------------------------------
 # piece 3b: A^2  (NeighborOverlap_large.py:68-74,112-119; utils.py:287-329)
 # ----------------------------------------------------------------------------------------------

@@ -131,3 +131,60 @@ def test_oracle_reproduces_reference_adj2byblock_and_calresadj():
         _same_sparse(R.adjoverlap(A, f, e), c["cn2"])
         for got, key in zip(R.adjoverlap(A, A, e, calresadj=True), ("overlap", "res1", "res2")):
             _same_sparse(got, c[key])
+
+
+# ---- cn2 = IncompleteCN1Predictor: fixtures produced by the reference's own class ----------------------
+
+CN2_FIXTURES = ["cn2_eval_cora", "cn2_train_tiny"]
+
+
+def _replay_draws(draws):
+    it = iter(draws)
+
+    def rand_fn(shape, device=None):
+        d = next(it)
+        assert tuple(d.shape) == tuple(shape), f"sampler asked for {tuple(shape)}, the reference drew {tuple(d.shape)}"
+        return d if device is None else d.to(device)
+    return rand_fn
+
+
+def _cn2_module(fx, device="cpu"):
+    from ocn_b200.completion import IncompleteCN1Predictor
+    pred = IncompleteCN1Predictor(64, 64, 1, 3, 0.0, trainresdeg=fx["trainresdeg"], testresdeg=fx["testresdeg"], depth=1)
+    missing = pred.load_state_dict(fx["state_dict"], strict=True)     # same parameter / buffer names as the reference
+    assert not missing.missing_keys and not missing.unexpected_keys
+    pred = pred.to(device)
+    pred.train() if fx["mode"] == "train" else pred.eval()
+    return pred
+
+
+@pytest.mark.parametrize("name", CN2_FIXTURES)
+def test_oracle_cn2_matches_the_reference_class(name):
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", f"ref_{name}.pt"))
+    mod = _cn2_module(fx)
+    A = R.sp_from_csr(fx["rowptr"], fx["col"])
+    state = R.InnerProdState()
+    with torch.no_grad():
+        for call in fx["calls"]:
+            out = R.cn2_forward(mod, fx["x"], A, call["edges"], state, fx["mode"] == "train", 1, _replay_draws(call["draws"]))
+            assert torch.allclose(out, call["out"], rtol=1e-4, atol=1e-5), (out - call["out"]).abs().max()
+            assert torch.allclose(state.innerprod, call["innerprod"], rtol=1e-5, atol=1e-6)
+            assert state.n == call["n"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CN2_FIXTURES)
+def test_cuda_cn2_matches_the_reference_class(name):
+    import ocn_b200 as ob
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", f"ref_{name}.pt"))
+    dev = "cuda:0"
+    pred = _cn2_module(fx, dev)
+    G = ob.Graph(fx["rowptr"].to(dev), fx["col"].to(dev), fx["n"])
+    x = fx["x"].to(dev)
+    with torch.no_grad():
+        for call in fx["calls"]:
+            pred.rand_fn = _replay_draws(call["draws"])
+            out = pred(x, G, call["edges"].to(dev))
+            assert torch.allclose(out.cpu(), call["out"], rtol=1e-4, atol=1e-5), (out.cpu() - call["out"]).abs().max()
+            assert torch.allclose(pred.innerprod.cpu(), call["innerprod"], rtol=1e-5, atol=1e-6)
+            assert pred.n == call["n"]
