@@ -216,7 +216,9 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n,
  * colstat: device buffer of num_batches * ocn_cn_colstat_bytes(n) bytes, ZERO on entry
  *          (ocn_cn_release restores that), or NULL when only the sets are wanted.
  * order in {1,2,3}; weighted != 0 keeps walk counts as values (pygho path), == 0 uses the 0/1
- * structure (torch_sparse path). */
+ * structure (torch_sparse path).  weighted == 2 (ocn_cn_build only; the later stages take 1): the
+ * shortest-path variant of SPD.py:65-126 -- the 2-walk count of a node that is itself a neighbour of the destination
+ * is zeroed (compute_adj2_with_shortest_paths masks the entries of A out of Ej . A). */
 int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n,
                  const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t batch_size,
                  int order, int weighted,

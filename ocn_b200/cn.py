@@ -170,8 +170,12 @@ class CNSession:
         self._released = False
 
     # -- steps ------------------------------------------------------------------------------
-    def build(self, order: int, weighted: bool, with_stats: bool = True) -> "CNSession":
+    def build(self, order: int, weighted: bool, with_stats: bool = True, spd: bool = False) -> "CNSession":
+        """``spd``: the shortest-path variant of SPD.py:65-126 -- 2-walk counts of nodes adjacent to the destination
+        are zeroed before the column statistics are taken (weighted sets only)."""
         g = self.g
+        if spd and not weighted:
+            raise ValueError("the shortest-path variant masks walk counts: it needs weighted=True (SPD.py builds pygho matrices)")
         if order > self.plan_order:
             raise ValueError(f"the session was planned for order {self.plan_order}; cannot build order {order}")
         if with_stats and self.colstat is not None and not self._released and self.order > 0:
@@ -187,7 +191,8 @@ class CNSession:
         with torch.cuda.device(self.dev):
             try:
                 _lib.check(self.L.ocn_cn_build(_lib.ptr(g.rowptr), _lib.ptr(g.col), g.n, _lib.ptr(self.src),
-                                               _lib.ptr(self.dst), self.T, self.batch_size, int(order), int(bool(weighted)),
+                                               _lib.ptr(self.dst), self.T, self.batch_size, int(order),
+                                               2 if spd else int(bool(weighted)),
                                                _lib.ptr(self.plan_scratch), _lib.ptr(self.plan), _lib.ptr(self.records),
                                                self.num_records, _lib.ptr(self.colstat) if with_stats else None,
                                                g.nnz, self.plan_host, _lib.ptr(hub_scratch), self.hub_bytes,

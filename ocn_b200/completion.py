@@ -76,6 +76,11 @@ class IncompleteCN1Predictor(CNLinkPredictor):
                  testresdeg=128, pt=0.5, learnablept=False, depth=1, splitsize=-1):
         super().__init__(in_channels, hidden_channels, out_channels, num_layers, dropout, edrop, ln, cndeg, use_xlin,
                          tailact, twolayerlin, beta)
+        if learnablept:
+            # model.py:947-949: clampprob(prob[nnz], pt[potcn[0]] of shape [nnz, 1]) broadcasts to [nnz, nnz] and that
+            # matrix is then stored as the VALUES of the residual matrix -- the branch cannot run on real sizes
+            raise NotImplementedError("learnablept=True: the reference's own branch broadcasts the residual weights to "
+                                      "[nnz, nnz] (model.py:947-949); no README command enables it")
         self.learnablept = learnablept
         self.depth = depth
         self.splitsize = splitsize
@@ -129,16 +134,8 @@ class IncompleteCN1Predictor(CNLinkPredictor):
             with torch.no_grad():
                 probcn1 = self._score_residual(x, adj, tar_ei[1], cnres1, filled1, depth - 1)
                 probcn2 = self._score_residual(x, adj, tar_ei[0], cnres2, filled1, depth - 1)
-            if self.learnablept:
-                if self.training and torch.is_grad_enabled():
-                    raise NotImplementedError("learnablept: the residual weights would need a gradient through the values "
-                                              "of the sparse operand of spmm_add, which ocn_spmm_csr_bwd does not produce")
-                pt = self.ptlin(xij)
-                probcn1 = self.clampprob(probcn1, pt[cnres1.row()])
-                probcn2 = self.clampprob(probcn2, pt[cnres2.row()])
-            else:
-                probcn1 = self.clampprob(probcn1, self.pt)
-                probcn2 = self.clampprob(probcn2, self.pt)
+            probcn1 = self.clampprob(probcn1, self.pt)
+            probcn2 = self.clampprob(probcn2, self.pt)
             cnres1 = SparseRows(cnres1.rowptr, cnres1.col, probcn1 * cnres1.value, cnres1.shape)
             cnres2 = SparseRows(cnres2.rowptr, cnres2.col, probcn2 * cnres2.value, cnres2.shape)
             # model.py:960-1123: the cn5 combination with the weighted residuals in the roles of cn1 / cn2

@@ -713,6 +713,16 @@ __global__ void k_cn_colstat(const int64_t* __restrict__ rowptr, const int32_t* 
 
 using namespace ocn;
 
+namespace ocn {
+__global__ void k_records_spd(Record* __restrict__ records, int64_t num_records) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < num_records; r += stride) {
+        const uint32_t x = records[r].x;
+        if ((x >> 31) && (x & 0x7fffffffu)) records[r].x = 0x80000000u;
+    }
+}
+}  // namespace ocn
+
 extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src,
                             const int64_t* dst, int64_t num_edges, int64_t batch_size, int order, int weighted,
                             const void* plan_scratch, const int64_t* plan, void* records, int64_t records_capacity,
@@ -773,6 +783,13 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
             rowptr, col, n, src, dst, order, rec_off, (const int32_t*)(base + L.run_start),
             (const int64_t*)(base + L.run_unit_off), (const int64_t*)(base + L.cost_pre), (int64_t*)plan,
             (Record*)records);
+        OCN_LAUNCH_CHECK();
+    }
+    if (weighted == 2 && order >= 2 && records_capacity > 0) {
+        // shortest-path variant (SPD.py:65-126): a 2-walk count only stands for nodes at distance exactly 2 from the
+        // destination, i.e. C2[p] = 0 wherever k_p is itself a neighbour of it -- which is the C1 bit of the record
+        const int64_t want = (records_capacity + 255) / 256, cap = (int64_t)sm_count() * 16;
+        k_records_spd<<<(int)(want < cap ? want : cap), 256, 0, st>>>((Record*)records, records_capacity);
         OCN_LAUNCH_CHECK();
     }
     const bool grouped = colstat != nullptr && use_grouped(num_edges, plan_host);

@@ -102,6 +102,7 @@ class _OCNBase(nn.Module):
         self.n = 0
         # values of CN_k for k >= 2: pygho walk counts (citation2/ppa drivers) or 0/1 (the _large drivers), SURVEY Q11
         self.weighted = weighted
+        self.spd = False  # SPD.py's get_cn1_cn2: CN2 counts only for nodes at distance exactly 2 from the destination
 
     def _extra_heads(self, i, h, dropout, ln):
         self.xcn4lin = _mlp3(i, h, dropout, ln)
@@ -149,7 +150,7 @@ class _OCNBase(nn.Module):
             return xcn1, xcn2, (xcn3 if xcn3.numel() else None), xij, sess
         if sess is None:
             sess = CNSession(adj, tar_ei, None, self.order)
-            sess.build(self.order, self.weighted)
+            sess.build(self.order, self.weighted, spd=self.spd)
         ip3 = self._ip3() if ip is None else ip.detach().float().reshape(-1)[:1].repeat(3).contiguous()
         if self.variant == 5 and ip is not None:
             if self.order >= 3:

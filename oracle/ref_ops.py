@@ -319,6 +319,30 @@ def get_cn(adj: Sp, tedge: Tensor, order: int = 2) -> List[Sp]:
 # piece 1b + 2: orthogonalised combination and CN-indicator SpMM
 # ----------------------------------------------------------------------------------------------
 
+def get_cn_spd(adj: Sp, tedge: Tensor, literal: bool = False) -> List[Sp]:
+    """SPD.py:98-126 with ``compute_adj2_with_shortest_paths`` (:65-95): ``Ej2 = Ej . A`` with the values at the
+    entries of ``A`` multiplied by 0 (the entries stay), then ``cn2 = Ei (.) Ej2``.
+
+    The reference's loop (:81-84) tests ``adj2_indices[0] == adj_indices[0][i]``: the row of ``Ej . A`` is a position
+    in the batch, the row of ``A`` a node id, so as written it masks (b, k) when k is a neighbour of NODE b
+    (``literal=True``); the masking the function is named after goes by the destination of link b (default).  Neither
+    can be produced by running the reference: :93 calls torch_sparse's constructor with pygho's arguments."""
+    Ei = index_select_rows(adj, tedge[0])
+    Ej = index_select_rows(adj, tedge[1])
+    cn1 = spsphadamard(Ei, Ej)
+    Ej2 = spspmm_expand(Ej, adj)
+    B = Ej2.shape[0]
+    owner = Ej2.row if literal else tedge[1][Ej2.row]          # whose neighbourhood masks the entry
+    ka = adj.row * adj.shape[1] + adj.col
+    ke = owner * adj.shape[1] + Ej2.col
+    idx = torch.searchsorted(ka, ke).clamp_(max=max(ka.numel() - 1, 0))
+    hit = (ka[idx] == ke) if ka.numel() else torch.zeros_like(ke, dtype=torch.bool)
+    if literal:
+        hit &= Ej2.row < min(B, adj.shape[0])
+    Ej2 = Sp(Ej2.row, Ej2.col, Ej2.values() * (~hit).to(torch.float32), Ej2.shape)
+    return [cn1, spsphadamard(Ei, Ej2)]
+
+
 def sp_sum_dim0(s: Sp) -> Tensor:
     """torch_sparse ``SparseTensor.sum(dim=0)``: scatter-add of values over col [recalled]."""
     return torch.zeros(s.shape[1], dtype=torch.float32).index_add_(0, s.col, s.values())
