@@ -269,7 +269,22 @@ def test_predictor_end_to_end_matches_oracle_heads():
 
 
 @pytest.mark.parametrize("name,F", [("tiny", 5), ("cora", 256), ("pubmed", 64), ("collab_s", 128), ("ddi_s", 64), ("citation2_s", 32)])
-def test_gnn_aggregation(name, F):
+def test_gnn_aggregation(name, F, lib_options):
+    lib_options(spmm_tma=2)          # the register gather (k_spmm)
+    _check_gnn_aggregation(name, F)
+
+
+@pytest.mark.parametrize("name,F", [("cora", 256), ("pubmed", 64), ("collab_s", 128), ("ddi_s", 64), ("citation2_s", 32)])
+def test_gnn_aggregation_bulk_gather(name, F, lib_options):
+    """The same checks with neighbour rows gathered by cp.async.bulk + mbarrier (k_spmm_tma), forced on."""
+    from ocn_b200 import _lib
+    lib_options(spmm_tma=1)
+    before = _lib.lib().ocn_launch_count()
+    _check_gnn_aggregation(name, F)
+    assert _lib.lib().ocn_launch_count() > before
+
+
+def _check_gnn_aggregation(name, F):
     g = GRAPHS[name]()
     G, A = _graph(g), _sp(g)
     x = g.features(F)
