@@ -106,7 +106,7 @@ def lib():
     return _lib
 
 
-OPTIONS = {"hub_window": 0, "hub_cta_window": 1, "hub_heavy_run": 2, "hub_walker": 3, "hub_seg_ctas": 4, "hub_exact": 5, "grouped_off": 6, "spgemm_mode": 7, "spmm_tma": 8}
+OPTIONS = {"hub_window": 0, "hub_cta_window": 1, "hub_heavy_run": 2, "hub_walker": 3, "hub_seg_ctas": 4, "hub_exact": 5, "grouped_off": 6, "spgemm_mode": 7, "spmm_tma": 8, "head_tc": 9}
 
 
 def set_option(name: str, value: int) -> None:
