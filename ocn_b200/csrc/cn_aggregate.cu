@@ -531,6 +531,7 @@ int ocn_cn_stats(const int64_t* rowptr, const int32_t* col, int64_t n, const int
                  int64_t batch_size, int order, int weighted, int variant, float fill, const float* ip, int stage,
                  const void* plan_scratch, const void* records, const void* colstat, float* batch_scalars,
                  const int64_t* plan_host, void* stream) {
+    OCN_RANGE("ocn_cn_stats");
     OCN_CHECK_ARG(rowptr && col && src && plan_scratch && colstat && batch_scalars, "ocn_cn_stats: null pointer");
     OCN_CHECK_ARG(num_edges > 0 && batch_size > 0 && n > 0, "ocn_cn_stats: sizes must be positive");
     OCN_CHECK_ARG(stage == 0 || stage == 1, "ocn_cn_stats: stage must be 0 or 1");
@@ -562,6 +563,7 @@ int ocn_cn_aggregate(const int64_t* rowptr, const int32_t* col, int64_t n, const
                      const float* ip, const void* plan_scratch, const void* records, const void* colstat,
                      const float* batch_scalars, const float* x, int64_t feat, float* xcn1, float* xcn2, float* xcn3,
                      float* xij, const int64_t* plan_host, void* stream) {
+    OCN_RANGE("ocn_cn_aggregate");
     OCN_CHECK_ARG(rowptr && col && src && dst && plan_scratch && colstat && batch_scalars && x && xcn1,
                   "ocn_cn_aggregate: null pointer");
     OCN_CHECK_ARG(num_edges > 0 && batch_size > 0 && n > 0, "ocn_cn_aggregate: sizes must be positive");
@@ -604,6 +606,7 @@ int ocn_cn_aggregate_bwd(const int64_t* rowptr, const int32_t* col, int64_t n, c
                          const void* colstat, const float* batch_scalars, const float* x, int64_t feat,
                          const float* g_xcn1, const float* g_xcn2, const float* g_xcn3, const float* g_xij,
                          float* grad_x, void* stream) {
+    OCN_RANGE("ocn_cn_aggregate_bwd");
     OCN_CHECK_ARG(rowptr && col && src && dst && plan_scratch && colstat && batch_scalars && grad_x,
                   "ocn_cn_aggregate_bwd: null pointer");
     OCN_CHECK_ARG(num_edges > 0 && batch_size > 0 && n > 0 && feat > 0, "ocn_cn_aggregate_bwd: sizes must be positive");
@@ -658,6 +661,7 @@ int ocn_cn_extract_fill(const int64_t* rowptr, const int32_t* col, int64_t n, co
 int ocn_cn_release(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, int64_t num_edges,
                    int64_t batch_size, const void* plan_scratch, const void* records, void* colstat,
                    const int64_t* plan_host, void* stream) {
+    OCN_RANGE("ocn_cn_release");
     OCN_CHECK_ARG(rowptr && col && src && plan_scratch && records && colstat, "ocn_cn_release: null pointer");
     OCN_CHECK_ARG(num_edges > 0 && batch_size > 0, "ocn_cn_release: sizes must be positive");
     cudaStream_t st = (cudaStream_t)stream;

@@ -728,6 +728,7 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
                             const void* plan_scratch, const int64_t* plan, void* records, int64_t records_capacity,
                             void* colstat, int64_t nnz, const int64_t* plan_host, void* hub_scratch,
                             size_t hub_scratch_bytes, void* node_scratch, void* stream) {
+    OCN_RANGE("ocn_cn_build");
     OCN_CHECK_ARG(rowptr && col && src && dst && plan_scratch && plan, "ocn_cn_build: null pointer");
     OCN_CHECK_ARG(order >= 1 && order <= 3, "ocn_cn_build: order must be 1, 2 or 3 (got %d)", order);
     OCN_CHECK_ARG(n > 0 && num_edges > 0 && batch_size > 0, "ocn_cn_build: sizes must be positive");

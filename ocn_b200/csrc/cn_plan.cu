@@ -294,6 +294,7 @@ size_t ocn_cn_record_bytes(void) { return sizeof(Record); }
 int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* src, const int64_t* dst, int64_t num_edges,
                 int64_t batch_size, int order, int64_t hub_degree, void* plan_scratch, size_t plan_scratch_bytes,
                 int64_t* out_plan, void* stream) {
+    OCN_RANGE("ocn_cn_plan");
     OCN_CHECK_ARG(rowptr && col && out_plan && plan_scratch, "ocn_cn_plan: null pointer");
     OCN_CHECK_ARG(n > 0 && num_edges > 0 && batch_size > 0, "ocn_cn_plan: n, num_edges and batch_size must be positive");
     OCN_CHECK_ARG(num_edges < (int64_t(1) << 30), "ocn_cn_plan: at most 2^30 links per call");

@@ -39,6 +39,14 @@ long long launch_count();
     } while (0)
 
 int sm_count();
+
+// NVTX range around an entry point (tracing): visible in Nsight Systems / ncu --nvtx, a no-op (one branch on a
+// cached flag inside the header-only nvtx3 shim) when no tool is attached
+struct NvtxRange {
+    explicit NvtxRange(const char* name);
+    ~NvtxRange();
+};
+#define OCN_RANGE(name) ::ocn::NvtxRange _ocn_range_(name)
 int64_t option(int key, int64_t dflt);  // ocn_set_option value, or dflt when unset (0)
 int set_option(int key, int64_t value);
 

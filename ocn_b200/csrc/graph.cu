@@ -3,9 +3,14 @@
 
 #include <atomic>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace ocn {
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 std::string& last_error() {
     static thread_local std::string s;
@@ -259,6 +264,7 @@ int ocn_rows_intersect_count(const int64_t* rowptr1, const int32_t* col1, int64_
 int ocn_rows_intersect_fill(const int64_t* rowptr1, const int32_t* col1, int64_t n1, const int64_t* rowptr2,
                             const int32_t* col2, int64_t n2, const int64_t* src, const int64_t* dst, int64_t num_edges,
                             const int64_t* out_rowptr, int64_t* out_col, void* stream) {
+    OCN_RANGE("ocn_rows_intersect_fill");
     OCN_CHECK_ARG(rowptr1 && rowptr2 && num_edges >= 0, "ocn_rows_intersect_fill: bad arguments");
     if (num_edges == 0) return OCN_OK;
     OCN_CHECK_ARG(src && dst && out_rowptr, "ocn_rows_intersect_fill: null edge/out pointer");
@@ -287,6 +293,7 @@ int ocn_rows_difference_count(const int64_t* rowptr1, const int32_t* col1, int64
 int ocn_rows_difference_fill(const int64_t* rowptr1, const int32_t* col1, int64_t n1, const int64_t* rowptr2,
                              const int32_t* col2, int64_t n2, const int64_t* src, const int64_t* dst, int64_t num_edges,
                              const int64_t* out_rowptr, int64_t* out_col, void* stream) {
+    OCN_RANGE("ocn_rows_difference_fill");
     OCN_CHECK_ARG(rowptr1 && rowptr2 && num_edges >= 0, "ocn_rows_difference_fill: bad arguments");
     if (num_edges == 0) return OCN_OK;
     OCN_CHECK_ARG(src && dst && out_rowptr, "ocn_rows_difference_fill: null edge/out pointer");

@@ -293,6 +293,7 @@ int ocn_graph_build_count(const int64_t* src, const int64_t* dst, const uint8_t*
 
 int ocn_graph_build_fill(const void* scratch, int64_t num_edges, int symmetric, int64_t n, int64_t nnz, int32_t* out_col,
                          int32_t* out_mult, void* stream) {
+    OCN_RANGE("ocn_graph_build_fill");
     OCN_CHECK_ARG(scratch && nnz >= 0 && n > 0, "ocn_graph_build_fill: bad arguments");
     if (nnz == 0) return OCN_OK;
     OCN_CHECK_ARG(out_col, "ocn_graph_build_fill: null output");
@@ -344,6 +345,7 @@ int ocn_graph_mask_count(const int64_t* rowptr, const int32_t* col, const int32_
 int ocn_graph_mask_fill(const int64_t* rowptr, const int32_t* col, const int32_t* mult, int64_t n, int64_t nnz,
                         const int64_t* src, const int64_t* dst, int64_t num_masked, int symmetric, int32_t* dec,
                         const void* scratch, int32_t* out_col, int32_t* out_mult, void* stream) {
+    OCN_RANGE("ocn_graph_mask_fill");
     OCN_CHECK_ARG(rowptr && dec && scratch && (col || nnz == 0), "ocn_graph_mask_fill: null pointer");
     OCN_CHECK_ARG(n > 0 && nnz >= 0 && num_masked >= 0, "ocn_graph_mask_fill: bad arguments");
     const MaskLayout L = mask_layout(num_masked);

@@ -196,6 +196,7 @@ int64_t ocn_cn_head_params(int in_ch, int hid, int out_ch, int flags, int branch
 int ocn_cn_head(const float* xcn1, const float* xcn2, const float* xcn3, const float* xij, int64_t num_links, int in_ch,
                 int hid, int out_ch, int flags, const float* params, int64_t params_len, const float* mix, float* out,
                 void* stream) {
+    OCN_RANGE("ocn_cn_head");
     OCN_CHECK_ARG(num_links >= 0, "ocn_cn_head: bad sizes");
     if (num_links == 0) return OCN_OK;
     OCN_CHECK_ARG(xcn1 && xcn2 && xij && params && mix && out, "ocn_cn_head: null pointer");

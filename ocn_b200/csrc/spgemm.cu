@@ -483,6 +483,7 @@ static int dense_structure(const int64_t* rowptr, const int32_t* col, int64_t n,
 
 int ocn_spgemm_a2_symbolic(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t nnz, int64_t fold, void* scratch,
                            int64_t* out_row_nnz, void* stream) {
+    OCN_RANGE("ocn_spgemm_a2_symbolic");
     OCN_CHECK_ARG(rowptr && col && scratch && out_row_nnz, "ocn_spgemm_a2_symbolic: null pointer");
     OCN_CHECK_ARG(n > 0 && nnz >= 0 && fold >= 0, "ocn_spgemm_a2_symbolic: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
@@ -512,6 +513,7 @@ int ocn_spgemm_a2_symbolic(const int64_t* rowptr, const int32_t* col, int64_t n,
 
 int ocn_spgemm_a2_numeric(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t nnz, int64_t fold, void* scratch,
                           const int64_t* out_rowptr, int32_t* out_col, float* out_val, void* stream) {
+    OCN_RANGE("ocn_spgemm_a2_numeric");
     OCN_CHECK_ARG(rowptr && col && scratch && out_rowptr && out_col, "ocn_spgemm_a2_numeric: null pointer");
     OCN_CHECK_ARG(n > 0 && nnz >= 0 && fold >= 0, "ocn_spgemm_a2_numeric: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;

@@ -465,6 +465,7 @@ extern "C" {
 
 int ocn_spmm_csr(const int64_t* rowptr, const int32_t* col, const float* val, int64_t num_rows, const float* x,
                  int64_t feat, int reduce, float* out, void* stream) {
+    OCN_RANGE("ocn_spmm_csr");
     OCN_CHECK_ARG(rowptr && x && out, "ocn_spmm_csr: null pointer");
     OCN_CHECK_ARG(num_rows >= 0 && feat > 0, "ocn_spmm_csr: bad sizes");
     OCN_CHECK_ARG(reduce >= 0 && reduce <= 2, "ocn_spmm_csr: reduce must be 0 (sum), 1 (mean) or 2 (max)");
@@ -474,6 +475,7 @@ int ocn_spmm_csr(const int64_t* rowptr, const int32_t* col, const float* val, in
 
 int ocn_spmm_csr_bwd(const int64_t* rowptr, const int32_t* col, const float* val, int64_t num_rows,
                      const float* grad_out, int64_t feat, int reduce, float* grad_x, void* stream) {
+    OCN_RANGE("ocn_spmm_csr_bwd");
     OCN_CHECK_ARG(rowptr && grad_out && grad_x, "ocn_spmm_csr_bwd: null pointer");
     OCN_CHECK_ARG(num_rows >= 0 && feat > 0, "ocn_spmm_csr_bwd: bad sizes");
     OCN_CHECK_ARG(reduce == 0 || reduce == 1, "ocn_spmm_csr_bwd: reduce must be 0 (sum) or 1 (mean)");
@@ -512,6 +514,7 @@ int ocn_gcn_norm(const int64_t* rowptr, const float* edge_w, int64_t n, float* o
 
 int ocn_gcn_spmm(const int64_t* rowptr, const int32_t* col, const float* edge_w, int64_t n, const float* norm,
                  int mode, const float* x, int64_t feat, float* out, void* stream) {
+    OCN_RANGE("ocn_gcn_spmm");
     OCN_CHECK_ARG(rowptr && norm && x && out, "ocn_gcn_spmm: null pointer");
     OCN_CHECK_ARG(mode == kGcnSelf || mode == kGcnNoSelf, "ocn_gcn_spmm: mode must be 3 (self term) or 4 (no self term)");
     OCN_CHECK_ARG(n >= 0 && feat > 0, "ocn_gcn_spmm: bad sizes");

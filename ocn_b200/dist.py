@@ -63,12 +63,35 @@ def deal_by_cost(costs: Sequence[int], world: int, per_rank: int) -> List[List[i
 
 def gather_scores(local_scores: Sequence[torch.Tensor], owned: Sequence[Tuple[int, int]], num_links: int) -> torch.Tensor:
     """All ranks contribute the scores of their batches; every rank receives the full [num_links] vector
-    in link order (fp32, 4 B per link over NCCL/NVLink, or gloo on CPU)."""
+    in link order (fp32, 4 B per link over NCCL/NVLink, or gloo on CPU).
+
+    One ``all_gather`` of the ranks' [start, end) lists (a few integers) and one ``all_gather_into_tensor`` of the
+    scores, padded to the longest rank: every link travels once (an all-reduce of a zero-padded full-length vector, the
+    first version, moved ``world`` times as much)."""
     dev = local_scores[0].device if len(local_scores) else torch.device("cpu")
-    full = torch.zeros(num_links, dtype=torch.float32, device=dev)
-    for sc, (s, e) in zip(local_scores, owned):
-        full[s:e] = sc.reshape(-1).float()
-    _all_reduce_sum(full)  # disjoint supports: a sum is a gather in link order
+    world = _world()
+    mine = torch.cat([sc.reshape(-1).float() for sc in local_scores]) if len(local_scores) else torch.zeros(0, device=dev)
+    full = torch.empty(num_links, dtype=torch.float32, device=dev)
+    if world <= 1:
+        o = 0
+        for (s, e) in owned:
+            full[s:e] = mine[o:o + (e - s)]
+            o += e - s
+        return full
+    ranges = [None] * world
+    dist.all_gather_object(ranges, [(int(s), int(e)) for (s, e) in owned])
+    longest = max(sum(e - s for (s, e) in r) for r in ranges)
+    host_hop = mine.is_cuda and dist.get_backend() == "gloo"     # (CPU tests, or two ranks sharing one GPU)
+    send = torch.zeros(longest, dtype=torch.float32, device="cpu" if host_hop else dev)
+    send[:mine.numel()] = mine
+    recv = torch.empty(world * longest, dtype=torch.float32, device=send.device)
+    dist.all_gather_into_tensor(recv, send)
+    recv = recv.to(dev).view(world, longest)
+    for r, rr in enumerate(ranges):
+        o = 0
+        for (s, e) in rr:
+            full[s:e] = recv[r, o:o + (e - s)]
+            o += e - s
     return full
 
 
@@ -136,10 +159,20 @@ def allreduce_gradients(tensors: Iterable[torch.Tensor]) -> None:
     for t in ts:
         if t.grad is None:
             t.grad = torch.zeros_like(t)
-    flat = torch.cat([t.grad.reshape(-1).float() for t in ts])
+    # large gradients (the [N, F] gradient of the detached embedding: 375 MB at citation2 shape, F = 32) are reduced in
+    # place, one collective each; the predictor's many small tensors share one flat bucket
+    small = []
+    for t in ts:
+        if t.grad.numel() >= (1 << 18) and t.grad.is_contiguous() and t.grad.dtype == torch.float32:
+            _all_reduce_sum(t.grad)
+        else:
+            small.append(t)
+    if not small:
+        return
+    flat = torch.cat([t.grad.reshape(-1).float() for t in small])
     _all_reduce_sum(flat)
     o = 0
-    for t in ts:
+    for t in small:
         k = t.numel()
         t.grad.copy_(flat[o:o + k].view_as(t.grad))
         o += k
