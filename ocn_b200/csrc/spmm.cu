@@ -229,6 +229,106 @@ __global__ void k_gcn_norm(const int64_t* __restrict__ rowptr, const float* __re
     }
 }
 
+// ---- lane-per-feature variant (F = 32 / 64 / 128 / 256) -----------------------------------------------------------------
+// k_spmm above covers a feature row with few lanes (float4 each) and gathers several neighbour rows per load
+// instruction; at F = 32 that costs shuffles, a butterfly reduction per output row and idle lane groups on short rows
+// (ncu, citation2 shape: 21 warp instructions per neighbour row, 42 % issue slots at 33 % occupancy), at F = 128 it
+// leaves two loads in flight per lane.  Here a lane owns VEC = F / 32 consecutive features of EVERY neighbour row:
+// a neighbour costs one coalesced load instruction per warp (128 x VEC bytes) and VEC FMAs, kU neighbour rows are
+// requested before the first is consumed, there is no cross-lane reduction and the output row is one coalesced store.
+template <int VEC, int kU>
+__global__ void __launch_bounds__(256)
+k_spmm_lane(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+            const float* __restrict__ norm, int64_t num_rows, const float* __restrict__ x, int mode, float* __restrict__ out) {
+    constexpr int F = 32 * VEC;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    const bool is_max = mode == kMax, gcn = mode >= kGcnSelf;
+    auto load_ptr = [&](int64_t rr, int64_t& s, int64_t& e) {
+        s = 0; e = 0;
+        if (rr < num_rows) { s = ldg_i64(rowptr + rr); e = ldg_i64(rowptr + rr + 1); }
+    };
+    auto load_cols = [&](int64_t at, int64_t e, int32_t& c, float& w) {
+        c = 0; w = 0.f;
+        if (at + lane < e) { c = ldg_i32(col + at + lane); w = val ? __ldg(val + at + lane) : 1.0f; }
+    };
+    auto load_vec = [&](int32_t c, float (&v)[VEC]) {
+        const float* p = x + (int64_t)c * F + lane * VEC;
+        if (VEC == 1) { v[0] = __ldg(p); }
+        else if (VEC == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y; }
+        else {
+#pragma unroll
+            for (int q = 0; q < VEC; q += 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p + q));
+                v[q] = t.x; v[q + 1] = t.y; v[q + 2] = t.z; v[q + 3] = t.w;
+            }
+        }
+    };
+    int64_t s1, e1, s2, e2;
+    int32_t c1;
+    float w1;
+    load_ptr(warp, s1, e1);
+    load_ptr(warp + nwarps, s2, e2);
+    load_cols(s1, e1, c1, w1);
+    for (int64_t r = warp; r < num_rows; r += nwarps) {
+        int64_t s3, e3;
+        load_ptr(r + 2 * nwarps, s3, e3);
+        int32_t c2;
+        float w2;
+        load_cols(s2, e2, c2, w2);
+        const int64_t s = s1, e = e1;
+        const float nr = gcn ? __ldg(norm + r) : 1.0f;
+        float self[VEC];
+        if (mode == kGcnSelf) load_vec((int32_t)r, self);   // requested now, used after the neighbours
+        float acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = is_max ? -FLT_MAX : 0.f;
+        for (int64_t base = s; base < e; base += 32) {
+            int32_t c = c1;
+            float w = w1;
+            if (base != s) load_cols(base, e, c, w);
+            const int cnt = (int)((e - base) < 32 ? (e - base) : 32);
+            const float nc = (gcn && lane < cnt) ? __ldg(norm + c) : 1.0f;   // D^-1/2 of this lane's neighbour: used after the x loads are out
+            for (int j = 0; j < cnt; j += kU) {
+                float xv[kU][VEC];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int32_t cc = __shfl_sync(0xffffffffu, c, (j + u) & 31);
+                    if (j + u < cnt) load_vec(cc, xv[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const float ww = __shfl_sync(0xffffffffu, w * nc, (j + u) & 31);
+                    if (j + u < cnt) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) acc[v] = is_max ? fmaxf(acc[v], ww * xv[u][v]) : fmaf(ww, xv[u][v], acc[v]);
+                    }
+                }
+            }
+        }
+        float* o = out + r * F + lane * VEC;
+        float res[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float a = acc[v];
+            if (is_max && e == s) a = 0.f;
+            if (mode == kMean) a *= 1.0f / (float)((e - s) > 0 ? (e - s) : 1);
+            else if (mode == kGcnSelf) a = nr * (a + nr * self[v]);
+            else if (mode == kGcnNoSelf) a = nr * a;
+            res[v] = a;
+        }
+        if (VEC == 1) o[0] = res[0];
+        else if (VEC == 2) *reinterpret_cast<float2*>(o) = make_float2(res[0], res[1]);
+        else {
+#pragma unroll
+            for (int q = 0; q < VEC; q += 4) *reinterpret_cast<float4*>(o + q) = make_float4(res[q], res[q + 1], res[q + 2], res[q + 3]);
+        }
+        s1 = s2; e1 = e2; c1 = c2; w1 = w2;
+        s2 = s3; e2 = e3;
+    }
+}
+
 // ---- TMA-gather variant -------------------------------------------------------------------------------------------
 // The gather of neighbour rows is latency-bound on a randomly labelled graph (ncu, citation2 shape, F = 32: DRAM 15 % busy,
 // L2 hit 36 %): what limits it is the number of bytes a warp keeps in flight.  Here every lane hands ONE whole neighbour
@@ -425,12 +525,12 @@ static int launch_spmm_tma(const int64_t* rowptr, const int32_t* col, const floa
 
 static int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* val, const float* norm,
                        int64_t num_rows, const float* x, int64_t feat, int mode, float* out, cudaStream_t st) {
-    // TMA gather (OCN_OPT_SPMM_TMA: 0 automatic, 1 on where it applies, 2 off): whole feature rows of 32 / 64 / 128 / 256
+    // OCN_OPT_SPMM_TMA: 0 automatic, 1 bulk (TMA) gather where it applies, 2 register gather, 3 lane-per-feature gather
+    // (measured behind both: profiles/r02_ab_spmm_v3.txt).  Bulk gather: whole feature rows of 32 / 64 / 128 / 256
     // floats, 16-byte aligned, every reduction but max
     int64_t tma = option(OCN_OPT_SPMM_TMA, 0);
     if (tma == 0)  // automatic: where the one-GPU A/B (profiles/r02_ab_spmm_tma.txt) has the bulk gather ahead
-        tma = (num_rows >= 100000 && (((feat == 64 || feat == 128) && (mode == kSum || mode == kMean)) ||
-                                      (feat == 64 && mode == kGcnSelf))) ? 1 : 2;
+        tma = (num_rows >= 100000 && feat == 128 && (mode == kSum || mode == kMean)) ? 1 : 2;
     if (tma == 1 && mode != kMax && (feat == 32 || feat == 64 || feat == 128 || feat == 256) &&
         (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
         if (feat == 32) return launch_spmm_tma<1>(rowptr, col, val, norm, num_rows, x, mode, out, st);
@@ -441,6 +541,14 @@ static int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* v
     int64_t want = (num_rows + 7) / 8;
     int64_t cap = (int64_t)sm_count() * 16;
     const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    if (tma == 3 && (feat == 32 || feat == 64 || feat == 128 || feat == 256) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        if (feat == 32) k_spmm_lane<1, 8><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, mode, out);
+        else if (feat == 64) k_spmm_lane<2, 8><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, mode, out);
+        else if (feat == 128) k_spmm_lane<4, 4><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, mode, out);
+        else k_spmm_lane<8, 2><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, mode, out);
+        OCN_LAUNCH_CHECK();
+        return OCN_OK;
+    }
     if (feat % 4 != 0 || feat > 1024) {
         k_spmm_scalar<<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, feat, mode, out);
     } else {

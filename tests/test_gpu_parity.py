@@ -284,6 +284,13 @@ def test_gnn_aggregation_bulk_gather(name, F, lib_options):
     assert _lib.lib().ocn_launch_count() > before
 
 
+@pytest.mark.parametrize("name,F", [("cora", 256), ("pubmed", 64), ("collab_s", 128), ("ddi_s", 64), ("citation2_s", 32)])
+def test_gnn_aggregation_lane_per_feature(name, F, lib_options):
+    """The same checks on k_spmm_lane (a lane owns F / 32 features of every neighbour row), forced on."""
+    lib_options(spmm_tma=3)
+    _check_gnn_aggregation(name, F)
+
+
 def _check_gnn_aggregation(name, F):
     g = GRAPHS[name]()
     G, A = _graph(g), _sp(g)

@@ -95,3 +95,21 @@ def test_shim_exposes_every_recorded_name_and_has_no_cpu_path():
     finally:
         shim.uninstall()
     assert sys.modules.get("torch_sparse") is before
+
+
+REF = os.environ.get("OCN_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "model.py")), reason="the reference's files are not on this machine")
+def test_reference_modules_import_and_build_over_the_shim():
+    """The reference's own model.py / utils.py import against the stand-ins and its classes construct (no compute: CPU)."""
+    import subprocess
+    code = (
+        "import sys; sys.path.insert(0, %r); import ocn_b200.shim as shim; shim.install(force=True); sys.path.insert(0, %r);\n"
+        "import model, utils; shim.accelerate(utils, model)\n"
+        "assert model.adjoverlap.__wrapped__ is not None and utils.adjoverlap is model.adjoverlap\n"
+        "for k in ('cn2', 'cn3', 'cn4', 'cn5', 'cn6', 'cn7'): model.predictor_dict[k](64, 64, 1, 3, 0.0)\n"
+        "for fn in ('gcn', 'gin', 'sage', 'max', 'puregcn'): model.GCN(8, 8, 8, 2, 0.0, conv_fn=fn)\n"
+        "print('ok')\n") % (ROOT, REF)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
