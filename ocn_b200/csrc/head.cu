@@ -169,7 +169,7 @@ k_cn_head(const float* __restrict__ xcn1, const float* __restrict__ xcn2, const 
 }
 
 int launch_head_tc(const float* xcn1, const float* xcn2, const float* xcn3, const float* xij, int64_t num_links, int out_ch,
-                   int flags, const float* params, const float* mix, float* out, cudaStream_t st);  // head_tc.cu
+                   int flags, const float* params, const float* mix, float* out, cudaStream_t st, int variant);  // head_tc.cu
 
 static int64_t head_params(int in_ch, int hid, int out_ch, int flags, int branches) {
     const bool ln = flags & 1, tailact = flags & 2, two = flags & 4;
@@ -206,9 +206,10 @@ int ocn_cn_head(const float* xcn1, const float* xcn2, const float* xcn3, const f
     OCN_CHECK_ARG(params_len == want, "ocn_cn_head: parameter buffer holds %lld floats, expected %lld", (long long)params_len,
                   (long long)want);
     cudaStream_t st = (cudaStream_t)stream;
-    // in = hidden = 32: tcgen05 kernel (head_tc.cu) unless OCN_OPT_HEAD_TC == 2; the CUDA-core kernel below otherwise
-    if (in_ch == 32 && hid == 32 && option(OCN_OPT_HEAD_TC, 1) == 1)
-        return launch_head_tc(xcn1, xcn2, xcn3, xij, num_links, out_ch, flags, params, mix, out, st);
+    // in = hidden = 32: tcgen05 kernel (head_tc.cu; OCN_OPT_HEAD_TC 0 / 3: four pipelines per SM, activations through
+    // tensor memory; 1: two pipelines, activations through shared memory) unless OCN_OPT_HEAD_TC == 2 (CUDA-core kernel below)
+    if (in_ch == 32 && hid == 32 && option(OCN_OPT_HEAD_TC, 3) != 2)
+        return launch_head_tc(xcn1, xcn2, xcn3, xij, num_links, out_ch, flags, params, mix, out, st, (int)option(OCN_OPT_HEAD_TC, 3));
     const size_t smem = sizeof(float) * (size_t)((params_len + 3) & ~int64_t(3));
     const int64_t groups = (num_links + kLinks - 1) / kLinks;
     int64_t blocks = (groups + (kHeadThreads / 32) - 1) / (kHeadThreads / 32);

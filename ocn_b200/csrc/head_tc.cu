@@ -18,7 +18,6 @@
 namespace ocn {
 namespace htc {
 
-constexpr int kGroups = 2;    // independent 128-link pipelines per CTA
 constexpr int kTile = 128;
 constexpr int H = 32;
 constexpr int kMat = H * H;                    // floats of one matrix
@@ -46,6 +45,27 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
         : "memory");
 }
 
@@ -99,10 +119,15 @@ __host__ __device__ inline int head_tc_mats(int flags, int branches, int* off, i
     return n;
 }
 
+// kGroups independent 128-link pipelines per CTA.  kATmem: the activations are the A operand FROM TENSOR MEMORY (written
+// with tcgen05.st, no shared-memory tile, no proxy fence), which leaves room for four pipelines per SM.
+template <int kGroups, bool kATmem>
 __global__ void __launch_bounds__(kGroups * kTile, 1)
 k_cn_head_tc(const float* __restrict__ xcn1, const float* __restrict__ xcn2, const float* __restrict__ xcn3,
              const float* __restrict__ xij, int64_t B, int out_ch, int flags, const float* __restrict__ params,
              const float* __restrict__ mix, float* __restrict__ out) {
+    constexpr int kColsPerGroup = kATmem ? 3 * H : H;                    // D (+ A hi, A lo)
+    constexpr int kCols = kGroups * kColsPerGroup <= 64 ? 64 : (kGroups * kColsPerGroup <= 128 ? 128 : (kGroups * kColsPerGroup <= 256 ? 256 : 512));
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) unsigned long long s_bar[kGroups];
@@ -138,7 +163,7 @@ k_cn_head_tc(const float* __restrict__ xcn1, const float* __restrict__ xcn2, con
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&s_bar[tid])), "r"(1) : "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem)), "r"(64)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem)), "r"(kCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -148,9 +173,11 @@ k_cn_head_tc(const float* __restrict__ xcn1, const float* __restrict__ xcn2, con
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem;
-    const uint32_t d_tmem = tmem_base + (uint32_t)(g * H);                              // this group's accumulator columns
-    const uint32_t ld_addr = d_tmem + ((uint32_t)((warp & 3) * 32) << 16);              // this warp's 32 lanes
-    float* A_hi = Asm + (size_t)g * 2 * kTile * H;
+    const uint32_t d_tmem = tmem_base + (uint32_t)(g * kColsPerGroup);                  // this group's accumulator columns
+    const uint32_t lanes = (uint32_t)((warp & 3) * 32) << 16;                           // this warp's 32 lanes
+    const uint32_t ld_addr = d_tmem + lanes;
+    const uint32_t a_hi_t = d_tmem + H, a_lo_t = d_tmem + 2 * H;                        // (kATmem) the A operand's columns
+    float* A_hi = Asm + (kATmem ? (size_t)0 : (size_t)g * 2 * kTile * H);   // (unused with kATmem: no tile is allocated)
     float* A_lo = A_hi + kTile * H;
     // descriptors are built once; a K step (8 tf32 = two 16-byte chunks) and a matrix advance the start-address field only
     const uint64_t a_hi_d = make_desc(smem_addr(A_hi)), a_lo_d = make_desc(smem_addr(A_lo)), w_d0 = make_desc(smem_addr(Wsm));
@@ -162,29 +189,53 @@ k_cn_head_tc(const float* __restrict__ xcn1, const float* __restrict__ xcn2, con
 
     // v <- v . W_m^T + bias (bias at params[moff[m] + kMat ..])
     auto linear = [&](float (&v)[32], int m) {
+        if (kATmem) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float4 hi, lo;
-            hi.x = __uint_as_float(__float_as_uint(v[4 * c]) & 0xffffe000u);     lo.x = v[4 * c] - hi.x;
-            hi.y = __uint_as_float(__float_as_uint(v[4 * c + 1]) & 0xffffe000u); lo.y = v[4 * c + 1] - hi.y;
-            hi.z = __uint_as_float(__float_as_uint(v[4 * c + 2]) & 0xffffe000u); lo.z = v[4 * c + 2] - hi.z;
-            hi.w = __uint_as_float(__float_as_uint(v[4 * c + 3]) & 0xffffe000u); lo.w = v[4 * c + 3] - hi.w;
-            const int o = core_off(tg, 4 * c);
-            *reinterpret_cast<float4*>(A_hi + o) = hi;
-            *reinterpret_cast<float4*>(A_lo + o) = lo;
+            for (int half = 0; half < 2; ++half) {
+                float hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    hi[j] = __uint_as_float(__float_as_uint(v[16 * half + j]) & 0xffffe000u);
+                    lo[j] = v[16 * half + j] - hi[j];
+                }
+                tmem_st16(a_hi_t + lanes + 16 * half, hi);
+                tmem_st16(a_lo_t + lanes + 16 * half, lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 hi, lo;
+                hi.x = __uint_as_float(__float_as_uint(v[4 * c]) & 0xffffe000u);     lo.x = v[4 * c] - hi.x;
+                hi.y = __uint_as_float(__float_as_uint(v[4 * c + 1]) & 0xffffe000u); lo.y = v[4 * c + 1] - hi.y;
+                hi.z = __uint_as_float(__float_as_uint(v[4 * c + 2]) & 0xffffe000u); lo.z = v[4 * c + 2] - hi.z;
+                hi.w = __uint_as_float(__float_as_uint(v[4 * c + 3]) & 0xffffe000u); lo.w = v[4 * c + 3] - hi.w;
+                const int o = core_off(tg, 4 * c);
+                *reinterpret_cast<float4*>(A_hi + o) = hi;
+                *reinterpret_cast<float4*>(A_lo + o) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(kTile) : "memory");
         if (tg == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t whi = w_d0 + (uint64_t)m * 2u * kMatD, wlo = whi + kMatD;
+            if (kATmem) {
 #pragma unroll
-            for (int j = 0; j < H / 8; ++j) mma_tf32(d_tmem, a_hi_d + j * kStepD, whi + j * kStepD, j > 0 ? 1u : 0u);
+                for (int j = 0; j < H / 8; ++j) mma_tf32_ts(d_tmem, a_hi_t + 8 * j, whi + j * kStepD, j > 0 ? 1u : 0u);
 #pragma unroll
-            for (int j = 0; j < H / 8; ++j) mma_tf32(d_tmem, a_lo_d + j * kStepD, whi + j * kStepD, 1u);
+                for (int j = 0; j < H / 8; ++j) mma_tf32_ts(d_tmem, a_lo_t + 8 * j, whi + j * kStepD, 1u);
 #pragma unroll
-            for (int j = 0; j < H / 8; ++j) mma_tf32(d_tmem, a_hi_d + j * kStepD, wlo + j * kStepD, 1u);
+                for (int j = 0; j < H / 8; ++j) mma_tf32_ts(d_tmem, a_hi_t + 8 * j, wlo + j * kStepD, 1u);
+            } else {
+#pragma unroll
+                for (int j = 0; j < H / 8; ++j) mma_tf32(d_tmem, a_hi_d + j * kStepD, whi + j * kStepD, j > 0 ? 1u : 0u);
+#pragma unroll
+                for (int j = 0; j < H / 8; ++j) mma_tf32(d_tmem, a_lo_d + j * kStepD, whi + j * kStepD, 1u);
+#pragma unroll
+                for (int j = 0; j < H / 8; ++j) mma_tf32(d_tmem, a_hi_d + j * kStepD, wlo + j * kStepD, 1u);
+            }
             mma_commit(bar);
         }
         bar_wait(bar, phase);
@@ -283,26 +334,37 @@ k_cn_head_tc(const float* __restrict__ xcn1, const float* __restrict__ xcn2, con
     __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kCols) : "memory");
     }
 }
 
 }  // namespace htc
 
 // in = hidden = 32 on the tensor cores; false when the shape is not served (the caller launches k_cn_head)
-int launch_head_tc(const float* xcn1, const float* xcn2, const float* xcn3, const float* xij, int64_t num_links, int out_ch,
-                   int flags, const float* params, const float* mix, float* out, cudaStream_t st) {
+template <int kGroups, bool kATmem>
+static int launch_head_tc_t(const float* xcn1, const float* xcn2, const float* xcn3, const float* xij, int64_t num_links,
+                            int out_ch, int flags, const float* params, const float* mix, float* out, cudaStream_t st) {
     using namespace htc;
     int moff[kMaxMats + 1], wo_off;
     const int nmat = head_tc_mats(flags, xcn3 ? 3 : 2, moff, &wo_off);
-    const size_t smem = sizeof(float) * ((size_t)nmat * 2 * kMat + (size_t)kGroups * 2 * kTile * H);
-    OCN_CUDA(cudaFuncSetAttribute(k_cn_head_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = sizeof(float) * ((size_t)nmat * 2 * kMat + (kATmem ? (size_t)0 : (size_t)kGroups * 2 * kTile * H));
+    OCN_CUDA(cudaFuncSetAttribute(k_cn_head_tc<kGroups, kATmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (num_links + kTile - 1) / kTile;
     int64_t blocks = (ntiles + kGroups - 1) / kGroups;
     if (blocks > sm_count()) blocks = sm_count();
-    k_cn_head_tc<<<(int)blocks, kGroups * kTile, smem, st>>>(xcn1, xcn2, xcn3, xij, num_links, out_ch, flags, params, mix, out);
+    k_cn_head_tc<kGroups, kATmem><<<(int)blocks, kGroups * kTile, smem, st>>>(xcn1, xcn2, xcn3, xij, num_links, out_ch, flags,
+                                                                              params, mix, out);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
+}
+
+// in = hidden = 32 on the tensor cores.  variant 1: two pipelines per SM, activations through shared memory; 3: four
+// pipelines, activations through tensor memory
+int launch_head_tc(const float* xcn1, const float* xcn2, const float* xcn3, const float* xij, int64_t num_links, int out_ch,
+                   int flags, const float* params, const float* mix, float* out, cudaStream_t st, int variant) {
+    if (variant == 3)
+        return launch_head_tc_t<4, true>(xcn1, xcn2, xcn3, xij, num_links, out_ch, flags, params, mix, out, st);
+    return launch_head_tc_t<2, false>(xcn1, xcn2, xcn3, xij, num_links, out_ch, flags, params, mix, out, st);
 }
 
 }  // namespace ocn

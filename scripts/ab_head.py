@@ -33,7 +33,7 @@ for cls, ln in (("cn6", False), ("cn6", True), ("cn5", False)):
 
     with torch.no_grad():
         res = {}
-        for name, opt, fuse in (("tcgen05", 1, True), ("cuda cores", 2, True), ("torch modules", 2, False)):
+        for name, opt, fuse in (("tcgen05", 1, True), ("tcgen05 A-in-TMEM x4", 3, True), ("cuda cores", 2, True), ("torch modules", 2, False)):
             _lib.set_option("head_tc", opt)
             pred.fuse_head = fuse
             out, ms = timed(lambda: pred._head(xs[0], xs[1], x3, xs[3]))

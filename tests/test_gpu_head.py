@@ -63,3 +63,24 @@ def test_parameter_cache_follows_updates():
         pred.lin[-1].bias.add_(1.0)
         b = pred._head(x, x, None, x)
     assert torch.allclose(b - a, torch.ones_like(a), atol=1e-5)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("cls,ln", [("cn5", False), ("cn6", True)])
+def test_head_kernel_variants_at_32(variant, cls, ln, lib_options):
+    """in = hidden = 32: tcgen05 with the activations through shared memory (1) / through tensor memory (3, the default)
+    and the CUDA-core kernel (2), each against the torch modules evaluated in float64, over several tiles per pipeline."""
+    import copy
+    lib_options(head_tc=variant)
+    torch.manual_seed(variant)
+    pred = ob.predictor_dict[cls](32, 32, 1, 3, 0.0, ln=ln).to(DEV).eval()
+    B = 148 * 4 * 128 * 2 + 77           # more than two rounds of tiles on every pipeline, ragged tail
+    xs = [torch.randn(B, 32, device=DEV) * s for s in (1.0, 3.0, 0.5, 2.0)]
+    x3 = xs[2] if cls == "cn6" else None
+    p64 = copy.deepcopy(pred).double()
+    p64.fuse_head = False
+    with torch.no_grad():
+        got = pred._head(xs[0], xs[1], x3, xs[3])
+        want = p64._head(xs[0].double(), xs[1].double(), None if x3 is None else x3.double(), xs[3].double())
+    err = (got.double() - want).abs().max().item()
+    assert err <= 5e-6 * (1.0 + want.abs().max().item()), err
