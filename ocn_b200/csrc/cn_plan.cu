@@ -181,8 +181,12 @@ k_plan_cost_long(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
 
 // the indexed path (cn_hub.cu) is used for order 3 when the stream has few runs (its run -> position table
 // lives in shared memory, and its index holds one entry per (position, neighbour of the position's node))
-__global__ void k_plan_hub_decide(int order, int64_t hub_degree, int64_t* __restrict__ plan) {
-    const bool fits = plan[OCN_PLAN_NUM_RUNS] <= kHubMaxRuns;
+// In automatic mode the stream must also HAVE runs: with one link per run (ungrouped links, the training shape) the
+// index holds a private neighbourhood per link and nothing is shared -- measured at citation2 shape, 2048 uniform links:
+// 6.6 ms indexed against 1.1 ms with the per-run tables (scripts/probe_uniform_order3.py).
+__global__ void k_plan_hub_decide(int order, int64_t hub_degree, int automatic, int64_t T, int64_t* __restrict__ plan) {
+    const int64_t runs = plan[OCN_PLAN_NUM_RUNS];
+    const bool fits = runs <= kHubMaxRuns && (!automatic || T >= 4 * runs);
     plan[OCN_PLAN_HUB_DEGREE] = (order >= 3 && hub_degree > 0 && fits) ? hub_degree : 0;
 }
 
@@ -323,6 +327,7 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
     int64_t* run_pos_heavy = (int64_t*)(base + L.run_pos_heavy);
     int64_t* pos_start = (int64_t*)(base + L.pos_start);
     int64_t* pos_scanN = (int64_t*)(base + L.pos_scanN);
+    const int automatic = hub_degree == 0;
     if (hub_degree == 0) {  // auto: share a row once about one link of the stream is expected to walk it
         hub_degree = (n + num_edges - 1) / num_edges;  // (citation2 shape, n/T = 45: flat optimum between 24 and 64)
         if (hub_degree < 32) hub_degree = 32;
@@ -334,7 +339,7 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
     OCN_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, run_id, run_id, (int)(T + 1), st));
     k_plan_runs<<<blocks, threads, 0, st>>>(rowptr, src, T, batch_size, run_id, run_start, out_plan);
     OCN_LAUNCH_CHECK();
-    k_plan_hub_decide<<<1, 1, 0, st>>>(order, hub_degree, out_plan);
+    k_plan_hub_decide<<<1, 1, 0, st>>>(order, hub_degree, automatic, T, out_plan);
     OCN_LAUNCH_CHECK();
     int blocks_w = (int)(((T + 1) * 32 + threads - 1) / threads);
     int32_t* chunk_off = (int32_t*)(base + L.chunk_off);
