@@ -324,6 +324,30 @@ def secondary(a, ob, synth, G, g, x, sampler, peak, dev):
         byt = 8 * (g.n + 1) + 4 * g.nnz + 4 * F * g.nnz + 4 * F * g.n
         measure(f"gnn_spmm_gcn_citation2_F{F}", lambda: ob.pure_conv(xf, G, "gcn", norm),
                 lambda ms: {"alg_GBs": byt / ms / 1e6, "frac_of_measured_hbm": byt / ms / 1e6 / peak})
+    xf = g.features(128, device=dev)
+    byt = 8 * (g.n + 1) + 4 * g.nnz + 4 * 128 * g.nnz + 4 * 128 * g.n
+    measure("gnn_spmm_sum_citation2_F128_bulk_gather", lambda: ob.pure_conv(xf, G, "sum"),
+            lambda ms: {"alg_GBs": byt / ms / 1e6, "frac_of_measured_hbm": byt / ms / 1e6 / peak,
+                        "kernel": "k_spmm_tma (cp.async.bulk + mbarrier)"})
+    del xf
+    byt = 8 * (g.n + 1) + 4 * g.nnz + 4 * a.feat * g.nnz + 4 * a.feat * g.n
+    measure(f"gnn_spmm_pureconv3_gcn_citation2_F{a.feat}", lambda: ob.pure_conv3_gcn(x, G, norm),
+            lambda ms: {"alg_GBs": byt / ms / 1e6, "frac_of_measured_hbm": byt / ms / 1e6 / peak})
+    # (1b) the predictor head of one session (65 536 links, cn6, in = hidden = 32): tensor cores against CUDA cores / torch
+    from ocn_b200 import _lib as _l
+    torch.manual_seed(0)
+    hp = ob.CNLinkPredictor3hopCNs(a.feat, a.feat, 1, 3, 0.0, weighted=True).to(dev).eval()
+    Th = a.batch * a.batches
+    hx = [torch.randn(Th, a.feat, device=dev) for _ in range(4)]
+    if a.feat == 32:
+        with torch.no_grad():
+            for label, opt, fuse in (("tcgen05", 3, True), ("cuda_cores", 2, True), ("torch_modules", 2, False)):
+                _l.set_option("head_tc", opt)
+                hp.fuse_head = fuse
+                measure(f"head_cn6_F32_{label}", lambda: hp._head(hx[0], hx[1], hx[2], hx[3]),
+                        lambda ms: {"links": Th, "us": ms * 1e3}, reps=5, warm=2)
+            _l.set_option("head_tc", 0)
+    del hp, hx
     # (2) order 2 on the same stream (get_cn1_cn2 as the reference's citation2 driver calls it)
     T = a.batch * a.batches
     e2 = g.stream_links(7 * T, 4 * T, device=dev)
