@@ -350,6 +350,20 @@ int ocn_cn_head(const float* xcn1, const float* xcn2, const float* xcn3, const f
                 int in_ch, int hid, int out_ch, int flags, const float* params, int64_t params_len,
                 const float* mix, float* out, void* stream);
 
+/* ---- wider heads: one fp32-accurate Linear layer with its element-wise tail on the tensor cores (csrc/linear_tc.cu) ----
+ * v = a[rows, k] . w[n, k]^T + bias; optional LayerNorm(gamma, beta, eps 1e-5); optional ReLU; then any of
+ *   out[rows, n] = v;   z[rows, n] = (z_accumulate ? z : 0) + z_scale * v;   out_final[rows, out_ch] = v . wo[out_ch, n]^T + bo
+ * (the layers of the nn.Sequential heads, model.py:2192-2235, 2429-2437, with the branch mix and the last Linear fused).
+ * n in {32, 64, 128, 256}, k a multiple of 32 (<= 1024).  `prepped` is w split hi + lo and laid out per 32-wide K chunk
+ * by ocn_linear_tc_prep (ocn_linear_tc_prep_floats(n, k) floats, -1 = shape not served); redo it when w changes.
+ * tcgen05.mma kind::tf32 with three products per K step: results agree with an fp32 GEMM to ~1e-6 relative. */
+int64_t ocn_linear_tc_prep_floats(int n, int k);
+int ocn_linear_tc_prep(const float* w, int n, int k, float* prepped, void* stream);
+int ocn_linear_tc(const float* a, int64_t rows, int k, int n, const float* prepped, const float* bias,
+                  const float* ln_gamma /* NULL = no LayerNorm */, const float* ln_beta, int relu,
+                  float* out /* or NULL */, float* z /* or NULL */, float z_scale, int z_accumulate,
+                  const float* wo /* or NULL */, const float* bo, int out_ch, float* out_final, void* stream);
+
 /* ---- the step after the path: ranking metrics on the device --------------------------
  * ogb Evaluator.eval as the drivers call it (NeighborOverlap_large.py:162-179: Hits@K over all positive /
  * negative scores of a split; NeighborOverlapCitation2.py:256-259: MRR of every source against its own

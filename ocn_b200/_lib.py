@@ -68,6 +68,9 @@ _SIGS = {
     "ocn_spgemm_a2_numeric": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P]),
     "ocn_cn_head_params": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "ocn_cn_head": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int64, _P, _P, _P]),
+    "ocn_linear_tc_prep_floats": (c_int64, [c_int, c_int]),
+    "ocn_linear_tc_prep": (c_int, [_P, c_int, c_int, _P, _P]),
+    "ocn_linear_tc": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, c_float, c_int, _P, _P, c_int, _P, _P]),
     "ocn_mrr": (c_int, [_P, _P, c_int64, c_int64, _P, _P]),
     "ocn_hits_bytes": (c_size_t, [c_int64]),
     "ocn_hits_at_k": (c_int, [_P, c_int64, _P, c_int64, c_int64, _P, c_size_t, _P, _P]),

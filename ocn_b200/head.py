@@ -97,3 +97,116 @@ def fused_head(pred, xcn1: Tensor, xcn2: Tensor, xcn3: Optional[Tensor], xij: Te
                                  in_ch, hid, out_ch, st["flags"], _lib.ptr(params), params.numel(), _lib.ptr(mix),
                                  _lib.ptr(out), _stream(xcn1.device)), "ocn_cn_head")
     return out
+
+
+# ---- wider heads: one tensor-core launch per Linear with its element-wise tail (csrc/linear_tc.cu) ------------------------
+
+def _layers(seq: nn.Sequential):
+    """[(Linear, LayerNorm or None, relu)] in module order (Dropout is the identity in eval mode, Identity is skipped)."""
+    out = []
+    for m in seq:
+        if isinstance(m, nn.Linear):
+            out.append([m, None, False])
+        elif isinstance(m, nn.LayerNorm):
+            out[-1][1] = m
+        elif isinstance(m, nn.ReLU):
+            out[-1][2] = True
+        elif not isinstance(m, (nn.Dropout, nn.Identity)):
+            raise TypeError(f"unexpected module in a predictor head: {type(m).__name__}")
+    return out
+
+
+def _wide_static(pred, in_ch: int):
+    st = pred.__dict__.get("_ocn_wide_static")
+    if st is None or st["in_ch"] != in_ch:
+        three = pred.order >= 3 and hasattr(pred, "xcn3lin")
+        names = [m for m in _HEAD_MODULES if m != "xcn3lin" or three]
+        plan = {m: _layers(getattr(pred, m)) for m in names}
+        L = _lib.lib()
+        ok = True
+        for m, layers in plan.items():
+            hidden = layers[:-1] if m == "lin" else layers
+            for lin, _, _ in hidden:
+                ok = ok and L.ocn_linear_tc_prep_floats(lin.out_features, lin.in_features) > 0
+        ok = ok and len(plan["lin"]) >= 2 and plan["lin"][-1][0].out_features <= 8
+        st = {"in_ch": in_ch, "plan": plan, "ok": bool(ok), "names": names}
+        pred.__dict__["_ocn_wide_static"] = st
+    return st
+
+
+def wide_supported(pred, in_ch: int) -> bool:
+    """Every Linear of the head but the last has 32 / 64 / 128 / 256 outputs and a multiple of 32 inputs."""
+    return _wide_static(pred, in_ch)["ok"]
+
+
+def _prepped(pred, lin: nn.Linear) -> Tensor:
+    """The weight of one Linear split and laid out for ocn_linear_tc; redone when the parameter changed."""
+    cache = pred.__dict__.setdefault("_ocn_wide_prepped", {})
+    key = (lin.weight.data_ptr(), lin.weight._version)
+    hit = cache.get(id(lin))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    L = _lib.lib()
+    n, k = lin.out_features, lin.in_features
+    w = lin.weight.detach().float().contiguous()
+    buf = torch.empty(L.ocn_linear_tc_prep_floats(n, k), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(L.ocn_linear_tc_prep(_lib.ptr(w), n, k, _lib.ptr(buf), _stream(w.device)), "ocn_linear_tc_prep")
+        torch.cuda.current_stream(w.device).synchronize()    # rare (a parameter changed): other streams may read the cache
+    cache[id(lin)] = (key, buf)
+    return buf
+
+
+def linear_tc(pred, x: Tensor, lin: nn.Linear, ln: Optional[nn.LayerNorm] = None, relu: bool = False, want_out: bool = True,
+              z: Optional[Tensor] = None, z_scale: float = 1.0, z_accumulate: bool = False,
+              final: Optional[nn.Linear] = None):
+    """One layer on the tensor cores: returns (out or None, out_final or None); ``z`` is updated in place."""
+    L = _lib.lib()
+    x = x.contiguous()
+    B, k = x.shape
+    n = lin.out_features
+    dev = x.device
+    out = torch.empty(B, n, dtype=torch.float32, device=dev) if want_out else None
+    fin = torch.empty(B, final.out_features, dtype=torch.float32, device=dev) if final is not None else None
+    f32 = lambda t: None if t is None else t.detach().float().contiguous()
+    bias, g, be = f32(lin.bias), f32(None if ln is None else ln.weight), f32(None if ln is None else ln.bias)
+    wo, bo = f32(None if final is None else final.weight), f32(None if final is None else final.bias)
+    with torch.cuda.device(dev):
+        _lib.check(L.ocn_linear_tc(_lib.ptr(x), B, k, n, _lib.ptr(_prepped(pred, lin)), _lib.ptr(bias), _lib.ptr(g), _lib.ptr(be),
+                                   int(relu), _lib.ptr(out), _lib.ptr(z), float(z_scale), int(z_accumulate), _lib.ptr(wo),
+                                   _lib.ptr(bo), 0 if final is None else final.out_features, _lib.ptr(fin), _stream(dev)),
+                   "ocn_linear_tc")
+    return out, fin
+
+
+def fused_head_wide(pred, xcn1: Tensor, xcn2: Tensor, xcn3: Optional[Tensor], xij: Tensor) -> Tensor:
+    """The head of ``fused_head`` for hidden widths up to 256: 11 - 13 ``ocn_linear_tc`` launches (bias / LayerNorm / ReLU,
+    the branch mix ``z += a_k * branch`` and the last Linear ride in the epilogues)."""
+    st = _wide_static(pred, xcn1.shape[1])
+    plan = st["plan"]
+    with torch.no_grad():
+        alpha = torch.sigmoid(pred.alpha).cumprod(-1)
+        mix = torch.cat((alpha[:3].float(), pred.beta.detach().float().reshape(1))).tolist()
+    B = xcn1.shape[0]
+    hid = plan["lin"][0][0].in_features
+    z = torch.empty(B, hid, dtype=torch.float32, device=xcn1.device)
+    first = True
+    for name, x, w in (("xcn1lin", xcn1, mix[0]), ("xcn2lin", xcn2, mix[1]), ("xcn3lin", xcn3, mix[2]), ("xijlin", xij, mix[3])):
+        if name not in plan:
+            continue
+        layers = plan[name]
+        t = x.float()
+        for k, (lin, ln, relu) in enumerate(layers):
+            if k == len(layers) - 1:
+                linear_tc(pred, t, lin, ln, relu, want_out=False, z=z, z_scale=w, z_accumulate=not first)
+                first = False
+            else:
+                t, _ = linear_tc(pred, t, lin, ln, relu)
+    layers = plan["lin"]
+    t = z
+    for k, (lin, ln, relu) in enumerate(layers[:-1]):
+        if k == len(layers) - 2:
+            _, out = linear_tc(pred, t, lin, ln, relu, want_out=False, final=layers[-1][0])
+            return out
+        t, _ = linear_tc(pred, t, lin, ln, relu)
+    raise AssertionError("unreachable")

@@ -178,13 +178,16 @@ class _OCNBase(nn.Module):
             sess.release()  # nothing will run backward through this session: hand the statistics buffer back
         return xcn1, xcn2, (xcn3 if xcn3.numel() else None), xij, sess
 
-    fuse_head = True  # inference: one fused kernel for hidden widths 32 / 64 (csrc/head.cu); else the torch modules
+    fuse_head = True  # inference: one fused kernel for hidden widths 32 / 64 (csrc/head.cu, head_tc.cu) ...
+    fuse_wide_head = True  # ... one tensor-core launch per layer up to hidden 256 (csrc/linear_tc.cu); else the torch modules
 
     def _head(self, xcn1, xcn2, xcn3, xij):
         if self.fuse_head and not self.training and not torch.is_grad_enabled() and xcn1.is_cuda:
             from . import head
             if head.supported(self, xcn1.shape[1]) > 0:
                 return head.fused_head(self, xcn1, xcn2, xcn3, xij)
+            if self.fuse_wide_head and xcn1.shape[0] >= 4096 and head.wide_supported(self, xcn1.shape[1]):  # (smaller: launch-bound)
+                return head.fused_head_wide(self, xcn1, xcn2, xcn3, xij)
         xij = self.xijlin(xij)
         xcn1 = self.xcn1lin(xcn1)
         xcn2 = self.xcn2lin(xcn2)

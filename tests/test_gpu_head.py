@@ -48,6 +48,11 @@ def test_unserved_widths_and_training_keep_the_modules():
     x = torch.randn(10, 256, device=DEV)
     with torch.no_grad():
         assert pred._head(x, x, None, x).shape == (10, 1)
+    odd = ob.CNLinkPredictorOringin(48, 48, 1, 3, 0.0).to(DEV).eval()      # not a multiple of 32 anywhere: torch modules
+    assert head.supported(odd, 48) == -1 and not head.wide_supported(odd, 48)
+    x = torch.randn(5000, 48, device=DEV)
+    with torch.no_grad():
+        assert odd._head(x, x, None, x).shape == (5000, 1)
     pred = ob.CNLinkPredictorOringin(32, 32, 1, 3, 0.0).to(DEV).train()
     x = torch.randn(10, 32, device=DEV, requires_grad=True)
     out = pred._head(x, x, None, x)
@@ -84,3 +89,42 @@ def test_head_kernel_variants_at_32(variant, cls, ln, lib_options):
         want = p64._head(xs[0].double(), xs[1].double(), None if x3 is None else x3.double(), xs[3].double())
     err = (got.double() - want).abs().max().item()
     assert err <= 5e-6 * (1.0 + want.abs().max().item()), err
+
+
+@pytest.mark.parametrize("cls,in_ch,hid,ln,tailact,two,out_ch", [
+    ("cn5", 64, 64, True, False, False, 1), ("cn6", 64, 64, False, True, True, 1), ("cn5", 128, 128, True, False, False, 1),
+    ("cn7", 256, 256, False, False, False, 1), ("cn5", 256, 256, True, False, True, 3), ("cn6", 128, 256, True, True, False, 1),
+    ("cn5", 256, 64, False, False, False, 2), ("cn5", 96, 128, True, False, False, 1)])
+def test_wide_head_on_the_tensor_cores(cls, in_ch, hid, ln, tailact, two, out_ch):
+    """ocn_linear_tc (tcgen05, hi/lo operand split, one launch per layer with its tail fused) against the torch modules in
+    float64: hidden 64 / 128 / 256, LayerNorm, tailact, twolayerlin, several outputs, inputs that are not a power of two."""
+    import copy
+    torch.manual_seed(in_ch + hid + out_ch)
+    pred = ob.predictor_dict[cls](in_ch, hid, out_ch, 3, 0.0, ln=ln, tailact=tailact, twolayerlin=two).to(DEV).eval()
+    with torch.no_grad():
+        pred.alpha.copy_(torch.tensor([0.3, -0.2, 1.1]))
+        pred.beta.fill_(0.7)
+    assert head.wide_supported(pred, in_ch)
+    B = 148 * 128 * 2 + 77                 # more tiles than resident CTAs, ragged tail
+    xs = [torch.randn(B, in_ch, device=DEV) * s for s in (1.0, 3.0, 0.5, 2.0)]
+    x3 = xs[2] if cls == "cn6" else None
+    p64 = copy.deepcopy(pred).double()
+    p64.fuse_head = False
+    with torch.no_grad():
+        got = head.fused_head_wide(pred, xs[0], xs[1], x3, xs[3])
+        want = p64._head(xs[0].double(), xs[1].double(), None if x3 is None else x3.double(), xs[3].double())
+        if head.supported(pred, in_ch) < 0:     # and it is what _head picks at this size
+            from ocn_b200 import _lib
+            before = _lib.lib().ocn_launch_count()
+            again = pred._head(xs[0], xs[1], x3, xs[3])
+            assert _lib.lib().ocn_launch_count() > before and torch.equal(again, got)
+    assert got.shape == want.shape == (B, out_ch)
+    err = (got.double() - want).abs().max().item()
+    assert err <= 1e-5 * (1.0 + want.abs().max().item()), err
+    # a parameter update reaches the cached split weights
+    with torch.no_grad():
+        pred.lin[0].weight.mul_(1.5)
+        p64.lin[0].weight.mul_(1.5)
+        got = head.fused_head_wide(pred, xs[0], xs[1], x3, xs[3])
+        want = p64._head(xs[0].double(), xs[1].double(), None if x3 is None else x3.double(), xs[3].double())
+    assert (got.double() - want).abs().max().item() <= 1e-5 * (1.0 + want.abs().max().item())
