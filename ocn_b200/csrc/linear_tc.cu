@@ -15,8 +15,9 @@
 //     core-matrix layout the descriptor names), so a chunk is ONE contiguous block of N x 256 bytes that one thread
 //     hands to the copy engine (cp.async.bulk -> shared memory, completion on an mbarrier): no thread touches a weight;
 //   * tcgen05.mma.cta_group::1.kind::tf32, M = 128, N, K = 8: hi.hi + lo.hi + hi.lo per K step (fp32 accuracy: the
-//     dropped lo.lo term is 2^-22 relative), accumulated in TMEM; two A buffers and two weight buffers, so staging chunk
-//     c + 1 overlaps the MMAs of chunk c (tcgen05.commit -> mbarrier frees a buffer);
+//     dropped lo.lo term is 2^-22 relative), accumulated in TMEM; two A buffers and a ring of 3 - 6 weight chunks, a fifth
+//     warp issues the copies and every MMA, so staging chunk c + 1 and the copies of chunks c + 2 .. overlap the MMAs of
+//     chunk c (tcgen05.commit -> mbarrier frees a buffer);
 //   * the tail runs out of TMEM with tcgen05.ld.32x32b.x32, 32 columns at a time, one thread per row: LayerNorm is two
 //     passes over the row's N accumulators, nothing is shuffled.
 #include "common.cuh"
@@ -108,21 +109,45 @@ __global__ void k_linear_tc_prep(const float* __restrict__ w, int n, int k, floa
     }
 }
 
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Stages of the weight ring (chunks of N x 256 bytes): N = 256 owns the SM (3 x 64 KB, all 512 tensor-memory columns);
+// narrower outputs leave room for two CTAs per SM (<= 96 KB and 256 columns each)
 template <int N>
-__global__ void __launch_bounds__(kRows)
+struct Ring {
+    static constexpr int kStages = N == 256 ? 3 : ((96 * 1024) / (N * 256) > 6 ? 6 : (96 * 1024) / (N * 256));
+    static constexpr int kPerSm = N == 256 ? 1 : 2;
+};
+
+// Warps 0-3: one thread per row (stage the A chunk into tensor memory, run the tail).  Warp 4, lane 0: the weight ring (bulk
+// copies two to five chunks ahead) and every MMA.  Measured and NOT kept (profiles/r02_ab_head_wide.txt): two threads per
+// row (column halves), stores through a shared-memory tile (4 rows x 128 bytes per instruction), every CTA starting K at
+// its own chunk -- none moved the layer time; with parts switched off (temporary switches) a 65 536 x 256 x 256 layer is
+// 29 us of staging + 20 us of MMAs + 36 us of tail that do not overlap yet (one accumulator, one set of row threads).
+// The roles meet on mbarriers only:
+//   wfull[s]  copy engine -> MMA issuer   (chunk landed)          wfree[s]  tcgen05.commit -> ring        (slot reusable)
+//   aready[b] 128 row threads -> issuer   (A chunk in TMEM)        afree[b]  tcgen05.commit -> row threads (A buffer reusable)
+//   dfull     tcgen05.commit -> row threads (tile accumulated)     dfree     128 row threads -> issuer     (tail has read D)
+template <int N>
+__global__ void __launch_bounds__(kRows + 32)
 k_linear_tc(const float* __restrict__ a, int64_t rows, int K, const float* __restrict__ prepped, const float* __restrict__ bias,
             const float* __restrict__ ln_g, const float* __restrict__ ln_b, int relu, float* __restrict__ out,
             float* __restrict__ z, float z_scale, int z_accumulate, const float* __restrict__ wo, const float* __restrict__ bo,
             int out_ch, float* __restrict__ out_final) {
+    constexpr int S = Ring<N>::kStages;
     constexpr int kCols = (N + 128 <= 256) ? 256 : 512;       // D (N) + two A buffers of hi 32 + lo 32
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
     constexpr uint32_t kChunkBytes = 2u * N * kKc * 4u;       // hi + lo of one K chunk
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint32_t s_tmem;
-    __shared__ __align__(8) unsigned long long s_bar[4];      // wfull[0], wfull[1], done[0], done[1]
+    __shared__ __align__(8) unsigned long long s_bar[2 * S + 6];   // wfull[S], wfree[S], aready[2], afree[2], dfull, dfree
     const int tid = threadIdx.x, warp = tid >> 5;
-    float* Wsm = reinterpret_cast<float*>(smem_raw);           // [2][2 * N * 32]
-    if (tid < 4) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&s_bar[tid])), "r"(1) : "memory");
+    if (tid < 2 * S + 6) {
+        const bool many = (tid == 2 * S || tid == 2 * S + 1 || tid == 2 * S + 5);     // aready[0..1], dfree: one arrival per row thread
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&s_bar[tid])), "r"(many ? kRows : 1) : "memory");
+    }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem)), "r"(kCols)
                      : "memory");
@@ -133,42 +158,84 @@ k_linear_tc(const float* __restrict__ a, int64_t rows, int K, const float* __res
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem;
-    const uint32_t lanes = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t d_tmem = tmem_base;
-    const uint32_t wfull[2] = {smem_addr(&s_bar[0]), smem_addr(&s_bar[1])};
-    const uint32_t done[2] = {smem_addr(&s_bar[2]), smem_addr(&s_bar[3])};
-    const uint32_t wsm_s[2] = {smem_addr(Wsm), smem_addr(Wsm) + kChunkBytes};
-    uint32_t wfull_phase[2] = {0u, 0u}, done_phase[2] = {0u, 0u};
-    bool pending[2] = {false, false};
+    const uint32_t bar0 = smem_addr(&s_bar[0]);
+    auto wfull = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto wfree = [&](int s) { return bar0 + 8u * (uint32_t)(S + s); };
+    auto aready = [&](int b) { return bar0 + 8u * (uint32_t)(2 * S + b); };
+    auto afree = [&](int b) { return bar0 + 8u * (uint32_t)(2 * S + 2 + b); };
+    const uint32_t dfull = bar0 + 8u * (uint32_t)(2 * S + 4), dfree = bar0 + 8u * (uint32_t)(2 * S + 5);
+    const uint32_t wsm0 = smem_addr(smem_raw);
     const int kch = K / kKc;
-
     const int64_t ntiles = (rows + kRows - 1) / kRows;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t row = tile * kRows + tid;
-        const bool valid = row < rows;
-        const float4* arow = reinterpret_cast<const float4*>(a + (valid ? row : 0) * K);
-        float cur[kKc], nxt[kKc];
-        auto load_chunk = [&](int c, float (&dst)[kKc]) {
+    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_tiles * kch;     // chunks this CTA consumes, in order
+
+    if (warp == 4) {
+        if ((tid & 31) == 0) {
+            auto issue = [&](int64_t g) {
+                const int s = (int)(g % S), c = (int)(g % kch);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wfull(s)), "r"(kChunkBytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 wsm0 + (uint32_t)s * kChunkBytes),
+                             "l"(prepped + (size_t)c * 2 * N * kKc), "r"(kChunkBytes), "r"(wfull(s))
+                             : "memory");
+            };
+            int64_t gi = 0;
+            for (; gi < S && gi < total; ++gi) issue(gi);
+            for (int64_t g = 0; g < total; ++g) {
+                const int s = (int)(g % S), c = (int)(g % kch), b = (int)(g & 1);
+                if (c == 0 && g > 0) bar_wait(dfree, (uint32_t)((g / kch - 1) & 1));      // the previous tile's tail has read D
+                bar_wait(wfull(s), (uint32_t)((g / S) & 1));
+                bar_wait(aready(b), (uint32_t)((g >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi_t = tmem_base + N + 64 * b, a_lo_t = a_hi_t + 32;
+                const uint32_t ws = wsm0 + (uint32_t)s * kChunkBytes;
+                const uint64_t whi = make_desc(ws), wlo = make_desc(ws + N * kKc * 4u);
 #pragma unroll
-            for (int q = 0; q < kKc / 4; ++q) {
-                const float4 t = valid ? __ldg(arow + c * (kKc / 4) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < kKc / 8; ++j) mma_ts(d_tmem, a_hi_t + 8 * j, whi + j * 16, kIdesc, (c > 0 || j > 0) ? 1u : 0u);
+#pragma unroll
+                for (int j = 0; j < kKc / 8; ++j) mma_ts(d_tmem, a_lo_t + 8 * j, whi + j * 16, kIdesc, 1u);
+#pragma unroll
+                for (int j = 0; j < kKc / 8; ++j) mma_ts(d_tmem, a_hi_t + 8 * j, wlo + j * 16, kIdesc, 1u);
+                mma_commit(wfree(s));
+                mma_commit(afree(b));
+                if (c == kch - 1) mma_commit(dfull);
+                // refill the slot of the chunk BEFORE this one (its MMAs are done or about to be): the ring stays S - 1 ahead
+                if (g >= 1 && gi < total) {
+                    bar_wait(wfree((int)((g - 1) % S)), (uint32_t)(((g - 1) / S) & 1));
+                    issue(gi);
+                    ++gi;
+                }
+            }
+        }
+    } else {
+        const uint32_t lanes = (uint32_t)((warp & 3) * 32) << 16;
+        int64_t g = 0;
+        // 32 consecutive parameters (bias / gamma / beta / a row of Wo) as eight 16-byte loads: every thread of the CTA asks
+        // for the same addresses, the loads are broadcasts
+        auto load32 = [&](const float* p32, float (&dst)[32]) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p32) + q);
                 dst[4 * q] = t.x; dst[4 * q + 1] = t.y; dst[4 * q + 2] = t.z; dst[4 * q + 3] = t.w;
             }
         };
-        load_chunk(0, cur);
-        for (int c = 0; c < kch; ++c) {
-            const int b = c & 1;
-            if (pending[b]) {          // the MMAs that read A buffer b / weight buffer b two chunks ago are done
-                bar_wait(done[b], done_phase[b]);
-                done_phase[b] ^= 1u;
-                pending[b] = false;
+        float bufA[kKc], bufB[kKc];
+        auto load_chunk = [&](int64_t tile, int c, float (&dst)[kKc]) {
+            const int64_t row = tile * kRows + tid;
+            const bool ok = row < rows && tile < ntiles;
+            const float4* arow = reinterpret_cast<const float4*>(a + (ok ? row : 0) * K);
+#pragma unroll
+            for (int q = 0; q < kKc / 4; ++q) {
+                const float4 t = ok ? __ldg(arow + c * (kKc / 4) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                dst[4 * q] = t.x; dst[4 * q + 1] = t.y; dst[4 * q + 2] = t.z; dst[4 * q + 3] = t.w;
             }
-            if (tid == 0) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wfull[b]), "r"(kChunkBytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(wsm_s[b]),
-                             "l"(prepped + (size_t)c * 2 * N * kKc), "r"(kChunkBytes), "r"(wfull[b])
-                             : "memory");
-            }
+        };
+        // one chunk: registers -> hi / lo -> tensor memory, then tell the issuer
+        auto stage = [&](const float (&cur)[kKc]) {
+            const int b = (int)(g & 1);
+            if (g >= 2) bar_wait(afree(b), (uint32_t)(((g >> 1) - 1) & 1));       // the MMAs that read this A buffer are done
             const uint32_t a_hi_t = tmem_base + N + 64 * b, a_lo_t = a_hi_t + 32;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -181,101 +248,103 @@ k_linear_tc(const float* __restrict__ a, int64_t rows, int K, const float* __res
                 tmem_st16(a_hi_t + lanes + 16 * half, hi);
                 tmem_st16(a_lo_t + lanes + 16 * half, lo);
             }
-            if (c + 1 < kch) load_chunk(c + 1, nxt);     // in flight while this chunk's MMAs are issued
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();
-            if (tid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                bar_wait(wfull[b], wfull_phase[b]);
-                const uint64_t whi = make_desc(wsm_s[b]), wlo = make_desc(wsm_s[b] + N * kKc * 4u);
-#pragma unroll
-                for (int j = 0; j < kKc / 8; ++j) mma_ts(d_tmem, a_hi_t + 8 * j, whi + j * 16, kIdesc, (c > 0 || j > 0) ? 1u : 0u);
-#pragma unroll
-                for (int j = 0; j < kKc / 8; ++j) mma_ts(d_tmem, a_lo_t + 8 * j, whi + j * 16, kIdesc, 1u);
-#pragma unroll
-                for (int j = 0; j < kKc / 8; ++j) mma_ts(d_tmem, a_hi_t + 8 * j, wlo + j * 16, kIdesc, 1u);
-                mma_commit(done[b]);
-            }
-            wfull_phase[b] ^= 1u;
-            pending[b] = true;
-            if (c + 1 < kch) {
-#pragma unroll
-                for (int j = 0; j < kKc; ++j) cur[j] = nxt[j];
-            }
-        }
-        // every MMA of the tile is complete once the commits have arrived
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            if (pending[b]) {
-                bar_wait(done[b], done_phase[b]);
-                done_phase[b] ^= 1u;
-                pending[b] = false;
-            }
-        }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- the tail, one thread per row, 32 accumulators at a time
-        float mean = 0.f, rstd = 1.f;
-        if (ln_g != nullptr) {
-            float s = 0.f, q = 0.f;
-            for (int p = 0; p < N / 32; ++p) {
-                float v[32];
-                tmem_ld32(d_tmem + lanes + 32 * p, v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) { v[j] += __ldg(bias + 32 * p + j); s += v[j]; }
-            }
-            mean = s * (1.0f / N);
-            for (int p = 0; p < N / 32; ++p) {       // second pass for the variance: the same arithmetic as torch's two-pass LayerNorm
-                float v[32];
-                tmem_ld32(d_tmem + lanes + 32 * p, v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) { const float d = v[j] + __ldg(bias + 32 * p + j) - mean; q = fmaf(d, d, q); }
-            }
-            rstd = rsqrtf(q * (1.0f / N) + 1e-5f);
-        }
-        float dots[8];
-#pragma unroll
-        for (int o = 0; o < 8; ++o) dots[o] = 0.f;
-        for (int p = 0; p < N / 32; ++p) {
-            float v[32];
-            tmem_ld32(d_tmem + lanes + 32 * p, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float t = v[j] + __ldg(bias + 32 * p + j);
-                if (ln_g != nullptr) t = (t - mean) * rstd * __ldg(ln_g + 32 * p + j) + __ldg(ln_b + 32 * p + j);
-                if (relu) t = fmaxf(t, 0.f);
-                v[j] = t;
-            }
-            if (valid) {
-                if (out != nullptr) {
-                    float4* o4 = reinterpret_cast<float4*>(out + row * N + 32 * p);
-#pragma unroll
-                    for (int q4 = 0; q4 < 8; ++q4) o4[q4] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+            bar_arrive(aready(b));
+            ++g;
+        };
+        load_chunk(blockIdx.x, 0, bufA);
+        for (int64_t tile = blockIdx.x, it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+            const int64_t row = tile * kRows + tid;
+            const bool valid = row < rows;
+            // chunks alternate between two register buffers: the loads of chunk c + 1 are issued before chunk c is staged and
+            // consumed one whole stage later
+            for (int c = 0; c < kch; c += 2) {
+                if (c + 1 < kch) load_chunk(tile, c + 1, bufB);
+                stage(bufA);
+                if (c + 1 < kch) {
+                    if (c + 2 < kch) load_chunk(tile, c + 2, bufA);
+                    else load_chunk(tile + gridDim.x, 0, bufA);          // the next tile's first chunk, in flight during the tail
+                    stage(bufB);
+                } else {
+                    load_chunk(tile + gridDim.x, 0, bufA);
                 }
-                if (z != nullptr) {
-                    float4* z4 = reinterpret_cast<float4*>(z + row * N + 32 * p);
+            }
+            bar_wait(dfull, (uint32_t)(it & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // ---- the tail, one thread per row, 32 accumulators at a time
+            float mean = 0.f, rstd = 1.f;
+            if (ln_g != nullptr) {
+                // mean and variance in ONE pass over the accumulators, sums taken about the row's first value (shifted data:
+                // no cancellation for rows whose mean is far from zero)
+                float sm = 0.f, q = 0.f, shift = 0.f;
+                for (int p = 0; p < N / 32; ++p) {
+                    float v[32], bb[32];
+                    tmem_ld32(d_tmem + lanes + 32 * p, v);
+                    load32(bias + 32 * p, bb);
+                    if (p == 0) shift = v[0] + bb[0];
 #pragma unroll
-                    for (int q4 = 0; q4 < 8; ++q4) {
-                        float4 t = z_accumulate ? z4[q4] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        t.x = fmaf(z_scale, v[4 * q4], t.x); t.y = fmaf(z_scale, v[4 * q4 + 1], t.y);
-                        t.z = fmaf(z_scale, v[4 * q4 + 2], t.z); t.w = fmaf(z_scale, v[4 * q4 + 3], t.w);
-                        z4[q4] = t;
+                    for (int j = 0; j < 32; ++j) { const float d = v[j] + bb[j] - shift; sm += d; q = fmaf(d, d, q); }
+                }
+                const float md = sm * (1.0f / N);
+                mean = shift + md;
+                rstd = rsqrtf(fmaxf(q * (1.0f / N) - md * md, 0.f) + 1e-5f);
+            }
+            float dots[8];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) dots[o] = 0.f;
+            for (int p = 0; p < N / 32; ++p) {
+                float v[32], bb[32];
+                tmem_ld32(d_tmem + lanes + 32 * p, v);
+                if (p == N / 32 - 1) {      // D is read: the issuer may start the next tile while the stores go out
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    bar_arrive(dfree);
+                }
+                load32(bias + 32 * p, bb);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += bb[j];
+                if (ln_g != nullptr) {
+                    load32(ln_g + 32 * p, bb);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd * bb[j];
+                    load32(ln_b + 32 * p, bb);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += bb[j];
+                }
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (valid) {
+                    if (out != nullptr) {
+                        float4* o4 = reinterpret_cast<float4*>(out + row * N + 32 * p);
+#pragma unroll
+                        for (int q4 = 0; q4 < 8; ++q4) o4[q4] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                    }
+                    if (z != nullptr) {
+                        float4* z4 = reinterpret_cast<float4*>(z + row * N + 32 * p);
+#pragma unroll
+                        for (int q4 = 0; q4 < 8; ++q4) {
+                            float4 t = z_accumulate ? z4[q4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                            t.x = fmaf(z_scale, v[4 * q4], t.x); t.y = fmaf(z_scale, v[4 * q4 + 1], t.y);
+                            t.z = fmaf(z_scale, v[4 * q4 + 2], t.z); t.w = fmaf(z_scale, v[4 * q4 + 3], t.w);
+                            z4[q4] = t;
+                        }
+                    }
+                }
+                if (wo != nullptr) {
+                    for (int o = 0; o < out_ch; ++o) {
+                        load32(wo + o * N + 32 * p, bb);
+                        float sd = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sd = fmaf(v[j], bb[j], sd);
+                        dots[o] += sd;
                     }
                 }
             }
-            if (wo != nullptr) {
-                for (int o = 0; o < out_ch; ++o) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) s = fmaf(v[j], __ldg(wo + o * N + 32 * p + j), s);
-                    dots[o] += s;
-                }
-            }
+            if (wo != nullptr && valid)
+                for (int o = 0; o < out_ch; ++o) out_final[row * out_ch + o] = dots[o] + __ldg(bo + o);
         }
-        if (wo != nullptr && valid)
-            for (int o = 0; o < out_ch; ++o) out_final[row * out_ch + o] = dots[o] + __ldg(bo + o);
-        // the accumulator is read: the next tile's first MMA may overwrite it (ordered by the barrier of its first chunk)
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -289,12 +358,12 @@ template <int N>
 static int launch(const float* a, int64_t rows, int k, const float* prepped, const float* bias, const float* ln_g, const float* ln_b,
                   int relu, float* out, float* z, float z_scale, int z_acc, const float* wo, const float* bo, int out_ch,
                   float* out_final, cudaStream_t st) {
-    const size_t smem = 2 * (size_t)2 * N * kKc * sizeof(float);
+    const size_t smem = (size_t)Ring<N>::kStages * 2 * N * kKc * sizeof(float);
     OCN_CUDA(cudaFuncSetAttribute(k_linear_tc<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int per_sm = (N + 128 <= 256) ? 2 : 1;    // tensor-memory columns: 256 or all 512
+    const int per_sm = Ring<N>::kPerSm;
     const int64_t ntiles = (rows + kRows - 1) / kRows;
     const int64_t cap = (int64_t)sm_count() * per_sm;
-    k_linear_tc<N><<<(int)(ntiles < cap ? ntiles : cap), kRows, smem, st>>>(a, rows, k, prepped, bias, ln_g, ln_b, relu, out, z, z_scale,
+    k_linear_tc<N><<<(int)(ntiles < cap ? ntiles : cap), kRows + 32, smem, st>>>(a, rows, k, prepped, bias, ln_g, ln_b, relu, out, z, z_scale,
                                                                            z_acc, wo, bo, out_ch, out_final);
     OCN_LAUNCH_CHECK();
     return OCN_OK;
