@@ -348,6 +348,18 @@ def secondary(a, ob, synth, G, g, x, sampler, peak, dev):
                         lambda ms: {"links": Th, "us": ms * 1e3}, reps=5, warm=2)
             _l.set_option("head_tc", 0)
     del hp, hx
+    # (1c) the wider heads of configs 1-3 (hidden 256): one tensor-core launch per layer against the torch modules
+    from ocn_b200 import head as _head
+    torch.manual_seed(0)
+    hp = ob.CNLinkPredictorOringin(256, 256, 1, 3, 0.0, ln=True).to(dev).eval()
+    hx = [torch.randn(Th, 256, device=dev) for _ in range(3)]
+    with torch.no_grad():
+        measure("head_cn5_F256_tcgen05_per_layer", lambda: _head.fused_head_wide(hp, hx[0], hx[1], None, hx[2]),
+                lambda ms: {"links": Th, "us": ms * 1e3}, reps=3, warm=1)
+        hp.fuse_head = False
+        measure("head_cn5_F256_torch_modules", lambda: hp._head(hx[0], hx[1], None, hx[2]),
+                lambda ms: {"links": Th, "us": ms * 1e3}, reps=3, warm=1)
+    del hp, hx
     # (2) order 2 on the same stream (get_cn1_cn2 as the reference's citation2 driver calls it)
     T = a.batch * a.batches
     e2 = g.stream_links(7 * T, 4 * T, device=dev)
