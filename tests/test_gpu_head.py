@@ -128,3 +128,50 @@ def test_wide_head_on_the_tensor_cores(cls, in_ch, hid, ln, tailact, two, out_ch
         got = head.fused_head_wide(pred, xs[0], xs[1], x3, xs[3])
         want = p64._head(xs[0].double(), xs[1].double(), None if x3 is None else x3.double(), xs[3].double())
     assert (got.double() - want).abs().max().item() <= 1e-5 * (1.0 + want.abs().max().item())
+
+
+@pytest.mark.parametrize("rows", [1, 127, 128, 129, 5000])
+@pytest.mark.parametrize("k,n", [(32, 32), (32, 256), (256, 32), (64, 128), (96, 64), (256, 256)])
+def test_linear_tc_shapes_and_tails(rows, k, n):
+    """ocn_linear_tc on its own: fewer rows than a tile, one K chunk (no ring refill), an odd number of chunks, every
+    output width; Linear, Linear + LayerNorm + ReLU with the z accumulation and the fused last Linear, against float64."""
+    torch.manual_seed(rows + k + n)
+    lin = torch.nn.Linear(k, n).to(DEV)
+    ln = torch.nn.LayerNorm(n).to(DEV)
+    fin = torch.nn.Linear(n, 3).to(DEV)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.normal_()
+    holder = ob.CNLinkPredictorOringin(32, 32, 1, 3, 0.0)      # only carries the cache of split weights
+    x = torch.randn(rows, k, device=DEV) * 2
+    z0 = torch.randn(rows, n, device=DEV)
+    with torch.no_grad():
+        out, _ = head.linear_tc(holder, x, lin)
+        want = lin.double()(x.double())
+        lin.float()
+        assert (out.double() - want).abs().max().item() <= 1e-5 * (1 + want.abs().max().item())
+        z = z0.clone()
+        out2, f2 = head.linear_tc(holder, x, lin, ln, True, want_out=True, z=z, z_scale=0.7, z_accumulate=True, final=fin)
+        v = torch.relu(ln.double()(lin.double()(x.double())))
+        lin.float(); ln.float()
+        tol = 1e-5 * (1 + v.abs().max().item())
+        assert (out2.double() - v).abs().max().item() <= tol
+        assert (z.double() - (z0.double() + 0.7 * v)).abs().max().item() <= tol
+        wf = fin.double()(v)
+        fin.float()
+        assert f2.shape == (rows, 3) and (f2.double() - wf).abs().max().item() <= 1e-5 * (1 + wf.abs().max().item())
+        z = z0.clone()
+        head.linear_tc(holder, x, lin, None, False, want_out=False, z=z, z_scale=-1.25, z_accumulate=False)
+        assert (z.double() - (-1.25) * want).abs().max().item() <= 1e-5 * (1 + want.abs().max().item())
+
+
+def test_linear_tc_refuses_what_it_does_not_serve():
+    from ocn_b200 import _lib
+    L = _lib.lib()
+    assert L.ocn_linear_tc_prep_floats(48, 64) == -1 and L.ocn_linear_tc_prep_floats(64, 48) == -1
+    assert L.ocn_linear_tc_prep_floats(256, 256) == 2 * 256 * 256
+    x = torch.randn(8, 64, device=DEV)
+    buf = torch.empty(2 * 64 * 64, device=DEV)
+    b = torch.zeros(64, device=DEV)
+    rc = L.ocn_linear_tc(x.data_ptr(), 8, 64, 64, buf.data_ptr(), b.data_ptr(), None, None, 0, None, None, 1.0, 0, None, None, 0, None, None)
+    assert rc != 0 and b"no output" in L.ocn_last_error()
