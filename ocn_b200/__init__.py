@@ -13,14 +13,17 @@ from . import ops  # noqa: F401  (registers torch.ops.ocn.*)
 from . import dist, metrics  # noqa: F401
 from .predictor import (CNLinkPredictor3hopCNs, CNLinkPredictorbaselearn, CNLinkPredictorOringin,  # noqa: F401
                         predictor_dict)
-from .completion import IncompleteCN1Predictor  # noqa: F401
+from .completion import (IncompleteCN1Predictor, IncompleteCN1Predictorhighorder,  # noqa: F401
+                         IncompleteCN1PredictorSaveMemory)
 from .sample import sparsesample_reweight  # noqa: F401
 
 predictor_dict["cn2"] = IncompleteCN1Predictor
+predictor_dict["cn3"] = IncompleteCN1Predictorhighorder
+predictor_dict["cn4"] = IncompleteCN1PredictorSaveMemory
 
 __all__ = [
     "Graph", "CNSession", "SparseRows", "adjoverlap", "cn_aggregate_eval", "get_cn", "get_cn1_cn2",
     "drop_adj", "gcn_norm", "gcnconv_propagate", "pure_conv", "pure_conv3_gcn", "sparse_tensor_multiply", "spgemm_a2",
     "spmm", "spmm_add", "spmm_max", "spmm_mean", "CNLinkPredictorOringin", "CNLinkPredictor3hopCNs",
-    "CNLinkPredictorbaselearn", "IncompleteCN1Predictor", "sparsesample_reweight", "predictor_dict", "synth", "reserve_stream_pool", "metrics", "dist",
+    "CNLinkPredictorbaselearn", "IncompleteCN1Predictor", "IncompleteCN1PredictorSaveMemory", "IncompleteCN1Predictorhighorder", "sparsesample_reweight", "predictor_dict", "synth", "reserve_stream_pool", "metrics", "dist",
 ]

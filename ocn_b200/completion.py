@@ -14,8 +14,9 @@ Data flow of one call at depth 1 (the default):
 3. the scores, squashed by ``clampprob``, become the values of the residual matrices, which then go through the cn5
    normalisation / running inner product / orthogonalisation (model.py:960-1123) and three ``spmm_add``.
 
-cn3 / cn4 (``IncompleteCN1Predictorhighorder`` / ``...SaveMemory``) recombine the same operators (plus a per-call A^2);
-they run unmodified on the import shim (``ocn_b200.shim``; traces in tests/golden/ref_trace_cn3_eval.pt, _cn4_eval.pt).
+cn3 / cn4 (``IncompleteCN1Predictorhighorder`` / ``...SaveMemory``, below) recombine the same operators (cn3: plus A^2 and
+its residual sets); all three also run unmodified on the import shim (``ocn_b200.shim``; traces in
+tests/golden/ref_trace_cn2_*.pt, _cn3_eval.pt, _cn4_eval.pt).
 """
 from __future__ import annotations
 
@@ -71,6 +72,9 @@ class CNLinkPredictor(nn.Module):
 
 
 class IncompleteCN1Predictor(CNLinkPredictor):
+    residual_fill = 0.0   # weight of a residual column that sums to exactly 1 (model.py:963-966)
+    xij_passes = 2        # xijlin is applied to the pair term this many times (model.py:902 and :1126)
+
     def __init__(self, in_channels, hidden_channels, out_channels, num_layers, dropout, edrop=0.0, ln=False, cndeg=-1,
                  use_xlin=False, tailact=False, twolayerlin=False, beta=1.0, alpha=1.0, scale=5, offset=3, trainresdeg=8,
                  testresdeg=128, pt=0.5, learnablept=False, depth=1, splitsize=-1):
@@ -139,7 +143,7 @@ class IncompleteCN1Predictor(CNLinkPredictor):
             cnres1 = SparseRows(cnres1.rowptr, cnres1.col, probcn1 * cnres1.value, cnres1.shape)
             cnres2 = SparseRows(cnres2.rowptr, cnres2.col, probcn2 * cnres2.value, cnres2.shape)
             # model.py:960-1123: the cn5 combination with the weighted residuals in the roles of cn1 / cn2
-            ncn1 = _normalise_cn1(cnres1, 0.0)
+            ncn1 = _normalise_cn1(cnres1, self.residual_fill)
             if self.training:
                 self._running_mean_update(_hadamard_sum(cnres2, ncn1).detach())
             ip = self.innerprod.detach().float()
@@ -150,10 +154,92 @@ class IncompleteCN1Predictor(CNLinkPredictor):
             coeff = torch.where(scale > 0, ip / torch.where(scale > 0, scale, torch.ones_like(scale)), ip)
             ncn2 = _orthogonalise(cnres2, ncn1, coeff)
             xcn = xcn + spmm_add(ncn2, x) + spmm_add(ncn1, x)
-        xij = self.xijlin(xij)
+        for _ in range(self.xij_passes - 1):
+            xij = self.xijlin(xij)
         return self.lin(self.xcnlin(xcn) * self.beta + xij)
 
     def forward(self, x, adj, tar_ei, filled1: bool = False, depth: Optional[int] = None):
         if depth is None:
             depth = self.depth
         return self.multidomainforward(x, adj, tar_ei, filled1, [], depth)
+
+
+class IncompleteCN1PredictorSaveMemory(IncompleteCN1Predictor):
+    """cn4 (model.py:1532-1886): cn2's forward with ``del`` statements and ``torch.cuda.empty_cache()`` between its steps and
+    TWO arithmetic differences: a residual column whose weights sum to exactly 1 keeps weight 1 instead of 0
+    (``inv_col_sum[inv_col_sum == 1] = 1``, model.py:1700-1703), and the pair term goes through ``xijlin`` a third time
+    (``xij = self.xijlin(xij)`` at :1861 and ``self.xijlin(xij)`` again inside the last line, :1863)."""
+    residual_fill = 1.0
+    xij_passes = 3
+
+
+class IncompleteCN1Predictorhighorder(IncompleteCN1Predictor):
+    """cn3 (model.py:1150-1530): CN1 = A[i] cap A[j] and CN2 = A[i] cap A^2[j] through the cn5 combination (singleton weight
+    1), plus -- at depth > 0 -- the four residual sets of A and A^2 scored by the depth - 1 pass and added unnormalised.
+    The reference rebuilds ``spadj @ spadj`` in EVERY call, the recursive ones included (:1211-1212); here A^2 is built once
+    per top-level call (``ocn_spgemm_a2_*``) and handed down.  Same signature: ``forward(x, adj, cn1, cn2, tar_ei, ...)``
+    (the ``cn1`` / ``cn2`` arguments are unused by the reference too)."""
+
+    def _weighted(self, x, adj, adj2, ends: Tensor, res: SparseRows, filled1, depth) -> SparseRows:
+        ei = torch.stack((ends[res.row()], res.col))
+        with torch.no_grad():
+            if ei.shape[1] == 0:
+                prob = x.new_zeros(0)
+            elif self.splitsize < 0:
+                prob = self.multidomainforward(x, adj, None, None, ei, filled1, [], depth, _adj2=adj2).flatten()
+            else:
+                prob = torch.empty(ei.shape[1], dtype=torch.float32, device=x.device)
+                for s in range(0, ei.shape[1], self.splitsize):
+                    prob[s:s + self.splitsize] = self.multidomainforward(x, adj, None, None, ei[:, s:s + self.splitsize], filled1,
+                                                                         [], depth, _adj2=adj2).flatten()
+        return SparseRows(res.rowptr, res.col, self.clampprob(prob, self.pt) * res.value, res.shape)
+
+    def multidomainforward(self, x, adj: Graph, cn1, cn2, tar_ei, filled1: bool = False, cndropprobs: Iterable[float] = [],
+                           depth: Optional[int] = None, _adj2: Optional[Graph] = None):
+        from .sparse_ops import spgemm_a2
+        assert len(cndropprobs) == 0
+        if depth is None:
+            depth = self.depth
+        adj = self.dropadj(adj)
+        xij = self.xijlin(x[tar_ei[0]] * x[tar_ei[1]])
+        x = x + self.xlin(x)
+        adj2 = _adj2 if _adj2 is not None else spgemm_a2(adj, 0, False)
+        resdeg = self.trainresdeg if self.training else self.testresdeg
+        if depth > 0.5:
+            cn, cnres1, cnres2 = adjoverlap(adj, adj, tar_ei, filled1, calresadj=True)
+            cn = self._sample(cn, self.cndeg)
+            cnres1, cnres2 = self._sample(cnres1, resdeg), self._sample(cnres2, resdeg)
+            cn22, cn2res1, cn2res2 = adjoverlap(adj, adj2, tar_ei, filled1, calresadj=True)
+            cn22 = self._sample(cn22, self.cndeg)
+            cn2res1, cn2res2 = self._sample(cn2res1, resdeg), self._sample(cn2res2, resdeg)
+        else:
+            cn = self._sample(adjoverlap(adj, adj, tar_ei, filled1), self.cndeg)
+            cn22, d1, d2 = adjoverlap(adj, adj2, tar_ei, filled1, calresadj=True)
+            cn22 = self._sample(cn22, self.cndeg)
+            self._sample(d1, resdeg), self._sample(d2, resdeg)      # built, sampled and dropped, as the reference does (:1240-1244)
+        # model.py:1245-1409: the cn5 combination of (cn, cn22), a column summing to exactly 1 keeps weight 1
+        ncn1 = _normalise_cn1(cn, 1.0)
+        if self.training:
+            self._running_mean_update(_hadamard_sum(cn22, ncn1).detach())
+        ip = self.innerprod.detach().float()
+        if cn.col.numel() + cn22.col.numel() > 0:
+            scale = ncn1.value.detach().abs().max() if ncn1.value.numel() else torch.zeros((), device=x.device)
+        else:
+            scale = torch.ones((), device=x.device)
+        coeff = torch.where(scale > 0, ip / torch.where(scale > 0, scale, torch.ones_like(scale)), ip)
+        ncn2 = _orthogonalise(cn22, ncn1, coeff)
+        xcn_a, xcn_b = spmm_add(ncn1, x), spmm_add(ncn2, x)
+        if depth > 0.5:
+            w1 = self._weighted(x, adj, adj2, tar_ei[1], cnres1, filled1, depth - 1)
+            w2 = self._weighted(x, adj, adj2, tar_ei[0], cnres2, filled1, depth - 1)
+            xcn_a = xcn_a + spmm_add(w2, x) + spmm_add(w1, x)
+            v1 = self._weighted(x, adj, adj2, tar_ei[1], cn2res1, filled1, depth - 1)
+            v2 = self._weighted(x, adj, adj2, tar_ei[0], cn2res2, filled1, depth - 1)
+            xcn_b = xcn_b + spmm_add(v2, x) + spmm_add(v1, x)
+        xij = self.xijlin(xij)
+        return self.lin(self.xcnlin(xcn_a) * self.beta + self.xcnlin(xcn_b) * self.beta + xij)
+
+    def forward(self, x, adj, cn1, cn2, tar_ei, filled1: bool = False, depth: Optional[int] = None):
+        if depth is None:
+            depth = self.depth
+        return self.multidomainforward(x, adj, cn1, cn2, tar_ei, filled1, [], depth)

@@ -156,7 +156,7 @@ def run_utils_case(graphs):
     print(f"wrote {path}: {len(cases)} case(s), {os.path.getsize(path) / 1024:.0f} KiB")
 
 
-def run_completion_case(name, graph, B, mode, ncalls, trainresdeg, testresdeg, seed):
+def run_completion_case(name, graph, B, mode, ncalls, trainresdeg, testresdeg, seed, cls_name="IncompleteCN1Predictor"):
     """cn2 = IncompleteCN1Predictor (model.py:843-1146) at depth 1, in = hidden = 64 (its xijlin is a Linear(64, .)
     applied twice).  The draws of sparsesample_reweight's torch.rand are recorded so that a replay is deterministic."""
     torch.manual_seed(seed)
@@ -165,7 +165,7 @@ def run_completion_case(name, graph, B, mode, ncalls, trainresdeg, testresdeg, s
     row = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
     adj = SparseTensor(row=row, col=col, sparse_sizes=(n, n), is_sorted=True)
     x = graph.features(64)
-    pred = ref_model.IncompleteCN1Predictor(64, 64, 1, 3, 0.0, trainresdeg=trainresdeg, testresdeg=testresdeg, depth=1)
+    pred = getattr(ref_model, cls_name)(64, 64, 1, 3, 0.0, trainresdeg=trainresdeg, testresdeg=testresdeg, depth=1)
     pred.train() if mode == "train" else pred.eval()
     draws = []
     real_rand = torch.rand
@@ -182,12 +182,12 @@ def run_completion_case(name, graph, B, mode, ncalls, trainresdeg, testresdeg, s
                 neg = torch.stack((synth.hash_randint(B - B // 2, n, 270 + s, 1, "cpu"), synth.hash_randint(B - B // 2, n, 270 + s, 2, "cpu")))
                 e = torch.cat((graph.query_edges(B // 2, "pos"), neg), 1)
                 first = len(draws)
-                out = pred(x, adj, e)
+                out = pred(x, adj, None, None, e) if cls_name.endswith("highorder") else pred(x, adj, e)
                 calls.append({"edges": e.clone(), "out": out.detach().clone(), "innerprod": pred.innerprod.detach().clone(),
                               "n": pred.n, "draws": draws[first:]})
     finally:
         torch.rand = real_rand
-    fx = {"name": name, "n": n, "rowptr": rowptr.clone(), "col": graph.col.clone(), "x": x, "mode": mode,
+    fx = {"name": name, "n": n, "rowptr": rowptr.clone(), "col": graph.col.clone(), "x": x, "mode": mode, "cls": cls_name,
           "trainresdeg": trainresdeg, "testresdeg": testresdeg,
           "state_dict": {k: v.clone() for k, v in pred.state_dict().items()}, "calls": calls}
     path = os.path.join(ROOT, "tests", "golden", f"ref_{name}.pt")
@@ -225,6 +225,14 @@ def main():
         run_completion_case("cn2_eval_cora", synth.make_graph("cora", scale=0.06), 32, "eval", 1, 8, 6, 11)
     if only.search("cn2_train_tiny"):
         run_completion_case("cn2_train_tiny", tiny, 24, "train", 3, 3, 128, 12)
+    if only.search("cn3_train_tiny"):
+        run_completion_case("cn3_train_tiny", synth.tiny_graph(40, 150, 11), 10, "train", 2, 3, 128, 14,
+                            cls_name="IncompleteCN1Predictorhighorder")
+    if only.search("cn3_eval_tiny"):
+        run_completion_case("cn3_eval_tiny", synth.tiny_graph(40, 150, 11), 10, "eval", 1, 8, 5, 15,
+                            cls_name="IncompleteCN1Predictorhighorder")
+    if only.search("cn4_train_tiny"):
+        run_completion_case("cn4_train_tiny", tiny, 24, "train", 2, 3, 128, 13, cls_name="IncompleteCN1PredictorSaveMemory")
     run_case("cn5_large_eval_tiny", tiny, 8, links(tiny, 48, 1), "cn5", "eval", "large")
     run_case("cn5_large_train_cora", cora, 16, links(cora, 96, 3), "cn5", "train", "large")
     run_case("cn5_large_eval_ln_cora", cora, 16, links(cora, 96, 1), "cn5", "eval", "large", ln=True)

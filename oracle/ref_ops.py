@@ -192,10 +192,12 @@ def sparsesample_reweight(adj: Sp, deg: int, rand_fn=None) -> Sp:
 
 
 def cn2_forward(mod, x: Tensor, adj: Sp, tar_ei: Tensor, state: "InnerProdState", training: bool, depth: int,
-                rand_fn=None) -> Tensor:
+                rand_fn=None, fill: float = 0.0, xij_passes: int = 2) -> Tensor:
     """``IncompleteCN1Predictor.multidomainforward`` (model.py:888-1131; edrop = 0, cndeg <= 0, use_xlin False).
     ``mod`` supplies the dense heads (xijlin, xcnlin, lin, ptlin), buffers (beta, alpha2, pt, scale, offset) and the
-    sampling degrees; the sparse part is restated here."""
+    sampling degrees; the sparse part is restated here.  ``fill = 1, xij_passes = 3`` is
+    ``IncompleteCN1PredictorSaveMemory`` (cn4, model.py:1585-1872): the same forward with singleton columns of the weighted
+    residual keeping weight 1 and ``xijlin`` applied a third time (:1861 and again inside :1863)."""
     xij = mod.xijlin(x[tar_ei[0]] * x[tar_ei[1]])
     resdeg = mod.trainresdeg if training else mod.testresdeg
     if depth > 0.5:
@@ -212,9 +214,9 @@ def cn2_forward(mod, x: Tensor, adj: Sp, tar_ei: Tensor, state: "InnerProdState"
             return mod.alpha2 * pt * p0 / (pt * p0 + 1 - p0)
         with torch.no_grad():
             probcn1 = cn2_forward(mod, x, adj, torch.stack((tar_ei[1][cnres1.row], cnres1.col)), state, training,
-                                  depth - 1, rand_fn).flatten()
+                                  depth - 1, rand_fn, fill, xij_passes).flatten()
             probcn2 = cn2_forward(mod, x, adj, torch.stack((tar_ei[0][cnres2.row], cnres2.col)), state, training,
-                                  depth - 1, rand_fn).flatten()
+                                  depth - 1, rand_fn, fill, xij_passes).flatten()
         if mod.learnablept:
             pt = mod.ptlin(xij)
             probcn1, probcn2 = clampprob(probcn1, pt[cnres1.row]), clampprob(probcn2, pt[cnres2.row])
@@ -222,10 +224,52 @@ def cn2_forward(mod, x: Tensor, adj: Sp, tar_ei: Tensor, state: "InnerProdState"
             probcn1, probcn2 = clampprob(probcn1, mod.pt), clampprob(probcn2, mod.pt)
         cnres1 = Sp(cnres1.row, cnres1.col, (probcn1 * cnres1.values()).detach(), cnres1.shape)
         cnres2 = Sp(cnres2.row, cnres2.col, (probcn2 * cnres2.values()).detach(), cnres2.shape)
-        xcn1, xcn2, _, _, _ = cn5_aggregate(cnres1, cnres2, x, tar_ei, state, training)     # model.py:960-1123
+        xcn1, xcn2, _, _, _ = cn5_aggregate(cnres1, cnres2, x, tar_ei, state, training, fill)     # model.py:960-1123
         xcn = xcn + xcn2 + xcn1
-    xij = mod.xijlin(xij)
+    for _ in range(xij_passes - 1):
+        xij = mod.xijlin(xij)
     return mod.lin(mod.xcnlin(xcn) * mod.beta + xij)
+
+
+def cn3_forward(mod, x: Tensor, adj: Sp, adj2: Sp, tar_ei: Tensor, state: "InnerProdState", training: bool, depth: int,
+                rand_fn=None) -> Tensor:
+    """``IncompleteCN1Predictorhighorder.multidomainforward`` (cn3, model.py:1195-1505; edrop = 0, cndeg <= 0):
+    CN1 = A[i] cap A[j] and CN2 = A[i] cap A^2[j] (``adj2``: the structure of A @ A, which the reference recomputes in
+    every call, :1211-1212) go through the cn5 combination with singleton weight 1 (:1247-1250); at depth > 0 the four
+    residual sets (of A and of A^2) are scored by the depth - 1 pass, squashed, and added UNNORMALISED (:1447-1449,
+    :1488-1490).  At depth 0 the residuals of A^2 are still built and sampled -- the draws are consumed -- and dropped
+    (:1240-1244)."""
+    xij = mod.xijlin(x[tar_ei[0]] * x[tar_ei[1]])
+    resdeg = mod.trainresdeg if training else mod.testresdeg
+    smp = (lambda m: sparsesample_reweight(m, resdeg, rand_fn)) if resdeg > 0 else (lambda m: m)
+    if depth > 0.5:
+        cn, cnres1, cnres2 = adjoverlap(adj, adj, tar_ei, calresadj=True)
+        cnres1, cnres2 = smp(cnres1), smp(cnres2)
+        cn22, cn2res1, cn2res2 = adjoverlap(adj, adj2, tar_ei, calresadj=True)
+        cn2res1, cn2res2 = smp(cn2res1), smp(cn2res2)
+    else:
+        cn = adjoverlap(adj, adj, tar_ei)
+        cn22, d1, d2 = adjoverlap(adj, adj2, tar_ei, calresadj=True)
+        smp(d1), smp(d2)
+    xcn_a, xcn_b, _, _, _ = cn5_aggregate(cn, cn22, x, tar_ei, state, training, fill=1.0)
+    if depth > 0.5:
+        def clampprob(prob, pt):
+            p0 = torch.sigmoid(mod.scale * (prob - mod.offset))
+            return mod.alpha2 * pt * p0 / (pt * p0 + 1 - p0)
+
+        def weighted(res, ends):
+            with torch.no_grad():
+                prob = cn3_forward(mod, x, adj, adj2, torch.stack((ends[res.row], res.col)), state, training, depth - 1,
+                                   rand_fn).flatten()
+            return Sp(res.row, res.col, (clampprob(prob, mod.pt) * res.values()).detach(), res.shape)
+        w1 = weighted(cnres1, tar_ei[1])
+        w2 = weighted(cnres2, tar_ei[0])
+        xcn_a = xcn_a + spmm_add(w2, x) + spmm_add(w1, x)
+        v1 = weighted(cn2res1, tar_ei[1])
+        v2 = weighted(cn2res2, tar_ei[0])
+        xcn_b = xcn_b + spmm_add(v2, x) + spmm_add(v1, x)
+    xij = mod.xijlin(xij)
+    return mod.lin(mod.xcnlin(xcn_a) * mod.beta + mod.xcnlin(xcn_b) * mod.beta + xij)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -417,10 +461,11 @@ def _scale_factor(base1: Sp, union_nnz: int) -> float:
     return 1.0
 
 
-def cn5_aggregate(cn1: Sp, cn2: Sp, x: Tensor, tar_ei: Tensor, state: InnerProdState, training: bool):
+def cn5_aggregate(cn1: Sp, cn2: Sp, x: Tensor, tar_ei: Tensor, state: InnerProdState, training: bool, fill: float = 0.0):
     """``CNLinkPredictorOringin.multidomainforward`` up to the MLP heads (model.py:2261-2429).
-    Returns (xcn1, xcn2, x_i * x_j, normalized_cn1, normalized_cn2)."""
-    normalized_cn1 = _normalise_cn1(cn1, 0.0)
+    Returns (xcn1, xcn2, x_i * x_j, normalized_cn1, normalized_cn2).  ``fill``: what a column summing to exactly 1
+    weighs (0 in cn5 / cn2, 1 in the same block of cn3 / cn4: model.py:1247-1250, 1679-1682)."""
+    normalized_cn1 = _normalise_cn1(cn1, fill)
     inner_product = state.innerprod1(cn2, normalized_cn1, training)
     union_nnz = int(torch.unique(torch.cat((cn2.row * cn2.shape[1] + cn2.col,
                                             cn1.row * cn1.shape[1] + cn1.col))).numel())

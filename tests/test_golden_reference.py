@@ -135,7 +135,7 @@ def test_oracle_reproduces_reference_adj2byblock_and_calresadj():
 
 # ---- cn2 = IncompleteCN1Predictor: fixtures produced by the reference's own class ----------------------
 
-CN2_FIXTURES = ["cn2_eval_cora", "cn2_train_tiny"]
+CN2_FIXTURES = ["cn2_eval_cora", "cn2_train_tiny", "cn4_train_tiny", "cn3_train_tiny", "cn3_eval_tiny"]
 
 
 def _replay_draws(draws):
@@ -149,8 +149,9 @@ def _replay_draws(draws):
 
 
 def _cn2_module(fx, device="cpu"):
-    from ocn_b200.completion import IncompleteCN1Predictor
-    pred = IncompleteCN1Predictor(64, 64, 1, 3, 0.0, trainresdeg=fx["trainresdeg"], testresdeg=fx["testresdeg"], depth=1)
+    from ocn_b200 import completion
+    cls = getattr(completion, fx.get("cls", "IncompleteCN1Predictor"))
+    pred = cls(64, 64, 1, 3, 0.0, trainresdeg=fx["trainresdeg"], testresdeg=fx["testresdeg"], depth=1)
     missing = pred.load_state_dict(fx["state_dict"], strict=True)     # same parameter / buffer names as the reference
     assert not missing.missing_keys and not missing.unexpected_keys
     pred = pred.to(device)
@@ -159,14 +160,19 @@ def _cn2_module(fx, device="cpu"):
 
 
 @pytest.mark.parametrize("name", CN2_FIXTURES)
-def test_oracle_cn2_matches_the_reference_class(name):
+def test_oracle_completion_predictors_match_the_reference_classes(name):
     fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", f"ref_{name}.pt"))
     mod = _cn2_module(fx)
     A = R.sp_from_csr(fx["rowptr"], fx["col"])
     state = R.InnerProdState()
     with torch.no_grad():
         for call in fx["calls"]:
-            out = R.cn2_forward(mod, fx["x"], A, call["edges"], state, fx["mode"] == "train", 1, _replay_draws(call["draws"]))
+            if fx.get("cls", "").endswith("highorder"):
+                out = R.cn3_forward(mod, fx["x"], A, R.adj2_true(A), call["edges"], state, fx["mode"] == "train", 1,
+                                    _replay_draws(call["draws"]))
+            else:
+                out = R.cn2_forward(mod, fx["x"], A, call["edges"], state, fx["mode"] == "train", 1, _replay_draws(call["draws"]),
+                                    fill=mod.residual_fill, xij_passes=mod.xij_passes)
             assert torch.allclose(out, call["out"], rtol=1e-4, atol=1e-5), (out - call["out"]).abs().max()
             assert torch.allclose(state.innerprod, call["innerprod"], rtol=1e-5, atol=1e-6)
             assert state.n == call["n"]
@@ -174,7 +180,7 @@ def test_oracle_cn2_matches_the_reference_class(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CN2_FIXTURES)
-def test_cuda_cn2_matches_the_reference_class(name):
+def test_cuda_completion_predictors_match_the_reference_classes(name):
     import ocn_b200 as ob
     fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", f"ref_{name}.pt"))
     dev = "cuda:0"
@@ -184,7 +190,8 @@ def test_cuda_cn2_matches_the_reference_class(name):
     with torch.no_grad():
         for call in fx["calls"]:
             pred.rand_fn = _replay_draws(call["draws"])
-            out = pred(x, G, call["edges"].to(dev))
+            e = call["edges"].to(dev)
+            out = pred(x, G, None, None, e) if fx.get("cls", "").endswith("highorder") else pred(x, G, e)
             assert torch.allclose(out.cpu(), call["out"], rtol=1e-4, atol=1e-5), (out.cpu() - call["out"]).abs().max()
             assert torch.allclose(pred.innerprod.cpu(), call["innerprod"], rtol=1e-5, atol=1e-6)
             assert pred.n == call["n"]
