@@ -54,7 +54,7 @@ int ocn_device_sm_count(void);
                                      (measured slower than the folded 64-bit sets on the bench workload; implied by WALKER = 1) */
 #define OCN_OPT_GROUPED_OFF 6     /* 1: never use the run-grouped statistics / aggregation kernels (cn_grouped.cu) */
 #define OCN_OPT_SPGEMM_MODE 7     /* A^2 kernel: 0 automatic, 1 global scratch, 2 shared-memory rows, 3 dense bit matrix */
-#define OCN_OPT_SPMM_TMA 8        /* k_spmm: 0 automatic, 1 gather neighbour rows with cp.async.bulk + mbarrier, 2 register gather, 3 lane-per-feature gather */
+#define OCN_OPT_SPMM_TMA 8        /* k_spmm: 0 automatic, 1 gather neighbour rows with cp.async.bulk + mbarrier, 2 register gather, 3 lane-per-feature gather, 4 shared-memory ring fed by per-thread cp.async */
 #define OCN_OPT_HEAD_TC 9         /* ocn_cn_head at in = hidden = 32: 0 / 3 tcgen05 kernel (tf32 x 3 split, fp32 accuracy; A operand in tensor memory, 4 pipelines per SM), 1 the same with A through shared memory (2 pipelines), 2 CUDA-core kernel */
 #define OCN_OPT_COUNT 16
 /* launches of the library's own kernels since the process started (CUB scans / sorts it calls are not counted) */

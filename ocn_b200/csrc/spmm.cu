@@ -509,6 +509,168 @@ k_spmm_tma(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
     }
 }
 
+// ---- cp.async variant of the ring above ------------------------------------------------------------------------------------
+// Same per-warp ring, weights and row order; the copies are per-thread cp.async.cg (16 bytes each, 4 / VEC whole neighbour rows
+// per instruction, completion by commit / wait groups) instead of one bulk copy per row: a bulk copy is issued one lane at a
+// time (ELECT / R2UR / UBLKCP), which is what kept the ring behind the register gather at F = 32.
+template <int VEC>
+__global__ void __launch_bounds__(kTmaWarps * 32)
+k_spmm_async(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+           const float* __restrict__ norm, int64_t num_rows, const float* __restrict__ x, int mode, float* __restrict__ out) {
+    constexpr int F = 32 * VEC;
+    constexpr int RPS = kTmaStageBytes / (F * 4);  // neighbour rows per stage: 32 / 16 / 8 / 4
+    constexpr int kFirst = 1, kLast = 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int wib = threadIdx.x >> 5, lane = lane_id();
+    unsigned char* base = smem_raw + (size_t)wib * kTmaWarpBytes;
+    float* ring = reinterpret_cast<float*>(base);
+    float* sw = reinterpret_cast<float*>(base + kTmaStages * kTmaStageBytes);
+    TmaMeta* meta = reinterpret_cast<TmaMeta*>(base + kTmaStages * (kTmaStageBytes + 128));
+    const uint32_t ring_s = smem_u32(ring);
+    constexpr int kLpr = 8 * VEC;          // 16-byte pieces (lanes) per neighbour row
+    const int64_t warp = (int64_t)blockIdx.x * kTmaWarps + wib, nwarps = (int64_t)gridDim.x * kTmaWarps;
+    const bool gcn = mode >= kGcnSelf;
+    const int self = mode == kGcnSelf ? 1 : 0;
+
+    // cursor over (row, chunk) of this warp's rows; the pointers of the following row are prefetched
+    int64_t cur = warp, rs = 0, re = 0, ns = 0, ne = 0, pos = 0;
+    auto load_ptr = [&](int64_t rr, int64_t& s, int64_t& e) {
+        s = 0; e = 0;
+        if (rr < num_rows) { s = ldg_i64(rowptr + rr); e = ldg_i64(rowptr + rr + 1); }
+    };
+    load_ptr(cur, rs, re);
+    load_ptr(cur + nwarps, ns, ne);
+    pos = rs;
+    // P: the chunk that will be issued next (its columns are already requested)
+    bool p_valid = false;
+    int64_t p_row = 0;
+    int p_cnt = 0, p_flags = 0, p_deg = 0;
+    int32_t p_c = 0;
+    float p_w = 1.0f;
+    auto fetch_next = [&]() {
+        p_valid = cur < num_rows;
+        if (!p_valid) return;
+        const int64_t vend = re + self;
+        const int64_t left = vend - pos;
+        const int cnt = (int)(left < RPS ? left : RPS);
+        p_row = cur; p_cnt = cnt; p_deg = (int)(re - rs);
+        p_flags = (pos == rs ? kFirst : 0) | (pos + cnt >= vend ? kLast : 0);
+        const int64_t idx = pos + lane;
+        const bool inrow = lane < cnt && idx < re;
+        p_c = lane < cnt ? (inrow ? ldg_i32(col + idx) : (int32_t)cur) : 0;
+        p_w = (inrow && val) ? __ldg(val + idx) : 1.0f;
+        pos += cnt;
+        if (pos >= vend) {
+            cur += nwarps; rs = ns; re = ne; pos = rs;
+            load_ptr(cur + nwarps, ns, ne);
+        }
+    };
+    // D: weights / meta of the stage issued last, parked in shared memory one iteration later
+    bool d_valid = false;
+    int d_k = 0, d_cnt = 0, d_flags = 0, d_deg = 0;
+    int64_t d_row = 0;
+    float d_w = 0.f, d_n = 1.f, d_nr = 1.f;
+    auto flush = [&]() {
+        if (d_valid) {
+            sw[d_k * 32 + lane] = d_w * d_n;
+            if (lane == 0) {
+                TmaMeta m;
+                m.row = d_row; m.cnt = d_cnt; m.flags = d_flags; m.nr = d_nr; m.deg = d_deg; m.pad0 = 0; m.pad1 = 0;
+                meta[d_k] = m;
+            }
+            d_valid = false;
+        }
+        __syncwarp();
+    };
+    auto issue = [&](int k) {
+        flush();
+        d_n = (gcn && lane < p_cnt) ? __ldg(norm + p_c) : 1.0f;
+        d_nr = gcn ? __ldg(norm + p_row) : 1.0f;
+        // the stage is 256 pieces of 16 bytes (row r = pieces r * kLpr ..): piece q is copied by lane q % 32 with cp.async --
+        // a per-thread copy with nothing to wait for in registers, 4 / VEC whole rows per instruction
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int q = lane + 32 * i, r = q / kLpr, part = q - r * kLpr;
+            const int32_t cc = __shfl_sync(0xffffffffu, p_c, r & 31);
+            if (r < p_cnt) {
+                const float* src = x + (int64_t)cc * F + part * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_s + (uint32_t)k * kTmaStageBytes + (uint32_t)q * 16u),
+                             "l"(src)
+                             : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        d_valid = true; d_k = k; d_cnt = p_cnt; d_flags = p_flags; d_deg = p_deg; d_row = p_row; d_w = p_w;
+        fetch_next();
+    };
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    auto consume = [&](int k, uint32_t parity) {
+        // this lane's copies of the stage are done once at most kTmaStages - 1 newer groups are pending; the warp barrier
+        // makes every lane's copies visible to every lane
+        asm volatile("cp.async.wait_group %0;" ::"n"(kTmaStages - 1) : "memory");
+        __syncwarp();
+        const TmaMeta m = meta[k];
+        if (m.flags & kFirst) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+        }
+        const float* st = ring + k * (kTmaStageBytes / 4) + lane * VEC;
+        const float* wk = sw + k * 32;
+        for (int j = 0; j < m.cnt; ++j) {
+            const float wj = wk[j];
+            if (VEC == 1) {
+                acc[0] = fmaf(wj, st[j * F], acc[0]);
+            } else if (VEC == 2) {
+                const float2 t = *reinterpret_cast<const float2*>(st + j * F);
+                acc[0] = fmaf(wj, t.x, acc[0]); acc[1] = fmaf(wj, t.y, acc[1]);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; v += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(st + j * F + v);
+                    acc[v] = fmaf(wj, t.x, acc[v]); acc[v + 1] = fmaf(wj, t.y, acc[v + 1]);
+                    acc[v + 2] = fmaf(wj, t.z, acc[v + 2]); acc[v + 3] = fmaf(wj, t.w, acc[v + 3]);
+                }
+            }
+        }
+        if (m.flags & kLast) {
+            float sc = 1.0f;
+            if (mode == kMean) sc = 1.0f / (float)(m.deg > 0 ? m.deg : 1);
+            else if (gcn) sc = m.nr;
+            float* o = out + m.row * F + lane * VEC;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) o[v] = acc[v] * sc;
+        }
+        __syncwarp();  // every lane is done with the stage before it is handed to the copy engine again
+    };
+    int64_t issued = 0, consumed = 0;
+    fetch_next();
+    while (issued < kTmaStages && p_valid) { issue((int)(issued % kTmaStages)); ++issued; }
+    for (int64_t pad = issued; pad < kTmaStages; ++pad) asm volatile("cp.async.commit_group;" ::: "memory");   // (group count stays aligned)
+    while (consumed < issued) {
+        if (d_valid && d_k == (int)(consumed % kTmaStages)) flush();  // (only when the newest stage is the next one read)
+        consume((int)(consumed % kTmaStages), 0u);
+        ++consumed;
+        if (p_valid) { issue((int)(issued % kTmaStages)); ++issued; }
+        else asm volatile("cp.async.commit_group;" ::: "memory");       // an empty group keeps "kTmaStages - 1 newer" true
+    }
+}
+
+template <int VEC>
+static int launch_spmm_async(const int64_t* rowptr, const int32_t* col, const float* val, const float* norm, int64_t num_rows,
+                             const float* x, int mode, float* out, cudaStream_t st) {
+    const size_t smem = (size_t)kTmaWarps * kTmaWarpBytes;
+    OCN_CUDA(cudaFuncSetAttribute(k_spmm_async<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = (int)((227 * 1024) / (smem + 1024));
+    int64_t want = (num_rows + kTmaWarps - 1) / kTmaWarps;
+    const int64_t cap = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 1);
+    k_spmm_async<VEC><<<(int)(want < cap ? (want < 1 ? 1 : want) : cap), kTmaWarps * 32, smem, st>>>(rowptr, col, val, norm, num_rows,
+                                                                                                     x, mode, out);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
 template <int VEC>
 static int launch_spmm_tma(const int64_t* rowptr, const int32_t* col, const float* val, const float* norm, int64_t num_rows,
                            const float* x, int mode, float* out, cudaStream_t st) {
@@ -526,11 +688,11 @@ static int launch_spmm_tma(const int64_t* rowptr, const int32_t* col, const floa
 static int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* val, const float* norm,
                        int64_t num_rows, const float* x, int64_t feat, int mode, float* out, cudaStream_t st) {
     // OCN_OPT_SPMM_TMA: 0 automatic, 1 bulk (TMA) gather where it applies, 2 register gather, 3 lane-per-feature gather
-    // (measured behind both: profiles/r02_ab_spmm_v3.txt).  Bulk gather: whole feature rows of 32 / 64 / 128 / 256
+    // (measured behind both: profiles/r02_ab_spmm_v3.txt), 4 the ring fed by per-thread cp.async (profiles/r02_ab_spmm_v4.txt).  Bulk gather: whole feature rows of 32 / 64 / 128 / 256
     // floats, 16-byte aligned, every reduction but max
     int64_t tma = option(OCN_OPT_SPMM_TMA, 0);
     if (tma == 0)  // automatic: where the one-GPU A/B (profiles/r02_ab_spmm_tma.txt) has the bulk gather ahead
-        tma = (num_rows >= 100000 && feat == 128 && (mode == kSum || mode == kMean)) ? 1 : 2;
+        tma = (num_rows >= 100000 && (mode == kSum || mode == kMean)) ? (feat == 128 ? 1 : ((feat == 32 || feat == 64) ? 4 : 2)) : 2;
     if (tma == 1 && mode != kMax && (feat == 32 || feat == 64 || feat == 128 || feat == 256) &&
         (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
         if (feat == 32) return launch_spmm_tma<1>(rowptr, col, val, norm, num_rows, x, mode, out, st);
@@ -541,6 +703,13 @@ static int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* v
     int64_t want = (num_rows + 7) / 8;
     int64_t cap = (int64_t)sm_count() * 16;
     const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    if (tma == 4 && mode != kMax && (feat == 32 || feat == 64 || feat == 128 || feat == 256) &&
+        (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        if (feat == 32) return launch_spmm_async<1>(rowptr, col, val, norm, num_rows, x, mode, out, st);
+        if (feat == 64) return launch_spmm_async<2>(rowptr, col, val, norm, num_rows, x, mode, out, st);
+        if (feat == 128) return launch_spmm_async<4>(rowptr, col, val, norm, num_rows, x, mode, out, st);
+        return launch_spmm_async<8>(rowptr, col, val, norm, num_rows, x, mode, out, st);
+    }
     if (tma == 3 && (feat == 32 || feat == 64 || feat == 128 || feat == 256) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
         if (feat == 32) k_spmm_lane<1, 8><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, mode, out);
         else if (feat == 64) k_spmm_lane<2, 8><<<grid, 256, 0, st>>>(rowptr, col, val, norm, num_rows, x, mode, out);

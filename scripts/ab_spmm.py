@@ -48,9 +48,11 @@ for F in (32, 64, 128, 256):
         got, t1, m1 = run(fn)
         _lib.set_option("spmm_tma", 3)
         got3, t3, m3 = run(fn)
+        _lib.set_option("spmm_tma", 4)
+        got4, t4, m4 = run(fn)
         _lib.set_option("spmm_tma", 0)
-        err = max((got - ref).abs().max().item(), (got3 - ref).abs().max().item()) / (1 + ref.abs().max().item())
+        err = max((got - ref).abs().max().item(), (got3 - ref).abs().max().item(), (got4 - ref).abs().max().item()) / (1 + ref.abs().max().item())
         alg = (8 * (g.n + 1) + 4 * G.nnz + 4 * F * G.nnz + 4 * F * g.n) / 1e9
         print(f"F={F:3d} {label:10s} register {t0:7.3f} ms (median {m0:7.3f}, {alg / t0 * 1e3:6.0f} GB/s)   "
-              f"bulk {t1:7.3f} ms (median {m1:7.3f}, {alg / t1 * 1e3:6.0f} GB/s)   lane {t3:7.3f} ms (median {m3:7.3f}, {alg / t3 * 1e3:6.0f} GB/s)   rel.err {err:.2e}", flush=True)
+              f"bulk {t1:7.3f} ms (median {m1:7.3f}, {alg / t1 * 1e3:6.0f} GB/s)   lane {t3:7.3f} ms ({alg / t3 * 1e3:6.0f} GB/s)   cp.async {t4:7.3f} ms (median {m4:7.3f}, {alg / t4 * 1e3:6.0f} GB/s)   rel.err {err:.2e}", flush=True)
     del x

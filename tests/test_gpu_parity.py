@@ -285,6 +285,13 @@ def test_gnn_aggregation_bulk_gather(name, F, lib_options):
 
 
 @pytest.mark.parametrize("name,F", [("cora", 256), ("pubmed", 64), ("collab_s", 128), ("ddi_s", 64), ("citation2_s", 32)])
+def test_gnn_aggregation_cp_async_ring(name, F, lib_options):
+    """The same checks on k_spmm_async (the per-warp shared-memory ring fed by per-thread cp.async), forced on."""
+    lib_options(spmm_tma=4)
+    _check_gnn_aggregation(name, F)
+
+
+@pytest.mark.parametrize("name,F", [("cora", 256), ("pubmed", 64), ("collab_s", 128), ("ddi_s", 64), ("citation2_s", 32)])
 def test_gnn_aggregation_lane_per_feature(name, F, lib_options):
     """The same checks on k_spmm_lane (a lane owns F / 32 features of every neighbour row), forced on."""
     lib_options(spmm_tma=3)
