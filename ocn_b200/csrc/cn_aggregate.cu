@@ -158,6 +158,28 @@ __global__ void k_stats_finalize(int64_t T, int64_t batch_size, int stage, const
     }
 }
 
+// for_each_heavy_link (common.cuh) with the threshold as an argument: the links whose source has more than `above`
+// neighbours among t = blockIdx.x, blockIdx.x + gridDim.x, ..., body(t) called with all the CTA's threads.
+template <typename Body>
+__device__ __forceinline__ void for_each_link_above(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ src,
+                                                    int64_t T, int64_t above, Body&& body) {
+    __shared__ int s_n;
+    __shared__ long long s_list[256];
+    for (int64_t c0 = 0; (int64_t)blockIdx.x + c0 * gridDim.x < T; c0 += blockDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        const int64_t t = (int64_t)blockIdx.x + (c0 + threadIdx.x) * gridDim.x;
+        if (t < T) {
+            const int64_t i = src[t];
+            if (rowptr[i + 1] - rowptr[i] > above) s_list[atomicAdd(&s_n, 1)] = t;
+        }
+        __syncthreads();
+        const int n = s_n;
+        for (int k = 0; k < n; ++k) body((int64_t)s_list[k]);
+    }
+}
+
 // ---- CN-indicator SpMM ---------------------------------------------------------------------
 // One warp per link.  A feature row is covered by LPR lanes (VPL float4 each); 32/LPR rows are
 // gathered at once.  The three weighted sums share one gather of x[k,:] because all three CN
@@ -172,7 +194,7 @@ k_cn_aggregate(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
                const ColStat* __restrict__ colstat, const float* __restrict__ bscal,
                const float* __restrict__ x, int nvec, int lpr,
                float* __restrict__ xcn1, float* __restrict__ xcn2, float* __restrict__ xcn3, float* __restrict__ xij,
-               int64_t min_deg) {
+               int64_t min_deg, int64_t wide_deg) {
     int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int lane = lane_id();
@@ -209,29 +231,48 @@ k_cn_aggregate(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
                 }
             }
             unsigned active = __ballot_sync(0xffffffffu, nz);
+            // kU rounds of row gathers are requested before the first is consumed (a round = one row per lane group): with a
+            // whole warp per 1 KB row (F = 256) one round at a time left a single row in flight per warp -- the collab-shape
+            // aggregate ran at an eighth of its bytes' worth.  The sums are still taken in ascending position order.
+            constexpr int kU = VPL == 2 ? 4 : (VPL == 1 ? 2 : 1);
             while (active) {
-                unsigned tmp = active;
-                for (int q = 0; q < grp; ++q) tmp &= tmp - 1;
-                const int sl = tmp ? (__ffs(tmp) - 1) : -1;
-                for (int q = 0; q < rpw && active; ++q) active &= active - 1;
-                const int srcl = sl < 0 ? 0 : sl;
-                const int32_t kk = __shfl_sync(0xffffffffu, k, srcl);
-                const float u1 = __shfl_sync(0xffffffffu, w1, srcl);
-                const float u2 = __shfl_sync(0xffffffffu, w2, srcl);
-                const float u3 = __shfl_sync(0xffffffffu, w3, srcl);
-                if (sl >= 0) {
+                int sls[kU];
+                float u1s[kU], u2s[kU], u3s[kU];
+                float4 xv[kU][VPL];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    unsigned tmp = active;
+                    for (int q = 0; q < grp; ++q) tmp &= tmp - 1;
+                    const int sl = tmp ? (__ffs(tmp) - 1) : -1;
+                    for (int q = 0; q < rpw && active; ++q) active &= active - 1;
+                    const int srcl = sl < 0 ? 0 : sl;
+                    const int32_t kk = __shfl_sync(0xffffffffu, k, srcl);
+                    u1s[u] = __shfl_sync(0xffffffffu, w1, srcl);
+                    u2s[u] = __shfl_sync(0xffffffffu, w2, srcl);
+                    u3s[u] = __shfl_sync(0xffffffffu, w3, srcl);
+                    sls[u] = sl;
+                    if (sl >= 0) {
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) {
+                            const int c = sub + v * lpr;
+                            xv[u][v] = (c < nvec) ? __ldg(x4 + (int64_t)kk * nvec + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    if (sls[u] < 0) continue;
+                    const float u1 = u1s[u], u2 = u2s[u], u3 = u3s[u];
 #pragma unroll
                     for (int v = 0; v < VPL; ++v) {
-                        const int c = sub + v * lpr;
-                        if (c < nvec) {
-                            const float4 xv = __ldg(x4 + (int64_t)kk * nvec + c);
-                            a1[v].x = fmaf(u1, xv.x, a1[v].x); a1[v].y = fmaf(u1, xv.y, a1[v].y);
-                            a1[v].z = fmaf(u1, xv.z, a1[v].z); a1[v].w = fmaf(u1, xv.w, a1[v].w);
-                            a2[v].x = fmaf(u2, xv.x, a2[v].x); a2[v].y = fmaf(u2, xv.y, a2[v].y);
-                            a2[v].z = fmaf(u2, xv.z, a2[v].z); a2[v].w = fmaf(u2, xv.w, a2[v].w);
-                            a3[v].x = fmaf(u3, xv.x, a3[v].x); a3[v].y = fmaf(u3, xv.y, a3[v].y);
-                            a3[v].z = fmaf(u3, xv.z, a3[v].z); a3[v].w = fmaf(u3, xv.w, a3[v].w);
-                        }
+                        if (sub + v * lpr >= nvec) continue;
+                        const float4 t4 = xv[u][v];
+                        a1[v].x = fmaf(u1, t4.x, a1[v].x); a1[v].y = fmaf(u1, t4.y, a1[v].y);
+                        a1[v].z = fmaf(u1, t4.z, a1[v].z); a1[v].w = fmaf(u1, t4.w, a1[v].w);
+                        a2[v].x = fmaf(u2, t4.x, a2[v].x); a2[v].y = fmaf(u2, t4.y, a2[v].y);
+                        a2[v].z = fmaf(u2, t4.z, a2[v].z); a2[v].w = fmaf(u2, t4.w, a2[v].w);
+                        a3[v].x = fmaf(u3, t4.x, a3[v].x); a3[v].y = fmaf(u3, t4.y, a3[v].y);
+                        a3[v].z = fmaf(u3, t4.z, a3[v].z); a3[v].w = fmaf(u3, t4.w, a3[v].w);
                     }
                 }
             }
@@ -282,22 +323,49 @@ k_cn_aggregate(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ c
     for (int64_t t = warp; t < T; t += nwarps) {  // one warp per link ...
         const int64_t i = src[t], j = dst[t];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
-        if (d > kHeavyLink || d <= min_deg) continue;
+        if (d > wide_deg || d <= min_deg) continue;
         float4 a1[VPL], a2[VPL], a3[VPL];
         walk(t, rs, d, 0, 32, a1, a2, a3);
         emit(t, a1, a2, a3, false);
         pair_term(t, i, j);
     }
-    // ... a whole CTA per link with a heavy source: every warp sums its share of the chunks, the shares are added to
-    // the output rows one warp after the other (warp order: run-to-run deterministic)
-    for_each_heavy_link(rowptr, src, T, rec_off, [&](int64_t t) {
+    // ... a whole CTA per link with a wide source (more than wide_deg neighbours: a warp gathers 32 / lpr rows at a time,
+    // so at F >= 128 a few links of some hundred neighbours each set the kernel's duration when a warp walks them alone):
+    // every warp sums its share of the chunks; the shares are added in warp order (run-to-run deterministic), through
+    // shared memory up to F = 256 and into the output rows one warp after the other beyond that
+    constexpr bool kSmemCombine = VPL <= 2;
+    __shared__ float4 s_part[kSmemCombine ? 8 : 1][3][kSmemCombine ? VPL * 32 : 1];
+    for_each_link_above(rowptr, src, T, wide_deg > min_deg ? wide_deg : min_deg, [&](int64_t t) {
         const int64_t i = src[t], j = dst[t];
         const int64_t rs = rowptr[i], d = rowptr[i + 1] - rs;
         float4 a1[VPL], a2[VPL], a3[VPL];
         walk(t, rs, d, 32 * (int64_t)wib, 32 * (int64_t)wpb, a1, a2, a3);
-        for (int w = 0; w < wpb; ++w) {
-            if (wib == w) emit(t, a1, a2, a3, w != 0);
+        if constexpr (kSmemCombine) {
+            if (grp == 0) {
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int c = sub + v * lpr;
+                    if (c < nvec) { s_part[wib][0][c] = a1[v]; s_part[wib][1][c] = a2[v]; s_part[wib][2][c] = a3[v]; }
+                }
+            }
             __syncthreads();
+            for (int e = threadIdx.x; e < 3 * nvec; e += blockDim.x) {
+                const int which = e / nvec, c = e - which * nvec;
+                float* o = which == 0 ? xcn1 : (which == 1 ? xcn2 : xcn3);
+                if (!o) continue;
+                float4 r = s_part[0][which][c];
+                for (int w = 1; w < wpb; ++w) {
+                    const float4 q = s_part[w][which][c];
+                    r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+                }
+                reinterpret_cast<float4*>(o + t * F)[c] = r;
+            }
+            __syncthreads();
+        } else {
+            for (int w = 0; w < wpb; ++w) {
+                if (wib == w) emit(t, a1, a2, a3, w != 0);
+                __syncthreads();
+            }
         }
         if (wib == 0) pair_term(t, i, j);
     });
@@ -587,10 +655,17 @@ int ocn_cn_aggregate(const int64_t* rowptr, const int32_t* col, int64_t n, const
     while (lpr < nvec && lpr < 32) lpr <<= 1;
     const int vpl = (nvec + 31) / 32;
     const int grid = grid_for_warps(num_edges);
+    // A warp walks a link alone while that link is a small share of the warp's work: beyond an eighth of the mean number
+    // of positions per resident warp (16 a multiprocessor) a whole CTA takes the link.  Streams of uniformly wide links
+    // (ddi: the CTA walk costs 30 % more there) keep the warp walk up to kHeavyLink; a stream with a skewed tail (collab:
+    // mean 30, maximum 751) hands the tail over (1190 -> 700 us; profiles/r02_ab_aggregate_wide.txt).
+    int64_t wide_deg = plan_host ? plan_host[OCN_PLAN_NUM_RECORDS] / ((int64_t)sm_count() * 16 * 8) : kHeavyLink;
+    if (wide_deg < 64) wide_deg = 64;
+    if (wide_deg > kHeavyLink) wide_deg = kHeavyLink;
 #define AGG(V)                                                                                                       \
     k_cn_aggregate<V><<<grid, 256, 0, st>>>(rowptr, col, n, src, dst, num_edges, batch_size, order, weighted, variant, \
                                             fill, ip, rec_off, (const Record*)records, (const ColStat*)colstat,      \
-                                            batch_scalars, x, nvec, lpr, xcn1, xcn2, xcn3, xij, min_deg)
+                                            batch_scalars, x, nvec, lpr, xcn1, xcn2, xcn3, xij, min_deg, wide_deg)
     if (vpl <= 1) AGG(1);
     else if (vpl <= 2) AGG(2);
     else if (vpl <= 4) AGG(4);
