@@ -741,6 +741,13 @@ int ocn_cn_release(const int64_t* rowptr, const int32_t* col, int64_t n, const i
     OCN_CHECK_ARG(num_edges > 0 && batch_size > 0, "ocn_cn_release: sizes must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     PLAN_PTRS();
+    // a stream with more positions than the statistics have entries (ddi: 21 M positions, 16 batches x 4267 columns) is
+    // cleaned by clearing the whole table instead of walking the records again
+    const int64_t num_batches = (num_edges + batch_size - 1) / batch_size;
+    if (plan_host != nullptr && plan_host[OCN_PLAN_NUM_RECORDS] >= num_batches * n) {
+        OCN_CUDA(cudaMemsetAsync(colstat, 0, sizeof(ColStat) * (size_t)num_batches * (size_t)n, st));
+        return OCN_OK;
+    }
     if (use_grouped(num_edges, plan_host))
         return grouped_release(rowptr, col, n, src, num_edges, batch_size, plan_scratch, (ColStat*)colstat, st);
     k_cn_release<<<grid_for_warps(num_edges), 256, 0, st>>>(rowptr, col, n, src, num_edges, batch_size, rec_off,

@@ -629,45 +629,201 @@ k_cn_build_direct(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
     }
 }
 
+// The link a record belongs to (the last t with rec_off[t] <= g; links without records share offsets), for a lane that
+// walks ascending records: the current link's bounds stay in registers, so a step inside one link costs a compare, a step
+// into one of the next few links a load each, and only the first call (or a jump over many links) a binary search.  (A
+// search from scratch per record was 590 warp instructions per 32 records in k_cn_build_from_a2: the ALU pipe was its limit.)
+struct RecordLink {
+    int64_t t = -1, off = 0, next = 0;  // rec_off[t] = off <= g < next = rec_off[t + 1]
+    __device__ __forceinline__ bool seek(const int64_t* __restrict__ rec_off, int64_t T, int64_t g) {  // true: another link
+        if (t >= 0 && g < next) return false;
+        int64_t lo = t < 0 ? 0 : t;
+        bool found = false;
+        if (t >= 0)
+            for (int s = 0; s < 4 && !found; ++s) {
+                if (ldg_i64(rec_off + lo + 1) <= g) ++lo; else found = true;
+            }
+        if (!found) {
+            int64_t hi = T;
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (ldg_i64(rec_off + mid) <= g) lo = mid; else hi = mid;
+            }
+        }
+        t = lo;
+        off = ldg_i64(rec_off + lo);
+        next = ldg_i64(rec_off + lo + 1);
+        return true;
+    }
+};
+
 // Orders 1-2 on a dense graph: a warp takes 32 consecutive records (link, position p), finds their links with one
-// search per lane, then computes one record at a time with the lanes spread over the W words of the two bit-vector
+// search per lane, then computes four records at a time with eight lanes over the words of the two bit-vector
 // rows: C2 = popc(row(dst) & row(k_p)) summed over the words, C1 = bit dst of row(k_p).
 __global__ void __launch_bounds__(256)
 k_cn_build_dense(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ src,
                  const int64_t* __restrict__ dst, int64_t T, int order, const int64_t* __restrict__ rec_off,
                  const uint32_t* __restrict__ bits, int W, Record* __restrict__ records) {
     const int lane = lane_id();
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5, warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t total = rec_off[T];
-    for (int64_t g0 = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * 32; g0 < total; g0 += nwarps * 32) {
+    const int64_t span = ((total + nwarps * 32 - 1) / (nwarps * 32)) * 32;  // a warp's records are consecutive
+    const int64_t end = (warp + 1) * span < total ? (warp + 1) * span : total;
+    RecordLink L;
+    int64_t j = -1, rs = 0;
+    for (int64_t g0 = warp * span; g0 < end; g0 += 32) {
         const int64_t g = g0 + lane;
-        int64_t j = -1;
         int32_t k = 0;
         if (g < total) {
-            int64_t lo_t = 0, hi_t = T;  // link of record g: the last t with rec_off[t] <= g
-            while (hi_t - lo_t > 1) {
-                const int64_t mid = (lo_t + hi_t) >> 1;
-                if (ldg_i64(rec_off + mid) <= g) lo_t = mid; else hi_t = mid;
+            if (L.seek(rec_off, T, g)) {
+                j = dst[L.t];
+                rs = ldg_i64(rowptr + src[L.t]);
             }
-            j = dst[lo_t];
-            k = ldg_i32(col + ldg_i64(rowptr + src[lo_t]) + (g - ldg_i64(rec_off + lo_t)));
+            k = ldg_i32(col + rs + (g - L.off));
         }
         const int cnt = (int)((total - g0) < 32 ? (total - g0) : 32);
         unsigned mine = 0u;
-        for (int q = 0; q < cnt; ++q) {
-            const int64_t jq = __shfl_sync(0xffffffffu, j, q);
-            const int32_t kq = __shfl_sync(0xffffffffu, k, q);
-            const uint32_t* rj = bits + jq * W;
-            const uint32_t* rk = bits + (int64_t)kq * W;
+        // four records at a time, eight lanes a record, 128-bit loads (W is a multiple of 4 words, rows are 16-byte
+        // aligned): 4 x 128 B per request.  One record at a time with the warp across 32-bit words cost 205 warp
+        // instructions a record at ddi (W = 136), most of them the per-record shuffle reduction and loop control.
+        const int sub = lane & 7, grp = lane >> 3, W4 = W >> 2;
+        for (int q0 = 0; q0 < cnt; q0 += 4) {
+            const int q = q0 + grp;
+            const int64_t jq = __shfl_sync(0xffffffffu, j, q & 31);
+            const int32_t kq = __shfl_sync(0xffffffffu, k, q & 31);
+            const bool valid = q < cnt;
             unsigned c2 = 0u;
-            if (order >= 2)
-                for (int w = lane; w < W; w += 32) c2 += __popc(__ldg(rj + w) & __ldg(rk + w));
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, o);
-            const unsigned c1 = (__ldg(rk + (jq >> 5)) >> (jq & 31)) & 1u;
-            if (lane == q) mine = c2 | (c1 << 31);
+            if (valid && order >= 2) {
+                const uint4* rj = reinterpret_cast<const uint4*>(bits + jq * W);
+                const uint4* rk = reinterpret_cast<const uint4*>(bits + (int64_t)kq * W);
+#pragma unroll 2
+                for (int w = sub; w < W4; w += 8) {
+                    const uint4 a = __ldg(rj + w), b = __ldg(rk + w);
+                    c2 += __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
+                }
+            }
+            c2 += __shfl_xor_sync(0xffffffffu, c2, 1);
+            c2 += __shfl_xor_sync(0xffffffffu, c2, 2);
+            c2 += __shfl_xor_sync(0xffffffffu, c2, 4);
+            unsigned val = 0u;
+            if (valid && sub == 0) val = c2 | (((__ldg(bits + (int64_t)kq * W + (jq >> 5)) >> (jq & 31)) & 1u) << 31);
+            const unsigned got = __shfl_sync(0xffffffffu, val, ((lane - q0) & 3) * 8);
+            if (lane >= q0 && lane < q0 + 4) mine = got;
         }
         if (g < total) records[g] = make_uint2(mine, 0u);
+    }
+}
+
+// The whole 2-walk count matrix of a dense symmetric graph, a2[j][k] = popc(row(j) & row(k)): a 64 x 64 tile per CTA,
+// 4 x 4 entries per thread (rows ty + 16 a, columns tx + 16 b: consecutive lanes read consecutive shared-memory rows of
+// 9 x 16 bytes, conflict free), the bit rows staged 32 words at a time.  Population counts are a quarter-rate
+// instruction, so the four words of a 128-bit step go through a carry-save adder tree first (ones / twos carried along
+// the row, one count of the fours per step): 13 instructions per entry and step.
+constexpr int kA2Tile = 64, kA2Chunk4 = 8, kA2Stride = kA2Chunk4 + 1;
+__global__ void __launch_bounds__(256)
+k_dense_a2(const uint32_t* __restrict__ bits, int64_t n, int W, uint32_t* __restrict__ a2) {
+    __shared__ uint4 sa[kA2Tile * kA2Stride], sb[kA2Tile * kA2Stride];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    if (blockIdx.x < blockIdx.y) return;  // written by the CTA of the mirror tile
+    const int64_t j0 = (int64_t)blockIdx.y * kA2Tile, k0 = (int64_t)blockIdx.x * kA2Tile;
+    unsigned ones[4][4], twos[4][4], fours[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) ones[a][b] = twos[a][b] = fours[a][b] = 0u;
+    const int W4 = W >> 2;
+    for (int c0 = 0; c0 < W4; c0 += kA2Chunk4) {
+        for (int e = threadIdx.x; e < kA2Tile * kA2Chunk4; e += 256) {
+            const int r = e >> 3, c = e & 7;
+            uint4 va = make_uint4(0u, 0u, 0u, 0u), vb = va;
+            if (c0 + c < W4) {
+                if (j0 + r < n) va = __ldg(reinterpret_cast<const uint4*>(bits + (j0 + r) * W) + c0 + c);
+                if (k0 + r < n) vb = __ldg(reinterpret_cast<const uint4*>(bits + (k0 + r) * W) + c0 + c);
+            }
+            sa[r * kA2Stride + c] = va;
+            sb[r * kA2Stride + c] = vb;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int c = 0; c < kA2Chunk4; ++c) {
+            uint4 va[4], vb[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                va[a] = sa[(ty + 16 * a) * kA2Stride + c];
+                vb[a] = sb[(tx + 16 * a) * kA2Stride + c];
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const unsigned v0 = va[a].x & vb[b].x, v1 = va[a].y & vb[b].y, v2 = va[a].z & vb[b].z, v3 = va[a].w & vb[b].w;
+                    const unsigned o = ones[a][b], t = twos[a][b];
+                    const unsigned ta = (o & v0) | ((o ^ v0) & v1), o1 = o ^ v0 ^ v1;
+                    const unsigned tb = (o1 & v2) | ((o1 ^ v2) & v3);
+                    ones[a][b] = o1 ^ v2 ^ v3;
+                    fours[a][b] += __popc((t & ta) | ((t ^ ta) & tb));
+                    twos[a][b] = t ^ ta ^ tb;
+                }
+        }
+        __syncthreads();
+    }
+    unsigned out[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) out[a][b] = 4u * fours[a][b] + 2u * __popc(twos[a][b]) + __popc(ones[a][b]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int64_t j = j0 + ty + 16 * a;
+        if (j >= n) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int64_t k = k0 + tx + 16 * b;
+            if (k < n) a2[j * n + k] = out[a][b];
+        }
+    }
+    if (blockIdx.x == blockIdx.y) return;
+    // the mirror tile (the graph is symmetric): transposed through shared memory so that its rows are written whole
+    __shared__ uint32_t st[kA2Tile][kA2Tile + 1];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) st[tx + 16 * b][ty + 16 * a] = out[a][b];
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int64_t k = k0 + ty + 16 * a;
+        if (k >= n) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int64_t j = j0 + tx + 16 * b;
+            if (j < n) a2[k * n + j] = st[ty + 16 * a][tx + 16 * b];
+        }
+    }
+}
+
+// records of a dense graph from the whole matrix: one lane per record, C2 = a2[dst][k_p], C1 = bit k_p of row(dst)
+__global__ void __launch_bounds__(256)
+k_cn_build_from_a2(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ src,
+                   const int64_t* __restrict__ dst, int64_t T, int order, const int64_t* __restrict__ rec_off,
+                   const uint32_t* __restrict__ bits, int W, const uint32_t* __restrict__ a2, int64_t n,
+                   Record* __restrict__ records) {
+    const int64_t total = rec_off[T];
+    const int lane = lane_id();
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5, warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t span = ((total + nwarps * 32 - 1) / (nwarps * 32)) * 32;  // a warp's records are consecutive
+    const int64_t end = (warp + 1) * span < total ? (warp + 1) * span : total;
+    RecordLink L;
+    int64_t j = 0, rs = 0;
+    for (int64_t g = warp * span + lane; g < end; g += 32) {
+        if (L.seek(rec_off, T, g)) {
+            j = dst[L.t];
+            rs = ldg_i64(rowptr + src[L.t]);
+        }
+        const int32_t k = ldg_i32(col + rs + (g - L.off));
+        const unsigned c2 = order >= 2 ? __ldg(a2 + j * n + k) : 0u;
+        const unsigned c1 = (__ldg(bits + j * W + (k >> 5)) >> (k & 31)) & 1u;
+        records[g] = make_uint2(c2 | (c1 << 31), 0u);
     }
 }
 
@@ -760,15 +916,26 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
     const bool dense = order <= 2 && plan_host != nullptr && plan_host[OCN_PLAN_DENSE] != 0 && hub_scratch != nullptr;
     if (dense) {
         const int W = dense_words(n);
-        const size_t need = sizeof(uint32_t) * (size_t)n * (size_t)W;
+        const size_t need = dense_whole_a2(n, plan_host) ? dense_bits_bytes(n) + sizeof(uint32_t) * (size_t)n * (size_t)n
+                                                         : sizeof(uint32_t) * (size_t)n * (size_t)W;
         if (hub_scratch_bytes < need) return fail(OCN_ENOSPACE, "ocn_cn_build: dense scratch %zu < %zu bytes", hub_scratch_bytes, need);
         uint32_t* bits = (uint32_t*)hub_scratch;
         k_dense_bits<<<(int)((n * 32 + 255) / 256), 256, 0, st>>>(rowptr, col, n, W, bits);
         OCN_LAUNCH_CHECK();
         int64_t want = (records_capacity / 32 + 7) / 8 + 1;
         int64_t cap = (int64_t)sm_count() * 16;
-        k_cn_build_dense<<<(int)(want < cap ? want : cap), 256, 0, st>>>(rowptr, col, src, dst, num_edges, order, rec_off, bits, W,
-                                                                        (Record*)records);
+        if (dense_whole_a2(n, plan_host)) {
+            uint32_t* a2 = (uint32_t*)((char*)hub_scratch + dense_bits_bytes(n));
+            const unsigned tiles = (unsigned)((n + kA2Tile - 1) / kA2Tile);
+            if (order >= 2) k_dense_a2<<<dim3(tiles, tiles), 256, 0, st>>>(bits, n, W, a2);
+            OCN_LAUNCH_CHECK();
+            const int64_t want1 = (records_capacity + 255) / 256 + 1;  // a lane per record
+            k_cn_build_from_a2<<<(int)(want1 < cap ? want1 : cap), 256, 0, st>>>(rowptr, col, src, dst, num_edges, order, rec_off,
+                                                                                bits, W, a2, n, (Record*)records);
+        } else {
+            k_cn_build_dense<<<(int)(want < cap ? want : cap), 256, 0, st>>>(rowptr, col, src, dst, num_edges, order, rec_off,
+                                                                            bits, W, (Record*)records);
+        }
         OCN_LAUNCH_CHECK();
         indexed = true;  // (skips the table kernel below)
     } else if (order <= 2) {  // the plan picked one of the two on the device (plan[OCN_PLAN_USE_DIRECT]); the other returns at once

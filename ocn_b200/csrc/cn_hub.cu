@@ -1260,7 +1260,8 @@ using namespace ocn;
 
 extern "C" size_t ocn_cn_hub_bytes(int64_t n, int64_t nnz, const int64_t* plan_host) {
     if (n <= 0 || nnz < 0 || plan_host == nullptr) return 0;
-    if (plan_host[OCN_PLAN_DENSE] != 0) return sizeof(uint32_t) * (size_t)n * (size_t)dense_words(n) + 256;
+    if (plan_host[OCN_PLAN_DENSE] != 0)
+        return dense_bits_bytes(n) + (dense_whole_a2(n, plan_host) ? sizeof(uint32_t) * (size_t)n * (size_t)n : 0) + 256;
     if (plan_host[OCN_PLAN_HUB_DEGREE] <= 0) return 0;
     const size_t one = hub_layout(n, nnz, plan_host[OCN_PLAN_HUB_PAIRS], plan_host[OCN_PLAN_HUB_ENTRIES],
                                   plan_host[OCN_PLAN_HUB_POSITIONS], plan_host[OCN_PLAN_NUM_CHUNKS]).total;

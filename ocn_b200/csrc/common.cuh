@@ -117,6 +117,13 @@ int run_hub_stage(const int64_t* rowptr, const int32_t* col, int64_t n, const in
 __global__ void k_dense_bits(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n, int W,
                              uint32_t* __restrict__ bits);
 inline int dense_words(int64_t n) { return (int)(((n + 31) / 32 + 3) & ~int64_t(3)); }
+// The dense build takes its 2-walk counts from the whole matrix A^2 (n x n uint32 behind the bit rows in the dense scratch, a
+// tiled AND / popcount product) when the stream has at least half as many positions as the matrix has entries and the matrix
+// stays within 256 MB; per-position row products otherwise.
+inline bool dense_whole_a2(int64_t n, const int64_t* plan_host) {
+    return n <= 8192 && plan_host[OCN_PLAN_NUM_RECORDS] * 2 >= n * n;
+}
+inline size_t dense_bits_bytes(int64_t n) { return (sizeof(uint32_t) * (size_t)n * (size_t)dense_words(n) + 255) & ~size_t(255); }
 
 // run-grouped kernels after the build (cn_grouped.cu): used when the stream averages >= kGroupedMinRun links per run
 constexpr int kGroupedMinRun = 16;
