@@ -551,6 +551,18 @@ k_cn_build(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
 // ended); pairs whose shorter row exceeds 32 columns are deferred.  Pass 2: the deferred pairs are intersected by
 // the whole warp (lanes stride over the shorter row), so a hub x hub pair costs len/32 * log steps instead of
 // len * log on one lane.  Records are written directly (no atomics): each (link, p) has one owner.
+// (row lengths and positions inside a row are 32-bit here: the search steps are most of this kernel's 4.9 G warp
+// instructions on a 16 384-link training batch, and 64-bit index arithmetic was a third of every step)
+__device__ __forceinline__ bool row_has(const int32_t* __restrict__ row, int len, int32_t key) {
+    int lo = 0, hi = len;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(row + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo < len && __ldg(row + lo) == key;
+}
+
+constexpr int kMergeRatio = 6;  // deferred pairs up to this length ratio are merged, longer ones searched
 __global__ void __launch_bounds__(256)
 k_cn_build_direct(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ src,
                   const int64_t* __restrict__ dst, int64_t T, int order, const int64_t* __restrict__ rec_off,
@@ -563,7 +575,8 @@ k_cn_build_direct(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
     for (int64_t g0 = warp * 32; g0 < total; g0 += nwarps * 32) {
         const int64_t g = g0 + lane;
         bool defer = false;
-        int64_t rs_k = 0, dk = 0, rs_j = 0, dj = 0;
+        int64_t rs_k = 0, rs_j = 0;
+        int dk = 0, dj = 0;
         unsigned c1 = 0u;
         if (g < total) {
             int64_t lo_t = 0, hi_t = T;  // link of record g: the last t with rec_off[t] <= g (links without records share offsets)
@@ -574,30 +587,30 @@ k_cn_build_direct(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
             const int64_t t = lo_t, p = g - ldg_i64(rec_off + t);
             const int64_t i = src[t], j = dst[t];
             rs_j = ldg_i64(rowptr + j);
-            dj = ldg_i64(rowptr + j + 1) - rs_j;
+            dj = (int)(ldg_i64(rowptr + j + 1) - rs_j);
             const int32_t* nj = col + rs_j;
             const int32_t k = ldg_i32(col + ldg_i64(rowptr + i) + p);
-            c1 = row_contains(nj, dj, k) ? 1u : 0u;
+            c1 = row_has(nj, dj, k) ? 1u : 0u;
             unsigned c2 = 0u;
             if (order >= 2) {
                 rs_k = ldg_i64(rowptr + k);
-                dk = ldg_i64(rowptr + k + 1) - rs_k;
+                dk = (int)(ldg_i64(rowptr + k + 1) - rs_k);
                 const int32_t* a = nj;          // shorter row
                 const int32_t* b = col + rs_k;  // longer row
-                int64_t la = dj, lb = dk;
+                int la = dj, lb = dk;
                 if (la > lb) {
                     const int32_t* tp = a; a = b; b = tp;
-                    const int64_t tl = la; la = lb; lb = tl;
+                    const int tl = la; la = lb; lb = tl;
                 }
                 if (la > 32) {
                     defer = true;
                 } else {
-                    int64_t lo = 0;  // both rows ascend: every search resumes where the previous one ended
-                    for (int64_t u = 0; u < la && lo < lb; ++u) {
+                    int lo = 0;  // both rows ascend: every search resumes where the previous one ended
+                    for (int u = 0; u < la && lo < lb; ++u) {
                         const int32_t v = ldg_i32(a + u);
-                        int64_t hi = lb;
+                        int hi = lb;
                         while (lo < hi) {
-                            const int64_t mid = (lo + hi) >> 1;
+                            const int mid = (lo + hi) >> 1;
                             if (ldg_i32(b + mid) < v) lo = mid + 1; else hi = mid;
                         }
                         if (lo < lb && ldg_i32(b + lo) == v) { ++c2; ++lo; }
@@ -610,18 +623,41 @@ k_cn_build_direct(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
         while (pending) {
             const int sl = __ffs(pending) - 1;
             pending &= pending - 1;
-            const int64_t rk = __shfl_sync(0xffffffffu, rs_k, sl), dkk = __shfl_sync(0xffffffffu, dk, sl);
-            const int64_t rj = __shfl_sync(0xffffffffu, rs_j, sl), djj = __shfl_sync(0xffffffffu, dj, sl);
+            const int64_t rk = __shfl_sync(0xffffffffu, rs_k, sl), rj = __shfl_sync(0xffffffffu, rs_j, sl);
+            const int dkk = __shfl_sync(0xffffffffu, dk, sl), djj = __shfl_sync(0xffffffffu, dj, sl);
             const unsigned cc1 = __shfl_sync(0xffffffffu, c1, sl);
             const int32_t* a = col + rj;
             const int32_t* b = col + rk;
-            int64_t la = djj, lb = dkk;
+            int la = djj, lb = dkk;
             if (la > lb) {
                 const int32_t* tp = a; a = b; b = tp;
-                const int64_t tl = la; la = lb; lb = tl;
+                const int tl = la; la = lb; lb = tl;
             }
             unsigned cnt = 0u;
-            for (int64_t u = lane; u < la; u += 32) cnt += row_contains(b, lb, ldg_i32(a + u)) ? 1u : 0u;
+            if (lb <= kMergeRatio * la) {
+                // rows of similar length (two thirds of the deferred search steps on a training batch are pairs within a
+                // factor of four): a lane takes a contiguous share of the shorter row, finds where it starts in the
+                // longer one and merges forward -- (la + lb) / 32 steps a lane instead of la / 32 * log2 lb
+                const int share = (la + 31) >> 5, ua = lane * share, ue = ua + share < la ? ua + share : la;
+                if (ua < ue) {
+                    int u = ua;
+                    int32_t va = ldg_i32(a + u);
+                    int lo = 0, hi = lb;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (ldg_i32(b + mid) < va) lo = mid + 1; else hi = mid;
+                    }
+                    int32_t vb = lo < lb ? ldg_i32(b + lo) : 0;
+                    while (u < ue && lo < lb) {
+                        const bool step_a = va <= vb, step_b = vb <= va;
+                        cnt += (step_a && step_b) ? 1u : 0u;
+                        if (step_a && ++u < ue) va = ldg_i32(a + u);
+                        if (step_b && ++lo < lb) vb = ldg_i32(b + lo);
+                    }
+                }
+            } else {
+                for (int u = lane; u < la; u += 32) cnt += row_has(b, lb, ldg_i32(a + u)) ? 1u : 0u;
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
             if (lane == 0) records[g0 + sl] = make_uint2(cnt | (cc1 << 31), 0u);

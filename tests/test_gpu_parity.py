@@ -115,6 +115,39 @@ def test_cn_sets_bit_exact(name, B):
     _assert_rows_equal(got_s[1], ref_s)
 
 
+@pytest.mark.parametrize("name,B,kind", [("tiny", 128, "mixed"), ("cora", 1152, "mixed"), ("pubmed", 2048, "pos"),
+                                         ("collab_s", 4096, "pos"), ("citation2_s", 2048, "pos")])
+def test_order2_direct_kernel_bit_exact(name, B, kind):
+    """Orders 1-2 on streams of short runs (k_cn_build_direct: flat over the records, sorted-list intersections) against
+    the oracle, walk counts included; "pos" = links drawn from the edges, as a training batch is."""
+    g = GRAPHS[name]()
+    G, A = _graph(g), _sp(g)
+    e = g.query_edges(B, kind)
+    got = ob.get_cn(G, e.to(DEV), 2, weighted=True)
+    ref = R.get_cn(A, e, 2)
+    for k in range(2):
+        _assert_rows_equal(got[k], ref[k])
+    got1 = ob.get_cn(G, e.to(DEV), 1, weighted=True)
+    _assert_rows_equal(got1[0], ref[0])
+
+
+def test_order2_direct_kernel_hub_rows():
+    """A 9 000-neighbour hub as source, as destination and as a common neighbour: lane walks (shorter row <= 32) and the
+    deferred whole-warp intersections of two long rows, against the oracle."""
+    n = 20000
+    hub = torch.arange(1, 9001)
+    src = torch.cat((torch.zeros(9000, dtype=torch.int64), synth.hash_randint(40000, n, 3, 1, "cpu")))
+    dst = torch.cat((hub, synth.hash_randint(40000, n, 3, 2, "cpu")))
+    G = ob.Graph.from_edge_index(torch.stack((src, dst)).to(DEV), n)
+    A = R.sp_from_csr(G.rowptr.cpu(), G.col.cpu())
+    e = torch.stack((torch.tensor([5, 0, 17, 9000, 3, 0]), torch.tensor([0, 7, 0, 0, 4, 12345])))
+    got = ob.get_cn(G, e.to(DEV), 2, weighted=True)
+    ref = R.get_cn(A, e, 2)
+    for k in range(2):
+        _assert_rows_equal(got[k], ref[k])
+    assert got[1].col.numel() > 9000
+
+
 def _oracle_cns(A, e, order, weighted):
     cns = R.get_cn(A, e, order)
     if not weighted:
