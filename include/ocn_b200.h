@@ -53,7 +53,7 @@ int ocn_device_sm_count(void);
 #define OCN_OPT_HUB_EXACT 5       /* 1: 32-byte node entries with exact run sets + run-segment starts for streams of <= 128 runs
                                      (measured slower than the folded 64-bit sets on the bench workload; implied by WALKER = 1) */
 #define OCN_OPT_GROUPED_OFF 6     /* 1: never use the run-grouped statistics / aggregation kernels (cn_grouped.cu) */
-#define OCN_OPT_SPGEMM_MODE 7     /* A^2 kernel: 0 automatic, 1 global scratch, 2 shared-memory rows, 3 dense bit matrix */
+#define OCN_OPT_SPGEMM_MODE 7     /* A^2 kernel: 0 automatic, 1 global scratch, 2 shared-memory rows, 3 dense bit matrix (structure + tiled counts), 4 dense whole count matrix + compaction (fold == 0, n <= 8192) */
 #define OCN_OPT_SPMM_TMA 8        /* k_spmm: 0 automatic, 1 gather neighbour rows with cp.async.bulk + mbarrier, 2 register gather, 3 lane-per-feature gather, 4 shared-memory ring fed by per-thread cp.async */
 #define OCN_OPT_HEAD_TC 9         /* ocn_cn_head at in = hidden = 32: 0 / 3 tcgen05 kernel (tf32 x 3 split, fp32 accuracy; A operand in tensor memory, 4 pipelines per SM), 1 the same with A through shared memory (2 pipelines), 2 CUDA-core kernel */
 #define OCN_OPT_COUNT 16
@@ -328,7 +328,10 @@ int ocn_gcn_spmm(const int64_t* rowptr, const int32_t* col, const float* edge_w,
  * block summed into the top-left corner.  Two phase: symbolic writes the nnz of
  * every output row, numeric fills ascending columns (+ fp32 2-walk counts if out_val != NULL).
  * scratch: ocn_spgemm_scratch_bytes(n, nnz, fold) bytes, zero on first use (left zero on return).  The library
- * picks one of three kernels from (n, nnz, fold) -- dense bit-matrix rows (ddi), a shared-memory row accumulator
+ * picks one of four kernels from (n, nnz, fold) -- dense bit-matrix rows (ddi; fold == 0 and n <= 8192: the whole count
+ * matrix by AND / popcount tiles, compacted by the numeric call, which reuses the symbolic call's matrix when it runs on
+ * the same scratch and graph; both dense forms count popc(row r & row c), i.e. they assume A symmetric as every adj of
+ * the reference is), a shared-memory row accumulator
  * (collab, Planetoid), a global-scratch accumulator (column spaces beyond shared memory); OCN_OPT_SPGEMM_MODE forces
  * one for tests. */
 size_t ocn_spgemm_scratch_bytes(int64_t n, int64_t nnz, int64_t fold);

@@ -757,7 +757,10 @@ k_cn_build_dense(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
 // the row, one count of the fours per step): 13 instructions per entry and step.
 constexpr int kA2Tile = 64, kA2Chunk4 = 8, kA2Stride = kA2Chunk4 + 1;
 __global__ void __launch_bounds__(256)
-k_dense_a2(const uint32_t* __restrict__ bits, int64_t n, int W, uint32_t* __restrict__ a2) {
+k_dense_a2(const uint32_t* __restrict__ bits, int64_t n, int W, uint32_t* __restrict__ a2,
+           const long long* __restrict__ skip_stamp, long long e0, long long e1, long long e2, long long e3) {
+    // (spgemm.cu: the matrix of this graph is already in a2 when the scratch carries its stamp)
+    if (skip_stamp != nullptr && skip_stamp[0] == e0 && skip_stamp[1] == e1 && skip_stamp[2] == e2 && skip_stamp[3] == e3) return;
     __shared__ uint4 sa[kA2Tile * kA2Stride], sb[kA2Tile * kA2Stride];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     if (blockIdx.x < blockIdx.y) return;  // written by the CTA of the mirror tile
@@ -963,7 +966,7 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
         if (dense_whole_a2(n, plan_host)) {
             uint32_t* a2 = (uint32_t*)((char*)hub_scratch + dense_bits_bytes(n));
             const unsigned tiles = (unsigned)((n + kA2Tile - 1) / kA2Tile);
-            if (order >= 2) k_dense_a2<<<dim3(tiles, tiles), 256, 0, st>>>(bits, n, W, a2);
+            if (order >= 2) k_dense_a2<<<dim3(tiles, tiles), 256, 0, st>>>(bits, n, W, a2, nullptr, 0, 0, 0, 0);
             OCN_LAUNCH_CHECK();
             const int64_t want1 = (records_capacity + 255) / 256 + 1;  // a lane per record
             k_cn_build_from_a2<<<(int)(want1 < cap ? want1 : cap), 256, 0, st>>>(rowptr, col, src, dst, num_edges, order, rec_off,

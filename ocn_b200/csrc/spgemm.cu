@@ -369,11 +369,11 @@ k_dense_counts(int64_t n, int64_t fold, int64_t out_rows, int W, int Wf, const u
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int64_t r0 = (int64_t)blockIdx.y * kDT, c0 = (int64_t)blockIdx.x * kDT;
     const int64_t step = fold > 0 ? fold : n;
-    unsigned acc[4][4];
+    unsigned acc[4][4], ones[4][4], twos[4][4];  // acc counts the fours
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0u;
+        for (int b = 0; b < 4; ++b) acc[a][b] = ones[a][b] = twos[a][b] = 0u;
     for (int64_t ra = 0; r0 + ra < n; ra += step) {
         for (int64_t cb = 0; c0 + cb < n; cb += step) {
             for (int wc = 0; wc < W; wc += WC) {
@@ -388,15 +388,31 @@ k_dense_counts(int64_t n, int64_t fold, int64_t out_rows, int W, int Wf, const u
                     Bs[w * (kDT + 4) + rr] = (okw && c0 + rr < out_rows && gj < n) ? __ldg(bits + gj * W + wc + w) : 0u;
                 }
                 __syncthreads();
-#pragma unroll 4
-                for (int w = 0; w < WC; ++w) {
-                    const uint4 a = *reinterpret_cast<const uint4*>(As + w * (kDT + 4) + 4 * ty);
-                    const uint4 b = *reinterpret_cast<const uint4*>(Bs + w * (kDT + 4) + 4 * tx);
-                    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+                // four words a step: the population count is a quarter-rate instruction, so the four ANDs of an output go
+                // through a carry-save adder tree first (ones / twos carried along, one count of the fours per step)
+#pragma unroll 2
+                for (int w = 0; w < WC; w += 4) {
+                    uint32_t av[4][4], bv[4][4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint4 a = *reinterpret_cast<const uint4*>(As + (w + k) * (kDT + 4) + 4 * ty);
+                        const uint4 b = *reinterpret_cast<const uint4*>(Bs + (w + k) * (kDT + 4) + 4 * tx);
+                        av[k][0] = a.x; av[k][1] = a.y; av[k][2] = a.z; av[k][3] = a.w;
+                        bv[k][0] = b.x; bv[k][1] = b.y; bv[k][2] = b.z; bv[k][3] = b.w;
+                    }
 #pragma unroll
                     for (int p = 0; p < 4; ++p)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[p][q] += __popc(av[p] & bv[q]);
+                        for (int q = 0; q < 4; ++q) {
+                            const unsigned v0 = av[0][p] & bv[0][q], v1 = av[1][p] & bv[1][q];
+                            const unsigned v2 = av[2][p] & bv[2][q], v3 = av[3][p] & bv[3][q];
+                            const unsigned o = ones[p][q], t = twos[p][q];
+                            const unsigned ta = (o & v0) | ((o ^ v0) & v1), o1 = o ^ v0 ^ v1;
+                            const unsigned tb = (o1 & v2) | ((o1 ^ v2) & v3);
+                            ones[p][q] = o1 ^ v2 ^ v3;
+                            acc[p][q] += __popc((t & ta) | ((t ^ ta) & tb));
+                            twos[p][q] = t ^ ta ^ tb;
+                        }
                 }
             }
         }
@@ -415,13 +431,52 @@ k_dense_counts(int64_t n, int64_t fold, int64_t out_rows, int W, int Wf, const u
             if ((word >> (c & 31)) & 1u) {
                 const int64_t o = obase + Sp[r * Wf + (c >> 5)] + __popc(word & ((1u << (c & 31)) - 1u));
                 out_col[o] = (int32_t)c;
-                if (out_val != nullptr) out_val[o] = (float)acc[p][q];
+                if (out_val != nullptr) out_val[o] = (float)(4u * acc[p][q] + 2u * __popc(twos[p][q]) + __popc(ones[p][q]));
             }
         }
     }
 }
 
-enum GemmMode { kModeGlobal = 0, kModeSmem = 1, kModeDense = 2 };
+// the whole count matrix of a dense graph (cn_build.cu: 64 x 64 AND / popcount tiles through carry-save adders, mirror
+// tiles written by the transposed CTA)
+__global__ void k_dense_a2(const uint32_t* __restrict__ bits, int64_t n, int W, uint32_t* __restrict__ a2,
+                           const long long* __restrict__ skip_stamp, long long e0, long long e1, long long e2, long long e3);
+
+// rows of the count matrix -> number of non-zero entries (a warp per row)
+__global__ void k_a2_row_nnz(const uint32_t* __restrict__ a2, int64_t n, int64_t* __restrict__ out_row_nnz) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    const uint32_t* row = a2 + r * n;
+    int cnt = 0;
+    for (int64_t c = lane; c < n; c += 32) cnt += __ldg(row + c) != 0u ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) out_row_nnz[r] = cnt;
+}
+
+// rows of the count matrix -> CSR entries in ascending column order (a warp per row, ballot ranks)
+__global__ void k_a2_fill(const uint32_t* __restrict__ a2, int64_t n, const int64_t* __restrict__ out_rowptr,
+                          int32_t* __restrict__ out_col, float* __restrict__ out_val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    const uint32_t* row = a2 + r * n;
+    int64_t base = out_rowptr[r];
+    for (int64_t c0 = 0; c0 < n; c0 += 32) {
+        const int64_t c = c0 + lane;
+        const uint32_t v = c < n ? __ldg(row + c) : 0u;
+        const unsigned bal = __ballot_sync(0xffffffffu, v != 0u);
+        if (v != 0u) {
+            const int64_t o = base + __popc(bal & ((1u << lane) - 1u));
+            out_col[o] = (int32_t)c;
+            if (out_val != nullptr) out_val[o] = (float)v;
+        }
+        base += __popc(bal);
+    }
+}
+
+enum GemmMode { kModeGlobal = 0, kModeSmem = 1, kModeDense = 2, kModeDenseWhole = 3 };
 
 // out-of-line so that the symbolic and the numeric call (and ocn_spgemm_scratch_bytes) agree
 static GemmMode gemm_mode(int64_t n, int64_t nnz, int64_t fold) {
@@ -429,10 +484,13 @@ static GemmMode gemm_mode(int64_t n, int64_t nnz, int64_t fold) {
     const int64_t ncols = fold > 0 ? (fold < n ? fold : n) : n;
     const bool dense_ok = n <= 32768 && (fold == 0 || fold % 32 == 0);
     const bool smem_ok = row_smem(ncols, true).total_bytes <= 200 * 1024;
+    // the true A^2 of a dense graph whose count matrix stays within 256 MB: tiles for the whole matrix, then a compaction
+    const bool whole_ok = dense_ok && fold == 0 && n <= 8192;
     if (forced == 3 && dense_ok) return kModeDense;
+    if (forced == 4 && whole_ok) return kModeDenseWhole;
     if (forced == 2 && smem_ok) return kModeSmem;
     if (forced == 1) return kModeGlobal;
-    if (dense_ok && nnz >= n * (n / 64 + 1)) return kModeDense;   // mean degree >= n / 64: A^2 is (close to) full
+    if (dense_ok && nnz >= n * (n / 64 + 1)) return whole_ok ? kModeDenseWhole : kModeDense;   // mean degree >= n / 64: A^2 is (close to) full
     return smem_ok ? kModeSmem : kModeGlobal;
 }
 
@@ -460,6 +518,7 @@ size_t ocn_spgemm_scratch_bytes(int64_t n, int64_t nnz, int64_t fold) {
     if (n <= 0) return 0;
     switch (gemm_mode(n, nnz, fold)) {
         case kModeDense: return dense_layout(n, fold).total;
+        case kModeDenseWhole: return 256 + dense_bits_bytes(n) + sizeof(uint32_t) * (size_t)n * (size_t)n;
         case kModeSmem: return 256;  // the row counter
         default: break;
     }
@@ -481,6 +540,28 @@ static int dense_structure(const int64_t* rowptr, const int32_t* col, int64_t n,
     return OCN_OK;
 }
 
+// kModeDenseWhole scratch: [stamp: 4 x int64 | bits | a2].  The symbolic call leaves the count matrix and a stamp of the
+// graph it was computed from (pointers, n, nnz); the numeric call on the same scratch and graph compacts it without
+// recomputing (the tile kernel's CTAs return at once when they find the stamp: no host read-back), then clears the stamp;
+// without the stamp (a caller that did not run symbolic first) the matrix is computed again.
+struct WholeStamp { long long rowptr, col, n, nnz; };
+__global__ void k_whole_stamp(WholeStamp* s, WholeStamp v) { *s = v; }
+
+static int dense_whole(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t nnz, void* scratch, bool skip_if_stamped,
+                       cudaStream_t st) {
+    const int W = dense_words(n);
+    uint32_t* bits = (uint32_t*)((char*)scratch + 256);
+    uint32_t* a2 = (uint32_t*)((char*)scratch + 256 + dense_bits_bytes(n));
+    k_dense_bits<<<(int)((n * 32 + 255) / 256), 256, 0, st>>>(rowptr, col, n, W, bits);
+    OCN_LAUNCH_CHECK();
+    const unsigned tiles = (unsigned)((n + 63) / 64);
+    // (skip_if_stamped: every CTA returns at once when the scratch carries this graph's stamp -- no host read-back)
+    k_dense_a2<<<dim3(tiles, tiles), 256, 0, st>>>(bits, n, W, a2, skip_if_stamped ? (const long long*)scratch : nullptr,
+                                                   (long long)(uintptr_t)rowptr, (long long)(uintptr_t)col, (long long)n, (long long)nnz);
+    OCN_LAUNCH_CHECK();
+    return OCN_OK;
+}
+
 int ocn_spgemm_a2_symbolic(const int64_t* rowptr, const int32_t* col, int64_t n, int64_t nnz, int64_t fold, void* scratch,
                            int64_t* out_row_nnz, void* stream) {
     OCN_RANGE("ocn_spgemm_a2_symbolic");
@@ -489,6 +570,16 @@ int ocn_spgemm_a2_symbolic(const int64_t* rowptr, const int32_t* col, int64_t n,
     cudaStream_t st = (cudaStream_t)stream;
     const GemmMode mode = gemm_mode(n, nnz, fold);
     const int64_t out_rows = fold > 0 ? (fold < n ? fold : n) : n;
+    if (mode == kModeDenseWhole) {
+        if (int rc = dense_whole(rowptr, col, n, nnz, scratch, false, st)) return rc;
+        const uint32_t* a2 = (const uint32_t*)((char*)scratch + 256 + dense_bits_bytes(n));
+        k_a2_row_nnz<<<(int)((n * 32 + 255) / 256), 256, 0, st>>>(a2, n, out_row_nnz);
+        OCN_LAUNCH_CHECK();
+        const WholeStamp stamp = {(long long)(uintptr_t)rowptr, (long long)(uintptr_t)col, (long long)n, (long long)nnz};
+        k_whole_stamp<<<1, 1, 0, st>>>((WholeStamp*)scratch, stamp);
+        OCN_LAUNCH_CHECK();
+        return OCN_OK;
+    }
     if (mode == kModeDense) {
         if (fold > 0 && out_rows < n) OCN_CUDA(cudaMemsetAsync(out_row_nnz + out_rows, 0, sizeof(int64_t) * (size_t)(n - out_rows), st));
         return dense_structure(rowptr, col, n, fold, scratch, out_row_nnz, st);
@@ -519,6 +610,14 @@ int ocn_spgemm_a2_numeric(const int64_t* rowptr, const int32_t* col, int64_t n, 
     cudaStream_t st = (cudaStream_t)stream;
     const GemmMode mode = gemm_mode(n, nnz, fold);
     const int64_t out_rows = fold > 0 ? (fold < n ? fold : n) : n;
+    if (mode == kModeDenseWhole) {
+        if (int rc = dense_whole(rowptr, col, n, nnz, scratch, true, st)) return rc;
+        const uint32_t* a2 = (const uint32_t*)((char*)scratch + 256 + dense_bits_bytes(n));
+        k_a2_fill<<<(int)((n * 32 + 255) / 256), 256, 0, st>>>(a2, n, out_rowptr, out_col, out_val);
+        OCN_LAUNCH_CHECK();
+        OCN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(WholeStamp), st));
+        return OCN_OK;
+    }
     if (mode == kModeDense) {
         if (int rc = dense_structure(rowptr, col, n, fold, scratch, nullptr, st)) return rc;
         const DenseLayout d = dense_layout(n, fold);

@@ -780,13 +780,14 @@ def test_out_of_range_links_raise():
         _assert_rows_equal(got[k], ref[k])
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 @pytest.mark.parametrize("name,fold", [("tiny", 0), ("tiny", 32), ("tiny_dense", 0), ("tiny_dense", 16), ("cora", 0), ("cora", 1024),
                                        ("ddi_s", 0), ("ddi_s", 64), ("ddi_s", 96), ("pubmed", 0), ("pubmed", 1024)])
 def test_spgemm_kernels_agree_with_the_oracle(lib_options, name, fold, mode):
-    """The three A^2 kernels -- global-scratch accumulator (1), shared-memory row accumulator (2), dense bit-matrix
-    rows (3) -- forced in turn: structure and 2-walk counts bit-exact against torch.sparse on the CPU, true and folded
-    (a fold that is no multiple of 32 leaves the dense kernel and falls back), structure-only too."""
+    """The four A^2 kernels -- global-scratch accumulator (1), shared-memory row accumulator (2), dense bit-matrix
+    rows (3), the whole dense count matrix + compaction (4: true A^2 only, folded calls fall back) -- forced in turn:
+    structure and 2-walk counts bit-exact against torch.sparse on the CPU, true and folded (a fold that is no
+    multiple of 32 leaves the dense kernel and falls back), structure-only too."""
     g = GRAPHS[name]()
     G, A = _graph(g), _sp(g)
     lib_options(spgemm_mode=mode)
@@ -797,3 +798,24 @@ def test_spgemm_kernels_agree_with_the_oracle(lib_options, name, fold, mode):
     assert torch.equal(got.value.cpu(), ref.values())
     s = ob.spgemm_a2(G, fold, False)
     assert s.value is None and torch.equal(s.rowptr, got.rowptr) and torch.equal(s.col, got.col)
+
+
+def test_spgemm_whole_matrix_numeric_without_symbolic():
+    """The numeric call of the whole-matrix mode reuses the symbolic call's count matrix through a stamp in the scratch;
+    on a scratch that does not carry the stamp (zeroed, or stamped for another graph) it must compute the matrix itself."""
+    from ocn_b200 import _lib
+    from ocn_b200.cn import _stream
+    g = GRAPHS["ddi_s"]()
+    G = _graph(g)
+    ref = ob.spgemm_a2(G, 0, True)
+    L = _lib.lib()
+    st = _stream(G.device)
+    scratch = torch.zeros(L.ocn_spgemm_scratch_bytes(G.n, G.nnz, 0), dtype=torch.uint8, device=DEV)
+    for dirty in (False, True):
+        if dirty:  # a stamp of some other graph, stale matrix contents
+            scratch.random_(0, 255)
+        col = torch.empty_like(ref.col)
+        val = torch.empty_like(ref.value)
+        _lib.check(L.ocn_spgemm_a2_numeric(_lib.ptr(G.rowptr), _lib.ptr(G.col), G.n, G.nnz, 0, _lib.ptr(scratch),
+                                           _lib.ptr(ref.rowptr), _lib.ptr(col), _lib.ptr(val), st), "ocn_spgemm_a2_numeric")
+        assert torch.equal(col, ref.col) and torch.equal(val, ref.value)
