@@ -145,7 +145,8 @@ template <bool NUMERIC>
 __global__ void __launch_bounds__(kRowThreads)
 k_spgemm_row_smem(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n, int64_t fold,
                   int64_t w0, int64_t w1, int64_t* __restrict__ out_row_nnz, const int64_t* __restrict__ out_rowptr,
-                  int32_t* __restrict__ out_col, float* __restrict__ out_val, unsigned long long* __restrict__ row_counter) {
+                  int32_t* __restrict__ out_col, float* __restrict__ out_val, unsigned long long* __restrict__ row_counter,
+                  const int32_t* __restrict__ row_list, const unsigned long long* __restrict__ row_list_n) {
     extern __shared__ uint32_t rs_smem[];
     using Scan = cub::BlockScan<int, kRowThreads>;
     __shared__ typename Scan::TempStorage scan_tmp;
@@ -159,7 +160,11 @@ k_spgemm_row_smem(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
     uint32_t* colbuf = cnt + (NUMERIC ? kRowStage : 0);
     uint32_t* prodbuf = colbuf + (NUMERIC ? kRowStage : 0);   // NUMERIC: the products of the row (second pass without global loads)
     __shared__ int s_np;
+    constexpr int kHubNeighbour = 256, kHubSlots = 64;
+    __shared__ long long s_hms[kHubSlots], s_hme[kHubSlots];
+    __shared__ int s_nh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_nh = 0;
     const int64_t out_rows = fold > 0 ? (fold < n ? fold : n) : n;
     const int64_t step = fold > 0 ? fold : n;
     const bool want_val = NUMERIC && out_val != nullptr;
@@ -169,23 +174,59 @@ k_spgemm_row_smem(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
     auto for_each_product = [&](int64_t r, auto&& body) {
         for (int64_t i = r; i < n; i += step) {
             const int64_t s = rowptr[i], e = rowptr[i + 1];
-            for (int64_t o = s + warp; o < e; o += kRowThreads / 32) {
-                const int32_t m = ldg_i32(col + o);
-                const int64_t ms = ldg_i64(rowptr + m), me = ldg_i64(rowptr + m + 1);
-                for (int64_t oo = ms + lane; oo < me; oo += 32) {
-                    int64_t l = ldg_i32(col + oo);
-                    if (fold > 0) l %= fold;
-                    body((uint32_t)l);
+            // the warp's neighbours (every 8th of the row), 32 at a time: their ranges are fetched by the lanes side by side,
+            // so the walk below waits for one load per neighbour instead of a chain of three
+            constexpr int kW = kRowThreads / 32;
+            for (int64_t o0 = s + warp; o0 < e; o0 += 32 * kW) {
+                int64_t ms_l = 0, me_l = 0;
+                if (o0 + (int64_t)lane * kW < e) {
+                    const int32_t m = ldg_i32(col + o0 + (int64_t)lane * kW);
+                    ms_l = ldg_i64(rowptr + m);
+                    me_l = ldg_i64(rowptr + m + 1);
+                }
+                const int64_t left = (e - o0 + kW - 1) / kW;
+                const int cnt = (int)(left < 32 ? left : 32);
+                for (int q = 0; q < cnt; ++q) {
+                    const int64_t ms = __shfl_sync(0xffffffffu, ms_l, q), me = __shfl_sync(0xffffffffu, me_l, q);
+                    if (me - ms > kHubNeighbour) {  // a hub among the neighbours: walked by the whole CTA below
+                        int slot = 0;
+                        if (lane == 0) slot = atomicAdd(&s_nh, 1);
+                        slot = __shfl_sync(0xffffffffu, slot, 0);
+                        if (slot < kHubSlots) {
+                            if (lane == 0) { s_hms[slot] = ms; s_hme[slot] = me; }
+                            continue;
+                        }
+                    }
+                    for (int64_t oo = ms + lane; oo < me; oo += 32) {
+                        int64_t l = ldg_i32(col + oo);
+                        if (fold > 0) l %= fold;
+                        body((uint32_t)l);
+                    }
                 }
             }
         }
+        // the hubs among the neighbours (ncu: a quarter of the stall samples sat at the barrier after this walk -- the warp
+        // that drew a 5 000-column neighbour kept the other seven waiting)
+        __syncthreads();
+        const int nh = s_nh < kHubSlots ? s_nh : kHubSlots;
+        for (int h = 0; h < nh; ++h) {
+            const int64_t ms = s_hms[h], me = s_hme[h];
+            for (int64_t oo = ms + tid; oo < me; oo += kRowThreads) {
+                int64_t l = ldg_i32(col + oo);
+                if (fold > 0) l %= fold;
+                body((uint32_t)l);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_nh = 0;
     };
     while (true) {
         // rows are handed out by a counter: their cost spans four orders of magnitude
         if (tid == 0) { s_row = (long long)atomicAdd(row_counter, 1ull); s_np = 0; }
         __syncthreads();
-        const int64_t r = s_row;
-        if (r >= out_rows) break;
+        // (row_list: the rows k_spgemm_row_warp left to this kernel, in the order they were found)
+        if (s_row >= (row_list != nullptr ? (long long)*row_list_n : (long long)out_rows)) break;
+        const int64_t r = row_list != nullptr ? (int64_t)row_list[s_row] : (int64_t)s_row;
         for_each_product(r, [&](uint32_t l) {
             const uint32_t w = l >> 5;
             if (atomicOr(&L0[w], 1u << (l & 31u)) == 0u) atomicOr(&L1[w >> 5], 1u << (w & 31u));  // first touch of the word
@@ -266,7 +307,21 @@ k_spgemm_row_smem(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
                 });
                 __syncthreads();
             }
-            // columns by rank: every thread expands the touched words of its level-1 words
+            // columns by rank.  Rows whose ranks fit 16 bits: the threads stride over the bitmap words, each word knows its rank
+            // (a thread per level-1 word expanded up to 1024 columns one after the other while the others of the 231 waited:
+            // the 12 % of collab's rows with more than 1024 distinct columns took most of the numeric pass)
+            if (small) {
+                for (int64_t w = tid; w < w0; w += kRowThreads) {
+                    uint32_t bits = L0[w];
+                    if (bits == 0u) continue;
+                    uint32_t rank = pref16[w];
+                    for (; bits; bits &= bits - 1) {
+                        const uint32_t c = (uint32_t)(w * 32 + (__ffs(bits) - 1));
+                        if (staged) colbuf[rank] = c; else out_col[obase + rank] = (int32_t)c;
+                        ++rank;
+                    }
+                }
+            } else
             for (int64_t j = tid; j < w1; j += kRowThreads) {
                 uint32_t rank = pref[j];
                 for (uint32_t b = L1[j]; b; b &= b - 1) {
@@ -586,12 +641,14 @@ int ocn_spgemm_a2_symbolic(const int64_t* rowptr, const int32_t* col, int64_t n,
     }
     if (mode == kModeSmem) {
         const RowSmem rsm = row_smem(out_rows, false);
-        OCN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long), st));
+        OCN_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(unsigned long long), st));
+        unsigned long long* counters = (unsigned long long*)scratch;
         OCN_CUDA(cudaFuncSetAttribute(k_spgemm_row_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm.total_bytes));
         int per_sm = (int)((200u * 1024u) / (rsm.total_bytes + 2048));
         per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
         k_spgemm_row_smem<false><<<sm_count() * per_sm, kRowThreads, rsm.total_bytes, st>>>(
-            rowptr, col, n, fold, (int64_t)rsm.w0, (int64_t)rsm.w1, out_row_nnz, nullptr, nullptr, nullptr, (unsigned long long*)scratch);
+            rowptr, col, n, fold, (int64_t)rsm.w0, (int64_t)rsm.w1, out_row_nnz, nullptr, nullptr, nullptr, counters,
+            nullptr, nullptr);
         OCN_LAUNCH_CHECK();
         return OCN_OK;
     }
@@ -631,12 +688,14 @@ int ocn_spgemm_a2_numeric(const int64_t* rowptr, const int32_t* col, int64_t n, 
     }
     if (mode == kModeSmem) {
         const RowSmem rsm = row_smem(out_rows, true);
-        OCN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long), st));
+        OCN_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(unsigned long long), st));
+        unsigned long long* counters = (unsigned long long*)scratch;
         OCN_CUDA(cudaFuncSetAttribute(k_spgemm_row_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm.total_bytes));
         int per_sm = (int)((200u * 1024u) / (rsm.total_bytes + 2048));
         per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
         k_spgemm_row_smem<true><<<sm_count() * per_sm, kRowThreads, rsm.total_bytes, st>>>(
-            rowptr, col, n, fold, (int64_t)rsm.w0, (int64_t)rsm.w1, nullptr, out_rowptr, out_col, out_val, (unsigned long long*)scratch);
+            rowptr, col, n, fold, (int64_t)rsm.w0, (int64_t)rsm.w1, nullptr, out_rowptr, out_col, out_val, counters,
+            nullptr, nullptr);
         OCN_LAUNCH_CHECK();
         return OCN_OK;
     }
