@@ -145,8 +145,7 @@ template <bool NUMERIC>
 __global__ void __launch_bounds__(kRowThreads)
 k_spgemm_row_smem(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n, int64_t fold,
                   int64_t w0, int64_t w1, int64_t* __restrict__ out_row_nnz, const int64_t* __restrict__ out_rowptr,
-                  int32_t* __restrict__ out_col, float* __restrict__ out_val, unsigned long long* __restrict__ row_counter,
-                  const int32_t* __restrict__ row_list, const unsigned long long* __restrict__ row_list_n) {
+                  int32_t* __restrict__ out_col, float* __restrict__ out_val, unsigned long long* __restrict__ row_counter) {
     extern __shared__ uint32_t rs_smem[];
     using Scan = cub::BlockScan<int, kRowThreads>;
     __shared__ typename Scan::TempStorage scan_tmp;
@@ -224,9 +223,8 @@ k_spgemm_row_smem(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
         // rows are handed out by a counter: their cost spans four orders of magnitude
         if (tid == 0) { s_row = (long long)atomicAdd(row_counter, 1ull); s_np = 0; }
         __syncthreads();
-        // (row_list: the rows k_spgemm_row_warp left to this kernel, in the order they were found)
-        if (s_row >= (row_list != nullptr ? (long long)*row_list_n : (long long)out_rows)) break;
-        const int64_t r = row_list != nullptr ? (int64_t)row_list[s_row] : (int64_t)s_row;
+        const int64_t r = s_row;
+        if (r >= out_rows) break;
         for_each_product(r, [&](uint32_t l) {
             const uint32_t w = l >> 5;
             if (atomicOr(&L0[w], 1u << (l & 31u)) == 0u) atomicOr(&L1[w >> 5], 1u << (w & 31u));  // first touch of the word
@@ -641,14 +639,13 @@ int ocn_spgemm_a2_symbolic(const int64_t* rowptr, const int32_t* col, int64_t n,
     }
     if (mode == kModeSmem) {
         const RowSmem rsm = row_smem(out_rows, false);
-        OCN_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(unsigned long long), st));
+        OCN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long), st));
         unsigned long long* counters = (unsigned long long*)scratch;
         OCN_CUDA(cudaFuncSetAttribute(k_spgemm_row_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm.total_bytes));
         int per_sm = (int)((200u * 1024u) / (rsm.total_bytes + 2048));
         per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
         k_spgemm_row_smem<false><<<sm_count() * per_sm, kRowThreads, rsm.total_bytes, st>>>(
-            rowptr, col, n, fold, (int64_t)rsm.w0, (int64_t)rsm.w1, out_row_nnz, nullptr, nullptr, nullptr, counters,
-            nullptr, nullptr);
+            rowptr, col, n, fold, (int64_t)rsm.w0, (int64_t)rsm.w1, out_row_nnz, nullptr, nullptr, nullptr, counters);
         OCN_LAUNCH_CHECK();
         return OCN_OK;
     }
@@ -688,14 +685,13 @@ int ocn_spgemm_a2_numeric(const int64_t* rowptr, const int32_t* col, int64_t n, 
     }
     if (mode == kModeSmem) {
         const RowSmem rsm = row_smem(out_rows, true);
-        OCN_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(unsigned long long), st));
+        OCN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long), st));
         unsigned long long* counters = (unsigned long long*)scratch;
         OCN_CUDA(cudaFuncSetAttribute(k_spgemm_row_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm.total_bytes));
         int per_sm = (int)((200u * 1024u) / (rsm.total_bytes + 2048));
         per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
         k_spgemm_row_smem<true><<<sm_count() * per_sm, kRowThreads, rsm.total_bytes, st>>>(
-            rowptr, col, n, fold, (int64_t)rsm.w0, (int64_t)rsm.w1, nullptr, out_rowptr, out_col, out_val, counters,
-            nullptr, nullptr);
+            rowptr, col, n, fold, (int64_t)rsm.w0, (int64_t)rsm.w1, nullptr, out_rowptr, out_col, out_val, counters);
         OCN_LAUNCH_CHECK();
         return OCN_OK;
     }

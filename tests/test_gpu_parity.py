@@ -443,7 +443,8 @@ def test_hub_stage_position_windows(lib_options, warp_win, cta_win):
 
 @pytest.mark.parametrize("n,links,whole", [(40, 400, True), (40, 64, False), (70, 900, True), (1500, 96, False), (1500, 20000, True),
                                            (3000, 96, False), (4267, 3000, False), (9000, 96, False)])
-def test_dense_build_equals_the_walk_kernels(n, links, whole):
+@pytest.mark.parametrize("order", [1, 2])
+def test_dense_build_equals_the_walk_kernels(n, links, whole, order):
     """Orders 1-2 on a dense graph (mean degree >= n / 64) come from bit-vector rows: per-position row products
     (k_cn_build_dense), or -- ``whole``: streams with at least n^2 / 2 positions -- a tiled product for the whole matrix
     A^2 and a gather (k_dense_a2, k_cn_build_from_a2).  The same session built by the walk kernels (the plan's dense flag
@@ -452,14 +453,14 @@ def test_dense_build_equals_the_walk_kernels(n, links, whole):
     g = synth.tiny_graph(n, n * (n // 48 + 2), 5)
     G = ob.Graph(g.rowptr.to(DEV), g.col.to(DEV), g.n)
     e = g.query_edges(links, "mixed").to(DEV)
-    a = ob.CNSession(G, e, 32, 2)
+    a = ob.CNSession(G, e, 32, order)
     assert a.dense, "this graph is meant to take the dense build"
     assert (n <= 8192 and 2 * a.num_records >= n * n) == whole
-    a.build(2, True)
-    b = ob.CNSession(G, e, 32, 2)
+    a.build(order, True)
+    b = ob.CNSession(G, e, 32, order)
     b.dense, b.hub_bytes = False, 0
     b.plan_host[PLAN_DENSE] = 0
-    b.build(2, True)
+    b.build(order, True)
     nb = a.num_records * 8
     assert nb > 0 and torch.equal(a.records[:nb], b.records[:nb])
     assert torch.equal(a.colstat, b.colstat)
