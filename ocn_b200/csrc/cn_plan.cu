@@ -282,6 +282,32 @@ __global__ void k_plan_finish(int64_t T, int64_t batch_size, int resident_ctas, 
     plan[OCN_PLAN_NUM_CHUNKS] = chunk_off[T];
 }
 
+// Small streams (a Cora / Pubmed batch: 1 - 2 thousand links) are launch-bound: the plan's eight prefix sums were sixteen
+// launches of cub::DeviceScan (init + scan).  Up to kSmallScan elements the sums of a group run as ONE launch, a CTA per
+// array (block scans of 1024 elements with a running carry, in place).
+constexpr int kSmallScan = 8192;
+struct ScanJob { void* data; int count; int is64; int inclusive; };
+struct ScanJobs { ScanJob job[3]; };
+__global__ void __launch_bounds__(1024) k_scan_small(ScanJobs jobs) {
+    using Scan = cub::BlockScan<long long, 1024>;
+    __shared__ typename Scan::TempStorage tmp;
+    const ScanJob J = jobs.job[blockIdx.x];
+    long long running = 0;
+    for (int base = 0; base < J.count; base += 1024) {
+        const int i = base + (int)threadIdx.x;
+        long long v = 0;
+        if (i < J.count) v = J.is64 ? reinterpret_cast<const long long*>(J.data)[i] : (long long)reinterpret_cast<const int*>(J.data)[i];
+        long long ex = 0, total = 0;
+        Scan(tmp).ExclusiveSum(v, ex, total);
+        const long long out = running + ex + (J.inclusive ? v : 0);
+        if (i < J.count) {
+            if (J.is64) reinterpret_cast<long long*>(J.data)[i] = out; else reinterpret_cast<int*>(J.data)[i] = (int)out;
+        }
+        running += total;
+        __syncthreads();
+    }
+}
+
 }  // namespace ocn
 
 using namespace ocn;
@@ -335,8 +361,15 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
     OCN_CUDA(cudaMemsetAsync(rec_off + T + 1, 0, sizeof(int64_t), st));
     k_plan_edges<<<blocks, threads, 0, st>>>(rowptr, n, src, dst, T, batch_size, rec_off, run_id, out_plan);
     OCN_LAUNCH_CHECK();
-    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, rec_off, rec_off, (int)(T + 1), st));
-    OCN_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, run_id, run_id, (int)(T + 1), st));
+    const bool small_scans = T + 2 <= kSmallScan;
+    if (small_scans) {
+        const ScanJobs jobs = {{{rec_off, (int)(T + 1), 1, 0}, {run_id, (int)(T + 1), 0, 1}, {nullptr, 0, 0, 0}}};
+        k_scan_small<<<2, 1024, 0, st>>>(jobs);
+        OCN_LAUNCH_CHECK();
+    } else {
+        OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, rec_off, rec_off, (int)(T + 1), st));
+        OCN_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, run_id, run_id, (int)(T + 1), st));
+    }
     k_plan_runs<<<blocks, threads, 0, st>>>(rowptr, src, T, batch_size, run_id, run_start, out_plan);
     OCN_LAUNCH_CHECK();
     k_plan_hub_decide<<<1, 1, 0, st>>>(order, hub_degree, automatic, T, out_plan);
@@ -350,17 +383,29 @@ int ocn_cn_plan(const int64_t* rowptr, const int32_t* col, int64_t n, const int6
         k_plan_cost_long<<<sm_count() * 2, 1024, 0, st>>>(rowptr, col, dst, cost_pre, hub_off, long_list, out_plan);
         OCN_LAUNCH_CHECK();
     }
-    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cost_pre, cost_pre, (int)(T + 1), st));
-    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, hub_off, hub_off, (int)(T + 1), st));
-    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, chunk_off, chunk_off, (int)(T + 1), st));
+    if (small_scans) {
+        const ScanJobs jobs = {{{cost_pre, (int)(T + 1), 1, 0}, {hub_off, (int)(T + 1), 0, 0}, {chunk_off, (int)(T + 1), 0, 0}}};
+        k_scan_small<<<3, 1024, 0, st>>>(jobs);
+        OCN_LAUNCH_CHECK();
+    } else {
+        OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cost_pre, cost_pre, (int)(T + 1), st));
+        OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, hub_off, hub_off, (int)(T + 1), st));
+        OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, chunk_off, chunk_off, (int)(T + 1), st));
+    }
     int blocks2 = (int)(((T + 2) * 32 + threads - 1) / threads);
     const int64_t heavy_run = option(OCN_OPT_HUB_HEAVY_RUN, kHeavyRun);
     k_plan_units<<<blocks2, threads, 0, st>>>(rowptr, col, src, T, run_start, cost_pre, resident_ctas, heavy_run, order,
                                               out_plan, run_unit_off, pos_scanN, run_pos_heavy);
     OCN_LAUNCH_CHECK();
-    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, run_unit_off, run_unit_off, (int)(T + 2), st));
-    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pos_scanN, pos_scanN, (int)(T + 2), st));
-    OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, run_pos_heavy, run_pos_heavy, (int)(T + 2), st));
+    if (small_scans) {
+        const ScanJobs jobs = {{{run_unit_off, (int)(T + 2), 1, 0}, {pos_scanN, (int)(T + 2), 1, 0}, {run_pos_heavy, (int)(T + 2), 1, 0}}};
+        k_scan_small<<<3, 1024, 0, st>>>(jobs);
+        OCN_LAUNCH_CHECK();
+    } else {
+        OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, run_unit_off, run_unit_off, (int)(T + 2), st));
+        OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pos_scanN, pos_scanN, (int)(T + 2), st));
+        OCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, run_pos_heavy, run_pos_heavy, (int)(T + 2), st));
+    }
     k_plan_positions<<<(int)((T + 2 + threads - 1) / threads), threads, 0, st>>>(out_plan, pos_scanN, run_pos_heavy, run_pos_off,
                                                                                 pos_start);
     OCN_LAUNCH_CHECK();
