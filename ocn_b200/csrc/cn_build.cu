@@ -952,6 +952,7 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
         if (rc != OCN_OK) return rc;
         indexed = true;
     }
+    const int direct_known = plan_host != nullptr ? (plan_host[OCN_PLAN_USE_DIRECT] != 0 ? 1 : 0) : -1;  // (a launch saved on small batches)
     const bool dense = order <= 2 && plan_host != nullptr && plan_host[OCN_PLAN_DENSE] != 0 && hub_scratch != nullptr;
     if (dense) {
         const int W = dense_words(n);
@@ -977,14 +978,15 @@ extern "C" int ocn_cn_build(const int64_t* rowptr, const int32_t* col, int64_t n
         }
         OCN_LAUNCH_CHECK();
         indexed = true;  // (skips the table kernel below)
-    } else if (order <= 2) {  // the plan picked one of the two on the device (plan[OCN_PLAN_USE_DIRECT]); the other returns at once
+    } else if (order <= 2 && direct_known != 0) {  // the plan picked one of the two on the device (plan[OCN_PLAN_USE_DIRECT]);
+        // without the host copy of the plan both are launched and the other returns at once
         int64_t want = (records_capacity / 32 + 7) / 8 + 1;  // a warp per 32 records
         int64_t cap = (int64_t)sm_count() * 16;
         k_cn_build_direct<<<(int)(want < cap ? want : cap), 256, 0, st>>>(rowptr, col, src, dst, num_edges, order, rec_off,
                                                                          plan, (Record*)records);
         OCN_LAUNCH_CHECK();
     }
-    if (!indexed) {
+    if (!indexed && !(order <= 2 && direct_known == 1)) {
         const int blocks = sm_count() * kBuildCtasPerSm;
         k_cn_build<<<blocks, kBuildThreads, sizeof(BuildSmem), st>>>(
             rowptr, col, n, src, dst, order, rec_off, (const int32_t*)(base + L.run_start),
