@@ -507,7 +507,8 @@ def main():
 
     out_host = torch.empty(a.steps * S * T, dtype=torch.float32).pin_memory()
     rank_scores = torch.empty(a.steps * S, T, dtype=torch.float32, device=dev) if world > 1 else None
-    gathered_host = torch.empty(world * a.steps * S * T, dtype=torch.float32).pin_memory() if world > 1 else None
+    # (rank 0 alone reads the gathered scores: the other ranks do not pin a world-sized host buffer)
+    gathered_host = torch.empty(world * a.steps * S * T, dtype=torch.float32).pin_memory() if (world > 1 and rank == 0) else None
 
     def session_e2e(q, timed):
         with torch.cuda.stream(plan_stream if plan_stream is not None else torch.cuda.current_stream()):
